@@ -1,0 +1,109 @@
+/* occ_b200.h -- C ABI of libocc_b200.so: the B200 (sm_100a) hot path of OccFormer.
+ *
+ * The reference has no C FFI on this path; its boundary is Python (mmcv Registry names, nn.Module forward
+ * signatures, one pybind11 torch extension).  This header is what the reference-side Python binds with ctypes
+ * (see INTEGRATION.md).  Each entry point cites the reference interface it replaces (paths relative to the
+ * reference checkout; P/ = projects/mmdet3d_plugin/, M/ = mmdetection3d/mmdet3d/).
+ *
+ * Conventions (all functions):
+ *   - pointers are DEVICE pointers to contiguous fp32 buffers unless stated; no torch types cross the ABI;
+ *   - return 0 on success, <0 for an argument error (-1 invalid, -2 unsupported shape, -3 driver entry point
+ *     missing), >0 = cudaError_t of a failed runtime call / launch;
+ *   - never allocate, never synchronise, never exit; all work is enqueued on `stream`;
+ *   - the current device must already be set by the caller (torch does this).
+ */
+#ifndef OCC_B200_H_
+#define OCC_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* occ_stream_t; /* = cudaStream_t */
+
+int occ_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * LSS voxel pooling.
+ * Replaces: mmdet3d.ops.bev_pool.bev_pool(feats, coords, B, D, H, W)      M/ops/bev_pool/bev_pool.py:83-97
+ *           bev_pool_ext.bev_pool_forward                                  M/ops/bev_pool/src/bev_pool.cpp:22-47
+ *           ViewTransformerLiftSplatShootVoxel.voxel_pooling / lift        P/occformer/image2bev/ViewTransformerLSSVoxel.py:77-100,110-115
+ * Output layout is channel-last (B, X, Y, Z, C); the Python wrapper returns permuted views carrying the
+ * reference's shapes ((B,C,Z,X,Y) for bev_pool, (B,C,X,Y,Z) for voxel_pooling).
+ * Bookkeeping left in the workspace after a call (byte offsets from occ_voxel_pool_workspace_layout):
+ *   vox_id[n_points] int32 (linear voxel id ((b*X+x)*Y+y)*Z+z, -1 = dropped), starts[B*X*Y*Z+1] int32
+ *   (exclusive prefix of per-voxel point counts; starts[V] = n_kept), order[n_kept] int32 (point ids by voxel).
+ */
+size_t occ_voxel_pool_workspace_bytes(int n_points, int B, int X, int Y, int Z);
+int occ_voxel_pool_workspace_layout(int n_points, int B, int X, int Y, int Z, size_t* off_counts,
+                                    size_t* off_starts, size_t* off_order, size_t* off_vox_id);
+/* depth softmax over D + NCHW->NHWC of the context features (ViewTransformerLSSVoxel.py:108-110):
+ * depth_logits (BN, D, HW), img_feat (BN, C, HW) -> depth_prob (BN, D, HW), feat_cl (BN, HW, C) */
+int occ_lift_prologue(const float* depth_logits, const float* img_feat, float* depth_prob, float* feat_cl, int BN,
+                      int D, int C, int HW, occ_stream_t stream);
+/* fused lift-splat: out[b,x,y,z,:] = sum_{p in voxel} depth_prob[p] * feat_cl[pixel(p), :]; geom (B*N*D*HW, 3);
+ * dx/bx/nx = the view transformer's float parameters (ViewTransformerLSSBEVDepth.py:21-25,81-83). */
+int occ_lift_splat(const float* depth_prob, const float* feat_cl, const float* geom, float* out, int B, int N, int D,
+                   int HW, int C, float dx0, float dx1, float dx2, float bx0, float bx1, float bx2, float nx0,
+                   float nx1, float nx2, int X, int Y, int Z, void* workspace, size_t workspace_bytes,
+                   int counts_are_zero, occ_stream_t stream);
+/* voxel_pooling(geom, volume) with a materialised volume: feats (B*points_per_batch, C), geom (same rows, 3)
+ * (ViewTransformerLSSVoxel.py:77-100) */
+int occ_voxel_pool_geom(const float* feats, const float* geom, float* out, int B, int points_per_batch, int C,
+                        float dx0, float dx1, float dx2, float bx0, float bx1, float bx2, float nx0, float nx1,
+                        float nx2, int X, int Y, int Z, void* workspace, size_t workspace_bytes, occ_stream_t stream);
+/* drop-in bev_pool: feats (n, C), coords (n, 4) int64 (x, y, z, b) -> out (B, X, Y, Z, C) */
+int occ_bev_pool(const float* feats, const long long* coords, float* out, int n, int C, int B, int X, int Y, int Z,
+                 void* workspace, size_t workspace_bytes, occ_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * TF32 tensor-core GEMM / implicit-GEMM convolution (tcgen05 + TMA), fused epilogues.
+ * Replaces the cuBLAS / cuDNN calls issued by nn.Linear / nn.Conv3d / nn.Conv2d inside
+ *   DualpathTransformerBlock  P/occformer/backbones/dualpath_block.py:36-48,79
+ *   SwinBlock / WindowMSA     P/occformer/backbones/modules/window_attention.py:65-67,336-344
+ *   BottleNeckASPP / ASPP     P/occformer/backbones/modules/aspp.py:49-172
+ *   Mask2Former*OccHead       P/occformer/mask2former/mask2former_nusc_occ.py:446-457 (mask einsum), decoder K/V proj
+ * out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); act: 0 none, 1 ReLU, 2 GELU(erf); round_out: round to tf32.
+ * gn_stats (optional): fp64 (sum, sumsq) per (batch, group) of the raw accumulator, cpg = channels per group. */
+int occ_gemm_tf32(const float* A, const float* W, float* out, int M, int N, int K, const float* bias,
+                  const float* residual, int act, int round_out, double* gn_stats, int cpg, int rows_per_batch,
+                  occ_stream_t stream);
+/* x (B,X,Y,Z,Cin) channel-last, w2 (Cout, KX*KY*KZ*Cin) tap-major, out (B,Xo,Yo,Zo,Cout); K in {1,3}, stride in
+ * {1,2}, "same" padding dil*(K-1)/2.  2-D convs: Z = KZ = 1. */
+int occ_conv_tf32(const float* x, const float* w2, float* out, int B, int X, int Y, int Z, int Cin, int Cout, int KX,
+                  int KY, int KZ, int stride, int dil, const float* bias, const float* residual, int act,
+                  int round_out, double* gn_stats, int cpg, occ_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Dual-path encoder block glue (P/occformer/backbones/dualpath_block.py:65-82).
+ * Token rows: voxel tokens ((b*X+x)*Y+y)*Z+z, then BEV tokens B*X*Y*Z + (b*X+x)*Y+y. */
+/* GroupNorm+ReLU of the raw conv output, Z-mean, LayerNorm1 (dualpath_block.py:43-48,69; window_attention.py:355) */
+int occ_gn_relu_zmean_ln(const float* y, const double* stats, const float* gn_w, const float* gn_b,
+                         const float* ln_w, const float* ln_b, float* tok, float* tokn, int B, int XY, int Z, int C,
+                         int groups, occ_stream_t stream);
+int occ_layernorm(const float* in, const float* w, const float* b, float* out, long long rows, int C, int round_out,
+                  occ_stream_t stream);
+/* out[row, out_off + c] = act(gn(in[row, c])) (+ residual[row, c]) -- ASPP norms (aspp.py:42-46,117-120,166-172) */
+int occ_gn_apply(const float* in, const double* stats, const float* w, const float* b, const float* residual,
+                 float* out, long long rows, int rows_per_batch, int C, int groups, int ldo, int out_off, int relu,
+                 int round_out, occ_stream_t stream);
+/* ASPP image-pooling branch: GAP -> 1x1 conv -> GN -> ReLU -> broadcast (aspp.py:89-95,113-114) */
+int occ_aspp_gap_branch(const float* in, double* sums_ws, const float* wconv, const float* gw, const float* gb,
+                        float* cat, int B, int rows_per_batch, int ch, int groups, int ldo, int out_off,
+                        occ_stream_t stream);
+/* coeff = sigmoid(<x,w>+b); out = x + coeff * bev + identity (identity optionally GroupNorm'd: strided skip path)
+ * dualpath_block.py:36-41,79-82 */
+int occ_dualpath_fuse(const float* x, const float* bev, const float* cw, float cbias, const float* identity,
+                      const double* id_stats, const float* id_w, const float* id_b, int groups, float* out, int B,
+                      int XY, int Z, int C, occ_stream_t stream);
+/* (shifted) 7x7 window attention core over B*(Z+1) images: ShiftWindowMSA.forward + WindowMSA.forward
+ * (window_attention.py:168-242, 69-107) minus the qkv / proj linears. bias_dense = table[index] as (heads,49,49). */
+int occ_window_attention(const float* qkv, const float* qkv_bias, const float* bias_dense, float* out, int B, int X,
+                         int Y, int Z, int C, int heads, int shift, occ_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCC_B200_H_ */

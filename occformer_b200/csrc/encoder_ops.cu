@@ -1,0 +1,400 @@
+// Normalisation / layout / fusion kernels of the dual-path encoder block (all HBM-bound, one pass each).
+//
+// Token layout used by the whole encoder: channel-last rows of C floats.
+//   voxel tokens  : row ((b*X + x)*Y + y)*Z + z           (the (B,X,Y,Z,C) tensor itself)
+//   BEV tokens    : row B*X*Y*Z + (b*X + x)*Y + y         (mean over Z, appended behind the voxel tokens)
+// so the reference's rearrange 'b c x y z -> (b z) c x y', cat, NCHW<->NLC permutes and their inverses
+// (projects/mmdet3d_plugin/occformer/backbones/dualpath_block.py:69-76, modules/window_attention.py:350,370)
+// disappear: every one of the B*(Z+1) images is addressed in place.
+#include "occ_common.cuh"
+#include "occ_ptx.cuh"
+
+namespace occ {
+
+constexpr float kEps = 1e-5f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// mean / rstd of one GroupNorm group from the fp64 (sum, sumsq) accumulated by the conv epilogue.
+__device__ __forceinline__ void gn_mean_rstd(const double* __restrict__ stats, int b, int groups, int g, double count,
+                                             float* mean, float* rstd) {
+  const double s = stats[((size_t)b * groups + g) * 2 + 0];
+  const double q = stats[((size_t)b * groups + g) * 2 + 1];
+  const double m = s / count;
+  double var = q / count - m * m;
+  if (var < 0.0) var = 0.0;
+  *mean = (float)m;
+  *rstd = (float)(1.0 / sqrt(var + (double)kEps));
+}
+
+// LayerNorm of a row held as NV float4 per lane (C = 128*NV).  two-pass in registers.
+template <int NV>
+__device__ __forceinline__ void warp_layernorm(float4 (&v)[NV], int C, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, int lane, bool round) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + kEps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c0);
+    const float4 bb = *reinterpret_cast<const float4*>(beta + c0);
+    v[i].x = (v[i].x - mean) * rstd * g.x + bb.x;
+    v[i].y = (v[i].y - mean) * rstd * g.y + bb.y;
+    v[i].z = (v[i].z - mean) * rstd * g.z + bb.z;
+    v[i].w = (v[i].w - mean) * rstd * g.w + bb.w;
+    if (round) {
+      v[i].x = round_tf32(v[i].x); v[i].y = round_tf32(v[i].y);
+      v[i].z = round_tf32(v[i].z); v[i].w = round_tf32(v[i].w);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// input_conv tail: GroupNorm + ReLU of the raw conv output, Z-mean (BEV token), LayerNorm1 of both.
+//   y     : (B*X*Y*Z, C) raw Conv3d output                     (dualpath_block.py:43-48)
+//   tok   : (B*X*Y*(Z+1), C) <- relu(gn(y)) and its mean over Z (dualpath_block.py:69)
+//   tokn  : same rows, LayerNorm1'd and rounded to tf32 (operand of the QKV GEMM; window_attention.py:355)
+// One CTA handles `cols` (b,x,y) columns, one warp per voxel row; the CTA's smem holds the column for the mean.
+template <int NV>
+__global__ void __launch_bounds__(512)
+gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gn_w,
+                        const float* __restrict__ gn_b, const float* __restrict__ ln_w,
+                        const float* __restrict__ ln_b, float* __restrict__ tok, float* __restrict__ tokn, int B,
+                        int XY, int Z, int C, int groups, int cols) {
+  extern __shared__ float col_smem[];  // [cols][Z][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col_local = warp / Z, z = warp % Z;
+  const long long col = (long long)blockIdx.x * cols + col_local;  // (b*XY + xy)
+  const long long ncols = (long long)B * XY;
+  const bool active = col_local < cols && col < ncols;
+  const int cpg = C / groups;
+  const double count = (double)XY * Z * cpg;
+  float4 v[NV];
+  if (active) {
+    const int b = (int)(col / XY);
+    const long long row = col * Z + z;
+    const float4* src = reinterpret_cast<const float4*>(y + row * C);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = (i * 32 + lane) * 4;
+      float4 t = __ldcs(src + i * 32 + lane);
+      float mean, rstd;
+      gn_mean_rstd(stats, b, groups, c0 / cpg, count, &mean, &rstd);  // cpg >= 4: one group per float4
+      const float4 g = *reinterpret_cast<const float4*>(gn_w + c0);
+      const float4 bb = *reinterpret_cast<const float4*>(gn_b + c0);
+      t.x = fmaxf((t.x - mean) * rstd * g.x + bb.x, 0.f);
+      t.y = fmaxf((t.y - mean) * rstd * g.y + bb.y, 0.f);
+      t.z = fmaxf((t.z - mean) * rstd * g.z + bb.z, 0.f);
+      t.w = fmaxf((t.w - mean) * rstd * g.w + bb.w, 0.f);
+      v[i] = t;
+      *reinterpret_cast<float4*>(tok + row * C + c0) = t;
+      *reinterpret_cast<float4*>(col_smem + ((size_t)col_local * Z + z) * C + c0) = t;
+    }
+    warp_layernorm<NV>(v, C, ln_w, ln_b, lane, true);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      *reinterpret_cast<float4*>(tokn + row * C + (i * 32 + lane) * 4) = v[i];
+  }
+  __syncthreads();
+  if (active && z == 0) {
+    const long long brow = ncols * Z + col;
+    const float inv = 1.0f / (float)Z;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = (i * 32 + lane) * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int zz = 0; zz < Z; ++zz) {
+        const float4 t = *reinterpret_cast<const float4*>(col_smem + ((size_t)col_local * Z + zz) * C + c0);
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+      v[i] = a;
+      *reinterpret_cast<float4*>(tok + brow * C + c0) = a;
+    }
+    warp_layernorm<NV>(v, C, ln_w, ln_b, lane, true);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      *reinterpret_cast<float4*>(tokn + brow * C + (i * 32 + lane) * 4) = v[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// plain LayerNorm over rows (norm2, window_attention.py:360); warp per row
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ b,
+                 float* __restrict__ out, long long rows, int C, int round) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(in + row * C + (i * 32 + lane) * 4);
+  warp_layernorm<NV>(v, C, w, b, lane, round != 0);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(out + row * C + (i * 32 + lane) * 4) = v[i];
+}
+
+// generic-width LayerNorm (C not a multiple of 128): one warp per row, scalar loop
+__global__ void __launch_bounds__(256)
+layernorm_generic_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ b,
+                         float* __restrict__ out, long long rows, int C, int round) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* src = in + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += src[c];
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = src[c] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + kEps);
+  for (int c = lane; c < C; c += 32) {
+    float o = (src[c] - mean) * rstd * w[c] + b[c];
+    out[row * C + c] = round ? round_tf32(o) : o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm apply for the small 2-D maps of BottleNeckASPP (aspp.py:49-172) and the strided skip path:
+//   out[row, out_off + c] = act(gn(in[row, c])) (+ residual[row, c]);  rows = B * rows_per_batch.
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const float* __restrict__ in, const double* __restrict__ stats, const float* __restrict__ w,
+                const float* __restrict__ b, const float* __restrict__ residual, float* __restrict__ out,
+                long long rows, int rows_per_batch, int C, int groups, int ldo, int out_off, int relu, int round) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C4 = C >> 2;
+  if (i4 >= rows * C4) return;
+  const long long row = i4 / C4;
+  const int c0 = (int)(i4 % C4) * 4;
+  const int bidx = (int)(row / rows_per_batch);
+  const int cpg = C / groups;
+  const double count = (double)rows_per_batch * cpg;
+  const float4 t = *reinterpret_cast<const float4*>(in + row * C + c0);
+  float v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float mean, rstd;
+    gn_mean_rstd(stats, bidx, groups, (c0 + j) / cpg, count, &mean, &rstd);
+    float o = (v[j] - mean) * rstd * w[c0 + j] + b[c0 + j];
+    if (relu) o = fmaxf(o, 0.f);
+    if (residual) o += residual[row * C + c0 + j];
+    v[j] = round ? round_tf32(o) : o;
+  }
+  *reinterpret_cast<float4*>(out + row * ldo + out_off + c0) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ASPP global-average-pool branch (aspp.py:89-95,113-114): column mean over the rows of each batch sample.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ in, double* __restrict__ sums, int rows_per_batch, int C, int chunk) {
+  // grid (chunks, B); block 256 threads = (256/C4) row lanes x C4 float4 columns
+  const int b = blockIdx.y;
+  const int C4 = C >> 2;
+  const int rl = threadIdx.x / C4, c4 = threadIdx.x % C4;
+  const int rstep = blockDim.x / C4;
+  const int r0 = blockIdx.x * chunk;
+  const int r1 = min(r0 + chunk, rows_per_batch);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < rstep) {
+    for (int r = r0 + rl; r < r1; r += rstep) {
+      const float4 t = *reinterpret_cast<const float4*>(in + ((size_t)b * rows_per_batch + r) * C + c4 * 4);
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    atomicAdd(&sums[(size_t)b * C + c4 * 4 + 0], (double)a.x);
+    atomicAdd(&sums[(size_t)b * C + c4 * 4 + 1], (double)a.y);
+    atomicAdd(&sums[(size_t)b * C + c4 * 4 + 2], (double)a.z);
+    atomicAdd(&sums[(size_t)b * C + c4 * 4 + 3], (double)a.w);
+  }
+}
+
+// GAP -> 1x1 conv (no bias) -> GN over a 1x1 map -> ReLU -> broadcast into the concat buffer
+// (bilinear align_corners=True upsample of a 1x1 map = broadcast, aspp.py:114).  One CTA per batch sample.
+__global__ void __launch_bounds__(256)
+aspp_gap_branch_kernel(const double* __restrict__ sums, const float* __restrict__ wconv, const float* __restrict__ gw,
+                       const float* __restrict__ gb, float* __restrict__ cat, int rows_per_batch, int ch, int groups,
+                       int ldo, int out_off) {
+  extern __shared__ float sm[];  // mean[ch], conv[ch], outv[ch]
+  float* mean = sm;
+  float* conv = sm + ch;
+  float* outv = sm + 2 * ch;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < ch; c += blockDim.x) mean[c] = (float)(sums[(size_t)b * ch + c] / (double)rows_per_batch);
+  __syncthreads();
+  for (int o = threadIdx.x; o < ch; o += blockDim.x) {
+    float a = 0.f;
+    for (int i = 0; i < ch; ++i) a += wconv[(size_t)o * ch + i] * mean[i];
+    conv[o] = a;
+  }
+  __syncthreads();
+  const int cpg = ch / groups;
+  for (int o = threadIdx.x; o < ch; o += blockDim.x) {
+    const int g = o / cpg;
+    float m = 0.f;
+    for (int i = 0; i < cpg; ++i) m += conv[g * cpg + i];
+    m /= (float)cpg;
+    float var = 0.f;
+    for (int i = 0; i < cpg; ++i) { const float d = conv[g * cpg + i] - m; var += d * d; }
+    var /= (float)cpg;
+    outv[o] = fmaxf((conv[o] - m) * rsqrtf(var + kEps) * gw[o] + gb[o], 0.f);
+  }
+  __syncthreads();
+  const int ch4 = ch >> 2;
+  for (long long i = threadIdx.x; i < (long long)rows_per_batch * ch4; i += blockDim.x) {
+    const long long r = i / ch4;
+    const int c0 = (int)(i % ch4) * 4;
+    *reinterpret_cast<float4*>(cat + ((size_t)b * rows_per_batch + r) * ldo + out_off + c0) =
+        make_float4(round_tf32(outv[c0]), round_tf32(outv[c0 + 1]), round_tf32(outv[c0 + 2]), round_tf32(outv[c0 + 3]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Dual-path fusion (dualpath_block.py:79-82):
+//   coeff = sigmoid(<x, w> + bias);  out = x + coeff * x_bev[col] + identity
+// identity = block input (stride 1) or GroupNorm(downsample conv raw output) (stride 2; :36-41).
+template <int NV>
+__global__ void __launch_bounds__(256)
+fuse_kernel(const float* __restrict__ x, const float* __restrict__ bev, const float* __restrict__ cw, float cbias,
+            const float* __restrict__ identity, const double* __restrict__ id_stats, const float* __restrict__ id_w,
+            const float* __restrict__ id_b, int groups, float* __restrict__ out, long long rows, int Z,
+            long long rows_per_batch, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long col = row / Z;
+  float4 xv[NV];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (i * 32 + lane) * 4;
+    xv[i] = *reinterpret_cast<const float4*>(x + row * C + c0);
+    const float4 w = *reinterpret_cast<const float4*>(cw + c0);
+    dot += xv[i].x * w.x + xv[i].y * w.y + xv[i].z * w.z + xv[i].w * w.w;
+  }
+  dot = warp_sum(dot) + cbias;
+  const float coeff = 1.0f / (1.0f + expf(-dot));
+  const int bidx = (int)(row / rows_per_batch);
+  const int cpg = C / groups;
+  const double count = (double)rows_per_batch * cpg;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (i * 32 + lane) * 4;
+    const float4 bv = *reinterpret_cast<const float4*>(bev + col * C + c0);
+    float4 idv = __ldcs(reinterpret_cast<const float4*>(identity + row * C + c0));
+    if (id_stats) {
+      float mean, rstd;
+      gn_mean_rstd(id_stats, bidx, groups, c0 / cpg, count, &mean, &rstd);
+      const float4 g = *reinterpret_cast<const float4*>(id_w + c0);
+      const float4 bb = *reinterpret_cast<const float4*>(id_b + c0);
+      idv.x = (idv.x - mean) * rstd * g.x + bb.x;
+      idv.y = (idv.y - mean) * rstd * g.y + bb.y;
+      idv.z = (idv.z - mean) * rstd * g.z + bb.z;
+      idv.w = (idv.w - mean) * rstd * g.w + bb.w;
+    }
+    float4 o;
+    o.x = xv[i].x + coeff * bv.x + idv.x;
+    o.y = xv[i].y + coeff * bv.y + idv.y;
+    o.z = xv[i].z + coeff * bv.z + idv.z;
+    o.w = xv[i].w + coeff * bv.w + idv.w;
+    *reinterpret_cast<float4*>(out + row * C + c0) = o;
+  }
+}
+
+}  // namespace occ
+
+using namespace occ;
+
+#define DISPATCH_NV(C, CALL)                     \
+  switch ((C) / 128) {                           \
+    case 1: { constexpr int NV = 1; CALL; } break; \
+    case 2: { constexpr int NV = 2; CALL; } break; \
+    case 4: { constexpr int NV = 4; CALL; } break; \
+    case 8: { constexpr int NV = 8; CALL; } break; \
+    default: return OCC_EUNSUPPORTED;            \
+  }
+
+extern "C" int occ_gn_relu_zmean_ln(const float* y, const double* stats, const float* gn_w, const float* gn_b,
+                                    const float* ln_w, const float* ln_b, float* tok, float* tokn, int B, int XY,
+                                    int Z, int C, int groups, cudaStream_t stream) {
+  OCC_REQUIRE(y && stats && gn_w && gn_b && ln_w && ln_b && tok && tokn);
+  OCC_REQUIRE(B > 0 && XY > 0 && Z > 0 && Z <= 16 && C % 128 == 0 && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0);
+  int cols = 8 / Z;
+  if (cols < 1) cols = 1;
+  const size_t smem = (size_t)cols * Z * C * 4;
+  OCC_REQUIRE(smem <= 48 * 1024);
+  const long long ncols = (long long)B * XY;
+  const int blocks = (int)((ncols + cols - 1) / cols);
+  const int threads = cols * Z * 32;
+  DISPATCH_NV(C, (gn_relu_zmean_ln_kernel<NV><<<blocks, threads, smem, stream>>>(y, stats, gn_w, gn_b, ln_w, ln_b, tok,
+                                                                               tokn, B, XY, Z, C, groups, cols)));
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_layernorm(const float* in, const float* w, const float* b, float* out, long long rows, int C,
+                             int round_out, cudaStream_t stream) {
+  OCC_REQUIRE(in && w && b && out && rows > 0 && C > 0);
+  const int blocks = (int)((rows + 7) / 8);
+  if (C % 128 == 0 && (C / 128 == 1 || C / 128 == 2 || C / 128 == 4 || C / 128 == 8)) {
+    DISPATCH_NV(C, (layernorm_kernel<NV><<<blocks, 256, 0, stream>>>(in, w, b, out, rows, C, round_out)));
+  } else {
+    layernorm_generic_kernel<<<blocks, 256, 0, stream>>>(in, w, b, out, rows, C, round_out);
+  }
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_gn_apply(const float* in, const double* stats, const float* w, const float* b,
+                            const float* residual, float* out, long long rows, int rows_per_batch, int C, int groups,
+                            int ldo, int out_off, int relu, int round_out, cudaStream_t stream) {
+  OCC_REQUIRE(in && stats && w && b && out && rows > 0 && rows_per_batch > 0 && rows % rows_per_batch == 0);
+  OCC_REQUIRE(C % 4 == 0 && groups > 0 && C % groups == 0 && ldo % 4 == 0 && out_off % 4 == 0);
+  const long long n4 = rows * (C / 4);
+  gn_apply_kernel<<<(int)((n4 + 255) / 256), 256, 0, stream>>>(in, stats, w, b, residual, out, rows, rows_per_batch, C,
+                                                               groups, ldo, out_off, relu, round_out);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_aspp_gap_branch(const float* in, double* sums_ws, const float* wconv, const float* gw,
+                                   const float* gb, float* cat, int B, int rows_per_batch, int ch, int groups, int ldo,
+                                   int out_off, cudaStream_t stream) {
+  OCC_REQUIRE(in && sums_ws && wconv && gw && gb && cat);
+  OCC_REQUIRE(B > 0 && rows_per_batch > 0 && ch % 4 == 0 && ch <= 1024 && groups > 0 && ch % groups == 0 && 256 % (ch / 4) == 0);
+  OCC_CUDA(cudaMemsetAsync(sums_ws, 0, (size_t)B * ch * sizeof(double), stream));
+  const int chunk = 512;
+  dim3 grid((rows_per_batch + chunk - 1) / chunk, B);
+  colsum_kernel<<<grid, 256, 0, stream>>>(in, sums_ws, rows_per_batch, ch, chunk);
+  OCC_LAUNCH_CHECK();
+  aspp_gap_branch_kernel<<<B, 256, 3 * ch * sizeof(float), stream>>>(sums_ws, wconv, gw, gb, cat, rows_per_batch, ch,
+                                                                    groups, ldo, out_off);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_dualpath_fuse(const float* x, const float* bev, const float* cw, float cbias, const float* identity,
+                                 const double* id_stats, const float* id_w, const float* id_b, int groups, float* out,
+                                 int B, int XY, int Z, int C, cudaStream_t stream) {
+  OCC_REQUIRE(x && bev && cw && identity && out && B > 0 && XY > 0 && Z > 0 && C % 128 == 0);
+  if (id_stats) OCC_REQUIRE(id_w && id_b && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0);
+  const long long rows = (long long)B * XY * Z;
+  const int blocks = (int)((rows + 7) / 8);
+  DISPATCH_NV(C, (fuse_kernel<NV><<<blocks, 256, 0, stream>>>(x, bev, cw, cbias, identity, id_stats, id_w, id_b,
+                                                              groups > 0 ? groups : 1, out, rows, Z,
+                                                              (long long)XY * Z, C)));
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}

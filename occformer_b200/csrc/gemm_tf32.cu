@@ -1,0 +1,457 @@
+// Persistent warp-specialised TF32 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   D[M,N] = epilogue( A[M,K] * W[N,K]^T )          (plain mode: A row-major, W = torch Linear weight)
+//   D[vox,Cout] = epilogue( im2col(x)[vox, taps*Cin] * W2[Cout, taps*Cin]^T )   (conv mode)
+//
+// One CTA per SM, 256 threads: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle), warp 1 =
+// tcgen05.mma issuer (kind::tf32, M=128, N=BN, K=8 per instruction, fp32 accumulators in TMEM, two
+// accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1), warp 2 = TMEM
+// allocator, warps 4..7 = epilogue (tcgen05.ld 32x32b -> registers -> bias / activation / residual /
+// GroupNorm statistics -> global).  Conv mode never materialises im2col: every filter tap is a 5-D TMA
+// box {32 ch, bz, by, bx, 1} with a shifted origin; out-of-bounds = zero fill = the conv padding;
+// stride-2 convs use the tensor map's elementStrides.
+//
+// Replaces on the reference path: cuDNN Conv3d + cuBLAS Linear calls inside DualpathTransformerBlock
+// (projects/mmdet3d_plugin/occformer/backbones/dualpath_block.py:36-48,79), SwinBlock / WindowMSA
+// linears (backbones/modules/window_attention.py:65-67,336-344), BottleNeckASPP convs
+// (backbones/modules/aspp.py:49-172) and the decoder's K/V projections + mask einsum
+// (mask2former/mask2former_nusc_occ.py:446-457).
+#include "occ_common.cuh"
+#include "occ_ptx.cuh"
+
+namespace occ {
+
+constexpr int BM = 128;
+constexpr int BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 4;
+
+struct GemmParams {
+  int M, N, K, num_k_blocks;
+  float* out;
+  int ldo;
+  const float* bias;
+  const float* residual;
+  int ldr;
+  int act;        // 0 none, 1 relu, 2 gelu(erf)
+  int round_out;  // round result to tf32 (consumer is another tf32 MMA)
+  // conv mode
+  int conv;
+  int Cin, KX, KY, KZ, dil, stride;
+  int padx, pady, padz;
+  int B, Xo, Yo, Zo;
+  int bx, by, bz, tiles_x, tiles_y, tiles_z;
+  // GroupNorm statistics (sum, sumsq per (batch, group)), accumulated in fp64
+  double* gn_stats;
+  int cpg;
+  int rows_per_batch;  // plain mode: rows per batch sample (for gn_stats), else 0
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int CPG>
+__device__ __forceinline__ void accum_stats(const float (&v)[32], float (&sv)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    sv[2 * (j / CPG)] += v[j];
+    sv[2 * (j / CPG) + 1] += v[j] * v[j];
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  constexpr int B_STAGE_BYTES = BN * BK * 4;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t IDESC = make_idesc_tf32(BM, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  double* stat_acc = reinterpret_cast<double*>(tmem_ptr + 2);  // [64] doubles: (sum, sumsq) per group, <= 32 groups
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_n_tiles = (p.N + BN - 1) / BN;
+  const int num_m_tiles = p.conv ? p.B * p.tiles_x * p.tiles_y * p.tiles_z : (p.M + BM - 1) / BM;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  if (threadIdx.x >= 128) {
+    for (int i = threadIdx.x - 128; i < 64; i += 128) stat_acc[i] = 0.0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int cblocks = p.conv ? (p.Cin / BK) : 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % num_n_tiles;
+        const int m_tile = tile / num_n_tiles;
+        int cb = 0, cx0 = 0, cy0 = 0, cz0 = 0;
+        if (p.conv) {
+          int t = m_tile;
+          const int tz = t % p.tiles_z; t /= p.tiles_z;
+          const int ty = t % p.tiles_y; t /= p.tiles_y;
+          const int tx = t % p.tiles_x; t /= p.tiles_x;
+          cb = t;
+          cx0 = tx * p.bx * p.stride - p.padx;
+          cy0 = ty * p.by * p.stride - p.pady;
+          cz0 = tz * p.bz * p.stride - p.padz;
+        }
+        int tap = 0, kc = 0, tx_ = 0, ty_ = 0, tz_ = 0;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (p.conv) {
+            tma_load_5d(sa, &tmA, &full_bar[stage], kc * BK, cz0 + tz_ * p.dil, cy0 + ty_ * p.dil,
+                        cx0 + tx_ * p.dil, cb);
+            if (++kc == cblocks) {
+              kc = 0;
+              ++tap;
+              if (++tz_ == p.KZ) {
+                tz_ = 0;
+                if (++ty_ == p.KY) { ty_ = 0; ++tx_; }
+              }
+            }
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_tile * BM);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_tile * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        (void)tap;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer (single thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty[buf], (((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t adesc = make_sw128_desc(sa, 1024, 16);
+          const uint64_t bdesc = make_sw128_desc(sb, 1024, 16);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            // advance 8 tf32 = 32 bytes = 2 (16-byte units) inside the 128-byte swizzle row
+            mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+          }
+          mma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&tmem_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------- epilogue warps
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    int it = 0;
+    int cur_b = -1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int n_tile = tile % num_n_tiles;
+      const int m_tile = tile / num_n_tiles;
+      const int n0 = n_tile * BN;
+      // ---- output row of this thread
+      long long m = -1;
+      int tile_b = 0;
+      if (p.conv) {
+        int t = m_tile;
+        const int tz = t % p.tiles_z; t /= p.tiles_z;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        tile_b = t;
+        const int dz = row % p.bz;
+        const int dy = (row / p.bz) % p.by;
+        const int dx = row / (p.bz * p.by);
+        const int x = tx * p.bx + dx, y = ty * p.by + dy, z = tz * p.bz + dz;
+        if (x < p.Xo && y < p.Yo && z < p.Zo)
+          m = (((long long)tile_b * p.Xo + x) * p.Yo + y) * p.Zo + z;
+      } else {
+        const long long mm = (long long)m_tile * BM + row;
+        if (mm < p.M) m = mm;
+        if (p.rows_per_batch > 0) tile_b = (int)(((long long)m_tile * BM) / p.rows_per_batch);
+      }
+      const bool valid = m >= 0;
+
+      if (p.gn_stats != nullptr && tile_b != cur_b) {
+        // flush the per-CTA fp64 partial sums of the previous batch sample
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (cur_b >= 0) {
+          const int ngroups2 = 2 * (p.N / p.cpg);
+          for (int i = threadIdx.x - 128; i < ngroups2; i += 128) {
+            const double v = stat_acc[i];
+            if (v != 0.0) atomicAdd(&p.gn_stats[(size_t)cur_b * ngroups2 + i], v);
+            stat_acc[i] = 0.0;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_b = tile_b;
+      }
+
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * BN;
+      float* orow = valid ? p.out + m * p.ldo : nullptr;
+      const float* rrow = (valid && p.residual) ? p.residual + m * p.ldr : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int nc = n0 + c * 32;
+        if (nc >= p.N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full_chunk = (nc + 32 <= p.N);
+        if (p.gn_stats != nullptr) {
+          // per-group sum / sumsq of the raw conv output, butterfly-reduced over the 32 rows of the warp
+          float sv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sv[j] = 0.f;
+          const int cpg = p.cpg;  // power of two in [2, 32]
+          if (valid) {
+            if (cpg == 2) accum_stats<2>(v, sv);
+            else if (cpg == 4) accum_stats<4>(v, sv);
+            else if (cpg == 8) accum_stats<8>(v, sv);
+            else if (cpg == 16) accum_stats<16>(v, sv);
+            else accum_stats<32>(v, sv);
+          }
+#pragma unroll
+          for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < n / 2; ++i) {
+              const float keep = upper ? sv[i + n / 2] : sv[i];
+              const float send = upper ? sv[i] : sv[i + n / 2];
+              sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          // lane L now holds the warp total of value L (value = 2*local_group + {0: sum, 1: sumsq})
+          if (lane < 2 * (32 / cpg)) atomicAdd(&stat_acc[2 * (nc / cpg) + lane], (double)sv[0]);
+        }
+        if (valid) {
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full_chunk || nc + j < p.N) v[j] += __ldg(p.bias + nc + j);
+          }
+          if (rrow) {
+            if (full_chunk) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 rr = *reinterpret_cast<const float4*>(rrow + nc + j);
+                v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nc + j < p.N) v[j] += rrow[nc + j];
+            }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (p.round_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+          }
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(orow + nc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.N) orow[nc + j] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+    if (p.gn_stats != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (cur_b >= 0) {
+        const int ngroups2 = 2 * (p.N / p.cpg);
+        for (int i = threadIdx.x - 128; i < ngroups2; i += 128) {
+          const double v = stat_acc[i];
+          if (v != 0.0) atomicAdd(&p.gn_stats[(size_t)cur_b * ngroups2 + i], v);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace occ
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+namespace occ {
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_tiles,
+                       cudaStream_t stream) {
+  constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BK * 4) + 1024 /*align*/ + 1024 /*barriers+stats*/;
+  static bool configured = false;
+  if (!configured) {
+    OCC_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    configured = true;
+  }
+  int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  if (grid < 1) grid = 1;
+  gemm_tf32_kernel<BN, STAGES><<<grid, 256, smem, stream>>>(tmA, tmB, p);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+static int dispatch_gemm(const CUtensorMap& tmA, const void* W, GemmParams& p, int num_m_tiles, cudaStream_t stream) {
+  int BN = p.N <= 32 ? 32 : p.N <= 64 ? 64 : (p.N <= 128 || (p.N % 256 != 0 && p.N % 128 == 0)) ? 128 : 256;
+  CUtensorMap tmB;
+  uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+  uint64_t strides[1] = {(uint64_t)p.K * 4};
+  uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+  int rc = make_tmap_f32(&tmB, W, 2, dims, strides, box, nullptr);
+  if (rc) return rc;
+  const int num_tiles = num_m_tiles * ((p.N + BN - 1) / BN);
+  switch (BN) {
+    case 32: return launch_gemm<32, 8>(tmA, tmB, p, num_tiles, stream);
+    case 64: return launch_gemm<64, 8>(tmA, tmB, p, num_tiles, stream);
+    case 128: return launch_gemm<128, 6>(tmA, tmB, p, num_tiles, stream);
+    default: return launch_gemm<256, 4>(tmA, tmB, p, num_tiles, stream);
+  }
+}
+
+}  // namespace occ
+
+using namespace occ;
+
+extern "C" int occ_gemm_tf32(const float* A, const float* W, float* out, int M, int N, int K, const float* bias,
+                             const float* residual, int act, int round_out, double* gn_stats, int cpg,
+                             int rows_per_batch, cudaStream_t stream) {
+  OCC_REQUIRE(A && W && out);
+  OCC_REQUIRE(M > 0 && N > 0 && K > 0);
+  OCC_REQUIRE(K % 4 == 0);  // 16-byte row pitch for TMA
+  OCC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  OCC_REQUIRE(act >= 0 && act <= 2);
+  if (gn_stats) OCC_REQUIRE(cpg >= 2 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && N % cpg == 0 && N / cpg <= 32 &&
+                            rows_per_batch > 0 && rows_per_batch % BM == 0);
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.num_k_blocks = (K + BK - 1) / BK;
+  p.out = out; p.ldo = N; p.bias = bias; p.residual = residual; p.ldr = N; p.act = act; p.round_out = round_out;
+  p.conv = 0; p.gn_stats = gn_stats; p.cpg = cpg; p.rows_per_batch = gn_stats ? rows_per_batch : 0;
+  CUtensorMap tmA;
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+  uint64_t strides[1] = {(uint64_t)K * 4};
+  uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+  int rc = make_tmap_f32(&tmA, A, 2, dims, strides, box, nullptr);
+  if (rc) return rc;
+  return dispatch_gemm(tmA, W, p, (M + BM - 1) / BM, stream);
+}
+
+// x: (B, X, Y, Z, Cin) channel-last fp32;  w2: (Cout, KX*KY*KZ*Cin) tap-major repacked weights;
+// out: (B, Xo, Yo, Zo, Cout).  pad = dil*(K-1)/2 per axis ("same" for stride 1), Xo = (X + 2p - dil*(K-1) - 1)/s + 1.
+extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B, int X, int Y, int Z, int Cin,
+                             int Cout, int KX, int KY, int KZ, int stride, int dil, const float* bias,
+                             const float* residual, int act, int round_out, double* gn_stats, int cpg,
+                             cudaStream_t stream) {
+  OCC_REQUIRE(x && w2 && out);
+  OCC_REQUIRE(B > 0 && X > 0 && Y > 0 && Z > 0 && Cin > 0 && Cout > 0);
+  OCC_REQUIRE(Cin % BK == 0);
+  OCC_REQUIRE((KX == 1 || KX == 3) && (KY == 1 || KY == 3) && (KZ == 1 || KZ == 3));
+  OCC_REQUIRE(stride == 1 || stride == 2);
+  OCC_REQUIRE(dil >= 1 && act >= 0 && act <= 2);
+  OCC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0);
+  if (gn_stats) OCC_REQUIRE(cpg >= 2 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && Cout % cpg == 0 && Cout / cpg <= 32);
+  GemmParams p{};
+  p.conv = 1;
+  p.Cin = Cin; p.KX = KX; p.KY = KY; p.KZ = KZ; p.dil = dil; p.stride = stride;
+  p.padx = dil * (KX - 1) / 2; p.pady = dil * (KY - 1) / 2; p.padz = dil * (KZ - 1) / 2;
+  p.B = B;
+  p.Xo = (X + 2 * p.padx - dil * (KX - 1) - 1) / stride + 1;
+  p.Yo = (Y + 2 * p.pady - dil * (KY - 1) - 1) / stride + 1;
+  p.Zo = (Z + 2 * p.padz - dil * (KZ - 1) - 1) / stride + 1;
+  p.bz = next_pow2(p.Zo) < BM ? next_pow2(p.Zo) : BM;
+  p.by = next_pow2(p.Yo) < BM / p.bz ? next_pow2(p.Yo) : BM / p.bz;
+  p.bx = BM / (p.bz * p.by);
+  p.tiles_x = (p.Xo + p.bx - 1) / p.bx;
+  p.tiles_y = (p.Yo + p.by - 1) / p.by;
+  p.tiles_z = (p.Zo + p.bz - 1) / p.bz;
+  p.N = Cout; p.K = KX * KY * KZ * Cin; p.num_k_blocks = p.K / BK;
+  p.M = B * p.Xo * p.Yo * p.Zo;
+  p.out = out; p.ldo = Cout; p.bias = bias; p.residual = residual; p.ldr = Cout; p.act = act; p.round_out = round_out;
+  p.gn_stats = gn_stats; p.cpg = cpg; p.rows_per_batch = 0;
+  OCC_REQUIRE(p.bx * stride <= 256 && p.by * stride <= 256 && p.bz * stride <= 256);
+  CUtensorMap tmA;
+  uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)Z, (uint64_t)Y, (uint64_t)X, (uint64_t)B};
+  uint64_t strides[4] = {(uint64_t)Cin * 4, (uint64_t)Z * Cin * 4, (uint64_t)Y * Z * Cin * 4,
+                         (uint64_t)X * Y * Z * Cin * 4};
+  uint32_t box[5] = {(uint32_t)BK, (uint32_t)(p.bz * stride), (uint32_t)(p.by * stride), (uint32_t)(p.bx * stride), 1};
+  uint32_t estr[5] = {1, (uint32_t)stride, (uint32_t)stride, (uint32_t)stride, 1};
+  int rc = make_tmap_f32(&tmA, x, 5, dims, strides, box, estr);
+  if (rc) return rc;
+  return dispatch_gemm(tmA, w2, p, B * p.tiles_x * p.tiles_y * p.tiles_z, stream);
+}

@@ -1,0 +1,278 @@
+"""B200-native dual-path voxel transformer encoder, drop-in for the reference's modules:
+
+    BACKBONES 'OccupancyEncoder'              projects/mmdet3d_plugin/occformer/backbones/occnet.py:12-74
+    DualpathTransformerBlock                  .../backbones/dualpath_block.py:13-82
+    SwinBlock / ShiftWindowMSA / WindowMSA    .../backbones/modules/window_attention.py:14-372
+    BottleNeckASPP / ASPP                     .../backbones/modules/aspp.py:49-172
+
+Same constructor kwargs, same ``forward(x (B,C,X,Y,Z)) -> list[Tensor (B,C,X',Y',Z')]``, same ``state_dict``
+keys and shapes -- the torch.nn sub-modules below are *parameter containers only*;
+all arithmetic runs in libocc_b200.so (tcgen05 TF32 GEMM / implicit-GEMM conv, fused norm / window
+attention / fusion kernels).  Inference (eval, no autograd) only.  Internally every tensor is channel-last
+(B,X,Y,Z,C); returned tensors are permuted *views* with the reference's shape.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .registry import BACKBONES
+
+
+def _gn(norm_cfg, channels, groups=None):
+    g = groups if groups is not None else norm_cfg.get("num_groups", 32)
+    return nn.GroupNorm(g, channels, eps=1e-5)
+
+
+class _WindowMSA(nn.Module):
+    def __init__(self, embed_dims, num_heads, ws=7):
+        super().__init__()
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws - 1) * (2 * ws - 1), num_heads))
+        seq1 = torch.arange(0, (2 * ws - 1) * ws, 2 * ws - 1)
+        seq2 = torch.arange(0, ws, 1)
+        c = (seq1[:, None] + seq2[None, :]).reshape(1, -1)
+        self.register_buffer("relative_position_index", (c + c.T).flip(1).contiguous())
+        self.qkv = nn.Linear(embed_dims, embed_dims * 3, bias=True)
+        self.proj = nn.Linear(embed_dims, embed_dims)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+
+
+class _ShiftWindowMSA(nn.Module):
+    def __init__(self, embed_dims, num_heads):
+        super().__init__()
+        self.w_msa = _WindowMSA(embed_dims, num_heads)
+
+
+class _FFN(nn.Module):
+    def __init__(self, embed_dims, hidden):
+        super().__init__()
+        self.layers = nn.Sequential(nn.Sequential(nn.Linear(embed_dims, hidden), nn.GELU(), nn.Dropout(0.0)),
+                                    nn.Linear(hidden, embed_dims), nn.Dropout(0.0))
+
+
+class _SwinBlock(nn.Module):
+    def __init__(self, embed_dims, num_heads, shift):
+        super().__init__()
+        self.shift = shift
+        self.num_heads = num_heads
+        self.norm1 = nn.LayerNorm(embed_dims)
+        self.attn = _ShiftWindowMSA(embed_dims, num_heads)
+        self.norm2 = nn.LayerNorm(embed_dims)
+        self.ffn = _FFN(embed_dims, embed_dims)
+
+
+class _ASPPModule(nn.Module):
+    def __init__(self, inplanes, planes, k, dilation, groups):
+        super().__init__()
+        self.atrous_conv = nn.Conv2d(inplanes, planes, k, stride=1, padding=0 if k == 1 else dilation,
+                                     dilation=dilation, bias=False)
+        self.bn = nn.GroupNorm(groups, planes)
+        nn.init.kaiming_normal_(self.atrous_conv.weight)
+
+
+class _ASPP(nn.Module):
+    def __init__(self, ch, dilations, groups):
+        super().__init__()
+        self.aspp1 = _ASPPModule(ch, ch, 1, dilations[0], groups)
+        self.aspp2 = _ASPPModule(ch, ch, 3, dilations[1], groups)
+        self.aspp3 = _ASPPModule(ch, ch, 3, dilations[2], groups)
+        self.aspp4 = _ASPPModule(ch, ch, 3, dilations[3], groups)
+        self.global_avg_pool = nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)), nn.Conv2d(ch, ch, 1, bias=False),
+                                             nn.GroupNorm(groups, ch), nn.ReLU())
+        self.conv1 = nn.Conv2d(5 * ch, ch, 1, bias=False)
+        self.bn1 = nn.GroupNorm(groups, ch)
+        nn.init.kaiming_normal_(self.conv1.weight)
+        nn.init.kaiming_normal_(self.global_avg_pool[1].weight)
+
+
+class _BottleNeckASPP(nn.Module):
+    def __init__(self, inplanes, norm_cfg, reduction=4, dilations=(1, 6, 12, 18)):
+        super().__init__()
+        ch = inplanes // reduction
+        ng = norm_cfg.get("num_groups", 32)
+        self.dilations = tuple(dilations)
+        self.inner_groups = ch // 2 if ch <= ng else ng  # aspp.py:150-154
+        self.outer_groups = ng
+        self.input_conv = nn.Sequential(nn.Conv2d(inplanes, ch, 1, bias=False), nn.GroupNorm(ng, ch), nn.ReLU())
+        self.aspp = _ASPP(ch, dilations, self.inner_groups)
+        self.output_conv = nn.Sequential(nn.Conv2d(ch, inplanes, 1, bias=False), nn.GroupNorm(ng, inplanes), nn.ReLU())
+
+
+class DualpathTransformerBlock(nn.Module):
+    """dualpath_block.py:13-82.  ``layer_index`` decides the window shift (odd = shifted)."""
+
+    def __init__(self, in_channels, channels, stride=1, norm_cfg=None, init_cfg=None, coeff_bias=True, aspp_drop=0.1,
+                 **kwargs):
+        super().__init__()
+        norm_cfg = dict(norm_cfg or dict(type="GN", num_groups=32))
+        assert norm_cfg.get("type", "GN") == "GN", "the B200 path implements the reference's GN configuration"
+        self.in_channels, self.channels, self.stride = in_channels, channels, stride
+        self.groups = norm_cfg.get("num_groups", 32)
+        self.shift = (kwargs["layer_index"] % 2) == 1
+        self.num_heads = int(channels / 32)
+        if stride > 1:
+            self.downsample = nn.Sequential(nn.Conv3d(in_channels, channels, 1, stride=stride, bias=False),
+                                            _gn(norm_cfg, channels))
+        else:
+            self.downsample = nn.Identity()
+        self.input_conv = nn.Sequential(nn.Conv3d(in_channels, channels, 3, padding=1, stride=stride, bias=False),
+                                        _gn(norm_cfg, channels), nn.ReLU())
+        self.bev_encoder = _SwinBlock(channels, self.num_heads, self.shift)
+        self.aspp = _BottleNeckASPP(channels, norm_cfg)
+        self.combine_coeff = nn.Conv3d(channels, 1, 1, bias=coeff_bias)
+        self._prep = None
+        self.register_load_state_dict_post_hook(lambda m, k: m._invalidate())
+
+    def _invalidate(self):
+        self._prep = None
+
+    def _apply(self, fn, *a, **k):
+        self._prep = None
+        return super()._apply(fn, *a, **k)
+
+    # ------------------------------------------------------------------ one-time weight preparation
+    @torch.no_grad()
+    def _prepare(self):
+        r = ops.round_tf32_
+        P = {}
+        P["w_in"], P["k_in"] = ops.repack_conv_weight(self.input_conv[0].weight.detach().float())
+        if self.stride > 1:
+            P["w_ds"], P["k_ds"] = ops.repack_conv_weight(self.downsample[0].weight.detach().float())
+        msa = self.bev_encoder.attn.w_msa
+        P["w_qkv"] = r(msa.qkv.weight.detach().float().clone().contiguous())
+        P["w_proj"] = r(msa.proj.weight.detach().float().clone().contiguous())
+        ffn = self.bev_encoder.ffn.layers
+        P["w_f1"] = r(ffn[0][0].weight.detach().float().clone().contiguous())
+        P["w_f2"] = r(ffn[1].weight.detach().float().clone().contiguous())
+        table = msa.relative_position_bias_table.detach().float()
+        idx = msa.relative_position_index.view(-1)
+        P["bias_dense"] = table[idx].view(49, 49, -1).permute(2, 0, 1).contiguous()  # (heads,49,49)
+        a = self.aspp
+        P["w_a_in"], P["k1"] = ops.repack_conv_weight(a.input_conv[0].weight.detach().float())
+        for i in (1, 2, 3, 4):
+            P[f"w_a{i}"], P[f"k_a{i}"] = ops.repack_conv_weight(getattr(a.aspp, f"aspp{i}").atrous_conv.weight.detach().float())
+        P["w_gap"] = a.aspp.global_avg_pool[1].weight.detach().float().reshape(a.aspp.global_avg_pool[1].weight.shape[0], -1).contiguous()
+        P["w_a_c1"], _ = ops.repack_conv_weight(a.aspp.conv1.weight.detach().float())
+        P["w_a_out"], _ = ops.repack_conv_weight(a.output_conv[0].weight.detach().float())
+        P["coeff_w"] = self.combine_coeff.weight.detach().float().reshape(-1).contiguous()
+        P["coeff_b"] = float(self.combine_coeff.bias.detach().float().item()) if self.combine_coeff.bias is not None else 0.0
+        self._prep = P
+        return P
+
+    # ------------------------------------------------------------------ forward on channel-last tensors
+    @torch.no_grad()
+    def forward_cl(self, x_cl):
+        """x_cl (B,X,Y,Z,Cin) contiguous channel-last -> (B,X',Y',Z',C) contiguous channel-last."""
+        P = self._prep or self._prepare()
+        B, X0, Y0, Z0, Cin = x_cl.shape
+        C, G, s = self.channels, self.groups, self.stride
+        dev = x_cl.device
+        stats = torch.zeros((10, B, 32, 2), dtype=torch.float64, device=dev)
+        # (A4) Conv3d 3x3x3 (+stride) -> raw output + GroupNorm statistics from the GEMM epilogue
+        y_raw = ops.conv(x_cl, P["w_in"], P["k_in"], stride=s, gn_stats=stats[0], cpg=C // G)
+        _, X, Y, Z, _ = y_raw.shape
+        XY = X * Y
+        nvox = B * XY * Z
+        ic, sw = self.input_conv, self.bev_encoder
+        # (A4/A5/A6) GN + ReLU, Z-mean BEV token, LayerNorm1 -- one pass
+        tok, tokn = ops.gn_relu_zmean_ln(y_raw.view(nvox, C), stats[0], ic[1].weight, ic[1].bias, sw.norm1.weight,
+                                         sw.norm1.bias, B, XY, Z, C, G)
+        msa = sw.attn.w_msa
+        # (A8) QKV projection of every token (pad tokens are synthesised from the bias inside the attention kernel)
+        qkv = ops.gemm(tokn, P["w_qkv"], bias=msa.qkv.bias)
+        # (A7/A8) shifted-window attention core, gathers/scatters windows in place
+        att = ops.window_attention(qkv, msa.qkv.bias, P["bias_dense"], B, X, Y, Z, C, self.num_heads, self.shift)
+        # proj + residual, LayerNorm2, FFN (GELU) + residual  (A6)
+        y1 = ops.gemm(att, P["w_proj"], bias=msa.proj.bias, residual=tok)
+        y1n = ops.layernorm(y1, sw.norm2.weight, sw.norm2.bias, round_out=True)
+        ffn = sw.ffn.layers
+        h = ops.gemm(y1n, P["w_f1"], bias=ffn[0][0].bias, act=2, round_out=True)
+        y2 = ops.gemm(h, P["w_f2"], bias=ffn[1].bias, residual=y1)
+        x_vox, x_bev = y2[:nvox], y2[nvox:]
+        # (A9) BottleNeckASPP on the BEV tokens (B, X, Y, 1, C)
+        bev_out = self._aspp(x_bev, B, X, Y, C, stats, P)
+        # (A10) fusion + skip connection
+        if s > 1:
+            id_raw = ops.conv(x_cl, P["w_ds"], P["k_ds"], stride=s, gn_stats=stats[9], cpg=C // G)
+            out = ops.dualpath_fuse(x_vox, bev_out, P["coeff_w"], P["coeff_b"], id_raw.view(nvox, C), B, XY, Z, C,
+                                    id_stats=stats[9], id_w=self.downsample[1].weight, id_b=self.downsample[1].bias,
+                                    groups=G)
+        else:
+            out = ops.dualpath_fuse(x_vox, bev_out, P["coeff_w"], P["coeff_b"], x_cl.view(nvox, C), B, XY, Z, C)
+        return out.view(B, X, Y, Z, C)
+
+    def _aspp(self, x_bev, B, X, Y, C, stats, P):
+        a = self.aspp
+        ch = C // 4
+        XY = X * Y
+        gi, go = a.inner_groups, a.outer_groups
+
+        def conv2d(t, w, k, dil=1, st=None, cpg=0):
+            cin = t.shape[-1]
+            return ops.conv(t.view(B, X, Y, 1, cin), w, k, dil=dil, gn_stats=st, cpg=cpg).view(B * XY, -1)
+
+        t = conv2d(x_bev, P["w_a_in"], (1, 1, 1), st=stats[1], cpg=ch // go)
+        y = ops.gn_apply(t, stats[1], a.input_conv[1].weight, a.input_conv[1].bias, XY, go)
+        cat = torch.empty((B * XY, 5 * ch), dtype=torch.float32, device=x_bev.device)
+        for i, d in zip((1, 2, 3, 4), a.dilations):
+            m = getattr(a.aspp, f"aspp{i}")
+            k = P[f"k_a{i}"]
+            t = conv2d(y, P[f"w_a{i}"], k, dil=d if k[0] == 3 else 1, st=stats[1 + i], cpg=ch // gi)
+            ops.gn_apply(t, stats[1 + i], m.bn.weight, m.bn.bias, XY, gi, out=cat, out_off=(i - 1) * ch, round_out=True)
+        gap = a.aspp.global_avg_pool
+        ops.aspp_gap_branch(y, P["w_gap"], gap[2].weight, gap[2].bias, cat, B, XY, gi, 4 * ch)
+        t = conv2d(cat, P["w_a_c1"], (1, 1, 1), st=stats[6], cpg=ch // gi)
+        y3 = ops.gn_apply(t, stats[6], a.aspp.bn1.weight, a.aspp.bn1.bias, XY, gi, residual=y)
+        t = conv2d(y3, P["w_a_out"], (1, 1, 1), st=stats[7], cpg=C // go)
+        return ops.gn_apply(t, stats[7], a.output_conv[1].weight, a.output_conv[1].bias, XY, go, residual=x_bev)
+
+    def forward(self, x):
+        return to_reference_layout(self.forward_cl(to_channel_last(x)))
+
+
+def to_channel_last(x):
+    """(B,C,X,Y,Z) reference-layout tensor (any strides) -> contiguous (B,X,Y,Z,C).  Zero-copy when x is
+    already a permuted view of channel-last memory (what this package's own modules hand around)."""
+    if not x.is_cuda:
+        raise RuntimeError("occformer_b200: the encoder runs on CUDA tensors only (no CPU fallback)")
+    return x.float().permute(0, 2, 3, 4, 1).contiguous()
+
+
+def to_reference_layout(x_cl):
+    return x_cl.permute(0, 4, 1, 2, 3)
+
+
+@BACKBONES.register_module()
+class OccupancyEncoder(nn.Module):
+    """occnet.py:12-74 -- same kwargs; ``with_cp`` is accepted and ignored (inference path)."""
+
+    def __init__(self, in_channels, num_stage=4, block_numbers=[2, 2, 2, 2], block_inplanes=[64, 128, 256, 512],
+                 block_strides=[1, 2, 2, 2], out_indices=(0, 1, 2, 3), norm_cfg=dict(type="BN3d", requires_grad=True),
+                 with_cp=True, **kwargs):
+        super().__init__()
+        self.out_indices = out_indices
+        self.num_layers = 0
+        self.layers = nn.ModuleList()
+        for i in range(num_stage):
+            blocks = []
+            stride = block_strides[i]
+            for _ in range(block_numbers[i]):
+                blocks.append(DualpathTransformerBlock(in_channels, block_inplanes[i], stride=stride, norm_cfg=norm_cfg,
+                                                       layer_index=self.num_layers, stage_index=i, **kwargs))
+                in_channels = block_inplanes[i]
+                stride = 1
+                self.num_layers += 1
+            self.layers.append(nn.Sequential(*blocks))
+        self.with_cp = with_cp
+
+    @torch.no_grad()
+    def forward_cl(self, x_cl):
+        res = []
+        for index, layer in enumerate(self.layers):
+            for blk in layer:
+                x_cl = blk.forward_cl(x_cl)
+            if index in self.out_indices:
+                res.append(x_cl)
+        return res
+
+    def forward(self, x):
+        return [to_reference_layout(t) for t in self.forward_cl(to_channel_last(x))]

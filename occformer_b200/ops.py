@@ -1,0 +1,249 @@
+"""Torch-tensor wrappers over the C-ABI kernels (device memory + streams are torch's; the math is ours).
+
+Every function checks device / dtype / contiguity, passes raw pointers and the current torch stream to
+libocc_b200.so and raises RuntimeError on a non-zero return code.  No fallback paths.
+"""
+import ctypes
+
+import torch
+
+from ._lib import check, lib
+
+LAUNCH_COUNT = [0]  # kernels launched by this library (bench.py reports it as gpu_launches)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, name, dtype=torch.float32):
+    if not t.is_cuda:
+        raise RuntimeError(f"occformer_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"occformer_b200: {name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"occformer_b200: {name} must be contiguous")
+    return t
+
+
+def round_tf32_(w):
+    """Round an fp32 tensor to the nearest tf32 value (ties away), in place.  Applied once to weights so the
+    tensor cores (which drop the low 13 mantissa bits) see correctly *rounded* operands."""
+    i = w.view(torch.int32)
+    i.add_(0x1000).bitwise_and_(-8192)  # 0xFFFFE000
+    return w
+
+
+# ----------------------------------------------------------------------------------------------- voxel pooling
+class VoxelPoolWorkspace:
+    def __init__(self, n_points, B, X, Y, Z, device):
+        l = lib()
+        self.key = (n_points, B, X, Y, Z)
+        self.nbytes = l.occ_voxel_pool_workspace_bytes(n_points, B, X, Y, Z)
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        offs = [ctypes.c_size_t() for _ in range(4)]
+        l.occ_voxel_pool_workspace_layout(n_points, B, X, Y, Z, *[ctypes.byref(o) for o in offs])
+        self.off_counts, self.off_starts, self.off_order, self.off_vox_id = (o.value for o in offs)
+        self.V = B * X * Y * Z
+        self.P = n_points
+
+    def _ints(self, off, n):
+        return self.buf[off:off + 4 * n].view(torch.int32)
+
+    @property
+    def starts(self):
+        return self._ints(self.off_starts, self.V + 1)
+
+    @property
+    def vox_id(self):
+        return self._ints(self.off_vox_id, self.P)
+
+    @property
+    def order(self):
+        return self._ints(self.off_order, self.P)
+
+
+_ws_cache = {}
+
+
+def _workspace(n_points, B, X, Y, Z, device):
+    key = (n_points, B, X, Y, Z, str(device))
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = VoxelPoolWorkspace(n_points, B, X, Y, Z, device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def lift_prologue(depth_logits, img_feat):
+    """depth_logits (BN,D,fH,fW), img_feat (BN,C,fH,fW) -> depth_prob (BN,D,fH,fW), feat_cl (BN,fH*fW,C)."""
+    _chk(depth_logits, "depth_logits"), _chk(img_feat, "img_feat")
+    BN, D, fH, fW = depth_logits.shape
+    C = img_feat.shape[1]
+    prob = torch.empty_like(depth_logits)
+    feat_cl = torch.empty((BN, fH * fW, C), dtype=torch.float32, device=img_feat.device)
+    check(lib().occ_lift_prologue(_ptr(depth_logits), _ptr(img_feat), _ptr(prob), _ptr(feat_cl), BN, D, C, fH * fW,
+                                  _stream()), "occ_lift_prologue")
+    LAUNCH_COUNT[0] += 2
+    return prob, feat_cl
+
+
+def lift_splat(depth_prob, feat_cl, geom, B, N, dx, bx, nx, grid, return_workspace=False):
+    """Fused lift-splat.  Returns the channel-last grid (B,X,Y,Z,C)."""
+    _chk(depth_prob, "depth_prob"), _chk(feat_cl, "feat_cl"), _chk(geom, "geom")
+    BN, D, fH, fW = depth_prob.shape
+    C = feat_cl.shape[-1]
+    X, Y, Z = grid
+    P = B * N * D * fH * fW
+    assert geom.numel() == 3 * P
+    ws = _workspace(P, B, X, Y, Z, geom.device)
+    out = torch.empty((B, X, Y, Z, C), dtype=torch.float32, device=geom.device)
+    f = [float(v) for v in (*dx, *bx, *nx)]
+    check(lib().occ_lift_splat(_ptr(depth_prob), _ptr(feat_cl), _ptr(geom), _ptr(out), B, N, D, fH * fW, C, *f, X, Y,
+                               Z, _ptr(ws.buf), ws.nbytes, 0, _stream()), "occ_lift_splat")
+    LAUNCH_COUNT[0] += 6
+    return (out, ws) if return_workspace else out
+
+
+def voxel_pool_geom(feats, geom, B, dx, bx, nx, grid, return_workspace=False):
+    """Materialised-volume voxel pooling: feats (P,C), geom (P,3) -> (B,X,Y,Z,C)."""
+    _chk(feats, "feats"), _chk(geom, "geom")
+    P_, C = feats.shape
+    X, Y, Z = grid
+    ws = _workspace(P_, B, X, Y, Z, feats.device)
+    out = torch.empty((B, X, Y, Z, C), dtype=torch.float32, device=feats.device)
+    f = [float(v) for v in (*dx, *bx, *nx)]
+    check(lib().occ_voxel_pool_geom(_ptr(feats), _ptr(geom), _ptr(out), B, P_ // B, C, *f, X, Y, Z, _ptr(ws.buf),
+                                    ws.nbytes, _stream()), "occ_voxel_pool_geom")
+    LAUNCH_COUNT[0] += 6
+    return (out, ws) if return_workspace else out
+
+
+def bev_pool_channel_last(feats, coords, B, X, Y, Z, return_workspace=False):
+    _chk(feats, "feats"), _chk(coords, "coords", torch.int64)
+    n, C = feats.shape
+    ws = _workspace(max(n, 1), B, X, Y, Z, feats.device)
+    out = torch.empty((B, X, Y, Z, C), dtype=torch.float32, device=feats.device)
+    check(lib().occ_bev_pool(_ptr(feats), _ptr(coords), _ptr(out), n, C, B, X, Y, Z, _ptr(ws.buf), ws.nbytes,
+                             _stream()), "occ_bev_pool")
+    LAUNCH_COUNT[0] += 6
+    return (out, ws) if return_workspace else out
+
+
+# ----------------------------------------------------------------------------------------------- GEMM / conv
+def gemm(a, w, bias=None, residual=None, act=0, round_out=False, out=None):
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual).  a, w should already be tf32-rounded."""
+    _chk(a, "a"), _chk(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    else:
+        _chk(out, "out")
+    if bias is not None:
+        _chk(bias, "bias")
+    if residual is not None:
+        _chk(residual, "residual")
+        assert residual.shape == (M, N)
+    check(lib().occ_gemm_tf32(_ptr(a), _ptr(w), _ptr(out), M, N, K, _ptr(bias), _ptr(residual), act, int(round_out),
+                              None, 0, 0, _stream()), "occ_gemm_tf32")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+def repack_conv_weight(w):
+    """(Cout, Cin, kx, ky[, kz]) -> (Cout, taps*Cin) tap-major [(kx*KY + ky)*KZ + kz][cin], tf32-rounded."""
+    if w.dim() == 4:
+        w = w.unsqueeze(-1)
+    Cout, Cin, KX, KY, KZ = w.shape
+    w2 = w.permute(0, 2, 3, 4, 1).reshape(Cout, KX * KY * KZ * Cin).contiguous().clone()
+    return round_tf32_(w2), (KX, KY, KZ)
+
+
+def conv(x_cl, w2, ksize, stride=1, dil=1, bias=None, residual=None, act=0, round_out=False, gn_stats=None, cpg=0):
+    """x_cl (B,X,Y,Z,Cin) channel-last; w2 from repack_conv_weight; returns (B,Xo,Yo,Zo,Cout) channel-last raw
+    output.  gn_stats: zero-initialised double tensor (B, groups, 2) receiving (sum, sumsq)."""
+    _chk(x_cl, "x_cl"), _chk(w2, "w2")
+    B, X, Y, Z, Cin = x_cl.shape
+    KX, KY, KZ = ksize
+    Cout = w2.shape[0]
+    assert w2.shape[1] == KX * KY * KZ * Cin
+
+    def osz(n, k):
+        p = dil * (k - 1) // 2
+        return (n + 2 * p - dil * (k - 1) - 1) // stride + 1
+
+    Xo, Yo, Zo = osz(X, KX), osz(Y, KY), osz(Z, KZ)
+    out = torch.empty((B, Xo, Yo, Zo, Cout), dtype=torch.float32, device=x_cl.device)
+    if gn_stats is not None:
+        _chk(gn_stats, "gn_stats", torch.float64)
+    check(lib().occ_conv_tf32(_ptr(x_cl), _ptr(w2), _ptr(out), B, X, Y, Z, Cin, Cout, KX, KY, KZ, stride, dil,
+                              _ptr(bias), _ptr(residual), act, int(round_out), _ptr(gn_stats), cpg, _stream()),
+          "occ_conv_tf32")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- encoder glue
+def gn_relu_zmean_ln(y, stats, gn_w, gn_b, ln_w, ln_b, B, XY, Z, C, groups):
+    rows = B * XY * (Z + 1)
+    tok = torch.empty((rows, C), dtype=torch.float32, device=y.device)
+    tokn = torch.empty((rows, C), dtype=torch.float32, device=y.device)
+    check(lib().occ_gn_relu_zmean_ln(_ptr(y), _ptr(stats), _ptr(gn_w), _ptr(gn_b), _ptr(ln_w), _ptr(ln_b), _ptr(tok),
+                                     _ptr(tokn), B, XY, Z, C, groups, _stream()), "occ_gn_relu_zmean_ln")
+    LAUNCH_COUNT[0] += 1
+    return tok, tokn
+
+
+def layernorm(x, w, b, round_out=False):
+    _chk(x, "x")
+    rows, C = x.shape
+    out = torch.empty_like(x)
+    check(lib().occ_layernorm(_ptr(x), _ptr(w), _ptr(b), _ptr(out), rows, C, int(round_out), _stream()), "occ_layernorm")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+def gn_apply(x, stats, w, b, rows_per_batch, groups, residual=None, out=None, out_off=0, relu=True, round_out=False):
+    _chk(x, "x")
+    rows, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    ldo = out.shape[1]
+    check(lib().occ_gn_apply(_ptr(x), _ptr(stats), _ptr(w), _ptr(b), _ptr(residual), _ptr(out), rows, rows_per_batch, C,
+                             groups, ldo, out_off, int(relu), int(round_out), _stream()), "occ_gn_apply")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+def aspp_gap_branch(x, wconv, gw, gb, cat, B, rows_per_batch, groups, out_off):
+    ch = x.shape[1]
+    sums = torch.empty((B, ch), dtype=torch.float64, device=x.device)
+    check(lib().occ_aspp_gap_branch(_ptr(x), _ptr(sums), _ptr(wconv), _ptr(gw), _ptr(gb), _ptr(cat), B, rows_per_batch,
+                                    ch, groups, cat.shape[1], out_off, _stream()), "occ_aspp_gap_branch")
+    LAUNCH_COUNT[0] += 3
+    return cat
+
+
+def dualpath_fuse(x, bev, cw, cbias, identity, B, XY, Z, C, id_stats=None, id_w=None, id_b=None, groups=0):
+    out = torch.empty((B * XY * Z, C), dtype=torch.float32, device=x.device)
+    check(lib().occ_dualpath_fuse(_ptr(x), _ptr(bev), _ptr(cw), float(cbias), _ptr(identity), _ptr(id_stats), _ptr(id_w),
+                                  _ptr(id_b), groups, _ptr(out), B, XY, Z, C, _stream()), "occ_dualpath_fuse")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+def window_attention(qkv, qkv_bias, bias_dense, B, X, Y, Z, C, heads, shift):
+    _chk(qkv, "qkv")
+    rows = B * X * Y * (Z + 1)
+    assert qkv.shape == (rows, 3 * C)
+    out = torch.empty((rows, C), dtype=torch.float32, device=qkv.device)
+    check(lib().occ_window_attention(_ptr(qkv), _ptr(qkv_bias), _ptr(bias_dense), _ptr(out), B, X, Y, Z, C, heads,
+                                     int(shift), _stream()), "occ_window_attention")
+    LAUNCH_COUNT[0] += 1
+    return out

@@ -1,0 +1,19 @@
+#!/bin/bash
+# One gpurun call = several independent stages, each under its own timeout, logs into gpurun_out/.
+# usage: scripts/gpu_session.sh stage1 stage2 ...   (stages: gemm pool encoder head all bench micro ncu)
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+for s in "$@"; do
+  case $s in
+    gemm)    timeout 300 python -m pytest tests/test_gpu_gemm.py -q -m gpu -x > gpurun_out/t_gemm.log 2>&1; echo "gemm rc=$?" ;;
+    gemmall) timeout 400 python -m pytest tests/test_gpu_gemm.py -q -m gpu > gpurun_out/t_gemm.log 2>&1; echo "gemm rc=$?" ;;
+    pool)    timeout 300 python -m pytest tests/test_gpu_voxel_pool.py -q -m gpu -s > gpurun_out/t_pool.log 2>&1; echo "pool rc=$?" ;;
+    encoder) timeout 600 python -m pytest tests/test_gpu_encoder.py -q -m gpu > gpurun_out/t_encoder.log 2>&1; echo "encoder rc=$?" ;;
+    head)    timeout 600 python -m pytest tests/test_gpu_head.py -q -m gpu > gpurun_out/t_head.log 2>&1; echo "head rc=$?" ;;
+    all)     timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/t_all.log 2>&1; echo "all rc=$?" ;;
+    micro)   timeout 600 python scripts/microbench.py > gpurun_out/micro.log 2>&1; echo "micro rc=$?" ;;
+    bench)   timeout 900 python bench.py > gpurun_out/bench.log 2>&1; echo "bench rc=$?" ;;
+    *) echo "unknown stage $s" ;;
+  esac
+done
+tail -n 25 gpurun_out/t_*.log gpurun_out/micro.log 2>/dev/null | tail -n 120

@@ -1,0 +1,70 @@
+"""Dual-path encoder (CUDA, through the C ABI) vs the oracle port and the reference-generated goldens.
+Tolerance = north_star's 1e-3 relative fp32 (tests/util.py)."""
+import pytest
+import torch
+
+from oracle import port
+from occformer_b200 import synth
+from util import assert_close, golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _block(cuda, cin, c, stride, shift, sd):
+    from occformer_b200.encoder import DualpathTransformerBlock
+    blk = DualpathTransformerBlock(cin, c, stride=stride, norm_cfg=dict(type="GN", num_groups=32, requires_grad=True),
+                                   layer_index=1 if shift else 0)
+    missing, unexpected = blk.load_state_dict(sd, strict=True)
+    return blk.to(cuda).eval()
+
+
+GOLD = [("block_c128_s1_plain", 128, 128, 1, False, (15, 10, 4), 1),
+        ("block_c256_s2_shift", 128, 256, 2, True, (15, 10, 4), 2),
+        ("block_c128_s1_shift", 128, 128, 1, True, (9, 16, 2), 3)]
+
+
+@pytest.mark.parametrize("case", GOLD)
+def test_block_vs_reference_golden(cuda, case):
+    name, cin, c, stride, shift, grid, seed = case
+    g = torch.Generator().manual_seed(seed)
+    sd = port.make_block_state(cin, c, stride, g)
+    blk = _block(cuda, cin, c, stride, shift, sd)
+    x = synth.encoder_input(1, cin, *grid, seed=seed + 100)
+    out = blk(x.to(cuda))
+    gold = torch.from_numpy(golden(name + ".npz")["out"])
+    ref = port.dualpath_block(x, sd, "", stride, shift)
+    assert rel_err(ref, gold) < 1e-5, "oracle port drifted from the reference golden"
+    assert out.shape == gold.shape
+    assert_close(out, gold, what=f"{name} vs reference golden")
+
+
+@pytest.mark.parametrize("cin,c,stride,shift,grid,B", [(128, 128, 1, False, (50, 50, 8), 1),
+                                                       (128, 128, 1, True, (50, 50, 8), 2),
+                                                       (128, 256, 2, True, (50, 50, 8), 1),
+                                                       (256, 512, 2, False, (25, 25, 4), 1),
+                                                       (512, 1024, 2, True, (13, 13, 2), 1)])
+def test_block_vs_oracle(cuda, cin, c, stride, shift, grid, B):
+    g = torch.Generator().manual_seed(c + stride)
+    sd = port.make_block_state(cin, c, stride, g)
+    blk = _block(cuda, cin, c, stride, shift, sd)
+    x = synth.encoder_input(B, cin, *grid, seed=7)
+    out = blk(x.to(cuda))
+    ref = port.dualpath_block(x, sd, "", stride, shift)
+    assert_close(out, ref, what=f"block {cin}->{c} s{stride} shift={shift} grid={grid}")
+
+
+def test_encoder_pr1(cuda):
+    """BASELINE.json configs[0] topology: 50x50x8 voxels, 2-layer dual-path (block_numbers=[1,1])."""
+    from occformer_b200.encoder import OccupancyEncoder
+    cfg = dict(in_channels=128, num_stage=2, block_numbers=[1, 1], block_inplanes=[128, 256], block_strides=[1, 2],
+               out_indices=(0, 1), norm_cfg=dict(type="GN", num_groups=32, requires_grad=True), with_cp=True)
+    sd = port.make_encoder_state(128, [128, 256], [1, 1], [1, 2], seed=0)
+    enc = OccupancyEncoder(**cfg)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(cuda).eval()
+    x = synth.encoder_input(1, 128, 50, 50, 8, seed=0)
+    outs = enc(x.to(cuda))
+    refs = port.occupancy_encoder(x, sd, [1, 1], [1, 2], (0, 1))
+    assert len(outs) == len(refs) == 2
+    for i, (o, r) in enumerate(zip(outs, refs)):
+        assert_close(o, r, what=f"encoder out[{i}]")

@@ -1,0 +1,85 @@
+"""tcgen05 TF32 GEMM / implicit-GEMM conv vs fp64 torch on tf32-rounded operands (kernel correctness is
+isolated from tf32 operand rounding: with pre-rounded inputs the only differences are fp32 accumulation order)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import assert_close, round_tf32
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, g, scale=1.0):
+    return round_tf32(torch.randn(*shape, generator=g) * scale)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 384, 128), (1000, 100, 192), (129, 18, 96), (128, 32, 32), (4096, 256, 256),
+                                   (777, 1024, 512), (100, 1536, 192), (100, 192, 1536), (5000, 64, 160)])
+def test_gemm_plain(cuda, M, N, K):
+    from occformer_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a, w = _mk((M, K), g), _mk((N, K), g, K ** -0.5)
+    out = ops.gemm(a.to(cuda), w.to(cuda))
+    ref = a.double() @ w.double().t()
+    assert_close(out, ref, 2e-5, f"gemm {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_epilogue(cuda, act):
+    from occformer_b200 import ops
+    g = torch.Generator().manual_seed(act)
+    M, N, K = 1500, 384, 128
+    a, w = _mk((M, K), g), _mk((N, K), g, K ** -0.5)
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    out = ops.gemm(a.to(cuda), w.to(cuda), bias=bias.to(cuda), residual=res.to(cuda), act=act)
+    ref = a.double() @ w.double().t() + bias.double() + res.double()
+    ref = [lambda x: x, F.relu, F.gelu][act](ref)
+    assert_close(out, ref, 2e-5, f"gemm epilogue act={act}")
+    out_r = ops.gemm(a.to(cuda), w.to(cuda), bias=bias.to(cuda), round_out=True)
+    ref_r = round_tf32((a.double() @ w.double().t() + bias.double()).float())
+    assert_close(out_r, ref_r, 1e-3, "round_out")
+    assert int((out_r.view(torch.int32) & 0x1FFF).abs().max()) == 0, "round_out must clear the low 13 mantissa bits"
+
+
+CONV_CASES = [
+    # B, X, Y, Z, Cin, Cout, k, stride, dil
+    (2, 15, 10, 4, 32, 64, (3, 3, 3), 1, 1),
+    (1, 15, 10, 4, 64, 128, (3, 3, 3), 2, 1),
+    (2, 9, 16, 2, 32, 32, (1, 1, 1), 2, 1),
+    (1, 50, 50, 8, 128, 128, (3, 3, 3), 1, 1),
+    (2, 25, 25, 1, 32, 32, (3, 3, 1), 1, 6),
+    (1, 30, 20, 1, 64, 64, (3, 3, 1), 1, 18),
+    (1, 7, 5, 3, 32, 256, (3, 3, 3), 2, 1),
+    (1, 13, 13, 1, 160, 32, (1, 1, 1), 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv(cuda, case):
+    from occformer_b200 import ops
+    B, X, Y, Z, Cin, Cout, k, stride, dil = case
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x = _mk((B, Cin, X, Y, Z), g)
+    w = _mk((Cout, Cin) + k, g, (Cin * k[0] * k[1] * k[2]) ** -0.5)
+    pad = tuple(dil * (kk - 1) // 2 for kk in k)
+    ref = F.conv3d(x.double(), w.double(), None, stride=stride, padding=pad, dilation=dil)
+    w2, ks = ops.repack_conv_weight(w.to(cuda))
+    groups = 16 if Cout == 32 else 32
+    stats = torch.zeros((B, groups, 2), dtype=torch.float64, device=cuda)
+    x_cl = x.to(cuda).permute(0, 2, 3, 4, 1).contiguous()
+    out = ops.conv(x_cl, w2, ks, stride=stride, dil=dil, gn_stats=stats, cpg=Cout // groups)
+    assert_close(out.permute(0, 4, 1, 2, 3), ref, 2e-5, f"conv {case}")
+    # GroupNorm statistics accumulated in the epilogue: (sum, sumsq) per (batch, group)
+    r = ref.reshape(B, groups, -1)
+    ref_stats = torch.stack((r.sum(-1), (r * r).sum(-1)), dim=-1)
+    assert_close(stats, ref_stats, 1e-5, f"conv gn_stats {case}")
+
+
+def test_gemm_rejects_bad_args(cuda):
+    from occformer_b200 import ops
+    a = torch.zeros(8, 30, device=cuda)  # K % 4 != 0
+    w = torch.zeros(16, 30, device=cuda)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, w)
+    with pytest.raises(RuntimeError):
+        ops.gemm(torch.zeros(8, 32), torch.zeros(16, 32))  # CPU tensors: no fallback

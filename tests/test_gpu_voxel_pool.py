@@ -1,0 +1,124 @@
+"""Voxel pooling (CUDA, through the C ABI) vs the oracle port and the reference-generated golden fixture.
+Bit-exact on the integer bookkeeping (voxel ids, kept mask, interval lengths); <= 1e-5 relative on the sums
+(summation order inside a voxel is unspecified in the reference as well: bev_pool.py:92 argsort is unstable)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from occformer_b200 import synth
+from util import assert_close, golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(grid_name, cams, input_size, B, N, C, seed):
+    gc = synth.grid_config(grid_name)
+    frustum = port.create_frustum(input_size, 16, gc["dbound"])
+    geom = port.get_geometry(frustum, **cams)
+    dx, bx, nx = port.gen_dx_bx(gc["xbound"], gc["ybound"], gc["zbound"])
+    D, fH, fW = frustum.shape[:3]
+    dd, feat = synth.lift_inputs(B, N, D, fH, fW, C, seed=seed)
+    return gc, geom, dx, bx, nx, dd, feat
+
+
+def _check_bookkeeping(ws, gf, kept, B, X, Y, Z):
+    """vox_id / kept mask / per-voxel counts must equal the reference's index math exactly."""
+    vox = ws.vox_id.cpu().long()
+    ref_lin = ((gf[:, 3] * X + gf[:, 0]) * Y + gf[:, 1]) * Z + gf[:, 2]
+    ref_vox = torch.where(kept, ref_lin, torch.full_like(ref_lin, -1))
+    assert torch.equal(vox, ref_vox), f"voxel ids differ at {(vox != ref_vox).sum()} points"
+    starts = ws.starts.cpu().long()
+    counts = starts[1:] - starts[:-1]
+    ref_counts = torch.bincount(ref_lin[kept], minlength=B * X * Y * Z)
+    assert torch.equal(counts, ref_counts)
+    assert int(starts[-1]) == int(kept.sum())
+    # interval bookkeeping in the reference's own rank order (bev_pool.py:86-93 / QuickCumsumCuda :40-45)
+    uniq, lens = port.bev_pool_bookkeeping(gf[kept], B, Z, X, Y)
+    nzv = torch.nonzero(counts).flatten()
+    b = nzv // (X * Y * Z); r = nzv % (X * Y * Z); x = r // (Y * Z); y = (r // Z) % Y; z = r % Z
+    my_ranks = x * (Y * Z * B) + y * (Z * B) + z * B + b
+    order = my_ranks.argsort()
+    assert torch.equal(my_ranks[order], uniq) and torch.equal(counts[nzv][order], lens)
+    # every kept point appears exactly once in the sorted order array
+    order_ids = ws.order.cpu().long()[: int(starts[-1])]
+    assert torch.equal(order_ids.sort().values, torch.nonzero(kept).flatten())
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_lift_splat_pr1(cuda, B):
+    from occformer_b200.view_transformer import ViewTransformerLiftSplatShootVoxel
+    C = 32
+    gc, geom, dx, bx, nx, dd, feat = _setup("pr1", synth.pr1_camera(B), (128, 128), B, 1, C, seed=1)
+    vt = ViewTransformerLiftSplatShootVoxel(grid_config=gc, data_config={"input_size": (128, 128)}, numC_input=64,
+                                            numC_Trans=C).to(cuda)
+    assert torch.equal(vt.dx.cpu(), dx) and torch.equal(vt.bx.cpu(), bx) and torch.equal(vt.nx.cpu(), nx)
+    geom_gpu = vt.get_geometry(**{k: v.to(cuda) for k, v in synth.pr1_camera(B).items()})
+    assert_close(geom_gpu, geom, 1e-5, "get_geometry (GPU plumbing vs CPU)")
+    grid, prob = vt.lift_splat(dd.to(cuda), feat.to(cuda), geom.to(cuda), B, 1)
+    vol, prob_ref = port.lift(dd, feat, B, 1)
+    ref, gf, kept = port.voxel_pooling(geom, vol, dx, bx, nx)
+    assert_close(prob, prob_ref, 1e-5, "depth_prob")
+    assert_close(grid.permute(0, 4, 1, 2, 3), ref, 1e-5, "lift_splat grid")
+    from occformer_b200 import ops
+    X, Y, Z = vt.grid_size()
+    ws = ops._workspace(geom.numel() // 3, B, X, Y, Z, cuda)
+    torch.cuda.synchronize()
+    _check_bookkeeping(ws, gf, kept, B, X, Y, Z)
+    if B == 2:  # golden fixture generated from the REAL reference (oracle/gen_golden.py)
+        gd = golden("voxel_pool_pr1.npz")
+        assert np.array_equal(gd["geom"], geom.numpy())
+        dense = torch.zeros(tuple(gd["shape"]))
+        idx = torch.from_numpy(gd["nonzero_index"]).long()
+        dense[idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3]] = torch.from_numpy(gd["nonzero_rows"])
+        assert_close(grid, dense, 1e-5, "lift_splat vs reference golden")
+
+
+def test_voxel_pooling_materialised_and_bev_pool(cuda):
+    """reference-signature entry points: voxel_pooling(geom, volume) and bev_pool(feats, coords, B, D, H, W)."""
+    from occformer_b200.view_transformer import ViewTransformerLiftSplatShootVoxel, bev_pool
+    B, C = 2, 32
+    gc, geom, dx, bx, nx, dd, feat = _setup("pr1", synth.pr1_camera(B), (128, 128), B, 1, C, seed=3)
+    vt = ViewTransformerLiftSplatShootVoxel(grid_config=gc, data_config={"input_size": (128, 128)}, numC_input=64,
+                                            numC_Trans=C).to(cuda)
+    vol, _ = port.lift(dd, feat, B, 1)
+    ref, gf, kept = port.voxel_pooling(geom, vol, dx, bx, nx)
+    out = vt.voxel_pooling(geom.to(cuda), vol.to(cuda))
+    assert out.shape == ref.shape
+    assert_close(out, ref, 1e-5, "voxel_pooling(geom, volume)")
+    # bev_pool drop-in, called exactly like the reference does (nx entries are 0-d float tensors)
+    x = vol.reshape(-1, C)[kept].to(cuda)
+    coords = gf[kept].to(cuda)
+    o2 = bev_pool(x, coords, B, vt.nx[2], vt.nx[0], vt.nx[1])
+    ref2 = port.bev_pool(vol.reshape(-1, C)[kept], gf[kept], B, nx[2], nx[0], nx[1])
+    assert o2.shape == ref2.shape
+    assert_close(o2, ref2, 1e-5, "bev_pool")
+    # empty input: all zeros
+    o3 = bev_pool(torch.zeros(0, C, device=cuda), torch.zeros(0, 4, dtype=torch.long, device=cuda), 1, 2, 3, 4)
+    assert o3.shape == (1, C, 2, 3, 4) and float(o3.abs().max()) == 0.0
+
+
+def test_lift_splat_nusc_properties(cuda):
+    """Full-size nuScenes geometry (6 cams, 200x200x16): size-independent properties -- mass conservation
+    (sum over the grid == sum over kept points), per-voxel counts == bincount of the oracle index math."""
+    from occformer_b200.view_transformer import ViewTransformerLiftSplatShootVoxel
+    from occformer_b200 import ops
+    B, N, C = 1, 6, 128
+    gc, geom, dx, bx, nx, dd, feat = _setup("nusc_200", synth.nusc_cameras(B, N), (256, 704), B, N, C, seed=5)
+    vt = ViewTransformerLiftSplatShootVoxel(grid_config=gc, data_config={"input_size": (256, 704)}, numC_Trans=C).to(cuda)
+    grid, prob = vt.lift_splat(dd.to(cuda), feat.to(cuda), geom.to(cuda), B, N)
+    idx = port.voxel_index(geom, dx, bx).view(-1, 3)
+    gf = torch.cat((idx, torch.zeros(idx.shape[0], 1, dtype=torch.long)), 1)
+    kept = port.kept_mask(gf, nx)
+    X, Y, Z = vt.grid_size()
+    ws = ops._workspace(idx.shape[0], B, X, Y, Z, cuda)
+    torch.cuda.synchronize()
+    _check_bookkeeping(ws, gf, kept, B, X, Y, Z)
+    # mass conservation per channel: sum_v out[v,c] == sum_{kept p} depth[p] * feat[pix(p), c]
+    prob_ref = dd.softmax(1)
+    D, HW = prob_ref.shape[1], prob_ref.shape[2] * prob_ref.shape[3]
+    w = (prob_ref.reshape(N, D, HW) * kept.view(N, D, HW)).sum(1)                   # (N, HW)
+    expect = torch.einsum("np,ncp->c", w.double(), feat.reshape(N, C, HW).double())
+    got = grid.double().sum(dim=(0, 1, 2, 3)).cpu()
+    assert_close(got, expect, 1e-5, "mass conservation")
+    print(f"nusc_200: n_pts={idx.shape[0]} n_kept={int(kept.sum())} nonempty={int((ws.starts[1:] - ws.starts[:-1]).ne(0).sum())}")
