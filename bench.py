@@ -1,0 +1,413 @@
+"""bench.py -- samples/s of the OccFormer hot path (6-cam 256x704 -> 200x200x16 voxel forward) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" = one pass of the hot path (LSS lift-splat voxel pooling -> OccupancyEncoder ->
+Mask2FormerNuscOccHead.simple_test) over one batch of synthetic samples per GPU, BASELINE.json configs[2]
+shapes (nuScenes R50: 6 cameras, 16x44 feature maps, D=112, C=128 -> 200x200x16 voxels, 100 queries, 17 classes).
+Data parallel over samples, no collective on the data path (weak scaling: fixed batch per GPU).
+
+One JSON line on stdout (rank 0).  `value` = inputs resident in HBM, CUDA-event timed, L2 flushed between steps;
+`e2e` = the same metric through the public module API with pinned HOST inputs copied H2D and the class-score
+volume copied D2H inside the timed region; `roofline` = the dominant kernel family, timed live with CUDA events;
+`cpu_baseline` = the CPU oracle (port of the reference's PyTorch path) on the host cores, bounded sample.
+`--impl reference` times that CPU path alone (the reference itself is Python under mmcv and cannot travel to the GPU
+box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "samples/sec (6-cam->200x200x16 voxel fwd)"
+UNIT = "samples/s"
+WORKLOAD = "nusc_r50_6cam_256x704_to_200x200x16"
+N_CAMS, INPUT_SIZE, DOWNSAMPLE, C_TRANS = 6, (256, 704), 16, 128
+PLANES, NUMS, STRIDES = [128, 256, 512, 1024], [2, 2, 2, 2], [1, 2, 2, 2]
+EMBED, QUERIES, CLASSES, DEC_LAYERS, HEADS = 192, 100, 17, 9, 6
+GRID = "nusc_200"
+PC_RANGE = [-40.0, -40.0, -1.0, 40.0, 40.0, 5.4]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in a side thread during the timed region)
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        # median over the busy samples (upper half): the sampler also sees the idle gaps between steps
+        busy = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# workload construction
+# ----------------------------------------------------------------------------------------------------------------------
+def head_available():
+    try:
+        import occformer_b200.head  # noqa: F401
+        return True
+    except ImportError:
+        return False
+
+
+def build_b200(dev, batch):
+    """Modules of the B200 path with deterministic synthetic weights (generated by the oracle's state-dict helper:
+    weights are INPUT DATA here, produced once before any timing; no oracle arithmetic is on the measured path)."""
+    from occformer_b200 import synth
+    from occformer_b200.encoder import OccupancyEncoder
+    from occformer_b200.view_transformer import ViewTransformerLiftSplatShootVoxel
+    from oracle import port  # synthetic state_dict generator only
+    gc = synth.grid_config(GRID)
+    vt = ViewTransformerLiftSplatShootVoxel(grid_config=gc, data_config={"input_size": INPUT_SIZE}, numC_input=64,
+                                            numC_Trans=C_TRANS, downsample=DOWNSAMPLE).to(dev)
+    enc = OccupancyEncoder(in_channels=C_TRANS, num_stage=4, block_numbers=NUMS, block_inplanes=PLANES,
+                           block_strides=STRIDES, out_indices=(0, 1, 2, 3), norm_cfg=dict(type="GN", num_groups=32))
+    enc.load_state_dict(port.make_encoder_state(C_TRANS, PLANES, NUMS, STRIDES, seed=0), strict=True)
+    enc = enc.to(dev).eval()
+    head = None
+    if head_available():
+        from occformer_b200.head import build_nusc_head
+        head = build_nusc_head(EMBED, QUERIES, CLASSES, DEC_LAYERS, HEADS, PC_RANGE)
+        head.load_state_dict(port.make_head_state(EMBED, QUERIES, CLASSES, DEC_LAYERS, 3, seed=1), strict=False)
+        head = head.to(dev).eval()
+    return vt, enc, head
+
+
+def host_inputs(batch, seed):
+    """Pinned host tensors of one step: post-DepthNet maps (B*N, D+C, fH, fW) + camera matrices + synthetic neck
+    outputs for the head (the 3-D deformable-attention neck between encoder and head is outside the hot path,
+    SURVEY.md 8(f)1; both arms consume the same synthetic 192-channel pyramid)."""
+    from occformer_b200 import synth
+    fH, fW = INPUT_SIZE[0] // DOWNSAMPLE, INPUT_SIZE[1] // DOWNSAMPLE
+    D = 112
+    dd, feat = synth.lift_inputs(batch, N_CAMS, D, fH, fW, C_TRANS, seed=seed)
+    x = torch.cat([dd, feat], dim=1).contiguous()
+    cams = synth.nusc_cameras(batch, N_CAMS, INPUT_SIZE)
+    out = {"x": x, **cams}
+    return {k: (v.pin_memory() if torch.cuda.is_available() else v) for k, v in out.items()}
+
+
+def neck_features(batch, dev, seed):
+    """Synthetic multi-scale neck outputs, channel-last memory viewed in the reference layout (B,192,X,Y,Z)."""
+    g = torch.Generator().manual_seed(seed)
+    sizes = [(200, 200, 16), (100, 100, 8), (50, 50, 4), (25, 25, 2)]
+    feats = []
+    for i, s in enumerate(sizes):
+        t = torch.randn(batch, *s, EMBED, generator=g) * (0.5 if i == 0 else 1.0)
+        feats.append(t.to(dev).permute(0, 4, 1, 2, 3))
+    return feats
+
+
+class Pipeline:
+    """The public-API call sequence of one step on device tensors."""
+
+    def __init__(self, dev, batch):
+        self.dev, self.batch = dev, batch
+        self.vt, self.enc, self.head = build_b200(dev, batch)
+        self.neck = neck_features(batch, dev, seed=5) if self.head is not None else None
+        self.D = self.vt.D
+
+    def stages(self):
+        return ["lift_splat", "occupancy_encoder"] + (["mask2former_head"] if self.head is not None else [])
+
+    @torch.no_grad()
+    def run(self, inp):
+        B, N = self.batch, N_CAMS
+        x = inp["x"]
+        geom = self.vt.get_geometry(inp["rots"], inp["trans"], inp["intrins"], inp["post_rots"], inp["post_trans"],
+                                    inp["bda"])
+        grid, _ = self.vt.lift_splat(x[:, :self.D], x[:, self.D:], geom, B, N)
+        feats = self.enc.forward_cl(grid)
+        if self.head is None:
+            return feats[-1]
+        # the encoder pyramid feeds the (out-of-scope) neck; the head consumes the synthetic neck pyramid
+        res = self.head.simple_test(self.neck, [dict(occ_size=[200, 200, 16], pc_range=PC_RANGE)] * B)
+        return res["output_voxels"][0]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline / --impl reference)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_sample(include_head, threads):
+    """One sample of the same workload through the CPU oracle (port of the reference's PyTorch path)."""
+    from occformer_b200 import synth
+    from oracle import port
+    torch.set_num_threads(threads)
+    gc = synth.grid_config(GRID)
+    frustum = port.create_frustum(INPUT_SIZE, DOWNSAMPLE, gc["dbound"])
+    cams = synth.nusc_cameras(1, N_CAMS, INPUT_SIZE)
+    D, fH, fW = frustum.shape[:3]
+    dd, feat = synth.lift_inputs(1, N_CAMS, D, fH, fW, C_TRANS, seed=0)
+    dx, bx, nx = port.gen_dx_bx(gc["xbound"], gc["ybound"], gc["zbound"])
+    sd_e = port.make_encoder_state(C_TRANS, PLANES, NUMS, STRIDES, seed=0)
+    sd_h = port.make_head_state(EMBED, QUERIES, CLASSES, DEC_LAYERS, 3, seed=1) if include_head else None
+    feats = None
+    if include_head:
+        from occformer_b200 import synth as s2
+        feats = s2.head_inputs(1, EMBED, [(200, 200, 16), (100, 100, 8), (50, 50, 4), (25, 25, 2)], seed=5)
+
+    def step():
+        with torch.no_grad():
+            geom = port.get_geometry(frustum, **cams)
+            vol, _ = port.lift(dd, feat, 1, N_CAMS)
+            grid, _, _ = port.voxel_pooling(geom, vol, dx, bx, nx)
+            outs = port.occupancy_encoder(grid, sd_e, NUMS, STRIDES, (0, 1, 2, 3))
+            if include_head:
+                res = port.head_simple_test(feats, sd_h, HEADS, DEC_LAYERS, (200, 200, 16))
+                return res["output_voxels"][0]
+            return outs[-1]
+
+    return step
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    include_head = head_available()
+    step = cpu_sample(include_head, threads)
+    budget_s = 150.0
+    t0 = time.perf_counter()
+    step()  # one warm-up (also the cost estimate)
+    est = time.perf_counter() - t0
+    k = max(1, min(args.steps, int(budget_s / max(est, 1e-3))))
+    ts = []
+    for _ in range(k):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    per = sum(ts) / len(ts)
+    val = 1.0 / per
+    sample = (f"1 sample/step of {WORKLOAD} (lift+voxel_pooling, OccupancyEncoder{', head.simple_test' if include_head else ''}) "
+              f"through the CPU oracle port, fp32, {threads} threads; 1 warm-up + {k} timed steps (requested {args.steps})")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
+            "warmup": 1, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": 1, "stages": ["lift_splat", "occupancy_encoder"] +
+                       (["mask2former_head"] if include_head else [])},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# B200 leg
+# ----------------------------------------------------------------------------------------------------------------------
+def time_kernel_family(pipe, dev, peak):
+    """Roofline of the dominant kernel family, timed live (CUDA events on the current stream, L2 flushed)."""
+    from occformer_b200 import ops
+    B = pipe.batch
+    X, Y, Z, C = 200, 200, 16, 128
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    x = torch.randn(B, X, Y, Z, C, device=dev)
+    w2, ks = ops.repack_conv_weight(torch.randn(C, C, 3, 3, 3, device=dev) * 0.02)
+    stats = torch.zeros(B, 32, 2, dtype=torch.float64, device=dev)
+    ts = []
+    for i in range(8):
+        flush.fill_(float(i))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.conv(x, w2, ks, gn_stats=stats, cpg=4)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(a.elapsed_time(b))
+    ms = sum(ts) / len(ts)
+    flops = 2.0 * 27 * C * C * B * X * Y * Z
+    achieved = flops / (ms * 1e-3) / 1e12
+    # TF32 dense peak = half the bf16 peak on this part (B200_PROFILING.md table: 1.1 vs 2.25 PF nominal)
+    pk = peak["tf"] / 2.0
+    return {"kernel": "gemm_tf32_kernel<conv3d 3x3x3, C=128, 200x200x16>", "bound": "tensor", "achieved": achieved,
+            "peak": pk, "unit": "TFLOP/s", "frac": achieved / pk, "traffic": None,
+            "note": f"algorithmic FLOPs 2*27*Cin*Cout*V = {flops / 1e9:.1f} GF per launch / {ms:.3f} ms (CUDA events); peak = "
+                    f"tf32 dense = measured bf16 burst / 2, {peak['src']}"}
+
+
+def run_b200(args, rank, world, local_rank):
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    from occformer_b200 import ops
+    peak = peaks()
+    pipe = Pipeline(dev, args.batch)
+    host = host_inputs(args.batch, seed=0)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- value: inputs resident in HBM
+    for _ in range(args.warmup):
+        pipe.run(resident)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCH_COUNT[0]
+    evs = []
+    for i in range(args.steps):
+        flush.fill_(float(i))  # L2 flush between timed iterations (untimed)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        pipe.run(resident)
+        b.record()
+        evs.append((a, b))
+    barrier()
+    launches = ops.LAUNCH_COUNT[0] - launches0
+    t_dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------------------------------------------------------- e2e: host buffers in, host result out
+    out_host = None
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    e2e_steps = args.steps
+    for _ in range(2):
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        res = pipe.run(inp)
+        if out_host is None:
+            out_host = torch.empty(res.shape, dtype=res.dtype).pin_memory()
+        out_host.copy_(res, non_blocking=True)
+    barrier()
+    d2h = out_host.numel() * out_host.element_size()
+    t0 = time.perf_counter()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e2e_steps):
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        res = pipe.run(inp)
+        out_host.copy_(res, non_blocking=True)
+    b.record()
+    barrier()
+    t_e2e_ms = a.elapsed_time(b)
+    _ = time.perf_counter() - t0
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([t_dev_ms, t_e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev_ms, t_e2e_ms = float(t[0]), float(t[1])
+    total_samples = args.batch * world * args.steps
+    value = total_samples / (t_dev_ms * 1e-3)
+    e2e_val = args.batch * world * e2e_steps / (t_e2e_ms * 1e-3)
+
+    if rank != 0:
+        return
+    roof = time_kernel_family(pipe, dev, peak)
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        step = cpu_sample(pipe.head is not None, threads)
+        t0 = time.perf_counter()
+        step()
+        per = time.perf_counter() - t0
+        cpu = {"value": 1.0 / per, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"1 sample of {WORKLOAD} ({', '.join(pipe.stages())}) through the CPU oracle port (torch fp32, "
+                         f"{threads} threads), single cold run = {per:.1f} s"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 operands / f32 accumulate+storage", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+                       "parallelism": f"dp{world}", "stages": pipe.stages(),
+                       "l2": "192 MiB flush write between timed steps; activations (328 MB/tensor) exceed L2",
+                       "neck": "MSDeformAttnPixelDecoder3D is outside the hot path (SURVEY 8(f)1): head consumes a synthetic pyramid"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": t_e2e_ms / e2e_steps},
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1, help="samples per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device; there is no CPU fallback for the hot path")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

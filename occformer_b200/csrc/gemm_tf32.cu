@@ -57,6 +57,21 @@ __device__ __forceinline__ void accum_stats(const float (&v)[32], float (&sv)[32
   }
 }
 
+// Sum each of 32 per-lane values over the 32 lanes of the warp with 31 shuffles; afterwards lane L holds
+// the total of value index L in v[0].
+__device__ __forceinline__ void warp_butterfly32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = upper ? v[i + n / 2] : v[i];
+      const float send = upper ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(256, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -249,29 +264,36 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool full_chunk = (nc + 32 <= p.N);
         if (p.gn_stats != nullptr) {
           // per-group sum / sumsq of the raw conv output, butterfly-reduced over the 32 rows of the warp
-          float sv[32];
+          const int cpg = p.cpg;  // power of two in [1, 32]
+          if (cpg == 1) {
+            // one group per channel: 32 sums and 32 sums of squares -> two butterflies
+            float ss[32], sq[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sv[j] = 0.f;
-          const int cpg = p.cpg;  // power of two in [2, 32]
-          if (valid) {
-            if (cpg == 2) accum_stats<2>(v, sv);
-            else if (cpg == 4) accum_stats<4>(v, sv);
-            else if (cpg == 8) accum_stats<8>(v, sv);
-            else if (cpg == 16) accum_stats<16>(v, sv);
-            else accum_stats<32>(v, sv);
-          }
-#pragma unroll
-          for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < n / 2; ++i) {
-              const float keep = upper ? sv[i + n / 2] : sv[i];
-              const float send = upper ? sv[i] : sv[i + n / 2];
-              sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            for (int j = 0; j < 32; ++j) {
+              ss[j] = valid ? v[j] : 0.f;
+              sq[j] = valid ? v[j] * v[j] : 0.f;
             }
+            warp_butterfly32(ss, lane);
+            warp_butterfly32(sq, lane);
+            if (nc + lane < p.N) {
+              atomicAdd(&stat_acc[2 * (nc + lane)], (double)ss[0]);
+              atomicAdd(&stat_acc[2 * (nc + lane) + 1], (double)sq[0]);
+            }
+          } else {
+            float sv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sv[j] = 0.f;
+            if (valid) {
+              if (cpg == 2) accum_stats<2>(v, sv);
+              else if (cpg == 4) accum_stats<4>(v, sv);
+              else if (cpg == 8) accum_stats<8>(v, sv);
+              else if (cpg == 16) accum_stats<16>(v, sv);
+              else accum_stats<32>(v, sv);
+            }
+            warp_butterfly32(sv, lane);
+            // lane L now holds the warp total of value L (value = 2*local_group + {0: sum, 1: sumsq})
+            if (lane < 2 * (32 / cpg)) atomicAdd(&stat_acc[2 * (nc / cpg) + lane], (double)sv[0]);
           }
-          // lane L now holds the warp total of value L (value = 2*local_group + {0: sum, 1: sumsq})
-          if (lane < 2 * (32 / cpg)) atomicAdd(&stat_acc[2 * (nc / cpg) + lane], (double)sv[0]);
         }
         if (valid) {
           if (p.bias) {
@@ -397,7 +419,7 @@ extern "C" int occ_gemm_tf32(const float* A, const float* W, float* out, int M, 
   OCC_REQUIRE(K % 4 == 0);  // 16-byte row pitch for TMA
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   OCC_REQUIRE(act >= 0 && act <= 2);
-  if (gn_stats) OCC_REQUIRE(cpg >= 2 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && N % cpg == 0 && N / cpg <= 32 &&
+  if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && N % cpg == 0 && N / cpg <= 32 &&
                             rows_per_batch > 0 && rows_per_batch % BM == 0);
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.num_k_blocks = (K + BK - 1) / BK;
@@ -425,7 +447,7 @@ extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B,
   OCC_REQUIRE(stride == 1 || stride == 2);
   OCC_REQUIRE(dil >= 1 && act >= 0 && act <= 2);
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0);
-  if (gn_stats) OCC_REQUIRE(cpg >= 2 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && Cout % cpg == 0 && Cout / cpg <= 32);
+  if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && Cout % cpg == 0 && Cout / cpg <= 32);
   GemmParams p{};
   p.conv = 1;
   p.Cin = Cin; p.KX = KX; p.KY = KY; p.KZ = KZ; p.dil = dil; p.stride = stride;

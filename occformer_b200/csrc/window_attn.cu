@@ -22,6 +22,7 @@ constexpr int WS = 7;
 constexpr int WT = WS * WS;  // 49 tokens
 constexpr int HD = 32;       // head dim (multihead_base_channel, dualpath_block.py:32)
 constexpr int KV_LD = 36;    // smem row pitch (floats)
+constexpr int WARP_SMEM = 2 * WT * KV_LD + ((WT * WT + 3) / 4) * 4;  // floats per warp, 16-byte multiple
 
 struct WinGeom {
   int B, X, Y, Z, C, heads, shift;
@@ -56,7 +57,7 @@ __device__ __forceinline__ long long window_token_row(const WinGeom& g, int img,
 __global__ void __launch_bounds__(128)
 window_attn_simt_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
                         const float* __restrict__ bias_dense /*(heads,49,49)*/, float* __restrict__ out, WinGeom g) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   __shared__ long long s_row[WT];
   __shared__ int s_region[WT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,7 +73,7 @@ window_attn_simt_kernel(const float* __restrict__ qkv, const float* __restrict__
   }
   __syncthreads();
   if (head >= g.heads) return;
-  float* sk = smem + (size_t)warp * (2 * WT * KV_LD + WT * WT);
+  float* sk = smem + (size_t)warp * WARP_SMEM;
   float* sv = sk + WT * KV_LD;
   float* sb = sv + WT * KV_LD;
   const int C = g.C;
@@ -159,7 +160,7 @@ extern "C" int occ_window_attention(const float* qkv, const float* qkv_bias, con
   g.vox_rows = (long long)B * X * Y * Z;
   const long long nwin = (long long)B * (Z + 1) * g.nWx * g.nWy;
   OCC_REQUIRE(nwin < (1ll << 31));
-  const size_t smem = 4 * (2 * WT * KV_LD + WT * WT) * sizeof(float);
+  const size_t smem = 4 * WARP_SMEM * sizeof(float);
   static bool configured = false;
   if (!configured) {
     OCC_CUDA(cudaFuncSetAttribute(window_attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,8 +1,11 @@
 """Per-kernel timings at BASELINE sizes (CUDA events, L2 flushed between iterations).  Development aid;
 bench.py is the contract benchmark."""
 import json
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 

@@ -68,3 +68,22 @@ def test_encoder_pr1(cuda):
     assert len(outs) == len(refs) == 2
     for i, (o, r) in enumerate(zip(outs, refs)):
         assert_close(o, r, what=f"encoder out[{i}]")
+
+
+def test_encoder_full_topology(cuda):
+    """The reference topology (4 stages x 2 blocks, C = 128/256/512/1024; occformer_nusc_r50_256x704.py:87-97)
+    on the PR1 grid -- error accumulation through all 8 stacked blocks must stay inside the tolerance."""
+    from occformer_b200.encoder import OccupancyEncoder
+    planes, nums, strides = [128, 256, 512, 1024], [2, 2, 2, 2], [1, 2, 2, 2]
+    cfg = dict(in_channels=128, num_stage=4, block_numbers=nums, block_inplanes=planes, block_strides=strides,
+               out_indices=(0, 1, 2, 3), norm_cfg=dict(type="GN", num_groups=32, requires_grad=True), with_cp=True)
+    sd = port.make_encoder_state(128, planes, nums, strides, seed=3)
+    enc = OccupancyEncoder(**cfg)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(cuda).eval()
+    x = synth.encoder_input(1, 128, 50, 50, 8, seed=11)
+    outs = enc(x.to(cuda))
+    refs = port.occupancy_encoder(x, sd, nums, strides, (0, 1, 2, 3))
+    for i, (o, r) in enumerate(zip(outs, refs)):
+        assert o.shape == r.shape
+        assert_close(o, r, what=f"full encoder out[{i}] {tuple(r.shape)}")

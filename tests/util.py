@@ -19,15 +19,23 @@ def rel_err(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
+def rel_rms(a, b):
+    """||a-b||_2 / ||b||_2 (per-tensor relative RMS error)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt().clamp_min(1e-30))
+
+
 def assert_close(a, b, tol=RTOL, what=""):
-    """per-tensor relative error <= tol AND allclose(rtol=tol, atol=tol*rms(b))."""
+    """The tolerance of every floating-point parity test: per output tensor,
+        max|a-b| / max|b| <= tol   and   ||a-b||_2 / ||b||_2 <= tol
+    (north_star: 1e-3 relative fp32 per output tensor).  An element-wise rtol is deliberately not used: outputs
+    cross zero, where a relative bound on a single element is ill-defined."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
-    r = rel_err(a, b)
-    rms = float(b.pow(2).mean().sqrt())
-    ok = torch.allclose(a, b, rtol=tol, atol=tol * max(rms, 1e-30))
-    frac_bad = float(((a - b).abs() > tol * rms + tol * b.abs()).double().mean())
-    assert r <= tol and ok, f"{what}: rel {r:.3e} (tol {tol:.0e}), allclose={ok}, frac_bad={frac_bad:.2e}, rms={rms:.3e}"
+    assert torch.isfinite(a).all(), f"{what}: non-finite values"
+    r, q = rel_err(a, b), rel_rms(a, b)
+    assert r <= tol and q <= tol, f"{what}: rel_max {r:.3e}, rel_rms {q:.3e} (tol {tol:.0e})"
+    print(f"[parity] {what}: rel_max {r:.2e} rel_rms {q:.2e} (tol {tol:.0e})")
     return r
 
 
