@@ -39,6 +39,11 @@ int occ_version(void);
 size_t occ_voxel_pool_workspace_bytes(int n_points, int B, int X, int Y, int Z);
 int occ_voxel_pool_workspace_layout(int n_points, int B, int X, int Y, int Z, size_t* off_counts,
                                     size_t* off_starts, size_t* off_order, size_t* off_vox_id);
+/* get_geometry (ViewTransformerLSSBEVDepth.py:117-150): frustum (P = D*fH*fW, 3) + camera matrices -> geom
+ * (B, N, P, 3) ego-frame points.  intrins (B,N,3,intrin_cols) with intrin_cols 3 or 4 (KITTI P2), bda (B,d,d), d 3|4. */
+int occ_lss_geometry(const float* frustum, int P, const float* rots, const float* trans, const float* intrins,
+                     int intrin_cols, const float* post_rots, const float* post_trans, const float* bda, int bda_dim,
+                     int B, int N, float* geom, occ_stream_t stream);
 /* depth softmax over D + NCHW->NHWC of the context features (ViewTransformerLSSVoxel.py:108-110):
  * depth_logits (BN, D, HW), img_feat (BN, C, HW) -> depth_prob (BN, D, HW), feat_cl (BN, HW, C) */
 int occ_lift_prologue(const float* depth_logits, const float* img_feat, float* depth_prob, float* feat_cl, int BN,
@@ -102,6 +107,59 @@ int occ_dualpath_fuse(const float* x, const float* bev, const float* cw, float c
  * (window_attention.py:168-242, 69-107) minus the qkv / proj linears. bias_dense = table[index] as (heads,49,49). */
 int occ_window_attention(const float* qkv, const float* qkv_bias, const float* bias_dense, float* out, int B, int X,
                          int Y, int Z, int C, int heads, int shift, occ_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Mask2Former-3D occupancy decoder head (P/occformer/mask2former/mask2former_nusc_occ.py, mask2former_occ.py).
+ * Layouts: voxel memories channel-last (B, S, E); queries (B, Q, E); mask logits "query-last" (B, S, Q).
+ * The voxel-side GEMMs (K/V projections :657-667 via nn.MultiheadAttention in_proj; mask einsum :457) go through
+ * occ_gemm_tf32; the entry points below are the fused query-side / reduction kernels. */
+/* SinePositionalEncoding3D.forward, normalize=True, all-False mask (positional_encoding.py:58-108): out (X*Y*Z, 3F) */
+int occ_sine_pos3d(float* out, int X, int Y, int Z, int num_feats, float temperature, float scale, float eps,
+                   float offset, occ_stream_t stream);
+/* level prep (mask2former_nusc_occ.py:614-630): mem = tf32(in + level_embed), kpos = tf32(in + level_embed + pos);
+ * in is channel-last (B,S,C) or the reference layout (B,C,S); level_embed / pos+kpos optional. */
+int occ_head_prep(const float* in, int in_channel_last, const float* level_embed, const float* pos, float* mem,
+                  float* kpos, int B, long long S, int C, occ_stream_t stream);
+/* forward_head query side (:446-455): post_norm LN -> cls_embed -> cls_out (rows, NC); mask_embed MLP ->
+ * membed_out (rows, E) tf32-rounded.  Weights K-major transposed (in, out). */
+int occ_query_head(const float* query, const float* pn_w, const float* pn_b, const float* clsT, const float* cls_b,
+                   int NC, const float* m0T, const float* m0b, const float* m1T, const float* m1b, const float* m2T,
+                   const float* m2b, float* cls_out, float* membed_out, int rows, int E, occ_stream_t stream);
+/* adaptive_max_pool3d of the mask logits (:463) -> pooled (B, Xo*Yo*Zo, Q); row_flag[b*Q+q] = 1 iff some key of
+ * the row is un-blocked (pooled >= 0), else the row attends everywhere (:652-653).  attn_mask == pooled < 0. */
+int occ_mask_pool(const float* mask, float* pooled, int* row_flag, int B, int X, int Y, int Z, int Xo, int Yo, int Zo,
+                  int Q, occ_stream_t stream);
+/* key-chunking of the masked cross attention for S keys */
+int occ_cross_attn_chunks(int S, int* chunk, int* nchunk);
+/* qh = ((query + query_pos) Wq^T + bq) * scale */
+int occ_query_proj(const float* query, const float* query_pos, int Q, const float* wqT, const float* bq, float scale,
+                   float* qh, int rows, int E, occ_stream_t stream);
+/* masked cross attention partials per key chunk (mmcv MultiheadAttention -> nn.MultiheadAttention, bool attn_mask):
+ * part (B, H, nchunk, Q, 34) = running max, running sum, 32 value accumulators */
+int occ_cross_attn_partial(const float* qh, const float* Kp, const float* Vp, int ld, int koff, int voff,
+                           const float* pooled, const int* row_flag, float* part, int B, int S, int Q, int E, int H,
+                           int chunk, int nchunk, occ_stream_t stream);
+/* merge partials -> out_proj -> +identity -> LN(norms.0) -> query1; self-attention in_proj -> sa_qkv (rows, 3E) */
+int occ_cross_merge(const float* part, int nchunk, int H, const float* query, const float* query_pos, int Q,
+                    const float* woT, const float* bo, const float* n0w, const float* n0b, const float* sa_inT,
+                    const float* sa_inb, float scale, float* query1, float* sa_qkv, int rows, int E,
+                    occ_stream_t stream);
+/* self attention over the Q queries -> out_proj -> +identity -> LN(norms.1) -> FFN(ReLU) -> +identity -> LN(norms.2) */
+int occ_self_attn_ffn(const float* sa_qkv, const float* query1, int Q, const float* woT, const float* bo,
+                      const float* n1w, const float* n1b, const float* f1T, const float* f1b, const float* f2T,
+                      const float* f2b, int F, const float* n2w, const float* n2b, float* query_out, int rows, int E,
+                      int H, occ_stream_t stream);
+/* simple_test tail (:725-736, format_results :691-696): trilinear upsample (align_corners=True) -> sigmoid ->
+ * einsum with softmax(cls)[..., :-1]; mask (B, X*Y*Z, Q), cls (B, Q, NC) -> out (B, NC-1, Xo, Yo, Zo) */
+int occ_classmix(const float* mask, const float* cls, float* out, int B, int X, int Y, int Z, int Xo, int Yo, int Zo,
+                 int Q, int NC, occ_stream_t stream);
+/* (B, S, Q) -> (B, Q, S): the reference's mask_pred layout, for forward()'s return value */
+int occ_transpose_sq(const float* in, float* out, int B, long long S, int Q, occ_stream_t stream);
+/* forward_lidarseg eval branch (:505-542): grid_sample of one sample's class volume (K,X,Y,Z) at n points
+ * (rows of pts_stride floats, xyz first) + softmax -> out (n, K) */
+int occ_lidarseg_points(const float* vox, const float* pts, int pts_stride, int n, float x_min, float y_min,
+                        float z_min, float x_max, float y_max, float z_max, int X, int Y, int Z, int K, int border,
+                        float* out, occ_stream_t stream);
 
 #ifdef __cplusplus
 }

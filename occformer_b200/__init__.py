@@ -6,5 +6,7 @@ projects/mmdet3d_plugin of the reference; all arithmetic runs in csrc/libocc_b20
 from .registry import BACKBONES, HEADS, NECKS  # noqa: F401
 from .encoder import DualpathTransformerBlock, OccupancyEncoder  # noqa: F401
 from .view_transformer import ViewTransformerLiftSplatShootVoxel, bev_pool  # noqa: F401
+from .head import (Mask2FormerNuscOccHead, Mask2FormerNuscPanopticOccHead, Mask2FormerOccHead,  # noqa: F401
+                   SinePositionalEncoding3D)
 
 __version__ = "0.1.0"

@@ -17,6 +17,7 @@ SIGNATURES = {
     "occ_version": (c_int, []),
     "occ_voxel_pool_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "occ_voxel_pool_workspace_layout": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "occ_lss_geometry": (c_int, [P, c_int, P, P, P, c_int, P, P, P, c_int, c_int, c_int, P, STREAM]),
     "occ_lift_prologue": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, STREAM]),
     "occ_lift_splat": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int] + [c_float] * 9 +
                        [c_int, c_int, c_int, P, c_size_t, c_int, STREAM]),
@@ -30,6 +31,18 @@ SIGNATURES = {
     "occ_aspp_gap_branch": (c_int, [P] * 6 + [c_int] * 6 + [STREAM]),
     "occ_dualpath_fuse": (c_int, [P, P, P, c_float, P, P, P, P, c_int, P, c_int, c_int, c_int, c_int, STREAM]),
     "occ_window_attention": (c_int, [P, P, P, P] + [c_int] * 7 + [STREAM]),
+    "occ_sine_pos3d": (c_int, [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, STREAM]),
+    "occ_head_prep": (c_int, [P, c_int, P, P, P, P, c_int, c_longlong, c_int, STREAM]),
+    "occ_query_head": (c_int, [P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, c_int, c_int, STREAM]),
+    "occ_mask_pool": (c_int, [P, P, P] + [c_int] * 8 + [STREAM]),
+    "occ_cross_attn_chunks": (c_int, [c_int, P, P]),
+    "occ_query_proj": (c_int, [P, P, c_int, P, P, c_float, P, c_int, c_int, STREAM]),
+    "occ_cross_attn_partial": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P] + [c_int] * 7 + [STREAM]),
+    "occ_cross_merge": (c_int, [P, c_int, c_int, P, P, c_int, P, P, P, P, P, P, c_float, P, P, c_int, c_int, STREAM]),
+    "occ_self_attn_ffn": (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, c_int, P, P, P, c_int, c_int, c_int, STREAM]),
+    "occ_classmix": (c_int, [P, P, P] + [c_int] * 9 + [STREAM]),
+    "occ_transpose_sq": (c_int, [P, P, c_int, c_longlong, c_int, STREAM]),
+    "occ_lidarseg_points": (c_int, [P, P, c_int, c_int] + [c_float] * 6 + [c_int] * 5 + [P, STREAM]),
 }
 
 

@@ -417,6 +417,7 @@ extern "C" int occ_gemm_tf32(const float* A, const float* W, float* out, int M, 
   OCC_REQUIRE(A && W && out);
   OCC_REQUIRE(M > 0 && N > 0 && K > 0);
   OCC_REQUIRE(K % 4 == 0);  // 16-byte row pitch for TMA
+  OCC_REQUIRE(N % 4 == 0 || N < 32);  // float4 epilogue stores need 16-byte aligned output rows
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   OCC_REQUIRE(act >= 0 && act <= 2);
   if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && N % cpg == 0 && N / cpg <= 32 &&

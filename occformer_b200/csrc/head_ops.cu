@@ -1,0 +1,804 @@
+// Mask2Former-3D occupancy decoder head kernels for sm_100a (everything except the two tensor-core GEMM families,
+// which reuse occ_gemm_tf32: the K/V projections of the voxel memories and the mask-embed x voxel-feature einsum).
+//
+// Reference path replaced (files under /root/reference, P/ = projects/mmdet3d_plugin/occformer/):
+//   P/mask2former/mask2former_nusc_occ.py:589-689  forward (level prep, 1+L forward_head calls, L decoder layers)
+//   P/mask2former/mask2former_nusc_occ.py:426-471  forward_head (post_norm LN, cls_embed, mask_embed MLP, einsum,
+//                                                  adaptive_max_pool3d, sigmoid < 0.5)
+//   P/mask2former/mask2former_nusc_occ.py:691-745  format_results / simple_test (trilinear upsample, sigmoid, class mix)
+//   P/mask2former/mask2former_nusc_occ.py:505-542  forward_lidarseg (grid_sample of the class volume at LiDAR points)
+//   P/mask2former/positional_encodings/positional_encoding.py:58-108  SinePositionalEncoding3D
+//   mmcv 1.4.0 BaseTransformerLayer / MultiheadAttention / FFN (un-vendored; semantics SURVEY.md Appendix C):
+//     cross-attn (q = query+query_pos, k = key+key_pos, v = key, bool mask) -> LN -> self-attn -> LN -> FFN -> LN
+//
+// Layouts: voxel tensors are channel-last rows (B, S, E); query state (B, Q, E); masks / mask logits (B, S, Q)
+// ("query-last", so that a voxel's Q logits are one contiguous row).  All arithmetic fp32 (SIMT) -- the query side
+// is 100 rows per sample; its cost is launch latency, not FLOPs.
+#include "occ_common.cuh"
+#include "occ_ptx.cuh"
+
+namespace occ {
+
+constexpr float kLnEps = 1e-5f;
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum over E = blockDim.x threads (E multiple of 32, <= 1024); red = smem scratch of 32 floats
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum_f(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+// LayerNorm of R rows held one element per thread (thread j <-> channel j): two-pass, like torch
+template <int R>
+__device__ __forceinline__ void block_layernorm(float (&x)[R], int E, const float* __restrict__ g,
+                                                const float* __restrict__ b, float* red) {
+  const int j = threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float mean = block_sum(x[r], red) / (float)E;
+    const float d = x[r] - mean;
+    const float var = block_sum(d * d, red) / (float)E;
+    x[r] = d * rsqrtf(var + kLnEps) * g[j] + b[j];
+  }
+}
+
+// out[r][j] = bias[j] + sum_k wT[k*ldw + j] * xs[r*K + k]   (thread j; wT is the K-major transposed weight so that
+// consecutive threads read consecutive addresses; xs in shared memory -> broadcast reads)
+template <int R>
+__device__ __forceinline__ void matvec_rows(const float* __restrict__ wT, int ldw, const float* __restrict__ bias,
+                                            const float* xs, int K, int j, float (&out)[R]) {
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float w = __ldg(wT + (size_t)k * ldw + j);
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = fmaf(w, xs[r * K + k], acc[r]);
+  }
+  const float bb = bias ? __ldg(bias + j) : 0.f;
+#pragma unroll
+  for (int r = 0; r < R; ++r) out[r] = acc[r] + bb;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SinePositionalEncoding3D (normalize=True, all-False mask): out (S = X*Y*Z, 3*F) rows in (x,y,z) order.
+__global__ void sine_pos3d_kernel(float* __restrict__ out, int X, int Y, int Z, int F, float temperature, float scale,
+                                  float eps, float offset) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int E = 3 * F;
+  const long long total = (long long)X * Y * Z * E;
+  if (i >= total) return;
+  const int c = (int)(i % E);
+  const long long s = i / E;
+  const int z = (int)(s % Z), y = (int)((s / Z) % Y), x = (int)(s / ((long long)Z * Y));
+  const int axis = c / F, f = c % F;
+  const float idx = axis == 0 ? (float)(x + 1) : axis == 1 ? (float)(y + 1) : (float)(z + 1);
+  const float last = axis == 0 ? (float)X : axis == 1 ? (float)Y : (float)Z;
+  const float e = (idx + offset) / (last + eps) * scale;
+  const float dim_t = powf(temperature, 2.0f * (float)(f / 2) / (float)F);
+  const float pe = e / dim_t;
+  out[i] = (f & 1) ? cosf(pe) : sinf(pe);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Level / mask-feature preparation: (optional NCDHW -> channel-last transpose) + level embed + positional encoding,
+// tf32-rounded operands for the projection GEMMs.
+//   in  : channel-last (B, S, C) when in_cl != 0, else reference layout (B, C, S)
+//   mem : (B, S, C) = round(in + level_embed)          (V-projection operand; also the mask-feature operand)
+//   kpos: (B, S, C) = round(in + level_embed + pos)    (K-projection operand; optional)
+__global__ void head_prep_cl_kernel(const float* __restrict__ in, const float* __restrict__ level_embed,
+                                    const float* __restrict__ pos, float* __restrict__ mem, float* __restrict__ kpos,
+                                    long long rows, long long S, int C) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C4 = C >> 2;
+  if (i4 >= rows * C4) return;
+  const long long row = i4 / C4;
+  const int c0 = (int)(i4 % C4) * 4;
+  float4 v = __ldcs(reinterpret_cast<const float4*>(in + row * C + c0));
+  if (level_embed) {
+    const float4 l = *reinterpret_cast<const float4*>(level_embed + c0);
+    v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+  }
+  *reinterpret_cast<float4*>(mem + row * C + c0) =
+      make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+  if (kpos) {
+    const float4 p = *reinterpret_cast<const float4*>(pos + (row % S) * C + c0);
+    *reinterpret_cast<float4*>(kpos + row * C + c0) =
+        make_float4(round_tf32(v.x + p.x), round_tf32(v.y + p.y), round_tf32(v.z + p.z), round_tf32(v.w + p.w));
+  }
+}
+
+__global__ void head_prep_ncs_kernel(const float* __restrict__ in, const float* __restrict__ level_embed,
+                                     const float* __restrict__ pos, float* __restrict__ mem, float* __restrict__ kpos,
+                                     long long S, int C) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32;
+  const long long s0 = (long long)blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long s = s0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && s < S) ? __ldcs(in + ((size_t)b * C + c) * S + s) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long s = s0 + i;
+    const int c = c0 + threadIdx.x;
+    if (s < S && c < C) {
+      float v = tile[threadIdx.x][i];
+      if (level_embed) v += level_embed[c];
+      const size_t o = ((size_t)b * S + s) * C + c;
+      mem[o] = round_tf32(v);
+      if (kpos) kpos[o] = round_tf32(v + pos[s * C + c]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward_head, query side: post_norm LN -> cls_embed, mask_embed MLP (Linear-ReLU-Linear-ReLU-Linear).
+//   query (B*Q, E); cls_out (B*Q, NC); membed_out (B*Q, E) tf32-rounded (B operand of the mask GEMM)
+template <int R>
+__global__ void __launch_bounds__(256)
+query_head_kernel(const float* __restrict__ query, const float* __restrict__ pn_w, const float* __restrict__ pn_b,
+                  const float* __restrict__ clsT, const float* __restrict__ cls_b, int NC,
+                  const float* __restrict__ m0T, const float* __restrict__ m0b, const float* __restrict__ m1T,
+                  const float* __restrict__ m1b, const float* __restrict__ m2T, const float* __restrict__ m2b,
+                  float* __restrict__ cls_out, float* __restrict__ membed_out, int rows, int E) {
+  extern __shared__ float sm[];  // xs[R*E], hs[R*E], red[32]
+  float* xs = sm;
+  float* hs = sm + R * E;
+  float* red = hs + R * E;
+  const int j = threadIdx.x;
+  const int row0 = blockIdx.x * R;
+  float x[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) x[r] = (row0 + r < rows) ? query[(size_t)(row0 + r) * E + j] : 0.f;
+  block_layernorm<R>(x, E, pn_w, pn_b, red);
+#pragma unroll
+  for (int r = 0; r < R; ++r) xs[r * E + j] = x[r];
+  __syncthreads();
+  if (j < NC) {
+    float c[R];
+    matvec_rows<R>(clsT, NC, cls_b, xs, E, j, c);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (row0 + r < rows) cls_out[(size_t)(row0 + r) * NC + j] = c[r];
+  }
+  float h[R];
+  matvec_rows<R>(m0T, E, m0b, xs, E, j, h);
+#pragma unroll
+  for (int r = 0; r < R; ++r) hs[r * E + j] = fmaxf(h[r], 0.f);
+  __syncthreads();
+  matvec_rows<R>(m1T, E, m1b, hs, E, j, h);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < R; ++r) xs[r * E + j] = fmaxf(h[r], 0.f);
+  __syncthreads();
+  matvec_rows<R>(m2T, E, m2b, xs, E, j, h);
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (row0 + r < rows) membed_out[(size_t)(row0 + r) * E + j] = round_tf32(h[r]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// adaptive_max_pool3d of the mask logits + "has an unmasked key" flag per (b, q).
+//   mask (B, X*Y*Z, Q) -> pooled (B, Xo*Yo*Zo, Q); window of output i along an axis: [floor(i*in/out), ceil((i+1)*in/out))
+__global__ void __launch_bounds__(256)
+mask_pool_kernel(const float* __restrict__ mask, float* __restrict__ pooled, int* __restrict__ row_flag, int B, int X,
+                 int Y, int Z, int Xo, int Yo, int Zo, int Q) {
+  const long long So = (long long)Xo * Yo * Zo;
+  const long long total = (long long)B * So * Q;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % Q);
+    long long t = i / Q;
+    const int zo = (int)(t % Zo); t /= Zo;
+    const int yo = (int)(t % Yo); t /= Yo;
+    const int xo = (int)(t % Xo);
+    const int b = (int)(t / Xo);
+    const int x0 = (int)(((long long)xo * X) / Xo), x1 = (int)(((long long)(xo + 1) * X + Xo - 1) / Xo);
+    const int y0 = (int)(((long long)yo * Y) / Yo), y1 = (int)(((long long)(yo + 1) * Y + Yo - 1) / Yo);
+    const int z0 = (int)(((long long)zo * Z) / Zo), z1 = (int)(((long long)(zo + 1) * Z + Zo - 1) / Zo);
+    float m = -INFINITY;
+    for (int x = x0; x < x1; ++x)
+      for (int y = y0; y < y1; ++y)
+        for (int z = z0; z < z1; ++z)
+          m = fmaxf(m, __ldg(mask + ((((size_t)b * X + x) * Y + y) * Z + z) * Q + q));
+    pooled[i] = m;
+    // attn_mask = sigmoid(m) < 0.5  <=>  m < 0 ; a row that is blocked everywhere is un-blocked (:652-653)
+    if (!(m < 0.f)) row_flag[b * Q + q] = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Masked cross-attention, flash-decoding style.  One CTA = (key chunk, head, batch); thread t <-> query t.
+//   qh     (B, Q, E)  projected queries, already scaled by hd^-0.5
+//   Kp, Vp (B*S, ld) projected keys / values of this level; this layer's slice starts at column koff / voff
+//   pooled (B, S, Q) pooled mask logits (blocked where < 0, unless row_flag[b,q] == 0)
+//   part   (B, H, nchunk, Q, 34): running max, sum, 32 accumulators
+constexpr int XA_HD = 32;
+constexpr int XA_TILE = 64;
+
+__global__ void __launch_bounds__(128)
+cross_attn_partial_kernel(const float* __restrict__ qh, const float* __restrict__ Kp, const float* __restrict__ Vp,
+                          int ld, int koff, int voff, const float* __restrict__ pooled,
+                          const int* __restrict__ row_flag, float* __restrict__ part, int S, int Q, int E, int H,
+                          int chunk, int nchunk) {
+  __shared__ __align__(16) float sk[XA_TILE][XA_HD];
+  __shared__ __align__(16) float sv[XA_TILE][XA_HD];
+  const int c = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int t = threadIdx.x;
+  const bool active = t < Q;
+  float q[XA_HD];
+  if (active) {
+    const float4* src = reinterpret_cast<const float4*>(qh + ((size_t)b * Q + t) * E + h * XA_HD);
+#pragma unroll
+    for (int d = 0; d < XA_HD / 4; ++d) {
+      const float4 v = src[d];
+      q[4 * d] = v.x; q[4 * d + 1] = v.y; q[4 * d + 2] = v.z; q[4 * d + 3] = v.w;
+    }
+  }
+  const bool use_mask = active && row_flag[b * Q + t] != 0;
+  float m = -INFINITY, l = 0.f, acc[XA_HD];
+#pragma unroll
+  for (int d = 0; d < XA_HD; ++d) acc[d] = 0.f;
+  const int s_begin = c * chunk, s_end = min(S, s_begin + chunk);
+  for (int s0 = s_begin; s0 < s_end; s0 += XA_TILE) {
+    const int n = min(XA_TILE, s_end - s0);
+    __syncthreads();
+    // stage K / V tile: 64 rows x 32 floats each = 512 float4 per matrix, 128 threads -> 4 each
+    for (int i = t; i < XA_TILE * (XA_HD / 4); i += 128) {
+      const int r = i >> 3, c4 = i & 7;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (r < n) {
+        const size_t row = (size_t)b * S + s0 + r;
+        kv = __ldg(reinterpret_cast<const float4*>(Kp + row * ld + koff + h * XA_HD) + c4);
+        vv = __ldg(reinterpret_cast<const float4*>(Vp + row * ld + voff + h * XA_HD) + c4);
+      }
+      *reinterpret_cast<float4*>(&sk[r][c4 * 4]) = kv;
+      *reinterpret_cast<float4*>(&sv[r][c4 * 4]) = vv;
+    }
+    __syncthreads();
+    if (active) {
+      const float* prow = pooled + ((size_t)b * S + s0) * Q + t;
+      for (int j = 0; j < n; ++j) {
+        if (use_mask && __ldg(prow + (size_t)j * Q) < 0.f) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < XA_HD; d += 4) {
+          const float4 kk = *reinterpret_cast<const float4*>(&sk[j][d]);
+          s = fmaf(q[d], kk.x, s); s = fmaf(q[d + 1], kk.y, s); s = fmaf(q[d + 2], kk.z, s); s = fmaf(q[d + 3], kk.w, s);
+        }
+        if (s > m) {
+          const float sc = __expf(m - s);  // m = -inf on the first key -> 0
+          l *= sc;
+#pragma unroll
+          for (int d = 0; d < XA_HD; ++d) acc[d] *= sc;
+          m = s;
+        }
+        const float p = __expf(s - m);
+        l += p;
+#pragma unroll
+        for (int d = 0; d < XA_HD; d += 4) {
+          const float4 vv = *reinterpret_cast<const float4*>(&sv[j][d]);
+          acc[d] = fmaf(p, vv.x, acc[d]); acc[d + 1] = fmaf(p, vv.y, acc[d + 1]);
+          acc[d + 2] = fmaf(p, vv.z, acc[d + 2]); acc[d + 3] = fmaf(p, vv.w, acc[d + 3]);
+        }
+      }
+    }
+  }
+  if (active) {
+    float* dst = part + ((((size_t)b * H + h) * nchunk + c) * Q + t) * (XA_HD + 2);
+    dst[0] = m;
+    dst[1] = l;
+#pragma unroll
+    for (int d = 0; d < XA_HD; ++d) dst[2 + d] = acc[d];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Projections of the query side of the cross attention:  qh = ((query + query_pos) Wq^T + bq) * hd^-0.5
+template <int R>
+__global__ void __launch_bounds__(256)
+query_proj_kernel(const float* __restrict__ query, const float* __restrict__ query_pos, int Q,
+                  const float* __restrict__ wqT, const float* __restrict__ bq, float scale, float* __restrict__ qh,
+                  int rows, int E) {
+  extern __shared__ float sm[];
+  float* xs = sm;
+  const int j = threadIdx.x;
+  const int row0 = blockIdx.x * R;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + r;
+    xs[r * E + j] = row < rows ? query[(size_t)row * E + j] + query_pos[(size_t)(row % Q) * E + j] : 0.f;
+  }
+  __syncthreads();
+  float o[R];
+  matvec_rows<R>(wqT, E, bq, xs, E, j, o);
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (row0 + r < rows) qh[(size_t)(row0 + r) * E + j] = o[r] * scale;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Cross-attention tail + self-attention in-projection, R rows per CTA, thread j <-> channel j (= head j/32, dim j%32):
+//   merge the key-chunk partials -> out_proj -> + identity -> LN(norms.0) -> query1
+//   self-attn in_proj: q = ((query1+pos) Wq^T + bq) * hd^-0.5, k = (query1+pos) Wk^T + bk, v = query1 Wv^T + bv
+template <int R>
+__global__ void __launch_bounds__(256)
+cross_merge_kernel(const float* __restrict__ part, int nchunk, int H, const float* __restrict__ query,
+                   const float* __restrict__ query_pos, int Q, const float* __restrict__ woT,
+                   const float* __restrict__ bo, const float* __restrict__ n0w, const float* __restrict__ n0b,
+                   const float* __restrict__ sa_inT /*(E, 3E) K-major*/, const float* __restrict__ sa_inb, float scale,
+                   float* __restrict__ query1, float* __restrict__ sa_qkv /*(rows, 3E)*/, int rows, int E) {
+  extern __shared__ float sm[];  // xs[R*E], ps[R*E], red[32]
+  float* xs = sm;
+  float* ps = sm + R * E;
+  float* red = ps + R * E;
+  const int j = threadIdx.x;
+  const int h = j / XA_HD, d = j % XA_HD;
+  const int row0 = blockIdx.x * R;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + r;
+    float o = 0.f;
+    if (row < rows) {
+      const int b = row / Q, t = row % Q;
+      const float* p = part + (((size_t)b * H + h) * nchunk * Q + t) * (XA_HD + 2);
+      const size_t cstride = (size_t)Q * (XA_HD + 2);
+      float M = -INFINITY;
+      for (int c = 0; c < nchunk; ++c) M = fmaxf(M, p[c * cstride]);
+      float L = 0.f, A = 0.f;
+      for (int c = 0; c < nchunk; ++c) {
+        const float mc = p[c * cstride];
+        if (mc == -INFINITY) continue;
+        const float w = __expf(mc - M);
+        L = fmaf(p[c * cstride + 1], w, L);
+        A = fmaf(p[c * cstride + 2 + d], w, A);
+      }
+      o = A / L;
+    }
+    xs[r * E + j] = o;
+  }
+  __syncthreads();
+  float x[R];
+  matvec_rows<R>(woT, E, bo, xs, E, j, x);
+#pragma unroll
+  for (int r = 0; r < R; ++r) x[r] += (row0 + r < rows) ? query[(size_t)(row0 + r) * E + j] : 0.f;
+  block_layernorm<R>(x, E, n0w, n0b, red);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + r;
+    if (row < rows) query1[(size_t)row * E + j] = x[r];
+    xs[r * E + j] = x[r];
+    ps[r * E + j] = x[r] + (row < rows ? query_pos[(size_t)(row % Q) * E + j] : 0.f);
+  }
+  __syncthreads();
+  float o[R];
+  matvec_rows<R>(sa_inT, 3 * E, sa_inb, ps, E, j, o);
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (row0 + r < rows) sa_qkv[(size_t)(row0 + r) * 3 * E + j] = o[r] * scale;
+  matvec_rows<R>(sa_inT + E, 3 * E, sa_inb + E, ps, E, j, o);
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (row0 + r < rows) sa_qkv[(size_t)(row0 + r) * 3 * E + E + j] = o[r];
+  matvec_rows<R>(sa_inT + 2 * E, 3 * E, sa_inb + 2 * E, xs, E, j, o);
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (row0 + r < rows) sa_qkv[(size_t)(row0 + r) * 3 * E + 2 * E + j] = o[r];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Self-attention over the Q queries + out_proj + LN(norms.1) + FFN (ReLU) + LN(norms.2); one row per CTA,
+// warp w <-> head w (hd = 32 = warp size), then thread j <-> channel j.
+__global__ void __launch_bounds__(256)
+self_attn_ffn_kernel(const float* __restrict__ sa_qkv, const float* __restrict__ query1, int Q,
+                     const float* __restrict__ woT, const float* __restrict__ bo, const float* __restrict__ n1w,
+                     const float* __restrict__ n1b, const float* __restrict__ f1T /*(E, F)*/,
+                     const float* __restrict__ f1b, const float* __restrict__ f2T /*(F, E)*/,
+                     const float* __restrict__ f2b, int F, const float* __restrict__ n2w,
+                     const float* __restrict__ n2b, float* __restrict__ query_out, int E) {
+  extern __shared__ float sm[];  // xs[E], hs[F], red[32]
+  float* xs = sm;
+  float* hs = sm + E;
+  float* red = hs + F;
+  const int j = threadIdx.x, lane = j & 31, h = j >> 5;
+  const int row = blockIdx.x;
+  const int b = row / Q;
+  const float* base = sa_qkv + (size_t)b * Q * 3 * E;
+  // scores of this head: lane handles keys lane, lane+32, lane+64, lane+96
+  const float qd = sa_qkv[(size_t)row * 3 * E + j];  // q[h*32 + lane]
+  float sc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int key = i * 32 + lane;
+    const float* krow = base + (size_t)min(key, Q - 1) * 3 * E + E + h * 32;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) s = fmaf(__shfl_sync(0xffffffffu, qd, d), krow[d], s);
+    sc[i] = key < Q ? s : -INFINITY;
+  }
+  float m = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+  m = warp_max_f(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sc[i] = (i * 32 + lane < Q) ? expf(sc[i] - m) : 0.f;
+    sum += sc[i];
+  }
+  sum = warp_sum_f(sum);
+  const float inv = 1.0f / sum;
+  float o = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    for (int k = 0; k < 32; ++k) {
+      const int key = i * 32 + k;
+      const float p = __shfl_sync(0xffffffffu, sc[i], k);
+      if (key < Q) o = fmaf(p, base[(size_t)key * 3 * E + 2 * E + j], o);
+    }
+  }
+  xs[j] = o * inv;
+  __syncthreads();
+  float x[1];
+  matvec_rows<1>(woT, E, bo, xs, E, j, x);
+  x[0] += query1[(size_t)row * E + j];
+  block_layernorm<1>(x, E, n1w, n1b, red);
+  __syncthreads();
+  xs[j] = x[0];
+  __syncthreads();
+  for (int f = j; f < F; f += E) {
+    float a[1];
+    matvec_rows<1>(f1T, F, f1b, xs, E, f, a);
+    hs[f] = fmaxf(a[0], 0.f);
+  }
+  __syncthreads();
+  float y[1];
+  matvec_rows<1>(f2T, E, f2b, hs, F, j, y);
+  y[0] += x[0];
+  block_layernorm<1>(y, E, n2w, n2b, red);
+  query_out[(size_t)row * E + j] = y[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// simple_test tail (mask2former_nusc_occ.py:725-736, 691-696): trilinear upsample (align_corners=True) of the last
+// mask logits -> sigmoid -> class mix with softmax(cls)[..., :-1].
+//   mask (B, X*Y*Z, Q), cls (B, Q, NC) -> out (B, NC-1, Xo, Yo, Zo)   (reference layout)
+constexpr int CM_THREADS = 128;
+
+template <int KMAX>
+__global__ void __launch_bounds__(CM_THREADS)
+classmix_kernel(const float* __restrict__ mask, const float* __restrict__ cls, float* __restrict__ out, int X, int Y,
+                int Z, int Xo, int Yo, int Zo, int Q, int NC) {
+  extern __shared__ __align__(16) float sm[];  // P[Q][KMAX] (zero padded), rows[CM_THREADS][Q+1] (identity path)
+  const int K = NC - 1;
+  float* P = sm;
+  float* rows = sm + Q * KMAX;
+  const int b = blockIdx.y;
+  // softmax over the NC class logits of every query, drop the last (no-object) column
+  for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+    const float* c = cls + ((size_t)b * Q + q) * NC;
+    float m = -INFINITY;
+    for (int k = 0; k < NC; ++k) m = fmaxf(m, c[k]);
+    float s = 0.f;
+    for (int k = 0; k < NC; ++k) s += expf(c[k] - m);
+    for (int k = 0; k < KMAX; ++k) P[q * KMAX + k] = k < K ? expf(c[k] - m) / s : 0.f;
+  }
+  const long long Vo = (long long)Xo * Yo * Zo;
+  const long long v0 = (long long)blockIdx.x * CM_THREADS;
+  const long long v = v0 + threadIdx.x;
+  const bool identity = (X == Xo && Y == Yo && Z == Zo);
+  float acc[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  if (identity) {
+    // coalesced stage of CM_THREADS voxel rows (Q floats each) through shared memory
+    const int nrows = (int)min((long long)CM_THREADS, Vo - v0);
+    const float* src = mask + ((size_t)b * Vo + v0) * Q;
+    for (int i = threadIdx.x; i < nrows * Q; i += blockDim.x) rows[(i / Q) * (Q + 1) + (i % Q)] = __ldcs(src + i);
+    __syncthreads();
+    if (v < Vo) {
+      const float* r = rows + threadIdx.x * (Q + 1);
+      for (int q = 0; q < Q; ++q) {
+        const float s = 1.0f / (1.0f + expf(-r[q]));
+#pragma unroll
+        for (int k = 0; k < KMAX; k += 4) {
+          const float4 pp = *reinterpret_cast<const float4*>(P + q * KMAX + k);
+          acc[k] = fmaf(pp.x, s, acc[k]); acc[k + 1] = fmaf(pp.y, s, acc[k + 1]);
+          acc[k + 2] = fmaf(pp.z, s, acc[k + 2]); acc[k + 3] = fmaf(pp.w, s, acc[k + 3]);
+        }
+      }
+    }
+  } else {
+    __syncthreads();
+    if (v < Vo) {
+      const int zo = (int)(v % Zo), yo = (int)((v / Zo) % Yo), xo = (int)(v / ((long long)Zo * Yo));
+      // torch upsample_trilinear3d, align_corners=True: src = dst * (in-1)/(out-1)
+      const float sx = Xo > 1 ? (float)(X - 1) / (float)(Xo - 1) : 0.f;
+      const float sy = Yo > 1 ? (float)(Y - 1) / (float)(Yo - 1) : 0.f;
+      const float sz = Zo > 1 ? (float)(Z - 1) / (float)(Zo - 1) : 0.f;
+      const float fx = sx * xo, fy = sy * yo, fz = sz * zo;
+      const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+      const int x1 = x0 + (x0 < X - 1), y1 = y0 + (y0 < Y - 1), z1 = z0 + (z0 < Z - 1);
+      const float lx = fx - x0, ly = fy - y0, lz = fz - z0;
+      const float hx = 1.f - lx, hy = 1.f - ly, hz = 1.f - lz;
+      const float* mb = mask + (size_t)b * X * Y * Z * Q;
+      const float* p000 = mb + (((size_t)x0 * Y + y0) * Z + z0) * Q;
+      const float* p001 = mb + (((size_t)x0 * Y + y0) * Z + z1) * Q;
+      const float* p010 = mb + (((size_t)x0 * Y + y1) * Z + z0) * Q;
+      const float* p011 = mb + (((size_t)x0 * Y + y1) * Z + z1) * Q;
+      const float* p100 = mb + (((size_t)x1 * Y + y0) * Z + z0) * Q;
+      const float* p101 = mb + (((size_t)x1 * Y + y0) * Z + z1) * Q;
+      const float* p110 = mb + (((size_t)x1 * Y + y1) * Z + z0) * Q;
+      const float* p111 = mb + (((size_t)x1 * Y + y1) * Z + z1) * Q;
+      for (int q = 0; q < Q; ++q) {
+        const float val = hx * (hy * (hz * __ldg(p000 + q) + lz * __ldg(p001 + q)) +
+                                ly * (hz * __ldg(p010 + q) + lz * __ldg(p011 + q))) +
+                          lx * (hy * (hz * __ldg(p100 + q) + lz * __ldg(p101 + q)) +
+                                ly * (hz * __ldg(p110 + q) + lz * __ldg(p111 + q)));
+        const float s = 1.0f / (1.0f + expf(-val));
+#pragma unroll
+        for (int k = 0; k < KMAX; k += 4) {
+          const float4 pp = *reinterpret_cast<const float4*>(P + q * KMAX + k);
+          acc[k] = fmaf(pp.x, s, acc[k]); acc[k + 1] = fmaf(pp.y, s, acc[k + 1]);
+          acc[k + 2] = fmaf(pp.z, s, acc[k + 2]); acc[k + 3] = fmaf(pp.w, s, acc[k + 3]);
+        }
+      }
+    }
+  }
+  if (v < Vo) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) __stcs(out + ((size_t)b * K + k) * Vo + v, acc[k]);
+  }
+}
+
+// (B, S, Q) query-last mask logits -> reference layout (B, Q, S)   (only for API parity of forward())
+__global__ void transpose_sq_kernel(const float* __restrict__ in, float* __restrict__ out, long long S, int Q) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long long s0 = (long long)blockIdx.x * 32;
+  const int q0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long s = s0 + i;
+    const int q = q0 + threadIdx.x;
+    tile[i][threadIdx.x] = (s < S && q < Q) ? in[((size_t)b * S + s) * Q + q] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int q = q0 + i;
+    const long long s = s0 + threadIdx.x;
+    if (q < Q && s < S) out[((size_t)b * Q + q) * S + s] = tile[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward_lidarseg (mask2former_nusc_occ.py:505-542, eval): grid_sample(bilinear, align_corners=True, padding_mode
+// border | zeros) of the class volume (K, X, Y, Z) at LiDAR points, then softmax over K.
+__global__ void lidarseg_kernel(const float* __restrict__ vox /*(K,X,Y,Z) of one sample*/,
+                                const float* __restrict__ pts, int pts_stride, int n, float x_min, float y_min,
+                                float z_min, float x_ext, float y_ext, float z_ext, int X, int Y, int Z, int K,
+                                int border, float* __restrict__ out /*(n,K)*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float px = pts[(size_t)i * pts_stride + 0], py = pts[(size_t)i * pts_stride + 1],
+              pz = pts[(size_t)i * pts_stride + 2];
+  // normalise to [-1, 1]; grid_sample's (x,y,z) = (W,H,D) = (Z,Y,X) axes of the volume after the [2,1,0] flip
+  const float gx = ((px - x_min) / x_ext) * 2.f - 1.f;
+  const float gy = ((py - y_min) / y_ext) * 2.f - 1.f;
+  const float gz = ((pz - z_min) / z_ext) * 2.f - 1.f;
+  float ix = (gx + 1.f) / 2.f * (float)(X - 1);
+  float iy = (gy + 1.f) / 2.f * (float)(Y - 1);
+  float iz = (gz + 1.f) / 2.f * (float)(Z - 1);
+  if (border) {
+    ix = fminf(fmaxf(ix, 0.f), (float)(X - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(Y - 1));
+    iz = fminf(fmaxf(iz, 0.f), (float)(Z - 1));
+  }
+  const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+  const float lx = ix - fx, ly = iy - fy, lz = iz - fz;
+  float logit[32];
+  float m = -INFINITY;
+  for (int k = 0; k < K; ++k) {
+    const float* vk = vox + (size_t)k * X * Y * Z;
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int xx = x0 + (c >> 2), yy = y0 + ((c >> 1) & 1), zz = z0 + (c & 1);
+      const float w = ((c >> 2) ? lx : 1.f - lx) * (((c >> 1) & 1) ? ly : 1.f - ly) * ((c & 1) ? lz : 1.f - lz);
+      if (xx >= 0 && xx < X && yy >= 0 && yy < Y && zz >= 0 && zz < Z) a += w * __ldg(vk + ((size_t)xx * Y + yy) * Z + zz);
+    }
+    logit[k] = a;
+    m = fmaxf(m, a);
+  }
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) { logit[k] = expf(logit[k] - m); s += logit[k]; }
+  for (int k = 0; k < K; ++k) out[(size_t)i * K + k] = logit[k] / s;
+}
+
+}  // namespace occ
+
+using namespace occ;
+
+extern "C" int occ_sine_pos3d(float* out, int X, int Y, int Z, int num_feats, float temperature, float scale,
+                              float eps, float offset, cudaStream_t stream) {
+  OCC_REQUIRE(out && X > 0 && Y > 0 && Z > 0 && num_feats > 0);
+  const long long total = (long long)X * Y * Z * 3 * num_feats;
+  sine_pos3d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(out, X, Y, Z, num_feats, temperature, scale, eps,
+                                                                        offset);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_head_prep(const float* in, int in_channel_last, const float* level_embed, const float* pos,
+                             float* mem, float* kpos, int B, long long S, int C, cudaStream_t stream) {
+  OCC_REQUIRE(in && mem && B > 0 && S > 0 && C > 0);
+  OCC_REQUIRE((kpos == nullptr) == (pos == nullptr));
+  if (in_channel_last) {
+    OCC_REQUIRE(C % 4 == 0);
+    const long long n4 = (long long)B * S * (C / 4);
+    head_prep_cl_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(in, level_embed, pos, mem, kpos,
+                                                                         (long long)B * S, S, C);
+  } else {
+    OCC_REQUIRE((S + 31) / 32 < (1ll << 31) && B <= 65535 && (C + 31) / 32 <= 65535);
+    dim3 grid((unsigned)((S + 31) / 32), (C + 31) / 32, B), block(32, 8);
+    head_prep_ncs_kernel<<<grid, block, 0, stream>>>(in, level_embed, pos, mem, kpos, S, C);
+  }
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+constexpr int QH_ROWS = 4;
+
+extern "C" int occ_query_head(const float* query, const float* pn_w, const float* pn_b, const float* clsT,
+                              const float* cls_b, int NC, const float* m0T, const float* m0b, const float* m1T,
+                              const float* m1b, const float* m2T, const float* m2b, float* cls_out, float* membed_out,
+                              int rows, int E, cudaStream_t stream) {
+  OCC_REQUIRE(query && pn_w && pn_b && clsT && cls_b && m0T && m0b && m1T && m1b && m2T && m2b && cls_out && membed_out);
+  OCC_REQUIRE(rows > 0 && E % 32 == 0 && E <= 256 && NC > 0 && NC <= E);
+  const size_t smem = (2 * QH_ROWS * E + 32) * sizeof(float);
+  query_head_kernel<QH_ROWS><<<(rows + QH_ROWS - 1) / QH_ROWS, E, smem, stream>>>(
+      query, pn_w, pn_b, clsT, cls_b, NC, m0T, m0b, m1T, m1b, m2T, m2b, cls_out, membed_out, rows, E);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_mask_pool(const float* mask, float* pooled, int* row_flag, int B, int X, int Y, int Z, int Xo,
+                             int Yo, int Zo, int Q, cudaStream_t stream) {
+  OCC_REQUIRE(mask && pooled && row_flag && B > 0 && X > 0 && Y > 0 && Z > 0 && Xo > 0 && Yo > 0 && Zo > 0 && Q > 0);
+  OCC_REQUIRE(Xo <= X && Yo <= Y && Zo <= Z);
+  OCC_CUDA(cudaMemsetAsync(row_flag, 0, (size_t)B * Q * sizeof(int), stream));
+  const long long total = (long long)B * Xo * Yo * Zo * Q;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  mask_pool_kernel<<<(unsigned)blocks, 256, 0, stream>>>(mask, pooled, row_flag, B, X, Y, Z, Xo, Yo, Zo, Q);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_cross_attn_chunks(int S, int* chunk, int* nchunk) {
+  // chunk size: multiple of XA_TILE, at most 64 chunks... enough CTAs (chunks * heads * B) to fill the machine
+  int c = XA_TILE * 4;  // 256 keys
+  while ((S + c - 1) / c > 512) c *= 2;
+  *chunk = c;
+  *nchunk = (S + c - 1) / c;
+  return OCC_OK;
+}
+
+extern "C" int occ_cross_attn_partial(const float* qh, const float* Kp, const float* Vp, int ld, int koff, int voff,
+                                      const float* pooled, const int* row_flag, float* part, int B, int S, int Q,
+                                      int E, int H, int chunk, int nchunk, cudaStream_t stream) {
+  OCC_REQUIRE(qh && Kp && Vp && pooled && row_flag && part);
+  OCC_REQUIRE(B > 0 && S > 0 && Q > 0 && Q <= 128 && H > 0 && E == H * XA_HD && chunk > 0 && chunk % XA_TILE == 0);
+  OCC_REQUIRE(nchunk == (S + chunk - 1) / chunk && ld % 4 == 0 && koff % 4 == 0 && voff % 4 == 0);
+  dim3 grid(nchunk, H, B);
+  cross_attn_partial_kernel<<<grid, 128, 0, stream>>>(qh, Kp, Vp, ld, koff, voff, pooled, row_flag, part, S, Q, E, H,
+                                                      chunk, nchunk);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_query_proj(const float* query, const float* query_pos, int Q, const float* wqT, const float* bq,
+                              float scale, float* qh, int rows, int E, cudaStream_t stream) {
+  OCC_REQUIRE(query && query_pos && wqT && bq && qh && rows > 0 && Q > 0 && E % 32 == 0 && E <= 256);
+  const size_t smem = QH_ROWS * E * sizeof(float);
+  query_proj_kernel<QH_ROWS><<<(rows + QH_ROWS - 1) / QH_ROWS, E, smem, stream>>>(query, query_pos, Q, wqT, bq, scale, qh,
+                                                                                  rows, E);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_cross_merge(const float* part, int nchunk, int H, const float* query, const float* query_pos, int Q,
+                               const float* woT, const float* bo, const float* n0w, const float* n0b,
+                               const float* sa_inT, const float* sa_inb, float scale, float* query1, float* sa_qkv,
+                               int rows, int E, cudaStream_t stream) {
+  OCC_REQUIRE(part && query && query_pos && woT && bo && n0w && n0b && sa_inT && sa_inb && query1 && sa_qkv);
+  OCC_REQUIRE(rows > 0 && Q > 0 && E == H * XA_HD && E <= 256 && nchunk > 0);
+  const size_t smem = (2 * QH_ROWS * E + 32) * sizeof(float);
+  cross_merge_kernel<QH_ROWS><<<(rows + QH_ROWS - 1) / QH_ROWS, E, smem, stream>>>(
+      part, nchunk, H, query, query_pos, Q, woT, bo, n0w, n0b, sa_inT, sa_inb, scale, query1, sa_qkv, rows, E);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_self_attn_ffn(const float* sa_qkv, const float* query1, int Q, const float* woT, const float* bo,
+                                 const float* n1w, const float* n1b, const float* f1T, const float* f1b,
+                                 const float* f2T, const float* f2b, int F, const float* n2w, const float* n2b,
+                                 float* query_out, int rows, int E, int H, cudaStream_t stream) {
+  OCC_REQUIRE(E == H * XA_HD);
+  OCC_REQUIRE(sa_qkv && query1 && woT && bo && n1w && n1b && f1T && f1b && f2T && f2b && n2w && n2b && query_out);
+  OCC_REQUIRE(rows > 0 && Q > 0 && Q <= 128 && E % 32 == 0 && E <= 256 && F > 0 && rows % Q == 0);
+  const size_t smem = (E + F + 32) * sizeof(float);
+  OCC_REQUIRE(smem <= 48 * 1024);
+  self_attn_ffn_kernel<<<rows, E, smem, stream>>>(sa_qkv, query1, Q, woT, bo, n1w, n1b, f1T, f1b, f2T, f2b, F, n2w, n2b,
+                                                  query_out, E);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_classmix(const float* mask, const float* cls, float* out, int B, int X, int Y, int Z, int Xo, int Yo,
+                            int Zo, int Q, int NC, cudaStream_t stream) {
+  OCC_REQUIRE(mask && cls && out && B > 0 && X > 0 && Y > 0 && Z > 0 && Xo > 0 && Yo > 0 && Zo > 0 && Q > 0);
+  OCC_REQUIRE(NC >= 2 && NC - 1 <= 32 && B <= 65535);
+  const long long Vo = (long long)Xo * Yo * Zo;
+  const int kmax = (NC - 1 <= 20) ? 20 : 32;
+  const size_t smem = ((size_t)Q * kmax + (size_t)CM_THREADS * (Q + 1)) * sizeof(float);
+  OCC_REQUIRE(smem <= 200 * 1024);
+  dim3 grid((unsigned)((Vo + CM_THREADS - 1) / CM_THREADS), B);
+  if (NC - 1 <= 20) {
+    static bool configured = false;
+    if (!configured) {
+      OCC_CUDA(cudaFuncSetAttribute(classmix_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    classmix_kernel<20><<<grid, CM_THREADS, smem, stream>>>(mask, cls, out, X, Y, Z, Xo, Yo, Zo, Q, NC);
+  } else {
+    static bool configured = false;
+    if (!configured) {
+      OCC_CUDA(cudaFuncSetAttribute(classmix_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    classmix_kernel<32><<<grid, CM_THREADS, smem, stream>>>(mask, cls, out, X, Y, Z, Xo, Yo, Zo, Q, NC);
+  }
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_transpose_sq(const float* in, float* out, int B, long long S, int Q, cudaStream_t stream) {
+  OCC_REQUIRE(in && out && B > 0 && S > 0 && Q > 0 && B <= 65535);
+  dim3 grid((unsigned)((S + 31) / 32), (Q + 31) / 32, B), block(32, 8);
+  transpose_sq_kernel<<<grid, block, 0, stream>>>(in, out, S, Q);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_lidarseg_points(const float* vox, const float* pts, int pts_stride, int n, float x_min, float y_min,
+                                   float z_min, float x_max, float y_max, float z_max, int X, int Y, int Z, int K,
+                                   int border, float* out, cudaStream_t stream) {
+  OCC_REQUIRE(vox && out && n >= 0 && X > 0 && Y > 0 && Z > 0 && K > 0 && K <= 32 && pts_stride >= 3);
+  if (n == 0) return OCC_OK;
+  OCC_REQUIRE(pts != nullptr);
+  lidarseg_kernel<<<(n + 127) / 128, 128, 0, stream>>>(vox, pts, pts_stride, n, x_min, y_min, z_min, x_max - x_min,
+                                                       y_max - y_min, z_max - z_min, X, Y, Z, K, border, out);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}

@@ -394,3 +394,90 @@ extern "C" int occ_voxel_pool_geom(const float* feats, const float* geom, float*
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ frustum geometry
+// ViewTransformerLSSBEVDepth.get_geometry (projects/mmdet3d_plugin/occformer/image2bev/ViewTransformerLSSBEVDepth.py:117-150)
+// as one kernel: undo the image augmentation (post_trans / post_rots), unproject with depth, camera -> ego
+// (rots * inv(intrins), + trans), then the BEV augmentation matrix bda.  The reference issues ~25 batched 3x3
+// cuBLAS gemv launches over 473k points for this; the arithmetic is 3 small matvecs per point.
+// One CTA column (blockIdx.y) per camera (b, n); thread = frustum point.
+namespace occ {
+
+__device__ __forceinline__ void inv3x3(const float* m, float* o) {
+  // adjugate / determinant in double, rounded once to fp32
+  const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+  const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+  const double det = a * A + b * B + c * C;
+  const double r = 1.0 / det;
+  o[0] = (float)(A * r); o[1] = (float)(-(b * i - c * h) * r); o[2] = (float)((b * f - c * e) * r);
+  o[3] = (float)(B * r); o[4] = (float)((a * i - c * g) * r);  o[5] = (float)(-(a * f - c * d) * r);
+  o[6] = (float)(C * r); o[7] = (float)(-(a * h - b * g) * r); o[8] = (float)((a * e - b * d) * r);
+}
+
+__device__ __forceinline__ void mv3(const float* m, float x, float y, float z, float& ox, float& oy, float& oz) {
+  ox = fmaf(m[2], z, fmaf(m[1], y, m[0] * x));
+  oy = fmaf(m[5], z, fmaf(m[4], y, m[3] * x));
+  oz = fmaf(m[8], z, fmaf(m[7], y, m[6] * x));
+}
+
+__global__ void __launch_bounds__(256)
+lss_geometry_kernel(const float* __restrict__ frustum /*(P,3)*/, int P, const float* __restrict__ rots,
+                    const float* __restrict__ trans, const float* __restrict__ intrins, int intrin_cols,
+                    const float* __restrict__ post_rots, const float* __restrict__ post_trans,
+                    const float* __restrict__ bda, int bda_dim, int N, float* __restrict__ geom) {
+  __shared__ float s_ipr[9], s_comb[9], s_vec[9], s_bda[16];
+  const int bn = blockIdx.y, b = bn / N;
+  if (threadIdx.x == 0) {
+    inv3x3(post_rots + (size_t)bn * 9, s_ipr);
+    float K[9], iK[9];
+    const float* I = intrins + (size_t)bn * 3 * intrin_cols;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) K[r * 3 + c] = I[r * intrin_cols + c];
+    inv3x3(K, iK);
+    const float* R = rots + (size_t)bn * 9;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        s_comb[r * 3 + c] = fmaf(R[r * 3 + 2], iK[6 + c], fmaf(R[r * 3 + 1], iK[3 + c], R[r * 3] * iK[c]));
+    for (int k = 0; k < 3; ++k) {
+      s_vec[k] = post_trans[(size_t)bn * 3 + k];
+      s_vec[3 + k] = trans[(size_t)bn * 3 + k];
+      s_vec[6 + k] = intrin_cols == 4 ? I[k * 4 + 3] : 0.f;  // KITTI P2 shift (:134-137)
+    }
+    for (int k = 0; k < bda_dim * bda_dim; ++k) s_bda[k] = bda[(size_t)b * bda_dim * bda_dim + k];
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float x = frustum[3 * (size_t)p] - s_vec[0], y = frustum[3 * (size_t)p + 1] - s_vec[1],
+        z = frustum[3 * (size_t)p + 2] - s_vec[2];
+  float u, v, w;
+  mv3(s_ipr, x, y, z, u, v, w);
+  u = u * w - s_vec[6]; v = v * w - s_vec[7]; w = w - s_vec[8];
+  mv3(s_comb, u, v, w, x, y, z);
+  x += s_vec[3]; y += s_vec[4]; z += s_vec[5];
+  float ox, oy, oz;
+  if (bda_dim == 4) {
+    ox = fmaf(s_bda[2], z, fmaf(s_bda[1], y, s_bda[0] * x)) + s_bda[3];
+    oy = fmaf(s_bda[6], z, fmaf(s_bda[5], y, s_bda[4] * x)) + s_bda[7];
+    oz = fmaf(s_bda[10], z, fmaf(s_bda[9], y, s_bda[8] * x)) + s_bda[11];
+  } else {
+    mv3(s_bda, x, y, z, ox, oy, oz);
+  }
+  float* o = geom + ((size_t)bn * P + p) * 3;
+  o[0] = ox; o[1] = oy; o[2] = oz;
+}
+
+}  // namespace occ
+
+extern "C" int occ_lss_geometry(const float* frustum, int P, const float* rots, const float* trans, const float* intrins,
+                                int intrin_cols, const float* post_rots, const float* post_trans, const float* bda,
+                                int bda_dim, int B, int N, float* geom, cudaStream_t stream) {
+  OCC_REQUIRE(frustum && rots && trans && intrins && post_rots && post_trans && bda && geom);
+  OCC_REQUIRE(P > 0 && B > 0 && N > 0 && (intrin_cols == 3 || intrin_cols == 4) && (bda_dim == 3 || bda_dim == 4));
+  OCC_REQUIRE((long long)B * N <= 65535);
+  dim3 grid((P + 255) / 256, B * N);
+  occ::lss_geometry_kernel<<<grid, 256, 0, stream>>>(frustum, P, rots, trans, intrins, intrin_cols, post_rots, post_trans,
+                                                     bda, bda_dim, N, geom);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}

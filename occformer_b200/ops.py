@@ -79,6 +79,19 @@ def _workspace(n_points, B, X, Y, Z, device):
     return ws
 
 
+def lss_geometry(frustum, rots, trans, intrins, post_rots, post_trans, bda):
+    """frustum (D,fH,fW,3) + camera matrices -> geom (B,N,D,fH,fW,3)."""
+    B, N = trans.shape[:2]
+    D, fH, fW, _ = frustum.shape
+    f = lambda t: _chk(t.float().contiguous(), "camera matrix")  # noqa: E731
+    geom = torch.empty((B, N, D, fH, fW, 3), dtype=torch.float32, device=frustum.device)
+    fr, r, t, k, pr, pt, bd = f(frustum), f(rots), f(trans), f(intrins), f(post_rots), f(post_trans), f(bda)
+    check(lib().occ_lss_geometry(_ptr(fr), D * fH * fW, _ptr(r), _ptr(t), _ptr(k), k.shape[-1], _ptr(pr), _ptr(pt),
+                                 _ptr(bd), bd.shape[-1], B, N, _ptr(geom), _stream()), "occ_lss_geometry")
+    LAUNCH_COUNT[0] += 1
+    return geom
+
+
 def lift_prologue(depth_logits, img_feat):
     """depth_logits (BN,D,fH,fW), img_feat (BN,C,fH,fW) -> depth_prob (BN,D,fH,fW), feat_cl (BN,fH*fW,C)."""
     _chk(depth_logits, "depth_logits"), _chk(img_feat, "img_feat")
@@ -245,5 +258,125 @@ def window_attention(qkv, qkv_bias, bias_dense, B, X, Y, Z, C, heads, shift):
     out = torch.empty((rows, C), dtype=torch.float32, device=qkv.device)
     check(lib().occ_window_attention(_ptr(qkv), _ptr(qkv_bias), _ptr(bias_dense), _ptr(out), B, X, Y, Z, C, heads,
                                      int(shift), _stream()), "occ_window_attention")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- decoder head
+def sine_pos3d(X, Y, Z, num_feats, device, temperature=10000.0, scale=6.283185307179586, eps=1e-6, offset=0.0):
+    out = torch.empty((X * Y * Z, 3 * num_feats), dtype=torch.float32, device=device)
+    check(lib().occ_sine_pos3d(_ptr(out), X, Y, Z, num_feats, temperature, scale, eps, offset, _stream()), "occ_sine_pos3d")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+def head_prep(x, channel_last, level_embed=None, pos=None):
+    """x: (B,S,C) channel-last memory or (B,C,S) reference layout -> mem (B,S,C) [, kpos (B,S,C)] tf32-rounded."""
+    _chk(x, "x")
+    if channel_last:
+        B, S, C = x.shape
+    else:
+        B, C, S = x.shape
+    mem = torch.empty((B, S, C), dtype=torch.float32, device=x.device)
+    kpos = torch.empty_like(mem) if pos is not None else None
+    check(lib().occ_head_prep(_ptr(x), int(channel_last), _ptr(level_embed), _ptr(pos), _ptr(mem), _ptr(kpos), B, S, C,
+                              _stream()), "occ_head_prep")
+    LAUNCH_COUNT[0] += 1
+    return mem, kpos
+
+
+def query_head(query, W, NC):
+    rows, E = query.shape
+    cls = torch.empty((rows, NC), dtype=torch.float32, device=query.device)
+    membed = torch.empty((rows, E), dtype=torch.float32, device=query.device)
+    check(lib().occ_query_head(_ptr(query), _ptr(W["pn_w"]), _ptr(W["pn_b"]), _ptr(W["clsT"]), _ptr(W["cls_b"]), NC,
+                               _ptr(W["m0T"]), _ptr(W["m0b"]), _ptr(W["m1T"]), _ptr(W["m1b"]), _ptr(W["m2T"]),
+                               _ptr(W["m2b"]), _ptr(cls), _ptr(membed), rows, E, _stream()), "occ_query_head")
+    LAUNCH_COUNT[0] += 1
+    return cls, membed
+
+
+def mask_pool(mask, B, grid, out_grid, Q):
+    X, Y, Z = grid
+    Xo, Yo, Zo = out_grid
+    pooled = torch.empty((B, Xo * Yo * Zo, Q), dtype=torch.float32, device=mask.device)
+    flag = torch.empty((B * Q,), dtype=torch.int32, device=mask.device)
+    check(lib().occ_mask_pool(_ptr(mask), _ptr(pooled), _ptr(flag), B, X, Y, Z, Xo, Yo, Zo, Q, _stream()), "occ_mask_pool")
+    LAUNCH_COUNT[0] += 2
+    return pooled, flag
+
+
+def cross_attn_chunks(S):
+    c, n = ctypes.c_int(), ctypes.c_int()
+    lib().occ_cross_attn_chunks(S, ctypes.byref(c), ctypes.byref(n))
+    return c.value, n.value
+
+
+def query_proj(query, query_pos, Q, wqT, bq, scale):
+    rows, E = query.shape
+    qh = torch.empty_like(query)
+    check(lib().occ_query_proj(_ptr(query), _ptr(query_pos), Q, _ptr(wqT), _ptr(bq), scale, _ptr(qh), rows, E, _stream()),
+          "occ_query_proj")
+    LAUNCH_COUNT[0] += 1
+    return qh
+
+
+def cross_attn_partial(qh, Kp, Vp, ld, koff, voff, pooled, flag, B, S, Q, E, H):
+    chunk, nchunk = cross_attn_chunks(S)
+    part = torch.empty((B, H, nchunk, Q, 34), dtype=torch.float32, device=qh.device)
+    check(lib().occ_cross_attn_partial(_ptr(qh), _ptr(Kp), _ptr(Vp), ld, koff, voff, _ptr(pooled), _ptr(flag), _ptr(part),
+                                       B, S, Q, E, H, chunk, nchunk, _stream()), "occ_cross_attn_partial")
+    LAUNCH_COUNT[0] += 1
+    return part, nchunk
+
+
+def cross_merge(part, nchunk, H, query, query_pos, Q, L, scale):
+    rows, E = query.shape
+    q1 = torch.empty_like(query)
+    sa = torch.empty((rows, 3 * E), dtype=torch.float32, device=query.device)
+    check(lib().occ_cross_merge(_ptr(part), nchunk, H, _ptr(query), _ptr(query_pos), Q, _ptr(L["ca_woT"]), _ptr(L["ca_bo"]),
+                                _ptr(L["n0w"]), _ptr(L["n0b"]), _ptr(L["sa_inT"]), _ptr(L["sa_inb"]), scale, _ptr(q1),
+                                _ptr(sa), rows, E, _stream()), "occ_cross_merge")
+    LAUNCH_COUNT[0] += 1
+    return q1, sa
+
+
+def self_attn_ffn(sa, q1, Q, L, H):
+    rows, E = q1.shape
+    out = torch.empty_like(q1)
+    F = L["f1b"].numel()
+    check(lib().occ_self_attn_ffn(_ptr(sa), _ptr(q1), Q, _ptr(L["sa_woT"]), _ptr(L["sa_bo"]), _ptr(L["n1w"]), _ptr(L["n1b"]),
+                                  _ptr(L["f1T"]), _ptr(L["f1b"]), _ptr(L["f2T"]), _ptr(L["f2b"]), F, _ptr(L["n2w"]),
+                                  _ptr(L["n2b"]), _ptr(out), rows, E, H, _stream()), "occ_self_attn_ffn")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+def classmix(mask, cls, B, grid, out_grid, Q, NC):
+    X, Y, Z = grid
+    Xo, Yo, Zo = out_grid
+    out = torch.empty((B, NC - 1, Xo, Yo, Zo), dtype=torch.float32, device=mask.device)
+    check(lib().occ_classmix(_ptr(mask), _ptr(cls), _ptr(out), B, X, Y, Z, Xo, Yo, Zo, Q, NC, _stream()), "occ_classmix")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+def transpose_sq(mask, B, S, Q):
+    out = torch.empty((B, Q, S), dtype=torch.float32, device=mask.device)
+    check(lib().occ_transpose_sq(_ptr(mask), _ptr(out), B, S, Q, _stream()), "occ_transpose_sq")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+def lidarseg_points(vox, pts, pc_range, border=True):
+    """vox (K,X,Y,Z) contiguous class volume of one sample; pts (n, >=3) -> (n, K) softmaxed point scores."""
+    _chk(vox, "vox")
+    K, X, Y, Z = vox.shape
+    pts = pts.float().contiguous()
+    n = pts.shape[0]
+    out = torch.empty((n, K), dtype=torch.float32, device=vox.device)
+    r = [float(v) for v in pc_range]
+    check(lib().occ_lidarseg_points(_ptr(vox), _ptr(pts) if n else None, pts.shape[1] if n else 3, n, r[0], r[1], r[2],
+                                    r[3], r[4], r[5], X, Y, Z, K, int(border), _ptr(out), _stream()), "occ_lidarseg_points")
     LAUNCH_COUNT[0] += 1
     return out

@@ -88,25 +88,10 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         return nn.Parameter(torch.stack((xs, ys, ds), -1), requires_grad=False)
 
     def get_geometry(self, rots, trans, intrins, post_rots, post_trans, bda):
-        """ViewTransformerLSSBEVDepth.py:117-150 -- camera-matrix plumbing (5.7 MB/sample), kept in torch."""
-        B, N, _ = trans.shape
-        points = self.frustum - post_trans.view(B, N, 1, 1, 1, 3)
-        points = torch.inverse(post_rots).view(B, N, 1, 1, 1, 3, 3).matmul(points.unsqueeze(-1))
-        points = torch.cat((points[:, :, :, :, :, :2] * points[:, :, :, :, :, 2:3], points[:, :, :, :, :, 2:3]), 5)
-        if intrins.shape[3] == 4:
-            shift = intrins[:, :, :3, 3]
-            points = points - shift.view(B, N, 1, 1, 1, 3, 1)
-            intrins = intrins[:, :, :3, :3]
-        combine = rots.matmul(torch.inverse(intrins))
-        points = combine.view(B, N, 1, 1, 1, 3, 3).matmul(points).squeeze(-1)
-        points = points + trans.view(B, N, 1, 1, 1, 3)
-        if bda.shape[-1] == 4:
-            points = torch.cat((points, torch.ones(*points.shape[:-1], 1).type_as(points)), dim=-1)
-            points = bda.view(B, 1, 1, 1, 1, 4, 4).matmul(points.unsqueeze(-1)).squeeze(-1)
-            points = points[..., :3]
-        else:
-            points = bda.view(B, 1, 1, 1, 1, 3, 3).matmul(points.unsqueeze(-1)).squeeze(-1)
-        return points
+        """ViewTransformerLSSBEVDepth.py:117-150 as one fused kernel (occ_lss_geometry): (B,N,D,fH,fW,3) ego points."""
+        if not trans.is_cuda:
+            raise RuntimeError("occformer_b200: get_geometry runs on CUDA tensors only (no CPU fallback)")
+        return ops.lss_geometry(self.frustum.data, rots, trans, intrins, post_rots, post_trans, bda)
 
     def get_depth_dist(self, x):
         return x.softmax(dim=1)

@@ -473,101 +473,7 @@ def head_simple_test(voxel_feats, sd, num_heads, num_layers, occ_size, num_level
 
 
 # =============================================================================
-# deterministic synthetic weights (same keys / shapes as the reference modules)
+# deterministic synthetic weights: shared with bench.py / smoke through occformer_b200.synth (pure data
+# generators, no arithmetic of the path); re-exported here so tests keep one entry point
 # =============================================================================
-
-
-def _randn(g, *shape, std=1.0):
-    return torch.randn(*shape, generator=g) * std
-
-
-def make_block_state(cin, c, stride, g, prefix=""):
-    """state_dict of one DualpathTransformerBlock, seeded generator ``g``.
-    Zero-initialised reference params are perturbed so that they matter."""
-    sd = {}
-    p = prefix
-
-    def norm(name, n):
-        sd[p + name + "weight"] = 1 + 0.1 * _randn(g, n)
-        sd[p + name + "bias"] = 0.1 * _randn(g, n)
-
-    def lin(name, o, i):
-        sd[p + name + "weight"] = _randn(g, o, i, std=i ** -0.5)
-        sd[p + name + "bias"] = 0.1 * _randn(g, o)
-
-    if stride > 1:
-        sd[p + "downsample.0.weight"] = _randn(g, c, cin, 1, 1, 1, std=cin ** -0.5)
-        norm("downsample.1.", c)
-    sd[p + "input_conv.0.weight"] = _randn(g, c, cin, 3, 3, 3, std=(27 * cin) ** -0.5)
-    norm("input_conv.1.", c)
-    be = "bev_encoder."
-    norm(be + "norm1.", c)
-    sd[p + be + "attn.w_msa.relative_position_bias_table"] = _randn(g, 169, c // 32, std=0.5)
-    sd[p + be + "attn.w_msa.relative_position_index"] = rel_position_index(7)
-    lin(be + "attn.w_msa.qkv.", 3 * c, c)
-    lin(be + "attn.w_msa.proj.", c, c)
-    norm(be + "norm2.", c)
-    lin(be + "ffn.layers.0.0.", c, c)
-    lin(be + "ffn.layers.1.", c, c)
-    ch = c // 4
-    sd[p + "aspp.input_conv.0.weight"] = _randn(g, ch, c, 1, 1, std=c ** -0.5)
-    norm("aspp.input_conv.1.", ch)
-    sd[p + "aspp.aspp.aspp1.atrous_conv.weight"] = _randn(g, ch, ch, 1, 1, std=ch ** -0.5)
-    norm("aspp.aspp.aspp1.bn.", ch)
-    for i in (2, 3, 4):
-        sd[p + f"aspp.aspp.aspp{i}.atrous_conv.weight"] = _randn(g, ch, ch, 3, 3, std=(9 * ch) ** -0.5)
-        norm(f"aspp.aspp.aspp{i}.bn.", ch)
-    sd[p + "aspp.aspp.global_avg_pool.1.weight"] = _randn(g, ch, ch, 1, 1, std=ch ** -0.5)
-    norm("aspp.aspp.global_avg_pool.2.", ch)
-    sd[p + "aspp.aspp.conv1.weight"] = _randn(g, ch, 5 * ch, 1, 1, std=(5 * ch) ** -0.5)
-    norm("aspp.aspp.bn1.", ch)
-    sd[p + "aspp.output_conv.0.weight"] = _randn(g, c, ch, 1, 1, std=ch ** -0.5)
-    norm("aspp.output_conv.1.", c)
-    sd[p + "combine_coeff.weight"] = _randn(g, 1, c, 1, 1, 1, std=c ** -0.5)
-    sd[p + "combine_coeff.bias"] = 0.1 * _randn(g, 1)
-    return sd
-
-
-def make_encoder_state(in_channels, block_inplanes, block_numbers, block_strides, seed=0, prefix=""):
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-    cin = in_channels
-    for s, (c, nb, st) in enumerate(zip(block_inplanes, block_numbers, block_strides)):
-        for b in range(nb):
-            sd.update(make_block_state(cin, c, st if b == 0 else 1, g, f"{prefix}layers.{s}.{b}."))
-            cin = c
-    return sd
-
-
-def make_head_state(E=192, Q=100, K=17, num_layers=9, num_levels=3, ffn=None, seed=0, prefix=""):
-    """state_dict of Mask2FormerNuscOccHead (inference params)."""
-    g = torch.Generator().manual_seed(seed)
-    ffn = ffn or 8 * E
-    sd = {}
-    p = prefix
-
-    def norm(name):
-        sd[p + name + "weight"] = 1 + 0.1 * _randn(g, E)
-        sd[p + name + "bias"] = 0.1 * _randn(g, E)
-
-    def lin(name, o, i, wname="weight", bname="bias"):
-        sd[p + name + wname] = _randn(g, o, i, std=i ** -0.5)
-        sd[p + name + bname] = 0.1 * _randn(g, o)
-
-    sd[p + "query_embed.weight"] = _randn(g, Q, E)
-    sd[p + "query_feat.weight"] = _randn(g, Q, E)
-    sd[p + "level_embed.weight"] = _randn(g, num_levels, E)
-    lin("cls_embed.", K + 1, E)
-    for i in (0, 2, 4):
-        lin(f"mask_embed.{i}.", E, E)
-    for l in range(num_layers):
-        lp = f"transformer_decoder.layers.{l}."
-        for a in (0, 1):
-            lin(lp + f"attentions.{a}.attn.", 3 * E, E, "in_proj_weight", "in_proj_bias")
-            lin(lp + f"attentions.{a}.attn.out_proj.", E, E)
-        lin(lp + "ffns.0.layers.0.0.", ffn, E)
-        lin(lp + "ffns.0.layers.1.", E, ffn)
-        for n in (0, 1, 2):
-            norm(lp + f"norms.{n}.")
-    norm("transformer_decoder.post_norm.")
-    return sd
+from occformer_b200.synth import make_block_state, make_encoder_state, make_head_state  # noqa: E402,F401

@@ -122,3 +122,31 @@ def test_lift_splat_nusc_properties(cuda):
     got = grid.double().sum(dim=(0, 1, 2, 3)).cpu()
     assert_close(got, expect, 1e-5, "mass conservation")
     print(f"nusc_200: n_pts={idx.shape[0]} n_kept={int(kept.sum())} nonempty={int((ws.starts[1:] - ws.starts[:-1]).ne(0).sum())}")
+
+
+@pytest.mark.parametrize("kind", ["nusc", "kitti"])
+def test_geometry_kernel_vs_oracle(cuda, kind):
+    """occ_lss_geometry vs the oracle's literal get_geometry (torch.inverse + batched matmuls): fp32 rounding only;
+    the voxel indices derived from both geometries may differ only for points within 1e-4 cells of a cell boundary."""
+    from occformer_b200.view_transformer import ViewTransformerLiftSplatShootVoxel
+    B, N = 2, 6
+    gc = synth.grid_config("nusc_200")
+    cams = synth.nusc_cameras(B, N)
+    if kind == "kitti":  # 3x4 intrinsics with a shift column and a 4x4 homogeneous bda (ViewTransformerLSSBEVDepth.py:134-146)
+        K = torch.tensor([[707.09, 0.0, 604.08, 45.76], [0.0, 707.09, 180.51, -0.35], [0.0, 0.0, 1.0, 0.005]])
+        cams["intrins"] = K.view(1, 1, 3, 4).repeat(B, N, 1, 1)
+        bda = torch.eye(4).repeat(B, 1, 1)
+        bda[:, 0, 0] = 0.98; bda[:, 0, 1] = 0.05; bda[:, 1, 0] = -0.05; bda[:, 1, 1] = 0.98; bda[:, 0, 3] = 0.3
+        cams["bda"] = bda
+    vt = ViewTransformerLiftSplatShootVoxel(grid_config=gc, data_config={"input_size": (256, 704)}, numC_Trans=32).to(cuda)
+    got = vt.get_geometry(**{k: v.to(cuda) for k, v in cams.items()})
+    ref = port.get_geometry(port.create_frustum((256, 704), 16, gc["dbound"]), **cams)
+    assert got.shape == ref.shape
+    assert_close(got, ref, 1e-5, f"get_geometry {kind}")
+    dx, bx, nx = port.gen_dx_bx(gc["xbound"], gc["ybound"], gc["zbound"])
+    ia, ib = port.voxel_index(got.cpu(), dx, bx), port.voxel_index(ref, dx, bx)
+    diff = (ia != ib).any(-1)
+    frac = ((ref - (bx - dx / 2.0)) / dx)
+    near = ((frac - frac.round()).abs() < 1e-4).any(-1)
+    assert bool((~diff | near).all()), "index flips away from cell boundaries"
+    print(f"geometry {kind}: {int(diff.sum())} of {diff.numel()} points change voxel (all within 1e-4 cells of a boundary)")
