@@ -104,9 +104,14 @@ int occ_dualpath_fuse(const float* x, const float* bev, const float* cw, float c
                       const double* id_stats, const float* id_w, const float* id_b, int groups, float* out, int B,
                       int XY, int Z, int C, occ_stream_t stream);
 /* (shifted) 7x7 window attention core over B*(Z+1) images: ShiftWindowMSA.forward + WindowMSA.forward
- * (window_attention.py:168-242, 69-107) minus the qkv / proj linears. bias_dense = table[index] as (heads,49,49). */
-int occ_window_attention(const float* qkv, const float* qkv_bias, const float* bias_dense, float* out, int B, int X,
+ * (window_attention.py:168-242, 69-107) minus the qkv / proj linears, on tcgen05 tensor cores.
+ * bias_pad = relative_position_bias_table[relative_position_index] as (heads, 49*49 padded to 2404 floats). */
+int occ_window_attention(const float* qkv, const float* qkv_bias, const float* bias_pad, float* out, int B, int X,
                          int Y, int Z, int C, int heads, int shift, occ_stream_t stream);
+/* development aid: unit 0 of CTA 0 dumps raw scores / probabilities / output rows into dbg (128,192); NULL = off */
+int occ_window_attention_set_debug(float* dbg);
+/* development probe of tcgen05 operand conventions: D[128x32] = A[128x64] V[64x32], mode 0..3 (csrc/umma_probe.cu) */
+int occ_debug_umma_probe(const float* A, const float* V, float* D, int mode, occ_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Mask2Former-3D occupancy decoder head (P/occformer/mask2former/mask2former_nusc_occ.py, mask2former_occ.py).

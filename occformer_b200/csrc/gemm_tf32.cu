@@ -24,6 +24,8 @@ namespace occ {
 constexpr int BM = 128;
 constexpr int BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 4;
+constexpr int EPI_LD = 36;  // padded row pitch (floats) of the epilogue transpose buffers: conflict-free float4 access
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
 
 struct GemmParams {
   int M, N, K, num_k_blocks;
@@ -91,6 +93,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   double* stat_acc = reinterpret_cast<double*>(tmem_ptr + 2);  // [64] doubles: (sum, sumsq) per group, <= 32 groups
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 1024);  // 4 warps x 32 rows x EPI_LD floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,6 +205,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------- epilogue warps
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
+    float* stage_buf = epi_smem + ew * 32 * EPI_LD;
+    const bool vec_ok = (p.ldo % 4 == 0) && (p.residual == nullptr || p.ldr % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.residual)) & 15) == 0;
+    const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
     int it = 0;
     int cur_b = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -249,8 +256,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * BN;
-      float* orow = valid ? p.out + m * p.ldo : nullptr;
-      const float* rrow = (valid && p.residual) ? p.residual + m * p.ldr : nullptr;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int nc = n0 + c * 32;
@@ -261,7 +266,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const bool full_chunk = (nc + 32 <= p.N);
         if (p.gn_stats != nullptr) {
           // per-group sum / sumsq of the raw conv output, butterfly-reduced over the 32 rows of the warp
           const int cpg = p.cpg;  // power of two in [1, 32]
@@ -295,44 +299,51 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane < 2 * (32 / cpg)) atomicAdd(&stat_acc[2 * (nc / cpg) + lane], (double)sv[0]);
           }
         }
-        if (valid) {
-          if (p.bias) {
+        // ---- transpose through shared memory so that every store instruction covers 4 rows x 128 contiguous bytes
+        //      (thread = row would touch 32 different lines per instruction), then bias / residual / activation /
+        //      rounding in the coalesced domain: lane -> (row i*4 + lane/8, columns (lane%8)*4 .. +3)
+        __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full_chunk || nc + j < p.N) v[j] += __ldg(p.bias + nc + j);
-          }
-          if (rrow) {
-            if (full_chunk) {
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage_buf + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const int cq = (lane & 7) * 4;
+        const int col = nc + cq;
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col < p.N) {
+          if (col + 3 < p.N && bias_vec) bq = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          else { if (col + 3 < p.N) bq.w = __ldg(p.bias + col + 3); bq.x = __ldg(p.bias + col); if (col + 1 < p.N) bq.y = __ldg(p.bias + col + 1); if (col + 2 < p.N) bq.z = __ldg(p.bias + col + 2); }
+        }
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 rr = *reinterpret_cast<const float4*>(rrow + nc + j);
-                v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
-              }
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);
+          const long long mr = __shfl_sync(0xffffffffu, m, r);
+          if (mr < 0 || col >= p.N) continue;
+          float4 t = *reinterpret_cast<const float4*>(stage_buf + r * EPI_LD + cq);
+          t.x += bq.x; t.y += bq.y; t.z += bq.z; t.w += bq.w;
+          const bool full4 = col + 3 < p.N;
+          if (p.residual) {
+            const float* rr = p.residual + mr * p.ldr + col;
+            if (full4 && vec_ok) {
+              const float4 q = *reinterpret_cast<const float4*>(rr);
+              t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
             } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nc + j < p.N) v[j] += rrow[nc + j];
+              t.x += rr[0]; if (col + 1 < p.N) t.y += rr[1]; if (col + 2 < p.N) t.z += rr[2]; if (col + 3 < p.N) t.w += rr[3];
             }
           }
           if (p.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
           } else if (p.act == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            t.x = gelu_erf(t.x); t.y = gelu_erf(t.y); t.z = gelu_erf(t.z); t.w = gelu_erf(t.w);
           }
           if (p.round_out) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+            t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w);
           }
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(orow + nc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          float* o = p.out + mr * p.ldo + col;
+          if (full4 && vec_ok) {
+            *reinterpret_cast<float4*>(o) = t;
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) orow[nc + j] = v[j];
+            o[0] = t.x; if (col + 1 < p.N) o[1] = t.y; if (col + 2 < p.N) o[2] = t.z; if (col + 3 < p.N) o[3] = t.w;
           }
         }
       }
@@ -376,7 +387,8 @@ static int next_pow2(int v) {
 template <int BN, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_tiles,
                        cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BK * 4) + 1024 /*align*/ + 1024 /*barriers+stats*/;
+  constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BK * 4) + 1024 /*align*/ + 1024 /*barriers+stats*/ +
+                          EPI_BYTES;
   static bool configured = false;
   if (!configured) {
     OCC_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -417,7 +429,6 @@ extern "C" int occ_gemm_tf32(const float* A, const float* W, float* out, int M, 
   OCC_REQUIRE(A && W && out);
   OCC_REQUIRE(M > 0 && N > 0 && K > 0);
   OCC_REQUIRE(K % 4 == 0);  // 16-byte row pitch for TMA
-  OCC_REQUIRE(N % 4 == 0 || N < 32);  // float4 epilogue stores need 16-byte aligned output rows
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   OCC_REQUIRE(act >= 0 && act <= 2);
   if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && N % cpg == 0 && N / cpg <= 32 &&

@@ -32,49 +32,55 @@ __device__ __forceinline__ float warp_max_f(float v) {
   return v;
 }
 
-// block-wide sum over E = blockDim.x threads (E multiple of 32, <= 1024); red = smem scratch of 32 floats
-__device__ __forceinline__ float block_sum(float v, float* red) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+// ---- query-side building blocks.  CTA = (E, 4) threads: thread (j, g) owns channel j of row row0 + g; the four
+// groups also split every reduction dimension four ways (4x fewer dependent iterations per mat-vec: these kernels
+// are latency-bound -- 100 rows per sample -- not throughput-bound).
+constexpr int QG = 4;  // rows per CTA = k-split groups
+
+// sum over the E threads of group g (E multiple of 32); red = smem [QG][8]
+__device__ __forceinline__ float group_sum(float v, int g, int j, int E, float* red) {
+  const int lane = j & 31, w = j >> 5, nw = E >> 5;
   v = warp_sum_f(v);
   __syncthreads();
-  if (lane == 0) red[w] = v;
+  if (lane == 0) red[g * 8 + w] = v;
   __syncthreads();
   float t = 0.f;
-  for (int i = 0; i < nw; ++i) t += red[i];
+  for (int i = 0; i < nw; ++i) t += red[g * 8 + i];
   return t;
 }
 
-// LayerNorm of R rows held one element per thread (thread j <-> channel j): two-pass, like torch
-template <int R>
-__device__ __forceinline__ void block_layernorm(float (&x)[R], int E, const float* __restrict__ g,
-                                                const float* __restrict__ b, float* red) {
-  const int j = threadIdx.x;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const float mean = block_sum(x[r], red) / (float)E;
-    const float d = x[r] - mean;
-    const float var = block_sum(d * d, red) / (float)E;
-    x[r] = d * rsqrtf(var + kLnEps) * g[j] + b[j];
-  }
+__device__ __forceinline__ float group_layernorm(float x, int g, int j, int E, const float* __restrict__ gamma,
+                                                 const float* __restrict__ beta, float* red) {
+  const float mean = group_sum(x, g, j, E, red) / (float)E;
+  const float d = x - mean;
+  const float var = group_sum(d * d, g, j, E, red) / (float)E;
+  return d * rsqrtf(var + kLnEps) * gamma[j] + beta[j];
 }
 
-// out[r][j] = bias[j] + sum_k wT[k*ldw + j] * xs[r*K + k]   (thread j; wT is the K-major transposed weight so that
-// consecutive threads read consecutive addresses; xs in shared memory -> broadcast reads)
-template <int R>
-__device__ __forceinline__ void matvec_rows(const float* __restrict__ wT, int ldw, const float* __restrict__ bias,
-                                            const float* xs, int K, int j, float (&out)[R]) {
-  float acc[R];
+// returns out[g][j] = bias[j] + sum_k wT[k*ldw + j] * xs[g*K + k]; all four groups cooperate: group g accumulates
+// the k-quarter [g*K/4, (g+1)*K/4) for all four rows, partial sums meet in shared memory.  wT is the K-major
+// transposed weight (consecutive threads read consecutive addresses); xs [QG][K] in shared memory (broadcast reads).
+__device__ __forceinline__ float matvec4(const float* __restrict__ wT, int ldw, const float* __restrict__ bias,
+                                         const float* xs, int K, int j, int g, int E, float* part /*[QG][QG][E]*/) {
+  float acc[QG];
 #pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
+  for (int r = 0; r < QG; ++r) acc[r] = 0.f;
+  const int kq = K / QG;
+  const int k0 = g * kq, k1 = (g == QG - 1) ? K : k0 + kq;
+#pragma unroll 8
+  for (int k = k0; k < k1; ++k) {
     const float w = __ldg(wT + (size_t)k * ldw + j);
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = fmaf(w, xs[r * K + k], acc[r]);
+    for (int r = 0; r < QG; ++r) acc[r] = fmaf(w, xs[r * K + k], acc[r]);
   }
-  const float bb = bias ? __ldg(bias + j) : 0.f;
 #pragma unroll
-  for (int r = 0; r < R; ++r) out[r] = acc[r] + bb;
+  for (int r = 0; r < QG; ++r) part[(g * QG + r) * E + j] = acc[r];
+  __syncthreads();
+  float o = bias ? __ldg(bias + j) : 0.f;
+#pragma unroll
+  for (int gg = 0; gg < QG; ++gg) o += part[(gg * QG + g) * E + j];
+  __syncthreads();
+  return o;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -154,47 +160,34 @@ __global__ void head_prep_ncs_kernel(const float* __restrict__ in, const float* 
 // ---------------------------------------------------------------------------------------------------------
 // forward_head, query side: post_norm LN -> cls_embed, mask_embed MLP (Linear-ReLU-Linear-ReLU-Linear).
 //   query (B*Q, E); cls_out (B*Q, NC); membed_out (B*Q, E) tf32-rounded (B operand of the mask GEMM)
-template <int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 query_head_kernel(const float* __restrict__ query, const float* __restrict__ pn_w, const float* __restrict__ pn_b,
                   const float* __restrict__ clsT, const float* __restrict__ cls_b, int NC,
                   const float* __restrict__ m0T, const float* __restrict__ m0b, const float* __restrict__ m1T,
                   const float* __restrict__ m1b, const float* __restrict__ m2T, const float* __restrict__ m2b,
                   float* __restrict__ cls_out, float* __restrict__ membed_out, int rows, int E) {
-  extern __shared__ float sm[];  // xs[R*E], hs[R*E], red[32]
+  extern __shared__ float sm[];  // xs[QG*E], part[QG*QG*E], red[32]
   float* xs = sm;
-  float* hs = sm + R * E;
-  float* red = hs + R * E;
-  const int j = threadIdx.x;
-  const int row0 = blockIdx.x * R;
-  float x[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) x[r] = (row0 + r < rows) ? query[(size_t)(row0 + r) * E + j] : 0.f;
-  block_layernorm<R>(x, E, pn_w, pn_b, red);
-#pragma unroll
-  for (int r = 0; r < R; ++r) xs[r * E + j] = x[r];
+  float* part = xs + QG * E;
+  float* red = part + QG * QG * E;
+  const int j = threadIdx.x % E, g = threadIdx.x / E;
+  const int row = blockIdx.x * QG + g;  // rows % QG == 0
+  float x = group_layernorm(query[(size_t)row * E + j], g, j, E, pn_w, pn_b, red);
+  xs[g * E + j] = x;
   __syncthreads();
-  if (j < NC) {
-    float c[R];
-    matvec_rows<R>(clsT, NC, cls_b, xs, E, j, c);
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (row0 + r < rows) cls_out[(size_t)(row0 + r) * NC + j] = c[r];
+  {  // class logits: NC <= E outputs; threads j >= NC idle along (all threads must reach the barriers)
+    const int jj = j < NC ? j : 0;
+    const float c = matvec4(clsT, NC, cls_b, xs, E, jj, g, E, part);
+    if (j < NC) cls_out[(size_t)row * NC + j] = c;
   }
-  float h[R];
-  matvec_rows<R>(m0T, E, m0b, xs, E, j, h);
-#pragma unroll
-  for (int r = 0; r < R; ++r) hs[r * E + j] = fmaxf(h[r], 0.f);
+  float h = fmaxf(matvec4(m0T, E, m0b, xs, E, j, g, E, part), 0.f);
+  xs[g * E + j] = h;
   __syncthreads();
-  matvec_rows<R>(m1T, E, m1b, hs, E, j, h);
+  h = fmaxf(matvec4(m1T, E, m1b, xs, E, j, g, E, part), 0.f);
+  xs[g * E + j] = h;
   __syncthreads();
-#pragma unroll
-  for (int r = 0; r < R; ++r) xs[r * E + j] = fmaxf(h[r], 0.f);
-  __syncthreads();
-  matvec_rows<R>(m2T, E, m2b, xs, E, j, h);
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (row0 + r < rows) membed_out[(size_t)(row0 + r) * E + j] = round_tf32(h[r]);
+  h = matvec4(m2T, E, m2b, xs, E, j, g, E, part);
+  membed_out[(size_t)row * E + j] = round_tf32(h);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -314,114 +307,86 @@ cross_attn_partial_kernel(const float* __restrict__ qh, const float* __restrict_
 
 // ---------------------------------------------------------------------------------------------------------
 // Projections of the query side of the cross attention:  qh = ((query + query_pos) Wq^T + bq) * hd^-0.5
-template <int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 query_proj_kernel(const float* __restrict__ query, const float* __restrict__ query_pos, int Q,
                   const float* __restrict__ wqT, const float* __restrict__ bq, float scale, float* __restrict__ qh,
                   int rows, int E) {
-  extern __shared__ float sm[];
+  extern __shared__ float sm[];  // xs[QG*E], part[QG*QG*E]
   float* xs = sm;
-  const int j = threadIdx.x;
-  const int row0 = blockIdx.x * R;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int row = row0 + r;
-    xs[r * E + j] = row < rows ? query[(size_t)row * E + j] + query_pos[(size_t)(row % Q) * E + j] : 0.f;
-  }
+  float* part = xs + QG * E;
+  const int j = threadIdx.x % E, g = threadIdx.x / E;
+  const int row = blockIdx.x * QG + g;
+  xs[g * E + j] = query[(size_t)row * E + j] + query_pos[(size_t)(row % Q) * E + j];
   __syncthreads();
-  float o[R];
-  matvec_rows<R>(wqT, E, bq, xs, E, j, o);
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (row0 + r < rows) qh[(size_t)(row0 + r) * E + j] = o[r] * scale;
+  qh[(size_t)row * E + j] = matvec4(wqT, E, bq, xs, E, j, g, E, part) * scale;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Cross-attention tail + self-attention in-projection, R rows per CTA, thread j <-> channel j (= head j/32, dim j%32):
+// Cross-attention tail + self-attention in-projection (thread (j, g): channel j = head j/32, dim j%32, of row row0+g):
 //   merge the key-chunk partials -> out_proj -> + identity -> LN(norms.0) -> query1
 //   self-attn in_proj: q = ((query1+pos) Wq^T + bq) * hd^-0.5, k = (query1+pos) Wk^T + bk, v = query1 Wv^T + bv
-template <int R>
-__global__ void __launch_bounds__(256)
-cross_merge_kernel(const float* __restrict__ part, int nchunk, int H, const float* __restrict__ query,
+__global__ void __launch_bounds__(1024)
+cross_merge_kernel(const float* __restrict__ part_in, int nchunk, int H, const float* __restrict__ query,
                    const float* __restrict__ query_pos, int Q, const float* __restrict__ woT,
                    const float* __restrict__ bo, const float* __restrict__ n0w, const float* __restrict__ n0b,
                    const float* __restrict__ sa_inT /*(E, 3E) K-major*/, const float* __restrict__ sa_inb, float scale,
                    float* __restrict__ query1, float* __restrict__ sa_qkv /*(rows, 3E)*/, int rows, int E) {
-  extern __shared__ float sm[];  // xs[R*E], ps[R*E], red[32]
+  extern __shared__ float sm[];  // xs[QG*E], ps[QG*E], part[QG*QG*E], red[32]
   float* xs = sm;
-  float* ps = sm + R * E;
-  float* red = ps + R * E;
-  const int j = threadIdx.x;
+  float* ps = xs + QG * E;
+  float* part = ps + QG * E;
+  float* red = part + QG * QG * E;
+  const int j = threadIdx.x % E, g = threadIdx.x / E;
   const int h = j / XA_HD, d = j % XA_HD;
-  const int row0 = blockIdx.x * R;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int row = row0 + r;
-    float o = 0.f;
-    if (row < rows) {
-      const int b = row / Q, t = row % Q;
-      const float* p = part + (((size_t)b * H + h) * nchunk * Q + t) * (XA_HD + 2);
-      const size_t cstride = (size_t)Q * (XA_HD + 2);
-      float M = -INFINITY;
-      for (int c = 0; c < nchunk; ++c) M = fmaxf(M, p[c * cstride]);
-      float L = 0.f, A = 0.f;
-      for (int c = 0; c < nchunk; ++c) {
-        const float mc = p[c * cstride];
-        if (mc == -INFINITY) continue;
-        const float w = __expf(mc - M);
-        L = fmaf(p[c * cstride + 1], w, L);
-        A = fmaf(p[c * cstride + 2 + d], w, A);
-      }
-      o = A / L;
+  const int row = blockIdx.x * QG + g;
+  {
+    const int b = row / Q, t = row % Q;
+    const float* p = part_in + (((size_t)b * H + h) * nchunk * Q + t) * (XA_HD + 2);
+    const size_t cstride = (size_t)Q * (XA_HD + 2);
+    float M = -INFINITY;
+    for (int c = 0; c < nchunk; ++c) M = fmaxf(M, __ldg(p + c * cstride));
+    float L = 0.f, A = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < nchunk; ++c) {
+      const float mc = __ldg(p + c * cstride);
+      const float w = (mc == -INFINITY) ? 0.f : __expf(mc - M);
+      L = fmaf(__ldg(p + c * cstride + 1), w, L);
+      A = fmaf(__ldg(p + c * cstride + 2 + d), w, A);
     }
-    xs[r * E + j] = o;
+    xs[g * E + j] = A / L;
   }
   __syncthreads();
-  float x[R];
-  matvec_rows<R>(woT, E, bo, xs, E, j, x);
-#pragma unroll
-  for (int r = 0; r < R; ++r) x[r] += (row0 + r < rows) ? query[(size_t)(row0 + r) * E + j] : 0.f;
-  block_layernorm<R>(x, E, n0w, n0b, red);
+  float x = matvec4(woT, E, bo, xs, E, j, g, E, part) + query[(size_t)row * E + j];
+  x = group_layernorm(x, g, j, E, n0w, n0b, red);
+  query1[(size_t)row * E + j] = x;
   __syncthreads();
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int row = row0 + r;
-    if (row < rows) query1[(size_t)row * E + j] = x[r];
-    xs[r * E + j] = x[r];
-    ps[r * E + j] = x[r] + (row < rows ? query_pos[(size_t)(row % Q) * E + j] : 0.f);
-  }
+  xs[g * E + j] = x;
+  ps[g * E + j] = x + query_pos[(size_t)(row % Q) * E + j];
   __syncthreads();
-  float o[R];
-  matvec_rows<R>(sa_inT, 3 * E, sa_inb, ps, E, j, o);
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (row0 + r < rows) sa_qkv[(size_t)(row0 + r) * 3 * E + j] = o[r] * scale;
-  matvec_rows<R>(sa_inT + E, 3 * E, sa_inb + E, ps, E, j, o);
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (row0 + r < rows) sa_qkv[(size_t)(row0 + r) * 3 * E + E + j] = o[r];
-  matvec_rows<R>(sa_inT + 2 * E, 3 * E, sa_inb + 2 * E, xs, E, j, o);
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (row0 + r < rows) sa_qkv[(size_t)(row0 + r) * 3 * E + 2 * E + j] = o[r];
+  float* dst = sa_qkv + (size_t)row * 3 * E;
+  dst[j] = matvec4(sa_inT, 3 * E, sa_inb, ps, E, j, g, E, part) * scale;
+  dst[E + j] = matvec4(sa_inT + E, 3 * E, sa_inb + E, ps, E, j, g, E, part);
+  dst[2 * E + j] = matvec4(sa_inT + 2 * E, 3 * E, sa_inb + 2 * E, xs, E, j, g, E, part);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Self-attention over the Q queries + out_proj + LN(norms.1) + FFN (ReLU) + LN(norms.2); one row per CTA,
-// warp w <-> head w (hd = 32 = warp size), then thread j <-> channel j.
-__global__ void __launch_bounds__(256)
+// Self-attention over the Q queries + out_proj + LN(norms.1) + FFN (ReLU) + LN(norms.2).  Thread (j, g): row row0+g,
+// warp j/32 of the group <-> head (hd = 32 = warp size), then channel j.
+__global__ void __launch_bounds__(1024)
 self_attn_ffn_kernel(const float* __restrict__ sa_qkv, const float* __restrict__ query1, int Q,
                      const float* __restrict__ woT, const float* __restrict__ bo, const float* __restrict__ n1w,
                      const float* __restrict__ n1b, const float* __restrict__ f1T /*(E, F)*/,
                      const float* __restrict__ f1b, const float* __restrict__ f2T /*(F, E)*/,
                      const float* __restrict__ f2b, int F, const float* __restrict__ n2w,
                      const float* __restrict__ n2b, float* __restrict__ query_out, int E) {
-  extern __shared__ float sm[];  // xs[E], hs[F], red[32]
+  extern __shared__ float sm[];  // xs[QG*E], part[QG*QG*E], red[32], hs[QG*F]
   float* xs = sm;
-  float* hs = sm + E;
-  float* red = hs + F;
-  const int j = threadIdx.x, lane = j & 31, h = j >> 5;
-  const int row = blockIdx.x;
+  float* part = xs + QG * E;
+  float* red = part + QG * QG * E;
+  float* hs = red + 32;
+  const int j = threadIdx.x % E, g = threadIdx.x / E;
+  const int lane = j & 31, h = j >> 5;
+  const int row = blockIdx.x * QG + g;
   const int b = row / Q;
   const float* base = sa_qkv + (size_t)b * Q * 3 * E;
   // scores of this head: lane handles keys lane, lane+32, lane+64, lane+96
@@ -445,7 +410,6 @@ self_attn_ffn_kernel(const float* __restrict__ sa_qkv, const float* __restrict__
     sum += sc[i];
   }
   sum = warp_sum_f(sum);
-  const float inv = 1.0f / sum;
   float o = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -455,26 +419,33 @@ self_attn_ffn_kernel(const float* __restrict__ sa_qkv, const float* __restrict__
       if (key < Q) o = fmaf(p, base[(size_t)key * 3 * E + 2 * E + j], o);
     }
   }
-  xs[j] = o * inv;
+  xs[g * E + j] = o / sum;
   __syncthreads();
-  float x[1];
-  matvec_rows<1>(woT, E, bo, xs, E, j, x);
-  x[0] += query1[(size_t)row * E + j];
-  block_layernorm<1>(x, E, n1w, n1b, red);
+  float x = matvec4(woT, E, bo, xs, E, j, g, E, part) + query1[(size_t)row * E + j];
+  x = group_layernorm(x, g, j, E, n1w, n1b, red);
   __syncthreads();
-  xs[j] = x[0];
+  xs[g * E + j] = x;
   __syncthreads();
-  for (int f = j; f < F; f += E) {
-    float a[1];
-    matvec_rows<1>(f1T, F, f1b, xs, E, f, a);
-    hs[f] = fmaxf(a[0], 0.f);
+  // FFN layer 1: F = nf*E hidden columns f = j + E*c; column block c is computed by group c % QG for all four rows
+  for (int c = g; c * E < F; c += QG) {
+    const int f = c * E + j;
+    float a[QG];
+#pragma unroll
+    for (int r = 0; r < QG; ++r) a[r] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < E; ++k) {
+      const float w = __ldg(f1T + (size_t)k * F + f);
+#pragma unroll
+      for (int r = 0; r < QG; ++r) a[r] = fmaf(w, xs[r * E + k], a[r]);
+    }
+    const float bb = __ldg(f1b + f);
+#pragma unroll
+    for (int r = 0; r < QG; ++r) hs[r * F + f] = fmaxf(a[r] + bb, 0.f);
   }
   __syncthreads();
-  float y[1];
-  matvec_rows<1>(f2T, E, f2b, hs, F, j, y);
-  y[0] += x[0];
-  block_layernorm<1>(y, E, n2w, n2b, red);
-  query_out[(size_t)row * E + j] = y[0];
+  float y = matvec4(f2T, E, f2b, hs, F, j, g, E, part) + x;
+  y = group_layernorm(y, g, j, E, n2w, n2b, red);
+  query_out[(size_t)row * E + j] = y;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -666,16 +637,14 @@ extern "C" int occ_head_prep(const float* in, int in_channel_last, const float* 
   return OCC_OK;
 }
 
-constexpr int QH_ROWS = 4;
-
 extern "C" int occ_query_head(const float* query, const float* pn_w, const float* pn_b, const float* clsT,
                               const float* cls_b, int NC, const float* m0T, const float* m0b, const float* m1T,
                               const float* m1b, const float* m2T, const float* m2b, float* cls_out, float* membed_out,
                               int rows, int E, cudaStream_t stream) {
   OCC_REQUIRE(query && pn_w && pn_b && clsT && cls_b && m0T && m0b && m1T && m1b && m2T && m2b && cls_out && membed_out);
-  OCC_REQUIRE(rows > 0 && E % 32 == 0 && E <= 256 && NC > 0 && NC <= E);
-  const size_t smem = (2 * QH_ROWS * E + 32) * sizeof(float);
-  query_head_kernel<QH_ROWS><<<(rows + QH_ROWS - 1) / QH_ROWS, E, smem, stream>>>(
+  OCC_REQUIRE(rows > 0 && rows % QG == 0 && E % 32 == 0 && E <= 256 && NC > 0 && NC <= E);
+  const size_t smem = ((QG + QG * QG) * E + 32) * sizeof(float);
+  query_head_kernel<<<rows / QG, E * QG, smem, stream>>>(
       query, pn_w, pn_b, clsT, cls_b, NC, m0T, m0b, m1T, m1b, m2T, m2b, cls_out, membed_out, rows, E);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
@@ -698,7 +667,7 @@ extern "C" int occ_mask_pool(const float* mask, float* pooled, int* row_flag, in
 extern "C" int occ_cross_attn_chunks(int S, int* chunk, int* nchunk) {
   // chunk size: multiple of XA_TILE, at most 64 chunks... enough CTAs (chunks * heads * B) to fill the machine
   int c = XA_TILE * 4;  // 256 keys
-  while ((S + c - 1) / c > 512) c *= 2;
+  while ((S + c - 1) / c > 96) c *= 2;
   *chunk = c;
   *nchunk = (S + c - 1) / c;
   return OCC_OK;
@@ -719,10 +688,9 @@ extern "C" int occ_cross_attn_partial(const float* qh, const float* Kp, const fl
 
 extern "C" int occ_query_proj(const float* query, const float* query_pos, int Q, const float* wqT, const float* bq,
                               float scale, float* qh, int rows, int E, cudaStream_t stream) {
-  OCC_REQUIRE(query && query_pos && wqT && bq && qh && rows > 0 && Q > 0 && E % 32 == 0 && E <= 256);
-  const size_t smem = QH_ROWS * E * sizeof(float);
-  query_proj_kernel<QH_ROWS><<<(rows + QH_ROWS - 1) / QH_ROWS, E, smem, stream>>>(query, query_pos, Q, wqT, bq, scale, qh,
-                                                                                  rows, E);
+  OCC_REQUIRE(query && query_pos && wqT && bq && qh && rows > 0 && rows % QG == 0 && Q > 0 && E % 32 == 0 && E <= 256);
+  const size_t smem = (QG + QG * QG) * E * sizeof(float);
+  query_proj_kernel<<<rows / QG, E * QG, smem, stream>>>(query, query_pos, Q, wqT, bq, scale, qh, rows, E);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -732,9 +700,9 @@ extern "C" int occ_cross_merge(const float* part, int nchunk, int H, const float
                                const float* sa_inT, const float* sa_inb, float scale, float* query1, float* sa_qkv,
                                int rows, int E, cudaStream_t stream) {
   OCC_REQUIRE(part && query && query_pos && woT && bo && n0w && n0b && sa_inT && sa_inb && query1 && sa_qkv);
-  OCC_REQUIRE(rows > 0 && Q > 0 && E == H * XA_HD && E <= 256 && nchunk > 0);
-  const size_t smem = (2 * QH_ROWS * E + 32) * sizeof(float);
-  cross_merge_kernel<QH_ROWS><<<(rows + QH_ROWS - 1) / QH_ROWS, E, smem, stream>>>(
+  OCC_REQUIRE(rows > 0 && rows % QG == 0 && Q > 0 && E == H * XA_HD && E <= 256 && nchunk > 0);
+  const size_t smem = ((2 * QG + QG * QG) * E + 32) * sizeof(float);
+  cross_merge_kernel<<<rows / QG, E * QG, smem, stream>>>(
       part, nchunk, H, query, query_pos, Q, woT, bo, n0w, n0b, sa_inT, sa_inb, scale, query1, sa_qkv, rows, E);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
@@ -746,10 +714,16 @@ extern "C" int occ_self_attn_ffn(const float* sa_qkv, const float* query1, int Q
                                  float* query_out, int rows, int E, int H, cudaStream_t stream) {
   OCC_REQUIRE(E == H * XA_HD);
   OCC_REQUIRE(sa_qkv && query1 && woT && bo && n1w && n1b && f1T && f1b && f2T && f2b && n2w && n2b && query_out);
-  OCC_REQUIRE(rows > 0 && Q > 0 && Q <= 128 && E % 32 == 0 && E <= 256 && F > 0 && rows % Q == 0);
-  const size_t smem = (E + F + 32) * sizeof(float);
-  OCC_REQUIRE(smem <= 48 * 1024);
-  self_attn_ffn_kernel<<<rows, E, smem, stream>>>(sa_qkv, query1, Q, woT, bo, n1w, n1b, f1T, f1b, f2T, f2b, F, n2w, n2b,
+  OCC_REQUIRE(rows > 0 && rows % QG == 0 && Q > 0 && Q <= 128 && E % 32 == 0 && E <= 256 && F > 0 && F % E == 0 &&
+              rows % Q == 0);
+  const size_t smem = ((QG + QG * QG) * E + 32 + (size_t)QG * F) * sizeof(float);
+  OCC_REQUIRE(smem <= 96 * 1024);
+  static bool configured = false;
+  if (!configured) {
+    OCC_CUDA(cudaFuncSetAttribute(self_attn_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  self_attn_ffn_kernel<<<rows / QG, E * QG, smem, stream>>>(sa_qkv, query1, Q, woT, bo, n1w, n1b, f1T, f1b, f2T, f2b, F, n2w, n2b,
                                                   query_out, E);
   OCC_LAUNCH_CHECK();
   return OCC_OK;

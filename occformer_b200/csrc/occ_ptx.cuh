@@ -110,6 +110,20 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// MN-major 32-bit (tf32) operand: the only legal swizzle is SWIZZLE_128B_BASE32B (layout type 1): rows of 128 bytes
+// (32 consecutive MN elements of one k), atoms of 4 k-rows (512 B), 32-byte chunk c of row r stored at chunk
+// c ^ (r & 3) (byte-address bits [5,7) ^= bits [7,9)).  SBO = byte stride between 4-row k groups, LBO = byte stride
+// between 32-element MN blocks.
+__device__ __forceinline__ uint64_t make_sw128b32_mn_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  d |= 1ull << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+
 // Instruction descriptor for kind::tf32 (and kind::f16 with other format codes): D = F32.
 //   c_format [4,6)=1 (F32), a_format [7,10), b_format [10,13) (2 = TF32), a_major bit 15, b_major bit 16
 //   (0 = K-major, 1 = MN-major), N>>3 in [17,23), M>>4 in [24,29).
@@ -164,6 +178,37 @@ __device__ __forceinline__ float round_tf32(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+}
+
+}  // namespace occ
+
+// ------------------------------------------------------------------ additions for the window-attention kernel
+namespace occ {
+
+// 32 registers per thread -> 32 lanes x 32 consecutive 32-bit TMEM columns (thread i <-> lane base+i)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 16-byte cp.async (LDGSTS) global -> shared, L1 bypass
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 }  // namespace occ

@@ -1,4 +1,5 @@
-// Shifted-window multi-head self-attention core over the B*(Z+1) X-Y images of the dual-path encoder.
+// Shifted-window multi-head self-attention core over the B*(Z+1) X-Y images of the dual-path encoder, on the
+// 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators and the probability operand in TMEM).
 //
 // Replaces ShiftWindowMSA.forward's pad / roll / mask build / window_partition / window_reverse / roll back /
 // crop and WindowMSA.forward's score pipeline (q*scale, QK^T, + relative-position bias, + shift mask, softmax,
@@ -7,12 +8,23 @@
 // from the token-ordered qkv tensor and scatters the result back to token order.  No (nW,49,49) mask tensor,
 // no score tensor in HBM.
 //
-// Semantics kept bit-for-bit in structure:
+// Semantics kept:
 //   * padding to a multiple of 7 happens AFTER LayerNorm: pad tokens are zeros, so their q/k/v equal the qkv
 //     bias and they take part in the softmax as real keys; their outputs are cropped.
 //   * shifted blocks: roll(-3,-3); region ids from slices (0,-7),(-7,-3),(-3,None) on the padded extent;
 //     additive mask -100.0 (not -inf) where ids differ.
 //   * relative-position bias added after the q*scale product.
+//
+// Work unit = (pair of windows, head): M = 128 query rows (window A in rows 0..63, window B in rows 64..127, 49
+// real rows each).  Persistent CTA, 512 threads:
+//   warps 12-15  loaders : cp.async gather of the Q / K / V head slices (128 B per token) into 128B-swizzled
+//                          K-major tiles, 3-stage ring, + the head's relative-position bias and the token metadata
+//   warp 0       MMA     : S = Q K^T (4 x tcgen05.mma 128x128x8, operands in smem), then O = P V (16 x 128x32x8 with
+//                          P read from TMEM and V as an MN-major smem operand (SWIZZLE_128B_BASE32B) -- no transpose
+//                          of V anywhere)
+//   warps 4-7 / 8-11     : two softmax warpgroups (even / odd units): tcgen05.ld S row -> scale, bias, shift mask,
+//                          softmax in registers -> tcgen05.st P (block-diagonal: the other window's columns are zero)
+//                          -> after PV: tcgen05.ld O, normalise, scatter 128 B per (token, head) to global.
 #include "occ_common.cuh"
 #include "occ_ptx.cuh"
 
@@ -21,13 +33,21 @@ namespace occ {
 constexpr int WS = 7;
 constexpr int WT = WS * WS;  // 49 tokens
 constexpr int HD = 32;       // head dim (multihead_base_channel, dualpath_block.py:32)
-constexpr int KV_LD = 36;    // smem row pitch (floats)
-constexpr int WARP_SMEM = 2 * WT * KV_LD + ((WT * WT + 3) / 4) * 4;  // floats per warp, 16-byte multiple
+constexpr int WA_STAGES = 3;
+constexpr int WA_TILE = 128 * HD * 4;                  // 16 KB: 128 rows x 128 B
+constexpr int WA_BIAS_FLOATS = 2404;                   // 49*49 padded to a 16-byte multiple
+constexpr int WA_OFF_BIAS = 3 * WA_TILE;               // 49152
+constexpr int WA_OFF_ROWS = WA_OFF_BIAS + WA_BIAS_FLOATS * 4;  // 58768 (8-byte aligned)
+constexpr int WA_OFF_REGION = WA_OFF_ROWS + 128 * 8;   // 59792
+constexpr int WA_STAGE_BYTES = 60 * 1024;              // 61440 >= 59792 + 512, multiple of 1024
+constexpr int WA_THREADS = 512;
+constexpr uint32_t WA_TMEM_COLS = 512;                 // S/P: 2 x 128, O: 2 x 32
 
 struct WinGeom {
   int B, X, Y, Z, C, heads, shift;
   int Xp, Yp, nWx, nWy;
   long long vox_rows;  // B*X*Y*Z
+  long long nwin;
 };
 
 // token t of window (img, wx, wy) -> global token row (or -1 for a pad token) and shift-mask region id
@@ -53,93 +73,253 @@ __device__ __forceinline__ long long window_token_row(const WinGeom& g, int img,
   return g.vox_rows + ((long long)b * g.X + x) * g.Y + y;
 }
 
-// SIMT version: one warp per (window, head); lane = query row (two passes for 49 rows).
-__global__ void __launch_bounds__(128)
-window_attn_simt_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
-                        const float* __restrict__ bias_dense /*(heads,49,49)*/, float* __restrict__ out, WinGeom g) {
-  extern __shared__ __align__(16) float smem[];
-  __shared__ long long s_row[WT];
-  __shared__ int s_region[WT];
+__global__ void __launch_bounds__(WA_THREADS, 1)
+window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
+                      const float* __restrict__ bias_pad /*(heads, 2404)*/, float* __restrict__ out, const WinGeom g,
+                      float* __restrict__ dbg /*optional (128, 192) dump of unit 0 of CTA 0*/) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WA_STAGES * WA_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + WA_STAGES;
+  uint64_t* s_ready = empty_bar + WA_STAGES;  // [2]
+  uint64_t* p_ready = s_ready + 2;            // [2]
+  uint64_t* o_ready = p_ready + 2;            // [2]
+  uint64_t* o_free = o_ready + 2;             // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 2);
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y * 4 + warp;
-  int w = blockIdx.x;
-  const int wy = w % g.nWy; w /= g.nWy;
-  const int wx = w % g.nWx; w /= g.nWx;
-  const int img = w;
-  if (threadIdx.x < WT) {
-    int region;
-    s_row[threadIdx.x] = window_token_row(g, img, wx, wy, threadIdx.x, &region);
-    s_region[threadIdx.x] = region;
+  const long long npairs = (g.nwin + 1) / 2;
+  const int H = g.heads;
+  // units of this CTA: pairs blockIdx.x, +gridDim.x, ...; heads innermost
+  const long long my_pairs = (npairs > blockIdx.x) ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long n_units = my_pairs * H;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < WA_STAGES; ++i) {
+      mbar_init(&full_bar[i], 4);   // one elected arrive per loader warp
+      mbar_init(&empty_bar[i], 1);  // tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_ready[i], 1);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&o_ready[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
+    fence_barrier_init();
   }
+  if (warp == 2) tmem_alloc<WA_TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
   __syncthreads();
-  if (head >= g.heads) return;
-  float* sk = smem + (size_t)warp * WARP_SMEM;
-  float* sv = sk + WT * KV_LD;
-  float* sb = sv + WT * KV_LD;
-  const int C = g.C;
-  const int qoff = head * HD, koff = C + head * HD, voff = 2 * C + head * HD;
-  for (int t = 0; t < WT; ++t) {
-    const long long r = s_row[t];
-    const float* src = r >= 0 ? qkv + r * 3 * C : qkv_bias;
-    sk[t * KV_LD + lane] = src[koff + lane];
-    sv[t * KV_LD + lane] = src[voff + lane];
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp >= 12) {
+    // ===================================================================== loaders
+    const int l = threadIdx.x - 12 * 32;  // 0..127
+    const int C = g.C;
+    auto issue = [&](long long u) {
+      const int s = (int)(u % WA_STAGES);
+      const long long pair = blockIdx.x + (u / H) * gridDim.x;
+      const int h = (int)(u % H);
+      uint8_t* st = smem + (size_t)s * WA_STAGE_BYTES;
+      long long* rows = reinterpret_cast<long long*>(st + WA_OFF_ROWS);
+      int* region = reinterpret_cast<int*>(st + WA_OFF_REGION);
+      mbar_wait(&empty_bar[s], (uint32_t)(((u / WA_STAGES) & 1) ^ 1));
+      {  // metadata of row l: window = 2*pair + l/64, token = l%64
+        const long long win = 2 * pair + (l >> 6);
+        const int t = l & 63;
+        long long r = -2;  // -2: MMA padding row (zero), -1: window pad token (qkv = bias)
+        int reg = 0;
+        if (t < WT && win < g.nwin) {
+          long long w = win;
+          const int wy = (int)(w % g.nWy); w /= g.nWy;
+          const int wx = (int)(w % g.nWx); w /= g.nWx;
+          r = window_token_row(g, (int)w, wx, wy, t, &reg);
+        }
+        rows[l] = r;
+        region[l] = reg;
+      }
+      named_bar_sync(2, 128);
+#pragma unroll 4
+      for (int i = 0; i < 24; ++i) {
+        const int idx = i * 128 + l;
+        const int tile = idx >> 10, rem = idx & 1023;
+        const int r = rem >> 3, c = rem & 7;
+        // Q, K: K-major SWIZZLE_128B (16-byte chunk c ^ (r & 7)); V: MN-major tf32 operand = SWIZZLE_128B_BASE32B
+        // (32-byte chunk (c >> 1) ^ (r & 3)) -- the only legal layout for a transposed 32-bit operand
+        const int off = tile < 2 ? ((c ^ (r & 7)) << 4) : ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));
+        uint8_t* dst = st + tile * WA_TILE + r * 128 + off;
+        const long long row = rows[r];
+        if (row == -2) {
+          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          const float* src = (row >= 0 ? qkv + row * 3 * C : qkv_bias) + tile * C + h * HD + c * 4;
+          cp_async_16(dst, src);
+        }
+      }
+      {
+        float* sb = reinterpret_cast<float*>(st + WA_OFF_BIAS);
+        const float* gb = bias_pad + (size_t)h * WA_BIAS_FLOATS;
+        for (int i = l; i < WA_BIAS_FLOATS / 4; i += 128) cp_async_16(sb + 4 * i, gb + 4 * i);
+      }
+      cp_async_commit();
+    };
+    if (n_units > 0) issue(0);
+    for (long long u = 0; u < n_units; ++u) {
+      if (u + 1 < n_units) {
+        issue(u + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[u % WA_STAGES]);
+    }
+  } else if (warp == 0) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC_QK = make_idesc_tf32(128, 128, 0, 0);
+      constexpr uint32_t IDESC_PV = make_idesc_tf32(128, HD, 0, 1);  // B = V tile, MN-major (d contiguous)
+      auto do_pv = [&](long long v) {
+        const int tb = (int)(v & 1), s = (int)(v % WA_STAGES);
+        const uint32_t k = (uint32_t)(v >> 1);
+        mbar_wait(&p_ready[tb], k & 1);
+        mbar_wait(&o_free[tb], (k & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t vaddr = smem_u32(smem + (size_t)s * WA_STAGE_BYTES + 2 * WA_TILE);
+        const uint64_t vdesc = make_sw128b32_mn_desc(vaddr, 512, 512);
+        const uint32_t p_tmem = tmem_base + tb * 128;
+        const uint32_t o_tmem = tmem_base + 256 + tb * HD;
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk)  // 8 keys per MMA = two 4-row (512 B) swizzle atoms of V rows
+          mma_tf32_ts(o_tmem, p_tmem + kk * 8, vdesc + (uint64_t)(kk * 64), IDESC_PV, kk != 0);
+        mma_commit(&o_ready[tb]);
+        mma_commit(&empty_bar[s]);
+      };
+      for (long long u = 0; u < n_units; ++u) {
+        const int tb = (int)(u & 1), s = (int)(u % WA_STAGES);
+        mbar_wait(&full_bar[s], (uint32_t)((u / WA_STAGES) & 1));
+        tc_fence_after();
+        const uint32_t qaddr = smem_u32(smem + (size_t)s * WA_STAGE_BYTES);
+        const uint64_t qdesc = make_sw128_desc(qaddr, 1024, 16);
+        const uint64_t kdesc = make_sw128_desc(qaddr + WA_TILE, 1024, 16);
+        const uint32_t s_tmem = tmem_base + tb * 128;
+#pragma unroll
+        for (int kk = 0; kk < HD / 8; ++kk) mma_tf32_ss(s_tmem, qdesc + 2 * kk, kdesc + 2 * kk, IDESC_QK, kk != 0);
+        mma_commit(&s_ready[tb]);
+        if (u > 0) do_pv(u - 1);
+      }
+      if (n_units > 0) do_pv(n_units - 1);
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===================================================================== softmax / epilogue warpgroups
+    const int wg = (warp - 4) >> 2;                 // 0: even units, 1: odd units
+    const int i = ((warp & 3) << 5) + lane;         // query row = TMEM lane 0..127
+    const int half = i >> 6, t = i & 63;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const float scale = 0.17677669529663687f;  // 32^-0.5
+    const int tb = wg;
+    for (long long u = wg; u < n_units; u += 2) {
+      const int s = (int)(u % WA_STAGES);
+      const uint32_t k = (uint32_t)(u >> 1);
+      const int h = (int)(u % H);
+      const uint8_t* st = smem + (size_t)s * WA_STAGE_BYTES;
+      const float* sb = reinterpret_cast<const float*>(st + WA_OFF_BIAS);
+      const long long* rows = reinterpret_cast<const long long*>(st + WA_OFF_ROWS);
+      const int* region = reinterpret_cast<const int*>(st + WA_OFF_REGION);
+      mbar_wait(&s_ready[tb], k & 1);
+      tc_fence_after();
+      const long long my_row = rows[i];
+      const int my_reg = region[i];
+      const float* brow = sb + (t < WT ? t : 0) * WT;
+      const int* kreg = region + half * 64;
+      const uint32_t s_col = lane_base + tb * 128 + half * 64;
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(s_col, ra);
+      tmem_ld_32x32(s_col + 32, rb);
+      tmem_ld_wait();
+      if (dbg && u == 0 && blockIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { dbg[i * 192 + j] = __uint_as_float(ra[j]); dbg[i * 192 + 32 + j] = __uint_as_float(rb[j]); }
+      }
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float z = fmaf(__uint_as_float(ra[j]), scale, brow[j]);
+        if (kreg[j] != my_reg) z += -100.0f;
+        ra[j] = __float_as_uint(z);
+        m = fmaxf(m, z);
+      }
+#pragma unroll
+      for (int j = 0; j < WT - 32; ++j) {
+        float z = fmaf(__uint_as_float(rb[j]), scale, brow[32 + j]);
+        if (kreg[32 + j] != my_reg) z += -100.0f;
+        rb[j] = __float_as_uint(z);
+        m = fmaxf(m, z);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float p = round_tf32(__expf(__uint_as_float(ra[j]) - m));
+        sum += p;
+        ra[j] = __float_as_uint(p);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float p = 0.f;
+        if (j < WT - 32) {
+          p = round_tf32(__expf(__uint_as_float(rb[j]) - m));
+          sum += p;
+        }
+        rb[j] = __float_as_uint(p);
+      }
+      if (dbg && u == 0 && blockIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { dbg[i * 192 + 64 + j] = __uint_as_float(ra[j]); dbg[i * 192 + 96 + j] = __uint_as_float(rb[j]); }
+        dbg[i * 192 + 160] = sum; dbg[i * 192 + 161] = m; dbg[i * 192 + 162] = (float)my_row; dbg[i * 192 + 163] = (float)my_reg;
+      }
+      // P row: own window's 64 key columns, zeros in the other window's 64 columns (block-diagonal)
+      tmem_st_32x32(s_col, ra);
+      tmem_st_32x32(s_col + 32, rb);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ra[j] = 0u;
+      const uint32_t o_col = lane_base + tb * 128 + (half ^ 1) * 64;
+      tmem_st_32x32(o_col, ra);
+      tmem_st_32x32(o_col + 32, ra);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[tb]);
+      // ---- epilogue of the same unit once PV has landed
+      mbar_wait(&o_ready[tb], k & 1);
+      tc_fence_after();
+      tmem_ld_32x32(lane_base + 256 + tb * HD, ra);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[tb]);
+      if (dbg && u == 0 && blockIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dbg[i * 192 + 128 + j] = __uint_as_float(ra[j]);
+      }
+      if (t < WT && my_row >= 0) {
+        const float inv = 1.0f / sum;
+        float4* dst = reinterpret_cast<float4*>(out + my_row * g.C + h * HD);
+#pragma unroll
+        for (int d = 0; d < HD; d += 4)
+          dst[d >> 2] = make_float4(round_tf32(__uint_as_float(ra[d]) * inv), round_tf32(__uint_as_float(ra[d + 1]) * inv),
+                                    round_tf32(__uint_as_float(ra[d + 2]) * inv), round_tf32(__uint_as_float(ra[d + 3]) * inv));
+      }
+    }
   }
-  for (int i = lane; i < WT * WT; i += 32) sb[i] = bias_dense[(size_t)head * WT * WT + i];
-  __syncwarp();
-  const float scale = 0.17677669529663687f;  // 32^-0.5
-  for (int pass = 0; pass < 2; ++pass) {
-    const int i = pass * 32 + lane;
-    if (i >= WT) break;
-    const long long r = s_row[i];
-    const float* qsrc = (r >= 0 ? qkv + r * 3 * C : qkv_bias) + qoff;
-    float q[HD];
-#pragma unroll
-    for (int d = 0; d < HD; d += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(qsrc + d);
-      q[d] = t.x * scale; q[d + 1] = t.y * scale; q[d + 2] = t.z * scale; q[d + 3] = t.w * scale;
-    }
-    float s[WT];
-    const int reg_i = s_region[i];
-    float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < WT; ++j) {
-      float a = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; d += 4) {
-        const float4 kk = *reinterpret_cast<const float4*>(sk + j * KV_LD + d);
-        a += q[d] * kk.x + q[d + 1] * kk.y + q[d + 2] * kk.z + q[d + 3] * kk.w;
-      }
-      a += sb[i * WT + j];
-      if (s_region[j] != reg_i) a += -100.0f;
-      s[j] = a;
-      m = fmaxf(m, a);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < WT; ++j) {
-      s[j] = expf(s[j] - m);
-      sum += s[j];
-    }
-    const float inv = 1.0f / sum;
-    float o[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
-#pragma unroll
-    for (int j = 0; j < WT; ++j) {
-      const float pj = s[j] * inv;
-#pragma unroll
-      for (int d = 0; d < HD; d += 4) {
-        const float4 vv = *reinterpret_cast<const float4*>(sv + j * KV_LD + d);
-        o[d] += pj * vv.x; o[d + 1] += pj * vv.y; o[d + 2] += pj * vv.z; o[d + 3] += pj * vv.w;
-      }
-    }
-    if (r >= 0) {
-      float* dst = out + r * C + head * HD;
-#pragma unroll
-      for (int d = 0; d < HD; d += 4)
-        *reinterpret_cast<float4*>(dst + d) =
-            make_float4(round_tf32(o[d]), round_tf32(o[d + 1]), round_tf32(o[d + 2]), round_tf32(o[d + 3]));
-    }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<WA_TMEM_COLS>(tmem_base);
   }
 }
 
@@ -147,27 +327,38 @@ window_attn_simt_kernel(const float* __restrict__ qkv, const float* __restrict__
 
 using namespace occ;
 
-// qkv (rows, 3C) with rows = B*X*Y*(Z+1) token-ordered (voxel tokens then BEV tokens); out (rows, C).
-// bias_dense = relative_position_bias_table[relative_position_index] arranged (heads, 49, 49).
-extern "C" int occ_window_attention(const float* qkv, const float* qkv_bias, const float* bias_dense, float* out, int B,
+static float* g_wattn_dbg = nullptr;
+
+// qkv (rows, 3C) with rows = B*X*Y*(Z+1) token-ordered (voxel tokens then BEV tokens); out (rows, C), tf32-rounded.
+// bias_pad = relative_position_bias_table[relative_position_index] arranged (heads, 49*49 padded to 2404 floats).
+extern "C" int occ_window_attention(const float* qkv, const float* qkv_bias, const float* bias_pad, float* out, int B,
                                     int X, int Y, int Z, int C, int heads, int shift, cudaStream_t stream) {
-  OCC_REQUIRE(qkv && qkv_bias && bias_dense && out);
+  OCC_REQUIRE(qkv && qkv_bias && bias_pad && out);
   OCC_REQUIRE(B > 0 && X > 0 && Y > 0 && Z > 0 && heads > 0 && C == heads * HD);
+  OCC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv_bias) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(bias_pad) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   WinGeom g;
   g.B = B; g.X = X; g.Y = Y; g.Z = Z; g.C = C; g.heads = heads; g.shift = shift ? 1 : 0;
   g.nWx = (X + WS - 1) / WS; g.nWy = (Y + WS - 1) / WS;
   g.Xp = g.nWx * WS; g.Yp = g.nWy * WS;
   g.vox_rows = (long long)B * X * Y * Z;
-  const long long nwin = (long long)B * (Z + 1) * g.nWx * g.nWy;
-  OCC_REQUIRE(nwin < (1ll << 31));
-  const size_t smem = 4 * WARP_SMEM * sizeof(float);
+  g.nwin = (long long)B * (Z + 1) * g.nWx * g.nWy;
+  OCC_REQUIRE(g.nwin < (1ll << 31));
+  const size_t smem = (size_t)WA_STAGES * WA_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool configured = false;
   if (!configured) {
-    OCC_CUDA(cudaFuncSetAttribute(window_attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OCC_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((unsigned)nwin, (heads + 3) / 4);
-  window_attn_simt_kernel<<<grid, 128, smem, stream>>>(qkv, qkv_bias, bias_dense, out, g);
+  const long long npairs = (g.nwin + 1) / 2;
+  const int grid = (int)(npairs < sm_count() ? npairs : sm_count());
+  window_attn_tc_kernel<<<grid, WA_THREADS, smem, stream>>>(qkv, qkv_bias, bias_pad, out, g, g_wattn_dbg);
   OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+// development aid: when set, unit 0 of CTA 0 dumps its score / probability / output rows to this (128,192) buffer
+extern "C" int occ_window_attention_set_debug(float* dbg) {
+  g_wattn_dbg = dbg;
   return OCC_OK;
 }

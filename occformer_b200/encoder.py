@@ -145,7 +145,8 @@ class DualpathTransformerBlock(nn.Module):
         P["w_f2"] = r(ffn[1].weight.detach().float().clone().contiguous())
         table = msa.relative_position_bias_table.detach().float()
         idx = msa.relative_position_index.view(-1)
-        P["bias_dense"] = table[idx].view(49, 49, -1).permute(2, 0, 1).contiguous()  # (heads,49,49)
+        dense = table[idx].view(49, 49, -1).permute(2, 0, 1).reshape(-1, 49 * 49)  # (heads, 49*49)
+        P["bias_pad"] = torch.nn.functional.pad(dense, (0, 2404 - 49 * 49)).contiguous()  # 16-byte multiple per head
         a = self.aspp
         P["w_a_in"], P["k1"] = ops.repack_conv_weight(a.input_conv[0].weight.detach().float())
         for i in (1, 2, 3, 4):
@@ -178,9 +179,9 @@ class DualpathTransformerBlock(nn.Module):
                                          sw.norm1.bias, B, XY, Z, C, G)
         msa = sw.attn.w_msa
         # (A8) QKV projection of every token (pad tokens are synthesised from the bias inside the attention kernel)
-        qkv = ops.gemm(tokn, P["w_qkv"], bias=msa.qkv.bias)
+        qkv = ops.gemm(tokn, P["w_qkv"], bias=msa.qkv.bias, round_out=True)
         # (A7/A8) shifted-window attention core, gathers/scatters windows in place
-        att = ops.window_attention(qkv, msa.qkv.bias, P["bias_dense"], B, X, Y, Z, C, self.num_heads, self.shift)
+        att = ops.window_attention(qkv, msa.qkv.bias, P["bias_pad"], B, X, Y, Z, C, self.num_heads, self.shift)
         # proj + residual, LayerNorm2, FFN (GELU) + residual  (A6)
         y1 = ops.gemm(att, P["w_proj"], bias=msa.proj.bias, residual=tok)
         y1n = ops.layernorm(y1, sw.norm2.weight, sw.norm2.bias, round_out=True)

@@ -251,12 +251,12 @@ def dualpath_fuse(x, bev, cw, cbias, identity, B, XY, Z, C, id_stats=None, id_w=
     return out
 
 
-def window_attention(qkv, qkv_bias, bias_dense, B, X, Y, Z, C, heads, shift):
+def window_attention(qkv, qkv_bias, bias_pad, B, X, Y, Z, C, heads, shift):
     _chk(qkv, "qkv")
     rows = B * X * Y * (Z + 1)
     assert qkv.shape == (rows, 3 * C)
     out = torch.empty((rows, C), dtype=torch.float32, device=qkv.device)
-    check(lib().occ_window_attention(_ptr(qkv), _ptr(qkv_bias), _ptr(bias_dense), _ptr(out), B, X, Y, Z, C, heads,
+    check(lib().occ_window_attention(_ptr(qkv), _ptr(qkv_bias), _ptr(bias_pad), _ptr(out), B, X, Y, Z, C, heads,
                                      int(shift), _stream()), "occ_window_attention")
     LAUNCH_COUNT[0] += 1
     return out

@@ -477,3 +477,29 @@ def head_simple_test(voxel_feats, sd, num_heads, num_layers, occ_size, num_level
 # generators, no arithmetic of the path); re-exported here so tests keep one entry point
 # =============================================================================
 from occformer_b200.synth import make_block_state, make_encoder_state, make_head_state  # noqa: E402,F401
+
+
+# =============================================================================
+# evaluation counts (the payload of the single metric all-gather)
+# =============================================================================
+def ssc_counts_ref(pred, target, num_classes):
+    """SSCMetrics.get_score_completion + get_score_semantic_and_completion, literal loops
+    (P/utils/ssc_metric.py:104-168) with mask = target != 255 and no nonempty mask."""
+    pred, target = pred.clone().long(), target.clone().long()
+    pred[target == 255] = 0
+    valid = target != 255
+    target[target == 255] = 0
+    bs = pred.shape[0]
+    p, t, m = pred.view(bs, -1), target.view(bs, -1), valid.view(bs, -1)
+    ctp = cfp = cfn = 0
+    tp = torch.zeros(num_classes, dtype=torch.long)
+    fp, fn = tp.clone(), tp.clone()
+    for i in range(bs):
+        yt, yp = t[i][m[i]], p[i][m[i]]
+        bt, bp = yt > 0, yp > 0
+        ctp += int((bt & bp).sum()); cfp += int((~bt & bp).sum()); cfn += int((bt & ~bp).sum())
+        for j in range(num_classes):
+            tp[j] += ((yt == j) & (yp == j)).sum()
+            fp[j] += ((yt != j) & (yp == j)).sum()
+            fn[j] += ((yt == j) & (yp != j)).sum()
+    return torch.cat([torch.tensor([ctp, cfp, cfn]), tp, fp, fn])

@@ -9,13 +9,14 @@ for s in "$@"; do
     gemmall) timeout 400 python -m pytest tests/test_gpu_gemm.py -q -m gpu > gpurun_out/t_gemm.log 2>&1; echo "gemm rc=$?" ;;
     pool)    timeout 300 python -m pytest tests/test_gpu_voxel_pool.py -q -m gpu -s > gpurun_out/t_pool.log 2>&1; echo "pool rc=$?" ;;
     encoder) timeout 600 python -m pytest tests/test_gpu_encoder.py -q -m gpu > gpurun_out/t_encoder.log 2>&1; echo "encoder rc=$?" ;;
+    wattn)   timeout 600 python -m pytest tests/test_gpu_window_attn.py -q -m gpu > gpurun_out/t_wattn.log 2>&1; echo "wattn rc=$?" ;;
     head)    timeout 600 python -m pytest tests/test_gpu_head.py -q -m gpu > gpurun_out/t_head.log 2>&1; echo "head rc=$?" ;;
     all)     timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/t_all.log 2>&1; echo "all rc=$?" ;;
     micro)   timeout 600 python scripts/microbench.py > gpurun_out/micro.log 2>&1; echo "micro rc=$?" ;;
     bench)   timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -n 3 gpurun_out/bench.log ;;
     benchref) timeout 900 python bench.py --impl reference --steps 2 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "benchref rc=$?"; tail -n 2 gpurun_out/bench_ref.log ;;
     smoke)   timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 3 gpurun_out/smoke.log ;;
-    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?" ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-1500} -c ${NCU_COUNT:-900} --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?" ;;
     ncu_*)   k=${s#ncu_}; timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 2 -f -o gpurun_out/prof_$k python scripts/microbench.py ${NCU_WHICH:-conv} > gpurun_out/ncu_$k.log 2>&1; echo "ncu $k rc=$?" ;;
     *) echo "unknown stage $s" ;;
   esac

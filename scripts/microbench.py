@@ -77,9 +77,10 @@ def main():
         M = X * Y * (Z + 1)
         qkv = torch.randn(M, 3 * C, device=dev)
         qb = torch.randn(3 * C, device=dev)
-        bd = torch.randn(4, 49, 49, device=dev)
+        bd = torch.randn(4, 2404, device=dev)
         t = timeit(lambda: ops.window_attention(qkv, qb, bd, 1, X, Y, Z, C, 4, True))
-        res["window_attn_simt_ms"] = t
+        res["window_attn_tc_ms"] = t
+        res["window_attn_GBps"] = (M * 3 * C * 4 + M * C * 4) / t / 1e6
     if "block" in which:
         from occformer_b200.encoder import OccupancyEncoder
         enc = OccupancyEncoder(in_channels=128, num_stage=4, block_numbers=[2, 2, 2, 2], block_inplanes=[128, 256, 512, 1024],

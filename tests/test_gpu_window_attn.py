@@ -1,0 +1,45 @@
+"""tcgen05 shifted-window attention core (occ_window_attention) vs the oracle's ShiftWindowMSA restatement
+(port.shift_window_msa with an identity output projection), on token-ordered qkv rows.  Operands are pre-rounded to
+exactly tf32-representable so that only the tf32 rounding of the probabilities and the accumulation order differ."""
+import pytest
+import torch
+
+from oracle import port
+from util import assert_close, round_tf32
+
+pytestmark = pytest.mark.gpu
+
+
+def _rows_from_images(img, B, X, Y, Z):
+    """img (B*(Z+1), X, Y, F): images (b,z) then the B BEV images -> token rows (voxel tokens, then BEV tokens)."""
+    F_ = img.shape[-1]
+    vox = img[:B * Z].view(B, Z, X, Y, F_).permute(0, 2, 3, 1, 4).reshape(B * X * Y * Z, F_)
+    bev = img[B * Z:].reshape(B * X * Y, F_)
+    return torch.cat([vox, bev], 0).contiguous()
+
+
+@pytest.mark.parametrize("B,X,Y,Z,C,shift", [(1, 14, 7, 1, 32, False), (1, 10, 16, 2, 128, True), (2, 15, 10, 4, 128, False),
+                                             (1, 9, 16, 2, 256, True), (1, 50, 50, 8, 128, True), (1, 7, 7, 1, 1024, True),
+                                             (1, 13, 13, 2, 512, False)])
+def test_window_attention_vs_oracle(cuda, B, X, Y, Z, C, shift):
+    from occformer_b200 import ops
+    heads = C // 32
+    g = torch.Generator().manual_seed(B * 1000 + X * 10 + C)
+    nimg = B * (Z + 1)
+    # operands that are exactly tf32-representable on both sides: x and the bias live on a 2^-6 grid and the qkv
+    # projection is three stacked identities, so q = k = v = x + b exactly (the kernel's tensor cores see the same values
+    # as the fp32 oracle; what remains is the tf32 rounding of the probabilities and the accumulation order)
+    x = (torch.randn(nimg, X * Y, C, generator=g) * 64).round().clamp(-255, 255) / 64
+    sd = {"w_msa.qkv.weight": torch.cat([torch.eye(C)] * 3, 0),
+          "w_msa.qkv.bias": (0.3 * torch.randn(3 * C, generator=g) * 64).round() / 64,
+          "w_msa.proj.weight": torch.eye(C), "w_msa.proj.bias": torch.zeros(C),
+          "w_msa.relative_position_bias_table": torch.randn(169, heads, generator=g)}
+    qkv_img = torch.nn.functional.linear(x, sd["w_msa.qkv.weight"], sd["w_msa.qkv.bias"]).view(nimg, X, Y, 3 * C)
+    ref = port.shift_window_msa(x, (X, Y), sd, "", heads, 3 if shift else 0).view(nimg, X, Y, C)
+    qkv_rows = _rows_from_images(qkv_img, B, X, Y, Z)
+    table = sd["w_msa.relative_position_bias_table"]
+    dense = table[port.rel_position_index(7).view(-1)].view(49, 49, heads).permute(2, 0, 1).reshape(heads, -1)
+    bias_pad = torch.nn.functional.pad(dense, (0, 2404 - 2401)).contiguous()
+    out = ops.window_attention(qkv_rows.to(cuda), sd["w_msa.qkv.bias"].to(cuda), bias_pad.to(cuda), B, X, Y, Z, C, heads, shift)
+    ref_rows = _rows_from_images(ref, B, X, Y, Z)
+    assert_close(out, ref_rows, 1e-3, f"window attention B{B} {X}x{Y}x{Z} C{C} shift={shift}")

@@ -35,7 +35,15 @@ def assert_close(a, b, tol=RTOL, what=""):
     assert torch.isfinite(a).all(), f"{what}: non-finite values"
     r, q = rel_err(a, b), rel_rms(a, b)
     assert r <= tol and q <= tol, f"{what}: rel_max {r:.3e}, rel_rms {q:.3e} (tol {tol:.0e})"
-    print(f"[parity] {what}: rel_max {r:.2e} rel_rms {q:.2e} (tol {tol:.0e})")
+    line = f"[parity] {what}: rel_max {r:.2e} rel_rms {q:.2e} (tol {tol:.0e})"
+    print(line)
+    log = os.environ.get("OCC_PARITY_LOG", os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", "parity.log"))
+    try:
+        os.makedirs(os.path.dirname(log), exist_ok=True)
+        with open(log, "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
     return r
 
 
