@@ -24,8 +24,8 @@ namespace occ {
 constexpr int BM = 128;
 constexpr int BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 4;
-constexpr int EPI_LD = 36;  // padded row pitch (floats) of the epilogue transpose buffers: conflict-free float4 access
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+constexpr int EPI_BUF_BYTES = 32 * 128;                 // one 32-row x 32-column fp32 chunk, 128-byte swizzled rows
+constexpr int EPI_BYTES = 4 /*warps*/ * 2 /*buffers*/ * EPI_BUF_BYTES;
 
 struct GemmParams {
   int M, N, K, num_k_blocks;
@@ -42,6 +42,7 @@ struct GemmParams {
   int padx, pady, padz;
   int B, Xo, Yo, Zo;
   int bx, by, bz, tiles_x, tiles_y, tiles_z;
+  int use_tma_store;  // epilogue writes through a TMA store (output rows 16-byte aligned)
   // GroupNorm statistics (sum, sumsq per (batch, group)), accumulated in fp64
   double* gn_stats;
   int cpg;
@@ -77,7 +78,7 @@ __device__ __forceinline__ void warp_butterfly32(float (&v)[32], int lane) {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(256, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BK * 4;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
@@ -93,7 +94,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   double* stat_acc = reinterpret_cast<double*>(tmem_ptr + 2);  // [64] doubles: (sum, sumsq) per group, <= 32 groups
-  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 1024);  // 4 warps x 32 rows x EPI_LD floats
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES + 1024;  // 4 warps x 2 buffers x 4 KB, 1024-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,6 +106,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -205,10 +207,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------- epilogue warps
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
-    float* stage_buf = epi_smem + ew * 32 * EPI_LD;
-    const bool vec_ok = (p.ldo % 4 == 0) && (p.residual == nullptr || p.ldr % 4 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.residual)) & 15) == 0;
-    const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+    uint8_t* stage_buf = epi_smem + ew * 2 * EPI_BUF_BYTES;
+    int sbuf = 0;
+    const bool row_vec = ((reinterpret_cast<uintptr_t>(p.residual) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0 &&
+                         p.ldr % 4 == 0 && p.ldo % 4 == 0;
     int it = 0;
     int cur_b = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -218,13 +220,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = n_tile * BN;
       // ---- output row of this thread
       long long m = -1;
-      int tile_b = 0;
+      int tile_b = 0, tile_x0 = 0, tile_y0 = 0, tile_z0 = 0;
       if (p.conv) {
         int t = m_tile;
         const int tz = t % p.tiles_z; t /= p.tiles_z;
         const int ty = t % p.tiles_y; t /= p.tiles_y;
         const int tx = t % p.tiles_x; t /= p.tiles_x;
         tile_b = t;
+        tile_x0 = tx * p.bx; tile_y0 = ty * p.by; tile_z0 = tz * p.bz;
         const int dz = row % p.bz;
         const int dy = (row / p.bz) % p.by;
         const int dx = row / (p.bz * p.by);
@@ -299,52 +302,67 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane < 2 * (32 / cpg)) atomicAdd(&stat_acc[2 * (nc / cpg) + lane], (double)sv[0]);
           }
         }
-        // ---- transpose through shared memory so that every store instruction covers 4 rows x 128 contiguous bytes
-        //      (thread = row would touch 32 different lines per instruction), then bias / residual / activation /
-        //      rounding in the coalesced domain: lane -> (row i*4 + lane/8, columns (lane%8)*4 .. +3)
-        __syncwarp();
+        // ---- epilogue math in the thread = row domain (32 consecutive output columns in registers)
+        const bool full_chunk = (nc + 32 <= p.N);
+        if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stage_buf + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
-        const int cq = (lane & 7) * 4;
-        const int col = nc + cq;
-        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col < p.N) {
-          if (col + 3 < p.N && bias_vec) bq = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-          else { if (col + 3 < p.N) bq.w = __ldg(p.bias + col + 3); bq.x = __ldg(p.bias + col); if (col + 1 < p.N) bq.y = __ldg(p.bias + col + 1); if (col + 2 < p.N) bq.z = __ldg(p.bias + col + 2); }
+          for (int j = 0; j < 32; ++j)
+            if (full_chunk || nc + j < p.N) v[j] += __ldg(p.bias + nc + j);
         }
+        if (p.residual && valid) {
+          const float* rrow = p.residual + m * p.ldr + nc;
+          if (full_chunk && row_vec) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + (lane >> 3);
-          const long long mr = __shfl_sync(0xffffffffu, m, r);
-          if (mr < 0 || col >= p.N) continue;
-          float4 t = *reinterpret_cast<const float4*>(stage_buf + r * EPI_LD + cq);
-          t.x += bq.x; t.y += bq.y; t.z += bq.z; t.w += bq.w;
-          const bool full4 = col + 3 < p.N;
-          if (p.residual) {
-            const float* rr = p.residual + mr * p.ldr + col;
-            if (full4 && vec_ok) {
-              const float4 q = *reinterpret_cast<const float4*>(rr);
-              t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
-            } else {
-              t.x += rr[0]; if (col + 1 < p.N) t.y += rr[1]; if (col + 2 < p.N) t.z += rr[2]; if (col + 3 < p.N) t.w += rr[3];
+            for (int j = 0; j < 32; j += 4) {
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + j));
+              v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
             }
-          }
-          if (p.act == 1) {
-            t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
-          } else if (p.act == 2) {
-            t.x = gelu_erf(t.x); t.y = gelu_erf(t.y); t.z = gelu_erf(t.z); t.w = gelu_erf(t.w);
-          }
-          if (p.round_out) {
-            t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w);
-          }
-          float* o = p.out + mr * p.ldo + col;
-          if (full4 && vec_ok) {
-            *reinterpret_cast<float4*>(o) = t;
           } else {
-            o[0] = t.x; if (col + 1 < p.N) o[1] = t.y; if (col + 2 < p.N) o[2] = t.z; if (col + 3 < p.N) o[3] = t.w;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.N) v[j] += rrow[j];
           }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (p.round_out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+        }
+        if (p.use_tma_store) {
+          // registers -> 128B-swizzled smem chunk (conflict-free) -> one TMA store per warp and chunk; the TMA unit
+          // generates the row addresses and clips rows >= M / columns >= N / voxels outside the grid
+          uint8_t* sb = stage_buf + sbuf * EPI_BUF_BYTES;
+          if (lane == 0) tma_store_wait_read<1>();  // the buffer used two chunks ago has been read
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.conv) {
+              // rows ew*32 .. ew*32+31 of the tile form a sub-box (ex, ey, ez) of the (bx, by, bz) voxel box
+              const int r0 = ew * 32;
+              tma_store_5d(&tmC, sb, nc, tile_z0 + r0 % p.bz, tile_y0 + (r0 / p.bz) % p.by, tile_x0 + r0 / (p.bz * p.by),
+                           tile_b);
+            } else {
+              tma_store_2d(&tmC, sb, nc, m_tile * BM + ew * 32);
+            }
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+        } else if (valid) {
+          float* orow = p.out + m * p.ldo + nc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nc + j < p.N) orow[j] = v[j];
         }
       }
       tc_fence_before();
@@ -361,6 +379,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+    if (lane == 0) tma_store_wait_all();  // all bulk stores of this warp have been written
   }
 
   tc_fence_before();
@@ -385,8 +404,8 @@ static int next_pow2(int v) {
 }
 
 template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_tiles,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                       int num_tiles, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BK * 4) + 1024 /*align*/ + 1024 /*barriers+stats*/ +
                           EPI_BYTES;
   static bool configured = false;
@@ -397,12 +416,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   if (grid < 1) grid = 1;
-  gemm_tf32_kernel<BN, STAGES><<<grid, 256, smem, stream>>>(tmA, tmB, p);
+  gemm_tf32_kernel<BN, STAGES><<<grid, 256, smem, stream>>>(tmA, tmB, tmC, p);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
 
-static int dispatch_gemm(const CUtensorMap& tmA, const void* W, GemmParams& p, int num_m_tiles, cudaStream_t stream) {
+static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmC, const void* W, GemmParams& p, int num_m_tiles,
+                         cudaStream_t stream) {
   int BN = p.N <= 32 ? 32 : p.N <= 64 ? 64 : (p.N <= 128 || (p.N % 256 != 0 && p.N % 128 == 0)) ? 128 : 256;
   CUtensorMap tmB;
   uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
@@ -412,10 +432,10 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* W, GemmParams& p, i
   if (rc) return rc;
   const int num_tiles = num_m_tiles * ((p.N + BN - 1) / BN);
   switch (BN) {
-    case 32: return launch_gemm<32, 8>(tmA, tmB, p, num_tiles, stream);
-    case 64: return launch_gemm<64, 8>(tmA, tmB, p, num_tiles, stream);
-    case 128: return launch_gemm<128, 6>(tmA, tmB, p, num_tiles, stream);
-    default: return launch_gemm<256, 4>(tmA, tmB, p, num_tiles, stream);
+    case 32: return launch_gemm<32, 8>(tmA, tmB, tmC, p, num_tiles, stream);
+    case 64: return launch_gemm<64, 8>(tmA, tmB, tmC, p, num_tiles, stream);
+    case 128: return launch_gemm<128, 5>(tmA, tmB, tmC, p, num_tiles, stream);
+    default: return launch_gemm<256, 4>(tmA, tmB, tmC, p, num_tiles, stream);
   }
 }
 
@@ -443,7 +463,16 @@ extern "C" int occ_gemm_tf32(const float* A, const float* W, float* out, int M, 
   uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
   int rc = make_tmap_f32(&tmA, A, 2, dims, strides, box, nullptr);
   if (rc) return rc;
-  return dispatch_gemm(tmA, W, p, (M + BM - 1) / BM, stream);
+  CUtensorMap tmC = tmA;  // placeholder when the TMA-store path is not usable (N % 4 != 0: scalar row stores)
+  p.use_tma_store = (N % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (p.use_tma_store) {
+    uint64_t cd[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t cs[1] = {(uint64_t)N * 4};
+    uint32_t cb[2] = {32u, 32u};
+    rc = make_tmap_f32(&tmC, out, 2, cd, cs, cb, nullptr);
+    if (rc) return rc;
+  }
+  return dispatch_gemm(tmA, tmC, W, p, (M + BM - 1) / BM, stream);
 }
 
 // x: (B, X, Y, Z, Cin) channel-last fp32;  w2: (Cout, KX*KY*KZ*Cin) tap-major repacked weights;
@@ -487,5 +516,19 @@ extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B,
   uint32_t estr[5] = {1, (uint32_t)stride, (uint32_t)stride, (uint32_t)stride, 1};
   int rc = make_tmap_f32(&tmA, x, 5, dims, strides, box, estr);
   if (rc) return rc;
-  return dispatch_gemm(tmA, w2, p, B * p.tiles_x * p.tiles_y * p.tiles_z, stream);
+  CUtensorMap tmC = tmA;
+  p.use_tma_store = (Cout % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (p.use_tma_store) {
+    // one epilogue warp owns 32 consecutive rows of the (bx, by, bz) box = a sub-box (ex, ey, ez)
+    const int ez = p.bz < 32 ? p.bz : 32;
+    const int ey = p.by < 32 / ez ? p.by : 32 / ez;
+    const int ex = 32 / (ez * ey);
+    uint64_t cd[5] = {(uint64_t)Cout, (uint64_t)p.Zo, (uint64_t)p.Yo, (uint64_t)p.Xo, (uint64_t)B};
+    uint64_t cs[4] = {(uint64_t)Cout * 4, (uint64_t)p.Zo * Cout * 4, (uint64_t)p.Yo * p.Zo * Cout * 4,
+                      (uint64_t)p.Xo * p.Yo * p.Zo * Cout * 4};
+    uint32_t cb[5] = {32u, (uint32_t)ez, (uint32_t)ey, (uint32_t)ex, 1u};
+    rc = make_tmap_f32(&tmC, out, 5, cd, cs, cb, nullptr);
+    if (rc) return rc;
+  }
+  return dispatch_gemm(tmA, tmC, w2, p, B * p.tiles_x * p.tiles_y * p.tiles_z, stream);
 }

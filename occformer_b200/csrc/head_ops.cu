@@ -193,29 +193,43 @@ query_head_kernel(const float* __restrict__ query, const float* __restrict__ pn_
 // ---------------------------------------------------------------------------------------------------------
 // adaptive_max_pool3d of the mask logits + "has an unmasked key" flag per (b, q).
 //   mask (B, X*Y*Z, Q) -> pooled (B, Xo*Yo*Zo, Q); window of output i along an axis: [floor(i*in/out), ceil((i+1)*in/out))
-__global__ void __launch_bounds__(256)
+// CTA = (128 q-threads, 4 window slices): thread.x <-> query (a voxel's Q logits are one contiguous row -> coalesced),
+// the four thread.y slices split the voxels of the pooling window and meet in shared memory.  32-bit index math only.
+__global__ void __launch_bounds__(512)
 mask_pool_kernel(const float* __restrict__ mask, float* __restrict__ pooled, int* __restrict__ row_flag, int B, int X,
                  int Y, int Z, int Xo, int Yo, int Zo, int Q) {
-  const long long So = (long long)Xo * Yo * Zo;
-  const long long total = (long long)B * So * Q;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % Q);
-    long long t = i / Q;
-    const int zo = (int)(t % Zo); t /= Zo;
-    const int yo = (int)(t % Yo); t /= Yo;
-    const int xo = (int)(t % Xo);
-    const int b = (int)(t / Xo);
+  __shared__ float red[4][128];
+  const int q = threadIdx.x, sl = threadIdx.y;
+  const int So = Xo * Yo * Zo;
+  const int ncell = B * So;
+  for (int cell = blockIdx.x; cell < ncell; cell += gridDim.x) {
+    int t = cell;
+    const int zo = t % Zo; t /= Zo;
+    const int yo = t % Yo; t /= Yo;
+    const int xo = t % Xo;
+    const int b = t / Xo;
     const int x0 = (int)(((long long)xo * X) / Xo), x1 = (int)(((long long)(xo + 1) * X + Xo - 1) / Xo);
     const int y0 = (int)(((long long)yo * Y) / Yo), y1 = (int)(((long long)(yo + 1) * Y + Yo - 1) / Yo);
     const int z0 = (int)(((long long)zo * Z) / Zo), z1 = (int)(((long long)(zo + 1) * Z + Zo - 1) / Zo);
+    const int wy = y1 - y0, wz = z1 - z0;
+    const int nvox = (x1 - x0) * wy * wz;
     float m = -INFINITY;
-    for (int x = x0; x < x1; ++x)
-      for (int y = y0; y < y1; ++y)
-        for (int z = z0; z < z1; ++z)
-          m = fmaxf(m, __ldg(mask + ((((size_t)b * X + x) * Y + y) * Z + z) * Q + q));
-    pooled[i] = m;
-    // attn_mask = sigmoid(m) < 0.5  <=>  m < 0 ; a row that is blocked everywhere is un-blocked (:652-653)
-    if (!(m < 0.f)) row_flag[b * Q + q] = 1;
+    if (q < Q) {
+      for (int i = sl; i < nvox; i += 4) {
+        const int dz = i % wz, dy = (i / wz) % wy, dx = i / (wz * wy);
+        const size_t v = (((size_t)b * X + x0 + dx) * Y + y0 + dy) * Z + z0 + dz;
+        m = fmaxf(m, __ldg(mask + v * Q + q));
+      }
+    }
+    red[sl][q] = m;
+    __syncthreads();
+    if (sl == 0 && q < Q) {
+      m = fmaxf(fmaxf(red[0][q], red[1][q]), fmaxf(red[2][q], red[3][q]));
+      pooled[(size_t)cell * Q + q] = m;
+      // attn_mask = sigmoid(m) < 0.5  <=>  m < 0 ; a row that is blocked everywhere is un-blocked (:652-653)
+      if (!(m < 0.f)) row_flag[b * Q + q] = 1;
+    }
+    __syncthreads();
   }
 }
 
@@ -235,6 +249,7 @@ cross_attn_partial_kernel(const float* __restrict__ qh, const float* __restrict_
                           int chunk, int nchunk) {
   __shared__ __align__(16) float sk[XA_TILE][XA_HD];
   __shared__ __align__(16) float sv[XA_TILE][XA_HD];
+  __shared__ float smask[XA_TILE][125];  // pooled mask logits of the key tile, [key][query <= 124 used] (odd pitch: conflict-free)
   const int c = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int t = threadIdx.x;
   const bool active = t < Q;
@@ -267,11 +282,14 @@ cross_attn_partial_kernel(const float* __restrict__ qh, const float* __restrict_
       *reinterpret_cast<float4*>(&sk[r][c4 * 4]) = kv;
       *reinterpret_cast<float4*>(&sv[r][c4 * 4]) = vv;
     }
+    {  // mask tile: n keys x Q logits are one contiguous block of the query-last pooled tensor -> coalesced
+      const float* ptile = pooled + ((size_t)b * S + s0) * Q;
+      for (int i = t; i < n * Q; i += 128) smask[i / Q][i % Q] = __ldg(ptile + i);
+    }
     __syncthreads();
     if (active) {
-      const float* prow = pooled + ((size_t)b * S + s0) * Q + t;
       for (int j = 0; j < n; ++j) {
-        if (use_mask && __ldg(prow + (size_t)j * Q) < 0.f) continue;
+        if (use_mask && smask[j][t] < 0.f) continue;
         float s = 0.f;
 #pragma unroll
         for (int d = 0; d < XA_HD; d += 4) {
@@ -655,11 +673,11 @@ extern "C" int occ_mask_pool(const float* mask, float* pooled, int* row_flag, in
   OCC_REQUIRE(mask && pooled && row_flag && B > 0 && X > 0 && Y > 0 && Z > 0 && Xo > 0 && Yo > 0 && Zo > 0 && Q > 0);
   OCC_REQUIRE(Xo <= X && Yo <= Y && Zo <= Z);
   OCC_CUDA(cudaMemsetAsync(row_flag, 0, (size_t)B * Q * sizeof(int), stream));
-  const long long total = (long long)B * Xo * Yo * Zo * Q;
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)sm_count() * 16;
+  OCC_REQUIRE(Q <= 128 && (long long)B * Xo * Yo * Zo < (1ll << 31));
+  long long blocks = (long long)B * Xo * Yo * Zo;
+  const long long cap = (long long)sm_count() * 32;
   if (blocks > cap) blocks = cap;
-  mask_pool_kernel<<<(unsigned)blocks, 256, 0, stream>>>(mask, pooled, row_flag, B, X, Y, Z, Xo, Yo, Zo, Q);
+  mask_pool_kernel<<<(unsigned)blocks, dim3(128, 4), 0, stream>>>(mask, pooled, row_flag, B, X, Y, Z, Xo, Yo, Zo, Q);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -677,7 +695,7 @@ extern "C" int occ_cross_attn_partial(const float* qh, const float* Kp, const fl
                                       const float* pooled, const int* row_flag, float* part, int B, int S, int Q,
                                       int E, int H, int chunk, int nchunk, cudaStream_t stream) {
   OCC_REQUIRE(qh && Kp && Vp && pooled && row_flag && part);
-  OCC_REQUIRE(B > 0 && S > 0 && Q > 0 && Q <= 128 && H > 0 && E == H * XA_HD && chunk > 0 && chunk % XA_TILE == 0);
+  OCC_REQUIRE(B > 0 && S > 0 && Q > 0 && Q <= 124 && H > 0 && E == H * XA_HD && chunk > 0 && chunk % XA_TILE == 0);
   OCC_REQUIRE(nchunk == (S + chunk - 1) / chunk && ld % 4 == 0 && koff % 4 == 0 && voff % 4 == 0);
   dim3 grid(nchunk, H, B);
   cross_attn_partial_kernel<<<grid, 128, 0, stream>>>(qh, Kp, Vp, ld, koff, voff, pooled, row_flag, part, S, Q, E, H,

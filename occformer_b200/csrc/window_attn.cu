@@ -97,7 +97,7 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < WA_STAGES; ++i) {
-      mbar_init(&full_bar[i], 4);   // one elected arrive per loader warp
+      mbar_init(&full_bar[i], 256); // per loader thread: one asynchronous cp.async arrival + one release arrival
       mbar_init(&empty_bar[i], 1);  // tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
@@ -163,20 +163,12 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         const float* gb = bias_pad + (size_t)h * WA_BIAS_FLOATS;
         for (int i = l; i < WA_BIAS_FLOATS / 4; i += 128) cp_async_16(sb + 4 * i, gb + 4 * i);
       }
-      cp_async_commit();
+      cp_async_mbar_arrive_noinc(&full_bar[s]);  // fires when this thread's copies of the unit have landed
+      mbar_arrive(&full_bar[s]);                 // release: zero-fill stores + metadata
     };
-    if (n_units > 0) issue(0);
-    for (long long u = 0; u < n_units; ++u) {
-      if (u + 1 < n_units) {
-        issue(u + 1);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[u % WA_STAGES]);
-    }
+    // the loaders never wait for their own copies: up to WA_STAGES units of gathers are in flight per CTA
+    for (long long u = 0; u < n_units; ++u) issue(u);
+    cp_async_wait<0>();
   } else if (warp == 0) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
@@ -198,9 +190,9 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         mma_commit(&o_ready[tb]);
         mma_commit(&empty_bar[s]);
       };
-      for (long long u = 0; u < n_units; ++u) {
+      auto do_qk = [&](long long u) {
         const int tb = (int)(u & 1), s = (int)(u % WA_STAGES);
-        mbar_wait(&full_bar[s], (uint32_t)((u / WA_STAGES) & 1));
+        fence_proxy_async_smem();  // cp.async / st.shared (generic proxy) -> tcgen05.mma operand reads (async proxy)
         tc_fence_after();
         const uint32_t qaddr = smem_u32(smem + (size_t)s * WA_STAGE_BYTES);
         const uint64_t qdesc = make_sw128_desc(qaddr, 1024, 16);
@@ -209,9 +201,26 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
 #pragma unroll
         for (int kk = 0; kk < HD / 8; ++kk) mma_tf32_ss(s_tmem, qdesc + 2 * kk, kdesc + 2 * kk, IDESC_QK, kk != 0);
         mma_commit(&s_ready[tb]);
-        if (u > 0) do_pv(u - 1);
+      };
+      // Polling state machine instead of a fixed QK/PV order: PV(u) must not queue behind the gathers of unit u+1,
+      // and QK(u+1) must not queue behind the softmax of unit u.  S/P buffer (u & 1) is free once PV(u-2) was issued
+      // (tcgen05 ops execute in issue order), hence the nq - np < 2 window.
+      long long nq = 0, np = 0;
+      while (np < n_units) {
+        if (nq < n_units && nq - np < 2 &&
+            mbar_try_wait(&full_bar[nq % WA_STAGES], (uint32_t)((nq / WA_STAGES) & 1))) {
+          do_qk(nq);
+          ++nq;
+        }
+        if (np < nq) {
+          const int tb = (int)(np & 1);
+          const uint32_t k = (uint32_t)(np >> 1);
+          if (mbar_try_wait(&p_ready[tb], k & 1) && mbar_try_wait(&o_free[tb], (k & 1) ^ 1)) {
+            do_pv(np);
+            ++np;
+          }
+        }
       }
-      if (n_units > 0) do_pv(n_units - 1);
     }
   } else if (warp >= 4 && warp < 12) {
     // ===================================================================== softmax / epilogue warpgroups

@@ -128,9 +128,9 @@ class _Mask2FormerOccBase(nn.Module):
         if E != feat_channels or enforce_decoder_input_project or out_channels != feat_channels:
             raise NotImplementedError("occformer_b200: decoder_input_projs other than Identity (feat_channels == embed_dims "
                                       "in every reference config, mask2former_nusc_occ.py:99-106)")
-        if E != self.num_heads * 32 or E % 32 or E > 256 or num_queries > 128 or num_queries % 4:
+        if E != self.num_heads * 32 or E % 32 or E > 256 or num_queries > 124 or num_queries % 4:
             raise NotImplementedError("occformer_b200: head kernels are built for head_dim 32, embed_dims <= 256, "
-                                      "num_queries <= 128 (multiple of 4)")
+                                      "num_queries <= 124 (multiple of 4)")
         if not pooling_attn_mask:
             raise NotImplementedError("occformer_b200: pooling_attn_mask=False (trilinear attn-mask downsampling)")
         self.transformer_decoder = _Decoder(E, self.ffn_channels, self.num_transformer_decoder_layers)
