@@ -94,7 +94,8 @@ int occ_layernorm(const float* in, const float* w, const float* b, float* out, l
 int occ_gn_apply(const float* in, const double* stats, const float* w, const float* b, const float* residual,
                  float* out, long long rows, int rows_per_batch, int C, int groups, int ldo, int out_off, int relu,
                  int round_out, occ_stream_t stream);
-/* ASPP image-pooling branch: GAP -> 1x1 conv -> GN -> ReLU -> broadcast (aspp.py:89-95,113-114) */
+/* ASPP image-pooling branch: GAP -> 1x1 conv -> GN -> ReLU -> broadcast (aspp.py:89-95,113-114).
+ * sums_ws: workspace of B*ch doubles followed by B*ch floats. */
 int occ_aspp_gap_branch(const float* in, double* sums_ws, const float* wconv, const float* gw, const float* gb,
                         float* cat, int B, int rows_per_batch, int ch, int groups, int ldo, int out_off,
                         occ_stream_t stream);
@@ -125,20 +126,20 @@ int occ_sine_pos3d(float* out, int X, int Y, int Z, int num_feats, float tempera
  * in is channel-last (B,S,C) or the reference layout (B,C,S); level_embed / pos+kpos optional. */
 int occ_head_prep(const float* in, int in_channel_last, const float* level_embed, const float* pos, float* mem,
                   float* kpos, int B, long long S, int C, occ_stream_t stream);
-/* forward_head query side (:446-455): post_norm LN -> cls_embed -> cls_out (rows, NC); mask_embed MLP ->
- * membed_out (rows, E) tf32-rounded.  Weights K-major transposed (in, out). */
-int occ_query_head(const float* query, const float* pn_w, const float* pn_b, const float* clsT, const float* cls_b,
-                   int NC, const float* m0T, const float* m0b, const float* m1T, const float* m1b, const float* m2T,
-                   const float* m2b, float* cls_out, float* membed_out, int rows, int E, occ_stream_t stream);
+/* forward_head query side (:446-455): [optional: query = LN(norms.2)(query_in) -> query_state] -> post_norm LN ->
+ * cls_embed -> cls_out (rows, NC); mask_embed MLP -> membed_out (rows, E) tf32-rounded; [optional: the NEXT layer's
+ * cross-attention query projection qh_out = ((query + query_pos) Wq^T + bq) * scale].  Weights K-major (in, out). */
+int occ_query_head(const float* query_in, const float* n2w, const float* n2b, float* query_state, const float* pn_w,
+                   const float* pn_b, const float* clsT, const float* cls_b, int NC, const float* m0T, const float* m0b,
+                   const float* m1T, const float* m1b, const float* m2T, const float* m2b, float* cls_out,
+                   float* membed_out, const float* query_pos, int Q, const float* wqT, const float* bq, float scale,
+                   float* qh_out, int rows, int E, occ_stream_t stream);
 /* adaptive_max_pool3d of the mask logits (:463) -> pooled (B, Xo*Yo*Zo, Q); row_flag[b*Q+q] = 1 iff some key of
  * the row is un-blocked (pooled >= 0), else the row attends everywhere (:652-653).  attn_mask == pooled < 0. */
 int occ_mask_pool(const float* mask, float* pooled, int* row_flag, int B, int X, int Y, int Z, int Xo, int Yo, int Zo,
                   int Q, occ_stream_t stream);
 /* key-chunking of the masked cross attention for S keys */
 int occ_cross_attn_chunks(int S, int* chunk, int* nchunk);
-/* qh = ((query + query_pos) Wq^T + bq) * scale */
-int occ_query_proj(const float* query, const float* query_pos, int Q, const float* wqT, const float* bq, float scale,
-                   float* qh, int rows, int E, occ_stream_t stream);
 /* masked cross attention partials per key chunk (mmcv MultiheadAttention -> nn.MultiheadAttention, bool attn_mask):
  * part (B, H, nchunk, Q, 34) = running max, running sum, 32 value accumulators */
 int occ_cross_attn_partial(const float* qh, const float* Kp, const float* Vp, int ld, int koff, int voff,
@@ -149,11 +150,11 @@ int occ_cross_merge(const float* part, int nchunk, int H, const float* query, co
                     const float* woT, const float* bo, const float* n0w, const float* n0b, const float* sa_inT,
                     const float* sa_inb, float scale, float* query1, float* sa_qkv, int rows, int E,
                     occ_stream_t stream);
-/* self attention over the Q queries -> out_proj -> +identity -> LN(norms.1) -> FFN(ReLU) -> +identity -> LN(norms.2) */
+/* self attention over the Q queries -> out_proj -> +identity -> LN(norms.1) -> x1; FFN(ReLU) + identity accumulated
+ * into ybuf (= x1 + FFN(x1), F/E column blocks, fp32 atomics); the closing LN(norms.2) runs in occ_query_head. */
 int occ_self_attn_ffn(const float* sa_qkv, const float* query1, int Q, const float* woT, const float* bo,
                       const float* n1w, const float* n1b, const float* f1T, const float* f1b, const float* f2T,
-                      const float* f2b, int F, const float* n2w, const float* n2b, float* query_out, int rows, int E,
-                      int H, occ_stream_t stream);
+                      const float* f2b, int F, float* x1, float* ybuf, int rows, int E, int H, occ_stream_t stream);
 /* simple_test tail (:725-736, format_results :691-696): trilinear upsample (align_corners=True) -> sigmoid ->
  * einsum with softmax(cls)[..., :-1]; mask (B, X*Y*Z, Q), cls (B, Q, NC) -> out (B, NC-1, Xo, Yo, Zo) */
 int occ_classmix(const float* mask, const float* cls, float* out, int B, int X, int Y, int Z, int Xo, int Yo, int Zo,

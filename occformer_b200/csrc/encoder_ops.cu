@@ -75,6 +75,8 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
                         const float* __restrict__ ln_b, float* __restrict__ tok, float* __restrict__ tokn, int B,
                         int XY, int Z, int C, int groups, int cols) {
   extern __shared__ float col_smem[];  // [cols][Z][C]
+  __shared__ float s_mean[8][32], s_rstd[8][32];  // GroupNorm mean / rstd per (column of this CTA, group): the fp64
+                                                  // division + sqrt runs once per CTA, not once per lane and row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col_local = warp / Z, z = warp % Z;
   const long long col = (long long)blockIdx.x * cols + col_local;  // (b*XY + xy)
@@ -82,6 +84,12 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
   const bool active = col_local < cols && col < ncols;
   const int cpg = C / groups;
   const double count = (double)XY * Z * cpg;
+  for (int i = threadIdx.x; i < cols * groups; i += blockDim.x) {
+    const int cl = i / groups, g = i % groups;
+    const long long cc = (long long)blockIdx.x * cols + cl;
+    if (cc < ncols) gn_mean_rstd(stats, (int)(cc / XY), groups, g, count, &s_mean[cl][g], &s_rstd[cl][g]);
+  }
+  __syncthreads();
   float4 v[NV];
   if (active) {
     const int b = (int)(col / XY);
@@ -91,8 +99,7 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
     for (int i = 0; i < NV; ++i) {
       const int c0 = (i * 32 + lane) * 4;
       float4 t = __ldcs(src + i * 32 + lane);
-      float mean, rstd;
-      gn_mean_rstd(stats, b, groups, c0 / cpg, count, &mean, &rstd);  // cpg >= 4: one group per float4
+      const float mean = s_mean[col_local][c0 / cpg], rstd = s_rstd[col_local][c0 / cpg];  // cpg >= 4: one group per float4
       const float4 g = *reinterpret_cast<const float4*>(gn_w + c0);
       const float4 bb = *reinterpret_cast<const float4*>(gn_b + c0);
       t.x = fmaxf((t.x - mean) * rstd * g.x + bb.x, 0.f);
@@ -225,8 +232,8 @@ colsum_kernel(const float* __restrict__ in, double* __restrict__ sums, int rows_
 // (bilinear align_corners=True upsample of a 1x1 map = broadcast, aspp.py:114).  One CTA per batch sample.
 __global__ void __launch_bounds__(256)
 aspp_gap_branch_kernel(const double* __restrict__ sums, const float* __restrict__ wconv, const float* __restrict__ gw,
-                       const float* __restrict__ gb, float* __restrict__ cat, int rows_per_batch, int ch, int groups,
-                       int ldo, int out_off) {
+                       const float* __restrict__ gb, float* __restrict__ sums_out /*(B, ch) fp32, aliases nothing*/,
+                       int rows_per_batch, int ch, int groups) {
   extern __shared__ float sm[];  // mean[ch], conv[ch], outv[ch]
   float* mean = sm;
   float* conv = sm + ch;
@@ -252,13 +259,21 @@ aspp_gap_branch_kernel(const double* __restrict__ sums, const float* __restrict_
     outv[o] = fmaxf((conv[o] - m) * rsqrtf(var + kEps) * gw[o] + gb[o], 0.f);
   }
   __syncthreads();
+  // the branch output of this sample (ch values, tf32-rounded: operand of the 1x1 conv that follows); the broadcast
+  // over the X*Y rows of the concat buffer is done by gap_broadcast_kernel with a full grid
+  for (int o = threadIdx.x; o < ch; o += blockDim.x) sums_out[(size_t)b * ch + o] = round_tf32(outv[o]);
+}
+
+__global__ void __launch_bounds__(256)
+gap_broadcast_kernel(const float* __restrict__ vals /*(B, ch)*/, float* __restrict__ cat, long long rows,
+                     int rows_per_batch, int ch, int ldo, int out_off) {
   const int ch4 = ch >> 2;
-  for (long long i = threadIdx.x; i < (long long)rows_per_batch * ch4; i += blockDim.x) {
-    const long long r = i / ch4;
-    const int c0 = (int)(i % ch4) * 4;
-    *reinterpret_cast<float4*>(cat + ((size_t)b * rows_per_batch + r) * ldo + out_off + c0) =
-        make_float4(round_tf32(outv[c0]), round_tf32(outv[c0 + 1]), round_tf32(outv[c0 + 2]), round_tf32(outv[c0 + 3]));
-  }
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ch4) return;
+  const long long r = i / ch4;
+  const int c0 = (int)(i % ch4) * 4;
+  const int b = (int)(r / rows_per_batch);
+  *reinterpret_cast<float4*>(cat + r * ldo + out_off + c0) = *reinterpret_cast<const float4*>(vals + (size_t)b * ch + c0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -330,7 +345,8 @@ extern "C" int occ_gn_relu_zmean_ln(const float* y, const double* stats, const f
                                     const float* ln_w, const float* ln_b, float* tok, float* tokn, int B, int XY,
                                     int Z, int C, int groups, cudaStream_t stream) {
   OCC_REQUIRE(y && stats && gn_w && gn_b && ln_w && ln_b && tok && tokn);
-  OCC_REQUIRE(B > 0 && XY > 0 && Z > 0 && Z <= 16 && C % 128 == 0 && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0);
+  OCC_REQUIRE(B > 0 && XY > 0 && Z > 0 && Z <= 16 && C % 128 == 0 && groups > 0 && groups <= 32 && C % groups == 0 &&
+              (C / groups) % 4 == 0);
   int cols = 8 / Z;
   if (cols < 1) cols = 1;
   const size_t smem = (size_t)cols * Z * C * 4;
@@ -379,8 +395,14 @@ extern "C" int occ_aspp_gap_branch(const float* in, double* sums_ws, const float
   dim3 grid((rows_per_batch + chunk - 1) / chunk, B);
   colsum_kernel<<<grid, 256, 0, stream>>>(in, sums_ws, rows_per_batch, ch, chunk);
   OCC_LAUNCH_CHECK();
-  aspp_gap_branch_kernel<<<B, 256, 3 * ch * sizeof(float), stream>>>(sums_ws, wconv, gw, gb, cat, rows_per_batch, ch,
-                                                                    groups, ldo, out_off);
+  // sums_ws holds B*ch doubles; the fp32 branch values are written behind them (caller allocates B*ch*12 bytes)
+  float* vals = reinterpret_cast<float*>(sums_ws + (size_t)B * ch);
+  aspp_gap_branch_kernel<<<B, 256, 3 * ch * sizeof(float), stream>>>(sums_ws, wconv, gw, gb, vals, rows_per_batch, ch,
+                                                                    groups);
+  OCC_LAUNCH_CHECK();
+  const long long n4 = (long long)B * rows_per_batch * (ch / 4);
+  gap_broadcast_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(vals, cat, (long long)B * rows_per_batch,
+                                                                        rows_per_batch, ch, ldo, out_off);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

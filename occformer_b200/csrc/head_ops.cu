@@ -161,18 +161,33 @@ __global__ void head_prep_ncs_kernel(const float* __restrict__ in, const float* 
 // forward_head, query side: post_norm LN -> cls_embed, mask_embed MLP (Linear-ReLU-Linear-ReLU-Linear).
 //   query (B*Q, E); cls_out (B*Q, NC); membed_out (B*Q, E) tf32-rounded (B operand of the mask GEMM)
 __global__ void __launch_bounds__(1024)
-query_head_kernel(const float* __restrict__ query, const float* __restrict__ pn_w, const float* __restrict__ pn_b,
+query_head_kernel(const float* __restrict__ query_in, const float* __restrict__ n2w, const float* __restrict__ n2b,
+                  float* __restrict__ query_state, const float* __restrict__ pn_w, const float* __restrict__ pn_b,
                   const float* __restrict__ clsT, const float* __restrict__ cls_b, int NC,
                   const float* __restrict__ m0T, const float* __restrict__ m0b, const float* __restrict__ m1T,
                   const float* __restrict__ m1b, const float* __restrict__ m2T, const float* __restrict__ m2b,
-                  float* __restrict__ cls_out, float* __restrict__ membed_out, int rows, int E) {
+                  float* __restrict__ cls_out, float* __restrict__ membed_out, const float* __restrict__ query_pos,
+                  int Q, const float* __restrict__ wqT, const float* __restrict__ bq, float scale,
+                  float* __restrict__ qh_out, int rows, int E) {
   extern __shared__ float sm[];  // xs[QG*E], part[QG*QG*E], red[32]
   float* xs = sm;
   float* part = xs + QG * E;
   float* red = part + QG * QG * E;
   const int j = threadIdx.x % E, g = threadIdx.x / E;
   const int row = blockIdx.x * QG + g;  // rows % QG == 0
-  float x = group_layernorm(query[(size_t)row * E + j], g, j, E, pn_w, pn_b, red);
+  float q = query_in[(size_t)row * E + j];
+  if (n2w) {  // last norm of the decoder layer (norms.2) on the FFN accumulator -> the layer's output query
+    q = group_layernorm(q, g, j, E, n2w, n2b, red);
+    query_state[(size_t)row * E + j] = q;
+  }
+  if (wqT) {  // cross-attention query projection of the NEXT layer: ((query + query_pos) Wq^T + bq) * hd^-0.5
+    __syncthreads();
+    xs[g * E + j] = q + query_pos[(size_t)(row % Q) * E + j];
+    __syncthreads();
+    qh_out[(size_t)row * E + j] = matvec4(wqT, E, bq, xs, E, j, g, E, part) * scale;
+  }
+  float x = group_layernorm(q, g, j, E, pn_w, pn_b, red);
+  __syncthreads();
   xs[g * E + j] = x;
   __syncthreads();
   {  // class logits: NC <= E outputs; threads j >= NC idle along (all threads must reach the barriers)
@@ -193,43 +208,34 @@ query_head_kernel(const float* __restrict__ query, const float* __restrict__ pn_
 // ---------------------------------------------------------------------------------------------------------
 // adaptive_max_pool3d of the mask logits + "has an unmasked key" flag per (b, q).
 //   mask (B, X*Y*Z, Q) -> pooled (B, Xo*Yo*Zo, Q); window of output i along an axis: [floor(i*in/out), ceil((i+1)*in/out))
-// CTA = (128 q-threads, 4 window slices): thread.x <-> query (a voxel's Q logits are one contiguous row -> coalesced),
-// the four thread.y slices split the voxels of the pooling window and meet in shared memory.  32-bit index math only.
+// CTA = (128 q-threads, 4 cells): thread.x <-> query (a voxel's Q logits are one contiguous row -> coalesced 400-byte
+// reads), thread.y <-> one pooled cell; all window loads of a thread are independent (no barriers), 32-bit index math.
 __global__ void __launch_bounds__(512)
 mask_pool_kernel(const float* __restrict__ mask, float* __restrict__ pooled, int* __restrict__ row_flag, int B, int X,
                  int Y, int Z, int Xo, int Yo, int Zo, int Q) {
-  __shared__ float red[4][128];
-  const int q = threadIdx.x, sl = threadIdx.y;
+  const int q = threadIdx.x;
   const int So = Xo * Yo * Zo;
   const int ncell = B * So;
-  for (int cell = blockIdx.x; cell < ncell; cell += gridDim.x) {
+  if (q >= Q) return;
+  for (int cell = blockIdx.x * 4 + threadIdx.y; cell < ncell; cell += gridDim.x * 4) {
     int t = cell;
     const int zo = t % Zo; t /= Zo;
     const int yo = t % Yo; t /= Yo;
     const int xo = t % Xo;
     const int b = t / Xo;
-    const int x0 = (int)(((long long)xo * X) / Xo), x1 = (int)(((long long)(xo + 1) * X + Xo - 1) / Xo);
-    const int y0 = (int)(((long long)yo * Y) / Yo), y1 = (int)(((long long)(yo + 1) * Y + Yo - 1) / Yo);
-    const int z0 = (int)(((long long)zo * Z) / Zo), z1 = (int)(((long long)(zo + 1) * Z + Zo - 1) / Zo);
-    const int wy = y1 - y0, wz = z1 - z0;
-    const int nvox = (x1 - x0) * wy * wz;
+    const int x0 = (xo * X) / Xo, x1 = ((xo + 1) * X + Xo - 1) / Xo;
+    const int y0 = (yo * Y) / Yo, y1 = ((yo + 1) * Y + Yo - 1) / Yo;
+    const int z0 = (zo * Z) / Zo, z1 = ((zo + 1) * Z + Zo - 1) / Zo;
     float m = -INFINITY;
-    if (q < Q) {
-      for (int i = sl; i < nvox; i += 4) {
-        const int dz = i % wz, dy = (i / wz) % wy, dx = i / (wz * wy);
-        const size_t v = (((size_t)b * X + x0 + dx) * Y + y0 + dy) * Z + z0 + dz;
-        m = fmaxf(m, __ldg(mask + v * Q + q));
+    for (int x = x0; x < x1; ++x)
+      for (int y = y0; y < y1; ++y) {
+        const float* p = mask + ((((size_t)b * X + x) * Y + y) * Z + z0) * Q + q;
+#pragma unroll 4
+        for (int z = 0; z < z1 - z0; ++z) m = fmaxf(m, __ldg(p + (size_t)z * Q));
       }
-    }
-    red[sl][q] = m;
-    __syncthreads();
-    if (sl == 0 && q < Q) {
-      m = fmaxf(fmaxf(red[0][q], red[1][q]), fmaxf(red[2][q], red[3][q]));
-      pooled[(size_t)cell * Q + q] = m;
-      // attn_mask = sigmoid(m) < 0.5  <=>  m < 0 ; a row that is blocked everywhere is un-blocked (:652-653)
-      if (!(m < 0.f)) row_flag[b * Q + q] = 1;
-    }
-    __syncthreads();
+    pooled[(size_t)cell * Q + q] = m;
+    // attn_mask = sigmoid(m) < 0.5  <=>  m < 0 ; a row that is blocked everywhere is un-blocked (:652-653)
+    if (!(m < 0.f)) row_flag[b * Q + q] = 1;
   }
 }
 
@@ -324,22 +330,6 @@ cross_attn_partial_kernel(const float* __restrict__ qh, const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Projections of the query side of the cross attention:  qh = ((query + query_pos) Wq^T + bq) * hd^-0.5
-__global__ void __launch_bounds__(1024)
-query_proj_kernel(const float* __restrict__ query, const float* __restrict__ query_pos, int Q,
-                  const float* __restrict__ wqT, const float* __restrict__ bq, float scale, float* __restrict__ qh,
-                  int rows, int E) {
-  extern __shared__ float sm[];  // xs[QG*E], part[QG*QG*E]
-  float* xs = sm;
-  float* part = xs + QG * E;
-  const int j = threadIdx.x % E, g = threadIdx.x / E;
-  const int row = blockIdx.x * QG + g;
-  xs[g * E + j] = query[(size_t)row * E + j] + query_pos[(size_t)(row % Q) * E + j];
-  __syncthreads();
-  qh[(size_t)row * E + j] = matvec4(wqT, E, bq, xs, E, j, g, E, part) * scale;
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // Cross-attention tail + self-attention in-projection (thread (j, g): channel j = head j/32, dim j%32, of row row0+g):
 //   merge the key-chunk partials -> out_proj -> + identity -> LN(norms.0) -> query1
 //   self-attn in_proj: q = ((query1+pos) Wq^T + bq) * hd^-0.5, k = (query1+pos) Wk^T + bk, v = query1 Wv^T + bv
@@ -388,20 +378,17 @@ cross_merge_kernel(const float* __restrict__ part_in, int nchunk, int H, const f
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Self-attention over the Q queries + out_proj + LN(norms.1) + FFN (ReLU) + LN(norms.2).  Thread (j, g): row row0+g,
-// warp j/32 of the group <-> head (hd = 32 = warp size), then channel j.
+// Self-attention over the Q queries + out_proj + LN(norms.1).  Thread (j, g): row row0+g, warp j/32 of the group <->
+// head (hd = 32 = warp size), then channel j.  Writes x1 (LN1 output) and seeds the FFN accumulator ybuf = x1 + b2.
 __global__ void __launch_bounds__(1024)
-self_attn_ffn_kernel(const float* __restrict__ sa_qkv, const float* __restrict__ query1, int Q,
-                     const float* __restrict__ woT, const float* __restrict__ bo, const float* __restrict__ n1w,
-                     const float* __restrict__ n1b, const float* __restrict__ f1T /*(E, F)*/,
-                     const float* __restrict__ f1b, const float* __restrict__ f2T /*(F, E)*/,
-                     const float* __restrict__ f2b, int F, const float* __restrict__ n2w,
-                     const float* __restrict__ n2b, float* __restrict__ query_out, int E) {
-  extern __shared__ float sm[];  // xs[QG*E], part[QG*QG*E], red[32], hs[QG*F]
+self_attn_kernel(const float* __restrict__ sa_qkv, const float* __restrict__ query1, int Q,
+                 const float* __restrict__ woT, const float* __restrict__ bo, const float* __restrict__ n1w,
+                 const float* __restrict__ n1b, const float* __restrict__ f2b, float* __restrict__ x1,
+                 float* __restrict__ ybuf, int E) {
+  extern __shared__ float sm[];  // xs[QG*E], part[QG*QG*E], red[32]
   float* xs = sm;
   float* part = xs + QG * E;
   float* red = part + QG * QG * E;
-  float* hs = red + 32;
   const int j = threadIdx.x % E, g = threadIdx.x / E;
   const int lane = j & 31, h = j >> 5;
   const int row = blockIdx.x * QG + g;
@@ -441,29 +428,30 @@ self_attn_ffn_kernel(const float* __restrict__ sa_qkv, const float* __restrict__
   __syncthreads();
   float x = matvec4(woT, E, bo, xs, E, j, g, E, part) + query1[(size_t)row * E + j];
   x = group_layernorm(x, g, j, E, n1w, n1b, red);
+  x1[(size_t)row * E + j] = x;
+  ybuf[(size_t)row * E + j] = x + f2b[j];
+}
+
+// FFN (mmcv FFN: Linear-ReLU-Linear + identity) as F/E independent column blocks: CTA (blockIdx.y = c) computes the
+// hidden units f in [c*E, (c+1)*E) of four rows and accumulates their contribution to the output into ybuf with
+// fp32 atomics (summation order over the F/E blocks is not fixed: differences at the 1e-7 level run to run).
+__global__ void __launch_bounds__(1024)
+ffn_block_kernel(const float* __restrict__ x1, const float* __restrict__ f1T /*(E, F)*/, const float* __restrict__ f1b,
+                 const float* __restrict__ f2T /*(F, E)*/, int F, float* __restrict__ ybuf, int E) {
+  extern __shared__ float sm[];  // xs[QG*E], hs[QG*E], part[QG*QG*E]
+  float* xs = sm;
+  float* hs = xs + QG * E;
+  float* part = hs + QG * E;
+  const int j = threadIdx.x % E, g = threadIdx.x / E;
+  const int row = blockIdx.x * QG + g;
+  const int c = blockIdx.y;
+  xs[g * E + j] = x1[(size_t)row * E + j];
   __syncthreads();
-  xs[g * E + j] = x;
+  const float hval = fmaxf(matvec4(f1T + (size_t)c * E, F, f1b + (size_t)c * E, xs, E, j, g, E, part), 0.f);
+  hs[g * E + j] = hval;
   __syncthreads();
-  // FFN layer 1: F = nf*E hidden columns f = j + E*c; column block c is computed by group c % QG for all four rows
-  for (int c = g; c * E < F; c += QG) {
-    const int f = c * E + j;
-    float a[QG];
-#pragma unroll
-    for (int r = 0; r < QG; ++r) a[r] = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < E; ++k) {
-      const float w = __ldg(f1T + (size_t)k * F + f);
-#pragma unroll
-      for (int r = 0; r < QG; ++r) a[r] = fmaf(w, xs[r * E + k], a[r]);
-    }
-    const float bb = __ldg(f1b + f);
-#pragma unroll
-    for (int r = 0; r < QG; ++r) hs[r * F + f] = fmaxf(a[r] + bb, 0.f);
-  }
-  __syncthreads();
-  float y = matvec4(f2T, E, f2b, hs, F, j, g, E, part) + x;
-  y = group_layernorm(y, g, j, E, n2w, n2b, red);
-  query_out[(size_t)row * E + j] = y;
+  const float y = matvec4(f2T + (size_t)c * E * E, E, nullptr, hs, E, j, g, E, part);
+  atomicAdd(ybuf + (size_t)row * E + j, y);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -501,7 +489,14 @@ classmix_kernel(const float* __restrict__ mask, const float* __restrict__ cls, f
     // coalesced stage of CM_THREADS voxel rows (Q floats each) through shared memory
     const int nrows = (int)min((long long)CM_THREADS, Vo - v0);
     const float* src = mask + ((size_t)b * Vo + v0) * Q;
-    for (int i = threadIdx.x; i < nrows * Q; i += blockDim.x) rows[(i / Q) * (Q + 1) + (i % Q)] = __ldcs(src + i);
+    {  // warp w copies rows w, w+4, ...: lanes stride over the Q contiguous floats of a row (no integer division)
+      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+      for (int r = w; r < nrows; r += CM_THREADS / 32) {
+        const float* rs = src + (size_t)r * Q;
+        float* rd = rows + r * (Q + 1);
+        for (int c = l; c < Q; c += 32) rd[c] = __ldcs(rs + c);
+      }
+    }
     __syncthreads();
     if (v < Vo) {
       const float* r = rows + threadIdx.x * (Q + 1);
@@ -655,15 +650,20 @@ extern "C" int occ_head_prep(const float* in, int in_channel_last, const float* 
   return OCC_OK;
 }
 
-extern "C" int occ_query_head(const float* query, const float* pn_w, const float* pn_b, const float* clsT,
-                              const float* cls_b, int NC, const float* m0T, const float* m0b, const float* m1T,
-                              const float* m1b, const float* m2T, const float* m2b, float* cls_out, float* membed_out,
-                              int rows, int E, cudaStream_t stream) {
-  OCC_REQUIRE(query && pn_w && pn_b && clsT && cls_b && m0T && m0b && m1T && m1b && m2T && m2b && cls_out && membed_out);
+extern "C" int occ_query_head(const float* query_in, const float* n2w, const float* n2b, float* query_state,
+                              const float* pn_w, const float* pn_b, const float* clsT, const float* cls_b, int NC,
+                              const float* m0T, const float* m0b, const float* m1T, const float* m1b, const float* m2T,
+                              const float* m2b, float* cls_out, float* membed_out, const float* query_pos, int Q,
+                              const float* wqT, const float* bq, float scale, float* qh_out, int rows, int E,
+                              cudaStream_t stream) {
+  OCC_REQUIRE(query_in && pn_w && pn_b && clsT && cls_b && m0T && m0b && m1T && m1b && m2T && m2b && cls_out && membed_out);
   OCC_REQUIRE(rows > 0 && rows % QG == 0 && E % 32 == 0 && E <= 256 && NC > 0 && NC <= E);
+  OCC_REQUIRE((n2w == nullptr) == (n2b == nullptr) && (n2w == nullptr || query_state != nullptr));
+  OCC_REQUIRE(wqT == nullptr || (bq && query_pos && qh_out && Q > 0));
   const size_t smem = ((QG + QG * QG) * E + 32) * sizeof(float);
-  query_head_kernel<<<rows / QG, E * QG, smem, stream>>>(
-      query, pn_w, pn_b, clsT, cls_b, NC, m0T, m0b, m1T, m1b, m2T, m2b, cls_out, membed_out, rows, E);
+  query_head_kernel<<<rows / QG, E * QG, smem, stream>>>(query_in, n2w, n2b, query_state, pn_w, pn_b, clsT, cls_b, NC, m0T,
+                                                         m0b, m1T, m1b, m2T, m2b, cls_out, membed_out, query_pos, Q, wqT,
+                                                         bq, scale, qh_out, rows, E);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -674,8 +674,9 @@ extern "C" int occ_mask_pool(const float* mask, float* pooled, int* row_flag, in
   OCC_REQUIRE(Xo <= X && Yo <= Y && Zo <= Z);
   OCC_CUDA(cudaMemsetAsync(row_flag, 0, (size_t)B * Q * sizeof(int), stream));
   OCC_REQUIRE(Q <= 128 && (long long)B * Xo * Yo * Zo < (1ll << 31));
-  long long blocks = (long long)B * Xo * Yo * Zo;
-  const long long cap = (long long)sm_count() * 32;
+  OCC_REQUIRE(X < 32768 && Y < 32768 && Z < 32768);
+  long long blocks = ((long long)B * Xo * Yo * Zo + 3) / 4;
+  const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   mask_pool_kernel<<<(unsigned)blocks, dim3(128, 4), 0, stream>>>(mask, pooled, row_flag, B, X, Y, Z, Xo, Yo, Zo, Q);
   OCC_LAUNCH_CHECK();
@@ -704,15 +705,6 @@ extern "C" int occ_cross_attn_partial(const float* qh, const float* Kp, const fl
   return OCC_OK;
 }
 
-extern "C" int occ_query_proj(const float* query, const float* query_pos, int Q, const float* wqT, const float* bq,
-                              float scale, float* qh, int rows, int E, cudaStream_t stream) {
-  OCC_REQUIRE(query && query_pos && wqT && bq && qh && rows > 0 && rows % QG == 0 && Q > 0 && E % 32 == 0 && E <= 256);
-  const size_t smem = (QG + QG * QG) * E * sizeof(float);
-  query_proj_kernel<<<rows / QG, E * QG, smem, stream>>>(query, query_pos, Q, wqT, bq, scale, qh, rows, E);
-  OCC_LAUNCH_CHECK();
-  return OCC_OK;
-}
-
 extern "C" int occ_cross_merge(const float* part, int nchunk, int H, const float* query, const float* query_pos, int Q,
                                const float* woT, const float* bo, const float* n0w, const float* n0b,
                                const float* sa_inT, const float* sa_inb, float scale, float* query1, float* sa_qkv,
@@ -728,21 +720,17 @@ extern "C" int occ_cross_merge(const float* part, int nchunk, int H, const float
 
 extern "C" int occ_self_attn_ffn(const float* sa_qkv, const float* query1, int Q, const float* woT, const float* bo,
                                  const float* n1w, const float* n1b, const float* f1T, const float* f1b,
-                                 const float* f2T, const float* f2b, int F, const float* n2w, const float* n2b,
-                                 float* query_out, int rows, int E, int H, cudaStream_t stream) {
+                                 const float* f2T, const float* f2b, int F, float* x1, float* ybuf, int rows, int E,
+                                 int H, cudaStream_t stream) {
   OCC_REQUIRE(E == H * XA_HD);
-  OCC_REQUIRE(sa_qkv && query1 && woT && bo && n1w && n1b && f1T && f1b && f2T && f2b && n2w && n2b && query_out);
+  OCC_REQUIRE(sa_qkv && query1 && woT && bo && n1w && n1b && f1T && f1b && f2T && f2b && x1 && ybuf);
   OCC_REQUIRE(rows > 0 && rows % QG == 0 && Q > 0 && Q <= 128 && E % 32 == 0 && E <= 256 && F > 0 && F % E == 0 &&
-              rows % Q == 0);
-  const size_t smem = ((QG + QG * QG) * E + 32 + (size_t)QG * F) * sizeof(float);
-  OCC_REQUIRE(smem <= 96 * 1024);
-  static bool configured = false;
-  if (!configured) {
-    OCC_CUDA(cudaFuncSetAttribute(self_attn_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured = true;
-  }
-  self_attn_ffn_kernel<<<rows / QG, E * QG, smem, stream>>>(sa_qkv, query1, Q, woT, bo, n1w, n1b, f1T, f1b, f2T, f2b, F, n2w, n2b,
-                                                  query_out, E);
+              rows % Q == 0 && F / E <= 65535);
+  const size_t smem = ((QG + QG * QG) * E + 32) * sizeof(float);
+  self_attn_kernel<<<rows / QG, E * QG, smem, stream>>>(sa_qkv, query1, Q, woT, bo, n1w, n1b, f2b, x1, ybuf, E);
+  OCC_LAUNCH_CHECK();
+  const size_t smem2 = (2 * QG + QG * QG) * E * sizeof(float);
+  ffn_block_kernel<<<dim3(rows / QG, F / E), E * QG, smem2, stream>>>(x1, f1T, f1b, f2T, F, ybuf, E);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

@@ -33,13 +33,16 @@ namespace occ {
 constexpr int WS = 7;
 constexpr int WT = WS * WS;  // 49 tokens
 constexpr int HD = 32;       // head dim (multihead_base_channel, dualpath_block.py:32)
-constexpr int WA_STAGES = 3;
+constexpr int WA_STAGES = 4;
 constexpr int WA_TILE = 128 * HD * 4;                  // 16 KB: 128 rows x 128 B
 constexpr int WA_BIAS_FLOATS = 2404;                   // 49*49 padded to a 16-byte multiple
-constexpr int WA_OFF_BIAS = 3 * WA_TILE;               // 49152
-constexpr int WA_OFF_ROWS = WA_OFF_BIAS + WA_BIAS_FLOATS * 4;  // 58768 (8-byte aligned)
-constexpr int WA_OFF_REGION = WA_OFF_ROWS + 128 * 8;   // 59792
-constexpr int WA_STAGE_BYTES = 60 * 1024;              // 61440 >= 59792 + 512, multiple of 1024
+constexpr int WA_OFF_ROWS = 3 * WA_TILE;               // 49152 (8-byte aligned)
+constexpr int WA_OFF_REGION = WA_OFF_ROWS + 128 * 8;   // 50176
+constexpr int WA_OFF_SAME = WA_OFF_REGION + 128 * 4;   // 50688: per window half, 9 x uint64 "key j is in region r" masks
+constexpr int WA_OFF_UNI = WA_OFF_SAME + 2 * 9 * 8;    // 50832: per window half, 1 if all 49 tokens share a region
+constexpr int WA_STAGE_BYTES = 50 * 1024;              // 51200 >= 50840, multiple of 1024
+constexpr int WA_BIAS_LD = 52;                         // padded bias row pitch (floats): 13 conflict-free LDS.128 per row
+constexpr int WA_BIAS_BYTES = 10240;                   // resident bias of this CTA's head, (49, 52) floats, * log2(e)
 constexpr int WA_THREADS = 512;
 constexpr uint32_t WA_TMEM_COLS = 512;                 // S/P: 2 x 128, O: 2 x 32
 
@@ -80,7 +83,8 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WA_STAGES * WA_STAGE_BYTES);
+  float* sb = reinterpret_cast<float*>(smem + WA_STAGES * WA_STAGE_BYTES);  // bias of head h, resident
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WA_STAGES * WA_STAGE_BYTES + WA_BIAS_BYTES);
   uint64_t* empty_bar = full_bar + WA_STAGES;
   uint64_t* s_ready = empty_bar + WA_STAGES;  // [2]
   uint64_t* p_ready = s_ready + 2;            // [2]
@@ -91,9 +95,16 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long npairs = (g.nwin + 1) / 2;
   const int H = g.heads;
-  // units of this CTA: pairs blockIdx.x, +gridDim.x, ...; heads innermost
-  const long long my_pairs = (npairs > blockIdx.x) ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const long long n_units = my_pairs * H;
+  // One head per CTA (gridDim.x is a multiple of H): CTA c works on head c % H of the window pairs c / H,
+  // + gridDim.x / H, ...  The H CTAs of a group walk the same pairs at the same time, so the 12 128-byte segments of
+  // every qkv token row (one DRAM page) are fetched together, and the head's bias table stays resident in smem.
+  const int h = blockIdx.x % H;
+  const int pair0 = blockIdx.x / H, pair_stride = gridDim.x / H;
+  const long long n_units = (npairs > pair0) ? (npairs - pair0 + pair_stride - 1) / pair_stride : 0;
+  for (int i = threadIdx.x; i < WT * WA_BIAS_LD; i += WA_THREADS) {  // scores live in the log2 domain (exp2 softmax)
+    const int r = i / WA_BIAS_LD, c = i % WA_BIAS_LD;
+    sb[i] = c < WT ? bias_pad[(size_t)h * WA_BIAS_FLOATS + r * WT + c] * 1.4426950408889634f : 0.f;
+  }
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < WA_STAGES; ++i) {
@@ -120,8 +131,7 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
     const int C = g.C;
     auto issue = [&](long long u) {
       const int s = (int)(u % WA_STAGES);
-      const long long pair = blockIdx.x + (u / H) * gridDim.x;
-      const int h = (int)(u % H);
+      const long long pair = pair0 + u * pair_stride;
       uint8_t* st = smem + (size_t)s * WA_STAGE_BYTES;
       long long* rows = reinterpret_cast<long long*>(st + WA_OFF_ROWS);
       int* region = reinterpret_cast<int*>(st + WA_OFF_REGION);
@@ -141,6 +151,18 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         region[l] = reg;
       }
       named_bar_sync(2, 128);
+      if (l < 18) {  // shift-mask bookkeeping of the two windows: which keys share region r, and is the window uniform
+        const int hf = l / 9, r = l % 9;
+        unsigned long long same = 0ull;
+        bool uni = true;
+        for (int j = 0; j < WT; ++j) {
+          const int rj = region[hf * 64 + j];
+          if (rj == r) same |= 1ull << j;
+          uni = uni && (rj == region[hf * 64]);
+        }
+        reinterpret_cast<unsigned long long*>(st + WA_OFF_SAME)[l] = same;
+        if (r == 0) reinterpret_cast<int*>(st + WA_OFF_UNI)[hf] = uni ? 1 : 0;
+      }
 #pragma unroll 4
       for (int i = 0; i < 24; ++i) {
         const int idx = i * 128 + l;
@@ -157,11 +179,6 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
           const float* src = (row >= 0 ? qkv + row * 3 * C : qkv_bias) + tile * C + h * HD + c * 4;
           cp_async_16(dst, src);
         }
-      }
-      {
-        float* sb = reinterpret_cast<float*>(st + WA_OFF_BIAS);
-        const float* gb = bias_pad + (size_t)h * WA_BIAS_FLOATS;
-        for (int i = l; i < WA_BIAS_FLOATS / 4; i += 128) cp_async_16(sb + 4 * i, gb + 4 * i);
       }
       cp_async_mbar_arrive_noinc(&full_bar[s]);  // fires when this thread's copies of the unit have landed
       mbar_arrive(&full_bar[s]);                 // release: zero-fill stores + metadata
@@ -233,17 +250,18 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
     for (long long u = wg; u < n_units; u += 2) {
       const int s = (int)(u % WA_STAGES);
       const uint32_t k = (uint32_t)(u >> 1);
-      const int h = (int)(u % H);
       const uint8_t* st = smem + (size_t)s * WA_STAGE_BYTES;
-      const float* sb = reinterpret_cast<const float*>(st + WA_OFF_BIAS);
       const long long* rows = reinterpret_cast<const long long*>(st + WA_OFF_ROWS);
       const int* region = reinterpret_cast<const int*>(st + WA_OFF_REGION);
       mbar_wait(&s_ready[tb], k & 1);
       tc_fence_after();
       const long long my_row = rows[i];
       const int my_reg = region[i];
-      const float* brow = sb + (t < WT ? t : 0) * WT;
-      const int* kreg = region + half * 64;
+      const bool uniform = reinterpret_cast<const int*>(st + WA_OFF_UNI)[half] != 0;
+      // keys that are NOT in this query's region get the additive -100 of the reference's shift mask
+      const unsigned long long diff =
+          uniform ? 0ull : ~reinterpret_cast<const unsigned long long*>(st + WA_OFF_SAME)[half * 9 + my_reg];
+      const float4* brow4 = reinterpret_cast<const float4*>(sb + (t < WT ? t : 0) * WA_BIAS_LD);
       const uint32_t s_col = lane_base + tb * 128 + half * 64;
       uint32_t ra[32], rb[32];
       tmem_ld_32x32(s_col, ra);
@@ -253,37 +271,55 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
 #pragma unroll
         for (int j = 0; j < 32; ++j) { dbg[i * 192 + j] = __uint_as_float(ra[j]); dbg[i * 192 + 32 + j] = __uint_as_float(rb[j]); }
       }
-      float m = -INFINITY;
+      // z = (s * scale + bias [- 100]) * log2(e): one FFMA per score (bias pre-multiplied), four independent max chains
+      const float sl2 = scale * 1.4426950408889634f, neg = -100.0f * 1.4426950408889634f;
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float z = fmaf(__uint_as_float(ra[j]), scale, brow[j]);
-        if (kreg[j] != my_reg) z += -100.0f;
-        ra[j] = __float_as_uint(z);
-        m = fmaxf(m, z);
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 bv = brow4[j4];
+        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * j4 + e;
+          float z = fmaf(__uint_as_float(ra[j]), sl2, bb[e]);
+          if (!uniform) z += ((diff >> j) & 1ull) ? neg : 0.f;
+          ra[j] = __float_as_uint(z);
+          mx[e] = fmaxf(mx[e], z);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < WT - 32; ++j) {
-        float z = fmaf(__uint_as_float(rb[j]), scale, brow[32 + j]);
-        if (kreg[32 + j] != my_reg) z += -100.0f;
-        rb[j] = __float_as_uint(z);
-        m = fmaxf(m, z);
+      for (int j4 = 0; j4 < 5; ++j4) {
+        const float4 bv = brow4[8 + j4];
+        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * j4 + e;
+          if (32 + j < WT) {
+            float z = fmaf(__uint_as_float(rb[j]), sl2, bb[e]);
+            if (!uniform) z += ((diff >> (32 + j)) & 1ull) ? neg : 0.f;
+            rb[j] = __float_as_uint(z);
+            mx[e] = fmaxf(mx[e], z);
+          }
+        }
       }
-      float sum = 0.f;
+      const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      float sm4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float p = round_tf32(__expf(__uint_as_float(ra[j]) - m));
-        sum += p;
+        const float p = round_tf32(exp2f(__uint_as_float(ra[j]) - m));
+        sm4[j & 3] += p;
         ra[j] = __float_as_uint(p);
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float p = 0.f;
         if (j < WT - 32) {
-          p = round_tf32(__expf(__uint_as_float(rb[j]) - m));
-          sum += p;
+          p = round_tf32(exp2f(__uint_as_float(rb[j]) - m));
+          sm4[j & 3] += p;
         }
         rb[j] = __float_as_uint(p);
       }
+      const float sum = (sm4[0] + sm4[1]) + (sm4[2] + sm4[3]);
       if (dbg && u == 0 && blockIdx.x == 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) { dbg[i * 192 + 64 + j] = __uint_as_float(ra[j]); dbg[i * 192 + 96 + j] = __uint_as_float(rb[j]); }
@@ -353,14 +389,17 @@ extern "C" int occ_window_attention(const float* qkv, const float* qkv_bias, con
   g.vox_rows = (long long)B * X * Y * Z;
   g.nwin = (long long)B * (Z + 1) * g.nWx * g.nWy;
   OCC_REQUIRE(g.nwin < (1ll << 31));
-  const size_t smem = (size_t)WA_STAGES * WA_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  const size_t smem = (size_t)WA_STAGES * WA_STAGE_BYTES + WA_BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool configured = false;
   if (!configured) {
     OCC_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const long long npairs = (g.nwin + 1) / 2;
-  const int grid = (int)(npairs < sm_count() ? npairs : sm_count());
+  OCC_REQUIRE(heads <= sm_count());
+  long long groups = sm_count() / heads;  // CTA groups of `heads` CTAs, one head each
+  if (groups > npairs) groups = npairs;
+  const int grid = (int)(groups * heads);
   window_attn_tc_kernel<<<grid, WA_THREADS, smem, stream>>>(qkv, qkv_bias, bias_pad, out, g, g_wattn_dbg);
   OCC_LAUNCH_CHECK();
   return OCC_OK;

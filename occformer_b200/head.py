@@ -247,30 +247,35 @@ class _Mask2FormerOccBase(nn.Module):
         query = self.query_feat.weight.detach().float().unsqueeze(0).expand(B, Q, E).reshape(B * Q, E).contiguous()
         qpos = P["query_pos"]
 
-        def forward_head(query, target):
-            cls, membed = ops.query_head(query, P["head"], NC)
-            mask = torch.empty((B, V, Q), dtype=torch.float32, device=query.device)
+        def forward_head(query_in, target, norm2=None, next_layer=None):
+            nq = None
+            if next_layer is not None:
+                Ln = P["layers"][next_layer]
+                nq = (qpos, Q, Ln["ca_wqT"], Ln["ca_bq"], scale)
+            cls, membed, query, qh = ops.query_head(query_in, P["head"], NC, norm2=norm2, next_q=nq)
+            mask = torch.empty((B, V, Q), dtype=torch.float32, device=query_in.device)
             for b in range(B):
                 ops.gemm(mf_r[b], membed[b * Q:(b + 1) * Q], out=mask[b])
             pooled, flag = ops.mask_pool(mask, B, grid, target, Q) if target is not None else (None, None)
-            return cls.view(B, Q, NC), mask, pooled, flag
+            return cls.view(B, Q, NC), mask, pooled, flag, query, qh
 
         cls_list, mask_list = [], []
-        cls, mask, pooled, flag = forward_head(query, sizes[0])
+        cls, mask, pooled, flag, query, qh = forward_head(query, sizes[0], next_layer=0 if L > 0 else None)
         cls_list.append(cls)
-        if keep_all_masks:
+        if keep_all_masks or L == 0:
             mask_list.append(mask)
         for i in range(L):
             lvl = i % nl
             S = sizes[lvl][0] * sizes[lvl][1] * sizes[lvl][2]
             Lw = P["layers"][i]
             off = P["slots"][i] * E
-            qh = ops.query_proj(query, qpos, Q, Lw["ca_wqT"], Lw["ca_bq"], scale)
             part, nchunk = ops.cross_attn_partial(qh, Kp[lvl], Vp[lvl], lds[lvl], off, off, pooled, flag, B, S, Q, E, H)
             q1, sa = ops.cross_merge(part, nchunk, H, query, qpos, Q, Lw, scale)
-            query = ops.self_attn_ffn(sa, q1, Q, Lw, H)
+            ybuf = ops.self_attn_ffn(sa, q1, Q, Lw, H)
             last = i == L - 1
-            cls, mask, pooled, flag = forward_head(query, None if last else sizes[(i + 1) % nl])
+            cls, mask, pooled, flag, query, qh = forward_head(ybuf, None if last else sizes[(i + 1) % nl],
+                                                              norm2=(Lw["n2w"], Lw["n2b"]),
+                                                              next_layer=None if last else i + 1)
             cls_list.append(cls)
             if keep_all_masks or last:
                 mask_list.append(mask)

@@ -236,10 +236,10 @@ def gn_apply(x, stats, w, b, rows_per_batch, groups, residual=None, out=None, ou
 
 def aspp_gap_branch(x, wconv, gw, gb, cat, B, rows_per_batch, groups, out_off):
     ch = x.shape[1]
-    sums = torch.empty((B, ch), dtype=torch.float64, device=x.device)
+    sums = torch.empty((B, ch * 3 // 2 + 2), dtype=torch.float64, device=x.device)  # B*ch doubles + B*ch floats
     check(lib().occ_aspp_gap_branch(_ptr(x), _ptr(sums), _ptr(wconv), _ptr(gw), _ptr(gb), _ptr(cat), B, rows_per_batch,
                                     ch, groups, cat.shape[1], out_off, _stream()), "occ_aspp_gap_branch")
-    LAUNCH_COUNT[0] += 3
+    LAUNCH_COUNT[0] += 4
     return cat
 
 
@@ -285,15 +285,23 @@ def head_prep(x, channel_last, level_embed=None, pos=None):
     return mem, kpos
 
 
-def query_head(query, W, NC):
-    rows, E = query.shape
-    cls = torch.empty((rows, NC), dtype=torch.float32, device=query.device)
-    membed = torch.empty((rows, E), dtype=torch.float32, device=query.device)
-    check(lib().occ_query_head(_ptr(query), _ptr(W["pn_w"]), _ptr(W["pn_b"]), _ptr(W["clsT"]), _ptr(W["cls_b"]), NC,
-                               _ptr(W["m0T"]), _ptr(W["m0b"]), _ptr(W["m1T"]), _ptr(W["m1b"]), _ptr(W["m2T"]),
-                               _ptr(W["m2b"]), _ptr(cls), _ptr(membed), rows, E, _stream()), "occ_query_head")
+def query_head(query_in, W, NC, norm2=None, next_q=None):
+    """forward_head query side.  norm2 = (w, b): query_in is the FFN accumulator, LN(norms.2) gives the layer output
+    (returned as `query`); next_q = (query_pos, Q, wqT, bq, scale): also project the next layer's cross-attn queries."""
+    rows, E = query_in.shape
+    cls = torch.empty((rows, NC), dtype=torch.float32, device=query_in.device)
+    membed = torch.empty((rows, E), dtype=torch.float32, device=query_in.device)
+    query = torch.empty_like(query_in) if norm2 is not None else query_in
+    qh = torch.empty_like(query_in) if next_q is not None else None
+    n2w, n2b = norm2 if norm2 is not None else (None, None)
+    qpos, Q, wqT, bq, scale = next_q if next_q is not None else (None, 0, None, None, 0.0)
+    check(lib().occ_query_head(_ptr(query_in), _ptr(n2w), _ptr(n2b), _ptr(query) if norm2 is not None else None,
+                               _ptr(W["pn_w"]), _ptr(W["pn_b"]), _ptr(W["clsT"]), _ptr(W["cls_b"]), NC, _ptr(W["m0T"]),
+                               _ptr(W["m0b"]), _ptr(W["m1T"]), _ptr(W["m1b"]), _ptr(W["m2T"]), _ptr(W["m2b"]), _ptr(cls),
+                               _ptr(membed), _ptr(qpos), Q, _ptr(wqT), _ptr(bq), scale, _ptr(qh), rows, E, _stream()),
+          "occ_query_head")
     LAUNCH_COUNT[0] += 1
-    return cls, membed
+    return cls, membed, query, qh
 
 
 def mask_pool(mask, B, grid, out_grid, Q):
@@ -310,15 +318,6 @@ def cross_attn_chunks(S):
     c, n = ctypes.c_int(), ctypes.c_int()
     lib().occ_cross_attn_chunks(S, ctypes.byref(c), ctypes.byref(n))
     return c.value, n.value
-
-
-def query_proj(query, query_pos, Q, wqT, bq, scale):
-    rows, E = query.shape
-    qh = torch.empty_like(query)
-    check(lib().occ_query_proj(_ptr(query), _ptr(query_pos), Q, _ptr(wqT), _ptr(bq), scale, _ptr(qh), rows, E, _stream()),
-          "occ_query_proj")
-    LAUNCH_COUNT[0] += 1
-    return qh
 
 
 def cross_attn_partial(qh, Kp, Vp, ld, koff, voff, pooled, flag, B, S, Q, E, H):
@@ -342,14 +341,16 @@ def cross_merge(part, nchunk, H, query, query_pos, Q, L, scale):
 
 
 def self_attn_ffn(sa, q1, Q, L, H):
+    """-> ybuf = x1 + FFN(x1) (pre-norms.2 accumulator of the decoder layer)."""
     rows, E = q1.shape
-    out = torch.empty_like(q1)
+    x1 = torch.empty_like(q1)
+    ybuf = torch.empty_like(q1)
     F = L["f1b"].numel()
     check(lib().occ_self_attn_ffn(_ptr(sa), _ptr(q1), Q, _ptr(L["sa_woT"]), _ptr(L["sa_bo"]), _ptr(L["n1w"]), _ptr(L["n1b"]),
-                                  _ptr(L["f1T"]), _ptr(L["f1b"]), _ptr(L["f2T"]), _ptr(L["f2b"]), F, _ptr(L["n2w"]),
-                                  _ptr(L["n2b"]), _ptr(out), rows, E, H, _stream()), "occ_self_attn_ffn")
-    LAUNCH_COUNT[0] += 1
-    return out
+                                  _ptr(L["f1T"]), _ptr(L["f1b"]), _ptr(L["f2T"]), _ptr(L["f2b"]), F, _ptr(x1), _ptr(ybuf),
+                                  rows, E, H, _stream()), "occ_self_attn_ffn")
+    LAUNCH_COUNT[0] += 2
+    return ybuf
 
 
 def classmix(mask, cls, B, grid, out_grid, Q, NC):
