@@ -134,17 +134,30 @@ int occ_query_head(const float* query_in, const float* n2w, const float* n2b, fl
                    const float* m1T, const float* m1b, const float* m2T, const float* m2b, float* cls_out,
                    float* membed_out, const float* query_pos, int Q, const float* wqT, const float* bq, float scale,
                    float* qh_out, int rows, int E, occ_stream_t stream);
-/* adaptive_max_pool3d of the mask logits (:463) -> pooled (B, Xo*Yo*Zo, Q); row_flag[b*Q+q] = 1 iff some key of
- * the row is un-blocked (pooled >= 0), else the row attends everywhere (:652-653).  attn_mask == pooled < 0. */
-int occ_mask_pool(const float* mask, float* pooled, int* row_flag, int B, int X, int Y, int Z, int Xo, int Yo, int Zo,
+/* adaptive_max_pool3d of the mask logits (:463), general windows -> pooled (B, Xo*Yo*Zo, Q) as order-preserving ints
+ * (see occ_mask_gemm_pool); row_flag[b*Q+q] = 1 iff some key of the row is un-blocked (pooled >= 0), else the row
+ * attends everywhere (:652-653).  attn_mask == pooled < 0. */
+int occ_mask_pool(const float* mask, int* pooled, int* row_flag, int B, int X, int Y, int Z, int Xo, int Yo, int Zo,
                   int Q, occ_stream_t stream);
+/* mask einsum with fused attention-mask pooling (:457-466) when the pooling windows are powers of two >= 2 dividing the
+ * grid: mask[b,v,q] = <mf[b,v,:], membed[b,q,:]> (written only if mask_out != NULL), pooled[b,cell,q] = window max as an
+ * order-preserving int (i >= 0 ? i : i ^ 0x7FFFFFFF of the float bits; blocked <=> value < 0), flag[b,q] as occ_mask_pool */
+int occ_mask_gemm_pool(const float* mf, const float* membed, float* mask_out, int* pooled, int* flag, int B, int X, int Y,
+                       int Z, int E, int Q, int Xo, int Yo, int Zo, occ_stream_t stream);
 /* key-chunking of the masked cross attention for S keys */
 int occ_cross_attn_chunks(int S, int* chunk, int* nchunk);
 /* masked cross attention partials per key chunk (mmcv MultiheadAttention -> nn.MultiheadAttention, bool attn_mask):
  * part (B, H, nchunk, Q, 34) = running max, running sum, 32 value accumulators */
 int occ_cross_attn_partial(const float* qh, const float* Kp, const float* Vp, int ld, int koff, int voff,
-                           const float* pooled, const int* row_flag, float* part, int B, int S, int Q, int E, int H,
+                           const int* pooled, const int* row_flag, float* part, int B, int S, int Q, int E, int H,
                            int chunk, int nchunk, occ_stream_t stream);
+/* the same masked cross attention on the tcgen05 tensor cores (128-key tiles, TMA operand loads, P in TMEM);
+ * writes occ_cross_attn_tc_partials(S) partials per (sample, head): part (B, H, npart, Q, 34) */
+int occ_cross_attn_tc_partials(int S);
+/* pooled (B,S,Q) ordered-int mask logits -> bits (B, 4*ceil(S/128), Q): one "blocked" bit per (key, query) */
+int occ_mask_bits(const int* pooled, unsigned* bits, int B, int S, int Q, occ_stream_t stream);
+int occ_cross_attn_tc(const float* qh, const float* Kp, const float* Vp, int ld, int koff, int voff, const unsigned* bits,
+                      const int* row_flag, float* part, int B, int S, int Q, int E, int H, occ_stream_t stream);
 /* merge partials -> out_proj -> +identity -> LN(norms.0) -> query1; self-attention in_proj -> sa_qkv (rows, 3E) */
 int occ_cross_merge(const float* part, int nchunk, int H, const float* query, const float* query_pos, int Q,
                     const float* woT, const float* bo, const float* n0w, const float* n0b, const float* sa_inT,

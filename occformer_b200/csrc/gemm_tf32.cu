@@ -43,6 +43,15 @@ struct GemmParams {
   int B, Xo, Yo, Zo;
   int bx, by, bz, tiles_x, tiles_y, tiles_z;
   int use_tma_store;  // epilogue writes through a TMA store (output rows 16-byte aligned)
+  // fused adaptive max pooling of the output (decoder mask logits -> attention-mask logits), conv mode only:
+  // pool_out[(cell), n] = max over the pw^3 voxels of the cell, as order-preserving ints (see enc_ordered)
+  int* pool_out;
+  int* pool_flag;  // [N]: set to 1 when some pooled value of column n is >= 0
+  int pwx, pwy, pwz, pXo, pYo, pZo;
+  int pool_nsteps, pool_stride[5];               // lane xor-strides of the in-warp butterfly (z, then y, then x bits)
+  int pool_cwx, pool_cwy, pool_cwz, pool_ncy, pool_ncz;  // cell extent inside a tile, cells per tile along y / z
+  int pool_complete;                             // every cell lies inside one tile: plain stores, no global atomics
+  int store_out;   // 0: the GEMM output itself is not written (only pooled)
   // GroupNorm statistics (sum, sumsq per (batch, group)), accumulated in fp64
   double* gn_stats;
   int cpg;
@@ -50,6 +59,13 @@ struct GemmParams {
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// order-preserving float <-> int map (signed compare of the ints == compare of the floats; sign is kept)
+__device__ __forceinline__ int enc_ordered(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+constexpr int ENC_NEG = (int)0x80808080;  // below every encoded finite float; also the byte pattern of the memset
 
 template <int CPG>
 __device__ __forceinline__ void accum_stats(const float (&v)[32], float (&sv)[32]) {
@@ -208,6 +224,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
     uint8_t* stage_buf = epi_smem + ew * 2 * EPI_BUF_BYTES;
+    if (p.pool_out != nullptr) {  // pooled mode never stores through the staging buffers: they hold the cell maxima
+      for (int i = threadIdx.x - 128; i < 8192; i += 128) reinterpret_cast<int*>(epi_smem)[i] = ENC_NEG;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     int sbuf = 0;
     const bool row_vec = ((reinterpret_cast<uintptr_t>(p.residual) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0 &&
                          p.ldr % 4 == 0 && p.ldo % 4 == 0;
@@ -259,16 +279,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * BN;
+      // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed
+      uint32_t rnext[32];
+      tmem_ld_32x32(t_row, rnext);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int nc = n0 + c * 32;
         if (nc >= p.N) break;
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rnext[j]);
+        if (c + 1 < BN / 32 && nc + 32 < p.N) tmem_ld_32x32(t_row + (c + 1) * 32, rnext);
         if (p.gn_stats != nullptr) {
           // per-group sum / sumsq of the raw conv output, butterfly-reduced over the 32 rows of the warp
           const int cpg = p.cpg;  // power of two in [1, 32]
@@ -305,9 +327,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ---- epilogue math in the thread = row domain (32 consecutive output columns in registers)
         const bool full_chunk = (nc + 32 <= p.N);
         if (p.bias) {
+          if (full_chunk && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full_chunk || nc + j < p.N) v[j] += __ldg(p.bias + nc + j);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + nc + j));
+              v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.N) v[j] += __ldg(p.bias + nc + j);
+          }
         }
         if (p.residual && valid) {
           const float* rrow = p.residual + m * p.ldr + nc;
@@ -334,7 +364,59 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
         }
-        if (p.use_tma_store) {
+        if (p.pool_out != nullptr) {
+          // ---- fused adaptive max pool (windows are powers of two >= 2 that divide the grid).  The G lanes of this
+          // warp's (ex, ey, ez) voxel sub-box that share a pooling cell reduce their 32 columns with a halving
+          // butterfly (lane keeps 32/G column maxima: 32 - 32/G shuffles instead of 32 log2 G), the partial maxima of
+          // the four warps meet through smem atomicMax, then one global atomicMax per (cell of the tile, column).
+          // Smem buffers alternate per chunk: one named barrier per chunk.
+          int* ps = reinterpret_cast<int*>(epi_smem) + (c & 1) * 4096;  // <= 64 cells x 32 columns per buffer
+          {
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = valid ? v[j] : -INFINITY;
+            int qoff = 0;  // first column (within the chunk) of the values this lane ends up holding
+            int n = 32;
+#pragma unroll
+            for (int st = 0; st < 5; ++st) {
+              if (st < p.pool_nsteps) {  // warp-uniform
+                const int o = p.pool_stride[st];
+                const bool upper = (lane & o) != 0;
+                const int half = 32 >> (st + 1);
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                  const float keep = upper ? w[i + half] : w[i];
+                  const float send = upper ? w[i] : w[i + half];
+                  w[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+                }
+                qoff += upper ? half : 0;
+                n = half;
+              }
+            }
+            const int dz = row % p.bz, dy = (row / p.bz) % p.by, dx = row / (p.bz * p.by);
+            const int cl = ((dx / p.pool_cwx) * p.pool_ncy + dy / p.pool_cwy) * p.pool_ncz + dz / p.pool_cwz;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)  // G >= 4 lanes per cell in every supported configuration -> n <= 8
+              if (i < n && w[i] > -INFINITY) atomicMax(&ps[cl * 32 + qoff + i], enc_ordered(w[i]));
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int ncell = (p.bx / p.pool_cwx) * p.pool_ncy * p.pool_ncz;
+          for (int i = threadIdx.x - 128; i < ncell * 32; i += 128) {
+            const int val = ps[i];
+            ps[i] = ENC_NEG;
+            const int cl = i >> 5, q = nc + (i & 31);
+            if (val == ENC_NEG || q >= p.N) continue;
+            const int cz = cl % p.pool_ncz, cy = (cl / p.pool_ncz) % p.pool_ncy, cx = cl / (p.pool_ncz * p.pool_ncy);
+            const int gx = (tile_x0 + cx * p.pool_cwx) / p.pwx, gy = (tile_y0 + cy * p.pool_cwy) / p.pwy,
+                      gz = (tile_z0 + cz * p.pool_cwz) / p.pwz;
+            int* dst = &p.pool_out[((((size_t)tile_b * p.pXo + gx) * p.pYo + gy) * p.pZo + gz) * p.N + q];
+            if (p.pool_complete) *dst = val; else atomicMax(dst, val);
+            if (val >= 0) p.pool_flag[(size_t)tile_b * p.N + q] = 1;
+          }
+        }
+        if (!p.store_out) {
+          // nothing else to write
+        } else if (p.use_tma_store) {
           // registers -> 128B-swizzled smem chunk (conflict-free) -> one TMA store per warp and chunk; the TMA unit
           // generates the row addresses and clips rows >= M / columns >= N / voxels outside the grid
           uint8_t* sb = stage_buf + sbuf * EPI_BUF_BYTES;
@@ -457,6 +539,7 @@ extern "C" int occ_gemm_tf32(const float* A, const float* W, float* out, int M, 
   p.M = M; p.N = N; p.K = K; p.num_k_blocks = (K + BK - 1) / BK;
   p.out = out; p.ldo = N; p.bias = bias; p.residual = residual; p.ldr = N; p.act = act; p.round_out = round_out;
   p.conv = 0; p.gn_stats = gn_stats; p.cpg = cpg; p.rows_per_batch = gn_stats ? rows_per_batch : 0;
+  p.pool_out = nullptr; p.pool_flag = nullptr; p.store_out = 1;
   CUtensorMap tmA;
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
   uint64_t strides[1] = {(uint64_t)K * 4};
@@ -507,6 +590,7 @@ extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B,
   p.M = B * p.Xo * p.Yo * p.Zo;
   p.out = out; p.ldo = Cout; p.bias = bias; p.residual = residual; p.ldr = Cout; p.act = act; p.round_out = round_out;
   p.gn_stats = gn_stats; p.cpg = cpg; p.rows_per_batch = 0;
+  p.pool_out = nullptr; p.pool_flag = nullptr; p.store_out = 1;
   OCC_REQUIRE(p.bx * stride <= 256 && p.by * stride <= 256 && p.bz * stride <= 256);
   CUtensorMap tmA;
   uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)Z, (uint64_t)Y, (uint64_t)X, (uint64_t)B};
@@ -531,4 +615,85 @@ extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B,
     if (rc) return rc;
   }
   return dispatch_gemm(tmA, tmC, w2, p, B * p.tiles_x * p.tiles_y * p.tiles_z, stream);
+}
+
+
+// Decoder mask logits with fused attention-mask pooling (mask2former_nusc_occ.py:457-466):
+//   mask[b, v, q] = <mask_feature[b, v, :], mask_embed[b, q, :]>   (1x1x1 "conv" over the voxel grid, K = E)
+//   pooled[b, cell, q] = max over the (X/Xo, Y/Yo, Z/Zo) voxels of the cell  (adaptive_max_pool3d with divisible,
+//   power-of-two windows), written as order-preserving ints (sign == sign of the logit: blocked <=> value < 0);
+//   flag[b, q] = 1 iff some pooled value of the row is >= 0.   mask_out may be NULL (intermediate decoder layers).
+extern "C" int occ_mask_gemm_pool(const float* mf, const float* membed, float* mask_out, int* pooled, int* flag, int B,
+                                  int X, int Y, int Z, int E, int Q, int Xo, int Yo, int Zo, cudaStream_t stream) {
+  OCC_REQUIRE(mf && membed && pooled && flag);
+  OCC_REQUIRE(B > 0 && X > 0 && Y > 0 && Z > 0 && E % BK == 0 && Q > 0 && Q % 4 == 0 && Q <= 128);
+  OCC_REQUIRE(Xo > 0 && Yo > 0 && Zo > 0 && X % Xo == 0 && Y % Yo == 0 && Z % Zo == 0);
+  const int wx = X / Xo, wy = Y / Yo, wz = Z / Zo;
+  auto pow2 = [](int v) { return v >= 2 && (v & (v - 1)) == 0; };
+  OCC_REQUIRE(pow2(wx) && pow2(wy) && pow2(wz));
+  OCC_REQUIRE((reinterpret_cast<uintptr_t>(mf) & 15) == 0 && (reinterpret_cast<uintptr_t>(membed) & 15) == 0);
+  OCC_CUDA(cudaMemsetAsync(pooled, 0x80, (size_t)B * Xo * Yo * Zo * Q * sizeof(int), stream));
+  OCC_CUDA(cudaMemsetAsync(flag, 0, (size_t)B * Q * sizeof(int), stream));
+  for (int b = 0; b < B; ++b) {
+    GemmParams p{};
+    p.conv = 1;
+    p.Cin = E; p.KX = p.KY = p.KZ = 1; p.dil = 1; p.stride = 1; p.padx = p.pady = p.padz = 0;
+    p.B = 1; p.Xo = X; p.Yo = Y; p.Zo = Z;
+    // voxel box of a tile: prefer a box that contains whole pooling cells (their maxima are then complete inside the
+    // CTA and are written with plain coalesced stores instead of global atomics)
+    p.bz = next_pow2(Z) < BM ? next_pow2(Z) : BM;
+    p.by = next_pow2(Y) < BM / p.bz ? next_pow2(Y) : BM / p.bz;
+    p.bx = BM / (p.bz * p.by);
+    for (int cz = (next_pow2(Z) < 16 ? next_pow2(Z) : 16); cz >= wz; cz >>= 1) {
+      if (cz * wy * wx > BM) continue;
+      int cy = wy, cx = wx;
+      while (cz * cy * cx < BM) {  // grow y / x alternately (powers of two stay multiples of the window)
+        if (cy <= cx) cy *= 2; else cx *= 2;
+      }
+      p.bz = cz; p.by = cy; p.bx = cx;
+      break;
+    }
+    p.pool_complete = (p.bx % wx == 0 && p.by % wy == 0 && p.bz % wz == 0) ? 1 : 0;
+    p.tiles_x = (X + p.bx - 1) / p.bx; p.tiles_y = (Y + p.by - 1) / p.by; p.tiles_z = (Z + p.bz - 1) / p.bz;
+    p.N = Q; p.K = E; p.num_k_blocks = E / BK; p.M = X * Y * Z;
+    float* out_b = mask_out ? mask_out + (size_t)b * X * Y * Z * Q : nullptr;
+    p.out = out_b; p.ldo = Q; p.bias = nullptr; p.residual = nullptr; p.ldr = Q; p.act = 0; p.round_out = 0;
+    p.gn_stats = nullptr; p.cpg = 0; p.rows_per_batch = 0;
+    p.pool_out = pooled + (size_t)b * Xo * Yo * Zo * Q; p.pool_flag = flag + (size_t)b * Q;
+    p.pwx = wx; p.pwy = wy; p.pwz = wz; p.pXo = Xo; p.pYo = Yo; p.pZo = Zo;
+    p.store_out = out_b != nullptr;
+    // cells of one tile: (bx/min(wx,bx)) * (by/min(wy,by)) * (bz/min(wz,bz)) <= 64 (smem pool buffers)
+    const int cwx = wx < p.bx ? wx : p.bx, cwy = wy < p.by ? wy : p.by, cwz = wz < p.bz ? wz : p.bz;
+    OCC_REQUIRE((p.bx / cwx) * (p.by / cwy) * (p.bz / cwz) <= 64);
+    p.pool_cwx = cwx; p.pool_cwy = cwy; p.pool_cwz = cwz; p.pool_ncy = p.by / cwy; p.pool_ncz = p.bz / cwz;
+    {  // in-warp butterfly: the warp's 32 rows are the (ex, ey, ez) sub-box, lane = (lx*ey + ly)*ez + lz
+      const int ez = p.bz < 32 ? p.bz : 32;
+      const int ey = p.by < 32 / ez ? p.by : 32 / ez;
+      const int ex = 32 / (ez * ey);
+      const int rz = wz < ez ? wz : ez, ry = wy < ey ? wy : ey, rx = wx < ex ? wx : ex;
+      int n = 0;
+      for (int o = 1; o < rz; o <<= 1) p.pool_stride[n++] = o;
+      for (int o = 1; o < ry; o <<= 1) p.pool_stride[n++] = o * ez;
+      for (int o = 1; o < rx; o <<= 1) p.pool_stride[n++] = o * ez * ey;
+      p.pool_nsteps = n;
+      OCC_REQUIRE(n >= 2 && n <= 5);  // >= 4 lanes per cell
+    }
+    const float* x = mf + (size_t)b * X * Y * Z * E;
+    CUtensorMap tmA;
+    uint64_t dims[5] = {(uint64_t)E, (uint64_t)Z, (uint64_t)Y, (uint64_t)X, 1};
+    uint64_t strides[4] = {(uint64_t)E * 4, (uint64_t)Z * E * 4, (uint64_t)Y * Z * E * 4, (uint64_t)X * Y * Z * E * 4};
+    uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.bz, (uint32_t)p.by, (uint32_t)p.bx, 1};
+    int rc = make_tmap_f32(&tmA, x, 5, dims, strides, box, nullptr);
+    if (rc) return rc;
+    CUtensorMap tmC = tmA;
+    p.use_tma_store = 0;
+    if (p.store_out) {
+      OCC_REQUIRE((reinterpret_cast<uintptr_t>(out_b) & 15) == 0);
+      // pooled mode keeps the cell maxima in the staging buffers, so the output rows are written directly
+      p.use_tma_store = 0;
+    }
+    rc = dispatch_gemm(tmA, tmC, membed + (size_t)b * Q * E, p, p.tiles_x * p.tiles_y * p.tiles_z, stream);
+    if (rc) return rc;
+  }
+  return OCC_OK;
 }

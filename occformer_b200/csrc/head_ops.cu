@@ -211,7 +211,7 @@ query_head_kernel(const float* __restrict__ query_in, const float* __restrict__ 
 // CTA = (128 q-threads, 4 cells): thread.x <-> query (a voxel's Q logits are one contiguous row -> coalesced 400-byte
 // reads), thread.y <-> one pooled cell; all window loads of a thread are independent (no barriers), 32-bit index math.
 __global__ void __launch_bounds__(512)
-mask_pool_kernel(const float* __restrict__ mask, float* __restrict__ pooled, int* __restrict__ row_flag, int B, int X,
+mask_pool_kernel(const float* __restrict__ mask, int* __restrict__ pooled, int* __restrict__ row_flag, int B, int X,
                  int Y, int Z, int Xo, int Yo, int Zo, int Q) {
   const int q = threadIdx.x;
   const int So = Xo * Yo * Zo;
@@ -233,7 +233,8 @@ mask_pool_kernel(const float* __restrict__ mask, float* __restrict__ pooled, int
 #pragma unroll 4
         for (int z = 0; z < z1 - z0; ++z) m = fmaxf(m, __ldg(p + (size_t)z * Q));
       }
-    pooled[(size_t)cell * Q + q] = m;
+    const int mi = __float_as_int(m);
+    pooled[(size_t)cell * Q + q] = mi >= 0 ? mi : mi ^ 0x7FFFFFFF;  // order-preserving int (sign kept)
     // attn_mask = sigmoid(m) < 0.5  <=>  m < 0 ; a row that is blocked everywhere is un-blocked (:652-653)
     if (!(m < 0.f)) row_flag[b * Q + q] = 1;
   }
@@ -250,12 +251,12 @@ constexpr int XA_TILE = 64;
 
 __global__ void __launch_bounds__(128)
 cross_attn_partial_kernel(const float* __restrict__ qh, const float* __restrict__ Kp, const float* __restrict__ Vp,
-                          int ld, int koff, int voff, const float* __restrict__ pooled,
+                          int ld, int koff, int voff, const int* __restrict__ pooled,
                           const int* __restrict__ row_flag, float* __restrict__ part, int S, int Q, int E, int H,
                           int chunk, int nchunk) {
   __shared__ __align__(16) float sk[XA_TILE][XA_HD];
   __shared__ __align__(16) float sv[XA_TILE][XA_HD];
-  __shared__ float smask[XA_TILE][125];  // pooled mask logits of the key tile, [key][query <= 124 used] (odd pitch: conflict-free)
+  __shared__ int smask[XA_TILE][125];  // pooled mask logits (ordered ints: blocked <=> negative), [key][query]
   const int c = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int t = threadIdx.x;
   const bool active = t < Q;
@@ -289,13 +290,13 @@ cross_attn_partial_kernel(const float* __restrict__ qh, const float* __restrict_
       *reinterpret_cast<float4*>(&sv[r][c4 * 4]) = vv;
     }
     {  // mask tile: n keys x Q logits are one contiguous block of the query-last pooled tensor -> coalesced
-      const float* ptile = pooled + ((size_t)b * S + s0) * Q;
+      const int* ptile = pooled + ((size_t)b * S + s0) * Q;
       for (int i = t; i < n * Q; i += 128) smask[i / Q][i % Q] = __ldg(ptile + i);
     }
     __syncthreads();
     if (active) {
       for (int j = 0; j < n; ++j) {
-        if (use_mask && smask[j][t] < 0.f) continue;
+        if (use_mask && smask[j][t] < 0) continue;
         float s = 0.f;
 #pragma unroll
         for (int d = 0; d < XA_HD; d += 4) {
@@ -668,7 +669,7 @@ extern "C" int occ_query_head(const float* query_in, const float* n2w, const flo
   return OCC_OK;
 }
 
-extern "C" int occ_mask_pool(const float* mask, float* pooled, int* row_flag, int B, int X, int Y, int Z, int Xo,
+extern "C" int occ_mask_pool(const float* mask, int* pooled, int* row_flag, int B, int X, int Y, int Z, int Xo,
                              int Yo, int Zo, int Q, cudaStream_t stream) {
   OCC_REQUIRE(mask && pooled && row_flag && B > 0 && X > 0 && Y > 0 && Z > 0 && Xo > 0 && Yo > 0 && Zo > 0 && Q > 0);
   OCC_REQUIRE(Xo <= X && Yo <= Y && Zo <= Z);
@@ -684,16 +685,17 @@ extern "C" int occ_mask_pool(const float* mask, float* pooled, int* row_flag, in
 }
 
 extern "C" int occ_cross_attn_chunks(int S, int* chunk, int* nchunk) {
-  // chunk size: multiple of XA_TILE, at most 64 chunks... enough CTAs (chunks * heads * B) to fill the machine
-  int c = XA_TILE * 4;  // 256 keys
-  while ((S + c - 1) / c > 96) c *= 2;
+  // a CTA walks its key chunk sequentially (latency ~ chunk length): make chunks as short as possible (>= one 64-key
+  // tile) while keeping the number of partials that cross_merge has to combine <= 96
+  int c = XA_TILE;
+  while ((S + c - 1) / c > 96) c += XA_TILE;
   *chunk = c;
   *nchunk = (S + c - 1) / c;
   return OCC_OK;
 }
 
 extern "C" int occ_cross_attn_partial(const float* qh, const float* Kp, const float* Vp, int ld, int koff, int voff,
-                                      const float* pooled, const int* row_flag, float* part, int B, int S, int Q,
+                                      const int* pooled, const int* row_flag, float* part, int B, int S, int Q,
                                       int E, int H, int chunk, int nchunk, cudaStream_t stream) {
   OCC_REQUIRE(qh && Kp && Vp && pooled && row_flag && part);
   OCC_REQUIRE(B > 0 && S > 0 && Q > 0 && Q <= 124 && H > 0 && E == H * XA_HD && chunk > 0 && chunk % XA_TILE == 0);

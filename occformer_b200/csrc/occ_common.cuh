@@ -67,7 +67,8 @@ inline int sm_count() {
 // fp32 tensor map, rank <= 5, 128-byte swizzle, zero OOB fill.  dims/box/estr innermost first;
 // strides_bytes[i] = byte stride of dim i+1.
 inline int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr) {
+                         const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr,
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return OCC_EDRIVER;
   cuuint64_t d[5], s[4];
@@ -75,7 +76,7 @@ inline int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint6
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = estr ? estr[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), d, s, b, e,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "occ_b200: cuTensorMapEncodeTiled failed (%d) rank=%d\n", (int)r, rank);

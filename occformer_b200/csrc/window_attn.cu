@@ -150,19 +150,17 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         rows[l] = r;
         region[l] = reg;
       }
-      named_bar_sync(2, 128);
-      if (l < 18) {  // shift-mask bookkeeping of the two windows: which keys share region r, and is the window uniform
-        const int hf = l / 9, r = l % 9;
-        unsigned long long same = 0ull;
-        bool uni = true;
-        for (int j = 0; j < WT; ++j) {
-          const int rj = region[hf * 64 + j];
-          if (rj == r) same |= 1ull << j;
-          uni = uni && (rj == region[hf * 64]);
+      {  // shift-mask bookkeeping: same[half][r] = 64-bit set of the window's keys that lie in region r (two warp ballots)
+        const int t = l & 63, wl = l >> 5;  // loader warp wl covers tokens 32*(wl&1) .. +31 of window half wl>>1
+        const bool tok = t < WT;
+        uint32_t* same32 = reinterpret_cast<uint32_t*>(st + WA_OFF_SAME);
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+          const uint32_t bal = __ballot_sync(0xffffffffu, tok && region[l] == r);
+          if (lane == 0) same32[((wl >> 1) * 9 + r) * 2 + (wl & 1)] = bal;
         }
-        reinterpret_cast<unsigned long long*>(st + WA_OFF_SAME)[l] = same;
-        if (r == 0) reinterpret_cast<int*>(st + WA_OFF_UNI)[hf] = uni ? 1 : 0;
       }
+      named_bar_sync(2, 128);
 #pragma unroll 4
       for (int i = 0; i < 24; ++i) {
         const int idx = i * 128 + l;
@@ -225,14 +223,14 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
       long long nq = 0, np = 0;
       while (np < n_units) {
         if (nq < n_units && nq - np < 2 &&
-            mbar_try_wait(&full_bar[nq % WA_STAGES], (uint32_t)((nq / WA_STAGES) & 1))) {
+            mbar_test(&full_bar[nq % WA_STAGES], (uint32_t)((nq / WA_STAGES) & 1))) {
           do_qk(nq);
           ++nq;
         }
         if (np < nq) {
           const int tb = (int)(np & 1);
           const uint32_t k = (uint32_t)(np >> 1);
-          if (mbar_try_wait(&p_ready[tb], k & 1) && mbar_try_wait(&o_free[tb], (k & 1) ^ 1)) {
+          if (mbar_test(&p_ready[tb], k & 1) && mbar_test(&o_free[tb], (k & 1) ^ 1)) {
             do_pv(np);
             ++np;
           }
@@ -257,10 +255,10 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
       tc_fence_after();
       const long long my_row = rows[i];
       const int my_reg = region[i];
-      const bool uniform = reinterpret_cast<const int*>(st + WA_OFF_UNI)[half] != 0;
       // keys that are NOT in this query's region get the additive -100 of the reference's shift mask
-      const unsigned long long diff =
-          uniform ? 0ull : ~reinterpret_cast<const unsigned long long*>(st + WA_OFF_SAME)[half * 9 + my_reg];
+      const uint2 same = reinterpret_cast<const uint2*>(st + WA_OFF_SAME)[half * 9 + my_reg];
+      const uint32_t diff_lo = ~same.x, diff_hi = ~same.y & 0x1FFFFu;  // 49 keys: 32 + 17
+      const bool uniform = (diff_lo | diff_hi) == 0u;  // true for every un-shifted block and for interior windows
       const float4* brow4 = reinterpret_cast<const float4*>(sb + (t < WT ? t : 0) * WA_BIAS_LD);
       const uint32_t s_col = lane_base + tb * 128 + half * 64;
       uint32_t ra[32], rb[32];
@@ -282,7 +280,7 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         for (int e = 0; e < 4; ++e) {
           const int j = 4 * j4 + e;
           float z = fmaf(__uint_as_float(ra[j]), sl2, bb[e]);
-          if (!uniform) z += ((diff >> j) & 1ull) ? neg : 0.f;
+          if (!uniform) z += ((diff_lo >> j) & 1u) ? neg : 0.f;
           ra[j] = __float_as_uint(z);
           mx[e] = fmaxf(mx[e], z);
         }
@@ -296,7 +294,7 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
           const int j = 4 * j4 + e;
           if (32 + j < WT) {
             float z = fmaf(__uint_as_float(rb[j]), sl2, bb[e]);
-            if (!uniform) z += ((diff >> (32 + j)) & 1ull) ? neg : 0.f;
+            if (!uniform) z += ((diff_hi >> j) & 1u) ? neg : 0.f;
             rb[j] = __float_as_uint(z);
             mx[e] = fmaxf(mx[e], z);
           }
@@ -306,7 +304,7 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
       float sm4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float p = round_tf32(exp2f(__uint_as_float(ra[j]) - m));
+        const float p = round_tf32(ex2_approx(__uint_as_float(ra[j]) - m));
         sm4[j & 3] += p;
         ra[j] = __float_as_uint(p);
       }
@@ -314,7 +312,7 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
       for (int j = 0; j < 32; ++j) {
         float p = 0.f;
         if (j < WT - 32) {
-          p = round_tf32(exp2f(__uint_as_float(rb[j]) - m));
+          p = round_tf32(ex2_approx(__uint_as_float(rb[j]) - m));
           sm4[j & 3] += p;
         }
         rb[j] = __float_as_uint(p);

@@ -241,8 +241,9 @@ class _Mask2FormerOccBase(nn.Module):
             if P["kw"][l] is None:
                 Kp.append(None), Vp.append(None), lds.append(0)
                 continue
-            Kp.append(ops.gemm(kpos_r.view(B * S, E), P["kw"][l], bias=P["kb"][l]))
-            Vp.append(ops.gemm(mem_r.view(B * S, E), P["vw"][l], bias=P["vb"][l]))
+            # tf32-rounded outputs: they are tensor-core operands of the cross-attention kernel
+            Kp.append(ops.gemm(kpos_r.view(B * S, E), P["kw"][l], bias=P["kb"][l], round_out=True))
+            Vp.append(ops.gemm(mem_r.view(B * S, E), P["vw"][l], bias=P["vb"][l], round_out=True))
             lds.append(P["kw"][l].shape[0])
         query = self.query_feat.weight.detach().float().unsqueeze(0).expand(B, Q, E).reshape(B * Q, E).contiguous()
         qpos = P["query_pos"]
@@ -253,10 +254,15 @@ class _Mask2FormerOccBase(nn.Module):
                 Ln = P["layers"][next_layer]
                 nq = (qpos, Q, Ln["ca_wqT"], Ln["ca_bq"], scale)
             cls, membed, query, qh = ops.query_head(query_in, P["head"], NC, norm2=norm2, next_q=nq)
-            mask = torch.empty((B, V, Q), dtype=torch.float32, device=query_in.device)
-            for b in range(B):
-                ops.gemm(mf_r[b], membed[b * Q:(b + 1) * Q], out=mask[b])
-            pooled, flag = ops.mask_pool(mask, B, grid, target, Q) if target is not None else (None, None)
+            if target is not None and ops.pool_fusable(grid, target):
+                # einsum + adaptive max pool + threshold bookkeeping in one kernel; the (B,V,Q) logits are only
+                # written when the caller wants every layer's mask_pred
+                mask, pooled, flag = ops.mask_gemm_pool(mf_r, membed, B, grid, target, Q, want_mask=keep_all_masks)
+            else:
+                mask = torch.empty((B, V, Q), dtype=torch.float32, device=query_in.device)
+                for b in range(B):
+                    ops.gemm(mf_r[b], membed[b * Q:(b + 1) * Q], out=mask[b])
+                pooled, flag = ops.mask_pool(mask, B, grid, target, Q) if target is not None else (None, None)
             return cls.view(B, Q, NC), mask, pooled, flag, query, qh
 
         cls_list, mask_list = [], []
@@ -269,7 +275,7 @@ class _Mask2FormerOccBase(nn.Module):
             S = sizes[lvl][0] * sizes[lvl][1] * sizes[lvl][2]
             Lw = P["layers"][i]
             off = P["slots"][i] * E
-            part, nchunk = ops.cross_attn_partial(qh, Kp[lvl], Vp[lvl], lds[lvl], off, off, pooled, flag, B, S, Q, E, H)
+            part, nchunk = ops.cross_attn_tc(qh, Kp[lvl], Vp[lvl], lds[lvl], off, off, pooled, flag, B, S, Q, E, H)
             q1, sa = ops.cross_merge(part, nchunk, H, query, qpos, Q, Lw, scale)
             ybuf = ops.self_attn_ffn(sa, q1, Q, Lw, H)
             last = i == L - 1

@@ -304,14 +304,47 @@ def query_head(query_in, W, NC, norm2=None, next_q=None):
     return cls, membed, query, qh
 
 
+def decode_ordered(t):
+    """order-preserving int32 -> float32 (inverse of the kernels' encoding; used by tests / debugging)."""
+    i = t.to(torch.int32)
+    return torch.where(i >= 0, i, i ^ 0x7FFFFFFF).view(torch.float32)
+
+
 def mask_pool(mask, B, grid, out_grid, Q):
+    """General adaptive max pool of the query-last mask logits -> (pooled ordered-int32 (B,So,Q), flag int32 (B*Q,))."""
     X, Y, Z = grid
     Xo, Yo, Zo = out_grid
-    pooled = torch.empty((B, Xo * Yo * Zo, Q), dtype=torch.float32, device=mask.device)
+    pooled = torch.empty((B, Xo * Yo * Zo, Q), dtype=torch.int32, device=mask.device)
     flag = torch.empty((B * Q,), dtype=torch.int32, device=mask.device)
     check(lib().occ_mask_pool(_ptr(mask), _ptr(pooled), _ptr(flag), B, X, Y, Z, Xo, Yo, Zo, Q, _stream()), "occ_mask_pool")
     LAUNCH_COUNT[0] += 2
     return pooled, flag
+
+
+def pool_fusable(grid, out_grid):
+    """occ_mask_gemm_pool handles windows that are powers of two >= 2 dividing the grid."""
+    for n, o in zip(grid, out_grid):
+        if n % o:
+            return False
+        w = n // o
+        if w < 2 or (w & (w - 1)):
+            return False
+    return True
+
+
+def mask_gemm_pool(mf_r, membed, B, grid, out_grid, Q, want_mask):
+    """mask logits (optional) + pooled attention-mask logits in one tensor-core kernel per sample."""
+    X, Y, Z = grid
+    Xo, Yo, Zo = out_grid
+    E = mf_r.shape[-1]
+    V = X * Y * Z
+    mask = torch.empty((B, V, Q), dtype=torch.float32, device=mf_r.device) if want_mask else None
+    pooled = torch.empty((B, Xo * Yo * Zo, Q), dtype=torch.int32, device=mf_r.device)
+    flag = torch.empty((B * Q,), dtype=torch.int32, device=mf_r.device)
+    check(lib().occ_mask_gemm_pool(_ptr(mf_r), _ptr(membed), _ptr(mask), _ptr(pooled), _ptr(flag), B, X, Y, Z, E, Q, Xo, Yo,
+                                   Zo, _stream()), "occ_mask_gemm_pool")
+    LAUNCH_COUNT[0] += 2 + B
+    return mask, pooled, flag
 
 
 def cross_attn_chunks(S):
@@ -327,6 +360,18 @@ def cross_attn_partial(qh, Kp, Vp, ld, koff, voff, pooled, flag, B, S, Q, E, H):
                                        B, S, Q, E, H, chunk, nchunk, _stream()), "occ_cross_attn_partial")
     LAUNCH_COUNT[0] += 1
     return part, nchunk
+
+
+def cross_attn_tc(qh, Kp, Vp, ld, koff, voff, pooled, flag, B, S, Q, E, H):
+    """Masked cross attention on the tensor cores -> (partials (B,H,npart,Q,34), npart)."""
+    npart = lib().occ_cross_attn_tc_partials(S)
+    part = torch.empty((B, H, npart, Q, 34), dtype=torch.float32, device=qh.device)
+    bits = torch.empty((B, 4 * ((S + 127) // 128), Q), dtype=torch.int32, device=qh.device)
+    check(lib().occ_mask_bits(_ptr(pooled), _ptr(bits), B, S, Q, _stream()), "occ_mask_bits")
+    check(lib().occ_cross_attn_tc(_ptr(qh), _ptr(Kp), _ptr(Vp), ld, koff, voff, _ptr(bits), _ptr(flag), _ptr(part), B, S, Q,
+                                  E, H, _stream()), "occ_cross_attn_tc")
+    LAUNCH_COUNT[0] += 2
+    return part, npart
 
 
 def cross_merge(part, nchunk, H, query, query_pos, Q, L, scale):

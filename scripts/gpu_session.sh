@@ -15,6 +15,7 @@ for s in "$@"; do
     micro)   timeout 600 python scripts/microbench.py > gpurun_out/micro.log 2>&1; echo "micro rc=$?" ;;
     bench)   timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -n 3 gpurun_out/bench.log ;;
     benchref) timeout 900 python bench.py --impl reference --steps 2 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "benchref rc=$?"; tail -n 2 gpurun_out/bench_ref.log ;;
+    ktimes)  timeout 600 python scripts/kernel_times.py gpurun_out/kernel_times.md > gpurun_out/kernel_times.log 2>&1; echo "ktimes rc=$?"; head -n 40 gpurun_out/kernel_times.md ;;
     smoke)   timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 3 gpurun_out/smoke.log ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-1500} -c ${NCU_COUNT:-900} --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?" ;;
     ncu_*)   k=${s#ncu_}; timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 2 -f -o gpurun_out/prof_$k python scripts/microbench.py ${NCU_WHICH:-conv} > gpurun_out/ncu_$k.log 2>&1; echo "ncu $k rc=$?" ;;

@@ -82,10 +82,11 @@ def test_mask_pool_and_flags_exact(cuda):
     for target in [(7, 5, 3), (13, 9, 5), (4, 3, 1), (1, 1, 1)]:
         ref = F.adaptive_max_pool3d(mask, target).flatten(2)  # (B,Q,S)
         ql = mask.flatten(2).permute(0, 2, 1).contiguous().to(cuda)
-        pooled, flag = ops.mask_pool(ql, B, grid, target, Q)
+        pooled_i, flag = ops.mask_pool(ql, B, grid, target, Q)
+        pooled = ops.decode_ordered(pooled_i)
         assert torch.equal(pooled.cpu().permute(0, 2, 1), ref), f"pooled logits differ for {target}"
         blocked = ref.sigmoid() < 0.5
-        assert torch.equal(pooled.cpu().permute(0, 2, 1) < 0, blocked)
+        assert torch.equal(pooled_i.cpu().permute(0, 2, 1) < 0, blocked)
         all_blocked = blocked.sum(-1) == blocked.shape[-1]
         assert torch.equal(flag.cpu().view(B, Q) == 0, all_blocked)
 
@@ -112,3 +113,30 @@ def test_head_kitti_variant_and_errors(cuda):
         head.simple_test(feats, [dict(occ_size=[16, 16, 8], pc_range=PC)])  # CPU tensors: no fallback
     with pytest.raises(NotImplementedError):
         head.forward_train()
+
+
+@pytest.mark.parametrize("grid,target,B", [((16, 12, 4), (8, 6, 2), 1), ((32, 24, 16), (4, 3, 2), 2), ((16, 16, 16), (8, 8, 8), 1),
+                                           ((24, 40, 8), (6, 10, 2), 1)])
+def test_fused_mask_gemm_pool(cuda, grid, target, B):
+    """occ_mask_gemm_pool (einsum + adaptive max pool in the GEMM epilogue) vs torch on tf32-exact operands: the mask
+    logits match the einsum, the pooled logits are exactly the window maxima of the kernel's own mask logits, and the
+    blocked / row-flag bookkeeping follows."""
+    import torch.nn.functional as F
+    from occformer_b200 import ops
+    from util import round_tf32
+    E, Q = 96, 12
+    g = torch.Generator().manual_seed(sum(grid))
+    V = grid[0] * grid[1] * grid[2]
+    mf = round_tf32(torch.randn(B, V, E, generator=g))
+    me = round_tf32(torch.randn(B * Q, E, generator=g) * E ** -0.5)
+    me[3] = -me[3].abs() * 0  # one all-zero query: pooled == 0 -> not blocked anywhere (0 < 0 is False)
+    mask, pooled_i, flag = ops.mask_gemm_pool(mf.to(cuda), me.to(cuda), B, grid, target, Q, want_mask=True)
+    ref = torch.einsum("bvc,bqc->bvq", mf.double(), me.view(B, Q, E).double())
+    assert_close(mask, ref, 2e-5, f"fused mask einsum {grid}")
+    own = mask.cpu().permute(0, 2, 1).reshape(B, Q, *grid)
+    ref_pool = F.adaptive_max_pool3d(own, target).flatten(2).permute(0, 2, 1)  # (B,So,Q)
+    assert torch.equal(ops.decode_ordered(pooled_i).cpu(), ref_pool), f"pooled maxima differ {grid}->{target}"
+    assert torch.equal(flag.cpu().view(B, Q) != 0, (ref_pool >= 0).any(1))
+    # without the mask output (intermediate decoder layers)
+    none, pooled2, flag2 = ops.mask_gemm_pool(mf.to(cuda), me.to(cuda), B, grid, target, Q, want_mask=False)
+    assert none is None and torch.equal(pooled2, pooled_i) and torch.equal(flag2, flag)
