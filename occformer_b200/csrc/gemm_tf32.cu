@@ -25,7 +25,7 @@ constexpr int BM = 128;
 constexpr int BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 4;
 constexpr int EPI_BUF_BYTES = 32 * 128;                 // one 32-row x 32-column fp32 chunk, 128-byte swizzled rows
-constexpr int EPI_BYTES = 4 /*warps*/ * 2 /*buffers*/ * EPI_BUF_BYTES;
+constexpr int EPI_BYTES = 8 /*warps*/ * EPI_BUF_BYTES;
 
 struct GemmParams {
   int M, N, K, num_k_blocks;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void warp_butterfly32(float (&v)[32], int lane) {
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BK * 4;
@@ -131,13 +131,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_ptr);
   if (threadIdx.x >= 128) {
-    for (int i = threadIdx.x - 128; i < 64; i += 128) stat_acc[i] = 0.0;
+    for (int i = threadIdx.x - 128; i < 64; i += 256) stat_acc[i] = 0.0;
   }
   tc_fence_before();
   __syncthreads();
@@ -221,14 +221,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------- epilogue warps
-    const int ew = warp - 4;
+    // eight epilogue warps: two warpgroups share the four TMEM lane quadrants (warp w may only touch lanes
+    // 32*(w%4)..+31); warpgroup 0 drains the even 32-column chunks of every tile, warpgroup 1 the odd ones
+    const int ew = (warp - 4) & 3;   // TMEM lane quadrant = 32-row slab of the tile
+    const int wg = (warp - 4) >> 2;  // 0 / 1
+    const int et = ew * 32 + lane;   // thread index inside the warpgroup
     const int row = ew * 32 + lane;
-    uint8_t* stage_buf = epi_smem + ew * 2 * EPI_BUF_BYTES;
+    uint8_t* stage_buf = epi_smem + (warp - 4) * EPI_BUF_BYTES;
     if (p.pool_out != nullptr) {  // pooled mode never stores through the staging buffers: they hold the cell maxima
-      for (int i = threadIdx.x - 128; i < 8192; i += 128) reinterpret_cast<int*>(epi_smem)[i] = ENC_NEG;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 128; i < 8192; i += 256) reinterpret_cast<int*>(epi_smem)[i] = ENC_NEG;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    int sbuf = 0;
     const bool row_vec = ((reinterpret_cast<uintptr_t>(p.residual) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0 &&
                          p.ldr % 4 == 0 && p.ldo % 4 == 0;
     int it = 0;
@@ -260,37 +263,58 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.rows_per_batch > 0) tile_b = (int)(((long long)m_tile * BM) / p.rows_per_batch);
       }
       const bool valid = m >= 0;
+      // pooled mode: this row's cell inside the tile and the (cell, column) slots this thread drains, once per tile
+      int pool_cl = 0, pool_n = 0;
+      long long pool_dst[8];
+      if (p.pool_out != nullptr) {
+        const int dz = row % p.bz, dy = (row / p.bz) % p.by, dx = row / (p.bz * p.by);
+        pool_cl = ((dx / p.pool_cwx) * p.pool_ncy + dy / p.pool_cwy) * p.pool_ncz + dz / p.pool_cwz;
+        const int ncell = (p.bx / p.pool_cwx) * p.pool_ncy * p.pool_ncz;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          pool_dst[e] = -1;
+          const int i = et + e * 128;
+          if (i < ncell * 32) {
+            pool_n = e + 1;
+            const int cl = i >> 5;
+            const int cz = cl % p.pool_ncz, cy = (cl / p.pool_ncz) % p.pool_ncy, cx = cl / (p.pool_ncz * p.pool_ncy);
+            const int vx = tile_x0 + cx * p.pool_cwx, vy = tile_y0 + cy * p.pool_cwy, vz = tile_z0 + cz * p.pool_cwz;
+            if (vx < p.Xo && vy < p.Yo && vz < p.Zo)
+              pool_dst[e] = ((((long long)tile_b * p.pXo + vx / p.pwx) * p.pYo + vy / p.pwy) * p.pZo + vz / p.pwz) * p.N;
+          }
+        }
+      }
 
       if (p.gn_stats != nullptr && tile_b != cur_b) {
         // flush the per-CTA fp64 partial sums of the previous batch sample
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (cur_b >= 0) {
           const int ngroups2 = 2 * (p.N / p.cpg);
-          for (int i = threadIdx.x - 128; i < ngroups2; i += 128) {
+          for (int i = threadIdx.x - 128; i < ngroups2; i += 256) {
             const double v = stat_acc[i];
             if (v != 0.0) atomicAdd(&p.gn_stats[(size_t)cur_b * ngroups2 + i], v);
             stat_acc[i] = 0.0;
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         cur_b = tile_b;
       }
 
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * BN;
-      // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed
+      // software-pipelined TMEM reads: the load of this warp's next chunk (c+2) is in flight while chunk c is processed
       uint32_t rnext[32];
-      tmem_ld_32x32(t_row, rnext);
+      if (n0 + wg * 32 < p.N && wg < BN / 32) tmem_ld_32x32(t_row + wg * 32, rnext);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = wg; c < BN / 32; c += 2) {
         const int nc = n0 + c * 32;
         if (nc >= p.N) break;
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rnext[j]);
-        if (c + 1 < BN / 32 && nc + 32 < p.N) tmem_ld_32x32(t_row + (c + 1) * 32, rnext);
+        if (c + 2 < BN / 32 && nc + 64 < p.N) tmem_ld_32x32(t_row + (c + 2) * 32, rnext);
         if (p.gn_stats != nullptr) {
           // per-group sum / sumsq of the raw conv output, butterfly-reduced over the 32 rows of the warp
           const int cpg = p.cpg;  // power of two in [1, 32]
@@ -370,7 +394,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // butterfly (lane keeps 32/G column maxima: 32 - 32/G shuffles instead of 32 log2 G), the partial maxima of
           // the four warps meet through smem atomicMax, then one global atomicMax per (cell of the tile, column).
           // Smem buffers alternate per chunk: one named barrier per chunk.
-          int* ps = reinterpret_cast<int*>(epi_smem) + (c & 1) * 4096;  // <= 64 cells x 32 columns per buffer
+          int* ps = reinterpret_cast<int*>(epi_smem) + (wg * 2 + ((c >> 1) & 1)) * 2048;  // <= 32 cells x 32 columns
           {
             float w[32];
 #pragma unroll
@@ -393,25 +417,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 n = half;
               }
             }
-            const int dz = row % p.bz, dy = (row / p.bz) % p.by, dx = row / (p.bz * p.by);
-            const int cl = ((dx / p.pool_cwx) * p.pool_ncy + dy / p.pool_cwy) * p.pool_ncz + dz / p.pool_cwz;
 #pragma unroll
             for (int i = 0; i < 8; ++i)  // G >= 4 lanes per cell in every supported configuration -> n <= 8
-              if (i < n && w[i] > -INFINITY) atomicMax(&ps[cl * 32 + qoff + i], enc_ordered(w[i]));
+              if (i < n && nc + qoff + i < p.N && w[i] > -INFINITY)
+                atomicMax(&ps[pool_cl * 32 + qoff + i], enc_ordered(w[i]));
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          const int ncell = (p.bx / p.pool_cwx) * p.pool_ncy * p.pool_ncz;
-          for (int i = threadIdx.x - 128; i < ncell * 32; i += 128) {
-            const int val = ps[i];
-            ps[i] = ENC_NEG;
-            const int cl = i >> 5, q = nc + (i & 31);
-            if (val == ENC_NEG || q >= p.N) continue;
-            const int cz = cl % p.pool_ncz, cy = (cl / p.pool_ncz) % p.pool_ncy, cx = cl / (p.pool_ncz * p.pool_ncy);
-            const int gx = (tile_x0 + cx * p.pool_cwx) / p.pwx, gy = (tile_y0 + cy * p.pool_cwy) / p.pwy,
-                      gz = (tile_z0 + cz * p.pool_cwz) / p.pwz;
-            int* dst = &p.pool_out[((((size_t)tile_b * p.pXo + gx) * p.pYo + gy) * p.pZo + gz) * p.N + q];
-            if (p.pool_complete) *dst = val; else atomicMax(dst, val);
-            if (val >= 0) p.pool_flag[(size_t)tile_b * p.N + q] = 1;
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory");  // the four warps of this warpgroup
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (e < pool_n) {
+              const int i = et + e * 128;
+              const int val = ps[i];
+              ps[i] = ENC_NEG;
+              const int q = nc + (i & 31);
+              if (val != ENC_NEG && q < p.N && pool_dst[e] >= 0) {
+                int* dst = p.pool_out + pool_dst[e] + q;
+                if (p.pool_complete) *dst = val; else atomicMax(dst, val);
+                if (val >= 0) p.pool_flag[(size_t)tile_b * p.N + q] = 1;
+              }
+            }
           }
         }
         if (!p.store_out) {
@@ -419,8 +443,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else if (p.use_tma_store) {
           // registers -> 128B-swizzled smem chunk (conflict-free) -> one TMA store per warp and chunk; the TMA unit
           // generates the row addresses and clips rows >= M / columns >= N / voxels outside the grid
-          uint8_t* sb = stage_buf + sbuf * EPI_BUF_BYTES;
-          if (lane == 0) tma_store_wait_read<1>();  // the buffer used two chunks ago has been read
+          uint8_t* sb = stage_buf;
+          if (lane == 0) tma_store_wait_read<0>();  // this warp's previous chunk has been read out of the buffer
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -439,7 +463,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             tma_store_commit();
           }
-          sbuf ^= 1;
         } else if (valid) {
           float* orow = p.out + m * p.ldo + nc;
 #pragma unroll
@@ -452,10 +475,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
     if (p.gn_stats != nullptr) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (cur_b >= 0) {
         const int ngroups2 = 2 * (p.N / p.cpg);
-        for (int i = threadIdx.x - 128; i < ngroups2; i += 128) {
+        for (int i = threadIdx.x - 128; i < ngroups2; i += 256) {
           const double v = stat_acc[i];
           if (v != 0.0) atomicAdd(&p.gn_stats[(size_t)cur_b * ngroups2 + i], v);
         }
@@ -498,7 +521,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   if (grid < 1) grid = 1;
-  gemm_tf32_kernel<BN, STAGES><<<grid, 256, smem, stream>>>(tmA, tmB, tmC, p);
+  gemm_tf32_kernel<BN, STAGES><<<grid, 384, smem, stream>>>(tmA, tmB, tmC, p);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -664,7 +687,7 @@ extern "C" int occ_mask_gemm_pool(const float* mf, const float* membed, float* m
     p.store_out = out_b != nullptr;
     // cells of one tile: (bx/min(wx,bx)) * (by/min(wy,by)) * (bz/min(wz,bz)) <= 64 (smem pool buffers)
     const int cwx = wx < p.bx ? wx : p.bx, cwy = wy < p.by ? wy : p.by, cwz = wz < p.bz ? wz : p.bz;
-    OCC_REQUIRE((p.bx / cwx) * (p.by / cwy) * (p.bz / cwz) <= 64);
+    OCC_REQUIRE((p.bx / cwx) * (p.by / cwy) * (p.bz / cwz) <= 32);  // <= 1024 (cell, column) slots: 8 per epilogue thread
     p.pool_cwx = cwx; p.pool_cwy = cwy; p.pool_cwz = cwz; p.pool_ncy = p.by / cwy; p.pool_ncz = p.bz / cwz;
     {  // in-warp butterfly: the warp's 32 rows are the (ex, ey, ez) sub-box, lane = (lx*ey + ly)*ez + lz
       const int ez = p.bz < 32 ? p.bz : 32;
