@@ -391,6 +391,18 @@ def run_b200(args, rank, world, local_rank):
     value = total_samples / (t_dev_ms * 1e-3)
     e2e_val = args.batch * world * e2e_steps / (t_e2e_ms * 1e-3)
 
+    # ---------------------------------------------------------------- the path's only collective: packed metric all-gather
+    # (outside the timed region; synthetic ground truth, so the score itself is meaningless -- the exchange is the point)
+    from occformer_b200 import dist_eval
+    out_dev = step_resident()
+    pred = out_dev.argmax(dim=1)  # (B, X, Y, Z) labels from the class-score volume
+    g = torch.Generator().manual_seed(1234 + rank)
+    gt = torch.randint(0, CLASSES, tuple(pred.shape), generator=g).to(dev)
+    counts = dist_eval.reduce_counts(dist_eval.ssc_counts(pred, gt, CLASSES))
+    scores = dist_eval.ssc_scores(counts.cpu(), CLASSES)
+    eval_info = {"collective": f"all_gather of {counts.numel()} int64 per rank (NCCL)" if world > 1 else "none (1 rank)",
+                 "voxels_scored": int(counts[3:3 + CLASSES].sum() + counts[3 + 2 * CLASSES:].sum()),
+                 "iou_ssc_mean_vs_random_gt": scores["iou_ssc_mean"]}
     if rank != 0:
         return
     roof = time_kernel_family(pipe, dev, peak)
@@ -415,7 +427,7 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": t_e2e_ms / e2e_steps},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "eval": eval_info}
     print(json.dumps(line), flush=True)
 
 

@@ -65,13 +65,19 @@ __device__ __forceinline__ float matvec4(const float* __restrict__ wT, int ldw, 
   float acc[QG];
 #pragma unroll
   for (int r = 0; r < QG; ++r) acc[r] = 0.f;
-  const int kq = K / QG;
-  const int k0 = g * kq, k1 = (g == QG - 1) ? K : k0 + kq;
-#pragma unroll 8
-  for (int k = k0; k < k1; ++k) {
-    const float w = __ldg(wT + (size_t)k * ldw + j);
+  const int kq = K / QG;  // multiple of 4 (K is a multiple of 32)
+  const int k0 = g * kq;
+  // four k per step: 4 independent coalesced weight loads + one LDS.128 per row (xs rows are k-contiguous, 16-byte
+  // aligned: K % 4 == 0), unrolled so that 16 weight loads are in flight
+#pragma unroll 4
+  for (int k = k0; k < k0 + kq; k += 4) {
+    const float w0 = __ldg(wT + (size_t)k * ldw + j), w1 = __ldg(wT + (size_t)(k + 1) * ldw + j),
+                w2 = __ldg(wT + (size_t)(k + 2) * ldw + j), w3 = __ldg(wT + (size_t)(k + 3) * ldw + j);
 #pragma unroll
-    for (int r = 0; r < QG; ++r) acc[r] = fmaf(w, xs[r * K + k], acc[r]);
+    for (int r = 0; r < QG; ++r) {
+      const float4 x = *reinterpret_cast<const float4*>(xs + r * K + k);
+      acc[r] = fmaf(w3, x.w, fmaf(w2, x.z, fmaf(w1, x.y, fmaf(w0, x.x, acc[r]))));
+    }
   }
 #pragma unroll
   for (int r = 0; r < QG; ++r) part[(g * QG + r) * E + j] = acc[r];
@@ -169,7 +175,7 @@ query_head_kernel(const float* __restrict__ query_in, const float* __restrict__ 
                   float* __restrict__ cls_out, float* __restrict__ membed_out, const float* __restrict__ query_pos,
                   int Q, const float* __restrict__ wqT, const float* __restrict__ bq, float scale,
                   float* __restrict__ qh_out, int rows, int E) {
-  extern __shared__ float sm[];  // xs[QG*E], part[QG*QG*E], red[32]
+  extern __shared__ __align__(16) float sm[];  // xs[QG*E], part[QG*QG*E], red[32]
   float* xs = sm;
   float* part = xs + QG * E;
   float* red = part + QG * QG * E;
@@ -340,7 +346,7 @@ cross_merge_kernel(const float* __restrict__ part_in, int nchunk, int H, const f
                    const float* __restrict__ bo, const float* __restrict__ n0w, const float* __restrict__ n0b,
                    const float* __restrict__ sa_inT /*(E, 3E) K-major*/, const float* __restrict__ sa_inb, float scale,
                    float* __restrict__ query1, float* __restrict__ sa_qkv /*(rows, 3E)*/, int rows, int E) {
-  extern __shared__ float sm[];  // xs[QG*E], ps[QG*E], part[QG*QG*E], red[32]
+  extern __shared__ __align__(16) float sm[];  // xs[QG*E], ps[QG*E], part[QG*QG*E], red[32]
   float* xs = sm;
   float* ps = xs + QG * E;
   float* part = ps + QG * E;
@@ -386,7 +392,7 @@ self_attn_kernel(const float* __restrict__ sa_qkv, const float* __restrict__ que
                  const float* __restrict__ woT, const float* __restrict__ bo, const float* __restrict__ n1w,
                  const float* __restrict__ n1b, const float* __restrict__ f2b, float* __restrict__ x1,
                  float* __restrict__ ybuf, int E) {
-  extern __shared__ float sm[];  // xs[QG*E], part[QG*QG*E], red[32]
+  extern __shared__ __align__(16) float sm[];  // xs[QG*E], part[QG*QG*E], red[32]
   float* xs = sm;
   float* part = xs + QG * E;
   float* red = part + QG * QG * E;
@@ -439,7 +445,7 @@ self_attn_kernel(const float* __restrict__ sa_qkv, const float* __restrict__ que
 __global__ void __launch_bounds__(1024)
 ffn_block_kernel(const float* __restrict__ x1, const float* __restrict__ f1T /*(E, F)*/, const float* __restrict__ f1b,
                  const float* __restrict__ f2T /*(F, E)*/, int F, float* __restrict__ ybuf, int E) {
-  extern __shared__ float sm[];  // xs[QG*E], hs[QG*E], part[QG*QG*E]
+  extern __shared__ __align__(16) float sm[];  // xs[QG*E], hs[QG*E], part[QG*QG*E]
   float* xs = sm;
   float* hs = xs + QG * E;
   float* part = hs + QG * E;

@@ -40,7 +40,8 @@ constexpr int WA_OFF_ROWS = 3 * WA_TILE;               // 49152 (8-byte aligned)
 constexpr int WA_OFF_REGION = WA_OFF_ROWS + 128 * 8;   // 50176
 constexpr int WA_OFF_SAME = WA_OFF_REGION + 128 * 4;   // 50688: per window half, 9 x uint64 "key j is in region r" masks
 constexpr int WA_OFF_UNI = WA_OFF_SAME + 2 * 9 * 8;    // 50832: per window half, 1 if all 49 tokens share a region
-constexpr int WA_STAGE_BYTES = 50 * 1024;              // 51200 >= 50840, multiple of 1024
+constexpr int WA_OFF_SRC = WA_OFF_UNI + 8;             // 50840: per row, the global source pointer of its q slice (8 B)
+constexpr int WA_STAGE_BYTES = 51 * 1024;              // 52224 >= 50840 + 1024, multiple of 1024
 constexpr int WA_BIAS_LD = 52;                         // padded bias row pitch (floats): 13 conflict-free LDS.128 per row
 constexpr int WA_BIAS_BYTES = 10240;                   // resident bias of this CTA's head, (49, 52) floats, * log2(e)
 constexpr int WA_THREADS = 512;
@@ -149,6 +150,9 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         }
         rows[l] = r;
         region[l] = reg;
+        // global address of this token's q head-slice (k / v follow at +C / +2C floats); pad tokens read the qkv bias
+        reinterpret_cast<const float**>(st + WA_OFF_SRC)[l] =
+            r >= 0 ? qkv + r * 3 * C + h * HD : (r == -1 ? qkv_bias + h * HD : nullptr);
       }
       {  // shift-mask bookkeeping: same[half][r] = 64-bit set of the window's keys that lie in region r (two warp ballots)
         const int t = l & 63, wl = l >> 5;  // loader warp wl covers tokens 32*(wl&1) .. +31 of window half wl>>1
@@ -161,21 +165,30 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         }
       }
       named_bar_sync(2, 128);
-#pragma unroll 4
-      for (int i = 0; i < 24; ++i) {
-        const int idx = i * 128 + l;
-        const int tile = idx >> 10, rem = idx & 1023;
-        const int r = rem >> 3, c = rem & 7;
-        // Q, K: K-major SWIZZLE_128B (16-byte chunk c ^ (r & 7)); V: MN-major tf32 operand = SWIZZLE_128B_BASE32B
-        // (32-byte chunk (c >> 1) ^ (r & 3)) -- the only legal layout for a transposed 32-bit operand
-        const int off = tile < 2 ? ((c ^ (r & 7)) << 4) : ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));
-        uint8_t* dst = st + tile * WA_TILE + r * 128 + off;
-        const long long row = rows[r];
-        if (row == -2) {
-          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          const float* src = (row >= 0 ? qkv + row * 3 * C : qkv_bias) + tile * C + h * HD + c * 4;
-          cp_async_16(dst, src);
+      // thread l copies 16-byte chunk c = l & 7 of rows (l >> 3) + 16*rr, rr = 0..7, for the three tiles.  (r & 7) and
+      // (r & 3) do not depend on rr, so the swizzled chunk offsets are per-thread constants:
+      //   Q, K: K-major SWIZZLE_128B (16-byte chunk c ^ (r & 7));  V: MN-major tf32 operand = SWIZZLE_128B_BASE32B
+      //   (32-byte chunk (c >> 1) ^ (r & 3)) -- the only legal layout for a transposed 32-bit operand
+      {
+        const int c = l & 7, rb = l >> 3;
+        const int off_qk = (c ^ (rb & 7)) << 4;
+        const int off_v = (((c >> 1) ^ (rb & 3)) << 5) | ((c & 1) << 4);
+        const float* const* srcp = reinterpret_cast<const float* const*>(st + WA_OFF_SRC);
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = rb + 16 * rr;
+          uint8_t* drow = st + r * 128;
+          const float* src = srcp[r];
+          if (src == nullptr) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(drow + off_qk) = z;
+            *reinterpret_cast<float4*>(drow + WA_TILE + off_qk) = z;
+            *reinterpret_cast<float4*>(drow + 2 * WA_TILE + off_v) = z;
+          } else {
+            cp_async_16(drow + off_qk, src + c * 4);
+            cp_async_16(drow + WA_TILE + off_qk, src + C + c * 4);
+            cp_async_16(drow + 2 * WA_TILE + off_v, src + 2 * C + c * 4);
+          }
         }
       }
       cp_async_mbar_arrive_noinc(&full_bar[s]);  // fires when this thread's copies of the unit have landed
