@@ -68,17 +68,20 @@ __device__ __forceinline__ void warp_layernorm(float4 (&v)[NV], int C, const flo
 //   tok   : (B*X*Y*(Z+1), C) <- relu(gn(y)) and its mean over Z (dualpath_block.py:69)
 //   tokn  : same rows, LayerNorm1'd and rounded to tf32 (operand of the QKV GEMM; window_attention.py:355)
 // One CTA handles `cols` (b,x,y) columns, one warp per voxel row; the CTA's smem holds the column for the mean.
-template <int NV>
+// R voxel rows (consecutive z of one column) per warp: all R row loads are issued before any of them is consumed, so a
+// warp keeps R x 512 B (C = 128) in flight -- with one row per warp the kernel sat at 2.4 TB/s on latency alone.
+template <int NV, int R>
 __global__ void __launch_bounds__(512)
 gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gn_w,
                         const float* __restrict__ gn_b, const float* __restrict__ ln_w,
                         const float* __restrict__ ln_b, float* __restrict__ tok, float* __restrict__ tokn, int B,
                         int XY, int Z, int C, int groups, int cols) {
   extern __shared__ float col_smem[];  // [cols][Z][C]
-  __shared__ float s_mean[8][32], s_rstd[8][32];  // GroupNorm mean / rstd per (column of this CTA, group): the fp64
-                                                  // division + sqrt runs once per CTA, not once per lane and row
+  __shared__ float s_mean[16][32], s_rstd[16][32];  // GroupNorm mean / rstd per (column of this CTA, group): the fp64
+                                                    // division + sqrt runs once per CTA, not once per lane and row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col_local = warp / Z, z = warp % Z;
+  const int wpc = Z / R;  // warps per column
+  const int col_local = warp / wpc, z0 = (warp % wpc) * R;
   const long long col = (long long)blockIdx.x * cols + col_local;  // (b*XY + xy)
   const long long ncols = (long long)B * XY;
   const bool active = col_local < cols && col < ncols;
@@ -90,33 +93,42 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
     if (cc < ncols) gn_mean_rstd(stats, (int)(cc / XY), groups, g, count, &s_mean[cl][g], &s_rstd[cl][g]);
   }
   __syncthreads();
-  float4 v[NV];
+  float4 v[R][NV];
   if (active) {
-    const int b = (int)(col / XY);
-    const long long row = col * Z + z;
-    const float4* src = reinterpret_cast<const float4*>(y + row * C);
+    const long long row0 = col * Z + z0;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c0 = (i * 32 + lane) * 4;
-      float4 t = __ldcs(src + i * 32 + lane);
-      const float mean = s_mean[col_local][c0 / cpg], rstd = s_rstd[col_local][c0 / cpg];  // cpg >= 4: one group per float4
-      const float4 g = *reinterpret_cast<const float4*>(gn_w + c0);
-      const float4 bb = *reinterpret_cast<const float4*>(gn_b + c0);
-      t.x = fmaxf((t.x - mean) * rstd * g.x + bb.x, 0.f);
-      t.y = fmaxf((t.y - mean) * rstd * g.y + bb.y, 0.f);
-      t.z = fmaxf((t.z - mean) * rstd * g.z + bb.z, 0.f);
-      t.w = fmaxf((t.w - mean) * rstd * g.w + bb.w, 0.f);
-      v[i] = t;
-      *reinterpret_cast<float4*>(tok + row * C + c0) = t;
-      *reinterpret_cast<float4*>(col_smem + ((size_t)col_local * Z + z) * C + c0) = t;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        v[r][i] = __ldcs(reinterpret_cast<const float4*>(y + (row0 + r) * C) + i * 32 + lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c0 = (i * 32 + lane) * 4;
+        float4 t = v[r][i];
+        const float mean = s_mean[col_local][c0 / cpg], rstd = s_rstd[col_local][c0 / cpg];  // cpg >= 4
+        const float4 g = *reinterpret_cast<const float4*>(gn_w + c0);
+        const float4 bb = *reinterpret_cast<const float4*>(gn_b + c0);
+        t.x = fmaxf((t.x - mean) * rstd * g.x + bb.x, 0.f);
+        t.y = fmaxf((t.y - mean) * rstd * g.y + bb.y, 0.f);
+        t.z = fmaxf((t.z - mean) * rstd * g.z + bb.z, 0.f);
+        t.w = fmaxf((t.w - mean) * rstd * g.w + bb.w, 0.f);
+        v[r][i] = t;
+        *reinterpret_cast<float4*>(tok + (row0 + r) * C + c0) = t;
+        *reinterpret_cast<float4*>(col_smem + ((size_t)col_local * Z + z0 + r) * C + c0) = t;
+      }
     }
-    warp_layernorm<NV>(v, C, ln_w, ln_b, lane, true);
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      *reinterpret_cast<float4*>(tokn + row * C + (i * 32 + lane) * 4) = v[i];
+    for (int r = 0; r < R; ++r) {
+      warp_layernorm<NV>(v[r], C, ln_w, ln_b, lane, true);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        *reinterpret_cast<float4*>(tokn + (row0 + r) * C + (i * 32 + lane) * 4) = v[r][i];
+    }
   }
   __syncthreads();
-  if (active && z == 0) {
+  if (active && z0 == 0) {
     const long long brow = ncols * Z + col;
     const float inv = 1.0f / (float)Z;
 #pragma unroll
@@ -128,13 +140,13 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
         a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
       }
       a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
-      v[i] = a;
+      v[0][i] = a;
       *reinterpret_cast<float4*>(tok + brow * C + c0) = a;
     }
-    warp_layernorm<NV>(v, C, ln_w, ln_b, lane, true);
+    warp_layernorm<NV>(v[0], C, ln_w, ln_b, lane, true);
 #pragma unroll
     for (int i = 0; i < NV; ++i)
-      *reinterpret_cast<float4*>(tokn + brow * C + (i * 32 + lane) * 4) = v[i];
+      *reinterpret_cast<float4*>(tokn + brow * C + (i * 32 + lane) * 4) = v[0][i];
   }
 }
 
@@ -347,15 +359,26 @@ extern "C" int occ_gn_relu_zmean_ln(const float* y, const double* stats, const f
   OCC_REQUIRE(y && stats && gn_w && gn_b && ln_w && ln_b && tok && tokn);
   OCC_REQUIRE(B > 0 && XY > 0 && Z > 0 && Z <= 16 && C % 128 == 0 && groups > 0 && groups <= 32 && C % groups == 0 &&
               (C / groups) % 4 == 0);
-  int cols = 8 / Z;
+  // rows per warp: 4 for the narrow (C = 128) stage when Z allows it, else 1; 16 warps per CTA where possible
+  const int R = (C == 128 && Z % 4 == 0) ? 4 : 1;
+  const int wpc = Z / R;
+  int cols = 16 / wpc;
   if (cols < 1) cols = 1;
+  if (cols > 16) cols = 16;
+  while ((size_t)cols * Z * C * 4 > 48 * 1024 && cols > 1) cols >>= 1;
   const size_t smem = (size_t)cols * Z * C * 4;
   OCC_REQUIRE(smem <= 48 * 1024);
   const long long ncols = (long long)B * XY;
   const int blocks = (int)((ncols + cols - 1) / cols);
-  const int threads = cols * Z * 32;
-  DISPATCH_NV(C, (gn_relu_zmean_ln_kernel<NV><<<blocks, threads, smem, stream>>>(y, stats, gn_w, gn_b, ln_w, ln_b, tok,
-                                                                               tokn, B, XY, Z, C, groups, cols)));
+  const int threads = cols * wpc * 32;
+  OCC_REQUIRE(threads <= 512);
+  if (R == 4) {
+    gn_relu_zmean_ln_kernel<1, 4><<<blocks, threads, smem, stream>>>(y, stats, gn_w, gn_b, ln_w, ln_b, tok, tokn, B, XY, Z,
+                                                                     C, groups, cols);
+  } else {
+    DISPATCH_NV(C, (gn_relu_zmean_ln_kernel<NV, 1><<<blocks, threads, smem, stream>>>(y, stats, gn_w, gn_b, ln_w, ln_b, tok,
+                                                                                    tokn, B, XY, Z, C, groups, cols)));
+  }
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

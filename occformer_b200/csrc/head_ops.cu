@@ -493,27 +493,36 @@ classmix_kernel(const float* __restrict__ mask, const float* __restrict__ cls, f
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
   if (identity) {
-    // coalesced stage of CM_THREADS voxel rows (Q floats each) through shared memory
+    // coalesced stage of CM_THREADS voxel rows (Q floats each, Q % 4 == 0) through shared memory: warp w copies rows
+    // w, w+4, ... with one float4 per lane; row pitch Q + 4 keeps the rows 16-byte aligned
+    const int QP = Q + 4;
     const int nrows = (int)min((long long)CM_THREADS, Vo - v0);
     const float* src = mask + ((size_t)b * Vo + v0) * Q;
-    {  // warp w copies rows w, w+4, ...: lanes stride over the Q contiguous floats of a row (no integer division)
+    {
       const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+      const int q4n = Q >> 2;
       for (int r = w; r < nrows; r += CM_THREADS / 32) {
-        const float* rs = src + (size_t)r * Q;
-        float* rd = rows + r * (Q + 1);
-        for (int c = l; c < Q; c += 32) rd[c] = __ldcs(rs + c);
+        const float4* rs = reinterpret_cast<const float4*>(src + (size_t)r * Q);
+        float4* rd = reinterpret_cast<float4*>(rows + r * QP);
+        for (int c = l; c < q4n; c += 32) rd[c] = __ldcs(rs + c);
       }
     }
     __syncthreads();
     if (v < Vo) {
-      const float* r = rows + threadIdx.x * (Q + 1);
-      for (int q = 0; q < Q; ++q) {
-        const float s = 1.0f / (1.0f + expf(-r[q]));
+      const float4* r4 = reinterpret_cast<const float4*>(rows + threadIdx.x * QP);
+      for (int q4 = 0; q4 < (Q >> 2); ++q4) {
+        const float4 lv = r4[q4];
+        const float lg[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
-        for (int k = 0; k < KMAX; k += 4) {
-          const float4 pp = *reinterpret_cast<const float4*>(P + q * KMAX + k);
-          acc[k] = fmaf(pp.x, s, acc[k]); acc[k + 1] = fmaf(pp.y, s, acc[k + 1]);
-          acc[k + 2] = fmaf(pp.z, s, acc[k + 2]); acc[k + 3] = fmaf(pp.w, s, acc[k + 3]);
+        for (int e = 0; e < 4; ++e) {
+          const float s = 1.0f / (1.0f + __expf(-lg[e]));
+          const float* pq = P + (4 * q4 + e) * KMAX;
+#pragma unroll
+          for (int k = 0; k < KMAX; k += 4) {
+            const float4 pp = *reinterpret_cast<const float4*>(pq + k);
+            acc[k] = fmaf(pp.x, s, acc[k]); acc[k + 1] = fmaf(pp.y, s, acc[k + 1]);
+            acc[k + 2] = fmaf(pp.z, s, acc[k + 2]); acc[k + 3] = fmaf(pp.w, s, acc[k + 3]);
+          }
         }
       }
     }
@@ -749,7 +758,8 @@ extern "C" int occ_classmix(const float* mask, const float* cls, float* out, int
   OCC_REQUIRE(NC >= 2 && NC - 1 <= 32 && B <= 65535);
   const long long Vo = (long long)Xo * Yo * Zo;
   const int kmax = (NC - 1 <= 20) ? 20 : 32;
-  const size_t smem = ((size_t)Q * kmax + (size_t)CM_THREADS * (Q + 1)) * sizeof(float);
+  OCC_REQUIRE(Q % 4 == 0);
+  const size_t smem = ((size_t)Q * kmax + (size_t)CM_THREADS * (Q + 4)) * sizeof(float);
   OCC_REQUIRE(smem <= 200 * 1024);
   dim3 grid((unsigned)((Vo + CM_THREADS - 1) / CM_THREADS), B);
   if (NC - 1 <= 20) {

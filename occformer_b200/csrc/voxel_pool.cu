@@ -166,8 +166,16 @@ vp_pool_kernel(const int* __restrict__ starts, const int* __restrict__ order, in
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int C4 = C >> 2;
-  for (int v = blockIdx.x * warps_per_block + (threadIdx.x >> 5); v < V; v += gridDim.x * warps_per_block) {
-    const int s0 = starts[v], s1 = starts[v + 1];
+  const int nbatch = (V + 31) >> 5;
+  // a warp owns 32 consecutive voxels per iteration: their interval bounds arrive with two coalesced loads (instead of
+  // two dependent scalar loads per voxel) and the warp streams 32 x C floats of contiguous output
+  for (int batch = blockIdx.x * warps_per_block + (threadIdx.x >> 5); batch < nbatch; batch += gridDim.x * warps_per_block) {
+    const int vb = batch << 5;
+    const int my_s0 = starts[min(vb + lane, V)], my_s1 = starts[min(vb + lane + 1, V)];
+    const int nv = min(32, V - vb);
+    for (int vi = 0; vi < nv; ++vi) {
+    const int v = vb + vi;
+    const int s0 = __shfl_sync(0xffffffffu, my_s0, vi), s1 = __shfl_sync(0xffffffffu, my_s1, vi);
     float4* orow = reinterpret_cast<float4*>(out + (size_t)v * C);
     for (int cbase = 0; cbase < C4; cbase += 32) {
       const int c4 = cbase + lane;
@@ -214,6 +222,7 @@ vp_pool_kernel(const int* __restrict__ starts, const int* __restrict__ order, in
         }
       }
       if (c4 < C4) __stcs(orow + c4, acc);  // streaming store: the grid is consumed by the next kernel from HBM/L2
+    }
     }
   }
 }

@@ -18,6 +18,8 @@ for s in "$@"; do
     ktimes)  timeout 600 python scripts/kernel_times.py gpurun_out/kernel_times.md > gpurun_out/kernel_times.log 2>&1; echo "ktimes rc=$?"; head -n 40 gpurun_out/kernel_times.md ;;
     smoke)   timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 3 gpurun_out/smoke.log ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-1500} -c ${NCU_COUNT:-900} --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?" ;;
+    ncupool) timeout 900 ncu --set full --clock-control none --import-source on -k regex:vp_ -s 12 -c 6 -f -o gpurun_out/prof_vp_pool python scripts/microbench.py pool > gpurun_out/ncu_vp_pool.log 2>&1; echo "ncupool rc=$?" ;;
+    ncuhead) timeout 900 ncu --set full --clock-control none --import-source on -k regex:cross_attn_tc -s 11 -c 1 -f -o gpurun_out/prof_cross_attn python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_cross_attn.log 2>&1; echo "ncuhead rc=$?" ;;
     ncu_*)   k=${s#ncu_}; timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 2 -f -o gpurun_out/prof_$k python scripts/microbench.py ${NCU_WHICH:-conv} > gpurun_out/ncu_$k.log 2>&1; echo "ncu $k rc=$?" ;;
     *) echo "unknown stage $s" ;;
   esac

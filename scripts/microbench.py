@@ -34,7 +34,7 @@ def timeit(fn, iters=5, warm=2):
 
 def main():
     res = {}
-    which = sys.argv[1:] or ["pool", "gemm", "conv", "attn", "block"]
+    which = sys.argv[1:] or ["pool", "fill", "gemm", "conv", "attn", "block"]
     X, Y, Z, C = 200, 200, 16, 128
     if "pool" in which:
         from oracle import port  # geometry only (inputs), not on the measured path
@@ -53,6 +53,15 @@ def main():
         res["lift_splat_GBps_fused_formula"] = alg / t / 1e6
         t2 = timeit(lambda: ops.lift_prologue(dd, feat))
         res["lift_prologue_ms"] = t2
+    if "fill" in which:
+        big = torch.empty(1, X, Y, Z, C, device=dev)
+        t = timeit(lambda: big.zero_())
+        res["torch_zero_328MB_ms"] = t
+        res["torch_zero_GBps"] = big.numel() * 4 / t / 1e6
+        src = torch.randn(1, X, Y, Z, C, device=dev)
+        t = timeit(lambda: big.copy_(src))
+        res["torch_copy_328MB_ms"] = t
+        res["torch_copy_GBps(read+write)"] = 2 * big.numel() * 4 / t / 1e6
     if "gemm" in which:
         M = X * Y * (Z + 1)
         a = torch.randn(M, C, device=dev)
