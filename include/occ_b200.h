@@ -169,9 +169,10 @@ int occ_self_attn_ffn(const float* sa_qkv, const float* query1, int Q, const flo
                       const float* n1w, const float* n1b, const float* f1T, const float* f1b, const float* f2T,
                       const float* f2b, int F, float* x1, float* ybuf, int rows, int E, int H, occ_stream_t stream);
 /* simple_test tail (:725-736, format_results :691-696): trilinear upsample (align_corners=True) -> sigmoid ->
- * einsum with softmax(cls)[..., :-1]; mask (B, X*Y*Z, Q), cls (B, Q, NC) -> out (B, NC-1, Xo, Yo, Zo) */
-int occ_classmix(const float* mask, const float* cls, float* out, int B, int X, int Y, int Z, int Xo, int Yo, int Zo,
-                 int Q, int NC, occ_stream_t stream);
+ * einsum with softmax(cls)[..., :-1]; mask (B, X*Y*Z, Q), cls (B, Q, NC) -> out (B, NC-1, Xo, Yo, Zo); labels (optional,
+ * (B, Xo, Yo, Zo) uint8) = argmax over the class axis (post_process_semantic, occupancyformer.py:238-243) */
+int occ_classmix(const float* mask, const float* cls, float* out, unsigned char* labels, int B, int X, int Y, int Z,
+                 int Xo, int Yo, int Zo, int Q, int NC, occ_stream_t stream);
 /* (B, S, Q) -> (B, Q, S): the reference's mask_pred layout, for forward()'s return value */
 int occ_transpose_sq(const float* in, float* out, int B, long long S, int Q, occ_stream_t stream);
 /* forward_lidarseg eval branch (:505-542): grid_sample of one sample's class volume (K,X,Y,Z) at n points

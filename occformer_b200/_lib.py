@@ -46,7 +46,7 @@ SIGNATURES = {
     "occ_cross_attn_tc": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P] + [c_int] * 5 + [STREAM]),
     "occ_cross_merge": (c_int, [P, c_int, c_int, P, P, c_int, P, P, P, P, P, P, c_float, P, P, c_int, c_int, STREAM]),
     "occ_self_attn_ffn": (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, STREAM]),
-    "occ_classmix": (c_int, [P, P, P] + [c_int] * 9 + [STREAM]),
+    "occ_classmix": (c_int, [P, P, P, P] + [c_int] * 9 + [STREAM]),
     "occ_transpose_sq": (c_int, [P, P, c_int, c_longlong, c_int, STREAM]),
     "occ_lidarseg_points": (c_int, [P, P, c_int, c_int] + [c_float] * 6 + [c_int] * 5 + [P, STREAM]),
 }

@@ -469,8 +469,8 @@ constexpr int CM_THREADS = 128;
 
 template <int KMAX>
 __global__ void __launch_bounds__(CM_THREADS)
-classmix_kernel(const float* __restrict__ mask, const float* __restrict__ cls, float* __restrict__ out, int X, int Y,
-                int Z, int Xo, int Yo, int Zo, int Q, int NC) {
+classmix_kernel(const float* __restrict__ mask, const float* __restrict__ cls, float* __restrict__ out,
+                unsigned char* __restrict__ labels, int X, int Y, int Z, int Xo, int Yo, int Zo, int Q, int NC) {
   extern __shared__ __align__(16) float sm[];  // P[Q][KMAX] (zero padded), rows[CM_THREADS][Q+1] (identity path)
   const int K = NC - 1;
   float* P = sm;
@@ -564,9 +564,15 @@ classmix_kernel(const float* __restrict__ mask, const float* __restrict__ cls, f
     }
   }
   if (v < Vo) {
+    float best = -INFINITY;
+    int arg = 0;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
-      if (k < K) __stcs(out + ((size_t)b * K + k) * Vo + v, acc[k]);
+      if (k < K) {
+        __stcs(out + ((size_t)b * K + k) * Vo + v, acc[k]);
+        if (acc[k] > best) { best = acc[k]; arg = k; }  // first maximum, like torch.argmax
+      }
+    if (labels) labels[(size_t)b * Vo + v] = (unsigned char)arg;
   }
 }
 
@@ -752,8 +758,8 @@ extern "C" int occ_self_attn_ffn(const float* sa_qkv, const float* query1, int Q
   return OCC_OK;
 }
 
-extern "C" int occ_classmix(const float* mask, const float* cls, float* out, int B, int X, int Y, int Z, int Xo, int Yo,
-                            int Zo, int Q, int NC, cudaStream_t stream) {
+extern "C" int occ_classmix(const float* mask, const float* cls, float* out, unsigned char* labels, int B, int X, int Y,
+                            int Z, int Xo, int Yo, int Zo, int Q, int NC, cudaStream_t stream) {
   OCC_REQUIRE(mask && cls && out && B > 0 && X > 0 && Y > 0 && Z > 0 && Xo > 0 && Yo > 0 && Zo > 0 && Q > 0);
   OCC_REQUIRE(NC >= 2 && NC - 1 <= 32 && B <= 65535);
   const long long Vo = (long long)Xo * Yo * Zo;
@@ -768,14 +774,14 @@ extern "C" int occ_classmix(const float* mask, const float* cls, float* out, int
       OCC_CUDA(cudaFuncSetAttribute(classmix_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
-    classmix_kernel<20><<<grid, CM_THREADS, smem, stream>>>(mask, cls, out, X, Y, Z, Xo, Yo, Zo, Q, NC);
+    classmix_kernel<20><<<grid, CM_THREADS, smem, stream>>>(mask, cls, out, labels, X, Y, Z, Xo, Yo, Zo, Q, NC);
   } else {
     static bool configured = false;
     if (!configured) {
       OCC_CUDA(cudaFuncSetAttribute(classmix_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
-    classmix_kernel<32><<<grid, CM_THREADS, smem, stream>>>(mask, cls, out, X, Y, Z, Xo, Yo, Zo, Q, NC);
+    classmix_kernel<32><<<grid, CM_THREADS, smem, stream>>>(mask, cls, out, labels, X, Y, Z, Xo, Yo, Zo, Q, NC);
   }
   OCC_LAUNCH_CHECK();
   return OCC_OK;

@@ -173,7 +173,21 @@ vp_pool_kernel(const int* __restrict__ starts, const int* __restrict__ order, in
     const int vb = batch << 5;
     const int my_s0 = starts[min(vb + lane, V)], my_s1 = starts[min(vb + lane + 1, V)];
     const int nv = min(32, V - vb);
-    for (int vi = 0; vi < nv; ++vi) {
+    // empty voxels (77 % of a nuScenes grid) first, as a plain zero stream; then the occupied ones
+    uint32_t occupied = __ballot_sync(0xffffffffu, lane < nv && my_s1 > my_s0);
+    {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int cbase = 0; cbase < C4; cbase += 32) {
+        if (cbase + lane < C4) {
+#pragma unroll 8
+          for (int vi = 0; vi < nv; ++vi)
+            if (!((occupied >> vi) & 1u)) __stcs(reinterpret_cast<float4*>(out + (size_t)(vb + vi) * C) + cbase + lane, z4);
+        }
+      }
+    }
+    while (occupied) {
+    const int vi = __ffs(occupied) - 1;
+    occupied &= occupied - 1;
     const int v = vb + vi;
     const int s0 = __shfl_sync(0xffffffffu, my_s0, vi), s1 = __shfl_sync(0xffffffffu, my_s1, vi);
     float4* orow = reinterpret_cast<float4*>(out + (size_t)v * C);

@@ -308,8 +308,10 @@ class _Mask2FormerOccBase(nn.Module):
         cls, mask = cls_list[-1].contiguous(), masks[-1]
         B, Q, NC = cls.shape
         occ_size = tuple(int(v) for v in img_metas[0]["occ_size"])
-        out = ops.classmix(mask, cls, B, grid, occ_size, Q, NC)
-        res = {"output_voxels": [out], "output_points": None}
+        out, labels = ops.classmix(mask, cls, B, grid, occ_size, Q, NC, with_labels=True)
+        # 'output_labels' is an addition to the reference's dict: argmax over classes (what its evaluation loop
+        # derives from output_voxels, occupancyformer.py:238-243), produced by the same kernel
+        res = {"output_voxels": [out], "output_points": None, "output_labels": labels}
         if self.lidarseg and points is not None:
             res["output_points"] = self.forward_lidarseg(cls, mask, points, img_metas, _grid=grid,
                                                          _native=out if occ_size == grid else None)

@@ -398,13 +398,15 @@ def self_attn_ffn(sa, q1, Q, L, H):
     return ybuf
 
 
-def classmix(mask, cls, B, grid, out_grid, Q, NC):
+def classmix(mask, cls, B, grid, out_grid, Q, NC, with_labels=False):
     X, Y, Z = grid
     Xo, Yo, Zo = out_grid
     out = torch.empty((B, NC - 1, Xo, Yo, Zo), dtype=torch.float32, device=mask.device)
-    check(lib().occ_classmix(_ptr(mask), _ptr(cls), _ptr(out), B, X, Y, Z, Xo, Yo, Zo, Q, NC, _stream()), "occ_classmix")
+    labels = torch.empty((B, Xo, Yo, Zo), dtype=torch.uint8, device=mask.device) if with_labels else None
+    check(lib().occ_classmix(_ptr(mask), _ptr(cls), _ptr(out), _ptr(labels), B, X, Y, Z, Xo, Yo, Zo, Q, NC, _stream()),
+          "occ_classmix")
     LAUNCH_COUNT[0] += 1
-    return out
+    return (out, labels) if with_labels else out
 
 
 def transpose_sq(mask, B, S, Q):

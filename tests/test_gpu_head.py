@@ -64,6 +64,9 @@ def test_head_vs_oracle_pr1_grid(cuda, B, layout):
     ref = port.head_simple_test(feats, sd, E // 32, L, [100, 100, 16], 3, points=pts, pc_range=PC)
     assert_close(res["output_voxels"][0], ref["output_voxels"][0], what="output_voxels (trilinear x2 upsample)")
     assert_close(res["output_points"], ref["output_points"], what="output_points")
+    # labels = argmax over the class axis of the kernel's own scores (first maximum), bit exact
+    assert res["output_labels"].dtype == torch.uint8
+    assert torch.equal(res["output_labels"].long(), res["output_voxels"][0].argmax(dim=1))
     # native-resolution output: the identity fast path of the class-mix kernel
     res2 = head.simple_test(dev_feats, [dict(occ_size=list(sizes[0]), pc_range=PC)] * B)
     ref2 = port.head_simple_test(feats, sd, E // 32, L, sizes[0], 3)
