@@ -33,12 +33,13 @@ int occ_version(void);
  * Output layout is channel-last (B, X, Y, Z, C); the Python wrapper returns permuted views carrying the
  * reference's shapes ((B,C,Z,X,Y) for bev_pool, (B,C,X,Y,Z) for voxel_pooling).
  * Bookkeeping left in the workspace after a call (byte offsets from occ_voxel_pool_workspace_layout):
- *   vox_id[n_points] int32 (linear voxel id ((b*X+x)*Y+y)*Z+z, -1 = dropped), starts[B*X*Y*Z+1] int32
- *   (exclusive prefix of per-voxel point counts; starts[V] = n_kept), order[n_kept] int32 (point ids by voxel).
+ *   vox_id[n_points] int32 (linear voxel id ((b*X+x)*Y+y)*Z+z, -1 = dropped), counts[B*X*Y*Z] int32 (points per
+ *   voxel = the reference's interval lengths), head[B*X*Y*Z] / next[n_points] int32 (per-voxel point lists, ids are
+ *   1-based, 0 terminates).
  */
 size_t occ_voxel_pool_workspace_bytes(int n_points, int B, int X, int Y, int Z);
 int occ_voxel_pool_workspace_layout(int n_points, int B, int X, int Y, int Z, size_t* off_counts,
-                                    size_t* off_starts, size_t* off_order, size_t* off_vox_id);
+                                    size_t* off_head, size_t* off_next, size_t* off_vox_id);
 /* get_geometry (ViewTransformerLSSBEVDepth.py:117-150): frustum (P = D*fH*fW, 3) + camera matrices -> geom
  * (B, N, P, 3) ego-frame points.  intrins (B,N,3,intrin_cols) with intrin_cols 3 or 4 (KITTI P2), bda (B,d,d), d 3|4. */
 int occ_lss_geometry(const float* frustum, int P, const float* rots, const float* trans, const float* intrins,

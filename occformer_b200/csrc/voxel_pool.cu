@@ -1,4 +1,4 @@
-// LSS lift-splat voxel pooling for sm_100a (HBM-bound; output-stationary, every grid row written once).
+// LSS lift-splat voxel pooling for sm_100a (HBM-bound; output-stationary, every grid row written once by its warp).
 //
 // Reference path replaced (files under /root/reference):
 //   projects/mmdet3d_plugin/occformer/image2bev/ViewTransformerLSSVoxel.py:77-100 (voxel_pooling: index,
@@ -7,14 +7,19 @@
 //   mmdetection3d/mmdet3d/ops/bev_pool/src/bev_pool_cuda.cu:20-42 (interval-sum kernel) + the
 //     (B,Z,X,Y,C)->(B,C,Z,X,Y) transpose copy (bev_pool.py:96).
 //
-// Pipeline (all on the caller's stream, no allocation, no sync):
+// Pipeline (all on the caller's stream, no allocation, no sync) -- one memset + two kernels:
+//   memset  : head[V] = 0 (empty), counts[V] = 0.
 //   index   : one thread per frustum point: exact fp32 voxel index ((g - (bx - dx/2)) / dx, trunc toward 0),
-//             kept test against float nx, linear voxel id, per-voxel count (integer atomics).
-//   scan    : exclusive prefix sum of the counts -> interval starts (3 small kernels).
-//   fill    : counting-sort placement of kept point ids into per-voxel segments.
-//   pool    : one warp per voxel: sums depth[p] * feat[pixel(p), :] (fused lift: the volume is never
-//             materialised) or rows of a materialised feats[n, C] (drop-in bev_pool), and writes the
-//             C-float row of out[b, x, y, z, :] exactly once -- empty voxels included, so no zero-fill pass.
+//             kept test against float nx, linear voxel id; the point is pushed onto its voxel's list
+//             (next[p] = atomicExch(&head[v], p + 1)) and counted (the reference's interval length).  No sort,
+//             no scan: the reference's argsort + interval bookkeeping (bev_pool.py:86-93) only groups points by voxel.
+//   pool    : a warp owns 32 consecutive voxels.  The rows of the empty ones (77 % of a nuScenes grid) are streamed
+//             out as zeros first.  Then, in rounds of four hops, every lane advances its own voxel's list
+//             (lane-parallel pointer chase) and the warp sums depth[p] * feat[pixel(p), :] (fused lift: the volume is
+//             never materialised) or rows of a materialised feats[n, C] (drop-in bev_pool), four voxels at a time so
+//             that 8-16 row loads are in flight; a voxel with more than four points accumulates into its own row in
+//             the following rounds.  (Near-camera voxels hold up to ~60 points and sit next to each other: walking
+//             those lists one hop at a time per warp was a 40-70 us tail.)
 // Output layout is channel-last (B, X, Y, Z, C); the Python boundary returns permuted views with the
 // reference's shapes.
 #include "occ_common.cuh"
@@ -27,7 +32,7 @@ namespace occ {
 __global__ void vp_index_geom_kernel(const float* __restrict__ geom, int P, int points_per_batch, float dx0,
                                      float dx1, float dx2, float bx0, float bx1, float bx2, float nx0, float nx1,
                                      float nx2, int X, int Y, int Z, int* __restrict__ vox_id,
-                                     int* __restrict__ counts) {
+                                     int* __restrict__ counts, int* __restrict__ head, int* __restrict__ next) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const float gx = geom[3 * (size_t)p + 0], gy = geom[3 * (size_t)p + 1], gz = geom[3 * (size_t)p + 2];
@@ -46,6 +51,7 @@ __global__ void vp_index_geom_kernel(const float* __restrict__ geom, int P, int 
     const int b = p / points_per_batch;
     v = ((b * X + (int)ix) * Y + (int)iy) * Z + (int)iz;
     atomicAdd(&counts[v], 1);
+    next[p] = atomicExch(&head[v], p + 1);  // 1-based ids: 0 = end of list / empty voxel
   }
   vox_id[p] = v;
 }
@@ -53,7 +59,8 @@ __global__ void vp_index_geom_kernel(const float* __restrict__ geom, int P, int 
 // coords: (n,4) int64 (x,y,z,b) as handed to mmdet3d.ops.bev_pool.bev_pool (already range-filtered by the
 // caller in the reference; we re-check and drop out-of-range rows instead of writing out of bounds).
 __global__ void vp_index_coords_kernel(const long long* __restrict__ coords, int n, int B, int X, int Y, int Z,
-                                       int* __restrict__ vox_id, int* __restrict__ counts) {
+                                       int* __restrict__ vox_id, int* __restrict__ counts, int* __restrict__ head,
+                                       int* __restrict__ next) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const long long x = coords[4 * (size_t)p + 0], y = coords[4 * (size_t)p + 1], z = coords[4 * (size_t)p + 2],
@@ -62,182 +69,174 @@ __global__ void vp_index_coords_kernel(const long long* __restrict__ coords, int
   if (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z && b >= 0 && b < B) {
     v = (((int)b * X + (int)x) * Y + (int)y) * Z + (int)z;
     atomicAdd(&counts[v], 1);
+    next[p] = atomicExch(&head[v], p + 1);
   }
   vox_id[p] = v;
 }
 
-// ------------------------------------------------------------------------------------------------ scan
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
-__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
-  __shared__ int warp_sums[SCAN_THREADS / 32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) warp_sums[w] = inc;
-  __syncthreads();
-  if (w == 0) {
-    int s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
-#pragma unroll
-    for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += t;
-    }
-    if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;
-  }
-  __syncthreads();
-  const int warp_off = w == 0 ? 0 : warp_sums[w - 1];
-  *total = warp_sums[SCAN_THREADS / 32 - 1];
-  __syncthreads();
-  return warp_off + inc - v;
-}
-
-__global__ void vp_scan_reduce_kernel(const int* __restrict__ counts, int V, int* __restrict__ block_sums) {
-  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  int s = 0;
-#pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) s += (base + i < V) ? counts[base + i] : 0;
-  int total;
-  block_exclusive_scan(s, &total);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-
-__global__ void vp_scan_blocksums_kernel(int* __restrict__ block_sums, int nb, int* __restrict__ grand_total) {
-  int carry = 0;
-  for (int base = 0; base < nb; base += SCAN_THREADS) {
-    const int i = base + threadIdx.x;
-    const int v = i < nb ? block_sums[i] : 0;
-    int total;
-    const int ex = block_exclusive_scan(v, &total);
-    if (i < nb) block_sums[i] = carry + ex;
-    carry += total;
-  }
-  if (threadIdx.x == 0) *grand_total = carry;
-}
-
-__global__ void vp_scan_apply_kernel(const int* __restrict__ counts, int V, const int* __restrict__ block_sums,
-                                     int* __restrict__ starts) {
-  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  int c[SCAN_ITEMS];
-  int s = 0;
-#pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) {
-    c[i] = (base + i < V) ? counts[base + i] : 0;
-    s += c[i];
-  }
-  int total;
-  int off = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
-#pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) {
-    if (base + i < V) starts[base + i] = off;
-    off += c[i];
-  }
-  // starts[V] (= n_kept) is written by vp_scan_blocksums_kernel through grand_total
-}
-
-// ------------------------------------------------------------------------------------------------ fill
-// Counting-sort placement; `counts` is consumed (decremented back to zero), so the workspace is clean
-// for the next call.  Order inside a voxel follows atomic arrival (the reference's argsort is unstable
-// too: bev_pool.py:92), the segment *sets* are deterministic.
-__global__ void vp_fill_kernel(const int* __restrict__ vox_id, int P, const int* __restrict__ starts,
-                               int* __restrict__ counts, int* __restrict__ order) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const int v = vox_id[p];
-  if (v < 0) return;
-  const int slot = starts[v] + atomicSub(&counts[v], 1) - 1;
-  order[slot] = p;
-}
-
 // ------------------------------------------------------------------------------------------------ pool
+// Exact unsigned division of n < 2^31 by a runtime constant: q = (n * mul) >> sh with mul = ceil(2^sh / d),
+// sh = 31 + ceil(log2 d) (error term n * (mul*d - 2^sh) < 2^31 * d <= 2^sh).
+struct FastDiv {
+  uint32_t mul, sh, d;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.sh = 31 + s;
+  f.mul = (uint32_t)(((1ull << f.sh) + d - 1) / d);
+  f.d = d;
+  return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
+  return (uint32_t)(((unsigned long long)n * f.mul) >> f.sh);
+}
+
 // MODE 0: fused lift  row(p) = depth_prob[p] * feat_cl[pixel(p), :]
 // MODE 1: materialised rows feats[p, :]
+// One warp owns 32 consecutive voxels (one z-column pair).  Empty voxels get their zero row streamed first; then
+// every lane walks the list of its own voxel (independent chains: the hop latencies overlap across lanes), and the
+// occupied voxels are reduced four at a time so that 8-16 row loads are in flight per warp.
 template <int MODE>
 __global__ void __launch_bounds__(256)
-vp_pool_kernel(const int* __restrict__ starts, const int* __restrict__ order, int V, int C,
-               const float* __restrict__ depth_prob, const float* __restrict__ feat, int D, int HW,
+vp_pool_kernel(const int* __restrict__ head, const int* __restrict__ next, int V, int C,
+               const float* __restrict__ depth_prob, const float* __restrict__ feat, FastDiv div_dhw, FastDiv div_hw,
                float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
   const int C4 = C >> 2;
-  const int nbatch = (V + 31) >> 5;
-  // a warp owns 32 consecutive voxels per iteration: their interval bounds arrive with two coalesced loads (instead of
-  // two dependent scalar loads per voxel) and the warp streams 32 x C floats of contiguous output
-  for (int batch = blockIdx.x * warps_per_block + (threadIdx.x >> 5); batch < nbatch; batch += gridDim.x * warps_per_block) {
-    const int vb = batch << 5;
-    const int my_s0 = starts[min(vb + lane, V)], my_s1 = starts[min(vb + lane + 1, V)];
-    const int nv = min(32, V - vb);
-    // empty voxels (77 % of a nuScenes grid) first, as a plain zero stream; then the occupied ones
-    uint32_t occupied = __ballot_sync(0xffffffffu, lane < nv && my_s1 > my_s0);
-    {
-      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int cbase = 0; cbase < C4; cbase += 32) {
-        if (cbase + lane < C4) {
-#pragma unroll 8
-          for (int vi = 0; vi < nv; ++vi)
-            if (!((occupied >> vi) & 1u)) __stcs(reinterpret_cast<float4*>(out + (size_t)(vb + vi) * C) + cbase + lane, z4);
+  const int batch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int vb = batch << 5;
+  if (vb >= V) return;
+  const int nv = min(32, V - vb);
+  const int h0 = lane < nv ? __ldg(head + vb + lane) : 0;
+  const uint32_t valid = nv == 32 ? 0xffffffffu : ((1u << nv) - 1u);
+  const uint32_t occupied = __ballot_sync(0xffffffffu, h0 != 0);
+  {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t e = valid & ~occupied; e != 0u; e &= e - 1u) {
+      float4* orow = reinterpret_cast<float4*>(out + (size_t)(vb + __ffs(e) - 1) * C);
+      for (int c4 = lane; c4 < C4; c4 += 32) __stcs(orow + c4, z4);
+    }
+  }
+  if (occupied == 0u) return;
+  // Rounds of four hops: every lane advances the list of its own voxel (independent chains, the hop latencies
+  // overlap across lanes), then the warp reduces the voxels that gained points this round, four voxels at a time
+  // (8-16 row loads in flight).  Voxels with more than four points continue in the next round and accumulate
+  // into their own output row (same lane wrote it: program order makes the partial sum visible).
+  int cur = h0;
+  bool first = true;
+  while (true) {
+    int frow[4];
+    float wgt[4];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      frow[j] = 0;
+      wgt[j] = 0.f;
+      if (cur != 0) {
+        const uint32_t p = (uint32_t)cur - 1u;
+        // MODE 0: p = ((bn*D + d)*HW + pix) -> feature row bn*HW + pix;  MODE 1: row p
+        if (MODE == 0) {
+          const uint32_t bn = fast_div(p, div_dhw);
+          const uint32_t pix = p - fast_div(p, div_hw) * div_hw.d;
+          frow[j] = (int)(bn * div_hw.d + pix);
+          wgt[j] = __ldg(depth_prob + p);
+        } else {
+          frow[j] = (int)p;
+          wgt[j] = 1.f;
         }
+        cur = __ldg(next + p);
+        ++cnt;
       }
     }
-    while (occupied) {
-    const int vi = __ffs(occupied) - 1;
-    occupied &= occupied - 1;
-    const int v = vb + vi;
-    const int s0 = __shfl_sync(0xffffffffu, my_s0, vi), s1 = __shfl_sync(0xffffffffu, my_s1, vi);
-    float4* orow = reinterpret_cast<float4*>(out + (size_t)v * C);
+    const uint32_t occ_round = __ballot_sync(0xffffffffu, cnt > 0);
+    const bool any_gt2 = __any_sync(0xffffffffu, cnt > 2);
     for (int cbase = 0; cbase < C4; cbase += 32) {
       const int c4 = cbase + lane;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = s0; s < s1; s += 32) {
-        const int cnt = min(32, s1 - s);
-        int pid = 0;
-        float w = 0.f;
-        size_t rowoff = 0;
-        if (lane < cnt) {
-          pid = order[s + lane];
-          if (MODE == 0) {
-            w = __ldg(depth_prob + pid);
-            // p = ((bn*D + d)*HW + pix)  ->  feature row = bn*HW + pix
-            const int bn = pid / (D * HW);
-            const int pix = pid % HW;
-            rowoff = ((size_t)bn * HW + pix) * C;
-          } else {
-            w = 1.f;
-            rowoff = (size_t)pid * C;
-          }
+      const bool active = c4 < C4;
+      const float4* fbase = reinterpret_cast<const float4*>(feat) + c4;
+      uint32_t occ = occ_round;
+      while (occ) {
+        int vi[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ok[u] = occ != 0u;
+          vi[u] = ok[u] ? __ffs(occ) - 1 : 0;
+          occ &= occ - 1u;  // 0 stays 0
         }
-        const bool active = c4 < C4;
-        int j = 0;
-        for (; j + 4 <= cnt; j += 4) {
-          float4 f[4];
-          float ww[4];
+        float4 acc[4];
+        int n[4];
+        {
+          int r0[4], r1[4];
+          float w0[4], w1[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const size_t ro = __shfl_sync(0xffffffffu, rowoff, j + u);
-            ww[u] = __shfl_sync(0xffffffffu, w, j + u);
-            f[u] = active ? __ldg(reinterpret_cast<const float4*>(feat + ro) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            n[u] = __shfl_sync(0xffffffffu, cnt, vi[u]);
+            r0[u] = __shfl_sync(0xffffffffu, frow[0], vi[u]);
+            w0[u] = __shfl_sync(0xffffffffu, wgt[0], vi[u]);
+            r1[u] = __shfl_sync(0xffffffffu, frow[1], vi[u]);
+            w1[u] = __shfl_sync(0xffffffffu, wgt[1], vi[u]);
+            if (!ok[u]) n[u] = 0;
+          }
+          float4 f0[4], f1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            f0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n[u] > 0 && active) f0[u] = __ldg(fbase + (size_t)r0[u] * C4);
+            if (n[u] > 1 && active) f1[u] = __ldg(fbase + (size_t)r1[u] * C4);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            acc.x += ww[u] * f[u].x; acc.y += ww[u] * f[u].y; acc.z += ww[u] * f[u].z; acc.w += ww[u] * f[u].w;
+            acc[u].x = w0[u] * f0[u].x + w1[u] * f1[u].x;
+            acc[u].y = w0[u] * f0[u].y + w1[u] * f1[u].y;
+            acc[u].z = w0[u] * f0[u].z + w1[u] * f1[u].z;
+            acc[u].w = w0[u] * f0[u].w + w1[u] * f1[u].w;
           }
         }
-        for (; j < cnt; ++j) {
-          const size_t ro = __shfl_sync(0xffffffffu, rowoff, j);
-          const float wj = __shfl_sync(0xffffffffu, w, j);
-          const float4 f = active ? __ldg(reinterpret_cast<const float4*>(feat + ro) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          acc.x += wj * f.x; acc.y += wj * f.y; acc.z += wj * f.z; acc.w += wj * f.w;
+        if (any_gt2) {
+          int r2[4], r3[4];
+          float w2[4], w3[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            r2[u] = __shfl_sync(0xffffffffu, frow[2], vi[u]);
+            w2[u] = __shfl_sync(0xffffffffu, wgt[2], vi[u]);
+            r3[u] = __shfl_sync(0xffffffffu, frow[3], vi[u]);
+            w3[u] = __shfl_sync(0xffffffffu, wgt[3], vi[u]);
+          }
+          float4 f2[4], f3[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            f2[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            f3[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n[u] > 2 && active) f2[u] = __ldg(fbase + (size_t)r2[u] * C4);
+            if (n[u] > 3 && active) f3[u] = __ldg(fbase + (size_t)r3[u] * C4);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[u].x += w2[u] * f2[u].x + w3[u] * f3[u].x;
+            acc[u].y += w2[u] * f2[u].y + w3[u] * f3[u].y;
+            acc[u].z += w2[u] * f2[u].z + w3[u] * f3[u].z;
+            acc[u].w += w2[u] * f2[u].w + w3[u] * f3[u].w;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (ok[u] && active) {
+            float4* dst = reinterpret_cast<float4*>(out + (size_t)(vb + vi[u]) * C) + c4;
+            if (!first) {
+              const float4 o = *dst;
+              acc[u].x += o.x; acc[u].y += o.y; acc[u].z += o.z; acc[u].w += o.w;
+            }
+            *dst = acc[u];
+          }
         }
       }
-      if (c4 < C4) __stcs(orow + c4, acc);  // streaming store: the grid is consumed by the next kernel from HBM/L2
     }
-    }
+    first = false;
+    if (!__any_sync(0xffffffffu, cur != 0)) break;
   }
 }
 
@@ -273,26 +272,10 @@ __global__ void vp_nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int 
   }
 }
 
-static int scan_and_fill(int* counts, int* starts, int* block_sums, int* order, const int* vox_id, int P, int V,
-                         cudaStream_t stream) {
-  const int nb = (V + SCAN_TILE - 1) / SCAN_TILE;
-  vp_scan_reduce_kernel<<<nb, SCAN_THREADS, 0, stream>>>(counts, V, block_sums);
-  OCC_LAUNCH_CHECK();
-  vp_scan_blocksums_kernel<<<1, SCAN_THREADS, 0, stream>>>(block_sums, nb, starts + V);
-  OCC_LAUNCH_CHECK();
-  vp_scan_apply_kernel<<<nb, SCAN_THREADS, 0, stream>>>(counts, V, block_sums, starts);
-  OCC_LAUNCH_CHECK();
-  if (P > 0) {
-    vp_fill_kernel<<<(P + 255) / 256, 256, 0, stream>>>(vox_id, P, starts, counts, order);
-    OCC_LAUNCH_CHECK();
-  }
-  return OCC_OK;
-}
-
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct VpWorkspace {
-  int *counts, *starts, *block_sums, *order, *vox_id;
+  int *head, *counts, *next, *vox_id;  // head and counts are adjacent: one memset clears both
 };
 
 static size_t vp_layout(void* base, int P, int V, VpWorkspace* ws) {
@@ -302,11 +285,9 @@ static size_t vp_layout(void* base, int P, int V, VpWorkspace* ws) {
     off += align_up(bytes, 256);
     return static_cast<int*>(p);
   };
-  const int nb = (V + SCAN_TILE - 1) / SCAN_TILE;
+  ws->head = take((size_t)V * 4);
   ws->counts = take((size_t)V * 4);
-  ws->starts = take((size_t)(V + 1) * 4);
-  ws->block_sums = take((size_t)nb * 4);
-  ws->order = take((size_t)P * 4);
+  ws->next = take((size_t)P * 4);
   ws->vox_id = take((size_t)P * 4);
   return off;
 }
@@ -321,7 +302,7 @@ extern "C" size_t occ_voxel_pool_workspace_bytes(int n_points, int B, int X, int
 }
 
 // Fused lift-splat.  depth_prob (B*N, D, fH*fW) fp32 (already softmaxed), feat_cl (B*N, fH*fW, C) channel-last,
-// geom (B*N*D*fH*fW, 3).  out (B, X, Y, Z, C).  Bookkeeping left in the workspace: vox_id[P], starts[V+1].
+// geom (B*N*D*fH*fW, 3).  out (B, X, Y, Z, C).  Bookkeeping left in the workspace: vox_id[P], counts[V], head[V], next[P].
 extern "C" int occ_lift_splat(const float* depth_prob, const float* feat_cl, const float* geom, float* out, int B,
                               int N, int D, int HW, int C, float dx0, float dx1, float dx2, float bx0, float bx1,
                               float bx2, float nx0, float nx1, float nx2, int X, int Y, int Z, void* workspace, size_t workspace_bytes, int counts_are_zero,
@@ -333,14 +314,14 @@ extern "C" int occ_lift_splat(const float* depth_prob, const float* feat_cl, con
   const int P = (int)Pll, V = (int)Vll;
   VpWorkspace ws;
   OCC_REQUIRE(vp_layout(workspace, P, V, &ws) <= workspace_bytes);
-  if (!counts_are_zero) OCC_CUDA(cudaMemsetAsync(ws.counts, 0, (size_t)V * 4, stream));
+  (void)counts_are_zero;
+  // head[V] and counts[V] are adjacent in the workspace: one memset
+  OCC_CUDA(cudaMemsetAsync(ws.head, 0, reinterpret_cast<char*>(ws.counts + V) - reinterpret_cast<char*>(ws.head), stream));
   vp_index_geom_kernel<<<(P + 255) / 256, 256, 0, stream>>>(geom, P, N * D * HW, dx0, dx1, dx2, bx0, bx1, bx2, nx0,
-                                                             nx1, nx2, X, Y, Z, ws.vox_id, ws.counts);
+                                                             nx1, nx2, X, Y, Z, ws.vox_id, ws.counts, ws.head, ws.next);
   OCC_LAUNCH_CHECK();
-  int rc = scan_and_fill(ws.counts, ws.starts, ws.block_sums, ws.order, ws.vox_id, P, V, stream);
-  if (rc) return rc;
-  const int blocks = sm_count() * 8;
-  vp_pool_kernel<0><<<blocks, 256, 0, stream>>>(ws.starts, ws.order, V, C, depth_prob, feat_cl, D, HW, out);
+  vp_pool_kernel<0><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, depth_prob, feat_cl,
+                                                                 make_fastdiv((uint32_t)D * HW), make_fastdiv(HW), out);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -357,14 +338,14 @@ extern "C" int occ_bev_pool(const float* feats, const long long* coords, float* 
   const int V = (int)Vll;
   VpWorkspace ws;
   OCC_REQUIRE(vp_layout(workspace, n, V, &ws) <= workspace_bytes);
-  OCC_CUDA(cudaMemsetAsync(ws.counts, 0, (size_t)V * 4, stream));
+  OCC_CUDA(cudaMemsetAsync(ws.head, 0, reinterpret_cast<char*>(ws.counts + V) - reinterpret_cast<char*>(ws.head), stream));
   if (n > 0) {
-    vp_index_coords_kernel<<<(n + 255) / 256, 256, 0, stream>>>(coords, n, B, X, Y, Z, ws.vox_id, ws.counts);
+    vp_index_coords_kernel<<<(n + 255) / 256, 256, 0, stream>>>(coords, n, B, X, Y, Z, ws.vox_id, ws.counts, ws.head,
+                                                                ws.next);
     OCC_LAUNCH_CHECK();
   }
-  int rc = scan_and_fill(ws.counts, ws.starts, ws.block_sums, ws.order, ws.vox_id, n, V, stream);
-  if (rc) return rc;
-  vp_pool_kernel<1><<<sm_count() * 8, 256, 0, stream>>>(ws.starts, ws.order, V, C, nullptr, feats, 1, 1, out);
+  vp_pool_kernel<1><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, nullptr, feats, make_fastdiv(1),
+                                                                 make_fastdiv(1), out);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -383,13 +364,13 @@ extern "C" int occ_lift_prologue(const float* depth_logits, const float* img_fea
 
 // Byte offsets of the bookkeeping arrays inside the workspace (for tests / callers that want them).
 extern "C" int occ_voxel_pool_workspace_layout(int n_points, int B, int X, int Y, int Z, size_t* off_counts,
-                                               size_t* off_starts, size_t* off_order, size_t* off_vox_id) {
+                                               size_t* off_head, size_t* off_next, size_t* off_vox_id) {
   VpWorkspace ws;
   char* base = reinterpret_cast<char*>(0x1000);
   vp_layout(base, n_points, B * X * Y * Z, &ws);
   *off_counts = reinterpret_cast<char*>(ws.counts) - base;
-  *off_starts = reinterpret_cast<char*>(ws.starts) - base;
-  *off_order = reinterpret_cast<char*>(ws.order) - base;
+  *off_head = reinterpret_cast<char*>(ws.head) - base;
+  *off_next = reinterpret_cast<char*>(ws.next) - base;
   *off_vox_id = reinterpret_cast<char*>(ws.vox_id) - base;
   return OCC_OK;
 }
@@ -407,13 +388,12 @@ extern "C" int occ_voxel_pool_geom(const float* feats, const float* geom, float*
   const int P = (int)Pll, V = (int)Vll;
   VpWorkspace ws;
   OCC_REQUIRE(vp_layout(workspace, P, V, &ws) <= workspace_bytes);
-  OCC_CUDA(cudaMemsetAsync(ws.counts, 0, (size_t)V * 4, stream));
+  OCC_CUDA(cudaMemsetAsync(ws.head, 0, reinterpret_cast<char*>(ws.counts + V) - reinterpret_cast<char*>(ws.head), stream));
   vp_index_geom_kernel<<<(P + 255) / 256, 256, 0, stream>>>(geom, P, points_per_batch, dx0, dx1, dx2, bx0, bx1, bx2,
-                                                             nx0, nx1, nx2, X, Y, Z, ws.vox_id, ws.counts);
+                                                             nx0, nx1, nx2, X, Y, Z, ws.vox_id, ws.counts, ws.head, ws.next);
   OCC_LAUNCH_CHECK();
-  int rc = scan_and_fill(ws.counts, ws.starts, ws.block_sums, ws.order, ws.vox_id, P, V, stream);
-  if (rc) return rc;
-  vp_pool_kernel<1><<<sm_count() * 8, 256, 0, stream>>>(ws.starts, ws.order, V, C, nullptr, feats, 1, 1, out);
+  vp_pool_kernel<1><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, nullptr, feats, make_fastdiv(1),
+                                                                 make_fastdiv(1), out);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

@@ -47,7 +47,7 @@ class VoxelPoolWorkspace:
         self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
         offs = [ctypes.c_size_t() for _ in range(4)]
         l.occ_voxel_pool_workspace_layout(n_points, B, X, Y, Z, *[ctypes.byref(o) for o in offs])
-        self.off_counts, self.off_starts, self.off_order, self.off_vox_id = (o.value for o in offs)
+        self.off_counts, self.off_head, self.off_next, self.off_vox_id = (o.value for o in offs)
         self.V = B * X * Y * Z
         self.P = n_points
 
@@ -55,16 +55,23 @@ class VoxelPoolWorkspace:
         return self.buf[off:off + 4 * n].view(torch.int32)
 
     @property
-    def starts(self):
-        return self._ints(self.off_starts, self.V + 1)
+    def counts(self):
+        """points per voxel (= the reference's interval lengths)"""
+        return self._ints(self.off_counts, self.V)
+
+    @property
+    def head(self):
+        """first point (1-based id, 0 = empty) of every voxel's list"""
+        return self._ints(self.off_head, self.V)
+
+    @property
+    def next(self):
+        """next point (1-based id, 0 = end) of every kept point"""
+        return self._ints(self.off_next, self.P)
 
     @property
     def vox_id(self):
         return self._ints(self.off_vox_id, self.P)
-
-    @property
-    def order(self):
-        return self._ints(self.off_order, self.P)
 
 
 _ws_cache = {}
@@ -118,7 +125,7 @@ def lift_splat(depth_prob, feat_cl, geom, B, N, dx, bx, nx, grid, return_workspa
     f = [float(v) for v in (*dx, *bx, *nx)]
     check(lib().occ_lift_splat(_ptr(depth_prob), _ptr(feat_cl), _ptr(geom), _ptr(out), B, N, D, fH * fW, C, *f, X, Y,
                                Z, _ptr(ws.buf), ws.nbytes, 0, _stream()), "occ_lift_splat")
-    LAUNCH_COUNT[0] += 6
+    LAUNCH_COUNT[0] += 3
     return (out, ws) if return_workspace else out
 
 
@@ -132,7 +139,7 @@ def voxel_pool_geom(feats, geom, B, dx, bx, nx, grid, return_workspace=False):
     f = [float(v) for v in (*dx, *bx, *nx)]
     check(lib().occ_voxel_pool_geom(_ptr(feats), _ptr(geom), _ptr(out), B, P_ // B, C, *f, X, Y, Z, _ptr(ws.buf),
                                     ws.nbytes, _stream()), "occ_voxel_pool_geom")
-    LAUNCH_COUNT[0] += 6
+    LAUNCH_COUNT[0] += 3
     return (out, ws) if return_workspace else out
 
 
@@ -143,7 +150,7 @@ def bev_pool_channel_last(feats, coords, B, X, Y, Z, return_workspace=False):
     out = torch.empty((B, X, Y, Z, C), dtype=torch.float32, device=feats.device)
     check(lib().occ_bev_pool(_ptr(feats), _ptr(coords), _ptr(out), n, C, B, X, Y, Z, _ptr(ws.buf), ws.nbytes,
                              _stream()), "occ_bev_pool")
-    LAUNCH_COUNT[0] += 6
+    LAUNCH_COUNT[0] += 3
     return (out, ws) if return_workspace else out
 
 

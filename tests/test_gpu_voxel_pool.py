@@ -28,11 +28,10 @@ def _check_bookkeeping(ws, gf, kept, B, X, Y, Z):
     ref_lin = ((gf[:, 3] * X + gf[:, 0]) * Y + gf[:, 1]) * Z + gf[:, 2]
     ref_vox = torch.where(kept, ref_lin, torch.full_like(ref_lin, -1))
     assert torch.equal(vox, ref_vox), f"voxel ids differ at {(vox != ref_vox).sum()} points"
-    starts = ws.starts.cpu().long()
-    counts = starts[1:] - starts[:-1]
+    counts = ws.counts.cpu().long()
     ref_counts = torch.bincount(ref_lin[kept], minlength=B * X * Y * Z)
     assert torch.equal(counts, ref_counts)
-    assert int(starts[-1]) == int(kept.sum())
+    assert int(counts.sum()) == int(kept.sum())
     # interval bookkeeping in the reference's own rank order (bev_pool.py:86-93 / QuickCumsumCuda :40-45)
     uniq, lens = port.bev_pool_bookkeeping(gf[kept], B, Z, X, Y)
     nzv = torch.nonzero(counts).flatten()
@@ -40,9 +39,22 @@ def _check_bookkeeping(ws, gf, kept, B, X, Y, Z):
     my_ranks = x * (Y * Z * B) + y * (Z * B) + z * B + b
     order = my_ranks.argsort()
     assert torch.equal(my_ranks[order], uniq) and torch.equal(counts[nzv][order], lens)
-    # every kept point appears exactly once in the sorted order array
-    order_ids = ws.order.cpu().long()[: int(starts[-1])]
-    assert torch.equal(order_ids.sort().values, torch.nonzero(kept).flatten())
+    # per-voxel point lists: walking head/next visits every kept point exactly once, inside its own voxel
+    head, nxt = ws.head.cpu().long(), ws.next.cpu().long()
+    assert torch.equal(head != 0, counts != 0)
+    visited = torch.zeros(vox.numel(), dtype=torch.long)
+    cur = head.clone()
+    vidx = torch.arange(head.numel())
+    for _ in range(int(counts.max()) + 1):
+        live = cur != 0
+        if not bool(live.any()):
+            break
+        p = cur[live] - 1
+        assert torch.equal(vox[p], vidx[live]), "a list contains a point of another voxel"
+        visited[p] += 1
+        cur = torch.where(live, torch.cat([nxt, torch.zeros(1, dtype=torch.long)])[(cur - 1).clamp(min=-1)], cur)
+    assert not bool((cur != 0).any()), "a list is longer than its voxel's count"
+    assert torch.equal(visited, kept.long()), "kept points and list membership differ"
 
 
 @pytest.mark.parametrize("B", [1, 2])
@@ -121,7 +133,7 @@ def test_lift_splat_nusc_properties(cuda):
     expect = torch.einsum("np,ncp->c", w.double(), feat.reshape(N, C, HW).double())
     got = grid.double().sum(dim=(0, 1, 2, 3)).cpu()
     assert_close(got, expect, 1e-5, "mass conservation")
-    print(f"nusc_200: n_pts={idx.shape[0]} n_kept={int(kept.sum())} nonempty={int((ws.starts[1:] - ws.starts[:-1]).ne(0).sum())}")
+    print(f"nusc_200: n_pts={idx.shape[0]} n_kept={int(kept.sum())} nonempty={int(ws.counts.ne(0).sum())}")
 
 
 @pytest.mark.parametrize("kind", ["nusc", "kitti"])
