@@ -646,6 +646,11 @@ extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B,
 //   pooled[b, cell, q] = max over the (X/Xo, Y/Yo, Z/Zo) voxels of the cell  (adaptive_max_pool3d with divisible,
 //   power-of-two windows), written as order-preserving ints (sign == sign of the logit: blocked <=> value < 0);
 //   flag[b, q] = 1 iff some pooled value of the row is >= 0.   mask_out may be NULL (intermediate decoder layers).
+namespace occ {
+int mask_pool_query_stationary(const float* mf, const float* membed, int* pooled, int* flag, int B, int X, int Y, int Z,
+                               int E, int Q, int Xo, int Yo, int Zo, cudaStream_t stream);
+}
+
 extern "C" int occ_mask_gemm_pool(const float* mf, const float* membed, float* mask_out, int* pooled, int* flag, int B,
                                   int X, int Y, int Z, int E, int Q, int Xo, int Yo, int Zo, cudaStream_t stream) {
   OCC_REQUIRE(mf && membed && pooled && flag);
@@ -655,6 +660,10 @@ extern "C" int occ_mask_gemm_pool(const float* mf, const float* membed, float* m
   auto pow2 = [](int v) { return v >= 2 && (v & (v - 1)) == 0; };
   OCC_REQUIRE(pow2(wx) && pow2(wy) && pow2(wz));
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(mf) & 15) == 0 && (reinterpret_cast<uintptr_t>(membed) & 15) == 0);
+  if (!mask_out) {  // only the pooled logits are wanted: query-stationary kernel (mask_pool_tc.cu), register pooling
+    const int rc = mask_pool_query_stationary(mf, membed, pooled, flag, B, X, Y, Z, E, Q, Xo, Yo, Zo, stream);
+    if (rc != 1) return rc;
+  }
   OCC_CUDA(cudaMemsetAsync(pooled, 0x80, (size_t)B * Xo * Yo * Zo * Q * sizeof(int), stream));
   OCC_CUDA(cudaMemsetAsync(flag, 0, (size_t)B * Q * sizeof(int), stream));
   for (int b = 0; b < B; ++b) {
