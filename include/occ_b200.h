@@ -105,6 +105,13 @@ int occ_aspp_gap_branch(const float* in, double* sums_ws, const float* wconv, co
 int occ_dualpath_fuse(const float* x, const float* bev, const float* cw, float cbias, const float* identity,
                       const double* id_stats, const float* id_w, const float* id_b, int groups, float* out, int B,
                       int XY, int Z, int C, occ_stream_t stream);
+/* Swin block tail for C == 128 in one tensor-core kernel (csrc/swin_mlp_fused.cu): y1 = tok + att Wp^T + bp (WindowMSA.proj
+ * + the ShiftWindowMSA residual, window_attention.py:105-107 / swin.py SwinBlock.forward), out = y1 + W2 GELU(W1 LN2(y1)
+ * + b1) + b2 (norm2 + FFN + residual).  Weights (out, in) row-major, tf32-rounded.  Returns -2 for C != 128 (the caller
+ * then uses occ_gemm_tf32 / occ_layernorm). */
+int occ_swin_proj_ffn(const float* att, const float* tok, const float* wp, const float* bp, const float* ln_w,
+                      const float* ln_b, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
+                      long long M, int C, occ_stream_t stream);
 /* (shifted) 7x7 window attention core over B*(Z+1) images: ShiftWindowMSA.forward + WindowMSA.forward
  * (window_attention.py:168-242, 69-107) minus the qkv / proj linears, on tcgen05 tensor cores.
  * bias_pad = relative_position_bias_table[relative_position_index] as (heads, 49*49 padded to 2404 floats). */

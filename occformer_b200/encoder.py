@@ -183,11 +183,16 @@ class DualpathTransformerBlock(nn.Module):
         # (A7/A8) shifted-window attention core, gathers/scatters windows in place
         att = ops.window_attention(qkv, msa.qkv.bias, P["bias_pad"], B, X, Y, Z, C, self.num_heads, self.shift)
         # proj + residual, LayerNorm2, FFN (GELU) + residual  (A6)
-        y1 = ops.gemm(att, P["w_proj"], bias=msa.proj.bias, residual=tok)
-        y1n = ops.layernorm(y1, sw.norm2.weight, sw.norm2.bias, round_out=True)
         ffn = sw.ffn.layers
-        h = ops.gemm(y1n, P["w_f1"], bias=ffn[0][0].bias, act=2, round_out=True)
-        y2 = ops.gemm(h, P["w_f2"], bias=ffn[1].bias, residual=y1)
+        if C == 128 and P["w_f1"].shape == (C, C):
+            # one kernel: the three 128x128 GEMMs are chained through TMEM, y1 / LN2(y1) / h never reach HBM
+            y2 = ops.swin_proj_ffn(att, tok, P["w_proj"], msa.proj.bias, sw.norm2.weight, sw.norm2.bias, P["w_f1"],
+                                   ffn[0][0].bias, P["w_f2"], ffn[1].bias)
+        else:
+            y1 = ops.gemm(att, P["w_proj"], bias=msa.proj.bias, residual=tok)
+            y1n = ops.layernorm(y1, sw.norm2.weight, sw.norm2.bias, round_out=True)
+            h = ops.gemm(y1n, P["w_f1"], bias=ffn[0][0].bias, act=2, round_out=True)
+            y2 = ops.gemm(h, P["w_f2"], bias=ffn[1].bias, residual=y1)
         x_vox, x_bev = y2[:nvox], y2[nvox:]
         # (A9) BottleNeckASPP on the BEV tokens (B, X, Y, 1, C)
         bev_out = self._aspp(x_bev, B, X, Y, C, stats, P)

@@ -229,6 +229,18 @@ def layernorm(x, w, b, round_out=False):
     return out
 
 
+def swin_proj_ffn(att, tok, wp, bp, ln_w, ln_b, w1, b1, w2, b2):
+    """Fused Swin block tail (C == 128): tok + proj(att) -> LN2 -> FFN(GELU) + residual, one kernel."""
+    _chk(att, "att"), _chk(tok, "tok")
+    M, C = att.shape
+    assert tok.shape == (M, C) and wp.shape == (C, C) and w1.shape == (C, C) and w2.shape == (C, C)
+    out = torch.empty_like(att)
+    check(lib().occ_swin_proj_ffn(_ptr(att), _ptr(tok), _ptr(wp), _ptr(bp), _ptr(ln_w), _ptr(ln_b), _ptr(w1), _ptr(b1),
+                                  _ptr(w2), _ptr(b2), _ptr(out), M, C, _stream()), "occ_swin_proj_ffn")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
 def gn_apply(x, stats, w, b, rows_per_batch, groups, residual=None, out=None, out_off=0, relu=True, round_out=False):
     _chk(x, "x")
     rows, C = x.shape

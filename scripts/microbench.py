@@ -90,6 +90,16 @@ def main():
         t = timeit(lambda: ops.window_attention(qkv, qb, bd, 1, X, Y, Z, C, 4, True))
         res["window_attn_tc_ms"] = t
         res["window_attn_GBps"] = (M * 3 * C * 4 + M * C * 4) / t / 1e6
+    if "swin" in which:
+        M = X * Y * (Z + 1)
+        att = ops.round_tf32_(torch.randn(M, C, device=dev))
+        tok = torch.randn(M, C, device=dev)
+        ws = [ops.round_tf32_(torch.randn(C, C, device=dev) * C ** -0.5) for _ in range(3)]
+        bs = [0.1 * torch.randn(C, device=dev) for _ in range(3)]
+        lw, lb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        t = timeit(lambda: ops.swin_proj_ffn(att, tok, ws[0], bs[0], lw, lb, ws[1], bs[1], ws[2], bs[2]))
+        res["swin_proj_ffn_fused_ms"] = t
+        res["swin_proj_ffn_GBps"] = 3 * M * C * 4 / t / 1e6
     if "block" in which:
         from occformer_b200.encoder import OccupancyEncoder
         enc = OccupancyEncoder(in_channels=128, num_stage=4, block_numbers=[2, 2, 2, 2], block_inplanes=[128, 256, 512, 1024],
