@@ -114,9 +114,11 @@ int occ_swin_proj_ffn(const float* att, const float* tok, const float* wp, const
                       long long M, int C, occ_stream_t stream);
 /* (shifted) 7x7 window attention core over B*(Z+1) images: ShiftWindowMSA.forward + WindowMSA.forward
  * (window_attention.py:168-242, 69-107) minus the qkv / proj linears, on tcgen05 tensor cores.
- * bias_pad = relative_position_bias_table[relative_position_index] as (heads, 49*49 padded to 2404 floats). */
+ * bias_pad = relative_position_bias_table[relative_position_index] as (heads, 49*49 padded to 2404 floats).
+ * qkv_head_major = 0: qkv / qkv_bias columns in the reference order [q|k|v][head][32] (WindowMSA.qkv);  1: [head][q|k|v][32]
+ * (the caller permuted the rows of the qkv weight: one contiguous 384-byte run per (token, head)). */
 int occ_window_attention(const float* qkv, const float* qkv_bias, const float* bias_pad, float* out, int B, int X,
-                         int Y, int Z, int C, int heads, int shift, occ_stream_t stream);
+                         int Y, int Z, int C, int heads, int shift, int qkv_head_major, occ_stream_t stream);
 /* development aid: unit 0 of CTA 0 dumps raw scores / probabilities / output rows into dbg (128,192); NULL = off */
 int occ_window_attention_set_debug(float* dbg);
 /* development probe of tcgen05 operand conventions: D[128x32] = A[128x64] V[64x32], mode 0..3 (csrc/umma_probe.cu) */

@@ -31,7 +31,7 @@ SIGNATURES = {
     "occ_aspp_gap_branch": (c_int, [P] * 6 + [c_int] * 6 + [STREAM]),
     "occ_dualpath_fuse": (c_int, [P, P, P, c_float, P, P, P, P, c_int, P, c_int, c_int, c_int, c_int, STREAM]),
     "occ_swin_proj_ffn": (c_int, [P] * 11 + [c_longlong, c_int, STREAM]),
-    "occ_window_attention": (c_int, [P, P, P, P] + [c_int] * 7 + [STREAM]),
+    "occ_window_attention": (c_int, [P, P, P, P] + [c_int] * 8 + [STREAM]),
     "occ_window_attention_set_debug": (c_int, [P]),
     "occ_debug_umma_probe": (c_int, [P, P, P, c_int, STREAM]),
     "occ_sine_pos3d": (c_int, [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, STREAM]),

@@ -34,6 +34,8 @@ struct GemmParams {
   const float* bias;
   const float* residual;
   int ldr;
+  int splits;     // split-K: > 1 => every tile's k-blocks are divided among `splits` CTAs, partial sums meet in `out`
+                  // (zero-initialised by the host) through TMA reduce-add; no bias / act / stats in the kernel
   int act;        // 0 none, 1 relu, 2 gelu(erf)
   int round_out;  // round result to tf32 (consumer is another tf32 MMA)
   // conv mode
@@ -117,7 +119,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int num_n_tiles = (p.N + BN - 1) / BN;
   const int num_m_tiles = p.conv ? p.B * p.tiles_x * p.tiles_y * p.tiles_z : (p.M + BM - 1) / BM;
-  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_tiles = num_m_tiles * num_n_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -151,8 +153,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       const int cblocks = p.conv ? (p.Cin / BK) : 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % num_n_tiles;
-        const int m_tile = tile / num_n_tiles;
+        const int split = tile % p.splits;
+        const int n_tile = (tile / p.splits) % num_n_tiles;
+        const int m_tile = tile / (p.splits * num_n_tiles);
+        const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
+        const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
         int cb = 0, cx0 = 0, cy0 = 0, cz0 = 0;
         if (p.conv) {
           int t = m_tile;
@@ -165,7 +170,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           cz0 = tz * p.bz * p.stride - p.padz;
         }
         int tap = 0, kc = 0, tx_ = 0, ty_ = 0, tz_ = 0;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        if (p.conv && kb0 > 0) {  // split-K: start in the middle of the tap sequence
+          tap = kb0 / cblocks;
+          kc = kb0 % cblocks;
+          tz_ = tap % p.KZ;
+          ty_ = (tap / p.KZ) % p.KY;
+          tx_ = tap / (p.KZ * p.KY);
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
@@ -201,7 +213,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tmem_empty[buf], (((it >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int split = tile % p.splits;
+        const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
+        const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -211,7 +226,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             // advance 8 tf32 = 32 bytes = 2 (16-byte units) inside the 128-byte swizzle row
-            mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, ((kb - kb0) | k) != 0);
           }
           mma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -238,8 +253,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int cur_b = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      const int n_tile = tile % num_n_tiles;
-      const int m_tile = tile / num_n_tiles;
+      const int n_tile = (tile / p.splits) % num_n_tiles;
+      const int m_tile = tile / (p.splits * num_n_tiles);
       const int n0 = n_tile * BN;
       // ---- output row of this thread
       long long m = -1;
@@ -456,8 +471,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.conv) {
               // rows ew*32 .. ew*32+31 of the tile form a sub-box (ex, ey, ez) of the (bx, by, bz) voxel box
               const int r0 = ew * 32;
-              tma_store_5d(&tmC, sb, nc, tile_z0 + r0 % p.bz, tile_y0 + (r0 / p.bz) % p.by, tile_x0 + r0 / (p.bz * p.by),
-                           tile_b);
+              if (p.splits > 1)
+                tma_reduce_add_5d(&tmC, sb, nc, tile_z0 + r0 % p.bz, tile_y0 + (r0 / p.bz) % p.by,
+                                  tile_x0 + r0 / (p.bz * p.by), tile_b);
+              else
+                tma_store_5d(&tmC, sb, nc, tile_z0 + r0 % p.bz, tile_y0 + (r0 / p.bz) % p.by,
+                             tile_x0 + r0 / (p.bz * p.by), tile_b);
+            } else if (p.splits > 1) {
+              tma_reduce_add_2d(&tmC, sb, nc, m_tile * BM + ew * 32);
             } else {
               tma_store_2d(&tmC, sb, nc, m_tile * BM + ew * 32);
             }
@@ -508,6 +529,46 @@ static int next_pow2(int v) {
   return p;
 }
 
+// GroupNorm statistics of a finished (B, rows_per_batch, C) conv output (split-K path): stats[b][g] += (sum, sumsq).
+// One CTA = 32 rows; thread t owns the float4 column t (t + 256, ...): eight independent row loads in flight, fp32 sums
+// over the 32 rows, fp64 per group in shared memory, one fp64 global atomic per (CTA, group, moment).
+constexpr int GS_ROWS = 32;
+__global__ void __launch_bounds__(256)
+conv_gn_stats_kernel(const float* __restrict__ out, double* __restrict__ stats, int rows_per_batch, int C, int cpg) {
+  __shared__ double sg[64];
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * GS_ROWS;
+  const int nr = min(GS_ROWS, rows_per_batch - r0);
+  const int groups = C / cpg;
+  const int C4 = C >> 2;
+  if (threadIdx.x < 64) sg[threadIdx.x] = 0.0;
+  __syncthreads();
+  const float4* base = reinterpret_cast<const float4*>(out + ((size_t)b * rows_per_batch + r0) * C);
+  for (int c4 = threadIdx.x; c4 < C4; c4 += 256) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int r = 0; r < nr; ++r) {
+      const float4 v = __ldg(base + (size_t)r * C4 + c4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
+    const int c = c4 << 2;
+    if (cpg >= 4) {  // the four columns share a group (cpg is a power of two)
+      atomicAdd(&sg[2 * (c / cpg)], (double)((s.x + s.y) + (s.z + s.w)));
+      atomicAdd(&sg[2 * (c / cpg) + 1], (double)((q.x + q.y) + (q.z + q.w)));
+    } else {
+      const float sv[4] = {s.x, s.y, s.z, s.w}, qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&sg[2 * ((c + j) / cpg)], (double)sv[j]);
+        atomicAdd(&sg[2 * ((c + j) / cpg) + 1], (double)qv[j]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * groups) atomicAdd(&stats[(size_t)b * 2 * groups + threadIdx.x], sg[threadIdx.x]);
+}
+
 template <int BN, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        int num_tiles, cudaStream_t stream) {
@@ -535,7 +596,8 @@ static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmC, const v
   uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
   int rc = make_tmap_f32(&tmB, W, 2, dims, strides, box, nullptr);
   if (rc) return rc;
-  const int num_tiles = num_m_tiles * ((p.N + BN - 1) / BN);
+  if (p.splits < 1) p.splits = 1;
+  const int num_tiles = num_m_tiles * ((p.N + BN - 1) / BN) * p.splits;
   switch (BN) {
     case 32: return launch_gemm<32, 8>(tmA, tmB, tmC, p, num_tiles, stream);
     case 64: return launch_gemm<64, 8>(tmA, tmB, tmC, p, num_tiles, stream);
@@ -637,7 +699,39 @@ extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B,
     rc = make_tmap_f32(&tmC, out, 5, cd, cs, cb, nullptr);
     if (rc) return rc;
   }
-  return dispatch_gemm(tmA, tmC, w2, p, B * p.tiles_x * p.tiles_y * p.tiles_z, stream);
+  const int num_m_tiles = B * p.tiles_x * p.tiles_y * p.tiles_z;
+  // Split-K for the deep stages (few output tiles, long K = 27 * Cin): a 512->512 conv on 50x50x4 voxels has 158 tiles
+  // for 148 SMs (second wave 7 % full), a 1024->1024 conv on 25x25x2 has 40.  The raw conv output of the encoder has
+  // no bias / activation (GroupNorm follows), so the partial sums can meet in `out` through TMA reduce-add; the
+  // GroupNorm statistics are then taken from the finished tensor.
+  p.splits = 1;
+  if (p.use_tma_store && !bias && !residual && act == 0 && !round_out) {
+    const int bn = Cout <= 32 ? 32 : Cout <= 64 ? 64 : (Cout <= 128 || (Cout % 256 != 0 && Cout % 128 == 0)) ? 128 : 256;
+    const long long tiles = (long long)num_m_tiles * ((Cout + bn - 1) / bn);
+    const int sms = sm_count();
+    auto eff = [&](int s) { const long long t = tiles * s; return (double)t / (double)(((t + sms - 1) / sms) * sms); };
+    if (tiles >= 4 && tiles < 2 * sms && p.num_k_blocks >= 64 && eff(1) < 0.85) {  // (a handful of tiles: latency-bound anyway)
+      int best = 1;
+      for (int sp = 2; sp <= 8 && sp * 8 <= p.num_k_blocks; ++sp) {
+        if (eff(sp) > eff(best) + 0.02) best = sp;
+        if (eff(best) >= 0.85) break;
+      }
+      p.splits = best;
+    }
+  }
+  if (p.splits > 1) {
+    OCC_CUDA(cudaMemsetAsync(out, 0, (size_t)p.M * Cout * sizeof(float), stream));
+    p.gn_stats = nullptr;
+  }
+  rc = dispatch_gemm(tmA, tmC, w2, p, num_m_tiles, stream);
+  if (rc) return rc;
+  if (p.splits > 1 && gn_stats) {
+    const int rows_per_batch = p.Xo * p.Yo * p.Zo;
+    dim3 grid((rows_per_batch + GS_ROWS - 1) / GS_ROWS, B);
+    conv_gn_stats_kernel<<<grid, 256, 0, stream>>>(out, gn_stats, rows_per_batch, Cout, cpg);
+    OCC_LAUNCH_CHECK();
+  }
+  return OCC_OK;
 }
 
 

@@ -471,10 +471,9 @@ template <int KMAX>
 __global__ void __launch_bounds__(CM_THREADS)
 classmix_kernel(const float* __restrict__ mask, const float* __restrict__ cls, float* __restrict__ out,
                 unsigned char* __restrict__ labels, int X, int Y, int Z, int Xo, int Yo, int Zo, int Q, int NC) {
-  extern __shared__ __align__(16) float sm[];  // P[Q][KMAX] (zero padded), rows[CM_THREADS][Q+1] (identity path)
+  extern __shared__ __align__(16) float sm[];  // P[Q][KMAX] (zero padded)
   const int K = NC - 1;
   float* P = sm;
-  float* rows = sm + Q * KMAX;
   const int b = blockIdx.y;
   // softmax over the NC class logits of every query, drop the last (no-object) column
   for (int q = threadIdx.x; q < Q; q += blockDim.x) {
@@ -493,30 +492,23 @@ classmix_kernel(const float* __restrict__ mask, const float* __restrict__ cls, f
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
   if (identity) {
-    // coalesced stage of CM_THREADS voxel rows (Q floats each, Q % 4 == 0) through shared memory: warp w copies rows
-    // w, w+4, ... with one float4 per lane; row pitch Q + 4 keeps the rows 16-byte aligned
-    const int QP = Q + 4;
-    const int nrows = (int)min((long long)CM_THREADS, Vo - v0);
-    const float* src = mask + ((size_t)b * Vo + v0) * Q;
-    {
-      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-      const int q4n = Q >> 2;
-      for (int r = w; r < nrows; r += CM_THREADS / 32) {
-        const float4* rs = reinterpret_cast<const float4*>(src + (size_t)r * Q);
-        float4* rd = reinterpret_cast<float4*>(rows + r * QP);
-        for (int c = l; c < q4n; c += 32) rd[c] = __ldcs(rs + c);
-      }
-    }
+    // thread = voxel: its Q logits are one contiguous run, read straight into registers in 32-byte pieces (no staging,
+    // no barrier after the class table: the occupancy hides the latency; every line is consumed completely)
     __syncthreads();
     if (v < Vo) {
-      const float4* r4 = reinterpret_cast<const float4*>(rows + threadIdx.x * QP);
-      for (int q4 = 0; q4 < (Q >> 2); ++q4) {
-        const float4 lv = r4[q4];
-        const float lg[4] = {lv.x, lv.y, lv.z, lv.w};
+      const float4* r4 = reinterpret_cast<const float4*>(mask + ((size_t)b * Vo + v) * Q);
+      for (int q8 = 0; q8 < Q; q8 += 8) {
+        float lg[8];
+        const float4 a = __ldcs(r4 + (q8 >> 2));
+        lg[0] = a.x; lg[1] = a.y; lg[2] = a.z; lg[3] = a.w;
+        const bool two = q8 + 4 < Q;
+        const float4 c = two ? __ldcs(r4 + (q8 >> 2) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        lg[4] = c.x; lg[5] = c.y; lg[6] = c.z; lg[7] = c.w;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 8; ++e) {
+          if (e >= 4 && !two) break;
           const float s = 1.0f / (1.0f + __expf(-lg[e]));
-          const float* pq = P + (4 * q4 + e) * KMAX;
+          const float* pq = P + (q8 + e) * KMAX;
 #pragma unroll
           for (int k = 0; k < KMAX; k += 4) {
             const float4 pp = *reinterpret_cast<const float4*>(pq + k);
@@ -765,7 +757,7 @@ extern "C" int occ_classmix(const float* mask, const float* cls, float* out, uns
   const long long Vo = (long long)Xo * Yo * Zo;
   const int kmax = (NC - 1 <= 20) ? 20 : 32;
   OCC_REQUIRE(Q % 4 == 0);
-  const size_t smem = ((size_t)Q * kmax + (size_t)CM_THREADS * (Q + 4)) * sizeof(float);
+  const size_t smem = (size_t)Q * kmax * sizeof(float);
   OCC_REQUIRE(smem <= 200 * 1024);
   dim3 grid((unsigned)((Vo + CM_THREADS - 1) / CM_THREADS), B);
   if (NC - 1 <= 20) {

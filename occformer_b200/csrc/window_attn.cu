@@ -49,6 +49,7 @@ constexpr uint32_t WA_TMEM_COLS = 512;                 // S/P: 2 x 128, O: 2 x 3
 
 struct WinGeom {
   int B, X, Y, Z, C, heads, shift;
+  int head_major;  // qkv columns ordered [head][q|k|v][32] instead of the reference's [q|k|v][head][32]
   int Xp, Yp, nWx, nWy;
   long long vox_rows;  // B*X*Y*Z
   long long nwin;
@@ -100,6 +101,10 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
   // + gridDim.x / H, ...  The H CTAs of a group walk the same pairs at the same time, so the 12 128-byte segments of
   // every qkv token row (one DRAM page) are fetched together, and the head's bias table stays resident in smem.
   const int h = blockIdx.x % H;
+  // head-major qkv: the head's q, k, v slices are one contiguous 384-byte run per token (three adjacent lines of one
+  // DRAM page); reference order: three 128-byte slices C floats apart
+  const int h_off = g.head_major ? h * 3 * HD : h * HD;
+  const int kv_step = g.head_major ? HD : g.C;
   const int pair0 = blockIdx.x / H, pair_stride = gridDim.x / H;
   const long long n_units = (npairs > pair0) ? (npairs - pair0 + pair_stride - 1) / pair_stride : 0;
   for (int i = threadIdx.x; i < WT * WA_BIAS_LD; i += WA_THREADS) {  // scores live in the log2 domain (exp2 softmax)
@@ -150,9 +155,10 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         }
         rows[l] = r;
         region[l] = reg;
-        // global address of this token's q head-slice (k / v follow at +C / +2C floats); pad tokens read the qkv bias
+        // global address of this token's q head-slice (k / v follow at +kv_step / +2 kv_step floats); pad tokens read
+        // the qkv bias
         reinterpret_cast<const float**>(st + WA_OFF_SRC)[l] =
-            r >= 0 ? qkv + r * 3 * C + h * HD : (r == -1 ? qkv_bias + h * HD : nullptr);
+            r >= 0 ? qkv + r * 3 * C + h_off : (r == -1 ? qkv_bias + h_off : nullptr);
       }
       {  // shift-mask bookkeeping: same[half][r] = 64-bit set of the window's keys that lie in region r (two warp ballots)
         const int t = l & 63, wl = l >> 5;  // loader warp wl covers tokens 32*(wl&1) .. +31 of window half wl>>1
@@ -186,8 +192,8 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
             *reinterpret_cast<float4*>(drow + 2 * WA_TILE + off_v) = z;
           } else {
             cp_async_16(drow + off_qk, src + c * 4);
-            cp_async_16(drow + WA_TILE + off_qk, src + C + c * 4);
-            cp_async_16(drow + 2 * WA_TILE + off_v, src + 2 * C + c * 4);
+            cp_async_16(drow + WA_TILE + off_qk, src + kv_step + c * 4);
+            cp_async_16(drow + 2 * WA_TILE + off_v, src + 2 * kv_step + c * 4);
           }
         }
       }
@@ -388,13 +394,15 @@ static float* g_wattn_dbg = nullptr;
 // qkv (rows, 3C) with rows = B*X*Y*(Z+1) token-ordered (voxel tokens then BEV tokens); out (rows, C), tf32-rounded.
 // bias_pad = relative_position_bias_table[relative_position_index] arranged (heads, 49*49 padded to 2404 floats).
 extern "C" int occ_window_attention(const float* qkv, const float* qkv_bias, const float* bias_pad, float* out, int B,
-                                    int X, int Y, int Z, int C, int heads, int shift, cudaStream_t stream) {
+                                    int X, int Y, int Z, int C, int heads, int shift, int qkv_head_major,
+                                    cudaStream_t stream) {
   OCC_REQUIRE(qkv && qkv_bias && bias_pad && out);
   OCC_REQUIRE(B > 0 && X > 0 && Y > 0 && Z > 0 && heads > 0 && C == heads * HD);
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv_bias) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(bias_pad) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   WinGeom g;
   g.B = B; g.X = X; g.Y = Y; g.Z = Z; g.C = C; g.heads = heads; g.shift = shift ? 1 : 0;
+  g.head_major = qkv_head_major ? 1 : 0;
   g.nWx = (X + WS - 1) / WS; g.nWy = (Y + WS - 1) / WS;
   g.Xp = g.nWx * WS; g.Yp = g.nWy * WS;
   g.vox_rows = (long long)B * X * Y * Z;

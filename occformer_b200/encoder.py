@@ -138,7 +138,11 @@ class DualpathTransformerBlock(nn.Module):
         if self.stride > 1:
             P["w_ds"], P["k_ds"] = ops.repack_conv_weight(self.downsample[0].weight.detach().float())
         msa = self.bev_encoder.attn.w_msa
-        P["w_qkv"] = r(msa.qkv.weight.detach().float().clone().contiguous())
+        # qkv rows permuted to [head][q|k|v][32]: the attention kernel then reads one contiguous 384-byte run per
+        # (token, head) instead of three 128-byte slices C floats apart
+        perm = ops.qkv_head_major_perm(msa.qkv.weight.shape[1], self.num_heads, msa.qkv.weight.device)
+        P["w_qkv"] = r(msa.qkv.weight.detach().float()[perm].clone().contiguous())
+        P["b_qkv"] = msa.qkv.bias.detach().float()[perm].clone().contiguous()
         P["w_proj"] = r(msa.proj.weight.detach().float().clone().contiguous())
         ffn = self.bev_encoder.ffn.layers
         P["w_f1"] = r(ffn[0][0].weight.detach().float().clone().contiguous())
@@ -179,9 +183,10 @@ class DualpathTransformerBlock(nn.Module):
                                          sw.norm1.bias, B, XY, Z, C, G)
         msa = sw.attn.w_msa
         # (A8) QKV projection of every token (pad tokens are synthesised from the bias inside the attention kernel)
-        qkv = ops.gemm(tokn, P["w_qkv"], bias=msa.qkv.bias, round_out=True)
+        qkv = ops.gemm(tokn, P["w_qkv"], bias=P["b_qkv"], round_out=True)
         # (A7/A8) shifted-window attention core, gathers/scatters windows in place
-        att = ops.window_attention(qkv, msa.qkv.bias, P["bias_pad"], B, X, Y, Z, C, self.num_heads, self.shift)
+        att = ops.window_attention(qkv, P["b_qkv"], P["bias_pad"], B, X, Y, Z, C, self.num_heads, self.shift,
+                                   head_major=True)
         # proj + residual, LayerNorm2, FFN (GELU) + residual  (A6)
         ffn = sw.ffn.layers
         if C == 128 and P["w_f1"].shape == (C, C):

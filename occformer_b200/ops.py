@@ -270,13 +270,20 @@ def dualpath_fuse(x, bev, cw, cbias, identity, B, XY, Z, C, id_stats=None, id_w=
     return out
 
 
-def window_attention(qkv, qkv_bias, bias_pad, B, X, Y, Z, C, heads, shift):
+def qkv_head_major_perm(C, heads, device=None):
+    """row permutation of WindowMSA.qkv (weight / bias): new row h*96 + which*32 + d <- reference row which*C + h*32 + d."""
+    hd = C // heads
+    idx = torch.arange(3 * C, device=device).view(3, heads, hd).permute(1, 0, 2).reshape(-1)
+    return idx
+
+
+def window_attention(qkv, qkv_bias, bias_pad, B, X, Y, Z, C, heads, shift, head_major=False):
     _chk(qkv, "qkv")
     rows = B * X * Y * (Z + 1)
     assert qkv.shape == (rows, 3 * C)
     out = torch.empty((rows, C), dtype=torch.float32, device=qkv.device)
     check(lib().occ_window_attention(_ptr(qkv), _ptr(qkv_bias), _ptr(bias_pad), _ptr(out), B, X, Y, Z, C, heads,
-                                     int(shift), _stream()), "occ_window_attention")
+                                     int(shift), int(head_major), _stream()), "occ_window_attention")
     LAUNCH_COUNT[0] += 1
     return out
 

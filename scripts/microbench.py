@@ -89,6 +89,7 @@ def main():
         bd = torch.randn(4, 2404, device=dev)
         t = timeit(lambda: ops.window_attention(qkv, qb, bd, 1, X, Y, Z, C, 4, True))
         res["window_attn_tc_ms"] = t
+        res["window_attn_tc_head_major_ms"] = timeit(lambda: ops.window_attention(qkv, qb, bd, 1, X, Y, Z, C, 4, True, head_major=True))
         res["window_attn_GBps"] = (M * 3 * C * 4 + M * C * 4) / t / 1e6
     if "swin" in which:
         M = X * Y * (Z + 1)

@@ -51,6 +51,9 @@ CONV_CASES = [
     (1, 30, 20, 1, 64, 64, (3, 3, 1), 1, 18),
     (1, 7, 5, 3, 32, 256, (3, 3, 3), 2, 1),
     (1, 13, 13, 1, 160, 32, (1, 1, 1), 1, 1),
+    # few output tiles, long K: split-K (partial sums meet through TMA reduce-add, GroupNorm statistics from the result)
+    (1, 25, 25, 4, 256, 512, (3, 3, 3), 1, 1),
+    (2, 50, 50, 8, 128, 256, (3, 3, 3), 2, 1),
 ]
 
 

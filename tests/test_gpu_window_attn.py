@@ -43,3 +43,8 @@ def test_window_attention_vs_oracle(cuda, B, X, Y, Z, C, shift):
     out = ops.window_attention(qkv_rows.to(cuda), sd["w_msa.qkv.bias"].to(cuda), bias_pad.to(cuda), B, X, Y, Z, C, heads, shift)
     ref_rows = _rows_from_images(ref, B, X, Y, Z)
     assert_close(out, ref_rows, 1e-3, f"window attention B{B} {X}x{Y}x{Z} C{C} shift={shift}")
+    # head-major qkv columns ([head][q|k|v][32], what the encoder feeds): identical arithmetic, identical result
+    perm = ops.qkv_head_major_perm(C, heads)
+    out_hm = ops.window_attention(qkv_rows[:, perm].contiguous().to(cuda), sd["w_msa.qkv.bias"][perm].contiguous().to(cuda),
+                                  bias_pad.to(cuda), B, X, Y, Z, C, heads, shift, head_major=True)
+    assert torch.equal(out_hm, out), "head-major qkv layout changes the result"
