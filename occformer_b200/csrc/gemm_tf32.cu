@@ -710,7 +710,9 @@ extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B,
     const long long tiles = (long long)num_m_tiles * ((Cout + bn - 1) / bn);
     const int sms = sm_count();
     auto eff = [&](int s) { const long long t = tiles * s; return (double)t / (double)(((t + sms - 1) / sms) * sms); };
-    if (tiles >= 4 && tiles < 2 * sms && p.num_k_blocks >= 64 && eff(1) < 0.85) {  // (a handful of tiles: latency-bound anyway)
+    // (not below 8 M-tiles = 1024 output rows: such convs are latency-bound either way, and keeping them on the
+    // single-pass path keeps small problems bit-reproducible -- the reduce-add order of the splits is not fixed)
+    if (num_m_tiles >= 8 && tiles < 2 * sms && p.num_k_blocks >= 64 && eff(1) < 0.85) {
       int best = 1;
       for (int sp = 2; sp <= 8 && sp * 8 <= p.num_k_blocks; ++sp) {
         if (eff(sp) > eff(best) + 0.02) best = sp;
