@@ -60,6 +60,12 @@ struct GemmParams {
   int rows_per_batch;  // plain mode: rows per batch sample (for gn_stats), else 0
 };
 
+// Split-K ordering: sem[(m, n) tile] counts the splits that have added their partial sum.  Split s adds after split
+// s - 1, so the fp32 reduce-add order -- and with it every bit of the result -- is fixed.  Zero at module load, and
+// reset to zero by the last split of every tile (convs on one stream reuse it; concurrent split-K convs on different
+// streams would only lose the fixed order, not correctness: the wait is bounded).
+__device__ int g_splitk_sem[1024];
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // order-preserving float <-> int map (signed compare of the ints == compare of the floats; sign is kept)
@@ -317,6 +323,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
+      if (p.splits > 1) {  // wait until the lower splits of this tile have added their partial sums
+        if (threadIdx.x == 128) {
+          const int want = tile % p.splits;
+          volatile int* sem = g_splitk_sem + ((tile / p.splits) & 1023);
+          for (int spin = 0; *sem != want && spin < (1 << 16); ++spin) __nanosleep(64);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * BN;
       // software-pipelined TMEM reads: the load of this warp's next chunk (c+2) is in flight while chunk c is processed
       uint32_t rnext[32];
@@ -494,6 +508,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (p.splits > 1) {  // publish: this split's reduce-adds are complete
+        if (lane == 0) tma_store_wait_all();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 128) {
+          __threadfence();
+          const int split = tile % p.splits;
+          atomicExch(g_splitk_sem + ((tile / p.splits) & 1023), split == p.splits - 1 ? 0 : split + 1);
+        }
+      }
     }
     if (p.gn_stats != nullptr) {
       asm volatile("bar.sync 1, 256;" ::: "memory");

@@ -76,6 +76,10 @@ def test_conv(cuda, case):
     r = ref.reshape(B, groups, -1)
     ref_stats = torch.stack((r.sum(-1), (r * r).sum(-1)), dim=-1)
     assert_close(stats, ref_stats, 1e-4, f"conv gn_stats {case}")  # tensor-core accumulation rounds toward zero
+    # bit-reproducible, also on the split-K path (the splits add their partial sums in a fixed order)
+    for _ in range(3):
+        again = ops.conv(x_cl, w2, ks, stride=stride, dil=dil)
+        assert torch.equal(again, out), f"conv {case} is not bit-reproducible"
 
 
 def test_gemm_rejects_bad_args(cuda):
