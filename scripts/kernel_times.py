@@ -10,8 +10,9 @@ from torch.profiler import ProfilerActivity, profile
 import bench
 
 dev = torch.device("cuda:0")
-pipe = bench.Pipeline(dev, 1)
-host = bench.host_inputs(1, 0)
+BATCH = int(os.environ.get("OCC_BATCH", "1"))  # OCC_BATCH=4 = the bench default
+pipe = bench.Pipeline(dev, BATCH)
+host = bench.host_inputs(BATCH, 0)
 res = {k: v.to(dev) for k, v in host.items()}
 for _ in range(3):
     pipe.run(res)
@@ -28,7 +29,7 @@ for e in prof.key_averages():
         rows.append((t, e.count, e.key))
 rows.sort(reverse=True)
 tot = sum(r[0] for r in rows)
-out = [f"# per-kernel device time of one step (torch.profiler), total {tot / 1e3:.3f} ms", "", "| kernel | launches | total us | share |",
+out = [f"# per-kernel device time of one step at batch {BATCH} (torch.profiler), total {tot / 1e3:.3f} ms", "", "| kernel | launches | total us | share |",
        "|---|---:|---:|---:|"]
 for t, c, k in rows[:45]:
     out.append(f"| {k[:90]} | {c} | {t:.1f} | {100 * t / tot:.1f}% |")
