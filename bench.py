@@ -260,6 +260,11 @@ def run_reference(args, rank, world):
 # ----------------------------------------------------------------------------------------------------------------------
 # B200 leg
 # ----------------------------------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum of one conv3d 3x3x3 C=128 launch on one 200x200x16 sample, from the
+# committed ncu --set full capture (profiles/r01_ncu_conv3d_gemm_tf32_v2.md); the kernel's traffic scales with the batch
+NCU_CONV_DRAM_BYTES_PER_SAMPLE = 329.548544e6 + 292.756224e6
+
+
 def time_kernel_family(pipe, dev, peak):
     """Roofline of the dominant kernel family, timed live (CUDA events on the current stream, L2 flushed)."""
     from occformer_b200 import ops
@@ -285,9 +290,11 @@ def time_kernel_family(pipe, dev, peak):
     # TF32 dense peak = half the bf16 peak on this part (B200_PROFILING.md table: 1.1 vs 2.25 PF nominal)
     pk = peak["tf"] / 2.0
     return {"kernel": "gemm_tf32_kernel<conv3d 3x3x3, C=128, 200x200x16>", "bound": "tensor", "achieved": achieved,
-            "peak": pk, "unit": "TFLOP/s", "frac": achieved / pk, "traffic": None,
+            "peak": pk, "unit": "TFLOP/s", "frac": achieved / pk, "traffic": NCU_CONV_DRAM_BYTES_PER_SAMPLE * B,
             "note": f"algorithmic FLOPs 2*27*Cin*Cout*V = {flops / 1e9:.1f} GF per launch / {ms:.3f} ms (CUDA events); peak = "
-                    f"tf32 dense = measured bf16 burst / 2, {peak['src']}"}
+                    f"tf32 dense = measured bf16 burst / 2, {peak['src']}; traffic = dram__bytes_read+write of this "
+                    f"kernel from the ncu --set full capture at batch 1 (profiles/r01_ncu_conv3d_gemm_tf32_v2.md: 329.5 + "
+                    f"292.8 MB) x batch {B}; algorithmic bytes = {2 * B * X * Y * Z * C * 4 / 1e6:.0f} MB"}
 
 
 def run_b200(args, rank, world, local_rank):
