@@ -99,14 +99,20 @@ __device__ __forceinline__ void warp_butterfly32(float (&v)[32], int lane) {
   }
 }
 
-template <int BN, int STAGES>
+// MT = M-tiles per CTA tile.  MT = 2 (stage-0 convs, N = 128): two 128-row accumulators share every B k-block, so the
+// TMA engine writes 48 KB instead of 64 KB of shared memory per two tiles -- the 128x128 tile is bound by the
+// shared-memory port (TMA writes + MMA operand reads), not by the tensor pipe.
+template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(384, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BK * 4;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                 : (2 * BN <= 256) ? 256 : 512;
+  constexpr int A_BYTES = MT * A_STAGE_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+  constexpr int ACC_COLS = BN * MT;  // accumulator columns of one tile (MT sub-tiles side by side)
+  static_assert(2 * ACC_COLS <= 512, "two accumulator buffers must fit TMEM");
+  constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
+                                 : (2 * ACC_COLS <= 256) ? 256 : 512;
   constexpr uint32_t IDESC = make_idesc_tf32(BM, BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
@@ -125,7 +131,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int num_n_tiles = (p.N + BN - 1) / BN;
   const int num_m_tiles = p.conv ? p.B * p.tiles_x * p.tiles_y * p.tiles_z : (p.M + BM - 1) / BM;
-  const int num_tiles = num_m_tiles * num_n_tiles * p.splits;
+  const int num_m_groups = (num_m_tiles + MT - 1) / MT;
+  const int num_tiles = num_m_groups * num_n_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -161,19 +168,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int split = tile % p.splits;
         const int n_tile = (tile / p.splits) % num_n_tiles;
-        const int m_tile = tile / (p.splits * num_n_tiles);
+        const int m_group = tile / (p.splits * num_n_tiles);
         const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
         const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
-        int cb = 0, cx0 = 0, cy0 = 0, cz0 = 0;
-        if (p.conv) {
-          int t = m_tile;
-          const int tz = t % p.tiles_z; t /= p.tiles_z;
-          const int ty = t % p.tiles_y; t /= p.tiles_y;
-          const int tx = t % p.tiles_x; t /= p.tiles_x;
-          cb = t;
-          cx0 = tx * p.bx * p.stride - p.padx;
-          cy0 = ty * p.by * p.stride - p.pady;
-          cz0 = tz * p.bz * p.stride - p.padz;
+        int cb[MT], cx0[MT], cy0[MT], cz0[MT];
+#pragma unroll
+        for (int sub = 0; sub < MT; ++sub) {
+          cb[sub] = cx0[sub] = cy0[sub] = cz0[sub] = 0;
+          if (p.conv) {
+            int t = m_group * MT + sub;  // past the last tile: cb == B, the TMA box is out of bounds and zero-filled
+            const int tz = t % p.tiles_z; t /= p.tiles_z;
+            const int ty = t % p.tiles_y; t /= p.tiles_y;
+            const int tx = t % p.tiles_x; t /= p.tiles_x;
+            cb[sub] = t;
+            cx0[sub] = tx * p.bx * p.stride - p.padx;
+            cy0[sub] = ty * p.by * p.stride - p.pady;
+            cz0[sub] = tz * p.bz * p.stride - p.padz;
+          }
         }
         int tap = 0, kc = 0, tx_ = 0, ty_ = 0, tz_ = 0;
         if (p.conv && kb0 > 0) {  // split-K: start in the middle of the tap sequence
@@ -186,11 +197,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           if (p.conv) {
-            tma_load_5d(sa, &tmA, &full_bar[stage], kc * BK, cz0 + tz_ * p.dil, cy0 + ty_ * p.dil,
-                        cx0 + tx_ * p.dil, cb);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub)
+              tma_load_5d(sa + sub * A_STAGE_BYTES, &tmA, &full_bar[stage], kc * BK, cz0[sub] + tz_ * p.dil,
+                          cy0[sub] + ty_ * p.dil, cx0[sub] + tx_ * p.dil, cb[sub]);
             if (++kc == cblocks) {
               kc = 0;
               ++tap;
@@ -200,7 +213,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           } else {
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_tile * BM);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub)
+              tma_load_2d(sa + sub * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, (m_group * MT + sub) * BM);
           }
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_tile * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -218,7 +233,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int buf = it & 1;
         mbar_wait(&tmem_empty[buf], (((it >> 1) & 1) ^ 1));
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
+        const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
         const int split = tile % p.splits;
         const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
         const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
@@ -226,13 +241,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
-          const uint64_t adesc = make_sw128_desc(sa, 1024, 16);
+          const uint32_t sb = sa + A_BYTES;
           const uint64_t bdesc = make_sw128_desc(sb, 1024, 16);
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            // advance 8 tf32 = 32 bytes = 2 (16-byte units) inside the 128-byte swizzle row
-            mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, ((kb - kb0) | k) != 0);
+          for (int sub = 0; sub < MT; ++sub) {
+            const uint64_t adesc = make_sw128_desc(sa + sub * A_STAGE_BYTES, 1024, 16);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              // advance 8 tf32 = 32 bytes = 2 (16-byte units) inside the 128-byte swizzle row
+              mma_tf32_ss(d_tmem + sub * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, ((kb - kb0) | k) != 0);
+            }
           }
           mma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -260,8 +278,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const int n_tile = (tile / p.splits) % num_n_tiles;
-      const int m_tile = tile / (p.splits * num_n_tiles);
+      const int m_group = tile / (p.splits * num_n_tiles);
       const int n0 = n_tile * BN;
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+      const int m_tile = m_group * MT + sub;
+      if (m_tile >= num_m_tiles) continue;  // odd tail of a paired tile (warp-uniform)
       // ---- output row of this thread
       long long m = -1;
       int tile_b = 0, tile_x0 = 0, tile_y0 = 0, tile_z0 = 0;
@@ -321,8 +345,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         cur_b = tile_b;
       }
 
-      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
-      tc_fence_after();
       if (p.splits > 1) {  // wait until the lower splits of this tile have added their partial sums
         if (threadIdx.x == 128) {
           const int want = tile % p.splits;
@@ -331,7 +353,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * ACC_COLS + sub * BN;
       // software-pipelined TMEM reads: the load of this warp's next chunk (c+2) is in flight while chunk c is processed
       uint32_t rnext[32];
       if (n0 + wg * 32 < p.N && wg < BN / 32) tmem_ld_32x32(t_row + wg * 32, rnext);
@@ -505,6 +527,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (nc + j < p.N) orow[j] = v[j];
         }
       }
+      }  // sub
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -592,20 +615,21 @@ conv_gn_stats_kernel(const float* __restrict__ out, double* __restrict__ stats, 
   if (threadIdx.x < 2 * groups) atomicAdd(&stats[(size_t)b * 2 * groups + threadIdx.x], sg[threadIdx.x]);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT = 1>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        int num_tiles, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BK * 4) + 1024 /*align*/ + 1024 /*barriers+stats*/ +
-                          EPI_BYTES;
+  constexpr size_t smem = (size_t)STAGES * (MT * A_STAGE_BYTES + BN * BK * 4) + 1024 /*align*/ +
+                          1024 /*barriers+stats*/ + EPI_BYTES;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    OCC_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    OCC_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     configured = true;
   }
   int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   if (grid < 1) grid = 1;
-  gemm_tf32_kernel<BN, STAGES><<<grid, 384, smem, stream>>>(tmA, tmB, tmC, p);
+  gemm_tf32_kernel<BN, STAGES, MT><<<grid, 384, smem, stream>>>(tmA, tmB, tmC, p);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -621,6 +645,10 @@ static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmC, const v
   if (rc) return rc;
   if (p.splits < 1) p.splits = 1;
   const int num_tiles = num_m_tiles * ((p.N + BN - 1) / BN) * p.splits;
+  // stage-0 convs (N = 128, thousands of M-tiles): pairs of M-tiles share every weight k-block (MT = 2)
+  if (BN == 128 && p.conv && p.splits == 1 && p.pool_out == nullptr && p.use_tma_store &&
+      num_m_tiles >= 4 * sm_count())
+    return launch_gemm<128, 4, 2>(tmA, tmB, tmC, p, ((num_m_tiles + 1) / 2) * ((p.N + BN - 1) / BN), stream);
   switch (BN) {
     case 32: return launch_gemm<32, 8>(tmA, tmB, tmC, p, num_tiles, stream);
     case 64: return launch_gemm<64, 8>(tmA, tmB, tmC, p, num_tiles, stream);

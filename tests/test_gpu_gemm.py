@@ -54,6 +54,8 @@ CONV_CASES = [
     # few output tiles, long K: split-K (partial sums meet through TMA reduce-add, GroupNorm statistics from the result)
     (1, 25, 25, 4, 256, 512, (3, 3, 3), 1, 1),
     (2, 50, 50, 8, 128, 256, (3, 3, 3), 2, 1),
+    # many M-tiles, N <= 128: paired M-tiles share the weight k-blocks (MT = 2); 611 tiles = odd tail pair
+    (1, 47, 51, 32, 32, 64, (3, 3, 3), 1, 1),
 ]
 
 
