@@ -261,8 +261,8 @@ def run_reference(args, rank, world):
 # B200 leg
 # ----------------------------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of one conv3d 3x3x3 C=128 launch on one 200x200x16 sample, from the
-# committed ncu --set full capture (profiles/r01_ncu_conv3d_gemm_tf32_v2.md); the kernel's traffic scales with the batch
-NCU_CONV_DRAM_BYTES_PER_SAMPLE = 329.548544e6 + 292.756224e6
+# committed ncu --set full capture (profiles/r01_ncu_conv3d_gemm_tf32_v3_mt2.md); the kernel's traffic scales with the batch
+NCU_CONV_DRAM_BYTES_PER_SAMPLE = 330.048512e6 + 288.318976e6
 
 
 def time_kernel_family(pipe, dev, peak):
@@ -293,8 +293,8 @@ def time_kernel_family(pipe, dev, peak):
             "peak": pk, "unit": "TFLOP/s", "frac": achieved / pk, "traffic": NCU_CONV_DRAM_BYTES_PER_SAMPLE * B,
             "note": f"algorithmic FLOPs 2*27*Cin*Cout*V = {flops / 1e9:.1f} GF per launch / {ms:.3f} ms (CUDA events); peak = "
                     f"tf32 dense = measured bf16 burst / 2, {peak['src']}; traffic = dram__bytes_read+write of this "
-                    f"kernel from the ncu --set full capture at batch 1 (profiles/r01_ncu_conv3d_gemm_tf32_v2.md: 329.5 + "
-                    f"292.8 MB) x batch {B}; algorithmic bytes = {2 * B * X * Y * Z * C * 4 / 1e6:.0f} MB"}
+                    f"kernel from the ncu --set full capture at batch 1 (profiles/r01_ncu_conv3d_gemm_tf32_v3_mt2.md: 330.0 + "
+                    f"288.3 MB) x batch {B}; algorithmic bytes = {2 * B * X * Y * Z * C * 4 / 1e6:.0f} MB"}
 
 
 def run_b200(args, rank, world, local_rank):
