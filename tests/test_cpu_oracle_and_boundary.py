@@ -163,3 +163,21 @@ def test_library_exports_every_declared_symbol():
     assert l.occ_version() >= 100
     # pure host-side helper (no GPU needed)
     assert l.occ_voxel_pool_workspace_bytes(1000, 1, 10, 10, 2) > (200 + 201 + 2000) * 4
+
+
+def test_qkv_head_major_permutation_matches_reference_split():
+    """ops.qkv_head_major_perm: the row permutation the encoder applies to WindowMSA.qkv so that a (token, head) reads one
+    contiguous [q|k|v] run.  Slicing the permuted projection per head must give the reference's q, k, v of that head
+    (window_attention.py:86-88: reshape(B, N, 3, heads, C // heads))."""
+    import torch
+    from occformer_b200 import ops
+    C, heads = 128, 4
+    hd = C // heads
+    perm = ops.qkv_head_major_perm(C, heads)
+    assert sorted(perm.tolist()) == list(range(3 * C))
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(5, C, generator=g)
+    w, b = torch.randn(3 * C, C, generator=g), torch.randn(3 * C, generator=g)
+    ref = torch.nn.functional.linear(x, w, b).view(5, 3, heads, hd)        # [token, q|k|v, head, d]
+    hm = torch.nn.functional.linear(x, w[perm], b[perm]).view(5, heads, 3, hd)  # [token, head, q|k|v, d]
+    assert torch.equal(hm.permute(0, 2, 1, 3), ref)
