@@ -9,6 +9,7 @@ The fixtures are what pins oracle/port.py (and, through it, the CUDA path) on th
 fixture stores the reference OUTPUT plus the recipe (shapes, seeds) needed to rebuild the input.
 """
 import os
+import sys
 
 import numpy as np
 import torch
@@ -31,11 +32,28 @@ HEAD_CASE = dict(E=96, Q=12, K=17, L=4, ffn=192, sizes=[(16, 12, 4), (8, 6, 2), 
 POOL_CASE = dict(grid="pr1", input_size=(128, 128), B=2, N=1, C=32, seed=1)
 
 
+def gen_neck():
+    """MSDeformAttnPixelDecoder3D: reference outputs for validate_port.NECK_CASE, B = 1."""
+    c, neck_inputs = port.NECK_CASE, port.neck_inputs
+    sd = port.make_neck_state(c["in_channels"], c["E"], c["layers"], c["heads"], c["levels"], c["points"], c["ffn"],
+                              seed=c["wseed"])
+    neck = refmodels.build_neck(c["in_channels"], c["strides"], c["E"], c["layers"], c["heads"], c["levels"],
+                                c["points"], c["ffn"], sd)
+    feats = neck_inputs(c, B=1)
+    with torch.no_grad():
+        outs = neck([f.clone() for f in feats])
+    np.savez(os.path.join(OUT, "neck_small.npz"), **{f"out{i}": o.numpy() for i, o in enumerate(outs)})
+    print("neck_small", [tuple(o.shape) for o in outs])
+
+
 def main():
     assert shim.reference_available(), "needs /root/reference"
     shim.install()
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
+    if "neck" in sys.argv[1:]:  # python -m oracle.gen_golden neck : only the neck fixture
+        gen_neck()
+        return
 
     # ---- voxel pooling (reference ViewTransformerLiftSplatShootVoxel + its own QuickCumsum fallback)
     pc = POOL_CASE
@@ -79,6 +97,7 @@ def main():
              mask_first=ml[0].numpy(), output_voxels=res["output_voxels"][0].numpy(),
              output_points=res["output_points"].numpy())
     print("head_nusc done")
+    gen_neck()
 
 
 if __name__ == "__main__":

@@ -473,6 +473,173 @@ def head_simple_test(voxel_feats, sd, num_heads, num_layers, occ_size, num_level
 
 
 # =============================================================================
+# MSDeformAttnPixelDecoder3D -- the neck between encoder and head (the first "next" row).
+# ORACLE ONLY in this round: no CUDA implementation yet; pinned against the reference module under the shim
+# (validate_port.check_neck) and by tests/golden/neck_small.npz.
+# =============================================================================
+
+
+def grid_priors_3d(shape, stride, offset=0.5):
+    """MlvlPointGenerator.single_level_grid_priors, 3-D (P/utils/point_generator.py:111-135): cell centres in stride
+    units, one row per voxel in (x slowest, z fastest) order, columns ordered (z, y, x) -- the order F.grid_sample wants
+    for a (X, Y, Z) volume."""
+    X, Y, Z = shape
+    cx = (torch.arange(X, dtype=torch.float32) + offset) * stride
+    cy = (torch.arange(Y, dtype=torch.float32) + offset) * stride
+    cz = (torch.arange(Z, dtype=torch.float32) + offset) * stride
+    gx, gy, gz = torch.meshgrid(cx, cy, cz, indexing="ij")
+    return torch.stack([gz.reshape(-1), gy.reshape(-1), gx.reshape(-1)], dim=-1)
+
+
+def ms_deform_attn_core_3d(value, shapes, loc, weights):
+    """multi_scale_deformable_attn_pytorch (P/occformer/necks/multi_scale_deform_attn_3d.py:17-80).
+    value (B, S, H, hd) with S = sum of level sizes; shapes [(X,Y,Z)] per level; loc (B, Nq, H, L, P, 3) in [0,1],
+    last dim (z, y, x); weights (B, Nq, H, L, P).  Trilinear sampling (zeros outside, align_corners=False) of every
+    level's value volume at the L*P points of every (query, head), weighted sum -> (B, Nq, H*hd)."""
+    B, _, H, hd = value.shape
+    Nq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
+    out = value.new_zeros(B * H, hd, Nq)
+    start = 0
+    for lvl, (X, Y, Z) in enumerate(shapes):
+        n = X * Y * Z
+        vol = value[:, start:start + n].permute(0, 2, 3, 1).reshape(B * H, hd, X, Y, Z)
+        start += n
+        grid = (2.0 * loc[:, :, :, lvl] - 1.0).permute(0, 2, 1, 3, 4).reshape(B * H, 1, Nq, P, 3)
+        samp = F.grid_sample(vol, grid, mode="bilinear", padding_mode="zeros", align_corners=False)  # (BH,hd,1,Nq,P)
+        w = weights[:, :, :, lvl].permute(0, 2, 1, 3).reshape(B * H, 1, Nq, P)
+        out = out + (samp[:, :, 0] * w).sum(-1)
+    return out.view(B, H * hd, Nq).transpose(1, 2).contiguous()
+
+
+def ms_deform_attn_3d(query, query_pos, ref_points, shapes, sd, p, num_heads, num_points):
+    """MultiScaleDeformableAttention3D.forward (multi_scale_deform_attn_3d.py:185-286) as called by BaseTransformerLayer
+    'self_attn' with batch_first=False, post-norm: value = identity = the un-positioned query.  query (Nq, B, E)."""
+    Nq, B, E = query.shape
+    L = len(shapes)
+    identity = query
+    q = (query + query_pos).permute(1, 0, 2)
+    v = F.linear(query.permute(1, 0, 2), sd[p + "value_proj.weight"], sd[p + "value_proj.bias"])
+    v = v.view(B, Nq, num_heads, E // num_heads)
+    off = F.linear(q, sd[p + "sampling_offsets.weight"], sd[p + "sampling_offsets.bias"])
+    off = off.view(B, Nq, num_heads, L, num_points, 3)
+    aw = F.linear(q, sd[p + "attention_weights.weight"], sd[p + "attention_weights.bias"])
+    aw = aw.view(B, Nq, num_heads, L * num_points).softmax(-1).view(B, Nq, num_heads, L, num_points)
+    norm = torch.tensor([[Z, Y, X] for (X, Y, Z) in shapes], dtype=query.dtype)  # offsets are in voxels of each level
+    loc = ref_points[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    out = ms_deform_attn_core_3d(v, shapes, loc, aw)
+    out = F.linear(out, sd[p + "output_proj.weight"], sd[p + "output_proj.bias"])
+    return out.permute(1, 0, 2) + identity
+
+
+def _conv_gn(x, sd, p, groups, padding=0, relu=False):
+    """mmcv ConvModule(conv -> GN [-> ReLU]) with the reference's key names (conv.weight / conv.bias? / gn.*)."""
+    x = F.conv3d(x, sd[p + "conv.weight"], sd.get(p + "conv.bias"), padding=padding)
+    x = F.group_norm(x, groups, sd[p + "gn.weight"], sd[p + "gn.bias"], 1e-5)
+    return F.relu(x) if relu else x
+
+
+def ms_deform_pixel_decoder_3d(feats, sd, strides, num_heads, num_layers, num_levels=3, num_points=4,
+                               norm_groups=32, prefix=""):
+    """MSDeformAttnPixelDecoder3D.forward (P/occformer/necks/multiscale_deformattn_3d.py:143-248).
+    feats: the 4 encoder outputs, high -> low resolution, (B, C_i, X_i, Y_i, Z_i).  Returns [mask_feature, multi-scale
+    memories low-res last ...] in the reference's order (outs[::-1])."""
+    nin = len(feats)
+    B = feats[0].shape[0]
+    E = sd[prefix + "level_encoding.weight"].shape[1]
+    tokens, poss, refs, shapes = [], [], [], []
+    for i in range(num_levels):  # encoder levels: coarsest first (:152-181)
+        li = nin - i - 1
+        f = feats[li]
+        X, Y, Z = f.shape[-3:]
+        proj = _conv_gn(f, sd, f"{prefix}input_convs.{i}.", norm_groups)
+        pos = sine_pos3d(B, X, Y, Z, E // 3) + sd[prefix + "level_encoding.weight"][i].view(1, -1, 1, 1, 1)
+        pts = grid_priors_3d((X, Y, Z), strides[li]) / (torch.tensor([[Z, Y, X]], dtype=torch.float32) * strides[li])
+        tokens.append(proj.flatten(2).permute(2, 0, 1))
+        poss.append(pos.flatten(2).permute(2, 0, 1))
+        refs.append(pts)
+        shapes.append((X, Y, Z))
+    x = torch.cat(tokens, 0)
+    qpos = torch.cat(poss, 0)
+    ref = torch.cat(refs, 0)[None, :, None].repeat(B, 1, num_levels, 1)  # the same point for every level (:199-201)
+    for l in range(num_layers):  # DetrTransformerEncoder of BaseTransformerLayer('self_attn','norm','ffn','norm')
+        p = f"{prefix}encoder.layers.{l}."
+        x = ms_deform_attn_3d(x, qpos, ref, shapes, sd, p + "attentions.0.", num_heads, num_points)
+        x = F.layer_norm(x, (E,), sd[p + "norms.0.weight"], sd[p + "norms.0.bias"], 1e-5)
+        h = F.relu(F.linear(x, sd[p + "ffns.0.layers.0.0.weight"], sd[p + "ffns.0.layers.0.0.bias"]))
+        x = x + F.linear(h, sd[p + "ffns.0.layers.1.weight"], sd[p + "ffns.0.layers.1.bias"])
+        x = F.layer_norm(x, (E,), sd[p + "norms.1.weight"], sd[p + "norms.1.bias"], 1e-5)
+    mem = x.permute(1, 2, 0)
+    outs, start = [], 0
+    for (X, Y, Z) in shapes:
+        n = X * Y * Z
+        outs.append(mem[:, :, start:start + n].reshape(B, E, X, Y, Z))
+        start += n
+    for i in range(nin - num_levels - 1, -1, -1):  # FPN path for the levels that skipped the encoder (:228-246)
+        cur = _conv_gn(feats[i], sd, f"{prefix}lateral_convs.{i}.", norm_groups)
+        y = cur + F.interpolate(outs[-1], size=cur.shape[-3:], mode="trilinear", align_corners=False)
+        outs.append(_conv_gn(y, sd, f"{prefix}output_convs.{i}.", norm_groups, padding=1, relu=True))
+    outs[-1] = F.conv3d(outs[-1], sd[prefix + "mask_feature.weight"], sd[prefix + "mask_feature.bias"])
+    return outs[::-1]
+
+
+def make_neck_state(in_channels, E, num_layers, num_heads, num_levels=3, num_points=4, ffn=None, seed=0):
+    """Deterministic weights with the reference's state_dict keys.  Unlike the reference's init (zero sampling-offset
+    and attention-weight matrices), every matrix is non-trivial so that a parity test moves the sampling points."""
+    g = torch.Generator().manual_seed(seed)
+    ffn = ffn or 4 * E
+    sd = {}
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    def gn(name, n):
+        sd[name + "weight"] = 1.0 + 0.1 * rn(n)
+        sd[name + "bias"] = 0.1 * rn(n)
+
+    nin = len(in_channels)
+    for i in range(num_levels):
+        cin = in_channels[nin - i - 1]
+        sd[f"input_convs.{i}.conv.weight"] = rn(E, cin, 1, 1, 1, std=cin ** -0.5)
+        sd[f"input_convs.{i}.conv.bias"] = 0.1 * rn(E)
+        gn(f"input_convs.{i}.gn.", E)
+    for l in range(num_layers):
+        p = f"encoder.layers.{l}."
+        n_off = num_heads * num_levels * num_points
+        sd[p + "attentions.0.sampling_offsets.weight"] = rn(3 * n_off, E, std=0.5 * E ** -0.5)
+        sd[p + "attentions.0.sampling_offsets.bias"] = rn(3 * n_off, std=1.0)
+        sd[p + "attentions.0.attention_weights.weight"] = rn(n_off, E, std=E ** -0.5)
+        sd[p + "attentions.0.attention_weights.bias"] = 0.1 * rn(n_off)
+        for nm in ("value_proj", "output_proj"):
+            sd[p + f"attentions.0.{nm}.weight"] = rn(E, E, std=E ** -0.5)
+            sd[p + f"attentions.0.{nm}.bias"] = 0.1 * rn(E)
+        sd[p + "ffns.0.layers.0.0.weight"] = rn(ffn, E, std=E ** -0.5)
+        sd[p + "ffns.0.layers.0.0.bias"] = 0.1 * rn(ffn)
+        sd[p + "ffns.0.layers.1.weight"] = rn(E, ffn, std=ffn ** -0.5)
+        sd[p + "ffns.0.layers.1.bias"] = 0.1 * rn(E)
+        gn(p + "norms.0.", E)
+        gn(p + "norms.1.", E)
+    sd["level_encoding.weight"] = rn(num_levels, E)
+    for i in range(nin - num_levels):
+        sd[f"lateral_convs.{i}.conv.weight"] = rn(E, in_channels[i], 1, 1, 1, std=in_channels[i] ** -0.5)
+        gn(f"lateral_convs.{i}.gn.", E)
+        sd[f"output_convs.{i}.conv.weight"] = rn(E, E, 3, 3, 3, std=(27 * E) ** -0.5)
+        gn(f"output_convs.{i}.gn.", E)
+    sd["mask_feature.weight"] = rn(E, E, 1, 1, 1, std=E ** -0.5)
+    sd["mask_feature.bias"] = 0.1 * rn(E)
+    return sd
+
+
+# the small neck configuration shared by validate_port.check_neck, gen_golden.gen_neck and the golden test
+NECK_CASE = dict(in_channels=[32, 64, 128, 256], strides=[2, 4, 8, 16], E=96, layers=2, heads=4, levels=3, points=4,
+                 ffn=192, sizes=[(16, 12, 8), (8, 6, 4), (4, 3, 2), (2, 2, 1)], wseed=21, xseed=23)
+
+
+def neck_inputs(case, B=1):
+    g = torch.Generator().manual_seed(case["xseed"])
+    return [torch.randn(B, c, *sz, generator=g) for c, sz in zip(case["in_channels"], case["sizes"])]
+
+
+# =============================================================================
 # deterministic synthetic weights: shared with bench.py / smoke through occformer_b200.synth (pure data
 # generators, no arithmetic of the path); re-exported here so tests keep one entry point
 # =============================================================================

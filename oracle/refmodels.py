@@ -106,3 +106,31 @@ def ref_lift_and_pool(vt, depth_digit, img_feat, geom, B, N):
     volume = volume.view(B, N, -1, vt.D, H, W)
     volume = volume.permute(0, 1, 3, 4, 5, 2)
     return vt.voxel_pooling(geom, volume), depth_prob
+
+
+def neck_cfg(in_channels, strides, E, num_layers, num_heads, num_levels, num_points, ffn):
+    return shim.to_cfg(dict(
+        in_channels=list(in_channels), strides=list(strides), feat_channels=E, out_channels=E, num_outs=3,
+        norm_cfg=dict(type="GN", num_groups=32), act_cfg=dict(type="ReLU"),
+        encoder=dict(
+            type="DetrTransformerEncoder", num_layers=num_layers,
+            transformerlayers=dict(
+                type="BaseTransformerLayer",
+                attn_cfgs=dict(type="MultiScaleDeformableAttention3D", embed_dims=E, num_heads=num_heads,
+                               num_levels=num_levels, num_points=num_points, im2col_step=64, dropout=0.0,
+                               batch_first=False, norm_cfg=None, init_cfg=None),
+                ffn_cfgs=dict(embed_dims=E), feedforward_channels=ffn, ffn_dropout=0.0,
+                operation_order=("self_attn", "norm", "ffn", "norm")),
+            init_cfg=None),
+        positional_encoding=dict(type="SinePositionalEncoding3D", num_feats=E // 3, normalize=True)))
+
+
+def build_neck(in_channels, strides, E, num_layers, num_heads, num_levels, num_points, ffn, sd):
+    """The reference MSDeformAttnPixelDecoder3D (P/occformer/necks/multiscale_deformattn_3d.py) with the port's weights."""
+    shim.install()
+    shim.load(OCC + "mask2former.positional_encodings.positional_encoding")  # registers SinePositionalEncoding3D
+    mod = shim.load(OCC + "necks.multiscale_deformattn_3d")
+    neck = mod.MSDeformAttnPixelDecoder3D(**neck_cfg(in_channels, strides, E, num_layers, num_heads, num_levels,
+                                                     num_points, ffn))
+    neck.load_state_dict(sd, strict=True)
+    return neck.eval()

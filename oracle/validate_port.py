@@ -84,6 +84,24 @@ def check_head(report, kitti=False):
             report("head simple_test output_points", rel(res["output_points"], res_ref["output_points"]), 2e-5)
 
 
+NECK_CASE, neck_inputs = port.NECK_CASE, port.neck_inputs
+
+
+def check_neck(report):
+    c = NECK_CASE
+    sd = port.make_neck_state(c["in_channels"], c["E"], c["layers"], c["heads"], c["levels"], c["points"], c["ffn"],
+                              seed=c["wseed"])
+    neck = refmodels.build_neck(c["in_channels"], c["strides"], c["E"], c["layers"], c["heads"], c["levels"],
+                                c["points"], c["ffn"], sd)
+    feats = neck_inputs(c, B=2)
+    with torch.no_grad():
+        ref = neck([f.clone() for f in feats])
+        out = port.ms_deform_pixel_decoder_3d(feats, sd, c["strides"], c["heads"], c["layers"], c["levels"], c["points"])
+    assert len(ref) == len(out)
+    for i, (a, b) in enumerate(zip(out, ref)):
+        report(f"MSDeformAttnPixelDecoder3D out[{i}] {tuple(a.shape)}", rel(a, b), 2e-5)
+
+
 def main():
     assert shim.reference_available(), "needs /root/reference"
     shim.install()
@@ -102,6 +120,7 @@ def main():
     check_encoder(report)
     check_head(report)
     check_head(report, kitti=True)
+    check_neck(report)
     if not all(worst):
         sys.exit(1)
     print("port == reference on all checks")

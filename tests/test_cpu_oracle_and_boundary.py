@@ -10,7 +10,7 @@ import torch
 
 from oracle import port
 from occformer_b200 import synth
-from util import GOLDEN, golden, rel_err
+from util import GOLDEN, assert_close, golden, rel_err
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -181,3 +181,20 @@ def test_qkv_head_major_permutation_matches_reference_split():
     ref = torch.nn.functional.linear(x, w, b).view(5, 3, heads, hd)        # [token, q|k|v, head, d]
     hm = torch.nn.functional.linear(x, w[perm], b[perm]).view(5, heads, 3, hd)  # [token, head, q|k|v, d]
     assert torch.equal(hm.permute(0, 2, 1, 3), ref)
+
+
+def test_neck_port_vs_reference_golden():
+    """MSDeformAttnPixelDecoder3D (the first "next" row): the oracle restatement reproduces the outputs
+    the reference module produced under the shim (tests/golden/neck_small.npz, oracle/gen_golden.py neck).  No CUDA
+    implementation of the neck exists yet; this pins its oracle for the next round."""
+    from oracle import port
+    from util import golden
+    c = port.NECK_CASE
+    sd = port.make_neck_state(c["in_channels"], c["E"], c["layers"], c["heads"], c["levels"], c["points"], c["ffn"],
+                              seed=c["wseed"])
+    feats = port.neck_inputs(c, B=1)
+    outs = port.ms_deform_pixel_decoder_3d(feats, sd, c["strides"], c["heads"], c["layers"], c["levels"], c["points"])
+    gold = golden("neck_small.npz")
+    assert len(outs) == 4
+    for i, o in enumerate(outs):
+        assert_close(o, torch.from_numpy(gold[f"out{i}"]), 2e-5, f"neck port out[{i}] vs reference golden")
