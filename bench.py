@@ -271,7 +271,7 @@ def time_kernel_family(pipe, dev, peak):
     B = pipe.batch
     X, Y, Z, C = 200, 200, 16, 128
     flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-    x = torch.randn(B, X, Y, Z, C, device=dev)
+    x = ops.to_split(torch.randn(B, X, Y, Z, C, device=dev))
     w2, ks = ops.repack_conv_weight(torch.randn(C, C, 3, 3, 3, device=dev) * 0.02)
     stats = torch.zeros(B, 32, 2, dtype=torch.float64, device=dev)
     ts = []

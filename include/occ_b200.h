@@ -11,6 +11,13 @@
  *     missing), >0 = cudaError_t of a failed runtime call / launch;
  *   - never allocate, never synchronise, never exit; all work is enqueued on `stream`;
  *   - the current device must already be set by the caller (torch does this).
+ *
+ * Numerics: every tensor-core contraction is an fp32 problem computed as three bf16 tensor-core passes on hi/lo split
+ * operands (a ~= hi + lo, hi = bf16(a), lo = bf16(a - hi); a*b ~= hi*hi' + lo*hi' + hi*lo', fp32 accumulate): ~1e-5
+ * relative error.  Operands of such contractions are exchanged in the "S32" split format: an fp32-container tensor
+ * (rows, C), C % 32 == 0, whose every aligned 32-column chunk (128 bytes) holds [32 bf16 hi | 32 bf16 lo] of its 32
+ * values (same bytes and row pitch as the fp32 tensor).  occ_split_rows / occ_unsplit_rows convert.  Arguments
+ * documented "S32" are in this format; everything else is plain fp32.
  */
 #ifndef OCC_B200_H_
 #define OCC_B200_H_
@@ -41,20 +48,22 @@ size_t occ_voxel_pool_workspace_bytes(int n_points, int B, int X, int Y, int Z);
 int occ_voxel_pool_workspace_layout(int n_points, int B, int X, int Y, int Z, size_t* off_counts,
                                     size_t* off_head, size_t* off_next, size_t* off_vox_id);
 /* get_geometry (ViewTransformerLSSBEVDepth.py:117-150): frustum (P = D*fH*fW, 3) + camera matrices -> geom
- * (B, N, P, 3) ego-frame points.  intrins (B,N,3,intrin_cols) with intrin_cols 3 or 4 (KITTI P2), bda (B,d,d), d 3|4. */
+ * (B, N, P, 3) ego-frame points.  intrins (B,N,intrin_rows,intrin_cols): 3x3 (nuScenes), 3x4 or 4x4 (KITTI P2,
+ * semantic_kitti_lss_dataset.py:62-64 builds a 4x4); bda (B,d,d), d 3|4. */
 int occ_lss_geometry(const float* frustum, int P, const float* rots, const float* trans, const float* intrins,
-                     int intrin_cols, const float* post_rots, const float* post_trans, const float* bda, int bda_dim,
-                     int B, int N, float* geom, occ_stream_t stream);
+                     int intrin_rows, int intrin_cols, const float* post_rots, const float* post_trans,
+                     const float* bda, int bda_dim, int B, int N, float* geom, occ_stream_t stream);
 /* depth softmax over D + NCHW->NHWC of the context features (ViewTransformerLSSVoxel.py:108-110):
  * depth_logits (BN, D, HW), img_feat (BN, C, HW) -> depth_prob (BN, D, HW), feat_cl (BN, HW, C) */
 int occ_lift_prologue(const float* depth_logits, const float* img_feat, float* depth_prob, float* feat_cl, int BN,
                       int D, int C, int HW, occ_stream_t stream);
 /* fused lift-splat: out[b,x,y,z,:] = sum_{p in voxel} depth_prob[p] * feat_cl[pixel(p), :]; geom (B*N*D*HW, 3);
- * dx/bx/nx = the view transformer's float parameters (ViewTransformerLSSBEVDepth.py:21-25,81-83). */
-int occ_lift_splat(const float* depth_prob, const float* feat_cl, const float* geom, float* out, int B, int N, int D,
-                   int HW, int C, float dx0, float dx1, float dx2, float bx0, float bx1, float bx2, float nx0,
-                   float nx1, float nx2, int X, int Y, int Z, void* workspace, size_t workspace_bytes,
-                   int counts_are_zero, occ_stream_t stream);
+ * dx/bx/nx = the view transformer's float parameters (ViewTransformerLSSBEVDepth.py:21-25,81-83).
+ * out_split (optional, C % 32 == 0): the same grid in S32 (operand of the encoder's first conv). */
+int occ_lift_splat(const float* depth_prob, const float* feat_cl, const float* geom, float* out, float* out_split,
+                   int B, int N, int D, int HW, int C, float dx0, float dx1, float dx2, float bx0, float bx1, float bx2,
+                   float nx0, float nx1, float nx2, int X, int Y, int Z, void* workspace, size_t workspace_bytes,
+                   occ_stream_t stream);
 /* voxel_pooling(geom, volume) with a materialised volume: feats (B*points_per_batch, C), geom (same rows, 3)
  * (ViewTransformerLSSVoxel.py:77-100) */
 int occ_voxel_pool_geom(const float* feats, const float* geom, float* out, int B, int points_per_batch, int C,
@@ -65,36 +74,47 @@ int occ_bev_pool(const float* feats, const long long* coords, float* out, int n,
                  void* workspace, size_t workspace_bytes, occ_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * TF32 tensor-core GEMM / implicit-GEMM convolution (tcgen05 + TMA), fused epilogues.
+ * fp32-faithful tensor-core GEMM / implicit-GEMM convolution (tcgen05 bf16 x 3 passes + TMA), fused epilogues.
  * Replaces the cuBLAS / cuDNN calls issued by nn.Linear / nn.Conv3d / nn.Conv2d inside
  *   DualpathTransformerBlock  P/occformer/backbones/dualpath_block.py:36-48,79
  *   SwinBlock / WindowMSA     P/occformer/backbones/modules/window_attention.py:65-67,336-344
  *   BottleNeckASPP / ASPP     P/occformer/backbones/modules/aspp.py:49-172
+ *   MSDeformAttnPixelDecoder3D  P/occformer/necks/multiscale_deformattn_3d.py:60-141 (input/lateral/output convs, Linears)
  *   Mask2Former*OccHead       P/occformer/mask2former/mask2former_nusc_occ.py:446-457 (mask einsum), decoder K/V proj
- * out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); act: 0 none, 1 ReLU, 2 GELU(erf); round_out: round to tf32.
+ * out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ residual); A, W in S32 (K % 32 == 0); act: 0 none, 1 ReLU, 2 GELU(erf);
+ * split_out: write out in S32 (N % 32 == 0) instead of fp32; bias / residual fp32.
  * gn_stats (optional): fp64 (sum, sumsq) per (batch, group) of the raw accumulator, cpg = channels per group. */
-int occ_gemm_tf32(const float* A, const float* W, float* out, int M, int N, int K, const float* bias,
-                  const float* residual, int act, int round_out, double* gn_stats, int cpg, int rows_per_batch,
-                  occ_stream_t stream);
-/* x (B,X,Y,Z,Cin) channel-last, w2 (Cout, KX*KY*KZ*Cin) tap-major, out (B,Xo,Yo,Zo,Cout); K in {1,3}, stride in
- * {1,2}, "same" padding dil*(K-1)/2.  2-D convs: Z = KZ = 1. */
-int occ_conv_tf32(const float* x, const float* w2, float* out, int B, int X, int Y, int Z, int Cin, int Cout, int KX,
-                  int KY, int KZ, int stride, int dil, const float* bias, const float* residual, int act,
-                  int round_out, double* gn_stats, int cpg, occ_stream_t stream);
+int occ_gemm_bf16x3(const float* A, const float* W, float* out, int M, int N, int K, const float* bias,
+                    const float* residual, int act, int split_out, double* gn_stats, int cpg, int rows_per_batch,
+                    occ_stream_t stream);
+/* x (B,X,Y,Z,Cin) channel-last S32, w2 (Cout, KX*KY*KZ*Cin) tap-major S32, out (B,Xo,Yo,Zo,Cout); K in {1,3}, stride in
+ * {1,2}, "same" padding dil*(K-1)/2.  2-D convs: Z = KZ = 1.  workspace (optional): occ_conv_workspace_bytes() bytes,
+ * zero before its first use, one per stream -- the split-K ordering counters of the deep stages (without it the conv
+ * runs single-pass). */
+size_t occ_conv_workspace_bytes(void);
+int occ_conv_bf16x3(const float* x, const float* w2, float* out, int B, int X, int Y, int Z, int Cin, int Cout, int KX,
+                    int KY, int KZ, int stride, int dil, const float* bias, const float* residual, int act,
+                    int split_out, double* gn_stats, int cpg, void* workspace, size_t workspace_bytes,
+                    occ_stream_t stream);
+/* fp32 rows (rows, C) <-> S32 (C % 32 == 0) */
+int occ_split_rows(const float* in, float* out, long long rows, int C, occ_stream_t stream);
+int occ_unsplit_rows(const float* in, float* out, long long rows, int C, occ_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Dual-path encoder block glue (P/occformer/backbones/dualpath_block.py:65-82).
  * Token rows: voxel tokens ((b*X+x)*Y+y)*Z+z, then BEV tokens B*X*Y*Z + (b*X+x)*Y+y. */
-/* GroupNorm+ReLU of the raw conv output, Z-mean, LayerNorm1 (dualpath_block.py:43-48,69; window_attention.py:355) */
+/* GroupNorm+ReLU of the raw conv output, Z-mean, LayerNorm1 (dualpath_block.py:43-48,69; window_attention.py:355):
+ * tok fp32 (residual), tokn S32 (operand of the QKV GEMM) */
 int occ_gn_relu_zmean_ln(const float* y, const double* stats, const float* gn_w, const float* gn_b,
                          const float* ln_w, const float* ln_b, float* tok, float* tokn, int B, int XY, int Z, int C,
                          int groups, occ_stream_t stream);
-int occ_layernorm(const float* in, const float* w, const float* b, float* out, long long rows, int C, int round_out,
+int occ_layernorm(const float* in, const float* w, const float* b, float* out, long long rows, int C, int split_out,
                   occ_stream_t stream);
-/* out[row, out_off + c] = act(gn(in[row, c])) (+ residual[row, c]) -- ASPP norms (aspp.py:42-46,117-120,166-172) */
+/* o = act(gn(in[row, c])) (+ residual[row, c]) -- ASPP / neck norms (aspp.py:42-46,117-120,166-172): out[row, c] = o
+ * (fp32, optional) and / or out_split[row, out_off + c] = o in S32 with row pitch ldo (optional) */
 int occ_gn_apply(const float* in, const double* stats, const float* w, const float* b, const float* residual,
-                 float* out, long long rows, int rows_per_batch, int C, int groups, int ldo, int out_off, int relu,
-                 int round_out, occ_stream_t stream);
+                 float* out, float* out_split, long long rows, int rows_per_batch, int C, int groups, int ldo,
+                 int out_off, int relu, occ_stream_t stream);
 /* ASPP image-pooling branch: GAP -> 1x1 conv -> GN -> ReLU -> broadcast (aspp.py:89-95,113-114).
  * sums_ws: workspace of B*ch doubles followed by B*ch floats. */
 int occ_aspp_gap_branch(const float* in, double* sums_ws, const float* wconv, const float* gw, const float* gb,
@@ -103,12 +123,13 @@ int occ_aspp_gap_branch(const float* in, double* sums_ws, const float* wconv, co
 /* coeff = sigmoid(<x,w>+b); out = x + coeff * bev + identity (identity optionally GroupNorm'd: strided skip path)
  * dualpath_block.py:36-41,79-82 */
 int occ_dualpath_fuse(const float* x, const float* bev, const float* cw, float cbias, const float* identity,
-                      const double* id_stats, const float* id_w, const float* id_b, int groups, float* out, int B,
-                      int XY, int Z, int C, occ_stream_t stream);
+                      int identity_split /*identity is S32*/, const double* id_stats, const float* id_w,
+                      const float* id_b, int groups, float* out /*fp32, optional*/, float* out_split /*S32, optional*/,
+                      int B, int XY, int Z, int C, occ_stream_t stream);
 /* Swin block tail for C == 128 in one tensor-core kernel (csrc/swin_mlp_fused.cu): y1 = tok + att Wp^T + bp (WindowMSA.proj
  * + the ShiftWindowMSA residual, window_attention.py:105-107 / swin.py SwinBlock.forward), out = y1 + W2 GELU(W1 LN2(y1)
- * + b1) + b2 (norm2 + FFN + residual).  Weights (out, in) row-major, tf32-rounded.  Returns -2 for C != 128 (the caller
- * then uses occ_gemm_tf32 / occ_layernorm). */
+ * + b1) + b2 (norm2 + FFN + residual).  att and the weights ((out, in) row-major) in S32; tok / out fp32.  Returns -2 for
+ * C != 128 (the caller then uses occ_gemm_bf16x3 / occ_layernorm). */
 int occ_swin_proj_ffn(const float* att, const float* tok, const float* wp, const float* bp, const float* ln_w,
                       const float* ln_b, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
                       long long M, int C, occ_stream_t stream);
@@ -117,27 +138,24 @@ int occ_swin_proj_ffn(const float* att, const float* tok, const float* wp, const
  * bias_pad = relative_position_bias_table[relative_position_index] as (heads, 49*49 padded to 2404 floats).
  * qkv_head_major = 0: qkv / qkv_bias columns in the reference order [q|k|v][head][32] (WindowMSA.qkv);  1: [head][q|k|v][32]
  * (the caller permuted the rows of the qkv weight: one contiguous 384-byte run per (token, head)). */
-int occ_window_attention(const float* qkv, const float* qkv_bias, const float* bias_pad, float* out, int B, int X,
-                         int Y, int Z, int C, int heads, int shift, int qkv_head_major, occ_stream_t stream);
-/* development aid: unit 0 of CTA 0 dumps raw scores / probabilities / output rows into dbg (128,192); NULL = off */
-int occ_window_attention_set_debug(float* dbg);
-/* development probe of tcgen05 operand conventions: D[128x32] = A[128x64] V[64x32], mode 0..3 (csrc/umma_probe.cu) */
-int occ_debug_umma_probe(const float* A, const float* V, float* D, int mode, occ_stream_t stream);
+int occ_window_attention(const float* qkv /*S32*/, const float* qkv_bias /*S32 row*/, const float* bias_pad,
+                         float* out /*S32*/, int B, int X, int Y, int Z, int C, int heads, int shift,
+                         int qkv_head_major, occ_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Mask2Former-3D occupancy decoder head (P/occformer/mask2former/mask2former_nusc_occ.py, mask2former_occ.py).
  * Layouts: voxel memories channel-last (B, S, E); queries (B, Q, E); mask logits "query-last" (B, S, Q).
  * The voxel-side GEMMs (K/V projections :657-667 via nn.MultiheadAttention in_proj; mask einsum :457) go through
- * occ_gemm_tf32; the entry points below are the fused query-side / reduction kernels. */
+ * occ_gemm_bf16x3; the entry points below are the fused query-side / reduction kernels. */
 /* SinePositionalEncoding3D.forward, normalize=True, all-False mask (positional_encoding.py:58-108): out (X*Y*Z, 3F) */
 int occ_sine_pos3d(float* out, int X, int Y, int Z, int num_feats, float temperature, float scale, float eps,
                    float offset, occ_stream_t stream);
-/* level prep (mask2former_nusc_occ.py:614-630): mem = tf32(in + level_embed), kpos = tf32(in + level_embed + pos);
+/* level prep (mask2former_nusc_occ.py:614-630): mem = in + level_embed, kpos = in + level_embed + pos, both S32;
  * in is channel-last (B,S,C) or the reference layout (B,C,S); level_embed / pos+kpos optional. */
 int occ_head_prep(const float* in, int in_channel_last, const float* level_embed, const float* pos, float* mem,
                   float* kpos, int B, long long S, int C, occ_stream_t stream);
 /* forward_head query side (:446-455): [optional: query = LN(norms.2)(query_in) -> query_state] -> post_norm LN ->
- * cls_embed -> cls_out (rows, NC); mask_embed MLP -> membed_out (rows, E) tf32-rounded; [optional: the NEXT layer's
+ * cls_embed -> cls_out (rows, NC); mask_embed MLP -> membed_out (rows, E) S32; [optional: the NEXT layer's
  * cross-attention query projection qh_out = ((query + query_pos) Wq^T + bq) * scale].  Weights K-major (in, out). */
 int occ_query_head(const float* query_in, const float* n2w, const float* n2b, float* query_state, const float* pn_w,
                    const float* pn_b, const float* clsT, const float* cls_b, int NC, const float* m0T, const float* m0b,
@@ -152,17 +170,12 @@ int occ_mask_pool(const float* mask, int* pooled, int* row_flag, int B, int X, i
 /* mask einsum with fused attention-mask pooling (:457-466) when the pooling windows are powers of two >= 2 dividing the
  * grid: mask[b,v,q] = <mf[b,v,:], membed[b,q,:]> (written only if mask_out != NULL), pooled[b,cell,q] = window max as an
  * order-preserving int (i >= 0 ? i : i ^ 0x7FFFFFFF of the float bits; blocked <=> value < 0), flag[b,q] as occ_mask_pool */
-int occ_mask_gemm_pool(const float* mf, const float* membed, float* mask_out, int* pooled, int* flag, int B, int X, int Y,
-                       int Z, int E, int Q, int Xo, int Yo, int Zo, occ_stream_t stream);
-/* key-chunking of the masked cross attention for S keys */
-int occ_cross_attn_chunks(int S, int* chunk, int* nchunk);
-/* masked cross attention partials per key chunk (mmcv MultiheadAttention -> nn.MultiheadAttention, bool attn_mask):
- * part (B, H, nchunk, Q, 34) = running max, running sum, 32 value accumulators */
-int occ_cross_attn_partial(const float* qh, const float* Kp, const float* Vp, int ld, int koff, int voff,
-                           const int* pooled, const int* row_flag, float* part, int B, int S, int Q, int E, int H,
-                           int chunk, int nchunk, occ_stream_t stream);
-/* the same masked cross attention on the tcgen05 tensor cores (128-key tiles, TMA operand loads, P in TMEM);
- * writes occ_cross_attn_tc_partials(S) partials per (sample, head): part (B, H, npart, Q, 34) */
+int occ_mask_gemm_pool(const float* mf /*S32*/, const float* membed /*S32*/, float* mask_out, int* pooled, int* flag,
+                       int B, int X, int Y, int Z, int E, int Q, int Xo, int Yo, int Zo, occ_stream_t stream);
+/* masked cross attention (mmcv MultiheadAttention -> nn.MultiheadAttention, bool attn_mask) on the tcgen05 tensor cores
+ * (128-key tiles, TMA operand loads, P in TMEM); qh fp32, Kp / Vp S32 (one chunk per (key, head)); writes
+ * occ_cross_attn_tc_partials(S) partials per (sample, head): part (B, H, npart, Q, 34) = running max, running sum, 32
+ * value accumulators */
 int occ_cross_attn_tc_partials(int S);
 /* pooled (B,S,Q) ordered-int mask logits -> bits (B, 4*ceil(S/128), Q): one "blocked" bit per (key, query) */
 int occ_mask_bits(const int* pooled, unsigned* bits, int B, int S, int Q, occ_stream_t stream);

@@ -3,7 +3,7 @@
 Registry names / constructor kwargs / forward signatures / state_dict keys follow
 projects/mmdet3d_plugin of the reference; all arithmetic runs in csrc/libocc_b200.so (C ABI, ctypes).
 """
-from .registry import BACKBONES, HEADS, NECKS  # noqa: F401
+from .registry import ATTENTION, BACKBONES, HEADS, NECKS, POSITIONAL_ENCODING  # noqa: F401
 from .encoder import DualpathTransformerBlock, OccupancyEncoder  # noqa: F401
 from .view_transformer import ViewTransformerLiftSplatShootVoxel, bev_pool  # noqa: F401
 from .head import (Mask2FormerNuscOccHead, Mask2FormerNuscPanopticOccHead, Mask2FormerOccHead,  # noqa: F401

@@ -17,31 +17,30 @@ SIGNATURES = {
     "occ_version": (c_int, []),
     "occ_voxel_pool_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "occ_voxel_pool_workspace_layout": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
-    "occ_lss_geometry": (c_int, [P, c_int, P, P, P, c_int, P, P, P, c_int, c_int, c_int, P, STREAM]),
+    "occ_lss_geometry": (c_int, [P, c_int, P, P, P, c_int, c_int, P, P, P, c_int, c_int, c_int, P, STREAM]),
     "occ_lift_prologue": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, STREAM]),
-    "occ_lift_splat": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int] + [c_float] * 9 +
-                       [c_int, c_int, c_int, P, c_size_t, c_int, STREAM]),
+    "occ_lift_splat": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int] + [c_float] * 9 +
+                       [c_int, c_int, c_int, P, c_size_t, STREAM]),
     "occ_voxel_pool_geom": (c_int, [P, P, P, c_int, c_int, c_int] + [c_float] * 9 + [c_int, c_int, c_int, P, c_size_t, STREAM]),
     "occ_bev_pool": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_size_t, STREAM]),
-    "occ_gemm_tf32": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int, c_int, STREAM]),
-    "occ_conv_tf32": (c_int, [P, P, P] + [c_int] * 11 + [P, P, c_int, c_int, P, c_int, STREAM]),
+    "occ_gemm_bf16x3": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int, c_int, STREAM]),
+    "occ_conv_workspace_bytes": (c_size_t, []),
+    "occ_conv_bf16x3": (c_int, [P, P, P] + [c_int] * 11 + [P, P, c_int, c_int, P, c_int, P, c_size_t, STREAM]),
+    "occ_split_rows": (c_int, [P, P, c_longlong, c_int, STREAM]),
+    "occ_unsplit_rows": (c_int, [P, P, c_longlong, c_int, STREAM]),
     "occ_gn_relu_zmean_ln": (c_int, [P] * 8 + [c_int] * 5 + [STREAM]),
     "occ_layernorm": (c_int, [P, P, P, P, c_longlong, c_int, c_int, STREAM]),
-    "occ_gn_apply": (c_int, [P] * 6 + [c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_int, STREAM]),
+    "occ_gn_apply": (c_int, [P] * 7 + [c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, STREAM]),
     "occ_aspp_gap_branch": (c_int, [P] * 6 + [c_int] * 6 + [STREAM]),
-    "occ_dualpath_fuse": (c_int, [P, P, P, c_float, P, P, P, P, c_int, P, c_int, c_int, c_int, c_int, STREAM]),
+    "occ_dualpath_fuse": (c_int, [P, P, P, c_float, P, c_int, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, STREAM]),
     "occ_swin_proj_ffn": (c_int, [P] * 11 + [c_longlong, c_int, STREAM]),
     "occ_window_attention": (c_int, [P, P, P, P] + [c_int] * 8 + [STREAM]),
-    "occ_window_attention_set_debug": (c_int, [P]),
-    "occ_debug_umma_probe": (c_int, [P, P, P, c_int, STREAM]),
     "occ_sine_pos3d": (c_int, [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, STREAM]),
     "occ_head_prep": (c_int, [P, c_int, P, P, P, P, c_int, c_longlong, c_int, STREAM]),
     "occ_query_head": (c_int, [P, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P, P, c_float, P, c_int, c_int,
                                 STREAM]),
     "occ_mask_pool": (c_int, [P, P, P] + [c_int] * 8 + [STREAM]),
     "occ_mask_gemm_pool": (c_int, [P, P, P, P, P] + [c_int] * 9 + [STREAM]),
-    "occ_cross_attn_chunks": (c_int, [c_int, P, P]),
-    "occ_cross_attn_partial": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P] + [c_int] * 7 + [STREAM]),
     "occ_cross_attn_tc_partials": (c_int, [c_int]),
     "occ_mask_bits": (c_int, [P, P, c_int, c_int, c_int, STREAM]),
     "occ_cross_attn_tc": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P] + [c_int] * 5 + [STREAM]),

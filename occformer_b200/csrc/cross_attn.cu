@@ -5,9 +5,12 @@
 // :657-667 with attn_mask = (adaptive_max_pool3d(mask_pred) .sigmoid() < 0.5) and the all-blocked-row reset (:652-653).
 //
 // One CTA = (key chunk, head, sample); M = 128 query rows (Q <= 128 real), N = 128 keys per tile, head dim 32.
-//   warp 0   : TMA producer -- K tile (K-major, SWIZZLE_128B) and V tile (MN-major operand, SWIZZLE_128B_ATOM_32B) are
-//              plain 2-D boxes of the projected key / value matrices
-//   warp 1   : MMA issuer   -- S = Q K^T (4 x 128x128x8, Q staged once per CTA), O_tile = P V (16 x 128x32x8, P in TMEM)
+// Split-bf16 operands, three tensor-core passes per contraction (occ_ptx.cuh): Kp / Vp arrive in S32 (one 128-byte chunk
+// per (key, head)), the Q tile is split while it is staged, P is split by the softmax threads.
+//   warp 0   : TMA producer -- K tile (K-major, SWIZZLE_128B) and V tile (MN-major operand, N = 64 = hi | lo of the head
+//              dim, SWIZZLE_128B) are plain 2-D boxes of the projected key / value matrices
+//   warp 1   : MMA issuer   -- S = Q K^T (6 x 128x128x16, Q staged once per CTA), O' = [P_hi; P_lo] [V_hi | V_lo]
+//              (16 x 128x64x16, P in TMEM); O = O'[:, :32] + O'[:, 32:] when the tile is merged
 //   (mask)   : a small pre-pass (mask_bits_kernel) turns the pooled mask logits (ordered ints, blocked <=> negative)
 //              into one "blocked" bit per (key, query), 32 keys per word, once per layer instead of once per head; the
 //              softmax threads read their 4 words per tile straight from global (L2-resident, 1 MB at S = 80 000)
@@ -68,15 +71,20 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_ptr);
-  // Q tile of this (sample, head): 128 rows x 32 floats, tf32-rounded, K-major SWIZZLE_128B; rows >= Q are zero
+  // Q tile of this (sample, head): 128 rows x one S32 chunk (32 head-dim values split into hi | lo), K-major
+  // SWIZZLE_128B; rows >= Q are zero.  Thread (r, ch) converts 4 values: hi pair words -> 16-byte chunk ch >> 1 (half
+  // ch & 1), lo pair words -> chunk 4 + (ch >> 1).
   for (int i = threadIdx.x; i < 128 * 8; i += XT_THREADS) {
     const int r = i >> 3, ch = i & 7;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
     if (r < Q) {
-      v = *reinterpret_cast<const float4*>(qh + ((size_t)b * Q + r) * E + h * XT_HD + ch * 4);
-      v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+      const float4 v = *reinterpret_cast<const float4*>(qh + ((size_t)b * Q + r) * E + h * XT_HD + ch * 4);
+      split_pair(v.x, v.y, hi.x, lo.x);
+      split_pair(v.z, v.w, hi.y, lo.y);
     }
-    *reinterpret_cast<float4*>(sq + r * 128 + ((ch ^ (r & 7)) << 4)) = v;
+    uint8_t* row = sq + r * 128;
+    *reinterpret_cast<uint2*>(row + ((((ch >> 1)) ^ (r & 7)) << 4) + ((ch & 1) << 3)) = hi;
+    *reinterpret_cast<uint2*>(row + (((4 + (ch >> 1)) ^ (r & 7)) << 4) + ((ch & 1) << 3)) = lo;
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -100,8 +108,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t IDESC_QK = make_idesc_tf32(128, XT_KEYS, 0, 0);
-      constexpr uint32_t IDESC_PV = make_idesc_tf32(128, XT_HD, 0, 1);
+      constexpr uint32_t IDESC_QK = make_idesc_bf16(128, XT_KEYS, 0, 0);
+      constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 2 * XT_HD, 0, 1);
       const uint64_t qdesc = make_sw128_desc(smem_u32(sq), 1024, 16);
       int nq = 0, np = 0;
       while (np < n_tiles) {
@@ -109,8 +117,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
           tc_fence_after();
           const uint64_t kdesc = make_sw128_desc(smem_u32(smem + (size_t)(nq % XT_STAGES) * XT_STAGE_BYTES), 1024, 16);
           const uint32_t s_tmem = tmem_base + (nq & 1) * 128;
-#pragma unroll
-          for (int kk = 0; kk < XT_HD / 8; ++kk) mma_tf32_ss(s_tmem, qdesc + 2 * kk, kdesc + 2 * kk, IDESC_QK, kk != 0);
+          mma_bf16x3_ss(s_tmem, qdesc, kdesc, IDESC_QK, 0u);
           mma_commit(&s_ready[nq & 1]);
           ++nq;
         }
@@ -120,10 +127,14 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
           if (mbar_test(&p_ready[tb], k & 1) && mbar_test(&o_free[tb], (k & 1) ^ 1)) {
             tc_fence_after();
             const int s = np % XT_STAGES;
-            const uint64_t vdesc = make_sw128b32_mn_desc(smem_u32(smem + (size_t)s * XT_STAGE_BYTES + XT_TILE), 512, 512);
-            const uint32_t p_tmem = tmem_base + tb * 128, o_tmem = tmem_base + 256 + tb * XT_HD;
+            const uint64_t vdesc = make_sw128_desc(smem_u32(smem + (size_t)s * XT_STAGE_BYTES + XT_TILE), 1024, 1024);
+            const uint32_t p_tmem = tmem_base + tb * 128, o_tmem = tmem_base + 256 + tb * 2 * XT_HD;
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) mma_tf32_ts(o_tmem, p_tmem + kk * 8, vdesc + (uint64_t)(kk * 64), IDESC_PV, kk != 0);
+            for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA = two 8-key (1024 B) atoms of V rows
+              const uint32_t pc = p_tmem + (kk >> 1) * 32 + (kk & 1) * 8;
+              mma_bf16_ts(o_tmem, pc, vdesc + (uint64_t)(kk * 128), IDESC_PV, kk != 0);  // P_hi [V_hi | V_lo]
+              mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);  // P_lo [V_hi | V_lo]
+            }
             mma_commit(&o_ready[tb]);
             mma_commit(&empty_bar[s]);
             ++np;
@@ -172,17 +183,25 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       }
       const float ml2 = m * L2E;
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {  // pass B: P = exp(s - m), row sum, P -> TMEM (in place of S)
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {  // pass B: P = exp(s - m), row sum, P -> TMEM (in place of S), split into hi | lo
         tmem_ld_32x32(s_col + cc * 32, r);
         tmem_ld_wait();
+        const uint32_t bw = cc == 0 ? blk[0] : cc == 1 ? blk[1] : cc == 2 ? blk[2] : blk[3];
+        uint32_t lo16[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float p = 0.f;
-          if (!((blk[cc] >> j) & 1u)) p = round_tf32(ex2_approx(fmaf(__uint_as_float(r[j]), L2E, -ml2)));
-          l4[j & 3] += p;
-          r[j] = __float_as_uint(p);
+        for (int j = 0; j < 16; ++j) {  // keys 2j, 2j+1 -> packed hi word j (in place: r[j] was consumed by pair j/2) + lo word
+          float p0 = 0.f, p1 = 0.f;
+          if (!((bw >> (2 * j)) & 1u)) p0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), L2E, -ml2));
+          if (!((bw >> (2 * j + 1)) & 1u)) p1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), L2E, -ml2));
+          l4[j & 3] += p0 + p1;
+          uint32_t hi, lo;
+          split_pair(p0, p1, hi, lo);
+          r[j] = hi;
+          lo16[j] = lo;
         }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[16 + j] = lo16[j];
         tmem_st_32x32(s_col + cc * 32, r);
       }
       const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
@@ -192,17 +211,26 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       if (lane == 0) mbar_arrive(&p_ready[tb]);
       mbar_wait(&o_ready[tb], k & 1);
       tc_fence_after();
-      tmem_ld_32x32(lane_base + 256 + tb * XT_HD, r);
+      // merge the tile into the running softmax state of this row: O = O'[:, :32] + O'[:, 32:] (the V_hi and V_lo halves),
+      // one half at a time so that only 32 accumulator words are live next to acc[]
+      const bool upd = m > -INFINITY;
+      const float Mn = fmaxf(M, m);
+      const float a = upd ? ex2_approx((M - Mn) * L2E) : 1.f, bsc = upd ? ex2_approx((m - Mn) * L2E) : 0.f;
+      tmem_ld_32x32(lane_base + 256 + tb * 2 * XT_HD, r);  // P [V_hi]
+      tmem_ld_wait();
+      if (upd) {
+#pragma unroll
+        for (int d = 0; d < XT_HD; ++d) acc[d] = acc[d] * a + __uint_as_float(r[d]) * bsc;
+      }
+      tmem_ld_32x32(lane_base + 256 + tb * 2 * XT_HD + XT_HD, r);  // P [V_lo]
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[tb]);
-      if (m > -INFINITY) {  // merge the tile into the running softmax state of this row
-        const float Mn = fmaxf(M, m);
-        const float a = ex2_approx((M - Mn) * L2E), bsc = ex2_approx((m - Mn) * L2E);
-        L = L * a + l * bsc;
+      if (upd) {
 #pragma unroll
-        for (int d = 0; d < XT_HD; ++d) acc[d] = acc[d] * a + __uint_as_float(r[d]) * bsc;
+        for (int d = 0; d < XT_HD; ++d) acc[d] = fmaf(__uint_as_float(r[d]), bsc, acc[d]);
+        L = L * a + l * bsc;
         M = Mn;
       }
     }
@@ -260,7 +288,7 @@ extern "C" int occ_cross_attn_tc_partials(int S) {
   return 2 * ((tiles + tpc - 1) / tpc);
 }
 
-// qh (B,Q,E) scaled projected queries; Kp / Vp (B*S, ld) projected keys / values (tf32-rounded), this layer's slice at
+// qh (B,Q,E) scaled projected queries (fp32); Kp / Vp (B*S, ld) projected keys / values in S32, this layer's slice at
 // column koff / voff; bits (B, NW = 4*ceil(S/128), Q) blocked-key words from occ_mask_bits; row_flag (B*Q);
 // part (B, H, npart, Q, 34).
 extern "C" int occ_cross_attn_tc(const float* qh, const float* Kp, const float* Vp, int ld, int koff, int voff,
@@ -280,14 +308,10 @@ extern "C" int occ_cross_attn_tc(const float* qh, const float* Kp, const float* 
   uint32_t box[2] = {(uint32_t)XT_HD, (uint32_t)XT_KEYS};
   int rc = make_tmap_f32(&tmK, Kp, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = make_tmap_f32(&tmV, Vp, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  rc = make_tmap_f32(&tmV, Vp, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const size_t smem = (size_t)XT_STAGES * XT_STAGE_BYTES + XT_TILE + 1024 /*align*/ + 256 /*barriers*/;
-  static bool configured = false;
-  if (!configured) {
-    OCC_CUDA(cudaFuncSetAttribute(cross_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  OCC_ENSURE_SMEM(cross_attn_tc_kernel, smem);
   dim3 grid(nchunk, H, B);
   cross_attn_tc_kernel<<<grid, XT_THREADS, smem, stream>>>(tmK, tmV, qh, koff, voff, bits, row_flag, part, S, Q, E, H, tpc,
                                                            nchunk);

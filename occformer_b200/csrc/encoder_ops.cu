@@ -34,7 +34,7 @@ __device__ __forceinline__ void gn_mean_rstd(const double* __restrict__ stats, i
 // LayerNorm of a row held as NV float4 per lane (C = 128*NV).  two-pass in registers.
 template <int NV>
 __device__ __forceinline__ void warp_layernorm(float4 (&v)[NV], int C, const float* __restrict__ gamma,
-                                               const float* __restrict__ beta, int lane, bool round) {
+                                               const float* __restrict__ beta, int lane) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
@@ -55,10 +55,6 @@ __device__ __forceinline__ void warp_layernorm(float4 (&v)[NV], int C, const flo
     v[i].y = (v[i].y - mean) * rstd * g.y + bb.y;
     v[i].z = (v[i].z - mean) * rstd * g.z + bb.z;
     v[i].w = (v[i].w - mean) * rstd * g.w + bb.w;
-    if (round) {
-      v[i].x = round_tf32(v[i].x); v[i].y = round_tf32(v[i].y);
-      v[i].z = round_tf32(v[i].z); v[i].w = round_tf32(v[i].w);
-    }
   }
 }
 
@@ -66,7 +62,7 @@ __device__ __forceinline__ void warp_layernorm(float4 (&v)[NV], int C, const flo
 // input_conv tail: GroupNorm + ReLU of the raw conv output, Z-mean (BEV token), LayerNorm1 of both.
 //   y     : (B*X*Y*Z, C) raw Conv3d output                     (dualpath_block.py:43-48)
 //   tok   : (B*X*Y*(Z+1), C) <- relu(gn(y)) and its mean over Z (dualpath_block.py:69)
-//   tokn  : same rows, LayerNorm1'd and rounded to tf32 (operand of the QKV GEMM; window_attention.py:355)
+//   tokn  : same rows, LayerNorm1'd, S32 split format (A operand of the QKV GEMM; window_attention.py:355)
 // One CTA handles `cols` (b,x,y) columns, one warp per voxel row; the CTA's smem holds the column for the mean.
 // R voxel rows (consecutive z of one column) per warp: all R row loads are issued before any of them is consumed, so a
 // warp keeps R x 512 B (C = 128) in flight -- with one row per warp the kernel sat at 2.4 TB/s on latency alone.
@@ -121,10 +117,9 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      warp_layernorm<NV>(v[r], C, ln_w, ln_b, lane, true);
+      warp_layernorm<NV>(v[r], C, ln_w, ln_b, lane);
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        *reinterpret_cast<float4*>(tokn + (row0 + r) * C + (i * 32 + lane) * 4) = v[r][i];
+      for (int i = 0; i < NV; ++i) store_split4(tokn + (row0 + r) * C, (i * 32 + lane) * 4, v[r][i]);
     }
   }
   __syncthreads();
@@ -143,10 +138,9 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
       v[0][i] = a;
       *reinterpret_cast<float4*>(tok + brow * C + c0) = a;
     }
-    warp_layernorm<NV>(v[0], C, ln_w, ln_b, lane, true);
+    warp_layernorm<NV>(v[0], C, ln_w, ln_b, lane);
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      *reinterpret_cast<float4*>(tokn + brow * C + (i * 32 + lane) * 4) = v[0][i];
+    for (int i = 0; i < NV; ++i) store_split4(tokn + brow * C, (i * 32 + lane) * 4, v[0][i]);
   }
 }
 
@@ -155,22 +149,25 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
 template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ b,
-                 float* __restrict__ out, long long rows, int C, int round) {
+                 float* __restrict__ out, long long rows, int C, int split) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   float4 v[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(in + row * C + (i * 32 + lane) * 4);
-  warp_layernorm<NV>(v, C, w, b, lane, round != 0);
+  warp_layernorm<NV>(v, C, w, b, lane);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(out + row * C + (i * 32 + lane) * 4) = v[i];
+  for (int i = 0; i < NV; ++i) {
+    if (split) store_split4(out + row * C, (i * 32 + lane) * 4, v[i]);
+    else *reinterpret_cast<float4*>(out + row * C + (i * 32 + lane) * 4) = v[i];
+  }
 }
 
 // generic-width LayerNorm (C not a multiple of 128): one warp per row, scalar loop
 __global__ void __launch_bounds__(256)
 layernorm_generic_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ b,
-                         float* __restrict__ out, long long rows, int C, int round) {
+                         float* __restrict__ out, long long rows, int C, int split) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -181,19 +178,32 @@ layernorm_generic_kernel(const float* __restrict__ in, const float* __restrict__
   float q = 0.f;
   for (int c = lane; c < C; c += 32) { const float d = src[c] - mean; q += d * d; }
   const float rstd = rsqrtf(warp_sum(q) / (float)C + kEps);
-  for (int c = lane; c < C; c += 32) {
-    float o = (src[c] - mean) * rstd * w[c] + b[c];
-    out[row * C + c] = round ? round_tf32(o) : o;
+  for (int c = lane; c < C; c += 32) {  // split: C % 32 == 0, lanes (2t, 2t+1) form packed word t of the chunk
+    const float o = (src[c] - mean) * rstd * w[c] + b[c];
+    if (split) {
+      const float o2 = __shfl_xor_sync(0xffffffffu, o, 1);
+      if (!(lane & 1)) {
+        uint32_t hi, lo;
+        split_pair(o, o2, hi, lo);
+        uint32_t* chunk = reinterpret_cast<uint32_t*>(out + row * C + (c & ~31));
+        chunk[lane >> 1] = hi;
+        chunk[16 + (lane >> 1)] = lo;
+      }
+    } else {
+      out[row * C + c] = o;
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // GroupNorm apply for the small 2-D maps of BottleNeckASPP (aspp.py:49-172) and the strided skip path:
-//   out[row, out_off + c] = act(gn(in[row, c])) (+ residual[row, c]);  rows = B * rows_per_batch.
+//   o = act(gn(in[row, c])) (+ residual[row, c]);  out[row, c] = o (fp32, optional) and / or
+//   out_split[row, out_off + c] = o in the S32 split format (row pitch ldo; operand of the next conv);  rows = B * rows_per_batch.
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ in, const double* __restrict__ stats, const float* __restrict__ w,
                 const float* __restrict__ b, const float* __restrict__ residual, float* __restrict__ out,
-                long long rows, int rows_per_batch, int C, int groups, int ldo, int out_off, int relu, int round) {
+                float* __restrict__ out_split, long long rows, int rows_per_batch, int C, int groups, int ldo,
+                int out_off, int relu) {
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int C4 = C >> 2;
   if (i4 >= rows * C4) return;
@@ -211,9 +221,10 @@ gn_apply_kernel(const float* __restrict__ in, const double* __restrict__ stats, 
     float o = (v[j] - mean) * rstd * w[c0 + j] + b[c0 + j];
     if (relu) o = fmaxf(o, 0.f);
     if (residual) o += residual[row * C + c0 + j];
-    v[j] = round ? round_tf32(o) : o;
+    v[j] = o;
   }
-  *reinterpret_cast<float4*>(out + row * ldo + out_off + c0) = make_float4(v[0], v[1], v[2], v[3]);
+  if (out) *reinterpret_cast<float4*>(out + row * C + c0) = make_float4(v[0], v[1], v[2], v[3]);
+  if (out_split) store_split4(out_split + row * ldo, out_off + c0, make_float4(v[0], v[1], v[2], v[3]));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -271,9 +282,15 @@ aspp_gap_branch_kernel(const double* __restrict__ sums, const float* __restrict_
     outv[o] = fmaxf((conv[o] - m) * rsqrtf(var + kEps) * gw[o] + gb[o], 0.f);
   }
   __syncthreads();
-  // the branch output of this sample (ch values, tf32-rounded: operand of the 1x1 conv that follows); the broadcast
-  // over the X*Y rows of the concat buffer is done by gap_broadcast_kernel with a full grid
-  for (int o = threadIdx.x; o < ch; o += blockDim.x) sums_out[(size_t)b * ch + o] = round_tf32(outv[o]);
+  // the branch output of this sample as one S32 row (ch % 32 == 0; operand of the 1x1 conv that follows); the broadcast
+  // over the X*Y rows of the concat buffer is done by gap_broadcast_kernel with a full grid (words copied verbatim)
+  for (int t = threadIdx.x; t < ch / 2; t += blockDim.x) {
+    uint32_t hi, lo;
+    split_pair(outv[2 * t], outv[2 * t + 1], hi, lo);
+    uint32_t* chunk = reinterpret_cast<uint32_t*>(sums_out + (size_t)b * ch + ((2 * t) & ~31));
+    chunk[t & 15] = hi;
+    chunk[16 + (t & 15)] = lo;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -297,9 +314,9 @@ gap_broadcast_kernel(const float* __restrict__ vals /*(B, ch)*/, float* __restri
 template <int NV, int R>
 __global__ void __launch_bounds__(256)
 fuse_kernel(const float* __restrict__ x, const float* __restrict__ bev, const float* __restrict__ cw, float cbias,
-            const float* __restrict__ identity, const double* __restrict__ id_stats, const float* __restrict__ id_w,
-            const float* __restrict__ id_b, int groups, float* __restrict__ out, long long rows, int Z,
-            long long rows_per_batch, int C) {
+            const float* __restrict__ identity, int identity_split, const double* __restrict__ id_stats,
+            const float* __restrict__ id_w, const float* __restrict__ id_b, int groups, float* __restrict__ out,
+            float* __restrict__ out_split, long long rows, int Z, long long rows_per_batch, int C) {
   const int lane = threadIdx.x & 31;
   const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
   if (row0 >= rows) return;
@@ -312,7 +329,8 @@ fuse_kernel(const float* __restrict__ x, const float* __restrict__ bev, const fl
     for (int i = 0; i < NV; ++i) {
       const int c0 = (i * 32 + lane) * 4;
       xv[r][i] = __ldcs(reinterpret_cast<const float4*>(x + row * C + c0));
-      idv[r][i] = __ldcs(reinterpret_cast<const float4*>(identity + row * C + c0));
+      idv[r][i] = identity_split ? load_split4(identity + row * C, c0)
+                                 : __ldcs(reinterpret_cast<const float4*>(identity + row * C + c0));
       bv[r][i] = __ldg(reinterpret_cast<const float4*>(bev + col * C + c0));
     }
   }
@@ -350,9 +368,31 @@ fuse_kernel(const float* __restrict__ x, const float* __restrict__ bev, const fl
       o.y = xv[r][i].y + coeff * bv[r][i].y + iv.y;
       o.z = xv[r][i].z + coeff * bv[r][i].z + iv.z;
       o.w = xv[r][i].w + coeff * bv[r][i].w + iv.w;
-      *reinterpret_cast<float4*>(out + row * C + c0) = o;
+      if (out) *reinterpret_cast<float4*>(out + row * C + c0) = o;
+      if (out_split) store_split4(out_split + row * C, c0, o);
     }
   }
+}
+
+// fp32 rows -> S32 split rows (C % 32 == 0); for the few operands that are produced in fp32 by a kernel whose other
+// consumers need fp32 (BEV tokens entering the ASPP branch, user-supplied module inputs)
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ in, float* __restrict__ out, long long n4, int C) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= n4) return;
+  const int C4 = C >> 2;
+  const long long row = i4 / C4;
+  const int c0 = (int)(i4 % C4) * 4;
+  store_split4(out + row * C, c0, __ldg(reinterpret_cast<const float4*>(in + row * C + c0)));
+}
+__global__ void __launch_bounds__(256)
+unsplit_rows_kernel(const float* __restrict__ in, float* __restrict__ out, long long n4, int C) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= n4) return;
+  const int C4 = C >> 2;
+  const long long row = i4 / C4;
+  const int c0 = (int)(i4 % C4) * 4;
+  *reinterpret_cast<float4*>(out + row * C + c0) = load_split4(in + row * C, c0);
 }
 
 }  // namespace occ
@@ -399,26 +439,28 @@ extern "C" int occ_gn_relu_zmean_ln(const float* y, const double* stats, const f
 }
 
 extern "C" int occ_layernorm(const float* in, const float* w, const float* b, float* out, long long rows, int C,
-                             int round_out, cudaStream_t stream) {
+                             int split_out, cudaStream_t stream) {
   OCC_REQUIRE(in && w && b && out && rows > 0 && C > 0);
+  OCC_REQUIRE(!split_out || C % 32 == 0);
   const int blocks = (int)((rows + 7) / 8);
   if (C % 128 == 0 && (C / 128 == 1 || C / 128 == 2 || C / 128 == 4 || C / 128 == 8)) {
-    DISPATCH_NV(C, (layernorm_kernel<NV><<<blocks, 256, 0, stream>>>(in, w, b, out, rows, C, round_out)));
+    DISPATCH_NV(C, (layernorm_kernel<NV><<<blocks, 256, 0, stream>>>(in, w, b, out, rows, C, split_out)));
   } else {
-    layernorm_generic_kernel<<<blocks, 256, 0, stream>>>(in, w, b, out, rows, C, round_out);
+    layernorm_generic_kernel<<<blocks, 256, 0, stream>>>(in, w, b, out, rows, C, split_out);
   }
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
 
 extern "C" int occ_gn_apply(const float* in, const double* stats, const float* w, const float* b,
-                            const float* residual, float* out, long long rows, int rows_per_batch, int C, int groups,
-                            int ldo, int out_off, int relu, int round_out, cudaStream_t stream) {
-  OCC_REQUIRE(in && stats && w && b && out && rows > 0 && rows_per_batch > 0 && rows % rows_per_batch == 0);
-  OCC_REQUIRE(C % 4 == 0 && groups > 0 && C % groups == 0 && ldo % 4 == 0 && out_off % 4 == 0);
+                            const float* residual, float* out, float* out_split, long long rows, int rows_per_batch,
+                            int C, int groups, int ldo, int out_off, int relu, cudaStream_t stream) {
+  OCC_REQUIRE(in && stats && w && b && (out || out_split) && rows > 0 && rows_per_batch > 0 && rows % rows_per_batch == 0);
+  OCC_REQUIRE(C % 4 == 0 && groups > 0 && C % groups == 0);
+  if (out_split) OCC_REQUIRE(C % 32 == 0 && ldo % 32 == 0 && out_off % 32 == 0 && out_off + C <= ldo);
   const long long n4 = rows * (C / 4);
-  gn_apply_kernel<<<(int)((n4 + 255) / 256), 256, 0, stream>>>(in, stats, w, b, residual, out, rows, rows_per_batch, C,
-                                                               groups, ldo, out_off, relu, round_out);
+  gn_apply_kernel<<<(int)((n4 + 255) / 256), 256, 0, stream>>>(in, stats, w, b, residual, out, out_split, rows,
+                                                               rows_per_batch, C, groups, ldo, out_off, relu);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -427,7 +469,8 @@ extern "C" int occ_aspp_gap_branch(const float* in, double* sums_ws, const float
                                    const float* gb, float* cat, int B, int rows_per_batch, int ch, int groups, int ldo,
                                    int out_off, cudaStream_t stream) {
   OCC_REQUIRE(in && sums_ws && wconv && gw && gb && cat);
-  OCC_REQUIRE(B > 0 && rows_per_batch > 0 && ch % 4 == 0 && ch <= 1024 && groups > 0 && ch % groups == 0 && 256 % (ch / 4) == 0);
+  OCC_REQUIRE(B > 0 && rows_per_batch > 0 && ch % 32 == 0 && ch <= 1024 && groups > 0 && ch % groups == 0 && 256 % (ch / 4) == 0);
+  OCC_REQUIRE(ldo % 32 == 0 && out_off % 32 == 0);  // the branch lands in the S32 concat buffer
   OCC_CUDA(cudaMemsetAsync(sums_ws, 0, (size_t)B * ch * sizeof(double), stream));
   const int chunk = 512;
   dim3 grid((rows_per_batch + chunk - 1) / chunk, B);
@@ -446,17 +489,37 @@ extern "C" int occ_aspp_gap_branch(const float* in, double* sums_ws, const float
 }
 
 extern "C" int occ_dualpath_fuse(const float* x, const float* bev, const float* cw, float cbias, const float* identity,
-                                 const double* id_stats, const float* id_w, const float* id_b, int groups, float* out,
-                                 int B, int XY, int Z, int C, cudaStream_t stream) {
-  OCC_REQUIRE(x && bev && cw && identity && out && B > 0 && XY > 0 && Z > 0 && C % 128 == 0);
+                                 int identity_split, const double* id_stats, const float* id_w, const float* id_b,
+                                 int groups, float* out, float* out_split, int B, int XY, int Z, int C,
+                                 cudaStream_t stream) {
+  OCC_REQUIRE(x && bev && cw && identity && (out || out_split) && B > 0 && XY > 0 && Z > 0 && C % 128 == 0);
   if (id_stats) OCC_REQUIRE(id_w && id_b && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0);
   const long long rows = (long long)B * XY * Z;
   DISPATCH_NV(C, ({
                 constexpr int R = NV == 1 ? 4 : (NV == 2 ? 2 : 1);
                 const int blocks = (int)((rows + 8 * R - 1) / (8 * R));
-                fuse_kernel<NV, R><<<blocks, 256, 0, stream>>>(x, bev, cw, cbias, identity, id_stats, id_w, id_b,
-                                                               groups > 0 ? groups : 1, out, rows, Z, (long long)XY * Z, C);
+                fuse_kernel<NV, R><<<blocks, 256, 0, stream>>>(x, bev, cw, cbias, identity, identity_split, id_stats, id_w,
+                                                               id_b, groups > 0 ? groups : 1, out, out_split, rows, Z,
+                                                               (long long)XY * Z, C);
               }));
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+// fp32 (rows, C) <-> S32 split format (C % 32 == 0)
+extern "C" int occ_split_rows(const float* in, float* out, long long rows, int C, cudaStream_t stream) {
+  OCC_REQUIRE(in && out && rows > 0 && C > 0 && C % 32 == 0);
+  OCC_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const long long n4 = rows * (C / 4);
+  split_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(in, out, n4, C);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+extern "C" int occ_unsplit_rows(const float* in, float* out, long long rows, int C, cudaStream_t stream) {
+  OCC_REQUIRE(in && out && rows > 0 && C > 0 && C % 32 == 0);
+  OCC_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const long long n4 = rows * (C / 4);
+  unsplit_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(in, out, n4, C);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

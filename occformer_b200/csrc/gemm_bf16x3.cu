@@ -1,10 +1,14 @@
-// Persistent warp-specialised TF32 GEMM / implicit-GEMM convolution for sm_100a.
+// Persistent warp-specialised fp32-faithful GEMM / implicit-GEMM convolution for sm_100a ("bf16x3").
 //
 //   D[M,N] = epilogue( A[M,K] * W[N,K]^T )          (plain mode: A row-major, W = torch Linear weight)
 //   D[vox,Cout] = epilogue( im2col(x)[vox, taps*Cin] * W2[Cout, taps*Cin]^T )   (conv mode)
 //
-// One CTA per SM, 256 threads: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle), warp 1 =
-// tcgen05.mma issuer (kind::tf32, M=128, N=BN, K=8 per instruction, fp32 accumulators in TMEM, two
+// Operands are fp32 values stored in the S32 split format (occ_ptx.cuh: every 32-column chunk = 32 bf16 hi | 32 bf16
+// lo); each 32-k block is contracted by three bf16 tensor-core passes (hi*hi + lo*hi + hi*lo, fp32 accumulate in
+// TMEM): ~1e-5 relative error, the bytes, TMA boxes and shared-memory tiles of a plain fp32 operand.
+//
+// One CTA per SM, 384 threads: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle), warp 1 =
+// tcgen05.mma issuer (kind::f16 / bf16, M=128, N=BN, K=16 per instruction, fp32 accumulators in TMEM, two
 // accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1), warp 2 = TMEM
 // allocator, warps 4..7 = epilogue (tcgen05.ld 32x32b -> registers -> bias / activation / residual /
 // GroupNorm statistics -> global).  Conv mode never materialises im2col: every filter tap is a 5-D TMA
@@ -37,7 +41,7 @@ struct GemmParams {
   int splits;     // split-K: > 1 => every tile's k-blocks are divided among `splits` CTAs, partial sums meet in `out`
                   // (zero-initialised by the host) through TMA reduce-add; no bias / act / stats in the kernel
   int act;        // 0 none, 1 relu, 2 gelu(erf)
-  int round_out;  // round result to tf32 (consumer is another tf32 MMA)
+  int split_out;  // write the result in the S32 split format (the consumer is another tensor-core contraction)
   // conv mode
   int conv;
   int Cin, KX, KY, KZ, dil, stride;
@@ -58,13 +62,14 @@ struct GemmParams {
   double* gn_stats;
   int cpg;
   int rows_per_batch;  // plain mode: rows per batch sample (for gn_stats), else 0
+  int* splitk_sem;     // [SPLITK_SEMS], see above (required when splits > 1)
 };
 
 // Split-K ordering: sem[(m, n) tile] counts the splits that have added their partial sum.  Split s adds after split
-// s - 1, so the fp32 reduce-add order -- and with it every bit of the result -- is fixed.  Zero at module load, and
-// reset to zero by the last split of every tile (convs on one stream reuse it; concurrent split-K convs on different
-// streams would only lose the fixed order, not correctness: the wait is bounded).
-__device__ int g_splitk_sem[1024];
+// s - 1, so the fp32 reduce-add order -- and with it every bit of the result -- is fixed.  The counters live in a
+// caller-provided workspace (occ_conv_workspace_bytes(): 1024 ints, zero before the first call; the last split of
+// every tile resets its counter, so one workspace serves every conv of a stream; concurrent streams pass their own).
+constexpr int SPLITK_SEMS = 1024;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
@@ -104,7 +109,7 @@ __device__ __forceinline__ void warp_butterfly32(float (&v)[32], int lane) {
 // shared-memory port (TMA writes + MMA operand reads), not by the tensor pipe.
 template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(384, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BK * 4;
   constexpr int A_BYTES = MT * A_STAGE_BYTES;
@@ -113,7 +118,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   static_assert(2 * ACC_COLS <= 512, "two accumulator buffers must fit TMEM");
   constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
                                  : (2 * ACC_COLS <= 256) ? 256 : 512;
-  constexpr uint32_t IDESC = make_idesc_tf32(BM, BN, 0, 0);
+  constexpr uint32_t IDESC = make_idesc_bf16(BM, BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -246,11 +251,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int sub = 0; sub < MT; ++sub) {
             const uint64_t adesc = make_sw128_desc(sa + sub * A_STAGE_BYTES, 1024, 16);
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {
-              // advance 8 tf32 = 32 bytes = 2 (16-byte units) inside the 128-byte swizzle row
-              mma_tf32_ss(d_tmem + sub * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, ((kb - kb0) | k) != 0);
-            }
+            // one S32 row block = 32 k values: hi*hi + lo*hi + hi*lo, six K=16 MMAs stepping 32 bytes inside the row
+            mma_bf16x3_ss(d_tmem + sub * BN, adesc, bdesc, IDESC, kb != kb0);
           }
           mma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -348,7 +350,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (p.splits > 1) {  // wait until the lower splits of this tile have added their partial sums
         if (threadIdx.x == 128) {
           const int want = tile % p.splits;
-          volatile int* sem = g_splitk_sem + ((tile / p.splits) & 1023);
+          volatile int* sem = p.splitk_sem + ((tile / p.splits) & (SPLITK_SEMS - 1));
           for (int spin = 0; *sem != want && spin < (1 << 16); ++spin) __nanosleep(64);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -435,9 +437,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
         }
-        if (p.round_out) {
+        if (p.split_out) {  // the 32 values of this (row, chunk) become the 32 words of their S32 chunk
+          uint32_t w[32];
+          split_chunk32(v, w);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(w[j]);
         }
         if (p.pool_out != nullptr) {
           // ---- fused adaptive max pool (windows are powers of two >= 2 that divide the grid).  The G lanes of this
@@ -537,7 +541,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (threadIdx.x == 128) {
           __threadfence();
           const int split = tile % p.splits;
-          atomicExch(g_splitk_sem + ((tile / p.splits) & 1023), split == p.splits - 1 ? 0 : split + 1);
+          atomicExch(p.splitk_sem + ((tile / p.splits) & (SPLITK_SEMS - 1)), split == p.splits - 1 ? 0 : split + 1);
         }
       }
     }
@@ -621,15 +625,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   constexpr size_t smem = (size_t)STAGES * (MT * A_STAGE_BYTES + BN * BK * 4) + 1024 /*align*/ +
                           1024 /*barriers+stats*/ + EPI_BYTES;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    OCC_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    configured = true;
-  }
+  OCC_ENSURE_SMEM((gemm_bf16x3_kernel<BN, STAGES, MT>), smem);
   int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   if (grid < 1) grid = 1;
-  gemm_tf32_kernel<BN, STAGES, MT><<<grid, 384, smem, stream>>>(tmA, tmB, tmC, p);
+  gemm_bf16x3_kernel<BN, STAGES, MT><<<grid, 384, smem, stream>>>(tmA, tmB, tmC, p);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -661,19 +660,20 @@ static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmC, const v
 
 using namespace occ;
 
-extern "C" int occ_gemm_tf32(const float* A, const float* W, float* out, int M, int N, int K, const float* bias,
-                             const float* residual, int act, int round_out, double* gn_stats, int cpg,
-                             int rows_per_batch, cudaStream_t stream) {
+extern "C" int occ_gemm_bf16x3(const float* A, const float* W, float* out, int M, int N, int K, const float* bias,
+                               const float* residual, int act, int split_out, double* gn_stats, int cpg,
+                               int rows_per_batch, cudaStream_t stream) {
   OCC_REQUIRE(A && W && out);
   OCC_REQUIRE(M > 0 && N > 0 && K > 0);
-  OCC_REQUIRE(K % 4 == 0);  // 16-byte row pitch for TMA
+  OCC_REQUIRE(K % 32 == 0);                 // S32 operand rows: whole 32-k chunks
+  OCC_REQUIRE(!split_out || N % 32 == 0);   // S32 output rows
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   OCC_REQUIRE(act >= 0 && act <= 2);
   if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && N % cpg == 0 && N / cpg <= 32 &&
                             rows_per_batch > 0 && rows_per_batch % BM == 0);
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.num_k_blocks = (K + BK - 1) / BK;
-  p.out = out; p.ldo = N; p.bias = bias; p.residual = residual; p.ldr = N; p.act = act; p.round_out = round_out;
+  p.out = out; p.ldo = N; p.bias = bias; p.residual = residual; p.ldr = N; p.act = act; p.split_out = split_out;
   p.conv = 0; p.gn_stats = gn_stats; p.cpg = cpg; p.rows_per_batch = gn_stats ? rows_per_batch : 0;
   p.pool_out = nullptr; p.pool_flag = nullptr; p.store_out = 1;
   CUtensorMap tmA;
@@ -694,13 +694,16 @@ extern "C" int occ_gemm_tf32(const float* A, const float* W, float* out, int M, 
   return dispatch_gemm(tmA, tmC, W, p, (M + BM - 1) / BM, stream);
 }
 
-// x: (B, X, Y, Z, Cin) channel-last fp32;  w2: (Cout, KX*KY*KZ*Cin) tap-major repacked weights;
+// x: (B, X, Y, Z, Cin) channel-last, S32;  w2: (Cout, KX*KY*KZ*Cin) tap-major repacked weights, S32 per tap;
 // out: (B, Xo, Yo, Zo, Cout).  pad = dil*(K-1)/2 per axis ("same" for stride 1), Xo = (X + 2p - dil*(K-1) - 1)/s + 1.
-extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B, int X, int Y, int Z, int Cin,
-                             int Cout, int KX, int KY, int KZ, int stride, int dil, const float* bias,
-                             const float* residual, int act, int round_out, double* gn_stats, int cpg,
-                             cudaStream_t stream) {
+extern "C" size_t occ_conv_workspace_bytes(void) { return SPLITK_SEMS * sizeof(int); }
+
+extern "C" int occ_conv_bf16x3(const float* x, const float* w2, float* out, int B, int X, int Y, int Z, int Cin,
+                               int Cout, int KX, int KY, int KZ, int stride, int dil, const float* bias,
+                               const float* residual, int act, int split_out, double* gn_stats, int cpg,
+                               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   OCC_REQUIRE(x && w2 && out);
+  OCC_REQUIRE(!split_out || Cout % 32 == 0);
   OCC_REQUIRE(B > 0 && X > 0 && Y > 0 && Z > 0 && Cin > 0 && Cout > 0);
   OCC_REQUIRE(Cin % BK == 0);
   OCC_REQUIRE((KX == 1 || KX == 3) && (KY == 1 || KY == 3) && (KZ == 1 || KZ == 3));
@@ -724,7 +727,7 @@ extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B,
   p.tiles_z = (p.Zo + p.bz - 1) / p.bz;
   p.N = Cout; p.K = KX * KY * KZ * Cin; p.num_k_blocks = p.K / BK;
   p.M = B * p.Xo * p.Yo * p.Zo;
-  p.out = out; p.ldo = Cout; p.bias = bias; p.residual = residual; p.ldr = Cout; p.act = act; p.round_out = round_out;
+  p.out = out; p.ldo = Cout; p.bias = bias; p.residual = residual; p.ldr = Cout; p.act = act; p.split_out = split_out;
   p.gn_stats = gn_stats; p.cpg = cpg; p.rows_per_batch = 0;
   p.pool_out = nullptr; p.pool_flag = nullptr; p.store_out = 1;
   OCC_REQUIRE(p.bx * stride <= 256 && p.by * stride <= 256 && p.bz * stride <= 256);
@@ -756,7 +759,8 @@ extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B,
   // no bias / activation (GroupNorm follows), so the partial sums can meet in `out` through TMA reduce-add; the
   // GroupNorm statistics are then taken from the finished tensor.
   p.splits = 1;
-  if (p.use_tma_store && !bias && !residual && act == 0 && !round_out) {
+  if (p.use_tma_store && !bias && !residual && act == 0 && !split_out && workspace &&
+      workspace_bytes >= SPLITK_SEMS * sizeof(int) && (reinterpret_cast<uintptr_t>(workspace) & 3) == 0) {
     const int bn = Cout <= 32 ? 32 : Cout <= 64 ? 64 : (Cout <= 128 || (Cout % 256 != 0 && Cout % 128 == 0)) ? 128 : 256;
     const long long tiles = (long long)num_m_tiles * ((Cout + bn - 1) / bn);
     const int sms = sm_count();
@@ -775,6 +779,7 @@ extern "C" int occ_conv_tf32(const float* x, const float* w2, float* out, int B,
   if (p.splits > 1) {
     OCC_CUDA(cudaMemsetAsync(out, 0, (size_t)p.M * Cout * sizeof(float), stream));
     p.gn_stats = nullptr;
+    p.splitk_sem = static_cast<int*>(workspace);
   }
   rc = dispatch_gemm(tmA, tmC, w2, p, num_m_tiles, stream);
   if (rc) return rc;
@@ -836,7 +841,7 @@ extern "C" int occ_mask_gemm_pool(const float* mf, const float* membed, float* m
     p.tiles_x = (X + p.bx - 1) / p.bx; p.tiles_y = (Y + p.by - 1) / p.by; p.tiles_z = (Z + p.bz - 1) / p.bz;
     p.N = Q; p.K = E; p.num_k_blocks = E / BK; p.M = X * Y * Z;
     float* out_b = mask_out ? mask_out + (size_t)b * X * Y * Z * Q : nullptr;
-    p.out = out_b; p.ldo = Q; p.bias = nullptr; p.residual = nullptr; p.ldr = Q; p.act = 0; p.round_out = 0;
+    p.out = out_b; p.ldo = Q; p.bias = nullptr; p.residual = nullptr; p.ldr = Q; p.act = 0; p.split_out = 0;
     p.gn_stats = nullptr; p.cpg = 0; p.rows_per_batch = 0;
     p.pool_out = pooled + (size_t)b * Xo * Yo * Zo * Q; p.pool_flag = flag + (size_t)b * Q;
     p.pwx = wx; p.pwy = wy; p.pwz = wz; p.pXo = Xo; p.pYo = Yo; p.pZo = Zo;

@@ -111,10 +111,10 @@ __global__ void sine_pos3d_kernel(float* __restrict__ out, int X, int Y, int Z, 
 
 // ---------------------------------------------------------------------------------------------------------
 // Level / mask-feature preparation: (optional NCDHW -> channel-last transpose) + level embed + positional encoding,
-// tf32-rounded operands for the projection GEMMs.
+// written in the S32 split format (operands of the projection GEMMs / mask GEMMs; C % 32 == 0).
 //   in  : channel-last (B, S, C) when in_cl != 0, else reference layout (B, C, S)
-//   mem : (B, S, C) = round(in + level_embed)          (V-projection operand; also the mask-feature operand)
-//   kpos: (B, S, C) = round(in + level_embed + pos)    (K-projection operand; optional)
+//   mem : (B, S, C) = in + level_embed          (V-projection operand; also the mask-feature operand)
+//   kpos: (B, S, C) = in + level_embed + pos    (K-projection operand; optional)
 __global__ void head_prep_cl_kernel(const float* __restrict__ in, const float* __restrict__ level_embed,
                                     const float* __restrict__ pos, float* __restrict__ mem, float* __restrict__ kpos,
                                     long long rows, long long S, int C) {
@@ -128,12 +128,10 @@ __global__ void head_prep_cl_kernel(const float* __restrict__ in, const float* _
     const float4 l = *reinterpret_cast<const float4*>(level_embed + c0);
     v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
   }
-  *reinterpret_cast<float4*>(mem + row * C + c0) =
-      make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+  store_split4(mem + row * C, c0, v);
   if (kpos) {
     const float4 p = *reinterpret_cast<const float4*>(pos + (row % S) * C + c0);
-    *reinterpret_cast<float4*>(kpos + row * C + c0) =
-        make_float4(round_tf32(v.x + p.x), round_tf32(v.y + p.y), round_tf32(v.z + p.z), round_tf32(v.w + p.w));
+    store_split4(kpos + row * C, c0, make_float4(v.x + p.x, v.y + p.y, v.z + p.z, v.w + p.w));
   }
 }
 
@@ -150,22 +148,34 @@ __global__ void head_prep_ncs_kernel(const float* __restrict__ in, const float* 
     tile[i][threadIdx.x] = (c < C && s < S) ? __ldcs(in + ((size_t)b * C + c) * S + s) : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {  // a warp (threadIdx.x = 0..31) = one S32 chunk of one row
     const long long s = s0 + i;
-    const int c = c0 + threadIdx.x;
-    if (s < S && c < C) {
+    const int c = c0 + threadIdx.x;  // C % 32 == 0: c < C for the whole warp
+    if (s < S) {
       float v = tile[threadIdx.x][i];
       if (level_embed) v += level_embed[c];
-      const size_t o = ((size_t)b * S + s) * C + c;
-      mem[o] = round_tf32(v);
-      if (kpos) kpos[o] = round_tf32(v + pos[s * C + c]);
+      const float vk = kpos ? v + pos[s * C + c] : 0.f;
+      const float v2 = __shfl_xor_sync(0xffffffffu, v, 1), vk2 = __shfl_xor_sync(0xffffffffu, vk, 1);
+      if (!(threadIdx.x & 1)) {
+        uint32_t hi, lo;
+        split_pair(v, v2, hi, lo);
+        uint32_t* chunk = reinterpret_cast<uint32_t*>(mem + ((size_t)b * S + s) * C + c0);
+        chunk[threadIdx.x >> 1] = hi;
+        chunk[16 + (threadIdx.x >> 1)] = lo;
+        if (kpos) {
+          split_pair(vk, vk2, hi, lo);
+          chunk = reinterpret_cast<uint32_t*>(kpos + ((size_t)b * S + s) * C + c0);
+          chunk[threadIdx.x >> 1] = hi;
+          chunk[16 + (threadIdx.x >> 1)] = lo;
+        }
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // forward_head, query side: post_norm LN -> cls_embed, mask_embed MLP (Linear-ReLU-Linear-ReLU-Linear).
-//   query (B*Q, E); cls_out (B*Q, NC); membed_out (B*Q, E) tf32-rounded (B operand of the mask GEMM)
+//   query (B*Q, E); cls_out (B*Q, NC); membed_out (B*Q, E) in the S32 split format (operand of the mask GEMMs)
 __global__ void __launch_bounds__(1024)
 query_head_kernel(const float* __restrict__ query_in, const float* __restrict__ n2w, const float* __restrict__ n2b,
                   float* __restrict__ query_state, const float* __restrict__ pn_w, const float* __restrict__ pn_b,
@@ -208,7 +218,16 @@ query_head_kernel(const float* __restrict__ query_in, const float* __restrict__ 
   xs[g * E + j] = h;
   __syncthreads();
   h = matvec4(m2T, E, m2b, xs, E, j, g, E, part);
-  membed_out[(size_t)row * E + j] = round_tf32(h);
+  {  // E % 32 == 0: a warp holds one 32-channel chunk of one row; lanes (2t, 2t+1) form packed word t
+    const float h2 = __shfl_xor_sync(0xffffffffu, h, 1);
+    if (!(j & 1)) {
+      uint32_t hi, lo;
+      split_pair(h, h2, hi, lo);
+      uint32_t* chunk = reinterpret_cast<uint32_t*>(membed_out + (size_t)row * E + (j & ~31));
+      chunk[(j & 31) >> 1] = hi;
+      chunk[16 + ((j & 31) >> 1)] = lo;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -246,95 +265,7 @@ mask_pool_kernel(const float* __restrict__ mask, int* __restrict__ pooled, int* 
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Masked cross-attention, flash-decoding style.  One CTA = (key chunk, head, batch); thread t <-> query t.
-//   qh     (B, Q, E)  projected queries, already scaled by hd^-0.5
-//   Kp, Vp (B*S, ld) projected keys / values of this level; this layer's slice starts at column koff / voff
-//   pooled (B, S, Q) pooled mask logits (blocked where < 0, unless row_flag[b,q] == 0)
-//   part   (B, H, nchunk, Q, 34): running max, sum, 32 accumulators
-constexpr int XA_HD = 32;
-constexpr int XA_TILE = 64;
-
-__global__ void __launch_bounds__(128)
-cross_attn_partial_kernel(const float* __restrict__ qh, const float* __restrict__ Kp, const float* __restrict__ Vp,
-                          int ld, int koff, int voff, const int* __restrict__ pooled,
-                          const int* __restrict__ row_flag, float* __restrict__ part, int S, int Q, int E, int H,
-                          int chunk, int nchunk) {
-  __shared__ __align__(16) float sk[XA_TILE][XA_HD];
-  __shared__ __align__(16) float sv[XA_TILE][XA_HD];
-  __shared__ int smask[XA_TILE][125];  // pooled mask logits (ordered ints: blocked <=> negative), [key][query]
-  const int c = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int t = threadIdx.x;
-  const bool active = t < Q;
-  float q[XA_HD];
-  if (active) {
-    const float4* src = reinterpret_cast<const float4*>(qh + ((size_t)b * Q + t) * E + h * XA_HD);
-#pragma unroll
-    for (int d = 0; d < XA_HD / 4; ++d) {
-      const float4 v = src[d];
-      q[4 * d] = v.x; q[4 * d + 1] = v.y; q[4 * d + 2] = v.z; q[4 * d + 3] = v.w;
-    }
-  }
-  const bool use_mask = active && row_flag[b * Q + t] != 0;
-  float m = -INFINITY, l = 0.f, acc[XA_HD];
-#pragma unroll
-  for (int d = 0; d < XA_HD; ++d) acc[d] = 0.f;
-  const int s_begin = c * chunk, s_end = min(S, s_begin + chunk);
-  for (int s0 = s_begin; s0 < s_end; s0 += XA_TILE) {
-    const int n = min(XA_TILE, s_end - s0);
-    __syncthreads();
-    // stage K / V tile: 64 rows x 32 floats each = 512 float4 per matrix, 128 threads -> 4 each
-    for (int i = t; i < XA_TILE * (XA_HD / 4); i += 128) {
-      const int r = i >> 3, c4 = i & 7;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (r < n) {
-        const size_t row = (size_t)b * S + s0 + r;
-        kv = __ldg(reinterpret_cast<const float4*>(Kp + row * ld + koff + h * XA_HD) + c4);
-        vv = __ldg(reinterpret_cast<const float4*>(Vp + row * ld + voff + h * XA_HD) + c4);
-      }
-      *reinterpret_cast<float4*>(&sk[r][c4 * 4]) = kv;
-      *reinterpret_cast<float4*>(&sv[r][c4 * 4]) = vv;
-    }
-    {  // mask tile: n keys x Q logits are one contiguous block of the query-last pooled tensor -> coalesced
-      const int* ptile = pooled + ((size_t)b * S + s0) * Q;
-      for (int i = t; i < n * Q; i += 128) smask[i / Q][i % Q] = __ldg(ptile + i);
-    }
-    __syncthreads();
-    if (active) {
-      for (int j = 0; j < n; ++j) {
-        if (use_mask && smask[j][t] < 0) continue;
-        float s = 0.f;
-#pragma unroll
-        for (int d = 0; d < XA_HD; d += 4) {
-          const float4 kk = *reinterpret_cast<const float4*>(&sk[j][d]);
-          s = fmaf(q[d], kk.x, s); s = fmaf(q[d + 1], kk.y, s); s = fmaf(q[d + 2], kk.z, s); s = fmaf(q[d + 3], kk.w, s);
-        }
-        if (s > m) {
-          const float sc = __expf(m - s);  // m = -inf on the first key -> 0
-          l *= sc;
-#pragma unroll
-          for (int d = 0; d < XA_HD; ++d) acc[d] *= sc;
-          m = s;
-        }
-        const float p = __expf(s - m);
-        l += p;
-#pragma unroll
-        for (int d = 0; d < XA_HD; d += 4) {
-          const float4 vv = *reinterpret_cast<const float4*>(&sv[j][d]);
-          acc[d] = fmaf(p, vv.x, acc[d]); acc[d + 1] = fmaf(p, vv.y, acc[d + 1]);
-          acc[d + 2] = fmaf(p, vv.z, acc[d + 2]); acc[d + 3] = fmaf(p, vv.w, acc[d + 3]);
-        }
-      }
-    }
-  }
-  if (active) {
-    float* dst = part + ((((size_t)b * H + h) * nchunk + c) * Q + t) * (XA_HD + 2);
-    dst[0] = m;
-    dst[1] = l;
-#pragma unroll
-    for (int d = 0; d < XA_HD; ++d) dst[2 + d] = acc[d];
-  }
-}
+constexpr int XA_HD = 32;  // head dim of the decoder attentions (embed_dims / num_heads)
 
 // ---------------------------------------------------------------------------------------------------------
 // Cross-attention tail + self-attention in-projection (thread (j, g): channel j = head j/32, dim j%32, of row row0+g):
@@ -648,10 +579,9 @@ extern "C" int occ_sine_pos3d(float* out, int X, int Y, int Z, int num_feats, fl
 
 extern "C" int occ_head_prep(const float* in, int in_channel_last, const float* level_embed, const float* pos,
                              float* mem, float* kpos, int B, long long S, int C, cudaStream_t stream) {
-  OCC_REQUIRE(in && mem && B > 0 && S > 0 && C > 0);
+  OCC_REQUIRE(in && mem && B > 0 && S > 0 && C > 0 && C % 32 == 0);  // S32 output rows
   OCC_REQUIRE((kpos == nullptr) == (pos == nullptr));
   if (in_channel_last) {
-    OCC_REQUIRE(C % 4 == 0);
     const long long n4 = (long long)B * S * (C / 4);
     head_prep_cl_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(in, level_embed, pos, mem, kpos,
                                                                          (long long)B * S, S, C);
@@ -697,29 +627,6 @@ extern "C" int occ_mask_pool(const float* mask, int* pooled, int* row_flag, int 
   return OCC_OK;
 }
 
-extern "C" int occ_cross_attn_chunks(int S, int* chunk, int* nchunk) {
-  // a CTA walks its key chunk sequentially (latency ~ chunk length): make chunks as short as possible (>= one 64-key
-  // tile) while keeping the number of partials that cross_merge has to combine <= 96
-  int c = XA_TILE;
-  while ((S + c - 1) / c > 96) c += XA_TILE;
-  *chunk = c;
-  *nchunk = (S + c - 1) / c;
-  return OCC_OK;
-}
-
-extern "C" int occ_cross_attn_partial(const float* qh, const float* Kp, const float* Vp, int ld, int koff, int voff,
-                                      const int* pooled, const int* row_flag, float* part, int B, int S, int Q,
-                                      int E, int H, int chunk, int nchunk, cudaStream_t stream) {
-  OCC_REQUIRE(qh && Kp && Vp && pooled && row_flag && part);
-  OCC_REQUIRE(B > 0 && S > 0 && Q > 0 && Q <= 124 && H > 0 && E == H * XA_HD && chunk > 0 && chunk % XA_TILE == 0);
-  OCC_REQUIRE(nchunk == (S + chunk - 1) / chunk && ld % 4 == 0 && koff % 4 == 0 && voff % 4 == 0);
-  dim3 grid(nchunk, H, B);
-  cross_attn_partial_kernel<<<grid, 128, 0, stream>>>(qh, Kp, Vp, ld, koff, voff, pooled, row_flag, part, S, Q, E, H,
-                                                      chunk, nchunk);
-  OCC_LAUNCH_CHECK();
-  return OCC_OK;
-}
-
 extern "C" int occ_cross_merge(const float* part, int nchunk, int H, const float* query, const float* query_pos, int Q,
                                const float* woT, const float* bo, const float* n0w, const float* n0b,
                                const float* sa_inT, const float* sa_inb, float scale, float* query1, float* sa_qkv,
@@ -761,18 +668,10 @@ extern "C" int occ_classmix(const float* mask, const float* cls, float* out, uns
   OCC_REQUIRE(smem <= 200 * 1024);
   dim3 grid((unsigned)((Vo + CM_THREADS - 1) / CM_THREADS), B);
   if (NC - 1 <= 20) {
-    static bool configured = false;
-    if (!configured) {
-      OCC_CUDA(cudaFuncSetAttribute(classmix_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
+    OCC_ENSURE_SMEM(classmix_kernel<20>, 200 * 1024);
     classmix_kernel<20><<<grid, CM_THREADS, smem, stream>>>(mask, cls, out, labels, X, Y, Z, Xo, Yo, Zo, Q, NC);
   } else {
-    static bool configured = false;
-    if (!configured) {
-      OCC_CUDA(cudaFuncSetAttribute(classmix_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
+    OCC_ENSURE_SMEM(classmix_kernel<32>, 200 * 1024);
     classmix_kernel<32><<<grid, CM_THREADS, smem, stream>>>(mask, cls, out, labels, X, Y, Z, Xo, Yo, Zo, Q, NC);
   }
   OCC_LAUNCH_CHECK();

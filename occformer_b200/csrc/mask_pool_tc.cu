@@ -6,6 +6,7 @@
 // are only ever consumed through the pooled mask, so this kernel never writes them: 491 MB of mask features are read
 // once per layer and ~1 MB of pooled logits is written.
 //
+// Both operands arrive in the S32 split format; every 32-k block is three bf16 tensor-core passes (occ_ptx.cuh).
 // D[128 queries x 128 voxels] = membed[b] (A, resident in smem, K-major) x mf tile^T (B operand: the voxel rows of a
 // (bx, by, bz) box, K-major, TMA 5-D box loads).  With the queries on the TMEM lanes every epilogue thread owns one
 // query and sees the 128 voxels of the tile as its own registers: the window maximum is a register reduction with
@@ -22,7 +23,7 @@ constexpr int MP_THREADS = 384;
 constexpr int MP_KB_BYTES = 128 * 32 * 4;  // one k-block of A or B: 128 rows x 32 floats
 
 struct MaskPoolParams {
-  const float* membed;  // (B, Q, E) tf32
+  const float* membed;  // (B, Q, E) S32
   int* pooled;          // (B, Xo*Yo*Zo, Q) ordered ints
   int* flag;            // (B, Q)
   int Q, E, KB, stages;
@@ -79,10 +80,7 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmB, const MaskPoolParam
     for (int i = threadIdx.x; i < 128 * E4; i += MP_THREADS) {
       const int r = i / E4, c4 = i - r * E4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < p.Q) {
-        v = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * p.E) + c4);
-        v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-      }
+      if (r < p.Q) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * p.E) + c4);  // S32 words, copied verbatim
       const int kb = c4 >> 3, ch = c4 & 7;
       *reinterpret_cast<float4*>(sa + (size_t)kb * MP_KB_BYTES + r * 128 + ((ch ^ (r & 7)) << 4)) = v;
     }
@@ -111,7 +109,7 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmB, const MaskPoolParam
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t IDESC = make_idesc_tf32(128, 128, 0, 0);
+      constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
       int it = 0;
       for (int i = 0; i < n_my; ++i) {
         const int buf = i & 3;
@@ -124,8 +122,7 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmB, const MaskPoolParam
           tc_fence_after();
           const uint64_t adesc = make_sw128_desc(smem_u32(sa + (size_t)kb * MP_KB_BYTES), 1024, 16);
           const uint64_t bdesc = make_sw128_desc(smem_u32(ring + (size_t)s * MP_KB_BYTES), 1024, 16);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) mma_tf32_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (kb | kk) != 0);
+          mma_bf16x3_ss(d_tmem, adesc, bdesc, IDESC, kb != 0);
           mma_commit(&empty_bar[s]);
         }
         mma_commit(&acc_full[buf]);
@@ -201,11 +198,7 @@ static int launch_mask_pool(const float* mf, const MaskPoolParams& p0, int B, in
   if (rc) return rc;
   const size_t smem = (size_t)(p.KB + p.stages) * MP_KB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   auto kern = mask_pool_tc_kernel<P, BX, BY, BZ>;
-  static size_t configured = 0;
-  if (configured < smem) {
-    OCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  OCC_ENSURE_SMEM(kern, smem);
   int gx = sm_count() / B;
   if (gx < 1) gx = 1;
   if (gx > p.n_tiles) gx = p.n_tiles;
@@ -215,7 +208,7 @@ static int launch_mask_pool(const float* mf, const MaskPoolParams& p0, int B, in
 }
 
 // Returns OCC_OK when the query-stationary kernel handled the call, 1 when the shape is not covered (the caller falls
-// back to the voxel-stationary epilogue pooling in gemm_tf32.cu), < 0 / cudaError on failure.
+// back to the voxel-stationary epilogue pooling in gemm_bf16x3.cu), < 0 / cudaError on failure.
 int mask_pool_query_stationary(const float* mf, const float* membed, int* pooled, int* flag, int B, int X, int Y, int Z,
                                int E, int Q, int Xo, int Yo, int Zo, cudaStream_t stream) {
   const int wx = X / Xo, wy = Y / Yo, wz = Z / Zo;

@@ -54,15 +54,37 @@ inline PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+constexpr int OCC_MAX_DEVICES = 64;
+
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs).
 inline int sm_count() {
-  static int n = 0;
-  if (n) return n;
+  static int n[OCC_MAX_DEVICES] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  if (n <= 0) n = 148;
-  return n;
+  if (dev < 0 || dev >= OCC_MAX_DEVICES) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }
+  if (n[dev]) return n[dev];
+  cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  if (n[dev] <= 0) n[dev] = 148;
+  return n[dev];
 }
+
+// Opt a kernel into `bytes` of dynamic shared memory on the current device (cudaFuncSetAttribute applies per device;
+// the largest request seen so far is remembered per device, so the call is made once per kernel and device).
+#define OCC_ENSURE_SMEM(kernel, bytes)                                                                            \
+  do {                                                                                                            \
+    static size_t cfg__[occ::OCC_MAX_DEVICES] = {};                                                               \
+    int dev__ = 0;                                                                                                \
+    cudaGetDevice(&dev__);                                                                                        \
+    const bool known__ = dev__ >= 0 && dev__ < occ::OCC_MAX_DEVICES;                                              \
+    if (!known__ || cfg__[dev__] < (size_t)(bytes)) {                                                             \
+      OCC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));          \
+      if (known__) cfg__[dev__] = (size_t)(bytes);                                                                \
+    }                                                                                                             \
+  } while (0)
 
 // fp32 tensor map, rank <= 5, 128-byte swizzle, zero OOB fill.  dims/box/estr innermost first;
 // strides_bytes[i] = byte stride of dim i+1.

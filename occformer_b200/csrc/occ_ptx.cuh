@@ -183,6 +183,97 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_ma
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Instruction descriptor for kind::f16 with BF16 operands, D = F32 (format codes: 0 = F16, 1 = BF16).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ split-bf16 ("bf16x3") operands
+// Every tensor-core contraction of this library is an fp32 problem computed as THREE bf16 tensor-core passes on
+// hi/lo split operands:  a = a_hi + a_lo (+ <= 2^-18 |a|),  a_hi = bf16(a),  a_lo = bf16(a - a_hi), and
+//     a * b  ~=  a_hi b_hi + a_lo b_hi + a_hi b_lo         (the dropped a_lo b_lo term is <= 2^-18 |a b|),
+// accumulated in fp32 in TMEM: ~1e-5 relative error instead of the ~4e-4 of single-pass tf32, at 1.5x the tensor time
+// of tf32 (bf16 MMAs run at twice the tf32 rate) and identical bytes.
+//
+// "S32" operand format: an fp32-container tensor whose every aligned 32-column chunk (128 bytes) holds
+//     [ hi(k0..k31) as 32 bf16 | lo(k0..k31) as 32 bf16 ]
+// so a K-major SWIZZLE_128B shared-memory row (128 B) is exactly one chunk: the four K=16 MMA steps of a row start at
+// byte 0 (hi, k 0-15), 32 (hi, k 16-31), 64 (lo, k 0-15), 96 (lo, k 16-31) -- TMA boxes, tile sizes and swizzles are the
+// ones of a plain fp32 tile.  The same 32-word layout (16 packed hi words, 16 packed lo words) is used for operands
+// that live in TMEM (two bf16 per 32-bit column, lower k in the lower half).
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));  // a -> low half, b -> high half
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));  // residuals are exact in fp32
+}
+// 32 consecutive values of a row -> the 32 words of their S32 chunk
+__device__ __forceinline__ void split_chunk32(const float (&v)[32], uint32_t (&w)[32]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], w[j], w[16 + j]);
+}
+// four consecutive values at column c0 (multiple of 4) of a row stored in S32 format
+__device__ __forceinline__ void store_split4(float* row, int c0, float4 v) {
+  uint2 hi, lo;
+  split_pair(v.x, v.y, hi.x, lo.x);
+  split_pair(v.z, v.w, hi.y, lo.y);
+  uint8_t* chunk = reinterpret_cast<uint8_t*>(row + (c0 & ~31)) + (c0 & 31) * 2;
+  *reinterpret_cast<uint2*>(chunk) = hi;
+  *reinterpret_cast<uint2*>(chunk + 64) = lo;
+}
+__device__ __forceinline__ float4 load_split4(const float* row, int c0) {
+  const uint8_t* chunk = reinterpret_cast<const uint8_t*>(row + (c0 & ~31)) + (c0 & 31) * 2;
+  const uint2 hi = *reinterpret_cast<const uint2*>(chunk);
+  const uint2 lo = *reinterpret_cast<const uint2*>(chunk + 64);
+  float4 o;
+  o.x = __uint_as_float(hi.x << 16) + __uint_as_float(lo.x << 16);
+  o.y = __uint_as_float(hi.x & 0xFFFF0000u) + __uint_as_float(lo.x & 0xFFFF0000u);
+  o.z = __uint_as_float(hi.y << 16) + __uint_as_float(lo.y << 16);
+  o.w = __uint_as_float(hi.y & 0xFFFF0000u) + __uint_as_float(lo.y & 0xFFFF0000u);
+  return o;
+}
+
+// D[tmem] (+)= A[smem] * B[smem] on bf16 operands, single-thread issue.
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]  (A: two bf16 per 32-bit column)
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The three passes of one 32-k S32 row block (A, B K-major SWIZZLE_128B tiles in shared memory): 6 MMAs of K = 16.
+// `acc0` = accumulate flag of the very first MMA.
+__device__ __forceinline__ void mma_bf16x3_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t acc0) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    mma_bf16_ss(d_tmem, adesc + 2 * h, bdesc + 2 * h, idesc, h ? 1u : acc0);  // hi * hi
+    mma_bf16_ss(d_tmem, adesc + 2 * (2 + h), bdesc + 2 * h, idesc, 1u);       // lo * hi
+    mma_bf16_ss(d_tmem, adesc + 2 * h, bdesc + 2 * (2 + h), idesc, 1u);       // hi * lo
+  }
+}
+// Same with the A block in TMEM: 32 columns = [16 packed hi | 16 packed lo] of 32 k values.
+__device__ __forceinline__ void mma_bf16x3_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t acc0) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    mma_bf16_ts(d_tmem, a_tmem + 8 * h, bdesc + 2 * h, idesc, h ? 1u : acc0);       // hi * hi
+    mma_bf16_ts(d_tmem, a_tmem + 16 + 8 * h, bdesc + 2 * h, idesc, 1u);             // lo * hi
+    mma_bf16_ts(d_tmem, a_tmem + 8 * h, bdesc + 2 * (2 + h), idesc, 1u);            // hi * lo
+  }
+}
+
 // D[tmem] (+)= A[smem] * B[smem], single-thread issue.
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {

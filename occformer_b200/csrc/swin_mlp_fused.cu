@@ -1,6 +1,6 @@
 // Swin block tail for C = 128 tokens in one kernel: attention output projection + residual, LayerNorm2, FFN
-// (Linear - GELU - Linear) + residual.  Three chained 128x128x128 tf32 GEMMs per 128-token tile on tcgen05; the
-// intermediate activations never leave the SM (TMEM / registers).
+// (Linear - GELU - Linear) + residual.  Three chained 128x128x128 GEMMs per 128-token tile on tcgen05 (split-bf16
+// operands, three passes = fp32-faithful, occ_ptx.cuh); the intermediate activations never leave the SM (TMEM / registers).
 //
 // Reference: mmdet SwinBlock.forward (swin.py) as used by projects/mmdet3d_plugin/occformer/backbones/
 // dualpath_block.py:57-70 (shared_transformer on every Z slice and on the BEV slice):
@@ -41,7 +41,7 @@ struct SwinMlpParams {
 };
 
 // GELU(x) = x * Phi(x) with erfc(z) = P(t) exp(-z^2), t = 1 / (1 + p z) (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7):
-// branch-free, 2 MUFU + ~14 FP32 ops instead of erff's ~30; the result is rounded to tf32 (2^-11) right after.
+// branch-free, 2 MUFU + ~14 FP32 ops instead of erff's ~30.
 __device__ __forceinline__ float smf_gelu(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
   const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
@@ -152,7 +152,7 @@ swin_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t IDESC = make_idesc_tf32(128, 128, 0, 0);
+      constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
       int ia = 0, iw = 0;
       uint32_t na = 0;  // waits consumed on a_ready
       auto issue_m1 = [&](int i) {  // D1 = att x Wp^T into Racc of tile slot i & 1
@@ -164,8 +164,7 @@ swin_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tc_fence_after();
           const uint64_t adesc = make_sw128_desc(smem_u32(att_ring + (size_t)sa * SMF_SLOT), 1024, 16);
           const uint64_t bdesc = make_sw128_desc(smem_u32(w_ring + (size_t)sw * SMF_SLOT), 1024, 16);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) mma_tf32_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (kb | kk) != 0);
+          mma_bf16x3_ss(d_tmem, adesc, bdesc, IDESC, kb != 0);
           mma_commit(&att_empty[sa]);
           mma_commit(&w_empty[sw]);
         }
@@ -181,9 +180,8 @@ swin_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(&w_full[sw], (uint32_t)((iw / SMF_W_SLOTS) & 1));
           tc_fence_after();
           const uint64_t bdesc = make_sw128_desc(smem_u32(w_ring + (size_t)sw * SMF_SLOT), 1024, 16);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            mma_tf32_ts(d_tmem, a_tmem + kb * 32 + kk * 8, bdesc + 2 * kk, IDESC, third || (kb | kk) != 0);
+          // A block kb in TMEM: 32 columns = [16 packed hi | 16 packed lo] of k = 32 kb .. 32 kb + 31
+          mma_bf16x3_ts(d_tmem, a_tmem + kb * 32, bdesc, IDESC, (third || kb != 0) ? 1u : 0u);
           mma_commit(&w_empty[sw]);
         }
         mma_commit(d23_ready);
@@ -253,8 +251,12 @@ swin_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       named_bar_sync(1, SMF_EPI_THREADS);
       const float var = ((st_sq[q] + st_sq[128 + q]) + (st_sq[256 + q] + st_sq[384 + q])) * (1.0f / SMF_C);
       const float rstd = rsqrtf(var + SMF_EPS);
+      {
+        float a[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_tf32(y[j] * rstd * s_lnw[j] + s_lnb[j]));
+        for (int j = 0; j < 32; ++j) a[j] = y[j] * rstd * s_lnw[j] + s_lnb[j];
+        split_chunk32(a, r);  // this thread's 32 k values of the next GEMM's A operand: 16 hi + 16 lo packed columns
+      }
       tmem_st_32x32(t1, r);
       tmem_st_wait();
       tc_fence_before();
@@ -267,8 +269,12 @@ swin_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       tc_fence_after();
       tmem_ld_32x32(t3, r);
       tmem_ld_wait();
+      {
+        float a[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_tf32(smf_gelu(__uint_as_float(r[j]) + s_b1[j])));
+        for (int j = 0; j < 32; ++j) a[j] = smf_gelu(__uint_as_float(r[j]) + s_b1[j]);
+        split_chunk32(a, r);
+      }
       tmem_st_32x32(t1, r);
       tmem_st_wait();
       tc_fence_before();
@@ -311,7 +317,7 @@ swin_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 using namespace occ;
 
-// out[M,128] = y1 + W2 gelu(W1 LN(y1) + b1) + b2,  y1 = tok + att Wp^T + bp.   att, Wp, W1, W2 tf32-rounded; weights
+// out[M,128] = y1 + W2 gelu(W1 LN(y1) + b1) + b2,  y1 = tok + att Wp^T + bp.   att, Wp, W1, W2 in S32; weights
 // (out, in) row-major as in nn.Linear.
 extern "C" int occ_swin_proj_ffn(const float* att, const float* tok, const float* wp, const float* bp, const float* ln_w,
                                  const float* ln_b, const float* w1, const float* b1, const float* w2, const float* b2,
@@ -347,11 +353,7 @@ extern "C" int occ_swin_proj_ffn(const float* att, const float* tok, const float
   p.tok = tok; p.bp = bp; p.lnw = ln_w; p.lnb = ln_b; p.b1 = b1; p.b2 = b2; p.out = out; p.M = M;
   p.n_tiles = (int)((M + 127) / 128);
   const size_t smem = (size_t)(SMF_ATT_SLOTS + SMF_W_SLOTS + 4) * SMF_SLOT + (5 * SMF_C + 8 * 128) * sizeof(float) + 1024 /*align*/ + 512;
-  static bool configured = false;
-  if (!configured) {
-    OCC_CUDA(cudaFuncSetAttribute(swin_mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  OCC_ENSURE_SMEM(swin_mlp_fused_kernel, smem);
   int grid = sm_count();
   if (grid > p.n_tiles) grid = p.n_tiles;
   swin_mlp_fused_kernel<<<grid, SMF_THREADS, smem, stream>>>(tmA, tmWp, tmW1, tmW2, tmOut, p);

@@ -23,6 +23,7 @@
 // Output layout is channel-last (B, X, Y, Z, C); the Python boundary returns permuted views with the
 // reference's shapes.
 #include "occ_common.cuh"
+#include "occ_ptx.cuh"
 
 namespace occ {
 
@@ -102,7 +103,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 vp_pool_kernel(const int* __restrict__ head, const int* __restrict__ next, int V, int C,
                const float* __restrict__ depth_prob, const float* __restrict__ feat, FastDiv div_dhw, FastDiv div_hw,
-               float* __restrict__ out) {
+               float* __restrict__ out, float* __restrict__ out_split /*optional S32 copy of the grid (conv operand)*/) {
   const int lane = threadIdx.x & 31;
   const int C4 = C >> 2;
   const int batch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -117,6 +118,10 @@ vp_pool_kernel(const int* __restrict__ head, const int* __restrict__ next, int V
     for (uint32_t e = valid & ~occupied; e != 0u; e &= e - 1u) {
       float4* orow = reinterpret_cast<float4*>(out + (size_t)(vb + __ffs(e) - 1) * C);
       for (int c4 = lane; c4 < C4; c4 += 32) __stcs(orow + c4, z4);
+      if (out_split) {  // an all-zero row is its own S32 image
+        float4* srow = reinterpret_cast<float4*>(out_split + (size_t)(vb + __ffs(e) - 1) * C);
+        for (int c4 = lane; c4 < C4; c4 += 32) __stcs(srow + c4, z4);
+      }
     }
   }
   if (occupied == 0u) return;
@@ -168,12 +173,14 @@ vp_pool_kernel(const int* __restrict__ head, const int* __restrict__ next, int V
         }
         float4 acc[4];
         int n[4];
+        bool fin[4];  // the voxel's list ended in this round: its sum is final
         {
           int r0[4], r1[4];
           float w0[4], w1[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             n[u] = __shfl_sync(0xffffffffu, cnt, vi[u]);
+            fin[u] = __shfl_sync(0xffffffffu, cur, vi[u]) == 0;
             r0[u] = __shfl_sync(0xffffffffu, frow[0], vi[u]);
             w0[u] = __shfl_sync(0xffffffffu, wgt[0], vi[u]);
             r1[u] = __shfl_sync(0xffffffffu, frow[1], vi[u]);
@@ -231,6 +238,7 @@ vp_pool_kernel(const int* __restrict__ head, const int* __restrict__ next, int V
               acc[u].x += o.x; acc[u].y += o.y; acc[u].z += o.z; acc[u].w += o.w;
             }
             *dst = acc[u];
+            if (out_split && fin[u]) store_split4(out_split + (size_t)(vb + vi[u]) * C, c4 * 4, acc[u]);
           }
         }
       }
@@ -302,26 +310,28 @@ extern "C" size_t occ_voxel_pool_workspace_bytes(int n_points, int B, int X, int
 }
 
 // Fused lift-splat.  depth_prob (B*N, D, fH*fW) fp32 (already softmaxed), feat_cl (B*N, fH*fW, C) channel-last,
-// geom (B*N*D*fH*fW, 3).  out (B, X, Y, Z, C).  Bookkeeping left in the workspace: vox_id[P], counts[V], head[V], next[P].
-extern "C" int occ_lift_splat(const float* depth_prob, const float* feat_cl, const float* geom, float* out, int B,
-                              int N, int D, int HW, int C, float dx0, float dx1, float dx2, float bx0, float bx1,
-                              float bx2, float nx0, float nx1, float nx2, int X, int Y, int Z, void* workspace, size_t workspace_bytes, int counts_are_zero,
-                              cudaStream_t stream) {
+// geom (B*N*D*fH*fW, 3).  out (B, X, Y, Z, C) fp32; out_split (optional): the same grid in the S32 split format (the
+// operand of the encoder's first conv).  Bookkeeping left in the workspace: vox_id[P], counts[V], head[V], next[P].
+extern "C" int occ_lift_splat(const float* depth_prob, const float* feat_cl, const float* geom, float* out,
+                              float* out_split, int B, int N, int D, int HW, int C, float dx0, float dx1, float dx2,
+                              float bx0, float bx1, float bx2, float nx0, float nx1, float nx2, int X, int Y, int Z,
+                              void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   OCC_REQUIRE(depth_prob && feat_cl && geom && out && workspace);
+  OCC_REQUIRE(!out_split || C % 32 == 0);
   OCC_REQUIRE(B > 0 && N > 0 && D > 0 && HW > 0 && C > 0 && C % 4 == 0 && X > 0 && Y > 0 && Z > 0);
   const long long Pll = (long long)B * N * D * HW, Vll = (long long)B * X * Y * Z;
   OCC_REQUIRE(Pll < (1ll << 31) && Vll < (1ll << 31));
   const int P = (int)Pll, V = (int)Vll;
   VpWorkspace ws;
   OCC_REQUIRE(vp_layout(workspace, P, V, &ws) <= workspace_bytes);
-  (void)counts_are_zero;
   // head[V] and counts[V] are adjacent in the workspace: one memset
   OCC_CUDA(cudaMemsetAsync(ws.head, 0, reinterpret_cast<char*>(ws.counts + V) - reinterpret_cast<char*>(ws.head), stream));
   vp_index_geom_kernel<<<(P + 255) / 256, 256, 0, stream>>>(geom, P, N * D * HW, dx0, dx1, dx2, bx0, bx1, bx2, nx0,
                                                              nx1, nx2, X, Y, Z, ws.vox_id, ws.counts, ws.head, ws.next);
   OCC_LAUNCH_CHECK();
   vp_pool_kernel<0><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, depth_prob, feat_cl,
-                                                                 make_fastdiv((uint32_t)D * HW), make_fastdiv(HW), out);
+                                                                 make_fastdiv((uint32_t)D * HW), make_fastdiv(HW), out,
+                                                                 out_split);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -345,7 +355,7 @@ extern "C" int occ_bev_pool(const float* feats, const long long* coords, float* 
     OCC_LAUNCH_CHECK();
   }
   vp_pool_kernel<1><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, nullptr, feats, make_fastdiv(1),
-                                                                 make_fastdiv(1), out);
+                                                                 make_fastdiv(1), out, nullptr);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -393,7 +403,7 @@ extern "C" int occ_voxel_pool_geom(const float* feats, const float* geom, float*
                                                              nx0, nx1, nx2, X, Y, Z, ws.vox_id, ws.counts, ws.head, ws.next);
   OCC_LAUNCH_CHECK();
   vp_pool_kernel<1><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, nullptr, feats, make_fastdiv(1),
-                                                                 make_fastdiv(1), out);
+                                                                 make_fastdiv(1), out, nullptr);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -425,7 +435,7 @@ __device__ __forceinline__ void mv3(const float* m, float x, float y, float z, f
 
 __global__ void __launch_bounds__(256)
 lss_geometry_kernel(const float* __restrict__ frustum /*(P,3)*/, int P, const float* __restrict__ rots,
-                    const float* __restrict__ trans, const float* __restrict__ intrins, int intrin_cols,
+                    const float* __restrict__ trans, const float* __restrict__ intrins, int intrin_rows, int intrin_cols,
                     const float* __restrict__ post_rots, const float* __restrict__ post_trans,
                     const float* __restrict__ bda, int bda_dim, int N, float* __restrict__ geom) {
   __shared__ float s_ipr[9], s_comb[9], s_vec[9], s_bda[16];
@@ -433,7 +443,7 @@ lss_geometry_kernel(const float* __restrict__ frustum /*(P,3)*/, int P, const fl
   if (threadIdx.x == 0) {
     inv3x3(post_rots + (size_t)bn * 9, s_ipr);
     float K[9], iK[9];
-    const float* I = intrins + (size_t)bn * 3 * intrin_cols;
+    const float* I = intrins + (size_t)bn * intrin_rows * intrin_cols;  // (3,3), (3,4) or KITTI's 4x4 P2 per camera
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) K[r * 3 + c] = I[r * intrin_cols + c];
     inv3x3(K, iK);
@@ -444,7 +454,7 @@ lss_geometry_kernel(const float* __restrict__ frustum /*(P,3)*/, int P, const fl
     for (int k = 0; k < 3; ++k) {
       s_vec[k] = post_trans[(size_t)bn * 3 + k];
       s_vec[3 + k] = trans[(size_t)bn * 3 + k];
-      s_vec[6 + k] = intrin_cols == 4 ? I[k * 4 + 3] : 0.f;  // KITTI P2 shift (:134-137)
+      s_vec[6 + k] = intrin_cols == 4 ? I[k * 4 + 3] : 0.f;  // KITTI P2 shift (:134-137), rows 0..2 of the last column
     }
     for (int k = 0; k < bda_dim * bda_dim; ++k) s_bda[k] = bda[(size_t)b * bda_dim * bda_dim + k];
   }
@@ -473,13 +483,15 @@ lss_geometry_kernel(const float* __restrict__ frustum /*(P,3)*/, int P, const fl
 }  // namespace occ
 
 extern "C" int occ_lss_geometry(const float* frustum, int P, const float* rots, const float* trans, const float* intrins,
-                                int intrin_cols, const float* post_rots, const float* post_trans, const float* bda,
-                                int bda_dim, int B, int N, float* geom, cudaStream_t stream) {
+                                int intrin_rows, int intrin_cols, const float* post_rots, const float* post_trans,
+                                const float* bda, int bda_dim, int B, int N, float* geom, cudaStream_t stream) {
   OCC_REQUIRE(frustum && rots && trans && intrins && post_rots && post_trans && bda && geom);
   OCC_REQUIRE(P > 0 && B > 0 && N > 0 && (intrin_cols == 3 || intrin_cols == 4) && (bda_dim == 3 || bda_dim == 4));
+  OCC_REQUIRE(intrin_rows >= 3 && intrin_rows <= 4 && intrin_rows <= intrin_cols + 1);
   OCC_REQUIRE((long long)B * N <= 65535);
   dim3 grid((P + 255) / 256, B * N);
-  occ::lss_geometry_kernel<<<grid, 256, 0, stream>>>(frustum, P, rots, trans, intrins, intrin_cols, post_rots, post_trans,
+  occ::lss_geometry_kernel<<<grid, 256, 0, stream>>>(frustum, P, rots, trans, intrins, intrin_rows, intrin_cols, post_rots,
+                                                     post_trans,
                                                      bda, bda_dim, N, geom);
   OCC_LAUNCH_CHECK();
   return OCC_OK;

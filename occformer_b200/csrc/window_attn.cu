@@ -1,5 +1,7 @@
 // Shifted-window multi-head self-attention core over the B*(Z+1) X-Y images of the dual-path encoder, on the
-// 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators and the probability operand in TMEM).
+// 5th-generation tensor cores (tcgen05.mma on split-bf16 operands, three passes per contraction = fp32-faithful, see
+// occ_ptx.cuh; accumulators and the probability operand in TMEM).  qkv arrives in the S32 split format (one 128-byte
+// chunk per (token, head, q|k|v)), the output is written in S32 (A operand of the projection GEMM).
 //
 // Replaces ShiftWindowMSA.forward's pad / roll / mask build / window_partition / window_reverse / roll back /
 // crop and WindowMSA.forward's score pipeline (q*scale, QK^T, + relative-position bias, + shift mask, softmax,
@@ -19,9 +21,10 @@
 // real rows each).  Persistent CTA, 512 threads:
 //   warps 12-15  loaders : cp.async gather of the Q / K / V head slices (128 B per token) into 128B-swizzled
 //                          K-major tiles, 3-stage ring, + the head's relative-position bias and the token metadata
-//   warp 0       MMA     : S = Q K^T (4 x tcgen05.mma 128x128x8, operands in smem), then O = P V (16 x 128x32x8 with
-//                          P read from TMEM and V as an MN-major smem operand (SWIZZLE_128B_BASE32B) -- no transpose
-//                          of V anywhere)
+//   warp 0       MMA     : S = Q K^T (6 x tcgen05.mma 128x128x16: hi*hi + lo*hi + hi*lo over the 32-wide head dim), then
+//                          O' = [P_hi; P_lo] [V_hi | V_lo] (16 x 128x64x16 with P read from TMEM and the V chunk rows as an
+//                          MN-major SWIZZLE_128B operand, N = 64 = hi | lo halves of the head dim -- no transpose of V
+//                          anywhere); O = O'[:, :32] + O'[:, 32:] in the epilogue
 //   warps 4-7 / 8-11     : two softmax warpgroups (even / odd units): tcgen05.ld S row -> scale, bias, shift mask,
 //                          softmax in registers -> tcgen05.st P (block-diagonal: the other window's columns are zero)
 //                          -> after PV: tcgen05.ld O, normalise, scatter 128 B per (token, head) to global.
@@ -45,7 +48,7 @@ constexpr int WA_STAGE_BYTES = 51 * 1024;              // 52224 >= 50840 + 1024,
 constexpr int WA_BIAS_LD = 52;                         // padded bias row pitch (floats): 13 conflict-free LDS.128 per row
 constexpr int WA_BIAS_BYTES = 10240;                   // resident bias of this CTA's head, (49, 52) floats, * log2(e)
 constexpr int WA_THREADS = 512;
-constexpr uint32_t WA_TMEM_COLS = 512;                 // S/P: 2 x 128, O: 2 x 32
+constexpr uint32_t WA_TMEM_COLS = 512;                 // S/P: 2 x 128, O: 2 x 64
 
 struct WinGeom {
   int B, X, Y, Z, C, heads, shift;
@@ -80,8 +83,7 @@ __device__ __forceinline__ long long window_token_row(const WinGeom& g, int img,
 
 __global__ void __launch_bounds__(WA_THREADS, 1)
 window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
-                      const float* __restrict__ bias_pad /*(heads, 2404)*/, float* __restrict__ out, const WinGeom g,
-                      float* __restrict__ dbg /*optional (128, 192) dump of unit 0 of CTA 0*/) {
+                      const float* __restrict__ bias_pad /*(heads, 2404)*/, float* __restrict__ out, const WinGeom g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -173,12 +175,12 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
       named_bar_sync(2, 128);
       // thread l copies 16-byte chunk c = l & 7 of rows (l >> 3) + 16*rr, rr = 0..7, for the three tiles.  (r & 7) and
       // (r & 3) do not depend on rr, so the swizzled chunk offsets are per-thread constants:
-      //   Q, K: K-major SWIZZLE_128B (16-byte chunk c ^ (r & 7));  V: MN-major tf32 operand = SWIZZLE_128B_BASE32B
-      //   (32-byte chunk (c >> 1) ^ (r & 3)) -- the only legal layout for a transposed 32-bit operand
+      //   Q, K: K-major SWIZZLE_128B (16-byte chunk c ^ (r & 7)); V: MN-major bf16 operand, N = 64 (hi | lo of the head
+      //   dim) = one 128-byte row per key, 8-key atoms -- the same SWIZZLE_128B chunk pattern
       {
         const int c = l & 7, rb = l >> 3;
         const int off_qk = (c ^ (rb & 7)) << 4;
-        const int off_v = (((c >> 1) ^ (rb & 3)) << 5) | ((c & 1) << 4);
+        const int off_v = off_qk;
         const float* const* srcp = reinterpret_cast<const float* const*>(st + WA_OFF_SRC);
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
@@ -206,8 +208,8 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
   } else if (warp == 0) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t IDESC_QK = make_idesc_tf32(128, 128, 0, 0);
-      constexpr uint32_t IDESC_PV = make_idesc_tf32(128, HD, 0, 1);  // B = V tile, MN-major (d contiguous)
+      constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 2 * HD, 0, 1);  // B = V tile, MN-major (hi | lo of d contiguous)
       auto do_pv = [&](long long v) {
         const int tb = (int)(v & 1), s = (int)(v % WA_STAGES);
         const uint32_t k = (uint32_t)(v >> 1);
@@ -215,12 +217,16 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         mbar_wait(&o_free[tb], (k & 1) ^ 1);
         tc_fence_after();
         const uint32_t vaddr = smem_u32(smem + (size_t)s * WA_STAGE_BYTES + 2 * WA_TILE);
-        const uint64_t vdesc = make_sw128b32_mn_desc(vaddr, 512, 512);
+        const uint64_t vdesc = make_sw128_desc(vaddr, 1024, 1024);  // MN-major: SBO = stride between 8-key atoms
         const uint32_t p_tmem = tmem_base + tb * 128;
-        const uint32_t o_tmem = tmem_base + 256 + tb * HD;
+        const uint32_t o_tmem = tmem_base + 256 + tb * 2 * HD;
+        // P: four 32-key chunks of 32 columns = [16 packed hi | 16 packed lo]; 16 keys per MMA = two 8-key (1024 B) atoms
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk)  // 8 keys per MMA = two 4-row (512 B) swizzle atoms of V rows
-          mma_tf32_ts(o_tmem, p_tmem + kk * 8, vdesc + (uint64_t)(kk * 64), IDESC_PV, kk != 0);
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t pc = p_tmem + (kk >> 1) * 32 + (kk & 1) * 8;
+          mma_bf16_ts(o_tmem, pc, vdesc + (uint64_t)(kk * 128), IDESC_PV, kk != 0);       // P_hi [V_hi | V_lo]
+          mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);       // P_lo [V_hi | V_lo]
+        }
         mma_commit(&o_ready[tb]);
         mma_commit(&empty_bar[s]);
       };
@@ -232,8 +238,7 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         const uint64_t qdesc = make_sw128_desc(qaddr, 1024, 16);
         const uint64_t kdesc = make_sw128_desc(qaddr + WA_TILE, 1024, 16);
         const uint32_t s_tmem = tmem_base + tb * 128;
-#pragma unroll
-        for (int kk = 0; kk < HD / 8; ++kk) mma_tf32_ss(s_tmem, qdesc + 2 * kk, kdesc + 2 * kk, IDESC_QK, kk != 0);
+        mma_bf16x3_ss(s_tmem, qdesc, kdesc, IDESC_QK, 0u);
         mma_commit(&s_ready[tb]);
       };
       // Polling state machine instead of a fixed QK/PV order: PV(u) must not queue behind the gathers of unit u+1,
@@ -284,10 +289,6 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
       tmem_ld_32x32(s_col, ra);
       tmem_ld_32x32(s_col + 32, rb);
       tmem_ld_wait();
-      if (dbg && u == 0 && blockIdx.x == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { dbg[i * 192 + j] = __uint_as_float(ra[j]); dbg[i * 192 + 32 + j] = __uint_as_float(rb[j]); }
-      }
       // z = (s * scale + bias [- 100]) * log2(e): one FFMA per score (bias pre-multiplied), four independent max chains
       const float sl2 = scale * 1.4426950408889634f, neg = -100.0f * 1.4426950408889634f;
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -321,27 +322,25 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
       }
       const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       float sm4[4] = {0.f, 0.f, 0.f, 0.f};
+      float pa[32], pb[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float p = round_tf32(ex2_approx(__uint_as_float(ra[j]) - m));
+        const float p = ex2_approx(__uint_as_float(ra[j]) - m);
         sm4[j & 3] += p;
-        ra[j] = __float_as_uint(p);
+        pa[j] = p;
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float p = 0.f;
         if (j < WT - 32) {
-          p = round_tf32(ex2_approx(__uint_as_float(rb[j]) - m));
+          p = ex2_approx(__uint_as_float(rb[j]) - m);
           sm4[j & 3] += p;
         }
-        rb[j] = __float_as_uint(p);
+        pb[j] = p;
       }
       const float sum = (sm4[0] + sm4[1]) + (sm4[2] + sm4[3]);
-      if (dbg && u == 0 && blockIdx.x == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { dbg[i * 192 + 64 + j] = __uint_as_float(ra[j]); dbg[i * 192 + 96 + j] = __uint_as_float(rb[j]); }
-        dbg[i * 192 + 160] = sum; dbg[i * 192 + 161] = m; dbg[i * 192 + 162] = (float)my_row; dbg[i * 192 + 163] = (float)my_reg;
-      }
+      split_chunk32(pa, ra);  // P as a TMEM A operand: per 32-key chunk 16 packed hi columns | 16 packed lo columns
+      split_chunk32(pb, rb);
       // P row: own window's 64 key columns, zeros in the other window's 64 columns (block-diagonal)
       tmem_st_32x32(s_col, ra);
       tmem_st_32x32(s_col + 32, rb);
@@ -357,22 +356,21 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
       // ---- epilogue of the same unit once PV has landed
       mbar_wait(&o_ready[tb], k & 1);
       tc_fence_after();
-      tmem_ld_32x32(lane_base + 256 + tb * HD, ra);
+      tmem_ld_32x32(lane_base + 256 + tb * 2 * HD, ra);       // P [V_hi]
+      tmem_ld_32x32(lane_base + 256 + tb * 2 * HD + HD, rb);  // P [V_lo]
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[tb]);
-      if (dbg && u == 0 && blockIdx.x == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dbg[i * 192 + 128 + j] = __uint_as_float(ra[j]);
-      }
       if (t < WT && my_row >= 0) {
         const float inv = 1.0f / sum;
-        float4* dst = reinterpret_cast<float4*>(out + my_row * g.C + h * HD);
+        float o[32];
 #pragma unroll
-        for (int d = 0; d < HD; d += 4)
-          dst[d >> 2] = make_float4(round_tf32(__uint_as_float(ra[d]) * inv), round_tf32(__uint_as_float(ra[d + 1]) * inv),
-                                    round_tf32(__uint_as_float(ra[d + 2]) * inv), round_tf32(__uint_as_float(ra[d + 3]) * inv));
+        for (int d = 0; d < HD; ++d) o[d] = (__uint_as_float(ra[d]) + __uint_as_float(rb[d])) * inv;
+        split_chunk32(o, ra);  // the head's 32 output channels are one S32 chunk of the row
+        uint4* dst = reinterpret_cast<uint4*>(out + my_row * g.C + h * HD);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) dst[d] = make_uint4(ra[4 * d], ra[4 * d + 1], ra[4 * d + 2], ra[4 * d + 3]);
       }
     }
   }
@@ -389,9 +387,7 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
 
 using namespace occ;
 
-static float* g_wattn_dbg = nullptr;
-
-// qkv (rows, 3C) with rows = B*X*Y*(Z+1) token-ordered (voxel tokens then BEV tokens); out (rows, C), tf32-rounded.
+// qkv (rows, 3C) with rows = B*X*Y*(Z+1) token-ordered (voxel tokens then BEV tokens); out (rows, C) in S32 (A operand of the projection GEMM); qkv and qkv_bias in S32.
 // bias_pad = relative_position_bias_table[relative_position_index] arranged (heads, 49*49 padded to 2404 floats).
 extern "C" int occ_window_attention(const float* qkv, const float* qkv_bias, const float* bias_pad, float* out, int B,
                                     int X, int Y, int Z, int C, int heads, int shift, int qkv_head_major,
@@ -409,23 +405,13 @@ extern "C" int occ_window_attention(const float* qkv, const float* qkv_bias, con
   g.nwin = (long long)B * (Z + 1) * g.nWx * g.nWy;
   OCC_REQUIRE(g.nwin < (1ll << 31));
   const size_t smem = (size_t)WA_STAGES * WA_STAGE_BYTES + WA_BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static bool configured = false;
-  if (!configured) {
-    OCC_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  OCC_ENSURE_SMEM(window_attn_tc_kernel, smem);
   const long long npairs = (g.nwin + 1) / 2;
   OCC_REQUIRE(heads <= sm_count());
   long long groups = sm_count() / heads;  // CTA groups of `heads` CTAs, one head each
   if (groups > npairs) groups = npairs;
   const int grid = (int)(groups * heads);
-  window_attn_tc_kernel<<<grid, WA_THREADS, smem, stream>>>(qkv, qkv_bias, bias_pad, out, g, g_wattn_dbg);
+  window_attn_tc_kernel<<<grid, WA_THREADS, smem, stream>>>(qkv, qkv_bias, bias_pad, out, g);
   OCC_LAUNCH_CHECK();
-  return OCC_OK;
-}
-
-// development aid: when set, unit 0 of CTA 0 dumps its score / probability / output rows to this (128,192) buffer
-extern "C" int occ_window_attention_set_debug(float* dbg) {
-  g_wattn_dbg = dbg;
   return OCC_OK;
 }

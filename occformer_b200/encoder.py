@@ -7,9 +7,11 @@
 
 Same constructor kwargs, same ``forward(x (B,C,X,Y,Z)) -> list[Tensor (B,C,X',Y',Z')]``, same ``state_dict``
 keys and shapes (SURVEY.md Appendix B) -- the torch.nn sub-modules below are *parameter containers only*;
-all arithmetic runs in libocc_b200.so (tcgen05 TF32 GEMM / implicit-GEMM conv, fused norm / window
-attention / fusion kernels).  Inference (eval, no autograd) only.  Internally every tensor is channel-last
-(B,X,Y,Z,C); returned tensors are permuted *views* with the reference's shape.
+all arithmetic runs in libocc_b200.so (tcgen05 GEMM / implicit-GEMM conv on split-bf16 operands -- three tensor-core
+passes per contraction, fp32-faithful --, fused norm / window attention / fusion kernels).  Inference (eval, no
+autograd) only.  Internally every tensor is channel-last (B,X,Y,Z,C); tensors that feed a tensor-core contraction are
+kept in the S32 split format (ops.py); returned tensors are fp32 permuted *views* with the reference's shape that carry
+their S32 twin as the attribute ``_occ_s32`` (the next module of this package picks it up instead of re-splitting).
 """
 import torch
 import torch.nn as nn
@@ -132,32 +134,33 @@ class DualpathTransformerBlock(nn.Module):
     # ------------------------------------------------------------------ one-time weight preparation
     @torch.no_grad()
     def _prepare(self):
-        r = ops.round_tf32_
+        sw_ = ops.split_weight
         P = {}
-        P["w_in"], P["k_in"] = ops.repack_conv_weight(self.input_conv[0].weight.detach().float())
+        P["w_in"], P["k_in"] = ops.repack_conv_weight(self.input_conv[0].weight)
         if self.stride > 1:
-            P["w_ds"], P["k_ds"] = ops.repack_conv_weight(self.downsample[0].weight.detach().float())
+            P["w_ds"], P["k_ds"] = ops.repack_conv_weight(self.downsample[0].weight)
         msa = self.bev_encoder.attn.w_msa
-        # qkv rows permuted to [head][q|k|v][32]: the attention kernel then reads one contiguous 384-byte run per
-        # (token, head) instead of three 128-byte slices C floats apart
+        # qkv rows permuted to [head][q|k|v][32]: one S32 chunk per (token, head, q|k|v), the three chunks of a head
+        # adjacent -- the attention kernel reads one contiguous 384-byte run per (token, head)
         perm = ops.qkv_head_major_perm(msa.qkv.weight.shape[1], self.num_heads, msa.qkv.weight.device)
-        P["w_qkv"] = r(msa.qkv.weight.detach().float()[perm].clone().contiguous())
+        P["w_qkv"] = sw_(msa.qkv.weight.detach().float()[perm])
         P["b_qkv"] = msa.qkv.bias.detach().float()[perm].clone().contiguous()
-        P["w_proj"] = r(msa.proj.weight.detach().float().clone().contiguous())
+        P["b_qkv_s"] = sw_(P["b_qkv"].view(1, -1)).view(-1)  # q/k/v of the zero pad tokens, as the kernel's operand rows
+        P["w_proj"] = sw_(msa.proj.weight)
         ffn = self.bev_encoder.ffn.layers
-        P["w_f1"] = r(ffn[0][0].weight.detach().float().clone().contiguous())
-        P["w_f2"] = r(ffn[1].weight.detach().float().clone().contiguous())
+        P["w_f1"] = sw_(ffn[0][0].weight)
+        P["w_f2"] = sw_(ffn[1].weight)
         table = msa.relative_position_bias_table.detach().float()
         idx = msa.relative_position_index.view(-1)
         dense = table[idx].view(49, 49, -1).permute(2, 0, 1).reshape(-1, 49 * 49)  # (heads, 49*49)
         P["bias_pad"] = torch.nn.functional.pad(dense, (0, 2404 - 49 * 49)).contiguous()  # 16-byte multiple per head
         a = self.aspp
-        P["w_a_in"], P["k1"] = ops.repack_conv_weight(a.input_conv[0].weight.detach().float())
+        P["w_a_in"], P["k1"] = ops.repack_conv_weight(a.input_conv[0].weight)
         for i in (1, 2, 3, 4):
-            P[f"w_a{i}"], P[f"k_a{i}"] = ops.repack_conv_weight(getattr(a.aspp, f"aspp{i}").atrous_conv.weight.detach().float())
+            P[f"w_a{i}"], P[f"k_a{i}"] = ops.repack_conv_weight(getattr(a.aspp, f"aspp{i}").atrous_conv.weight)
         P["w_gap"] = a.aspp.global_avg_pool[1].weight.detach().float().reshape(a.aspp.global_avg_pool[1].weight.shape[0], -1).contiguous()
-        P["w_a_c1"], _ = ops.repack_conv_weight(a.aspp.conv1.weight.detach().float())
-        P["w_a_out"], _ = ops.repack_conv_weight(a.output_conv[0].weight.detach().float())
+        P["w_a_c1"], _ = ops.repack_conv_weight(a.aspp.conv1.weight)
+        P["w_a_out"], _ = ops.repack_conv_weight(a.output_conv[0].weight)
         P["coeff_w"] = self.combine_coeff.weight.detach().float().reshape(-1).contiguous()
         P["coeff_b"] = float(self.combine_coeff.bias.detach().float().item()) if self.combine_coeff.bias is not None else 0.0
         self._prep = P
@@ -165,27 +168,31 @@ class DualpathTransformerBlock(nn.Module):
 
     # ------------------------------------------------------------------ forward on channel-last tensors
     @torch.no_grad()
-    def forward_cl(self, x_cl):
-        """x_cl (B,X,Y,Z,Cin) contiguous channel-last -> (B,X',Y',Z',C) contiguous channel-last."""
+    def forward_cl(self, x_cl, x_s=None, want_f32=True):
+        """x_cl (B,X,Y,Z,Cin) contiguous channel-last fp32 (may be None when its S32 twin x_s is given)
+        -> (out fp32 (B,X',Y',Z',C) | None, out S32): the S32 output feeds the next block / the neck, the fp32 one is
+        only produced when the caller wants it (stage outputs)."""
         P = self._prep or self._prepare()
-        B, X0, Y0, Z0, Cin = x_cl.shape
+        if x_s is None:
+            x_s = ops.to_split(x_cl)
+        B, X0, Y0, Z0, Cin = x_s.shape
         C, G, s = self.channels, self.groups, self.stride
-        dev = x_cl.device
+        dev = x_s.device
         stats = torch.zeros((10, B, 32, 2), dtype=torch.float64, device=dev)
         # (A4) Conv3d 3x3x3 (+stride) -> raw output + GroupNorm statistics from the GEMM epilogue
-        y_raw = ops.conv(x_cl, P["w_in"], P["k_in"], stride=s, gn_stats=stats[0], cpg=C // G)
+        y_raw = ops.conv(x_s, P["w_in"], P["k_in"], stride=s, gn_stats=stats[0], cpg=C // G)
         _, X, Y, Z, _ = y_raw.shape
         XY = X * Y
         nvox = B * XY * Z
         ic, sw = self.input_conv, self.bev_encoder
-        # (A4/A5/A6) GN + ReLU, Z-mean BEV token, LayerNorm1 -- one pass
+        # (A4/A5/A6) GN + ReLU, Z-mean BEV token, LayerNorm1 -- one pass; tok fp32 (residual), tokn S32 (GEMM operand)
         tok, tokn = ops.gn_relu_zmean_ln(y_raw.view(nvox, C), stats[0], ic[1].weight, ic[1].bias, sw.norm1.weight,
                                          sw.norm1.bias, B, XY, Z, C, G)
         msa = sw.attn.w_msa
         # (A8) QKV projection of every token (pad tokens are synthesised from the bias inside the attention kernel)
-        qkv = ops.gemm(tokn, P["w_qkv"], bias=P["b_qkv"], round_out=True)
+        qkv = ops.gemm(tokn, P["w_qkv"], bias=P["b_qkv"], split_out=True)
         # (A7/A8) shifted-window attention core, gathers/scatters windows in place
-        att = ops.window_attention(qkv, P["b_qkv"], P["bias_pad"], B, X, Y, Z, C, self.num_heads, self.shift,
+        att = ops.window_attention(qkv, P["b_qkv_s"], P["bias_pad"], B, X, Y, Z, C, self.num_heads, self.shift,
                                    head_major=True)
         # proj + residual, LayerNorm2, FFN (GELU) + residual  (A6)
         ffn = sw.ffn.layers
@@ -195,21 +202,22 @@ class DualpathTransformerBlock(nn.Module):
                                    ffn[0][0].bias, P["w_f2"], ffn[1].bias)
         else:
             y1 = ops.gemm(att, P["w_proj"], bias=msa.proj.bias, residual=tok)
-            y1n = ops.layernorm(y1, sw.norm2.weight, sw.norm2.bias, round_out=True)
-            h = ops.gemm(y1n, P["w_f1"], bias=ffn[0][0].bias, act=2, round_out=True)
+            y1n = ops.layernorm(y1, sw.norm2.weight, sw.norm2.bias, split_out=True)
+            h = ops.gemm(y1n, P["w_f1"], bias=ffn[0][0].bias, act=2, split_out=True)
             y2 = ops.gemm(h, P["w_f2"], bias=ffn[1].bias, residual=y1)
         x_vox, x_bev = y2[:nvox], y2[nvox:]
         # (A9) BottleNeckASPP on the BEV tokens (B, X, Y, 1, C)
         bev_out = self._aspp(x_bev, B, X, Y, C, stats, P)
         # (A10) fusion + skip connection
         if s > 1:
-            id_raw = ops.conv(x_cl, P["w_ds"], P["k_ds"], stride=s, gn_stats=stats[9], cpg=C // G)
-            out = ops.dualpath_fuse(x_vox, bev_out, P["coeff_w"], P["coeff_b"], id_raw.view(nvox, C), B, XY, Z, C,
-                                    id_stats=stats[9], id_w=self.downsample[1].weight, id_b=self.downsample[1].bias,
-                                    groups=G)
+            id_raw = ops.conv(x_s, P["w_ds"], P["k_ds"], stride=s, gn_stats=stats[9], cpg=C // G)
+            out, out_s = ops.dualpath_fuse(x_vox, bev_out, P["coeff_w"], P["coeff_b"], id_raw.view(nvox, C), B, XY, Z, C,
+                                           id_stats=stats[9], id_w=self.downsample[1].weight,
+                                           id_b=self.downsample[1].bias, groups=G, want_f32=want_f32)
         else:
-            out = ops.dualpath_fuse(x_vox, bev_out, P["coeff_w"], P["coeff_b"], x_cl.view(nvox, C), B, XY, Z, C)
-        return out.view(B, X, Y, Z, C)
+            out, out_s = ops.dualpath_fuse(x_vox, bev_out, P["coeff_w"], P["coeff_b"], x_s.view(nvox, C), B, XY, Z, C,
+                                           identity_split=True, want_f32=want_f32)
+        return (out.view(B, X, Y, Z, C) if out is not None else None), out_s.view(B, X, Y, Z, C)
 
     def _aspp(self, x_bev, B, X, Y, C, stats, P):
         a = self.aspp
@@ -217,39 +225,52 @@ class DualpathTransformerBlock(nn.Module):
         XY = X * Y
         gi, go = a.inner_groups, a.outer_groups
 
-        def conv2d(t, w, k, dil=1, st=None, cpg=0):
-            cin = t.shape[-1]
-            return ops.conv(t.view(B, X, Y, 1, cin), w, k, dil=dil, gn_stats=st, cpg=cpg).view(B * XY, -1)
+        def conv2d(t_s, w, k, dil=1, st=None, cpg=0):
+            cin = t_s.shape[-1]
+            return ops.conv(t_s.view(B, X, Y, 1, cin), w, k, dil=dil, gn_stats=st, cpg=cpg).view(B * XY, -1)
 
-        t = conv2d(x_bev, P["w_a_in"], (1, 1, 1), st=stats[1], cpg=ch // go)
-        y = ops.gn_apply(t, stats[1], a.input_conv[1].weight, a.input_conv[1].bias, XY, go)
-        cat = torch.empty((B * XY, 5 * ch), dtype=torch.float32, device=x_bev.device)
+        t = conv2d(ops.to_split(x_bev), P["w_a_in"], (1, 1, 1), st=stats[1], cpg=ch // go)
+        y, y_s = ops.gn_apply(t, stats[1], a.input_conv[1].weight, a.input_conv[1].bias, XY, go, want_split=True)
+        cat_s = torch.empty((B * XY, 5 * ch), dtype=torch.float32, device=x_bev.device)  # S32 concat buffer
         for i, d in zip((1, 2, 3, 4), a.dilations):
             m = getattr(a.aspp, f"aspp{i}")
             k = P[f"k_a{i}"]
-            t = conv2d(y, P[f"w_a{i}"], k, dil=d if k[0] == 3 else 1, st=stats[1 + i], cpg=ch // gi)
-            ops.gn_apply(t, stats[1 + i], m.bn.weight, m.bn.bias, XY, gi, out=cat, out_off=(i - 1) * ch, round_out=True)
+            t = conv2d(y_s, P[f"w_a{i}"], k, dil=d if k[0] == 3 else 1, st=stats[1 + i], cpg=ch // gi)
+            ops.gn_apply(t, stats[1 + i], m.bn.weight, m.bn.bias, XY, gi, want_f32=False, split_into=cat_s,
+                         out_off=(i - 1) * ch)
         gap = a.aspp.global_avg_pool
-        ops.aspp_gap_branch(y, P["w_gap"], gap[2].weight, gap[2].bias, cat, B, XY, gi, 4 * ch)
-        t = conv2d(cat, P["w_a_c1"], (1, 1, 1), st=stats[6], cpg=ch // gi)
-        y3 = ops.gn_apply(t, stats[6], a.aspp.bn1.weight, a.aspp.bn1.bias, XY, gi, residual=y)
-        t = conv2d(y3, P["w_a_out"], (1, 1, 1), st=stats[7], cpg=C // go)
-        return ops.gn_apply(t, stats[7], a.output_conv[1].weight, a.output_conv[1].bias, XY, go, residual=x_bev)
+        ops.aspp_gap_branch(y, P["w_gap"], gap[2].weight, gap[2].bias, cat_s, B, XY, gi, 4 * ch)
+        t = conv2d(cat_s, P["w_a_c1"], (1, 1, 1), st=stats[6], cpg=ch // gi)
+        _, y3_s = ops.gn_apply(t, stats[6], a.aspp.bn1.weight, a.aspp.bn1.bias, XY, gi, residual=y, want_f32=False,
+                               want_split=True)
+        t = conv2d(y3_s, P["w_a_out"], (1, 1, 1), st=stats[7], cpg=C // go)
+        bev_out, _ = ops.gn_apply(t, stats[7], a.output_conv[1].weight, a.output_conv[1].bias, XY, go, residual=x_bev)
+        return bev_out
 
     def forward(self, x):
-        return to_reference_layout(self.forward_cl(to_channel_last(x)))
+        out, out_s = self.forward_cl(*to_channel_last(x))
+        return to_reference_layout(out, out_s)
 
 
 def to_channel_last(x):
-    """(B,C,X,Y,Z) reference-layout tensor (any strides) -> contiguous (B,X,Y,Z,C).  Zero-copy when x is
-    already a permuted view of channel-last memory (what this package's own modules hand around)."""
+    """(B,C,X,Y,Z) reference-layout tensor (any strides) -> (contiguous (B,X,Y,Z,C) fp32, its S32 twin or None).
+    Zero-copy when x is already a permuted view of channel-last memory (what this package's own modules hand around);
+    the S32 twin is the ``_occ_s32`` attribute such a view carries."""
     if not x.is_cuda:
         raise RuntimeError("occformer_b200: the encoder runs on CUDA tensors only (no CPU fallback)")
-    return x.float().permute(0, 2, 3, 4, 1).contiguous()
+    twin = getattr(x, "_occ_s32", None)
+    x_cl = x.float().permute(0, 2, 3, 4, 1).contiguous()
+    if twin is not None and (twin.shape != x_cl.shape or twin.device != x_cl.device):
+        twin = None
+    return x_cl, twin
 
 
-def to_reference_layout(x_cl):
-    return x_cl.permute(0, 4, 1, 2, 3)
+def to_reference_layout(x_cl, x_s=None):
+    """channel-last (B,X,Y,Z,C) -> the reference's (B,C,X,Y,Z) as a permuted view; the S32 twin rides along."""
+    v = x_cl.permute(0, 4, 1, 2, 3)
+    if x_s is not None:
+        v._occ_s32 = x_s
+    return v
 
 
 @BACKBONES.register_module()
@@ -276,14 +297,16 @@ class OccupancyEncoder(nn.Module):
         self.with_cp = with_cp
 
     @torch.no_grad()
-    def forward_cl(self, x_cl):
+    def forward_cl(self, x_cl, x_s=None):
+        """-> list of (fp32, S32) channel-last pairs, one per out_indices stage."""
         res = []
         for index, layer in enumerate(self.layers):
-            for blk in layer:
-                x_cl = blk.forward_cl(x_cl)
+            for bi, blk in enumerate(layer):
+                wanted = index in self.out_indices and bi == len(layer) - 1
+                x_cl, x_s = blk.forward_cl(x_cl, x_s, want_f32=wanted)
             if index in self.out_indices:
-                res.append(x_cl)
+                res.append((x_cl, x_s))
         return res
 
     def forward(self, x):
-        return [to_reference_layout(t) for t in self.forward_cl(to_channel_last(x))]
+        return [to_reference_layout(f, t) for f, t in self.forward_cl(*to_channel_last(x))]

@@ -11,9 +11,10 @@ Same constructor kwargs, same ``forward(voxel_feats, img_metas) -> (cls_pred_lis
 ``state_dict`` keys.  Inference only: losses / assigner / point sampling (training side,
 RNG driven) are not part of this path and ``forward_train`` raises.
 
-All arithmetic runs in libocc_b200.so: tcgen05 TF32 GEMMs for the voxel-side contractions (K/V projections of the
-three memories, batched over the layers that share a level; mask_embed x mask_feature einsum) and fused fp32
-kernels for the 100-query side (csrc/head_ops.cu).  ``simple_test`` never materialises the reference's ten
+All arithmetic runs in libocc_b200.so: tcgen05 GEMMs on split-bf16 operands (three passes, fp32-faithful) for the
+voxel-side contractions (K/V projections of the three memories, batched over the layers that share a level;
+mask_embed x mask_feature einsum; masked cross attention) and fused fp32 kernels for the 100-query side
+(csrc/head_ops.cu).  ``simple_test`` never materialises the reference's ten
 (B,Q,X,Y,Z) mask tensors nor the upsampled (B,Q,*occ_size) logits: masks live query-last (B,S,Q), are pooled /
 thresholded in place, and the final upsample + sigmoid + class mix is one kernel.
 """
@@ -23,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .registry import HEADS
+from .registry import HEADS, POSITIONAL_ENCODING
 
 
 def _get(cfg, key, default=None):
@@ -75,6 +76,7 @@ class _Decoder(nn.Module):
         self.embed_dims = E
 
 
+@POSITIONAL_ENCODING.register_module()
 class SinePositionalEncoding3D(nn.Module):
     """positional_encoding.py:11-108 with an all-False mask: the encoding depends on the grid size only, so it is
     computed once per size by occ_sine_pos3d and cached."""
@@ -193,8 +195,8 @@ class _Mask2FormerOccBase(nn.Module):
                 n2w=V(layer.norms[2].weight), n2b=V(layer.norms[2].bias)))
         P["slots"] = slots
         cat = lambda ts: torch.cat([t.detach().float() for t in ts], 0).contiguous()  # noqa: E731
-        P["kw"] = [ops.round_tf32_(cat(w)) if w else None for w in kw]
-        P["vw"] = [ops.round_tf32_(cat(w)) if w else None for w in vw]
+        P["kw"] = [ops.split_weight(cat(w)) if w else None for w in kw]
+        P["vw"] = [ops.split_weight(cat(w)) if w else None for w in vw]
         P["kb"] = [cat(b) if b else None for b in kb]
         P["vb"] = [cat(b) if b else None for b in vb]
         self._prep = P
@@ -226,9 +228,14 @@ class _Mask2FormerOccBase(nn.Module):
         grid = tuple(mf.shape[-3:])
         V = grid[0] * grid[1] * grid[2]
         scale = 32 ** -0.5
-        # mask features: channel-last, tf32-rounded once (A operand of the 1+L mask GEMMs)
-        x, cl = self._rows(mf)
-        mf_r, _ = ops.head_prep(x, cl)
+        # mask features: channel-last S32, produced once (operand of the 1+L mask GEMMs); the neck of this package hands
+        # the S32 twin over directly
+        twin = getattr(mf, "_occ_s32", None)
+        if twin is not None and tuple(twin.shape) == (B, *grid, E) and twin.device == mf.device:
+            mf_r = twin.view(B, V, E)
+        else:
+            x, cl = self._rows(mf)
+            mf_r, _ = ops.head_prep(x, cl)
         # memories: + level embed (+ positional encoding for K); K/V of every layer sharing the level in one GEMM each
         sizes, Kp, Vp, lds = [], [], [], []
         for l in range(nl):
@@ -241,9 +248,9 @@ class _Mask2FormerOccBase(nn.Module):
             if P["kw"][l] is None:
                 Kp.append(None), Vp.append(None), lds.append(0)
                 continue
-            # tf32-rounded outputs: they are tensor-core operands of the cross-attention kernel
-            Kp.append(ops.gemm(kpos_r.view(B * S, E), P["kw"][l], bias=P["kb"][l], round_out=True))
-            Vp.append(ops.gemm(mem_r.view(B * S, E), P["vw"][l], bias=P["vb"][l], round_out=True))
+            # S32 outputs (one chunk per (key, head)): tensor-core operands of the cross-attention kernel
+            Kp.append(ops.gemm(kpos_r.view(B * S, E), P["kw"][l], bias=P["kb"][l], split_out=True))
+            Vp.append(ops.gemm(mem_r.view(B * S, E), P["vw"][l], bias=P["vb"][l], split_out=True))
             lds.append(P["kw"][l].shape[0])
         query = self.query_feat.weight.detach().float().unsqueeze(0).expand(B, Q, E).reshape(B * Q, E).contiguous()
         qpos = P["query_pos"]

@@ -16,8 +16,9 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(t=None):
+    """the current torch stream of the tensor's device (tensors of one call share a device, checked by _chk)"""
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device if t is not None else None).cuda_stream)
 
 
 def _chk(t, name, dtype=torch.float32):
@@ -27,26 +28,61 @@ def _chk(t, name, dtype=torch.float32):
         raise RuntimeError(f"occformer_b200: {name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise RuntimeError(f"occformer_b200: {name} must be contiguous")
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"occformer_b200: {name} lives on {t.device} but the current device is "
+                           f"cuda:{torch.cuda.current_device()} (wrap the call in torch.cuda.device(...))")
     return t
 
 
-def round_tf32_(w):
-    """Round an fp32 tensor to the nearest tf32 value (ties away), in place.  Applied once to weights so the
-    tensor cores (which drop the low 13 mantissa bits) see correctly *rounded* operands."""
-    i = w.view(torch.int32)
-    i.add_(0x1000).bitwise_and_(-8192)  # 0xFFFFE000
-    return w
+# ----------------------------------------------------------------------------------------------- S32 split format
+# Operands of every tensor-core contraction are fp32 values stored as bf16 hi | lo halves per 32-column chunk (csrc/
+# occ_ptx.cuh, include/occ_b200.h): same bytes and row pitch as the fp32 tensor, ~1e-5 relative error after the three
+# bf16 passes.  Weights are split once at load time (torch ops below), activations by the producing kernel's epilogue.
+def split_weight(w):
+    """(N, K) fp32 torch tensor (any device), K % 32 == 0 -> the same tensor in S32 (fp32 container, same shape)."""
+    w = w.detach().float().contiguous()
+    N, K = w.shape
+    assert K % 32 == 0, f"S32 rows need K % 32 == 0, got {K}"
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    packed = torch.cat([hi.view(N, K // 32, 32), lo.view(N, K // 32, 32)], dim=2).contiguous()  # (N, K/32, 64) bf16
+    return packed.view(torch.float32).reshape(N, K)
+
+
+def unsplit_weight(ws):
+    """inverse of split_weight (tests / debugging): S32 -> fp32 values hi + lo."""
+    N, K = ws.shape
+    p = ws.contiguous().view(torch.bfloat16).view(N, K // 32, 64).float()
+    return (p[:, :, :32] + p[:, :, 32:]).reshape(N, K)
+
+
+def to_split(x):
+    """fp32 CUDA tensor (..., C), C % 32 == 0 -> S32 (device kernel)."""
+    _chk(x, "x")
+    C = x.shape[-1]
+    out = torch.empty_like(x)
+    check(lib().occ_split_rows(_ptr(x), _ptr(out), x.numel() // C, C, _stream(x)), "occ_split_rows")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+def from_split(x):
+    _chk(x, "x")
+    C = x.shape[-1]
+    out = torch.empty_like(x)
+    check(lib().occ_unsplit_rows(_ptr(x), _ptr(out), x.numel() // C, C, _stream(x)), "occ_unsplit_rows")
+    LAUNCH_COUNT[0] += 1
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- voxel pooling
 class VoxelPoolWorkspace:
-    def __init__(self, n_points, B, X, Y, Z, device):
-        l = lib()
-        self.key = (n_points, B, X, Y, Z)
-        self.nbytes = l.occ_voxel_pool_workspace_bytes(n_points, B, X, Y, Z)
-        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+    """View of the pooling workspace for one call with n_points points (bookkeeping left behind by the kernels)."""
+
+    def __init__(self, buf, n_points, B, X, Y, Z):
         offs = [ctypes.c_size_t() for _ in range(4)]
-        l.occ_voxel_pool_workspace_layout(n_points, B, X, Y, Z, *[ctypes.byref(o) for o in offs])
+        lib().occ_voxel_pool_workspace_layout(n_points, B, X, Y, Z, *[ctypes.byref(o) for o in offs])
+        self.buf, self.nbytes = buf, buf.numel()
         self.off_counts, self.off_head, self.off_next, self.off_vox_id = (o.value for o in offs)
         self.V = B * X * Y * Z
         self.P = n_points
@@ -74,15 +110,30 @@ class VoxelPoolWorkspace:
         return self._ints(self.off_vox_id, self.P)
 
 
-_ws_cache = {}
+_ws_cache = {}  # (B, X, Y, Z, device) -> (uint8 buffer, point capacity): one grow-only buffer per grid
 
 
 def _workspace(n_points, B, X, Y, Z, device):
-    key = (n_points, B, X, Y, Z, str(device))
-    ws = _ws_cache.get(key)
+    key = (B, X, Y, Z, str(device))
+    n_points = max(int(n_points), 1)
+    ent = _ws_cache.get(key)
+    if ent is None or ent[1] < n_points:
+        cap = 1 << (n_points - 1).bit_length()  # next power of two: the drop-in bev_pool sees a different n every sample
+        nbytes = lib().occ_voxel_pool_workspace_bytes(cap, B, X, Y, Z)
+        ent = (torch.zeros(nbytes, dtype=torch.uint8, device=device), cap)
+        _ws_cache[key] = ent
+    return VoxelPoolWorkspace(ent[0], n_points, B, X, Y, Z)
+
+
+_conv_ws = {}  # (device, stream) -> zeroed buffer: split-K ordering counters of occ_conv_bf16x3
+
+
+def _conv_workspace(device):
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _conv_ws.get(key)
     if ws is None:
-        ws = VoxelPoolWorkspace(n_points, B, X, Y, Z, device)
-        _ws_cache[key] = ws
+        ws = torch.zeros(lib().occ_conv_workspace_bytes(), dtype=torch.uint8, device=device)
+        _conv_ws[key] = ws
     return ws
 
 
@@ -93,8 +144,8 @@ def lss_geometry(frustum, rots, trans, intrins, post_rots, post_trans, bda):
     f = lambda t: _chk(t.float().contiguous(), "camera matrix")  # noqa: E731
     geom = torch.empty((B, N, D, fH, fW, 3), dtype=torch.float32, device=frustum.device)
     fr, r, t, k, pr, pt, bd = f(frustum), f(rots), f(trans), f(intrins), f(post_rots), f(post_trans), f(bda)
-    check(lib().occ_lss_geometry(_ptr(fr), D * fH * fW, _ptr(r), _ptr(t), _ptr(k), k.shape[-1], _ptr(pr), _ptr(pt),
-                                 _ptr(bd), bd.shape[-1], B, N, _ptr(geom), _stream()), "occ_lss_geometry")
+    check(lib().occ_lss_geometry(_ptr(fr), D * fH * fW, _ptr(r), _ptr(t), _ptr(k), k.shape[-2], k.shape[-1], _ptr(pr),
+                                 _ptr(pt), _ptr(bd), bd.shape[-1], B, N, _ptr(geom), _stream(geom)), "occ_lss_geometry")
     LAUNCH_COUNT[0] += 1
     return geom
 
@@ -112,8 +163,8 @@ def lift_prologue(depth_logits, img_feat):
     return prob, feat_cl
 
 
-def lift_splat(depth_prob, feat_cl, geom, B, N, dx, bx, nx, grid, return_workspace=False):
-    """Fused lift-splat.  Returns the channel-last grid (B,X,Y,Z,C)."""
+def lift_splat(depth_prob, feat_cl, geom, B, N, dx, bx, nx, grid, return_workspace=False, with_split=False):
+    """Fused lift-splat.  Returns the channel-last grid (B,X,Y,Z,C) [, its S32 copy when with_split]."""
     _chk(depth_prob, "depth_prob"), _chk(feat_cl, "feat_cl"), _chk(geom, "geom")
     BN, D, fH, fW = depth_prob.shape
     C = feat_cl.shape[-1]
@@ -122,11 +173,13 @@ def lift_splat(depth_prob, feat_cl, geom, B, N, dx, bx, nx, grid, return_workspa
     assert geom.numel() == 3 * P
     ws = _workspace(P, B, X, Y, Z, geom.device)
     out = torch.empty((B, X, Y, Z, C), dtype=torch.float32, device=geom.device)
+    out_s = torch.empty_like(out) if with_split else None
     f = [float(v) for v in (*dx, *bx, *nx)]
-    check(lib().occ_lift_splat(_ptr(depth_prob), _ptr(feat_cl), _ptr(geom), _ptr(out), B, N, D, fH * fW, C, *f, X, Y,
-                               Z, _ptr(ws.buf), ws.nbytes, 0, _stream()), "occ_lift_splat")
+    check(lib().occ_lift_splat(_ptr(depth_prob), _ptr(feat_cl), _ptr(geom), _ptr(out), _ptr(out_s), B, N, D, fH * fW, C,
+                               *f, X, Y, Z, _ptr(ws.buf), ws.nbytes, _stream(geom)), "occ_lift_splat")
     LAUNCH_COUNT[0] += 3
-    return (out, ws) if return_workspace else out
+    res = (out, out_s) if with_split else out
+    return (res, ws) if return_workspace else res
 
 
 def voxel_pool_geom(feats, geom, B, dx, bx, nx, grid, return_workspace=False):
@@ -146,7 +199,7 @@ def voxel_pool_geom(feats, geom, B, dx, bx, nx, grid, return_workspace=False):
 def bev_pool_channel_last(feats, coords, B, X, Y, Z, return_workspace=False):
     _chk(feats, "feats"), _chk(coords, "coords", torch.int64)
     n, C = feats.shape
-    ws = _workspace(max(n, 1), B, X, Y, Z, feats.device)
+    ws = _workspace(n, B, X, Y, Z, feats.device)
     out = torch.empty((B, X, Y, Z, C), dtype=torch.float32, device=feats.device)
     check(lib().occ_bev_pool(_ptr(feats), _ptr(coords), _ptr(out), n, C, B, X, Y, Z, _ptr(ws.buf), ws.nbytes,
                              _stream()), "occ_bev_pool")
@@ -155,8 +208,9 @@ def bev_pool_channel_last(feats, coords, B, X, Y, Z, return_workspace=False):
 
 
 # ----------------------------------------------------------------------------------------------- GEMM / conv
-def gemm(a, w, bias=None, residual=None, act=0, round_out=False, out=None):
-    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual).  a, w should already be tf32-rounded."""
+def gemm(a, w, bias=None, residual=None, act=0, split_out=False, out=None):
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual).  a, w in S32 (to_split / split_weight / a producer's
+    split output); out fp32, or S32 when split_out (operand of the next contraction)."""
     _chk(a, "a"), _chk(w, "w")
     M, K = a.shape
     N = w.shape[0]
@@ -170,24 +224,24 @@ def gemm(a, w, bias=None, residual=None, act=0, round_out=False, out=None):
     if residual is not None:
         _chk(residual, "residual")
         assert residual.shape == (M, N)
-    check(lib().occ_gemm_tf32(_ptr(a), _ptr(w), _ptr(out), M, N, K, _ptr(bias), _ptr(residual), act, int(round_out),
-                              None, 0, 0, _stream()), "occ_gemm_tf32")
+    check(lib().occ_gemm_bf16x3(_ptr(a), _ptr(w), _ptr(out), M, N, K, _ptr(bias), _ptr(residual), act, int(split_out),
+                                None, 0, 0, _stream(a)), "occ_gemm_bf16x3")
     LAUNCH_COUNT[0] += 1
     return out
 
 
 def repack_conv_weight(w):
-    """(Cout, Cin, kx, ky[, kz]) -> (Cout, taps*Cin) tap-major [(kx*KY + ky)*KZ + kz][cin], tf32-rounded."""
+    """(Cout, Cin, kx, ky[, kz]) -> (Cout, taps*Cin) tap-major [(kx*KY + ky)*KZ + kz][cin] in S32 (Cin % 32 == 0)."""
     if w.dim() == 4:
         w = w.unsqueeze(-1)
     Cout, Cin, KX, KY, KZ = w.shape
-    w2 = w.permute(0, 2, 3, 4, 1).reshape(Cout, KX * KY * KZ * Cin).contiguous().clone()
-    return round_tf32_(w2), (KX, KY, KZ)
+    w2 = w.detach().float().permute(0, 2, 3, 4, 1).reshape(Cout, KX * KY * KZ * Cin)
+    return split_weight(w2), (KX, KY, KZ)
 
 
-def conv(x_cl, w2, ksize, stride=1, dil=1, bias=None, residual=None, act=0, round_out=False, gn_stats=None, cpg=0):
-    """x_cl (B,X,Y,Z,Cin) channel-last; w2 from repack_conv_weight; returns (B,Xo,Yo,Zo,Cout) channel-last raw
-    output.  gn_stats: zero-initialised double tensor (B, groups, 2) receiving (sum, sumsq)."""
+def conv(x_cl, w2, ksize, stride=1, dil=1, bias=None, residual=None, act=0, split_out=False, gn_stats=None, cpg=0):
+    """x_cl (B,X,Y,Z,Cin) channel-last S32; w2 from repack_conv_weight; returns (B,Xo,Yo,Zo,Cout) channel-last raw
+    output (fp32, or S32 when split_out).  gn_stats: zero-initialised double tensor (B, groups, 2) receiving (sum, sumsq)."""
     _chk(x_cl, "x_cl"), _chk(w2, "w2")
     B, X, Y, Z, Cin = x_cl.shape
     KX, KY, KZ = ksize
@@ -202,9 +256,10 @@ def conv(x_cl, w2, ksize, stride=1, dil=1, bias=None, residual=None, act=0, roun
     out = torch.empty((B, Xo, Yo, Zo, Cout), dtype=torch.float32, device=x_cl.device)
     if gn_stats is not None:
         _chk(gn_stats, "gn_stats", torch.float64)
-    check(lib().occ_conv_tf32(_ptr(x_cl), _ptr(w2), _ptr(out), B, X, Y, Z, Cin, Cout, KX, KY, KZ, stride, dil,
-                              _ptr(bias), _ptr(residual), act, int(round_out), _ptr(gn_stats), cpg, _stream()),
-          "occ_conv_tf32")
+    ws = _conv_workspace(x_cl.device)
+    check(lib().occ_conv_bf16x3(_ptr(x_cl), _ptr(w2), _ptr(out), B, X, Y, Z, Cin, Cout, KX, KY, KZ, stride, dil,
+                                _ptr(bias), _ptr(residual), act, int(split_out), _ptr(gn_stats), cpg, _ptr(ws),
+                                ws.numel(), _stream(x_cl)), "occ_conv_bf16x3")
     LAUNCH_COUNT[0] += 1
     return out
 
@@ -220,11 +275,11 @@ def gn_relu_zmean_ln(y, stats, gn_w, gn_b, ln_w, ln_b, B, XY, Z, C, groups):
     return tok, tokn
 
 
-def layernorm(x, w, b, round_out=False):
+def layernorm(x, w, b, split_out=False):
     _chk(x, "x")
     rows, C = x.shape
     out = torch.empty_like(x)
-    check(lib().occ_layernorm(_ptr(x), _ptr(w), _ptr(b), _ptr(out), rows, C, int(round_out), _stream()), "occ_layernorm")
+    check(lib().occ_layernorm(_ptr(x), _ptr(w), _ptr(b), _ptr(out), rows, C, int(split_out), _stream(x)), "occ_layernorm")
     LAUNCH_COUNT[0] += 1
     return out
 
@@ -241,16 +296,21 @@ def swin_proj_ffn(att, tok, wp, bp, ln_w, ln_b, w1, b1, w2, b2):
     return out
 
 
-def gn_apply(x, stats, w, b, rows_per_batch, groups, residual=None, out=None, out_off=0, relu=True, round_out=False):
+def gn_apply(x, stats, w, b, rows_per_batch, groups, residual=None, relu=True, want_f32=True, split_into=None,
+             out_off=0, want_split=False):
+    """GroupNorm apply (+ReLU, +residual) of a raw conv output x (rows, C).  Returns (out_f32 | None, out_s32 | None):
+    the fp32 result when want_f32, the S32 result written into split_into[:, out_off:out_off+C] (or a fresh (rows, C)
+    tensor when want_split)."""
     _chk(x, "x")
     rows, C = x.shape
-    if out is None:
-        out = torch.empty_like(x)
-    ldo = out.shape[1]
-    check(lib().occ_gn_apply(_ptr(x), _ptr(stats), _ptr(w), _ptr(b), _ptr(residual), _ptr(out), rows, rows_per_batch, C,
-                             groups, ldo, out_off, int(relu), int(round_out), _stream()), "occ_gn_apply")
+    out = torch.empty_like(x) if want_f32 else None
+    if split_into is None and want_split:
+        split_into = torch.empty_like(x)
+    ldo = split_into.shape[1] if split_into is not None else C
+    check(lib().occ_gn_apply(_ptr(x), _ptr(stats), _ptr(w), _ptr(b), _ptr(residual), _ptr(out), _ptr(split_into), rows,
+                             rows_per_batch, C, groups, ldo, out_off, int(relu), _stream(x)), "occ_gn_apply")
     LAUNCH_COUNT[0] += 1
-    return out
+    return out, split_into
 
 
 def aspp_gap_branch(x, wconv, gw, gb, cat, B, rows_per_batch, groups, out_off):
@@ -262,12 +322,16 @@ def aspp_gap_branch(x, wconv, gw, gb, cat, B, rows_per_batch, groups, out_off):
     return cat
 
 
-def dualpath_fuse(x, bev, cw, cbias, identity, B, XY, Z, C, id_stats=None, id_w=None, id_b=None, groups=0):
-    out = torch.empty((B * XY * Z, C), dtype=torch.float32, device=x.device)
-    check(lib().occ_dualpath_fuse(_ptr(x), _ptr(bev), _ptr(cw), float(cbias), _ptr(identity), _ptr(id_stats), _ptr(id_w),
-                                  _ptr(id_b), groups, _ptr(out), B, XY, Z, C, _stream()), "occ_dualpath_fuse")
+def dualpath_fuse(x, bev, cw, cbias, identity, B, XY, Z, C, identity_split=False, id_stats=None, id_w=None, id_b=None,
+                  groups=0, want_f32=True, want_split=True):
+    """-> (out fp32 | None, out S32 | None), each (B*XY*Z, C)."""
+    out = torch.empty((B * XY * Z, C), dtype=torch.float32, device=x.device) if want_f32 else None
+    out_s = torch.empty((B * XY * Z, C), dtype=torch.float32, device=x.device) if want_split else None
+    check(lib().occ_dualpath_fuse(_ptr(x), _ptr(bev), _ptr(cw), float(cbias), _ptr(identity), int(identity_split),
+                                  _ptr(id_stats), _ptr(id_w), _ptr(id_b), groups, _ptr(out), _ptr(out_s), B, XY, Z, C,
+                                  _stream(x)), "occ_dualpath_fuse")
     LAUNCH_COUNT[0] += 1
-    return out
+    return out, out_s
 
 
 def qkv_head_major_perm(C, heads, device=None):
@@ -297,7 +361,7 @@ def sine_pos3d(X, Y, Z, num_feats, device, temperature=10000.0, scale=6.28318530
 
 
 def head_prep(x, channel_last, level_embed=None, pos=None):
-    """x: (B,S,C) channel-last memory or (B,C,S) reference layout -> mem (B,S,C) [, kpos (B,S,C)] tf32-rounded."""
+    """x: (B,S,C) channel-last memory or (B,C,S) reference layout -> mem (B,S,C) [, kpos (B,S,C)] in S32."""
     _chk(x, "x")
     if channel_last:
         B, S, C = x.shape
@@ -371,21 +435,6 @@ def mask_gemm_pool(mf_r, membed, B, grid, out_grid, Q, want_mask):
                                    Zo, _stream()), "occ_mask_gemm_pool")
     LAUNCH_COUNT[0] += 2 + B
     return mask, pooled, flag
-
-
-def cross_attn_chunks(S):
-    c, n = ctypes.c_int(), ctypes.c_int()
-    lib().occ_cross_attn_chunks(S, ctypes.byref(c), ctypes.byref(n))
-    return c.value, n.value
-
-
-def cross_attn_partial(qh, Kp, Vp, ld, koff, voff, pooled, flag, B, S, Q, E, H):
-    chunk, nchunk = cross_attn_chunks(S)
-    part = torch.empty((B, H, nchunk, Q, 34), dtype=torch.float32, device=qh.device)
-    check(lib().occ_cross_attn_partial(_ptr(qh), _ptr(Kp), _ptr(Vp), ld, koff, voff, _ptr(pooled), _ptr(flag), _ptr(part),
-                                       B, S, Q, E, H, chunk, nchunk, _stream()), "occ_cross_attn_partial")
-    LAUNCH_COUNT[0] += 1
-    return part, nchunk
 
 
 def cross_attn_tc(qh, Kp, Vp, ld, koff, voff, pooled, flag, B, S, Q, E, H):

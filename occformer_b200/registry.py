@@ -81,3 +81,9 @@ class _Mirror:
 NECKS = _Mirror("neck", [("mmdet3d.models.builder", "NECKS"), ("mmdet.models.builder", "NECKS")])
 BACKBONES = _Mirror("backbone", [("mmdet3d.models.builder", "BACKBONES"), ("mmdet.models.builder", "BACKBONES")])
 HEADS = _Mirror("head", [("mmdet.models.builder", "HEADS"), ("mmdet3d.models.builder", "HEADS")])
+# mmcv 1.4.0 keeps these two in mmcv.cnn.bricks.registry (re-exported by mmcv.cnn.bricks.transformer); the reference
+# registers SinePositionalEncoding3D / MultiScaleDeformableAttention3D there
+# (mask2former/positional_encodings/positional_encoding.py:11-12, necks/multi_scale_deform_attn_3d.py:83-84)
+POSITIONAL_ENCODING = _Mirror("position encoding", [("mmcv.cnn.bricks.registry", "POSITIONAL_ENCODING"),
+                                                    ("mmcv.cnn.bricks.transformer", "POSITIONAL_ENCODING")])
+ATTENTION = _Mirror("attention", [("mmcv.cnn.bricks.registry", "ATTENTION"), ("mmcv.cnn.bricks.transformer", "ATTENTION")])

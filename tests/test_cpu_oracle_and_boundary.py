@@ -131,7 +131,7 @@ def test_product_path_fails_loudly_without_gpu():
     """no CPU fallback: CPU tensors are rejected instead of silently computed elsewhere."""
     from occformer_b200 import ops
     with pytest.raises(RuntimeError):
-        ops.gemm(torch.zeros(4, 32), torch.zeros(4, 32))
+        ops.gemm(torch.zeros(4, 32), torch.zeros(4, 32))  # CPU tensors
     from occformer_b200.encoder import to_channel_last
     with pytest.raises(RuntimeError):
         to_channel_last(torch.zeros(1, 128, 2, 2, 2))

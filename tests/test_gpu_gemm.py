@@ -1,16 +1,31 @@
-"""tcgen05 TF32 GEMM / implicit-GEMM conv vs fp64 torch on tf32-rounded operands (kernel correctness is
-isolated from tf32 operand rounding: with pre-rounded inputs the only differences are fp32 accumulation order)."""
+"""tcgen05 split-bf16 (three-pass, fp32-faithful) GEMM / implicit-GEMM conv vs fp64 torch on arbitrary fp32 operands.
+Expected error: ~4e-6 rms / ~2e-5 worst case relative (dropped lo*lo term + hi/lo roundings, <= 3 * 2^-18 per product);
+gate 5e-5 on both SURVEY criteria -- 20x inside the 1e-3 north-star tolerance."""
 import pytest
 import torch
 import torch.nn.functional as F
 
-from util import assert_close, round_tf32
+from util import assert_close
+
+TOL = 5e-5
 
 pytestmark = pytest.mark.gpu
 
 
 def _mk(shape, g, scale=1.0):
-    return round_tf32(torch.randn(*shape, generator=g) * scale)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def test_split_roundtrip(cuda):
+    """S32 format: device split == torch split (ops.split_weight), unsplit(split(x)) == x to 2^-17 relative."""
+    from occformer_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(257, 160, generator=g) * torch.logspace(-3, 3, 160)
+    xs = ops.to_split(x.to(cuda))
+    assert torch.equal(xs.cpu().view(torch.int32), ops.split_weight(x).view(torch.int32)), "device / host split differ"
+    back = ops.from_split(xs).cpu()
+    assert float(((back - x).abs() / x.abs().clamp_min(1e-30)).max()) < 2 ** -16
+    assert torch.equal(ops.unsplit_weight(xs.cpu()), back)
 
 
 @pytest.mark.parametrize("M,N,K", [(300, 384, 128), (1000, 100, 192), (129, 18, 96), (128, 32, 32), (4096, 256, 256),
@@ -19,9 +34,9 @@ def test_gemm_plain(cuda, M, N, K):
     from occformer_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
     a, w = _mk((M, K), g), _mk((N, K), g, K ** -0.5)
-    out = ops.gemm(a.to(cuda), w.to(cuda))
+    out = ops.gemm(ops.to_split(a.to(cuda)), ops.split_weight(w).to(cuda))
     ref = a.double() @ w.double().t()
-    assert_close(out, ref, 2e-5, f"gemm {M}x{N}x{K}")
+    assert_close(out, ref, TOL, f"gemm {M}x{N}x{K}")
 
 
 @pytest.mark.parametrize("act", [0, 1, 2])
@@ -31,14 +46,15 @@ def test_gemm_epilogue(cuda, act):
     M, N, K = 1500, 384, 128
     a, w = _mk((M, K), g), _mk((N, K), g, K ** -0.5)
     bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
-    out = ops.gemm(a.to(cuda), w.to(cuda), bias=bias.to(cuda), residual=res.to(cuda), act=act)
+    a_s, w_s = ops.to_split(a.to(cuda)), ops.split_weight(w).to(cuda)
+    out = ops.gemm(a_s, w_s, bias=bias.to(cuda), residual=res.to(cuda), act=act)
     ref = a.double() @ w.double().t() + bias.double() + res.double()
     ref = [lambda x: x, F.relu, F.gelu][act](ref)
-    assert_close(out, ref, 2e-5, f"gemm epilogue act={act}")
-    out_r = ops.gemm(a.to(cuda), w.to(cuda), bias=bias.to(cuda), round_out=True)
-    ref_r = round_tf32((a.double() @ w.double().t() + bias.double()).float())
-    assert_close(out_r, ref_r, 1e-3, "round_out")
-    assert int((out_r.view(torch.int32) & 0x1FFF).abs().max()) == 0, "round_out must clear the low 13 mantissa bits"
+    assert_close(out, ref, TOL, f"gemm epilogue act={act}")
+    # split_out: the epilogue writes the S32 format directly (operand of the next contraction) == split(fp32 output)
+    plain = ops.gemm(a_s, w_s, bias=bias.to(cuda))
+    out_s = ops.gemm(a_s, w_s, bias=bias.to(cuda), split_out=True)
+    assert torch.equal(out_s.view(torch.int32), ops.to_split(plain).view(torch.int32)), "split_out != split(out)"
 
 
 CONV_CASES = [
@@ -68,12 +84,13 @@ def test_conv(cuda, case):
     w = _mk((Cout, Cin) + k, g, (Cin * k[0] * k[1] * k[2]) ** -0.5)
     pad = tuple(dil * (kk - 1) // 2 for kk in k)
     ref = F.conv3d(x.double(), w.double(), None, stride=stride, padding=pad, dilation=dil)
-    w2, ks = ops.repack_conv_weight(w.to(cuda))
+    w2, ks = ops.repack_conv_weight(w)
+    w2 = w2.to(cuda)
     groups = 32 if (Cout == 32 and Cin == 160) else (16 if Cout == 32 else 32)  # covers cpg = 1, 2, 4, 8
     stats = torch.zeros((B, groups, 2), dtype=torch.float64, device=cuda)
-    x_cl = x.to(cuda).permute(0, 2, 3, 4, 1).contiguous()
+    x_cl = ops.to_split(x.to(cuda).permute(0, 2, 3, 4, 1).contiguous())
     out = ops.conv(x_cl, w2, ks, stride=stride, dil=dil, gn_stats=stats, cpg=Cout // groups)
-    assert_close(out.permute(0, 4, 1, 2, 3), ref, 2e-5, f"conv {case}")
+    assert_close(out.permute(0, 4, 1, 2, 3), ref, TOL, f"conv {case}")
     # GroupNorm statistics accumulated in the epilogue: (sum, sumsq) per (batch, group)
     r = ref.reshape(B, groups, -1)
     ref_stats = torch.stack((r.sum(-1), (r * r).sum(-1)), dim=-1)
@@ -86,8 +103,8 @@ def test_conv(cuda, case):
 
 def test_gemm_rejects_bad_args(cuda):
     from occformer_b200 import ops
-    a = torch.zeros(8, 30, device=cuda)  # K % 4 != 0
-    w = torch.zeros(16, 30, device=cuda)
+    a = torch.zeros(8, 48, device=cuda)  # K % 32 != 0: not a whole number of S32 chunks
+    w = torch.zeros(16, 48, device=cuda)
     with pytest.raises(RuntimeError):
         ops.gemm(a, w)
     with pytest.raises(RuntimeError):

@@ -126,16 +126,16 @@ def test_fused_mask_gemm_pool(cuda, grid, target, B):
     blocked / row-flag bookkeeping follows."""
     import torch.nn.functional as F
     from occformer_b200 import ops
-    from util import round_tf32
     E, Q = 96, 12
     g = torch.Generator().manual_seed(sum(grid))
     V = grid[0] * grid[1] * grid[2]
-    mf = round_tf32(torch.randn(B, V, E, generator=g))
-    me = round_tf32(torch.randn(B * Q, E, generator=g) * E ** -0.5)
+    mf = torch.randn(B, V, E, generator=g)
+    me = torch.randn(B * Q, E, generator=g) * E ** -0.5
     me[3] = -me[3].abs() * 0  # one all-zero query: pooled == 0 -> not blocked anywhere (0 < 0 is False)
-    mask, pooled_i, flag = ops.mask_gemm_pool(mf.to(cuda), me.to(cuda), B, grid, target, Q, want_mask=True)
+    mf_s, me_s = ops.to_split(mf.to(cuda)), ops.to_split(me.to(cuda))
+    mask, pooled_i, flag = ops.mask_gemm_pool(mf_s, me_s, B, grid, target, Q, want_mask=True)
     ref = torch.einsum("bvc,bqc->bvq", mf.double(), me.view(B, Q, E).double())
-    assert_close(mask, ref, 2e-5, f"fused mask einsum {grid}")
+    assert_close(mask, ref, 5e-5, f"fused mask einsum {grid}")
     own = mask.cpu().permute(0, 2, 1).reshape(B, Q, *grid)
     ref_pool = F.adaptive_max_pool3d(own, target).flatten(2).permute(0, 2, 1)  # (B,So,Q)
     assert torch.equal(ops.decode_ordered(pooled_i).cpu(), ref_pool), f"pooled maxima differ {grid}->{target}"
@@ -143,11 +143,11 @@ def test_fused_mask_gemm_pool(cuda, grid, target, B):
     # without the mask output (intermediate decoder layers)
     # (cubic power-of-two windows on box-divisible grids run the query-stationary kernel of mask_pool_tc.cu: same
     # products, but a different accumulator orientation, so the comparison is against the fp64 window maxima)
-    none, pooled2, flag2 = ops.mask_gemm_pool(mf.to(cuda), me.to(cuda), B, grid, target, Q, want_mask=False)
+    none, pooled2, flag2 = ops.mask_gemm_pool(mf_s, me_s, B, grid, target, Q, want_mask=False)
     assert none is None
     ref_pool64 = F.adaptive_max_pool3d(ref.permute(0, 2, 1).reshape(B, Q, *grid), target).flatten(2).permute(0, 2, 1)
     got = ops.decode_ordered(pooled2).cpu()
-    assert_close(got, ref_pool64, 2e-5, f"query-stationary pooled maxima {grid}->{target}")
+    assert_close(got, ref_pool64, 5e-5, f"query-stationary pooled maxima {grid}->{target}")
     assert torch.equal(flag2.cpu().view(B, Q) != 0, (got >= 0).any(1))
     assert torch.equal(got[0, :, 3], torch.zeros_like(got[0, :, 3]))  # the all-zero query (sample 0) pools to exactly +0
 
@@ -158,18 +158,17 @@ def test_query_stationary_mask_pool_full_grid(cuda, target):
     all three decoder pooling levels, vs the fp64 einsum + adaptive_max_pool3d."""
     import torch.nn.functional as F
     from occformer_b200 import ops
-    from util import round_tf32
     grid, B, E, Q = (200, 200, 16), 2, 192, 100
     g = torch.Generator().manual_seed(7)
     V = grid[0] * grid[1] * grid[2]
-    mf = round_tf32(torch.randn(B, V, E, generator=g)).to(cuda)
-    me = round_tf32(torch.randn(B * Q, E, generator=g) * E ** -0.5).to(cuda)
+    mf = torch.randn(B, V, E, generator=g).to(cuda)
+    me = (torch.randn(B * Q, E, generator=g) * E ** -0.5).to(cuda)
     me.view(B, Q, E)[:, 5] = -me.view(B, Q, E)[:, 5].abs()
     mf_pos = mf.abs()  # with positive features query 5 is negative everywhere -> its row must be flagged "all blocked"
-    none, pooled, flag = ops.mask_gemm_pool(mf_pos, me, B, grid, target, Q, want_mask=False)
+    none, pooled, flag = ops.mask_gemm_pool(ops.to_split(mf_pos), ops.to_split(me), B, grid, target, Q, want_mask=False)
     ref = torch.einsum("bvc,bqc->bqv", mf_pos.double(), me.view(B, Q, E).double()).view(B, Q, *grid)
     ref_pool = F.adaptive_max_pool3d(ref, target).flatten(2).permute(0, 2, 1)
     got = ops.decode_ordered(pooled)
-    assert_close(got, ref_pool, 2e-5, f"query-stationary pooled maxima full grid ->{target}")
+    assert_close(got, ref_pool, 5e-5, f"query-stationary pooled maxima full grid ->{target}")
     assert torch.equal(flag.view(B, Q) != 0, (got >= 0).any(1))
     assert not bool(flag.view(B, Q)[:, 5].any())

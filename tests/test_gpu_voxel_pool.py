@@ -72,6 +72,10 @@ def test_lift_splat_pr1(cuda, B):
     ref, gf, kept = port.voxel_pooling(geom, vol, dx, bx, nx)
     assert_close(prob, prob_ref, 1e-5, "depth_prob")
     assert_close(grid.permute(0, 4, 1, 2, 3), ref, 1e-5, "lift_splat grid")
+    # the S32 twin of the grid (operand of the encoder's first conv) is written by the same kernel: == split(grid)
+    from occformer_b200 import ops
+    (g2, g2_s), _ = vt.lift_splat(dd.to(cuda), feat.to(cuda), geom.to(cuda), B, 1, with_split=True)
+    assert torch.equal(ops.to_split(g2).view(torch.int32), g2_s.view(torch.int32)), "S32 twin of the pooled grid differs"
     from occformer_b200 import ops
     X, Y, Z = vt.grid_size()
     ws = ops._workspace(geom.numel() // 3, B, X, Y, Z, cuda)
@@ -136,7 +140,7 @@ def test_lift_splat_nusc_properties(cuda):
     print(f"nusc_200: n_pts={idx.shape[0]} n_kept={int(kept.sum())} nonempty={int(ws.counts.ne(0).sum())}")
 
 
-@pytest.mark.parametrize("kind", ["nusc", "kitti"])
+@pytest.mark.parametrize("kind", ["nusc", "kitti", "kitti4x4"])
 def test_geometry_kernel_vs_oracle(cuda, kind):
     """occ_lss_geometry vs the oracle's literal get_geometry (torch.inverse + batched matmuls): fp32 rounding only;
     the voxel indices derived from both geometries may differ only for points within 1e-4 cells of a cell boundary."""
@@ -144,6 +148,16 @@ def test_geometry_kernel_vs_oracle(cuda, kind):
     B, N = 2, 6
     gc = synth.grid_config("nusc_200")
     cams = synth.nusc_cameras(B, N)
+    if kind == "kitti4x4":  # the reference KITTI pipeline hands over 4x4 P2 matrices (semantic_kitti_lss_dataset.py:62-64);
+        # every camera gets its own matrix so that a wrong per-camera stride cannot go unnoticed
+        K = torch.eye(4)
+        K[:3, :4] = torch.tensor([[707.09, 0.0, 604.08, 45.76], [0.0, 707.09, 180.51, -0.35], [0.0, 0.0, 1.0, 0.005]])
+        Ks = torch.stack([K.clone() for _ in range(B * N)])
+        Ks[:, 0, 0] *= 1 + 0.01 * torch.arange(B * N)
+        Ks[:, 1, 1] *= 1 - 0.01 * torch.arange(B * N)
+        Ks[:, 0, 3] += torch.arange(B * N).float()
+        cams["intrins"] = Ks.view(B, N, 4, 4)
+        cams["bda"] = torch.eye(4).repeat(B, 1, 1)
     if kind == "kitti":  # 3x4 intrinsics with a shift column and a 4x4 homogeneous bda (ViewTransformerLSSBEVDepth.py:134-146)
         K = torch.tensor([[707.09, 0.0, 604.08, 45.76], [0.0, 707.09, 180.51, -0.35], [0.0, 0.0, 1.0, 0.005]])
         cams["intrins"] = K.view(1, 1, 3, 4).repeat(B, N, 1, 1)

@@ -1,11 +1,11 @@
 """tcgen05 shifted-window attention core (occ_window_attention) vs the oracle's ShiftWindowMSA restatement
-(port.shift_window_msa with an identity output projection), on token-ordered qkv rows.  Operands are pre-rounded to
-exactly tf32-representable so that only the tf32 rounding of the probabilities and the accumulation order differ."""
+(port.shift_window_msa with an identity output projection), on token-ordered qkv rows in the S32 split format.  Split-bf16
+operands and probabilities (three tensor-core passes): expected error ~1e-5; gate 1e-4 on both SURVEY criteria."""
 import pytest
 import torch
 
 from oracle import port
-from util import assert_close, round_tf32
+from util import assert_close
 
 pytestmark = pytest.mark.gpu
 
@@ -26,12 +26,11 @@ def test_window_attention_vs_oracle(cuda, B, X, Y, Z, C, shift):
     heads = C // 32
     g = torch.Generator().manual_seed(B * 1000 + X * 10 + C)
     nimg = B * (Z + 1)
-    # operands that are exactly tf32-representable on both sides: x and the bias live on a 2^-6 grid and the qkv
-    # projection is three stacked identities, so q = k = v = x + b exactly (the kernel's tensor cores see the same values
-    # as the fp32 oracle; what remains is the tf32 rounding of the probabilities and the accumulation order)
-    x = (torch.randn(nimg, X * Y, C, generator=g) * 64).round().clamp(-255, 255) / 64
+    # the qkv projection is three stacked identities, so q = k = v = x + b exactly on both sides and the test isolates the
+    # attention core (scores, bias, shift mask, softmax, PV)
+    x = torch.randn(nimg, X * Y, C, generator=g)
     sd = {"w_msa.qkv.weight": torch.cat([torch.eye(C)] * 3, 0),
-          "w_msa.qkv.bias": (0.3 * torch.randn(3 * C, generator=g) * 64).round() / 64,
+          "w_msa.qkv.bias": 0.3 * torch.randn(3 * C, generator=g),
           "w_msa.proj.weight": torch.eye(C), "w_msa.proj.bias": torch.zeros(C),
           "w_msa.relative_position_bias_table": torch.randn(169, heads, generator=g)}
     qkv_img = torch.nn.functional.linear(x, sd["w_msa.qkv.weight"], sd["w_msa.qkv.bias"]).view(nimg, X, Y, 3 * C)
@@ -40,11 +39,14 @@ def test_window_attention_vs_oracle(cuda, B, X, Y, Z, C, shift):
     table = sd["w_msa.relative_position_bias_table"]
     dense = table[port.rel_position_index(7).view(-1)].view(49, 49, heads).permute(2, 0, 1).reshape(heads, -1)
     bias_pad = torch.nn.functional.pad(dense, (0, 2404 - 2401)).contiguous()
-    out = ops.window_attention(qkv_rows.to(cuda), sd["w_msa.qkv.bias"].to(cuda), bias_pad.to(cuda), B, X, Y, Z, C, heads, shift)
+    S = lambda t: ops.to_split(t.contiguous().to(cuda))  # noqa: E731
+    bias_s = lambda b: ops.split_weight(b.view(1, -1)).view(-1).to(cuda)  # noqa: E731
+    out_s = ops.window_attention(S(qkv_rows), bias_s(sd["w_msa.qkv.bias"]), bias_pad.to(cuda), B, X, Y, Z, C, heads, shift)
+    out = ops.from_split(out_s)
     ref_rows = _rows_from_images(ref, B, X, Y, Z)
-    assert_close(out, ref_rows, 1e-3, f"window attention B{B} {X}x{Y}x{Z} C{C} shift={shift}")
+    assert_close(out, ref_rows, 1e-4, f"window attention B{B} {X}x{Y}x{Z} C{C} shift={shift}")
     # head-major qkv columns ([head][q|k|v][32], what the encoder feeds): identical arithmetic, identical result
     perm = ops.qkv_head_major_perm(C, heads)
-    out_hm = ops.window_attention(qkv_rows[:, perm].contiguous().to(cuda), sd["w_msa.qkv.bias"][perm].contiguous().to(cuda),
+    out_hm = ops.window_attention(S(qkv_rows[:, perm]), bias_s(sd["w_msa.qkv.bias"][perm].contiguous()),
                                   bias_pad.to(cuda), B, X, Y, Z, C, heads, shift, head_major=True)
-    assert torch.equal(out_hm, out), "head-major qkv layout changes the result"
+    assert torch.equal(out_hm, out_s), "head-major qkv layout changes the result"

@@ -25,28 +25,23 @@ def rel_rms(a, b):
     return float((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt().clamp_min(1e-30))
 
 
-# The extreme-value companion of the tolerance.  For an output tensor of n ~ 1e4..1e7 elements whose error is the sum of
-# many independent tf32 operand roundings (approximately Gaussian), max|a-b| sits at ~4.5..5.5 sigma while max|b| is
-# ~4..5 rms(b), so max|a-b|/max|b| scatters around the relative L2 error with a +-25 % run-to-run spread: it moves
-# whenever the accumulation ORDER changes (measured on the same code and data: 0.78e-3 ... 1.12e-3 for the stage-1
-# output of the full-topology encoder test, whose relative L2 error stayed at 0.700e-3 ... 0.701e-3).  The L2 ratio is
-# the per-tensor relative error that is held to north_star's 1e-3; the L-infinity ratio is bounded at 2x as an outlier
-# check (a single wrong element in a 1e6-element tensor moves it, but not the L2 ratio).
-LINF_FACTOR = 2.0
+def allclose_violations(a, b, tol=RTOL):
+    """SURVEY.md 8(d), second criterion: allclose(rtol=tol, atol=tol * rms(b)); returns the number of violating elements."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    rms = float(b.pow(2).mean().sqrt())
+    return int(((a - b).abs() > tol * rms + tol * b.abs()).sum())
 
 
 def assert_close(a, b, tol=RTOL, what=""):
-    """The tolerance of every floating-point parity test: per output tensor,
-        ||a-b||_2 / ||b||_2 <= tol   (north_star: 1e-3 relative fp32 per output tensor)   and
-        max|a-b| / max|b|   <= 2 tol (outlier check, see LINF_FACTOR).
-    An element-wise rtol is deliberately not used: outputs cross zero, where a relative bound on a single element is
-    ill-defined."""
+    """The tolerance of every floating-point parity test, exactly as SURVEY.md 8(d) fixes it -- per output tensor BOTH
+        max|a-b| / max|b| <= tol                         (north_star: 1e-3 relative fp32)   and
+        allclose(a, b, rtol=tol, atol=tol * rms(b))      (no element off by more than tol*(rms + |b|)).
+    OCC_PARITY_REPORT_ONLY=1 logs the numbers without asserting (used to record a before/after table)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
     assert torch.isfinite(a).all(), f"{what}: non-finite values"
-    r, q = rel_err(a, b), rel_rms(a, b)
-    assert q <= tol and r <= LINF_FACTOR * tol, f"{what}: rel_max {r:.3e}, rel_rms {q:.3e} (tol {tol:.0e})"
-    line = f"[parity] {what}: rel_max {r:.2e} rel_rms {q:.2e} (tol {tol:.0e})"
+    r, q, nv = rel_err(a, b), rel_rms(a, b), allclose_violations(a, b, tol)
+    line = f"[parity] {what}: rel_max {r:.2e} rel_rms {q:.2e} allclose_violations {nv}/{a.numel()} (tol {tol:.0e})"
     print(line)
     log = os.environ.get("OCC_PARITY_LOG", os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", "parity.log"))
     try:
@@ -55,6 +50,8 @@ def assert_close(a, b, tol=RTOL, what=""):
             f.write(line + "\n")
     except OSError:
         pass
+    if os.environ.get("OCC_PARITY_REPORT_ONLY") != "1":
+        assert r <= tol and nv == 0, f"{what}: rel_max {r:.3e}, rel_rms {q:.3e}, allclose violations {nv} (tol {tol:.0e})"
     return r
 
 
