@@ -143,6 +143,33 @@ int occ_window_attention(const float* qkv /*S32*/, const float* qkv_bias /*S32 r
                          int qkv_head_major, occ_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * MSDeformAttnPixelDecoder3D, the neck between encoder and head (P/occformer/necks/multiscale_deformattn_3d.py:143-248,
+ * P/occformer/necks/multi_scale_deform_attn_3d.py:17-80,185-286).  Token rows are "level-major":
+ * row(l, b, x, y, z) = B*start_l + b*n_l + (x*Y_l + y)*Z_l + z with the L levels ordered coarse -> fine (start_l = tokens
+ * of the coarser levels of one sample), so every level is a contiguous channel-last (B, X_l, Y_l, Z_l, C) tensor.
+ * `grids` = L x (X, Y, Z) ints in HOST memory.  The Linears / 1x1x1 / 3x3x3 convolutions go through occ_gemm_bf16x3 /
+ * occ_conv_bf16x3. */
+/* [LayerNorm (norms.k of the encoder layer) of each row ->] out_f32 = x (fp32), out_s32 = x (S32), out_pos = x + pos[token]
+ * (S32; pos (Nq, C) = SinePositionalEncoding3D + level_encoding of the token's level: query_pos of the reference); any of
+ * the three outputs may be NULL; ln_w / ln_b NULL = no normalisation. */
+int occ_neck_token_prep(const float* in, const float* ln_w, const float* ln_b, const float* pos, float* out_f32,
+                        float* out_s32, float* out_pos, int L, int B, const int* grids, int C, occ_stream_t stream);
+/* multi_scale_deformable_attn_pytorch + the sampling-location arithmetic of MultiScaleDeformableAttention3D.forward:
+ * value (rows, E) = value_proj output; ow (rows, H*L*P*4) = [sampling_offsets (h,l,p,(z,y,x)) | attention logits (h,l,p)];
+ * out (rows, E) S32 = sum_{l,p} softmax(logits) * trilinear(value level l)(ref + offset / (Z_l,Y_l,X_l)), zeros outside,
+ * align_corners=False; strides = the L feature strides (HOST floats; reference-point arithmetic). */
+int occ_ms_deform_attn(const float* value, const float* ow, float* out, int L, int B, const int* grids,
+                       const float* strides, int E, int H, int P, occ_stream_t stream);
+/* FPN step (:228-240): out_s (S32) = GroupNorm(cur raw lateral-conv output, stats) + trilinear upsample
+ * (align_corners=False) of coarse (B, Xc, Yc, Zc, C) fp32 */
+int occ_gn_upsample_add(const float* cur, const double* stats, const float* gw, const float* gb, int groups,
+                        const float* coarse, float* out_s, int B, int X, int Y, int Z, int Xc, int Yc, int Zc, int C,
+                        occ_stream_t stream);
+/* GroupNorm statistics of a finished tensor x (B, rows_per_batch, C): stats (B, C/cpg, 2) fp64 += (sum, sumsq); for the
+ * group sizes the conv epilogue does not accumulate itself (cpg not a power of two: 192 channels / 32 groups) */
+int occ_gn_stats(const float* x, double* stats, int B, int rows_per_batch, int C, int cpg, occ_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Mask2Former-3D occupancy decoder head (P/occformer/mask2former/mask2former_nusc_occ.py, mask2former_occ.py).
  * Layouts: voxel memories channel-last (B, S, E); queries (B, Q, E); mask logits "query-last" (B, S, Q).
  * The voxel-side GEMMs (K/V projections :657-667 via nn.MultiheadAttention in_proj; mask einsum :457) go through

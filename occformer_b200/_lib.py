@@ -35,6 +35,10 @@ SIGNATURES = {
     "occ_dualpath_fuse": (c_int, [P, P, P, c_float, P, c_int, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, STREAM]),
     "occ_swin_proj_ffn": (c_int, [P] * 11 + [c_longlong, c_int, STREAM]),
     "occ_window_attention": (c_int, [P, P, P, P] + [c_int] * 8 + [STREAM]),
+    "occ_neck_token_prep": (c_int, [P] * 7 + [c_int, c_int, P, c_int, STREAM]),
+    "occ_ms_deform_attn": (c_int, [P, P, P, c_int, c_int, P, P, c_int, c_int, c_int, STREAM]),
+    "occ_gn_upsample_add": (c_int, [P] * 4 + [c_int, P, P] + [c_int] * 8 + [STREAM]),
+    "occ_gn_stats": (c_int, [P, P, c_int, c_int, c_int, c_int, STREAM]),
     "occ_sine_pos3d": (c_int, [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, STREAM]),
     "occ_head_prep": (c_int, [P, c_int, P, P, P, P, c_int, c_longlong, c_int, STREAM]),
     "occ_query_head": (c_int, [P, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P, P, c_float, P, c_int, c_int,

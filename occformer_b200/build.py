@@ -57,10 +57,12 @@ def build_library(force=False, verbose=True):
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
         results = list(ex.map(_compile, sources()))
     objs = [o for o, _ in results]
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB + ".tmp"  # link next to the target, then rename: a concurrent reader never sees a half-written library
+    cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     if verbose:
         print(f"built {LIB} from {len(objs)} objects", file=sys.stderr)
     return LIB

@@ -635,7 +635,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmC, const void* W, GemmParams& p, int num_m_tiles,
                          cudaStream_t stream) {
-  int BN = p.N <= 32 ? 32 : p.N <= 64 ? 64 : (p.N <= 128 || (p.N % 256 != 0 && p.N % 128 == 0)) ? 128 : 256;
+  // N-tile: 192-wide tiles for the 192-channel neck / head matrices (N = 192, 576: no padded columns), else 128 / 256
+  int BN = p.N <= 32 ? 32 : p.N <= 64 ? 64 : (p.N <= 128 || (p.N % 256 != 0 && p.N % 128 == 0)) ? 128
+           : (p.N % 192 == 0 && p.N % 256 != 0) ? 192 : 256;
   CUtensorMap tmB;
   uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
   uint64_t strides[1] = {(uint64_t)p.K * 4};
@@ -652,6 +654,7 @@ static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmC, const v
     case 32: return launch_gemm<32, 8>(tmA, tmB, tmC, p, num_tiles, stream);
     case 64: return launch_gemm<64, 8>(tmA, tmB, tmC, p, num_tiles, stream);
     case 128: return launch_gemm<128, 5>(tmA, tmB, tmC, p, num_tiles, stream);
+    case 192: return launch_gemm<192, 4>(tmA, tmB, tmC, p, num_tiles, stream);
     default: return launch_gemm<256, 4>(tmA, tmB, tmC, p, num_tiles, stream);
   }
 }
@@ -761,7 +764,8 @@ extern "C" int occ_conv_bf16x3(const float* x, const float* w2, float* out, int 
   p.splits = 1;
   if (p.use_tma_store && !bias && !residual && act == 0 && !split_out && workspace &&
       workspace_bytes >= SPLITK_SEMS * sizeof(int) && (reinterpret_cast<uintptr_t>(workspace) & 3) == 0) {
-    const int bn = Cout <= 32 ? 32 : Cout <= 64 ? 64 : (Cout <= 128 || (Cout % 256 != 0 && Cout % 128 == 0)) ? 128 : 256;
+    const int bn = Cout <= 32 ? 32 : Cout <= 64 ? 64 : (Cout <= 128 || (Cout % 256 != 0 && Cout % 128 == 0)) ? 128
+                   : (Cout % 192 == 0 && Cout % 256 != 0) ? 192 : 256;
     const long long tiles = (long long)num_m_tiles * ((Cout + bn - 1) / bn);
     const int sms = sm_count();
     auto eff = [&](int s) { const long long t = tiles * s; return (double)t / (double)(((t + sms - 1) / sms) * sms); };

@@ -1,0 +1,367 @@
+// MSDeformAttnPixelDecoder3D (the neck between the dual-path encoder and the Mask2Former-3D head):
+// the kernels that are not GEMMs / convolutions.
+//
+//   projects/mmdet3d_plugin/occformer/necks/multiscale_deformattn_3d.py:143-248   (MSDeformAttnPixelDecoder3D.forward)
+//   projects/mmdet3d_plugin/occformer/necks/multi_scale_deform_attn_3d.py:17-80   (multi_scale_deformable_attn_pytorch)
+//                                                                     :185-286  (MultiScaleDeformableAttention3D.forward)
+//
+// Token layout ("level-major"): the Nq = sum_l X_l*Y_l*Z_l query / value tokens of the B samples are stored level by
+// level, row(l, b, x, y, z) = B*start_l + b*n_l + (x*Y_l + y)*Z_l + z, C channels per row (channel-last).  Every level is
+// then one contiguous (B, X_l, Y_l, Z_l, C) channel-last tensor: the 1x1x1 input convolutions write their level in place,
+// and the encoder output of a level is handed to the FPN / the head without a copy.  (The reference concatenates the
+// levels per sample, (Nq, B, C); only the row order differs -- every op of the encoder is per token except the
+// deformable gather, which addresses (level, sample, voxel) explicitly.)
+#include "occ_common.cuh"
+#include "occ_ptx.cuh"
+
+namespace occ {
+
+constexpr int NK_MAX_LEVELS = 4;
+
+struct NeckLevels {
+  int L, B;
+  int X[NK_MAX_LEVELS], Y[NK_MAX_LEVELS], Z[NK_MAX_LEVELS];
+  int start[NK_MAX_LEVELS];  // first token of the level inside one sample's Nq tokens (levels coarse -> fine)
+  int n[NK_MAX_LEVELS];      // X*Y*Z
+  float stride[NK_MAX_LEVELS];
+  long long rows;            // B * Nq
+};
+
+// global row -> (level, sample, local voxel index)
+__device__ __forceinline__ void nk_locate(const NeckLevels& g, long long row, int& lvl, int& b, int& local) {
+  lvl = 0;
+#pragma unroll
+  for (int l = 1; l < NK_MAX_LEVELS; ++l)
+    if (l < g.L && row >= (long long)g.B * g.start[l]) lvl = l;
+  const long long r = row - (long long)g.B * g.start[lvl];
+  b = (int)(r / g.n[lvl]);
+  local = (int)(r - (long long)b * g.n[lvl]);
+}
+
+__device__ __forceinline__ float nk_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Token preparation: [LayerNorm] of a row, written as up to three tensors
+//   out_f32  : x            fp32   (residual of the next sub-layer)
+//   out_s32  : x            S32    (operand of value_proj / of the FFN)
+//   out_pos  : x + pos[row] S32    (operand of the sampling_offsets | attention_weights projection; pos = sine
+//                                   positional encoding + level embedding of the token, a per-grid constant (Nq, C))
+// One warp per row, C % 32 == 0, C <= 1024; lane owns element `lane` of every 32-column chunk (coalesced 128-byte loads,
+// lanes (2t, 2t+1) form packed word t of a chunk for the S32 stores).
+template <int NCH>
+__global__ void __launch_bounds__(256)
+token_prep_kernel(const float* __restrict__ in, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                  const float* __restrict__ pos, float* __restrict__ out_f32, float* __restrict__ out_s32,
+                  float* __restrict__ out_pos, const NeckLevels g, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= g.rows) return;
+  float v[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) v[c] = __ldcs(in + row * C + c * 32 + lane);
+  if (ln_w) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) s += v[c];
+    const float mean = nk_warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { const float d = v[c] - mean; q += d * d; }
+    const float rstd = rsqrtf(nk_warp_sum(q) / (float)C + 1e-5f);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) v[c] = (v[c] - mean) * rstd * __ldg(ln_w + c * 32 + lane) + __ldg(ln_b + c * 32 + lane);
+  }
+  long long prow = 0;
+  if (out_pos) {
+    int lvl, b, local;
+    nk_locate(g, row, lvl, b, local);
+    prow = (long long)g.start[lvl] + local;
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float x = v[c];
+    if (out_f32) out_f32[row * C + c * 32 + lane] = x;
+    const float xp = out_pos ? x + __ldg(pos + prow * C + c * 32 + lane) : 0.f;
+    const float x2 = __shfl_xor_sync(0xffffffffu, x, 1), xp2 = __shfl_xor_sync(0xffffffffu, xp, 1);
+    if (!(lane & 1)) {
+      uint32_t hi, lo;
+      if (out_s32) {
+        split_pair(x, x2, hi, lo);
+        uint32_t* chunk = reinterpret_cast<uint32_t*>(out_s32 + row * C + c * 32);
+        chunk[lane >> 1] = hi;
+        chunk[16 + (lane >> 1)] = lo;
+      }
+      if (out_pos) {
+        split_pair(xp, xp2, hi, lo);
+        uint32_t* chunk = reinterpret_cast<uint32_t*>(out_pos + row * C + c * 32);
+        chunk[lane >> 1] = hi;
+        chunk[16 + (lane >> 1)] = lo;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-scale deformable attention core, 3-D (multi_scale_deform_attn_3d.py:17-80 + the location arithmetic of :258-272).
+//   value (rows, E)            value_proj output, level-major, head h = channels [h*hd, (h+1)*hd)
+//   ow    (rows, H*L*P*4)      [ sampling_offsets (h, l, p, 3: z, y, x) | attention logits (h, l, p) ] of the same token
+//   out   (rows, E)  S32       sum_{l,p} softmax(logits)[l,p] * trilinear(value level l)(loc), zeros outside,
+//                              align_corners=False;  loc = ref + offset / (Z_l, Y_l, X_l),  ref = voxel centre of the
+//                              query in its own level, normalised to [0,1] (the same point for every value level)
+// One CTA = NQ queries x (E/4) threads; thread = (query, float4 of channels) -> head = 4*t / hd.  The 8 corner rows of a
+// sampling point are 8 independent 16-byte loads per thread (96-byte runs per head: whole 32-byte sectors); neighbouring
+// queries sample neighbouring voxels, so most of the traffic is served by L1 / L2 (the value tensor, 70 MB at 91 250
+// tokens, is L2 resident).
+template <int L, int P>
+__global__ void __launch_bounds__(256)
+ms_deform_attn_kernel(const float* __restrict__ value, const float* __restrict__ ow, float* __restrict__ out,
+                      const NeckLevels g, int E, int H, int NQ) {
+  const int T = E >> 2;  // threads per query
+  const int ql = threadIdx.x / T, t = threadIdx.x - ql * T;
+  const long long row = (long long)blockIdx.x * NQ + ql;
+  if (ql >= NQ || row >= g.rows) return;
+  const int hd = E / H;
+  const int h = (4 * t) / hd;
+  int lq, b, local;
+  nk_locate(g, row, lq, b, local);
+  // reference point (normalised voxel centre), computed as the reference does: ((i + 0.5) * stride) / (dim * stride)
+  float rz, ry, rx;
+  {
+    const int Zq = g.Z[lq], Yq = g.Y[lq], Xq = g.X[lq];
+    const int z = local % Zq, y = (local / Zq) % Yq, x = local / (Zq * Yq);
+    const float st = g.stride[lq];
+    rz = ((float)z + 0.5f) * st / ((float)Zq * st);
+    ry = ((float)y + 0.5f) * st / ((float)Yq * st);
+    rx = ((float)x + 0.5f) * st / ((float)Xq * st);
+  }
+  const int LP = L * P;
+  const float* orow = ow + row * (size_t)(H * LP * 4);
+  const float* offs = orow + (size_t)h * LP * 3;
+  const float* logit = orow + (size_t)H * LP * 3 + (size_t)h * LP;
+  float w[L * P];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < L * P; ++i) { w[i] = __ldg(logit + i); m = fmaxf(m, w[i]); }
+  float den = 0.f;
+#pragma unroll
+  for (int i = 0; i < L * P; ++i) { w[i] = expf(w[i] - m); den += w[i]; }
+  const float inv = 1.0f / den;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* vbase = reinterpret_cast<const float4*>(value) + t;
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int Xl = g.X[l], Yl = g.Y[l], Zl = g.Z[l];
+    const long long lrow0 = (long long)g.B * g.start[l] + (long long)b * g.n[l];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const int i = l * P + p;
+      // grid_sample(align_corners=False) un-normalisation, in torch's own form: ((g + 1) * size - 1) / 2 with g = 2 loc - 1
+      const float lz = rz + __ldg(offs + 3 * i + 0) / (float)Zl;
+      const float ly = ry + __ldg(offs + 3 * i + 1) / (float)Yl;
+      const float lx = rx + __ldg(offs + 3 * i + 2) / (float)Xl;
+      const float fz = (((2.0f * lz - 1.0f) + 1.0f) * (float)Zl - 1.0f) * 0.5f;
+      const float fy = (((2.0f * ly - 1.0f) + 1.0f) * (float)Yl - 1.0f) * 0.5f;
+      const float fx = (((2.0f * lx - 1.0f) + 1.0f) * (float)Xl - 1.0f) * 0.5f;
+      const float z0f = floorf(fz), y0f = floorf(fy), x0f = floorf(fx);
+      const int z0 = (int)z0f, y0 = (int)y0f, x0 = (int)x0f;
+      const float tz = fz - z0f, ty = fy - y0f, tx = fx - x0f;
+      const float wa = w[i] * inv;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 c[8];
+      float cw[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int dz = k & 1, dy = (k >> 1) & 1, dx = k >> 2;
+        const int zz = z0 + dz, yy = y0 + dy, xx = x0 + dx;
+        const bool ok = zz >= 0 && zz < Zl && yy >= 0 && yy < Yl && xx >= 0 && xx < Xl;
+        cw[k] = ok ? (dz ? tz : 1.f - tz) * (dy ? ty : 1.f - ty) * (dx ? tx : 1.f - tx) : 0.f;
+        c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) c[k] = __ldg(vbase + (lrow0 + ((long long)xx * Yl + yy) * Zl + zz) * T);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s.x = fmaf(cw[k], c[k].x, s.x); s.y = fmaf(cw[k], c[k].y, s.y);
+        s.z = fmaf(cw[k], c[k].z, s.z); s.w = fmaf(cw[k], c[k].w, s.w);
+      }
+      acc.x = fmaf(wa, s.x, acc.x); acc.y = fmaf(wa, s.y, acc.y);
+      acc.z = fmaf(wa, s.z, acc.z); acc.w = fmaf(wa, s.w, acc.w);
+    }
+  }
+  store_split4(out + row * E, 4 * t, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FPN step (multiscale_deformattn_3d.py:228-240): y = GroupNorm(lateral conv raw output) + trilinear upsample
+// (align_corners=False) of the coarser level; written in S32 (operand of the 3x3x3 output conv).
+//   cur (B, X, Y, Z, C) raw lateral conv output + its GN statistics;  coarse (B, Xc, Yc, Zc, C) fp32.
+__global__ void __launch_bounds__(256)
+gn_upsample_add_kernel(const float* __restrict__ cur, const double* __restrict__ stats, const float* __restrict__ gw,
+                       const float* __restrict__ gb, int groups, const float* __restrict__ coarse, float* __restrict__ out_s,
+                       int B, int X, int Y, int Z, int Xc, int Yc, int Zc, int C) {
+  const int C4 = C >> 2;
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long V = (long long)X * Y * Z;
+  if (i4 >= (long long)B * V * C4) return;
+  const long long row = i4 / C4;
+  const int c0 = (int)(i4 - row * C4) * 4;
+  const int b = (int)(row / V);
+  const long long r = row - (long long)b * V;
+  const int z = (int)(r % Z), y = (int)((r / Z) % Y), x = (int)(r / ((long long)Z * Y));
+  const int cpg = C / groups;
+  const double count = (double)V * cpg;
+  const float4 raw = __ldcs(reinterpret_cast<const float4*>(cur + row * C + c0));
+  float v[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int gi = (c0 + j) / cpg;
+    const double s = stats[((size_t)b * groups + gi) * 2], q = stats[((size_t)b * groups + gi) * 2 + 1];
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    v[j] = (v[j] - (float)mean) * (float)(1.0 / sqrt(var + 1e-5)) * __ldg(gw + c0 + j) + __ldg(gb + c0 + j);
+  }
+  // F.interpolate(trilinear, align_corners=False): src = (dst + 0.5) * (in / out) - 0.5, clamped at 0; the upper
+  // neighbour index is clamped to the last element (its weight is then irrelevant: both neighbours coincide)
+  auto axis = [](int d, int n_out, int n_in, int& i0, int& i1, float& t) {
+    float s = ((float)d + 0.5f) * ((float)n_in / (float)n_out) - 0.5f;
+    if (s < 0.f) s = 0.f;
+    i0 = (int)s;
+    if (i0 > n_in - 1) i0 = n_in - 1;
+    i1 = i0 + 1 < n_in ? i0 + 1 : n_in - 1;
+    t = s - (float)i0;
+  };
+  int x0, x1, y0, y1, z0, z1;
+  float tx, ty, tz;
+  axis(x, X, Xc, x0, x1, tx);
+  axis(y, Y, Yc, y0, y1, ty);
+  axis(z, Z, Zc, z0, z1, tz);
+  const float4* cb = reinterpret_cast<const float4*>(coarse + (size_t)b * Xc * Yc * Zc * C + c0);
+  auto ld = [&](int xx, int yy, int zz) { return __ldg(cb + (((size_t)xx * Yc + yy) * Zc + zz) * C4); };
+  float up[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int dz = k & 1, dy = (k >> 1) & 1, dx = k >> 2;
+    const float wgt = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
+    const float4 cv = ld(dx ? x1 : x0, dy ? y1 : y0, dz ? z1 : z0);
+    up[0] = fmaf(wgt, cv.x, up[0]); up[1] = fmaf(wgt, cv.y, up[1]);
+    up[2] = fmaf(wgt, cv.z, up[2]); up[3] = fmaf(wgt, cv.w, up[3]);
+  }
+  store_split4(out_s + row * C, c0, make_float4(v[0] + up[0], v[1] + up[1], v[2] + up[2], v[3] + up[3]));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm statistics of a finished (B, rows_per_batch, C) tensor for group sizes the GEMM epilogue does not cover
+// (cpg = 6 for 192 channels / 32 groups): stats[b][g] += (sum, sumsq) in fp64.  CTA = 64 rows; thread = column.
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int rows_per_batch, int C, int cpg) {
+  __shared__ double sg[128];
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * 64;
+  const int nr = min(64, rows_per_batch - r0);
+  const int groups = C / cpg;
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sg[i] = 0.0;
+  __syncthreads();
+  const float* base = x + ((size_t)b * rows_per_batch + r0) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int r = 0; r < nr; ++r) {
+      const float v = __ldg(base + (size_t)r * C + c);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    atomicAdd(&sg[2 * (c / cpg)], (double)s);
+    atomicAdd(&sg[2 * (c / cpg) + 1], (double)q);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(size_t)b * 2 * groups + i], sg[i]);
+}
+
+static int fill_levels(NeckLevels& g, int L, int B, const int* grids, const float* strides) {
+  if (L < 1 || L > NK_MAX_LEVELS || B < 1) return OCC_EINVAL;
+  g.L = L; g.B = B;
+  int start = 0;
+  for (int l = 0; l < NK_MAX_LEVELS; ++l) {
+    if (l < L) {
+      g.X[l] = grids[3 * l]; g.Y[l] = grids[3 * l + 1]; g.Z[l] = grids[3 * l + 2];
+      if (g.X[l] < 1 || g.Y[l] < 1 || g.Z[l] < 1) return OCC_EINVAL;
+      g.n[l] = g.X[l] * g.Y[l] * g.Z[l];
+      g.start[l] = start;
+      g.stride[l] = strides ? strides[l] : 1.f;
+      start += g.n[l];
+    } else {
+      g.X[l] = g.Y[l] = g.Z[l] = 1; g.n[l] = 1; g.start[l] = 0x3fffffff; g.stride[l] = 1.f;
+    }
+  }
+  g.rows = (long long)B * start;
+  return OCC_OK;
+}
+
+}  // namespace occ
+
+using namespace occ;
+
+// grids: L x (X, Y, Z) ints on the HOST, levels in token order (coarse -> fine); rows = B * sum X*Y*Z.
+extern "C" int occ_neck_token_prep(const float* in, const float* ln_w, const float* ln_b, const float* pos,
+                                   float* out_f32, float* out_s32, float* out_pos, int L, int B, const int* grids,
+                                   int C, cudaStream_t stream) {
+  OCC_REQUIRE(in && grids && (out_f32 || out_s32 || out_pos));
+  OCC_REQUIRE((ln_w == nullptr) == (ln_b == nullptr) && (out_pos == nullptr || pos != nullptr));
+  OCC_REQUIRE(C % 32 == 0 && C >= 32 && C <= 1024);
+  NeckLevels g;
+  OCC_REQUIRE(fill_levels(g, L, B, grids, nullptr) == OCC_OK);
+  const unsigned blocks = (unsigned)((g.rows + 7) / 8);
+  switch (C / 32) {
+#define TP_CASE(n) case n: token_prep_kernel<n><<<blocks, 256, 0, stream>>>(in, ln_w, ln_b, pos, out_f32, out_s32, out_pos, g, C); break;
+    TP_CASE(1) TP_CASE(2) TP_CASE(3) TP_CASE(4) TP_CASE(6) TP_CASE(8) TP_CASE(12) TP_CASE(16) TP_CASE(24) TP_CASE(32)
+#undef TP_CASE
+    default: return OCC_EUNSUPPORTED;
+  }
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+// value (rows, E), ow (rows, H*L*P*4) = [offsets (h,l,p,3) | logits (h,l,p)], out (rows, E) S32.
+// strides: the L feature strides of the levels (reference-point arithmetic, multiscale_deformattn_3d.py:166-171).
+extern "C" int occ_ms_deform_attn(const float* value, const float* ow, float* out, int L, int B, const int* grids,
+                                  const float* strides, int E, int H, int P, cudaStream_t stream) {
+  OCC_REQUIRE(value && ow && out && grids && strides);
+  OCC_REQUIRE(E % 32 == 0 && H > 0 && E % H == 0 && (E / H) % 4 == 0 && E / 4 <= 256);
+  OCC_REQUIRE((reinterpret_cast<uintptr_t>(value) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  NeckLevels g;
+  OCC_REQUIRE(fill_levels(g, L, B, grids, strides) == OCC_OK);
+  const int T = E / 4;
+  const int NQ = 256 / T >= 1 ? 256 / T : 1;
+  const unsigned blocks = (unsigned)((g.rows + NQ - 1) / NQ);
+  if (L == 3 && P == 4) ms_deform_attn_kernel<3, 4><<<blocks, NQ * T, 0, stream>>>(value, ow, out, g, E, H, NQ);
+  else if (L == 1 && P == 4) ms_deform_attn_kernel<1, 4><<<blocks, NQ * T, 0, stream>>>(value, ow, out, g, E, H, NQ);
+  else if (L == 2 && P == 4) ms_deform_attn_kernel<2, 4><<<blocks, NQ * T, 0, stream>>>(value, ow, out, g, E, H, NQ);
+  else if (L == 4 && P == 4) ms_deform_attn_kernel<4, 4><<<blocks, NQ * T, 0, stream>>>(value, ow, out, g, E, H, NQ);
+  else return OCC_EUNSUPPORTED;
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+extern "C" int occ_gn_upsample_add(const float* cur, const double* stats, const float* gw, const float* gb, int groups,
+                                   const float* coarse, float* out_s, int B, int X, int Y, int Z, int Xc, int Yc, int Zc,
+                                   int C, cudaStream_t stream) {
+  OCC_REQUIRE(cur && stats && gw && gb && coarse && out_s);
+  OCC_REQUIRE(B > 0 && X > 0 && Y > 0 && Z > 0 && Xc > 0 && Yc > 0 && Zc > 0 && C % 32 == 0 && groups > 0 && C % groups == 0);
+  const long long n4 = (long long)B * X * Y * Z * (C / 4);
+  gn_upsample_add_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(cur, stats, gw, gb, groups, coarse, out_s, B, X,
+                                                                          Y, Z, Xc, Yc, Zc, C);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+// stats (B, C/cpg, 2) fp64, zero-initialised by the caller: += (sum, sumsq) of x (B, rows_per_batch, C) per (sample, group)
+extern "C" int occ_gn_stats(const float* x, double* stats, int B, int rows_per_batch, int C, int cpg, cudaStream_t stream) {
+  OCC_REQUIRE(x && stats && B > 0 && B <= 65535 && rows_per_batch > 0 && C > 0 && cpg > 0 && C % cpg == 0 && C / cpg <= 64);
+  dim3 grid((rows_per_batch + 63) / 64, B);
+  gn_stats_kernel<<<grid, 256, 0, stream>>>(x, stats, rows_per_batch, C, cpg);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}

@@ -297,13 +297,16 @@ def swin_proj_ffn(att, tok, wp, bp, ln_w, ln_b, w1, b1, w2, b2):
 
 
 def gn_apply(x, stats, w, b, rows_per_batch, groups, residual=None, relu=True, want_f32=True, split_into=None,
-             out_off=0, want_split=False):
+             out_off=0, want_split=False, out_f32=None):
     """GroupNorm apply (+ReLU, +residual) of a raw conv output x (rows, C).  Returns (out_f32 | None, out_s32 | None):
     the fp32 result when want_f32, the S32 result written into split_into[:, out_off:out_off+C] (or a fresh (rows, C)
     tensor when want_split)."""
     _chk(x, "x")
     rows, C = x.shape
-    out = torch.empty_like(x) if want_f32 else None
+    out = out_f32 if out_f32 is not None else (torch.empty_like(x) if want_f32 else None)
+    if out is not None:
+        _chk(out, "out_f32")
+        assert out.shape == x.shape
     if split_into is None and want_split:
         split_into = torch.empty_like(x)
     ldo = split_into.shape[1] if split_into is not None else C
@@ -501,5 +504,58 @@ def lidarseg_points(vox, pts, pc_range, border=True):
     r = [float(v) for v in pc_range]
     check(lib().occ_lidarseg_points(_ptr(vox), _ptr(pts) if n else None, pts.shape[1] if n else 3, n, r[0], r[1], r[2],
                                     r[3], r[4], r[5], X, Y, Z, K, int(border), _ptr(out), _stream()), "occ_lidarseg_points")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- neck (pixel decoder)
+def _grids_arr(grids):
+    flat = [int(v) for g in grids for v in g]
+    return (ctypes.c_int * len(flat))(*flat)
+
+
+def gn_stats(x, B, rows_per_batch, C, groups):
+    """fp64 (sum, sumsq) per (sample, group) of x (B*rows_per_batch, C) -> (B, groups, 2); for the group sizes the conv
+    epilogue does not accumulate (C / groups not a power of two)."""
+    _chk(x, "x")
+    stats = torch.zeros((B, groups, 2), dtype=torch.float64, device=x.device)
+    check(lib().occ_gn_stats(_ptr(x), _ptr(stats), B, rows_per_batch, C, C // groups, _stream(x)), "occ_gn_stats")
+    LAUNCH_COUNT[0] += 2
+    return stats
+
+
+def neck_token_prep(x, grids, B, ln=None, pos=None, want_f32=True, want_s32=True, want_pos=False):
+    """[LayerNorm] of level-major token rows x (B*Nq, C) -> (x fp32 | None, x S32 | None, (x + pos) S32 | None)."""
+    _chk(x, "x")
+    rows, C = x.shape
+    f32 = torch.empty_like(x) if want_f32 else None
+    s32 = torch.empty_like(x) if want_s32 else None
+    ps = torch.empty_like(x) if want_pos else None
+    lw, lb = ln if ln is not None else (None, None)
+    check(lib().occ_neck_token_prep(_ptr(x), _ptr(lw), _ptr(lb), _ptr(pos), _ptr(f32), _ptr(s32), _ptr(ps), len(grids), B,
+                                    _grids_arr(grids), C, _stream(x)), "occ_neck_token_prep")
+    LAUNCH_COUNT[0] += 1
+    return f32, s32, ps
+
+
+def ms_deform_attn(value, ow, grids, strides, B, E, H, P):
+    """3-D multi-scale deformable attention core on level-major rows -> (rows, E) in S32."""
+    _chk(value, "value"), _chk(ow, "ow")
+    out = torch.empty_like(value)
+    st = (ctypes.c_float * len(strides))(*[float(v) for v in strides])
+    check(lib().occ_ms_deform_attn(_ptr(value), _ptr(ow), _ptr(out), len(grids), B, _grids_arr(grids), st, E, H, P,
+                                   _stream(value)), "occ_ms_deform_attn")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
+def gn_upsample_add(cur, stats, gw, gb, groups, coarse):
+    """cur (B,X,Y,Z,C) raw conv output (+ stats), coarse (B,Xc,Yc,Zc,C) fp32 -> GN(cur) + trilinear_up(coarse) in S32."""
+    _chk(cur, "cur"), _chk(coarse, "coarse")
+    B, X, Y, Z, C = cur.shape
+    _, Xc, Yc, Zc, _ = coarse.shape
+    out = torch.empty_like(cur)
+    check(lib().occ_gn_upsample_add(_ptr(cur), _ptr(stats), _ptr(gw), _ptr(gb), groups, _ptr(coarse), _ptr(out), B, X, Y, Z,
+                                    Xc, Yc, Zc, C, _stream(cur)), "occ_gn_upsample_add")
     LAUNCH_COUNT[0] += 1
     return out
