@@ -4,15 +4,17 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A "step" = one pass of the hot path (LSS lift-splat voxel pooling -> OccupancyEncoder ->
-Mask2FormerNuscOccHead.simple_test) over one batch of synthetic samples per GPU, BASELINE.json configs[2]
-shapes (nuScenes R50: 6 cameras, 16x44 feature maps, D=112, C=128 -> 200x200x16 voxels, 100 queries, 17 classes).
-Data parallel over samples, no collective on the data path (weak scaling: fixed batch per GPU).
+A "step" = one connected pass of the hot path (ViewTransformerLiftSplatShootVoxel.forward (lift-splat
+voxel pooling) -> OccupancyEncoder.forward -> MSDeformAttnPixelDecoder3D.forward -> Mask2FormerNuscOccHead.simple_test,
+every module built from the registry and called through its own forward) over one batch of synthetic samples per GPU,
+BASELINE.json configs[2] shapes (nuScenes R50: 6 cameras, 16x44 feature maps, D=112, C=128 -> 200x200x16 voxels, 100
+queries, 17 classes).  Data parallel over samples, no collective on the data path (weak scaling: fixed batch per GPU).
 
 One JSON line on stdout (rank 0).  `value` = inputs resident in HBM, CUDA-event timed, L2 flushed between steps;
-`e2e` = the same metric through the public module API with pinned HOST inputs copied H2D and the per-voxel class
-labels (uint8) copied D2H inside the timed region; `roofline` = the dominant kernel family, timed live with CUDA events;
-`cpu_baseline` = the CPU oracle (port of the reference's PyTorch path) on the host cores, bounded sample.
+`e2e` = the same metric with pinned HOST inputs copied H2D, the per-voxel class labels (uint8) copied D2H and -- for N > 1
+-- the metric all-gather inside the timed region; `roofline` = the dominant kernel, `roofline_extra` = window attention and
+voxel pooling (the two kernels BASELINE.json's metric names), all timed live with CUDA events;
+`cpu_baseline` = the CPU oracle (port of the reference's PyTorch path) on the host cores, bounded sample, per segment.
 `--impl reference` times that CPU path alone (the reference itself is Python under mmcv and cannot travel to the GPU
 box).
 """
@@ -102,85 +104,75 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # workload construction
 # ----------------------------------------------------------------------------------------------------------------------
-def head_available():
-    try:
-        import occformer_b200.head  # noqa: F401
-        return True
-    except ImportError:
-        return False
+NECK = dict(strides=[2, 4, 8, 16], layers=6, heads=8, levels=3, points=4, ffn=4 * EMBED)
+OCC_SIZE = [200, 200, 16]
+STAGES_ALL = ["view_transformer(lift_splat)", "occupancy_encoder", "msdeform_pixel_decoder_3d", "mask2former_head.simple_test"]
 
 
-def build_b200(dev, batch):
-    """Modules of the B200 path with deterministic synthetic weights (occformer_b200.synth; the oracle is not imported
-    on this leg)."""
-    from occformer_b200 import synth
-    from occformer_b200.encoder import OccupancyEncoder
-    from occformer_b200.view_transformer import ViewTransformerLiftSplatShootVoxel
+class PassThroughDepthNet(torch.nn.Module):
+    """The step starts from post-DepthNet maps on both arms (image backbone + DepthNet are cuDNN-class work in front of
+    the hot path): ``depth_net(x, mlp_input)`` hands its input through."""
+
+    def forward(self, x, mlp_input=None):
+        return x
+
+
+def build_b200(dev):
+    """The registered modules of the B200 path, built through the registries from config-style dicts, with deterministic
+    synthetic weights (occformer_b200.synth; the oracle is not imported on this leg)."""
+    from occformer_b200 import BACKBONES, HEADS as HEAD_REG, NECKS, synth
+    from occformer_b200.head import head_cfg
+    from occformer_b200.neck import neck_cfg
     gc = synth.grid_config(GRID)
-    vt = ViewTransformerLiftSplatShootVoxel(grid_config=gc, data_config={"input_size": INPUT_SIZE}, numC_input=64,
-                                            numC_Trans=C_TRANS, downsample=DOWNSAMPLE).to(dev)
-    enc = OccupancyEncoder(in_channels=C_TRANS, num_stage=4, block_numbers=NUMS, block_inplanes=PLANES,
-                           block_strides=STRIDES, out_indices=(0, 1, 2, 3), norm_cfg=dict(type="GN", num_groups=32))
+    vt = NECKS.build(dict(type="ViewTransformerLiftSplatShootVoxel", loss_depth_weight=1.0, grid_config=gc,
+                          data_config={"input_size": INPUT_SIZE}, numC_input=112 + C_TRANS, numC_Trans=C_TRANS,
+                          downsample=DOWNSAMPLE, depth_net=PassThroughDepthNet())).to(dev)
+    enc = BACKBONES.build(dict(type="OccupancyEncoder", in_channels=C_TRANS, num_stage=4, block_numbers=NUMS,
+                               block_inplanes=PLANES, block_strides=STRIDES, out_indices=(0, 1, 2, 3),
+                               norm_cfg=dict(type="GN", num_groups=32, requires_grad=True), with_cp=True))
     enc.load_state_dict(synth.make_encoder_state(C_TRANS, PLANES, NUMS, STRIDES, seed=0), strict=True)
-    enc = enc.to(dev).eval()
-    head = None
-    if head_available():
-        from occformer_b200.head import build_nusc_head
-        head = build_nusc_head(EMBED, QUERIES, CLASSES, DEC_LAYERS, HEADS, PC_RANGE)
-        head.load_state_dict(synth.make_head_state(EMBED, QUERIES, CLASSES, DEC_LAYERS, 3, seed=1), strict=True)
-        head = head.to(dev).eval()
-    return vt, enc, head
+    neck = NECKS.build(dict(type="MSDeformAttnPixelDecoder3D", **neck_cfg(PLANES, NECK["strides"], EMBED, NECK["layers"],
+                                                                          NECK["heads"], NECK["levels"], NECK["points"],
+                                                                          NECK["ffn"])))
+    neck.load_state_dict(synth.make_neck_state(PLANES, EMBED, NECK["layers"], NECK["heads"], NECK["levels"], NECK["points"],
+                                               NECK["ffn"], seed=2), strict=True)
+    head = HEAD_REG.build(dict(type="Mask2FormerNuscOccHead", **head_cfg(EMBED, QUERIES, CLASSES, DEC_LAYERS, HEADS, PC_RANGE)))
+    head.load_state_dict(synth.make_head_state(EMBED, QUERIES, CLASSES, DEC_LAYERS, 3, seed=1), strict=True)
+    return vt, enc.to(dev).eval(), neck.to(dev).eval(), head.to(dev).eval()
 
 
 def host_inputs(batch, seed):
-    """Pinned host tensors of one step: post-DepthNet maps (B*N, D+C, fH, fW) + camera matrices + synthetic neck
-    outputs for the head (the 3-D deformable-attention neck between encoder and head is outside the hot path,
-    SURVEY.md 8(f)1; both arms consume the same synthetic 192-channel pyramid)."""
+    """Pinned host tensors of one step: post-DepthNet maps (B, N, D+C, fH, fW) + the camera matrices."""
     from occformer_b200 import synth
     fH, fW = INPUT_SIZE[0] // DOWNSAMPLE, INPUT_SIZE[1] // DOWNSAMPLE
     D = 112
     dd, feat = synth.lift_inputs(batch, N_CAMS, D, fH, fW, C_TRANS, seed=seed)
-    x = torch.cat([dd, feat], dim=1).contiguous()
+    x = torch.cat([dd, feat], dim=1).view(batch, N_CAMS, D + C_TRANS, fH, fW).contiguous()
     cams = synth.nusc_cameras(batch, N_CAMS, INPUT_SIZE)
     out = {"x": x, **cams}
     return {k: (v.pin_memory() if torch.cuda.is_available() else v) for k, v in out.items()}
 
 
-def neck_features(batch, dev, seed):
-    """Synthetic multi-scale neck outputs, channel-last memory viewed in the reference layout (B,192,X,Y,Z)."""
-    g = torch.Generator().manual_seed(seed)
-    sizes = [(200, 200, 16), (100, 100, 8), (50, 50, 4), (25, 25, 2)]
-    feats = []
-    for i, s in enumerate(sizes):
-        t = torch.randn(batch, *s, EMBED, generator=g) * (0.5 if i == 0 else 1.0)
-        feats.append(t.to(dev).permute(0, 4, 1, 2, 3))
-    return feats
-
-
 class Pipeline:
-    """The public-API call sequence of one step on device tensors."""
+    """One step = the registered modules' own ``forward`` calls, in the order the reference detector issues them
+    (OccupancyFormer.extract_img_feat / simple_test, occupancyformer.py:77-80,115-123,211-217)."""
 
     def __init__(self, dev, batch):
         self.dev, self.batch = dev, batch
-        self.vt, self.enc, self.head = build_b200(dev, batch)
-        self.neck = neck_features(batch, dev, seed=5) if self.head is not None else None
-        self.D = self.vt.D
+        self.vt, self.enc, self.neck, self.head = build_b200(dev)
+        self.metas = [dict(occ_size=OCC_SIZE, pc_range=PC_RANGE)] * batch
+        self.labels = None
 
     def stages(self):
-        return ["lift_splat", "occupancy_encoder"] + (["mask2former_head"] if self.head is not None else [])
+        return list(STAGES_ALL)
 
     @torch.no_grad()
     def run(self, inp):
-        B, N = self.batch, N_CAMS
-        x = inp["x"]
-        geom = self.vt.get_geometry(inp["rots"], inp["trans"], inp["intrins"], inp["post_rots"], inp["post_trans"],
-                                    inp["bda"])
-        grid, _ = self.vt.lift_splat(x[:, :self.D], x[:, self.D:], geom, B, N)
-        feats = self.enc.forward_cl(grid)
-        if self.head is None:
-            return feats[-1]
-        # the encoder pyramid feeds the (out-of-scope) neck; the head consumes the synthetic neck pyramid
-        res = self.head.simple_test(self.neck, [dict(occ_size=[200, 200, 16], pc_range=PC_RANGE)] * B)
+        mats = [inp[k] for k in ("rots", "trans", "intrins", "post_rots", "post_trans", "bda")]
+        voxel, _ = self.vt([inp["x"]] + mats + [None])           # ViewTransformerLiftSplatShootVoxel.forward(input)
+        feats = self.enc(voxel)                                   # OccupancyEncoder.forward(x) -> 4 levels
+        feats = self.neck(feats)                                  # MSDeformAttnPixelDecoder3D.forward(feats)
+        res = self.head.simple_test(feats, self.metas)            # Mask2FormerNuscOccHead.simple_test
         self.labels = res["output_labels"]
         return res["output_voxels"][0]
 
@@ -188,8 +180,9 @@ class Pipeline:
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline / --impl reference)
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_sample(include_head, threads):
-    """One sample of the same workload through the CPU oracle (port of the reference's PyTorch path)."""
+def cpu_sample(threads):
+    """One sample of the same connected workload through the CPU oracle (port of the reference's PyTorch path), with a
+    timer per segment (pooling / encoder / neck / head)."""
     from occformer_b200 import synth
     from oracle import port
     torch.set_num_threads(threads)
@@ -199,23 +192,29 @@ def cpu_sample(include_head, threads):
     D, fH, fW = frustum.shape[:3]
     dd, feat = synth.lift_inputs(1, N_CAMS, D, fH, fW, C_TRANS, seed=0)
     dx, bx, nx = port.gen_dx_bx(gc["xbound"], gc["ybound"], gc["zbound"])
-    sd_e = port.make_encoder_state(C_TRANS, PLANES, NUMS, STRIDES, seed=0)
-    sd_h = port.make_head_state(EMBED, QUERIES, CLASSES, DEC_LAYERS, 3, seed=1) if include_head else None
-    feats = None
-    if include_head:
-        from occformer_b200 import synth as s2
-        feats = s2.head_inputs(1, EMBED, [(200, 200, 16), (100, 100, 8), (50, 50, 4), (25, 25, 2)], seed=5)
+    sd_e = synth.make_encoder_state(C_TRANS, PLANES, NUMS, STRIDES, seed=0)
+    sd_n = synth.make_neck_state(PLANES, EMBED, NECK["layers"], NECK["heads"], NECK["levels"], NECK["points"], NECK["ffn"], seed=2)
+    sd_h = synth.make_head_state(EMBED, QUERIES, CLASSES, DEC_LAYERS, 3, seed=1)
 
     def step():
+        seg = {}
         with torch.no_grad():
+            t0 = time.perf_counter()
             geom = port.get_geometry(frustum, **cams)
             vol, _ = port.lift(dd, feat, 1, N_CAMS)
             grid, _, _ = port.voxel_pooling(geom, vol, dx, bx, nx)
+            del vol
+            t1 = time.perf_counter()
             outs = port.occupancy_encoder(grid, sd_e, NUMS, STRIDES, (0, 1, 2, 3))
-            if include_head:
-                res = port.head_simple_test(feats, sd_h, HEADS, DEC_LAYERS, (200, 200, 16))
-                return res["output_voxels"][0]
-            return outs[-1]
+            t2 = time.perf_counter()
+            feats = port.ms_deform_pixel_decoder_3d(outs, sd_n, NECK["strides"], NECK["heads"], NECK["layers"], NECK["levels"],
+                                                    NECK["points"])
+            t3 = time.perf_counter()
+            res = port.head_simple_test(feats, sd_h, HEADS, DEC_LAYERS, OCC_SIZE)
+            t4 = time.perf_counter()
+        seg.update(voxel_pooling_s=t1 - t0, occupancy_encoder_s=t2 - t1, pixel_decoder_s=t3 - t2, head_simple_test_s=t4 - t3,
+                   total_s=t4 - t0)
+        return res["output_voxels"][0], seg
 
     return step
 
@@ -226,32 +225,35 @@ def cpu_threads():
     return int(os.environ.get("OCC_CPU_THREADS", min(os.cpu_count() or 1, 32)))
 
 
+def cpu_measure(threads, max_timed, budget_s):
+    """1 warm-up + up to max_timed timed samples inside budget_s; returns (median seconds per sample, per-segment medians, k)."""
+    step = cpu_sample(threads)
+    t0 = time.perf_counter()
+    _, seg0 = step()
+    est = time.perf_counter() - t0
+    k = max(1, min(max_timed, int(budget_s / max(est, 1e-3))))
+    segs = []
+    for _ in range(k):
+        _, sg = step()
+        segs.append(sg)
+    med = lambda key: sorted(sg[key] for sg in segs)[len(segs) // 2]  # noqa: E731
+    return med("total_s"), {key: med(key) for key in segs[0]}, k, est
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = cpu_threads()
-    include_head = head_available()
-    step = cpu_sample(include_head, threads)
-    budget_s = 150.0
-    t0 = time.perf_counter()
-    step()  # one warm-up (also the cost estimate)
-    est = time.perf_counter() - t0
-    k = max(1, min(args.steps, int(budget_s / max(est, 1e-3))))
-    ts = []
-    for _ in range(k):
-        t0 = time.perf_counter()
-        step()
-        ts.append(time.perf_counter() - t0)
-    per = sum(ts) / len(ts)
+    per, seg, k, warm = cpu_measure(threads, args.steps, 170.0)
     val = 1.0 / per
-    sample = (f"1 sample/step of {WORKLOAD} (lift+voxel_pooling, OccupancyEncoder{', head.simple_test' if include_head else ''}) "
-              f"through the CPU oracle port, fp32, {threads} threads; 1 warm-up + {k} timed steps (requested {args.steps})")
+    sample = (f"1 sample/step of {WORKLOAD} (connected: {', '.join(STAGES_ALL)}) through the CPU oracle port, fp32, "
+              f"{threads} threads of {os.cpu_count()} cores; 1 warm-up ({warm:.1f} s) + median of {k} timed steps (requested {args.steps})")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
             "warmup": 1, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": 1, "stages": ["lift_splat", "occupancy_encoder"] +
-                       (["mask2former_head"] if include_head else [])},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": 1, "stages": STAGES_ALL},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "segments_s": seg},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -260,52 +262,98 @@ def run_reference(args, rank, world):
 # ----------------------------------------------------------------------------------------------------------------------
 # B200 leg
 # ----------------------------------------------------------------------------------------------------------------------
-# dram__bytes_read.sum + dram__bytes_write.sum of one conv3d 3x3x3 C=128 launch on one 200x200x16 sample, from the
-# committed ncu --set full capture (profiles/r01_ncu_conv3d_gemm_tf32_v3_mt2.md); the kernel's traffic scales with the batch
-NCU_CONV_DRAM_BYTES_PER_SAMPLE = 330.048512e6 + 288.318976e6
+def _time_cuda(fn, dev, iters=5, warm=3, flush=None):
+    ts = []
+    for i in range(warm + iters):
+        if flush is not None:
+            flush.fill_(float(i))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            ts.append(a.elapsed_time(b))
+    return sum(ts) / len(ts)
 
 
-def time_kernel_family(pipe, dev, peak):
-    """Roofline of the dominant kernel family, timed live (CUDA events on the current stream, L2 flushed)."""
-    from occformer_b200 import ops
+def rooflines(pipe, dev, peak):
+    """Rooflines of the dominant kernel and of the two kernels BASELINE.json's metric names (window attention: tensor
+    pipe; voxel pooling: HBM), each timed live with CUDA events on the current stream, L2 flushed before every launch.
+    Algorithmic work per launch = SURVEY.md 8(d) per-unit figures x units per launch."""
+    from occformer_b200 import ops, synth
     B = pipe.batch
     X, Y, Z, C = 200, 200, 16, 128
     flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    # ---- 1. Conv3d 3x3x3, C = 128, stage-0 grid: the largest FLOP item of the step
     x = ops.to_split(torch.randn(B, X, Y, Z, C, device=dev))
-    w2, ks = ops.repack_conv_weight(torch.randn(C, C, 3, 3, 3, device=dev) * 0.02)
+    w2, ks = ops.repack_conv_weight(torch.randn(C, C, 3, 3, 3) * 0.02)
+    w2 = w2.to(dev)
     stats = torch.zeros(B, 32, 2, dtype=torch.float64, device=dev)
-    ts = []
-    for i in range(8):
-        flush.fill_(float(i))
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        ops.conv(x, w2, ks, gn_stats=stats, cpg=4)
-        b.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            ts.append(a.elapsed_time(b))
-    ms = sum(ts) / len(ts)
+    ms = _time_cuda(lambda: ops.conv(x, w2, ks, gn_stats=stats, cpg=4), dev, flush=flush)
     flops = 2.0 * 27 * C * C * B * X * Y * Z
-    achieved = flops / (ms * 1e-3) / 1e12
-    # TF32 dense peak = half the bf16 peak on this part (B200_PROFILING.md table: 1.1 vs 2.25 PF nominal)
-    pk = peak["tf"] / 2.0
-    return {"kernel": "gemm_tf32_kernel<conv3d 3x3x3, C=128, 200x200x16>", "bound": "tensor", "achieved": achieved,
-            "peak": pk, "unit": "TFLOP/s", "frac": achieved / pk, "traffic": NCU_CONV_DRAM_BYTES_PER_SAMPLE * B,
-            "note": f"algorithmic FLOPs 2*27*Cin*Cout*V = {flops / 1e9:.1f} GF per launch / {ms:.3f} ms (CUDA events); peak = "
-                    f"tf32 dense = measured bf16 burst / 2, {peak['src']}; traffic = dram__bytes_read+write of this "
-                    f"kernel from the ncu --set full capture at batch 1 (profiles/r01_ncu_conv3d_gemm_tf32_v3_mt2.md: 330.0 + "
-                    f"288.3 MB) x batch {B}; algorithmic bytes = {2 * B * X * Y * Z * C * 4 / 1e6:.0f} MB"}
+    ach = flops / (ms * 1e-3) / 1e12
+    conv = {"kernel": "gemm_bf16x3_kernel<conv3d 3x3x3, C=128, 200x200x16>", "bound": "tensor", "achieved": ach,
+            "peak": peak["tf"], "unit": "TFLOP/s", "frac": ach / peak["tf"], "traffic": None, "passes": 3,
+            "frac_of_3pass_ceiling": 3.0 * ach / peak["tf"], "ms_per_launch": ms,
+            "peak_src": f"bf16 dense burst, {peak['src']}",
+            "note": f"algorithmic (fp32-problem) FLOPs 2*27*Cin*Cout*V = {flops / 1e9:.1f} GF per launch; the kernel executes "
+                    f"3 bf16 tensor-core passes per algorithmic FLOP (split-bf16 operands, fp32-faithful), so its ceiling is "
+                    f"peak/3 = {peak['tf'] / 3:.0f} TF/s algorithmic; algorithmic bytes = {2 * B * X * Y * Z * C * 4 / 1e6:.0f} MB"}
+    del x
+    # ---- 2. window attention core (A7/A8), stage-0 tokens
+    heads = C // 32
+    rows = B * X * Y * (Z + 1)
+    qkv = ops.to_split(torch.randn(rows, 3 * C, device=dev))
+    qb = ops.split_weight(torch.randn(1, 3 * C) * 0.1).view(-1).to(dev)
+    bias_pad = torch.randn(heads, 2404, device=dev) * 0.1
+    ms = _time_cuda(lambda: ops.window_attention(qkv, qb, bias_pad, B, X, Y, Z, C, heads, True, head_major=True), dev, flush=flush)
+    nwin = B * (Z + 1) * ((X + 6) // 7) * ((Y + 6) // 7)
+    fl = nwin * 4.0 * 49 * 49 * C  # QK^T + PV per window, all heads (SURVEY 8(d): 4*49^2*C)
+    by = rows * 4.0 * C * 4       # qkv read + out write
+    wattn = {"kernel": "window_attn_tc_kernel (stage 0, 200x200x(16+1) images)", "bound": "hbm",
+             "achieved": by / (ms * 1e-3) / 1e9, "peak": peak["hbm"], "unit": "GB/s", "frac": by / (ms * 1e-3) / 1e9 / peak["hbm"],
+             "traffic": None, "ms_per_launch": ms, "algorithmic_tflops": fl / (ms * 1e-3) / 1e12,
+             "tensor_frac_algorithmic": fl / (ms * 1e-3) / 1e12 / peak["tf"], "peak_src": peak["src"],
+             "note": f"unfused attention core: rows*(3C+C)*4 = {by / 1e9:.2f} GB in/out per launch bound it by HBM; "
+                     f"algorithmic QK^T+PV = {fl / 1e9:.1f} GF; tensor-pipe % from ncu: profiles/"}
+    del qkv
+    # ---- 3. voxel pooling (fused lift-splat), with and without the prologue (depth softmax, NCHW->NHWC, geometry)
+    gc = synth.grid_config(GRID)
+    fH, fW = INPUT_SIZE[0] // DOWNSAMPLE, INPUT_SIZE[1] // DOWNSAMPLE
+    dd, feat = synth.lift_inputs(B, N_CAMS, 112, fH, fW, C_TRANS, seed=0)
+    dd, feat = dd.to(dev), feat.to(dev)
+    cams = {k: v.to(dev) for k, v in synth.nusc_cameras(B, N_CAMS, INPUT_SIZE).items()}
+    vt = pipe.vt
+    dxbx = vt._host_params()
+    geom = vt.get_geometry(**cams)
+    prob, feat_cl = ops.lift_prologue(dd, feat)
+    ms_pool = _time_cuda(lambda: ops.lift_splat(prob, feat_cl, geom, B, N_CAMS, *dxbx, vt.grid_size(), with_split=True), dev, flush=flush)
+    ms_all = _time_cuda(lambda: vt.lift_splat(dd, feat, vt.get_geometry(**cams), B, N_CAMS, with_split=True), dev, flush=flush)
+    npts = B * N_CAMS * 112 * fH * fW
+    V = B * X * Y * Z
+    by = npts * 4 + B * N_CAMS * fH * fW * C_TRANS * 4 + npts * 12 + V * C_TRANS * 4  # SURVEY 8(d) fused-lift formula
+    pool = {"kernel": "vp_index_geom + vp_pool_kernel (fused lift-splat, 6 cams -> 200x200x16)", "bound": "hbm",
+            "achieved": by / (ms_pool * 1e-3) / 1e9, "peak": peak["hbm"], "unit": "GB/s",
+            "frac": by / (ms_pool * 1e-3) / 1e9 / peak["hbm"], "traffic": None, "ms_per_launch": ms_pool,
+            "with_prologue": {"ms": ms_all, "achieved": by / (ms_all * 1e-3) / 1e9, "frac": by / (ms_all * 1e-3) / 1e9 / peak["hbm"]},
+            "peak_src": peak["src"],
+            "note": f"algorithmic bytes n_pts*4 + N*fH*fW*C*4 + n_pts*12 + V*C*4 = {by / 1e6:.0f} MB per launch (+ the S32 twin of "
+                    f"the grid, {V * C_TRANS * 4 / 1e6:.0f} MB, written for the encoder's first conv, not counted)"}
+    return conv, {"window_attn": wattn, "voxel_pool": pool}
 
 
 def run_b200(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    from occformer_b200 import ops
+    from occformer_b200 import dist_eval, ops
     peak = peaks()
     pipe = Pipeline(dev, args.batch)
     host = host_inputs(args.batch, seed=0)
     resident = {k: v.to(dev) for k, v in host.items()}
     flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    gt = torch.randint(0, CLASSES, (args.batch, *OCC_SIZE), generator=g).to(torch.uint8).to(dev)  # synthetic ground truth
     torch.cuda.synchronize()
 
     def barrier():
@@ -320,11 +368,10 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(args.warmup):
         pipe.run(resident)
     barrier()
-    # The step is a fixed sequence of ~300 kernel launches on static shapes: capture it once in a CUDA graph and replay
-    # (the launches are the same kernels on the same buffers; only the CPU-side launch cost disappears).
+    # The step is a fixed sequence of kernel launches on static shapes: capture it once in a CUDA graph and replay
+    # (the same kernels on the same buffers; only the CPU-side launch cost disappears).
     graph, graph_out, launches_per_step = None, None, None
     if not args.no_graph:
-        l0 = ops.LAUNCH_COUNT[0]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -360,42 +407,38 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------------------------------------------------------- e2e: host buffers in, host result out
-    out_host = None
+    # every step: H2D of the step's inputs from pinned host memory, the registered modules' forward, D2H of the per-voxel
+    # class labels (uint8; what the reference's evaluation loop consumes, occupancyformer.py:238-243), the evaluation
+    # counts of the step (confusion-matrix kernel) and -- with more than one rank -- the path's only collective, the
+    # all-gather of the packed count vector (apis/test.py:195-212), INSIDE the timed region.
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     e2e_steps = args.steps
+    totals = torch.zeros(3 + 3 * CLASSES, dtype=torch.int64, device=dev)
+
     def step_e2e():
         if graph is not None:  # static device buffers: H2D into the graph's inputs, replay, D2H of its output
             for k, v in host.items():
                 resident[k].copy_(v, non_blocking=True)
             graph.replay()
-            return graph_out
-        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        return pipe.run(inp)
+        else:
+            pipe.run({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+        out_host.copy_(pipe.labels, non_blocking=True)
+        counts = dist_eval.ssc_counts(pipe.labels, gt, CLASSES)
+        totals.add_(dist_eval.reduce_counts(counts))
 
-    # host result of a step = the per-voxel class labels (B,200,200,16) uint8 -- what the reference's evaluation loop
-    # consumes (argmax of output_voxels, occupancyformer.py:238-243); the fp32 class-score volume stays on the device
-    def result():
-        return pipe.labels if getattr(pipe, "labels", None) is not None else step_e2e_last[0]
-
-    step_e2e_last = [None]
+    out_host = torch.empty((args.batch, *OCC_SIZE), dtype=torch.uint8).pin_memory()
     for _ in range(2):
-        step_e2e_last[0] = step_e2e()
-        res = result()
-        if out_host is None:
-            out_host = torch.empty(res.shape, dtype=res.dtype).pin_memory()
-        out_host.copy_(res, non_blocking=True)
+        step_e2e()
     barrier()
+    totals.zero_()
     d2h = out_host.numel() * out_host.element_size()
-    t0 = time.perf_counter()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(e2e_steps):
-        step_e2e_last[0] = step_e2e()
-        out_host.copy_(result(), non_blocking=True)
+        step_e2e()
     b.record()
     barrier()
     t_e2e_ms = a.elapsed_time(b)
-    _ = time.perf_counter() - t0
 
     # max over ranks
     if world > 1:
@@ -405,44 +448,36 @@ def run_b200(args, rank, world, local_rank):
     total_samples = args.batch * world * args.steps
     value = total_samples / (t_dev_ms * 1e-3)
     e2e_val = args.batch * world * e2e_steps / (t_e2e_ms * 1e-3)
-
-    # ---------------------------------------------------------------- the path's only collective: packed metric all-gather
-    # (outside the timed region; synthetic ground truth, so the score itself is meaningless -- the exchange is the point)
-    from occformer_b200 import dist_eval
-    out_dev = step_resident()
-    pred = pipe.labels.long() if getattr(pipe, "labels", None) is not None else out_dev.argmax(dim=1)
-    g = torch.Generator().manual_seed(1234 + rank)
-    gt = torch.randint(0, CLASSES, tuple(pred.shape), generator=g).to(dev)
-    counts = dist_eval.reduce_counts(dist_eval.ssc_counts(pred, gt, CLASSES))
-    scores = dist_eval.ssc_scores(counts.cpu(), CLASSES)
-    eval_info = {"collective": f"all_gather of {counts.numel()} int64 per rank (NCCL)" if world > 1 else "none (1 rank)",
-                 "voxels_scored": int(counts[3:3 + CLASSES].sum() + counts[3 + 2 * CLASSES:].sum()),
+    scores = dist_eval.ssc_scores(totals.cpu(), CLASSES)
+    eval_info = {"collective": (f"all_gather of {totals.numel()} int64 per rank per step (NCCL), inside the e2e timed region"
+                                if world > 1 else "none (1 rank)"),
+                 "voxels_scored": int(totals[3:3 + CLASSES].sum() + totals[3 + 2 * CLASSES:].sum()),
                  "iou_ssc_mean_vs_random_gt": scores["iou_ssc_mean"]}
     if rank != 0:
         return
-    roof = time_kernel_family(pipe, dev, peak)
+    roof, roof_extra = rooflines(pipe, dev, peak)
     cpu = None
     if not args.no_cpu_baseline:
         threads = cpu_threads()
-        step = cpu_sample(pipe.head is not None, threads)
-        t0 = time.perf_counter()
-        step()
-        per = time.perf_counter() - t0
-        cpu = {"value": 1.0 / per, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"1 sample of {WORKLOAD} ({', '.join(pipe.stages())}) through the CPU oracle port (torch fp32, "
-                         f"{threads} threads), single cold run = {per:.1f} s"}
+        per, seg, k, warm = cpu_measure(threads, 2, 100.0)
+        cpu = {"value": 1.0 / per, "unit": UNIT, "cores": threads, "kind": "port", "segments_s": seg,
+               "sample": f"1 sample of {WORKLOAD} (connected: {', '.join(STAGES_ALL)}) through the CPU oracle port (torch fp32, "
+                         f"{threads} threads of {os.cpu_count()} cores): 1 warm-up ({warm:.1f} s) + median of {k} timed = {per:.1f} s"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 operands / f32 accumulate+storage", "data": "synthetic",
+            "dtype": "f32 (split-bf16 hi/lo operands, 3 tensor-core passes per contraction, f32 accumulate + storage)",
+            "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
                        "parallelism": f"dp{world}", "stages": pipe.stages(),
+                       "api": "registry-built modules, forward() / simple_test() of each (connected: encoder pyramid -> neck -> head)",
                        "launch": "cuda_graph_replay" if graph is not None else "eager",
                        "l2": "192 MiB flush write between timed steps; activations (328 MB/tensor) exceed L2",
-                       "neck": "MSDeformAttnPixelDecoder3D is outside the hot path (SURVEY 8(f)1): head consumes a synthetic pyramid"},
+                       "input": "post-DepthNet maps (depth logits + context) + camera matrices; image backbone / DepthNet are "
+                                "in front of the hot path (SURVEY 8(f)3)"},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": t_e2e_ms / e2e_steps},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "eval": eval_info}
+            "gpu_launches": launches, "roofline": roof, "roofline_extra": roof_extra, "cpu_baseline": cpu, "eval": eval_info}
     print(json.dumps(line), flush=True)
 
 

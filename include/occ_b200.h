@@ -231,6 +231,19 @@ int occ_lidarseg_points(const float* vox, const float* pts, int pts_stride, int 
                         float z_min, float x_max, float y_max, float z_max, int X, int Y, int Z, int K, int border,
                         float* out, occ_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Evaluation tail: the integer counts behind the path's single collective
+ * (P/occformer/apis/test.py:195-212 sums them over ranks). */
+/* SSCMetrics.get_score_completion + get_score_semantic_and_completion (P/utils/ssc_metric.py:104-168), masked by
+ * target != ignore: pred / target n uint8 voxel labels -> out[0..2] = completion tp, fp, fn; out[3 + c], out[3 + K + c],
+ * out[3 + 2K + c] = semantic tp, fp, fn of class c (3 + 3K int64).  conf_ws: K*K int64 scratch. */
+int occ_ssc_counts(const unsigned char* pred, const unsigned char* target, long long n, int K, int ignore,
+                   long long* conf_ws, long long* out, occ_stream_t stream);
+/* OccupancyFormer.simple_evaluation_semantic (P/occformer/detectors/occupancyformer.py:219-224,246-254) + fast_hist_crop
+ * (P/utils/metric_util.py:8-23): scores (n, K) point class scores, labels (n) int64 -> hist[(gt-1)*(K-1) + (pred-1)] += 1
+ * for gt in 1..K-1, pred = 1 + argmax(scores[:, 1:]); hist ((K-1)^2 int64) is accumulated. */
+int occ_lidarseg_hist(const float* scores, const long long* labels, int n, int K, long long* hist, occ_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

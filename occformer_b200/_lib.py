@@ -52,6 +52,8 @@ SIGNATURES = {
     "occ_self_attn_ffn": (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, STREAM]),
     "occ_classmix": (c_int, [P, P, P, P] + [c_int] * 9 + [STREAM]),
     "occ_transpose_sq": (c_int, [P, P, c_int, c_longlong, c_int, STREAM]),
+    "occ_ssc_counts": (c_int, [P, P, c_longlong, c_int, c_int, P, P, STREAM]),
+    "occ_lidarseg_hist": (c_int, [P, P, c_int, c_int, P, STREAM]),
     "occ_lidarseg_points": (c_int, [P, P, c_int, c_int] + [c_float] * 6 + [c_int] * 5 + [P, STREAM]),
 }
 

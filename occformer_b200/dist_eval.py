@@ -3,24 +3,30 @@
 The forward pass shards by sample (every op is per sample); ranks exchange nothing until the end of
 evaluation, when one packed int64 vector per rank is all-gathered and summed:
 
-    [ completion tp, fp, fn | semantic tp[K], fp[K], fn[K] ]            (3 + 3K int64, <= 3 KB)
+    [ lidarseg hist (K-1)x(K-1) | completion tp, fp, fn | semantic tp[K], fp[K], fn[K] ]     ((K-1)^2 + 3 + 3K int64, < 3 KB)
 
 Reference semantics: SSCMetrics.get_score_completion / get_score_semantic_and_completion / compute
 (projects/mmdet3d_plugin/utils/ssc_metric.py:104-168, 88-102), summed over ranks like the reference's
 `dist.all_reduce(evaluation_semantic, SUM)` / `collect_results_cpu` (occformer/apis/test.py:195-212).  The counts
-are computed with one confusion-matrix bincount instead of the reference's K x 3 masked sums -- same integers.
+are computed from one confusion matrix (device kernel occ_ssc_counts / occ_lidarseg_hist) instead of the reference's K x 3
+masked sums and numpy bincount -- same integers.
 """
 import torch
 import torch.distributed as dist
 
 
 def ssc_counts(pred, target, num_classes, ignore=255):
-    """pred, target: integer label volumes of identical shape (any leading batch dims).  -> int64 (3 + 3K,)"""
+    """pred, target: integer label volumes of identical shape (any leading batch dims).  -> int64 (3 + 3K,)
+    CUDA tensors: one pass of the confusion-matrix kernel (occ_ssc_counts, csrc/eval_ops.cu).  CPU tensors (the host-side
+    sharding / reduction logic is exercised on CPU under gloo): the same integers from torch.bincount."""
+    K = num_classes
+    if pred.is_cuda:
+        from . import ops
+        return ops.ssc_counts(pred, target, K, ignore)
     pred = pred.reshape(-1).long()
     target = target.reshape(-1).long()
     keep = target != ignore  # reference: predict[target==255] = 0; target[target==255] = 0, then mask = target != 255
     pred, target = pred[keep], target[keep]
-    K = num_classes
     conf = torch.bincount(target * K + pred, minlength=K * K).view(K, K)  # conf[true, pred]
     tp = conf.diag()
     fp = conf.sum(0) - tp
@@ -30,6 +36,40 @@ def ssc_counts(pred, target, num_classes, ignore=255):
     cfp = (~occ_t & occ_p).sum()
     cfn = (occ_t & ~occ_p).sum()
     return torch.cat([torch.stack([ctp, cfp, cfn]).long(), tp.long(), fp.long(), fn.long()])
+
+
+def lidarseg_hist(point_scores, point_labels, num_classes, hist=None):
+    """OccupancyFormer.simple_evaluation_semantic (occupancyformer.py:219-224,246-254): point_scores (n, K) from
+    forward_lidarseg, point_labels (n,) integer in 0..K-1 (0 = unlabelled) -> (K-1, K-1) int64 hist[gt-1, pred-1] with
+    pred = 1 + argmax(scores[:, 1:]); accumulated into `hist` when given."""
+    K = num_classes
+    if point_scores.is_cuda:
+        from . import ops
+        return ops.lidarseg_hist(point_scores, point_labels, K, hist)
+    pred = point_scores[:, 1:].argmax(1) + 1
+    gt = point_labels.long()
+    keep = (gt >= 1) & (gt < K)
+    h = torch.bincount((gt[keep] - 1) * (K - 1) + (pred[keep] - 1), minlength=(K - 1) ** 2).view(K - 1, K - 1)
+    return h if hist is None else hist.add_(h)
+
+
+def pack(ssc_vec, hist=None, num_classes=None):
+    """The payload of the single collective: [ lidarseg hist (K-1)^2 | SC tp, fp, fn | SSC tp[K], fp[K], fn[K] ]"""
+    if hist is None:
+        hist = torch.zeros((num_classes - 1) ** 2, dtype=torch.int64, device=ssc_vec.device)
+    return torch.cat([hist.reshape(-1).to(ssc_vec.device), ssc_vec])
+
+
+def unpack(vec, num_classes):
+    n = (num_classes - 1) ** 2
+    return vec[:n].view(num_classes - 1, num_classes - 1), vec[n:]
+
+
+def lidarseg_miou(hist):
+    """per_class_iu (utils/metric_util.py:14-15): diag / (row + col - diag), mean over the K-1 classes"""
+    h = hist.double()
+    iu = h.diag() / (h.sum(1) + h.sum(0) - h.diag())
+    return float(iu[~torch.isnan(iu)].mean()) if bool((~torch.isnan(iu)).any()) else float("nan")
 
 
 def reduce_counts(vec, group=None):

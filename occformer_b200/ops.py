@@ -559,3 +559,27 @@ def gn_upsample_add(cur, stats, gw, gb, groups, coarse):
                                     Xc, Yc, Zc, C, _stream(cur)), "occ_gn_upsample_add")
     LAUNCH_COUNT[0] += 1
     return out
+
+
+# ----------------------------------------------------------------------------------------------- evaluation tail
+def ssc_counts(pred, target, K, ignore=255):
+    """uint8 label volumes (any shape) -> int64 (3 + 3K,): completion tp/fp/fn, semantic tp/fp/fn per class."""
+    p = _chk(pred.reshape(-1).to(torch.uint8).contiguous(), "pred", torch.uint8)
+    t = _chk(target.reshape(-1).to(torch.uint8).contiguous(), "target", torch.uint8)
+    assert p.numel() == t.numel()
+    ws = torch.empty(K * K, dtype=torch.int64, device=p.device)
+    out = torch.empty(3 + 3 * K, dtype=torch.int64, device=p.device)
+    check(lib().occ_ssc_counts(_ptr(p), _ptr(t), p.numel(), K, ignore, _ptr(ws), _ptr(out), _stream(p)), "occ_ssc_counts")
+    LAUNCH_COUNT[0] += 2
+    return out
+
+
+def lidarseg_hist(scores, labels, K, hist=None):
+    _chk(scores, "scores")
+    labels = _chk(labels.long().contiguous(), "labels", torch.int64)
+    if hist is None:
+        hist = torch.zeros((K - 1, K - 1), dtype=torch.int64, device=scores.device)
+    check(lib().occ_lidarseg_hist(_ptr(scores), _ptr(labels), scores.shape[0], K, _ptr(hist), _stream(scores)),
+          "occ_lidarseg_hist")
+    LAUNCH_COUNT[0] += 1
+    return hist

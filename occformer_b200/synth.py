@@ -193,3 +193,50 @@ def make_head_state(E=192, Q=100, K=17, num_layers=9, num_levels=3, ffn=None, se
             norm(lp + f"norms.{n}.")
     norm("transformer_decoder.post_norm.")
     return sd
+
+
+def make_neck_state(in_channels, E, num_layers, num_heads, num_levels=3, num_points=4, ffn=None, seed=0):
+    """Deterministic weights with the reference's state_dict keys.  Unlike the reference's init (zero sampling-offset
+    and attention-weight matrices), every matrix is non-trivial so that a parity test moves the sampling points."""
+    g = torch.Generator().manual_seed(seed)
+    ffn = ffn or 4 * E
+    sd = {}
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    def gn(name, n):
+        sd[name + "weight"] = 1.0 + 0.1 * rn(n)
+        sd[name + "bias"] = 0.1 * rn(n)
+
+    nin = len(in_channels)
+    for i in range(num_levels):
+        cin = in_channels[nin - i - 1]
+        sd[f"input_convs.{i}.conv.weight"] = rn(E, cin, 1, 1, 1, std=cin ** -0.5)
+        sd[f"input_convs.{i}.conv.bias"] = 0.1 * rn(E)
+        gn(f"input_convs.{i}.gn.", E)
+    for l in range(num_layers):
+        p = f"encoder.layers.{l}."
+        n_off = num_heads * num_levels * num_points
+        sd[p + "attentions.0.sampling_offsets.weight"] = rn(3 * n_off, E, std=0.5 * E ** -0.5)
+        sd[p + "attentions.0.sampling_offsets.bias"] = rn(3 * n_off, std=1.0)
+        sd[p + "attentions.0.attention_weights.weight"] = rn(n_off, E, std=E ** -0.5)
+        sd[p + "attentions.0.attention_weights.bias"] = 0.1 * rn(n_off)
+        for nm in ("value_proj", "output_proj"):
+            sd[p + f"attentions.0.{nm}.weight"] = rn(E, E, std=E ** -0.5)
+            sd[p + f"attentions.0.{nm}.bias"] = 0.1 * rn(E)
+        sd[p + "ffns.0.layers.0.0.weight"] = rn(ffn, E, std=E ** -0.5)
+        sd[p + "ffns.0.layers.0.0.bias"] = 0.1 * rn(ffn)
+        sd[p + "ffns.0.layers.1.weight"] = rn(E, ffn, std=ffn ** -0.5)
+        sd[p + "ffns.0.layers.1.bias"] = 0.1 * rn(E)
+        gn(p + "norms.0.", E)
+        gn(p + "norms.1.", E)
+    sd["level_encoding.weight"] = rn(num_levels, E)
+    for i in range(nin - num_levels):
+        sd[f"lateral_convs.{i}.conv.weight"] = rn(E, in_channels[i], 1, 1, 1, std=in_channels[i] ** -0.5)
+        gn(f"lateral_convs.{i}.gn.", E)
+        sd[f"output_convs.{i}.conv.weight"] = rn(E, E, 3, 3, 3, std=(27 * E) ** -0.5)
+        gn(f"output_convs.{i}.gn.", E)
+    sd["mask_feature.weight"] = rn(E, E, 1, 1, 1, std=E ** -0.5)
+    sd["mask_feature.bias"] = 0.1 * rn(E)
+    return sd

@@ -12,7 +12,7 @@ for s in "$@"; do
     wattn)   timeout 600 python -m pytest tests/test_gpu_window_attn.py -q -m gpu > gpurun_out/t_wattn.log 2>&1; echo "wattn rc=$?" ;;
     head)    timeout 600 python -m pytest tests/test_gpu_head.py -q -m gpu > gpurun_out/t_head.log 2>&1; echo "head rc=$?" ;;
     full)    timeout 1200 python -m pytest tests/test_gpu_fullsize.py -q -m gpu -s > gpurun_out/t_full.log 2>&1; echo "full rc=$?" ;;
-    neck)    timeout 600 python -m pytest tests/test_gpu_neck.py -q -m gpu > gpurun_out/t_neck.log 2>&1; echo "neck rc=$?" ;;
+    neck)    timeout 600 python -m pytest tests/test_gpu_neck.py tests/test_gpu_eval.py -q -m gpu > gpurun_out/t_neck.log 2>&1; echo "neck rc=$?" ;;
     all)     timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/t_all.log 2>&1; echo "all rc=$?" ;;
     micro)   timeout 600 python scripts/microbench.py > gpurun_out/micro.log 2>&1; echo "micro rc=$?" ;;
     bench)   timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -n 3 gpurun_out/bench.log ;;
