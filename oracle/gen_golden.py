@@ -46,6 +46,68 @@ def gen_neck():
     print("neck_small", [tuple(o.shape) for o in outs])
 
 
+DEPTHNET_CASE = dict(cin=32, mid=32, ctx=16, D=12, cam=27, B=1, N=2, fH=6, fW=9, wseed=31, xseed=33)
+
+
+def depthnet_state(ref_module, seed):
+    """The reference DepthNet's own state_dict with every tensor made non-trivial (BN running statistics, the
+    zero-initialised DCN offset conv)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = ref_module.state_dict()
+    for k, v in sd.items():
+        if "num_batches_tracked" in k:
+            continue
+        if "running_var" in k:
+            v.copy_(0.5 + torch.rand(v.shape, generator=g))
+        elif "running_mean" in k:
+            v.copy_(0.2 * torch.randn(v.shape, generator=g))
+        elif "conv_offset" in k:
+            v.copy_(0.3 * torch.randn(v.shape, generator=g))
+        else:
+            v.copy_(torch.randn(v.shape, generator=g) * (0.1 if v.dim() == 1 else (v[0].numel()) ** -0.5))
+            if v.dim() == 1 and ("bn" in k or k.endswith("1.weight")) and k.endswith("weight"):
+                v.add_(1.0)
+    return sd
+
+
+def gen_depthnet():
+    """DepthNet: reference class under the shim (mmdet BasicBlock / mmcv DCN restated in oracle/shim.py),
+    its state_dict KEYS + SHAPES (the checkpoint contract) and its output on a seeded input."""
+    import json
+    c = DEPTHNET_CASE
+    base = shim.load(refmodels.OCC + "image2bev.ViewTransformerLSSBEVDepth")
+    torch.manual_seed(c["wseed"])
+    ref = base.DepthNet(c["cin"], c["mid"], c["ctx"], c["D"], cam_channels=c["cam"]).eval()
+    sd = depthnet_state(ref, c["wseed"])
+    ref.load_state_dict(sd)
+    g = torch.Generator().manual_seed(c["xseed"])
+    x = torch.randn(c["B"] * c["N"], c["cin"], c["fH"], c["fW"], generator=g)
+    mlp = torch.randn(c["B"], c["N"], c["cam"], generator=g)
+    with torch.no_grad():
+        y = ref(x, mlp)
+    np.savez(os.path.join(OUT, "depthnet_small.npz"), out=y.numpy(), **{"w:" + k: v.numpy() for k, v in sd.items()})
+    # the key / shape contract of the full-size module of the nuScenes config (numC_input = 512, numC_Trans = 128, D = 112)
+    full = base.DepthNet(512, 512, 128, 112, cam_channels=27)
+    with open(os.path.join(OUT, "depthnet_keys_nusc.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in full.state_dict().items()}, f, indent=0)
+    print("depthnet_small", tuple(y.shape), len(sd), "keys")
+
+
+def gen_model_cfg():
+    """The ``model`` dict of the UNMODIFIED reference configs as plain data (the config files are pure-python assignments;
+    ``_base_`` inheritance only adds dataset / runtime keys): the sections our registries must build from."""
+    import json
+    for name, rel in (("nusc_r50", "projects/configs/occformer_nusc/occformer_nusc_r50_256x704.py"),
+                      ("kitti", "projects/configs/occformer_kitti/occformer_kitti.py")):
+        ns = {}
+        exec(compile(open(os.path.join(shim.REFERENCE_ROOT, rel)).read(), rel, "exec"), ns)
+        m = ns["model"]
+        keep = {k: m[k] for k in ("img_view_transformer", "img_bev_encoder_backbone", "img_bev_encoder_neck", "pts_bbox_head")}
+        with open(os.path.join(OUT, f"model_cfg_{name}.json"), "w") as f:
+            json.dump(keep, f, indent=1, default=lambda o: list(o))
+        print("model_cfg", name, list(keep))
+
+
 def main():
     assert shim.reference_available(), "needs /root/reference"
     shim.install()
@@ -53,6 +115,12 @@ def main():
     torch.manual_seed(0)
     if "neck" in sys.argv[1:]:  # python -m oracle.gen_golden neck : only the neck fixture
         gen_neck()
+        return
+    if "depthnet" in sys.argv[1:]:
+        gen_depthnet()
+        return
+    if "cfg" in sys.argv[1:]:
+        gen_model_cfg()
         return
 
     # ---- voxel pooling (reference ViewTransformerLiftSplatShootVoxel + its own QuickCumsum fallback)
@@ -98,6 +166,8 @@ def main():
              output_points=res["output_points"].numpy())
     print("head_nusc done")
     gen_neck()
+    gen_depthnet()
+    gen_model_cfg()
 
 
 if __name__ == "__main__":

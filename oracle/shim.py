@@ -145,7 +145,79 @@ def build_norm_layer(cfg, num_features, postfix=""):
     return abbr + str(postfix), layer
 
 
-CONV_LAYERS = {"Conv1d": nn.Conv1d, "Conv2d": nn.Conv2d, "Conv3d": nn.Conv3d, "Conv": nn.Conv2d}
+class DeformConv2dPack(nn.Module):
+    """mmcv-full 1.4.0 ``mmcv/ops/deform_conv.py`` DeformConv2dPack ('DCN' in CONV_LAYERS), restated on CPU (the op is a
+    CUDA-only extension in mmcv): ``weight`` (out, in/groups, kh, kw) without bias, ``conv_offset`` = Conv2d(in,
+    deform_groups*2*kh*kw, k, stride, padding, dilation, bias=True) zero-initialised; forward = deform_conv2d(x, offset,
+    weight) where offset channel 2k / 2k+1 of a deformable group is the (dy, dx) of kernel point k, sampling is bilinear
+    with zero contribution from out-of-map corners (deform_conv_cuda_kernel.cuh dmcn_im2col_bilinear semantics of v1:
+    points with h <= -1 || h >= H || w <= -1 || w >= W give 0).  Explicit corner gathers -- deliberately NOT grid_sample,
+    so that it is an independent check of occformer_b200/depthnet.py."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, deform_groups=1,
+                 bias=False, im2col_step=32, **kw):
+        super().__init__()
+        assert not bias and deform_groups == 1 and stride == 1
+        self.k, self.padding, self.dilation, self.groups = kernel_size, padding, dilation, groups
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, kernel_size, kernel_size))
+        nn.init.kaiming_uniform_(self.weight, nonlinearity="relu")
+        self.conv_offset = nn.Conv2d(in_channels, 2 * kernel_size * kernel_size, kernel_size, stride=stride,
+                                     padding=padding, dilation=dilation, bias=True)
+        nn.init.zeros_(self.conv_offset.weight)
+        nn.init.zeros_(self.conv_offset.bias)
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        k, pad, dil = self.k, self.padding, self.dilation
+        off = self.conv_offset(x)
+        ys = torch.arange(H, dtype=x.dtype).view(1, H, 1)
+        xs = torch.arange(W, dtype=x.dtype).view(1, 1, W)
+        xf = x.reshape(B, C, H * W)
+        cols = []
+        for kk in range(k * k):
+            py = ys - pad + (kk // k) * dil + off[:, 2 * kk]
+            px = xs - pad + (kk % k) * dil + off[:, 2 * kk + 1]
+            y0, x0 = torch.floor(py), torch.floor(px)
+            val = torch.zeros(B, C, H, W, dtype=x.dtype)
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    yy, xx = y0 + dy, x0 + dx
+                    w = (1 - (py - yy).abs()) * (1 - (px - xx).abs())
+                    ok = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < W)
+                    idx = (yy.clamp(0, H - 1) * W + xx.clamp(0, W - 1)).long().view(B, 1, H * W).expand(B, C, H * W)
+                    val = val + torch.gather(xf, 2, idx).view(B, C, H, W) * (w * ok).unsqueeze(1)
+            cols.append(val)
+        col = torch.stack(cols, dim=2)  # (B, C, k*k, H, W)
+        g = self.groups
+        col = col.view(B, g, (C // g) * k * k, H * W)
+        w = self.weight.view(g, -1, (C // g) * k * k)
+        return torch.einsum("bgkp,gok->bgop", col, w).reshape(B, -1, H, W)
+
+
+class BasicBlock(nn.Module):
+    """mmdet 2.14.0 ``mmdet/models/backbones/resnet.py`` BasicBlock as DepthNet uses it (stride 1, no downsample, BN):
+    conv1 -> bn1 -> relu -> conv2 -> bn2 -> (+identity) -> relu; norm layers are registered under 'bn1' / 'bn2'."""
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, style="pytorch", with_cp=False, conv_cfg=None,
+                 norm_cfg=dict(type="BN"), dcn=None, plugins=None, init_cfg=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride=stride, padding=dilation, dilation=dilation, bias=False)
+        self.add_module("bn1", nn.BatchNorm2d(planes))
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.add_module("bn2", nn.BatchNorm2d(planes))
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        identity = x
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        if self.downsample is not None:
+            identity = self.downsample(x)
+        return self.relu(out + identity)
+
+
+CONV_LAYERS = {"Conv1d": nn.Conv1d, "Conv2d": nn.Conv2d, "Conv3d": nn.Conv3d, "Conv": nn.Conv2d, "DCN": DeformConv2dPack}
 
 
 def build_conv_layer(cfg, *args, **kwargs):
@@ -557,7 +629,7 @@ def install():
     _mod("mmdet.models.builder", NECKS=NECKS, HEADS=HEADS, BACKBONES=BACKBONES, DETECTORS=DETECTORS,
          LOSSES=LOSSES, build_loss=lambda cfg: None)
     _mod("mmdet.models.backbones")
-    _mod("mmdet.models.backbones.resnet", BasicBlock=nn.Identity)
+    _mod("mmdet.models.backbones.resnet", BasicBlock=BasicBlock)
     _mod("mmdet.models.utils")
     _mod("mmdet3d")
     _mod("mmdet3d.models")

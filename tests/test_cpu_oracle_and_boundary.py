@@ -198,3 +198,59 @@ def test_neck_port_vs_reference_golden():
     assert len(outs) == 4
     for i, o in enumerate(outs):
         assert_close(o, torch.from_numpy(gold[f"out{i}"]), 2e-5, f"neck port out[{i}] vs reference golden")
+
+
+# ------------------------------------------------------------------ boundary: DepthNet + the unmodified reference configs
+def test_depthnet_vs_reference_golden():
+    """occformer_b200.depthnet.DepthNet loads the REFERENCE class's own state_dict strictly and
+    reproduces its output (tests/golden/depthnet_small.npz: reference DepthNet under the shim, oracle/gen_golden.py;
+    the shim's DCN is an explicit-gather restatement of mmcv's DeformConv2dPack, ours goes through grid_sample)."""
+    from oracle.gen_golden import DEPTHNET_CASE as c
+    from occformer_b200.depthnet import DepthNet
+    gd = golden("depthnet_small.npz")
+    sd = {k[2:]: torch.from_numpy(gd[k]) for k in gd.files if k.startswith("w:")}
+    net = DepthNet(c["cin"], c["mid"], c["ctx"], c["D"], cam_channels=c["cam"]).eval()
+    net.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(c["xseed"])
+    x = torch.randn(c["B"] * c["N"], c["cin"], c["fH"], c["fW"], generator=g)
+    mlp = torch.randn(c["B"], c["N"], c["cam"], generator=g)
+    with torch.no_grad():
+        y = net(x, mlp)
+    assert_close(y, torch.from_numpy(gd["out"]), 1e-5, "DepthNet vs reference golden")
+
+
+@pytest.mark.parametrize("name", ["nusc_r50", "kitti"])
+def test_modules_build_from_unmodified_reference_config(name):
+    """The four hot-path sections of the reference's own config files (tests/golden/model_cfg_*.json = the ``model`` dict
+    of projects/configs/occformer_{nusc/occformer_nusc_r50_256x704,kitti/occformer_kitti}.py, extracted verbatim by
+    oracle/gen_golden.py) build through our registries, with the reference's state_dict key sets."""
+    import json
+    from occformer_b200 import BACKBONES, HEADS, NECKS, POSITIONAL_ENCODING
+    cfg = json.load(open(os.path.join(GOLDEN, f"model_cfg_{name}.json")))
+    vt = NECKS.build(cfg["img_view_transformer"])
+    enc = BACKBONES.build(cfg["img_bev_encoder_backbone"])
+    neck = NECKS.build(cfg["img_bev_encoder_neck"])
+    head = HEADS.build(cfg["pts_bbox_head"])
+    assert POSITIONAL_ENCODING.get("SinePositionalEncoding3D") is not None
+    kitti = name == "kitti"
+    assert vt.D == 112 and vt.cam_channels == (33 if kitti else 27) and vt.numC_input == (640 if kitti else 512)
+    assert vt.grid_size() == (128, 128, 16)
+    assert len(enc.layers) == 4 and [len(l) for l in enc.layers] == [2, 2, 2, 2]
+    assert neck.num_encoder_levels == 3 and len(neck.encoder.layers) == 6 and neck.num_heads == 8
+    assert head.num_queries == 100 and head.num_classes == (20 if kitti else 17) and head.num_transformer_decoder_layers == 9
+    # state_dict contracts: encoder / neck / head keys == the key sets validated against the real reference classes
+    E = 192
+    assert set(enc.state_dict()) == set(synth.make_encoder_state(128, [128, 256, 512, 1024], [2, 2, 2, 2], [1, 2, 2, 2]))
+    assert set(neck.state_dict()) == set(synth.make_neck_state([128, 256, 512, 1024], E, 6, 8, 3, 4, 4 * E))
+    assert set(head.state_dict()) == set(synth.make_head_state(E, 100, 20 if kitti else 17, 9, 3))
+    if not kitti:  # img_view_transformer.* of a reference checkpoint: dx / bx / nx / frustum + depth_net.*
+        want = json.load(open(os.path.join(GOLDEN, "depthnet_keys_nusc.json")))
+        mine = {k[len("depth_net."):]: list(v.shape) for k, v in vt.state_dict().items() if k.startswith("depth_net.")}
+        assert mine == want, "depth_net.* keys / shapes differ from the reference DepthNet(512, 512, 128, 112, cam_channels=27)"
+        assert {k for k in vt.state_dict() if not k.startswith("depth_net.")} == {"dx", "bx", "nx", "frustum"}
+    # get_mlp_input (occupancyformer.py:77) matches cam_channels
+    B, N = 1, (1 if kitti else 6)
+    r, t = torch.eye(3).view(1, 1, 3, 3).repeat(B, N, 1, 1), torch.zeros(B, N, 3)
+    k = torch.eye(4).view(1, 1, 4, 4).repeat(B, N, 1, 1) if kitti else r
+    bda = torch.eye(4).view(1, 4, 4) if kitti else torch.eye(3).view(1, 3, 3)
+    assert vt.get_mlp_input(r, t, k, r, t, bda).shape == (B, N, vt.cam_channels)
