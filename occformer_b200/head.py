@@ -107,6 +107,7 @@ class _Mask2FormerOccBase(nn.Module):
     def __init__(self, feat_channels, out_channels, num_occupancy_classes=20, num_queries=100,
                  num_transformer_feat_level=3, enforce_decoder_input_project=False, transformer_decoder=None,
                  positional_encoding=None, pooling_attn_mask=True, point_cloud_range=None, padding_mode="border",
+                 sample_weight_gamma=0.25,
                  loss_cls=None, loss_mask=None, loss_dice=None, train_cfg=None, test_cfg=None, init_cfg=None, **kwargs):
         super().__init__()
         self.num_occupancy_classes = self.num_classes = num_occupancy_classes
@@ -150,6 +151,7 @@ class _Mask2FormerOccBase(nn.Module):
                                         nn.Linear(feat_channels, out_channels))
         self.test_cfg, self.train_cfg = test_cfg, train_cfg
         self.pooling_attn_mask = pooling_attn_mask
+        self.sample_weight_gamma = sample_weight_gamma
         self.align_corners = True
         self.padding_mode = padding_mode
         self._prep = None
@@ -338,9 +340,20 @@ class _Mask2FormerOccBase(nn.Module):
                 for b, pts in enumerate(points)]
         return torch.cat(outs, dim=0)
 
+    def get_sampling_weights(self):
+        """mask2former_occ.py:158-166: class-frequency sampling weights ** gamma (KITTI heads; the nuScenes head samples
+        LiDAR points instead)."""
+        from . import sampling
+        self.sample_weights = sampling.class_sampling_weights(sampling.SEMANTIC_KITTI_CLASS_FREQUENCIES,
+                                                              self.sample_weight_gamma)
+        return self.sample_weights
+
     def forward_train(self, *a, **k):
-        raise NotImplementedError("occformer_b200 covers the inference forward (SURVEY.md section 8); training losses, the "
-                                  "Hungarian assigner and class-guided point sampling stay in the reference")
+        raise NotImplementedError(
+            "occformer_b200 covers the inference forward (SURVEY.md section 8).  The training step (losses, Hungarian "
+            "assigner) stays in the reference plugin; its class-guided point sampling (SURVEY.md A18 / A19) is available as "
+            "host functions under the reference names in occformer_b200.sampling, and forward() / simple_test() of this head "
+            "return the same cls / mask predictions the reference's loss code consumes.")
 
 
 @HEADS.register_module()

@@ -254,3 +254,38 @@ def test_modules_build_from_unmodified_reference_config(name):
     k = torch.eye(4).view(1, 1, 4, 4).repeat(B, N, 1, 1) if kitti else r
     bda = torch.eye(4).view(1, 4, 4) if kitti else torch.eye(3).view(1, 3, 3)
     assert vt.get_mlp_input(r, t, k, r, t, bda).shape == (B, N, vt.cam_channels)
+
+
+# ------------------------------------------------------------------ A18 / A19: class-guided sampling (host functions, RNG driven)
+def test_class_guided_sampling_host_functions():
+    """Distributional / structural checks only (RNG driven, not parity-checkable bit-wise)."""
+    from occformer_b200 import sampling as S
+    torch.manual_seed(0)
+    shape = (12, 10, 6)
+    idx = torch.randint(0, 720, (3, 50))
+    assert np.array_equal(S.unravel_indices(idx, shape).numpy(), np.stack(np.unravel_index(idx.numpy(), shape), -1))
+    vol = torch.randn(2, 1, *shape)
+    pts = torch.rand(2, 40, 3)
+    got = S.point_sample_3d(vol, pts[..., [2, 1, 0]], align_corners=True)
+    ref = torch.nn.functional.grid_sample(vol, (pts[..., [2, 1, 0]] * 2 - 1)[:, :, None, None], align_corners=True)[..., 0, 0]
+    assert torch.equal(got, ref) and got.shape == (2, 1, 40)
+    # two instances: a rare class (label 2, high weight) and a frequent one (label 1); voxels outside both are never drawn
+    gt_labels = torch.tensor([1, 2])
+    gt_masks = torch.zeros(2, *shape)
+    gt_masks[0, :6] = 1
+    gt_masks[1, 8:] = 1
+    w = S.class_sampling_weights(S.SEMANTIC_KITTI_CLASS_FREQUENCIES, 0.25)
+    assert w.min() == 1.0 and w[2] > w[1] > w[0]
+    pidx, pc = S.sample_valid_coords_with_frequencies(300, gt_labels, gt_masks, sample_weights=w)
+    occ = (gt_masks.sum(0) > 0).view(-1)
+    assert bool(occ[pidx].all()) and pidx.unique().numel() == 300 and float(pc.min()) >= 0 and float(pc.max()) <= 1
+    frac_rare = float((gt_masks[1].view(-1)[pidx] > 0).float().mean())
+    assert frac_rare > 0.5, "the rare class (3.4x the weight, 2/5 of the valid voxels) must dominate the draw"
+    mask_pred = torch.randn(2, *shape)
+    bi, bc = S.get_uncertain_point_coords_3d_with_frequency(mask_pred, None, [gt_labels], [gt_masks], w, 64, 3.0, 0.75)
+    assert bi.shape == (2, 64) and bc.shape == (2, 64, 3) and bool(occ[bi].all())
+    # the importance-sampled part are the most uncertain of the over-sampled candidates: |logit| there is small on average
+    assert float(mask_pred.view(2, -1).gather(1, bi[:, :48]).abs().mean()) < float(mask_pred.abs().mean())
+    lidar = [torch.cat([torch.rand(30, 3) * 20 - 10, torch.ones(30, 1)], 1)]
+    c = S.get_nusc_lidarseg_point_coords(torch.randn(2, 1, *shape), lidar, [gt_labels], 40, 3.0, 0.75, [-10, -10, -10, 10, 10, 10])
+    assert c.shape == (2, 40, 3)
