@@ -142,6 +142,12 @@ int occ_window_attention(const float* qkv /*S32*/, const float* qkv_bias /*S32 r
                          float* out /*S32*/, int B, int X, int Y, int Z, int C, int heads, int shift,
                          int qkv_head_major, occ_stream_t stream);
 
+/* The same attention with the QKV projection fused in (C == 128; csrc/swin_attn_fused.cu): tokn (rows, 128) S32 =
+ * LayerNorm1'ed tokens, wqkv (384, 128) S32 / bqkv (384) fp32 = WindowMSA.qkv with HEAD-MAJOR rows [head][q|k|v][32]; the
+ * q/k/v tensor never exists in HBM.  Returns -2 for C != 128 (use occ_gemm_bf16x3 + occ_window_attention). */
+int occ_swin_qkv_attention(const float* tokn, const float* wqkv, const float* bqkv, const float* bias_pad, float* out,
+                           int B, int X, int Y, int Z, int C, int heads, int shift, occ_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * MSDeformAttnPixelDecoder3D, the neck between encoder and head (P/occformer/necks/multiscale_deformattn_3d.py:143-248,
  * P/occformer/necks/multi_scale_deform_attn_3d.py:17-80,185-286).  Token rows are "level-major":

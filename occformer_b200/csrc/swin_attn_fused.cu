@@ -1,0 +1,397 @@
+// Shifted-window attention with the QKV projection fused in (C = 128): the kernel reads the LayerNorm'ed tokens once
+// (S32, 512 B per token) instead of a materialised q/k/v tensor (1.5 KB per token written by a GEMM and read back).
+//
+//   WindowMSA.forward: qkv = Linear(C -> 3C)(x) ... attn = softmax(q k^T * scale + bias [+ mask]) v
+//   (projects/mmdet3d_plugin/occformer/backbones/modules/window_attention.py:69-107), ShiftWindowMSA pad / roll / mask /
+//   partition / reverse (:168-242) as index arithmetic, exactly as in window_attn.cu (same geometry header).
+//
+// Work unit = (pair of windows, head), one head per CTA (gridDim.x is a multiple of the head count): the head's 96 x 128
+// slice of the qkv weight (rows [q | k | v] x 32, head-major) stays resident in shared memory for the whole kernel.
+// Per unit:
+//   loaders  (warps 12-15)  cp.async gather of the 128 token rows (49 + 49 real, S32) -> A tile, 4 K-major k-blocks
+//   MMA      (warp 0)       M1: D[128 x 96] = A W_h^T            (4 k-blocks x 6 tcgen05.mma 128x96x16: three bf16 passes)
+//                           QK: S = Q K^T, PV: O' = [P_hi; P_lo][V_hi | V_lo]   (as in window_attn.cu)
+//   two warpgroups (warps 4-7 / 8-11, even / odd units):
+//       convert : tcgen05.ld D -> + bias -> split -> Q / K / V operand tiles in shared memory (double buffered)
+//       softmax : S row -> scale, relative-position bias, shift mask, exp2 -> P (TMEM, split)      (unchanged)
+//       epilogue: O -> normalise -> S32 scatter to the token-ordered output (A operand of the projection GEMM)
+// The conversion of unit u+1 (other warpgroup) overlaps the softmax of unit u; M1(u+1) overlaps both.
+// HBM: tokens in (rows*C*4) + attention out (rows*C*4); the 4 head-CTAs of a group walk the same window pairs at the
+// same time, so three of the four token reads are L2 hits.
+#include "window_geom.cuh"
+
+namespace occ {
+
+constexpr int SF_C = 128;
+constexpr int SF_KB = SF_C / 32;                      // k-blocks of the projection
+constexpr int SF_W_BYTES = SF_KB * 96 * 128;          // 49152: W_h as 4 K-major SWIZZLE_128B tiles of 96 rows
+constexpr int SF_A_BYTES = SF_KB * 128 * 128;         // 65536: token tile, 4 k-blocks of 128 rows
+constexpr int SF_QKV_BYTES = 3 * WA_TILE;             // 49152: Q, K, V operand tiles of one unit
+constexpr int SF_META_BYTES = 1792;                   // rows (1024) + region (512) + same masks (144), padded
+constexpr int SF_META_SLOTS = 4;
+constexpr int SF_OFF_A = SF_W_BYTES;
+constexpr int SF_OFF_QKV = SF_OFF_A + SF_A_BYTES;                       // 114688
+constexpr int SF_OFF_BIAS = SF_OFF_QKV + 2 * SF_QKV_BYTES;              // 212992: relative-position bias (49, 52) * log2 e
+constexpr int SF_OFF_QB = SF_OFF_BIAS + WA_BIAS_BYTES;                  // 223232: this head's 96 qkv bias values
+constexpr int SF_OFF_META = SF_OFF_QB + 384;                            // 223616
+constexpr int SF_OFF_BAR = SF_OFF_META + SF_META_SLOTS * SF_META_BYTES; // 230784
+constexpr int SF_SMEM = SF_OFF_BAR + 256 + 1024;                        // 232064 <= 232448 (227 KB)
+constexpr uint32_t SF_TMEM_D = 0, SF_TMEM_S = 128, SF_TMEM_O = 384;     // D: 96 cols, S/P: 2 x 128, O: 2 x 64
+
+__global__ void __launch_bounds__(WA_THREADS, 1)
+swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const float* __restrict__ wqkv /*(384, 128) S32,
+                     head-major rows*/, const float* __restrict__ bqkv /*(384) fp32, head-major*/,
+                     const float* __restrict__ bias_pad /*(heads, 2404)*/, float* __restrict__ out, const WinGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sw = smem;
+  uint8_t* sa = smem + SF_OFF_A;
+  float* sb = reinterpret_cast<float*>(smem + SF_OFF_BIAS);
+  float* sqb = reinterpret_cast<float*>(smem + SF_OFF_QB);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SF_OFF_BAR);
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* d_ready = a_empty + 1;
+  uint64_t* d_free = d_ready + 1;
+  uint64_t* qkv_full = d_free + 1;    // [2]
+  uint64_t* qkv_empty = qkv_full + 2; // [2]
+  uint64_t* s_ready = qkv_empty + 2;  // [2]
+  uint64_t* p_ready = s_ready + 2;    // [2]
+  uint64_t* o_ready = p_ready + 2;    // [2]
+  uint64_t* o_free = o_ready + 2;     // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long npairs = (g.nwin + 1) / 2;
+  const int H = g.heads;
+  const int h = blockIdx.x % H;
+  const int pair0 = blockIdx.x / H, pair_stride = gridDim.x / H;
+  const long long n_units = (npairs > pair0) ? (npairs - pair0 + pair_stride - 1) / pair_stride : 0;
+
+  // resident operands of this head: W_h (96 rows of the head-major qkv weight) as 4 K-major swizzled k-blocks, its bias,
+  // the relative-position bias table (log2 domain)
+  for (int i = threadIdx.x; i < 96 * 32; i += WA_THREADS) {  // 16-byte chunks: row r, chunk cc of the 512-byte row
+    const int r = i >> 5, cc = i & 31;
+    const int kb = cc >> 3, c = cc & 7;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(wqkv + ((size_t)h * 96 + r) * SF_C) + cc);
+    *reinterpret_cast<float4*>(sw + kb * (96 * 128) + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+  }
+  if (threadIdx.x < 96) sqb[threadIdx.x] = bqkv[h * 96 + threadIdx.x];
+  for (int i = threadIdx.x; i < WT * WA_BIAS_LD; i += WA_THREADS) {
+    const int r = i / WA_BIAS_LD, c = i % WA_BIAS_LD;
+    sb[i] = c < WT ? bias_pad[(size_t)h * WA_BIAS_FLOATS + r * WT + c] * 1.4426950408889634f : 0.f;
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(a_full, 256);   // per loader thread: one cp.async arrival + one release arrival
+    mbar_init(a_empty, 1);    // tcgen05.commit after M1
+    mbar_init(d_ready, 1);    // tcgen05.commit after M1
+    mbar_init(d_free, 4);     // the four warps of the converting warpgroup
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qkv_full[i], 4);
+      mbar_init(&qkv_empty[i], 1);
+      mbar_init(&s_ready[i], 1);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&o_ready[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  fence_proxy_async_smem();  // W_h was written with generic stores; the MMAs read it through the async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp >= 12) {
+    // ===================================================================== loaders
+    const int l = threadIdx.x - 12 * 32;  // 0..127
+    for (long long u = 0; u < n_units; ++u) {
+      const long long pair = pair0 + u * pair_stride;
+      uint8_t* meta = smem + SF_OFF_META + (size_t)(u % SF_META_SLOTS) * SF_META_BYTES;
+      long long* rows = reinterpret_cast<long long*>(meta);
+      int* region = reinterpret_cast<int*>(meta + 1024);
+      mbar_wait(a_empty, (uint32_t)((u & 1) ^ 1));
+      {
+        const long long win = 2 * pair + (l >> 6);
+        const int t = l & 63;
+        long long r = -2;  // -2: MMA padding row, -1: window pad token (zero token: q/k/v = bias)
+        int reg = 0;
+        if (t < WT && win < g.nwin) {
+          long long w = win;
+          const int wy = (int)(w % g.nWy); w /= g.nWy;
+          const int wx = (int)(w % g.nWx); w /= g.nWx;
+          r = window_token_row(g, (int)w, wx, wy, t, &reg);
+        }
+        rows[l] = r;
+        region[l] = reg;
+      }
+      {
+        const int t = l & 63, wl = l >> 5;
+        const bool tok = t < WT;
+        uint32_t* same32 = reinterpret_cast<uint32_t*>(meta + 1536);
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+          const uint32_t bal = __ballot_sync(0xffffffffu, tok && region[l] == r);
+          if (lane == 0) same32[((wl >> 1) * 9 + r) * 2 + (wl & 1)] = bal;
+        }
+      }
+      named_bar_sync(2, 128);
+      {  // thread l copies 16-byte chunk c = l & 7 of rows (l >> 3) + 16*rr, for the 4 k-blocks of the token row
+        const int c = l & 7, rb = l >> 3;
+        const int off = (c ^ (rb & 7)) << 4;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = rb + 16 * rr;
+          const long long grow = rows[r];
+          uint8_t* drow = sa + r * 128 + off;
+          if (grow < 0) {  // zero token: the projection adds the bias in the conversion step
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int kb = 0; kb < SF_KB; ++kb) *reinterpret_cast<float4*>(drow + kb * (128 * 128)) = z;
+          } else {
+            const float* src = tokn + grow * SF_C + c * 4;
+#pragma unroll
+            for (int kb = 0; kb < SF_KB; ++kb) cp_async_16(drow + kb * (128 * 128), src + kb * 32);
+          }
+        }
+      }
+      cp_async_mbar_arrive_noinc(a_full);
+      mbar_arrive(a_full);
+    }
+    cp_async_wait<0>();
+  } else if (warp == 0) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC_M1 = make_idesc_bf16(128, 96, 0, 0);
+      constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 2 * HD, 0, 1);
+      long long n1 = 0, nq = 0, np = 0;
+      while (np < n_units) {
+        // M1(n1): token tile landed, D free (the conversion of unit n1 - 1 has read it)
+        if (n1 < n_units && mbar_test(a_full, (uint32_t)(n1 & 1)) && mbar_test(d_free, (uint32_t)((n1 & 1) ^ 1))) {
+          fence_proxy_async_smem();
+          tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < SF_KB; ++kb) {
+            const uint64_t adesc = make_sw128_desc(smem_u32(sa + kb * (128 * 128)), 1024, 16);
+            const uint64_t bdesc = make_sw128_desc(smem_u32(sw + kb * (96 * 128)), 1024, 16);
+            mma_bf16x3_ss(tmem_base + SF_TMEM_D, adesc, bdesc, IDESC_M1, kb != 0);
+          }
+          mma_commit(a_empty);
+          mma_commit(d_ready);
+          ++n1;
+        }
+        // QK(nq): Q / K / V tiles of the unit converted; S/P buffer free once PV(nq - 2) has been issued
+        if (nq < n1 && nq - np < 2 && mbar_test(&qkv_full[nq & 1], (uint32_t)((nq >> 1) & 1))) {
+          fence_proxy_async_smem();
+          tc_fence_after();
+          const uint32_t qaddr = smem_u32(smem + SF_OFF_QKV + (size_t)(nq & 1) * SF_QKV_BYTES);
+          const uint64_t qdesc = make_sw128_desc(qaddr, 1024, 16);
+          const uint64_t kdesc = make_sw128_desc(qaddr + WA_TILE, 1024, 16);
+          mma_bf16x3_ss(tmem_base + SF_TMEM_S + (uint32_t)(nq & 1) * 128, qdesc, kdesc, IDESC_QK, 0u);
+          mma_commit(&s_ready[nq & 1]);
+          ++nq;
+        }
+        if (np < nq) {
+          const int tb = (int)(np & 1);
+          const uint32_t k = (uint32_t)(np >> 1);
+          if (mbar_test(&p_ready[tb], k & 1) && mbar_test(&o_free[tb], (k & 1) ^ 1)) {
+            tc_fence_after();
+            const uint32_t vaddr = smem_u32(smem + SF_OFF_QKV + (size_t)tb * SF_QKV_BYTES + 2 * WA_TILE);
+            const uint64_t vdesc = make_sw128_desc(vaddr, 1024, 1024);
+            const uint32_t p_tmem = tmem_base + SF_TMEM_S + tb * 128;
+            const uint32_t o_tmem = tmem_base + SF_TMEM_O + tb * 2 * HD;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint32_t pc = p_tmem + (kk >> 1) * 32 + (kk & 1) * 8;
+              mma_bf16_ts(o_tmem, pc, vdesc + (uint64_t)(kk * 128), IDESC_PV, kk != 0);
+              mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);
+            }
+            mma_commit(&o_ready[tb]);
+            mma_commit(&qkv_empty[tb]);  // Q, K (read by QK, issued earlier) and V of this buffer are free again
+            ++np;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===================================================================== conversion / softmax / epilogue warpgroups
+    const int wg = (warp - 4) >> 2;
+    const int i = ((warp & 3) << 5) + lane;  // token row of the tile = TMEM lane
+    const int half = i >> 6, t = i & 63;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const float scale = 0.17677669529663687f;  // 32^-0.5
+    const int tb = wg;
+    for (long long u = wg; u < n_units; u += 2) {
+      const uint32_t k = (uint32_t)(u >> 1);
+      const uint8_t* meta = smem + SF_OFF_META + (size_t)(u % SF_META_SLOTS) * SF_META_BYTES;
+      const long long* rows = reinterpret_cast<const long long*>(meta);
+      const int* region = reinterpret_cast<const int*>(meta + 1024);
+      // ---- conversion: D row (q | k | v of this head) + bias -> S32 rows of the Q / K / V operand tiles
+      mbar_wait(d_ready, (uint32_t)(u & 1));
+      mbar_wait(&qkv_empty[tb], (k & 1) ^ 1);
+      tc_fence_after();
+      uint32_t ra[32], rb[32];
+      {
+        uint8_t* qkv_s = smem + SF_OFF_QKV + (size_t)tb * SF_QKV_BYTES;
+        const int sw7 = i & 7;
+#pragma unroll 1
+        for (int which = 0; which < 3; ++which) {  // q, k, v: 32 accumulator columns each (one at a time: register budget)
+          tmem_ld_32x32(lane_base + SF_TMEM_D + which * 32, ra);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + sqb[which * 32 + j];
+          split_chunk32(v, rb);
+          uint8_t* drow = qkv_s + which * WA_TILE + i * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(drow + ((c ^ sw7) << 4)) = make_uint4(rb[4 * c], rb[4 * c + 1], rb[4 * c + 2], rb[4 * c + 3]);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(d_free);
+          mbar_arrive(&qkv_full[tb]);
+        }
+      }
+      // ---- softmax (as window_attn.cu)
+      mbar_wait(&s_ready[tb], k & 1);
+      tc_fence_after();
+      const long long my_row = rows[i];
+      const int my_reg = region[i];
+      const uint2 same = reinterpret_cast<const uint2*>(meta + 1536)[half * 9 + my_reg];
+      const uint32_t diff_lo = ~same.x, diff_hi = ~same.y & 0x1FFFFu;
+      const bool uniform = (diff_lo | diff_hi) == 0u;
+      const float4* brow4 = reinterpret_cast<const float4*>(sb + (t < WT ? t : 0) * WA_BIAS_LD);
+      const uint32_t s_col = lane_base + SF_TMEM_S + tb * 128 + half * 64;
+      tmem_ld_32x32(s_col, ra);
+      tmem_ld_32x32(s_col + 32, rb);
+      tmem_ld_wait();
+      const float sl2 = scale * 1.4426950408889634f, neg = -100.0f * 1.4426950408889634f;
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 bv = brow4[j4];
+        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * j4 + e;
+          float z = fmaf(__uint_as_float(ra[j]), sl2, bb[e]);
+          if (!uniform) z += ((diff_lo >> j) & 1u) ? neg : 0.f;
+          ra[j] = __float_as_uint(z);
+          mx[e] = fmaxf(mx[e], z);
+        }
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < 5; ++j4) {
+        const float4 bv = brow4[8 + j4];
+        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * j4 + e;
+          if (32 + j < WT) {
+            float z = fmaf(__uint_as_float(rb[j]), sl2, bb[e]);
+            if (!uniform) z += ((diff_hi >> j) & 1u) ? neg : 0.f;
+            rb[j] = __float_as_uint(z);
+            mx[e] = fmaxf(mx[e], z);
+          }
+        }
+      }
+      const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      float sm4[4] = {0.f, 0.f, 0.f, 0.f};
+      float pa[32], pb[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float p = ex2_approx(__uint_as_float(ra[j]) - m);
+        sm4[j & 3] += p;
+        pa[j] = p;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float p = 0.f;
+        if (j < WT - 32) {
+          p = ex2_approx(__uint_as_float(rb[j]) - m);
+          sm4[j & 3] += p;
+        }
+        pb[j] = p;
+      }
+      const float sum = (sm4[0] + sm4[1]) + (sm4[2] + sm4[3]);
+      split_chunk32(pa, ra);
+      split_chunk32(pb, rb);
+      tmem_st_32x32(s_col, ra);
+      tmem_st_32x32(s_col + 32, rb);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ra[j] = 0u;
+      const uint32_t o_col = lane_base + SF_TMEM_S + tb * 128 + (half ^ 1) * 64;
+      tmem_st_32x32(o_col, ra);
+      tmem_st_32x32(o_col + 32, ra);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[tb]);
+      // ---- epilogue
+      mbar_wait(&o_ready[tb], k & 1);
+      tc_fence_after();
+      tmem_ld_32x32(lane_base + SF_TMEM_O + tb * 2 * HD, ra);
+      tmem_ld_32x32(lane_base + SF_TMEM_O + tb * 2 * HD + HD, rb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[tb]);
+      if (t < WT && my_row >= 0) {
+        const float inv = 1.0f / sum;
+        float o[32];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] = (__uint_as_float(ra[d]) + __uint_as_float(rb[d])) * inv;
+        split_chunk32(o, ra);
+        uint4* dst = reinterpret_cast<uint4*>(out + my_row * g.C + h * HD);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) dst[d] = make_uint4(ra[4 * d], ra[4 * d + 1], ra[4 * d + 2], ra[4 * d + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace occ
+
+using namespace occ;
+
+// tokn (rows, 128) S32 = LayerNorm1'ed tokens (rows = B*X*Y*(Z+1), voxel tokens then BEV tokens); wqkv (384, 128) S32 and
+// bqkv (384) fp32 with HEAD-MAJOR rows [head][q|k|v][32]; bias_pad as occ_window_attention; out (rows, 128) S32.
+// Returns -2 (unsupported) for C != 128: the caller then runs occ_gemm_bf16x3 + occ_window_attention.
+extern "C" int occ_swin_qkv_attention(const float* tokn, const float* wqkv, const float* bqkv, const float* bias_pad,
+                                      float* out, int B, int X, int Y, int Z, int C, int heads, int shift,
+                                      cudaStream_t stream) {
+  OCC_REQUIRE(tokn && wqkv && bqkv && bias_pad && out);
+  OCC_REQUIRE(B > 0 && X > 0 && Y > 0 && Z > 0 && heads > 0 && C == heads * HD);
+  if (C != SF_C) return OCC_EUNSUPPORTED;
+  OCC_REQUIRE((reinterpret_cast<uintptr_t>(tokn) & 15) == 0 && (reinterpret_cast<uintptr_t>(wqkv) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(bias_pad) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  WinGeom g;
+  g.B = B; g.X = X; g.Y = Y; g.Z = Z; g.C = C; g.heads = heads; g.shift = shift ? 1 : 0;
+  g.head_major = 1;
+  g.nWx = (X + WS - 1) / WS; g.nWy = (Y + WS - 1) / WS;
+  g.Xp = g.nWx * WS; g.Yp = g.nWy * WS;
+  g.vox_rows = (long long)B * X * Y * Z;
+  g.nwin = (long long)B * (Z + 1) * g.nWx * g.nWy;
+  OCC_REQUIRE(g.nwin < (1ll << 31));
+  static_assert(SF_SMEM <= 227 * 1024, "shared memory budget");
+  OCC_ENSURE_SMEM(swin_qkv_attn_kernel, SF_SMEM);
+  const long long npairs = (g.nwin + 1) / 2;
+  long long groups = sm_count() / heads;
+  if (groups > npairs) groups = npairs;
+  if (groups < 1) groups = 1;
+  swin_qkv_attn_kernel<<<(int)(groups * heads), WA_THREADS, SF_SMEM, stream>>>(tokn, wqkv, bqkv, bias_pad, out, g);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}

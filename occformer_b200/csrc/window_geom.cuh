@@ -1,0 +1,57 @@
+// Shared geometry of the two window-attention kernels (window_attn.cu: q/k/v from HBM; swin_attn_fused.cu: QKV
+// projection inside the kernel): 7x7 windows over the B*(Z+1) X-Y images, token -> global row, shift-mask regions.
+#pragma once
+#include "occ_common.cuh"
+#include "occ_ptx.cuh"
+
+namespace occ {
+
+constexpr int WS = 7;
+constexpr int WT = WS * WS;  // 49 tokens
+constexpr int HD = 32;       // head dim (multihead_base_channel, dualpath_block.py:32)
+constexpr int WA_STAGES = 4;
+constexpr int WA_TILE = 128 * HD * 4;                  // 16 KB: 128 rows x 128 B
+constexpr int WA_BIAS_FLOATS = 2404;                   // 49*49 padded to a 16-byte multiple
+constexpr int WA_OFF_ROWS = 3 * WA_TILE;               // 49152 (8-byte aligned)
+constexpr int WA_OFF_REGION = WA_OFF_ROWS + 128 * 8;   // 50176
+constexpr int WA_OFF_SAME = WA_OFF_REGION + 128 * 4;   // 50688: per window half, 9 x uint64 "key j is in region r" masks
+constexpr int WA_OFF_UNI = WA_OFF_SAME + 2 * 9 * 8;    // 50832: per window half, 1 if all 49 tokens share a region
+constexpr int WA_OFF_SRC = WA_OFF_UNI + 8;             // 50840: per row, the global source pointer of its q slice (8 B)
+constexpr int WA_STAGE_BYTES = 51 * 1024;              // 52224 >= 50840 + 1024, multiple of 1024
+constexpr int WA_BIAS_LD = 52;                         // padded bias row pitch (floats): 13 conflict-free LDS.128 per row
+constexpr int WA_BIAS_BYTES = 10240;                   // resident bias of this CTA's head, (49, 52) floats, * log2(e)
+constexpr int WA_THREADS = 512;
+constexpr uint32_t WA_TMEM_COLS = 512;                 // S/P: 2 x 128, O: 2 x 64
+
+struct WinGeom {
+  int B, X, Y, Z, C, heads, shift;
+  int head_major;  // qkv columns ordered [head][q|k|v][32] instead of the reference's [q|k|v][head][32]
+  int Xp, Yp, nWx, nWy;
+  long long vox_rows;  // B*X*Y*Z
+  long long nwin;
+};
+
+// token t of window (img, wx, wy) -> global token row (or -1 for a pad token) and shift-mask region id
+__device__ __forceinline__ long long window_token_row(const WinGeom& g, int img, int wx, int wy, int t, int* region) {
+  const int i = t / WS, j = t % WS;
+  const int xs = wx * WS + i, ys = wy * WS + j;
+  int x = xs, y = ys;
+  if (g.shift) {
+    x = xs + 3; if (x >= g.Xp) x -= g.Xp;
+    y = ys + 3; if (y >= g.Yp) y -= g.Yp;
+    const int rx = xs < g.Xp - WS ? 0 : (xs < g.Xp - 3 ? 1 : 2);
+    const int ry = ys < g.Yp - WS ? 0 : (ys < g.Yp - 3 ? 1 : 2);
+    *region = rx * 3 + ry;
+  } else {
+    *region = 0;
+  }
+  if (x >= g.X || y >= g.Y) return -1;
+  if (img < g.B * g.Z) {
+    const int b = img / g.Z, z = img % g.Z;
+    return (((long long)b * g.X + x) * g.Y + y) * g.Z + z;
+  }
+  const int b = img - g.B * g.Z;
+  return g.vox_rows + ((long long)b * g.X + x) * g.Y + y;
+}
+
+}  // namespace occ

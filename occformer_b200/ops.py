@@ -355,6 +355,19 @@ def window_attention(qkv, qkv_bias, bias_pad, B, X, Y, Z, C, heads, shift, head_
     return out
 
 
+def swin_qkv_attention(tokn, w_qkv, b_qkv, bias_pad, B, X, Y, Z, C, heads, shift):
+    """QKV projection + (shifted) window attention in one kernel (C == 128): tokn (rows, C) S32, w_qkv (3C, C) S32 and
+    b_qkv (3C,) fp32 with head-major rows -> attention output (rows, C) S32."""
+    _chk(tokn, "tokn"), _chk(w_qkv, "w_qkv"), _chk(b_qkv, "b_qkv")
+    rows = B * X * Y * (Z + 1)
+    assert tokn.shape == (rows, C) and w_qkv.shape == (3 * C, C)
+    out = torch.empty((rows, C), dtype=torch.float32, device=tokn.device)
+    check(lib().occ_swin_qkv_attention(_ptr(tokn), _ptr(w_qkv), _ptr(b_qkv), _ptr(bias_pad), _ptr(out), B, X, Y, Z, C, heads,
+                                       int(shift), _stream(tokn)), "occ_swin_qkv_attention")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- decoder head
 def sine_pos3d(X, Y, Z, num_feats, device, temperature=10000.0, scale=6.283185307179586, eps=1e-6, offset=0.0):
     out = torch.empty((X * Y * Z, 3 * num_feats), dtype=torch.float32, device=device)
