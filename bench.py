@@ -35,12 +35,27 @@ import torch.distributed as dist  # noqa: E402
 
 METRIC = "samples/sec (6-cam->200x200x16 voxel fwd)"
 UNIT = "samples/s"
-WORKLOAD = "nusc_r50_6cam_256x704_to_200x200x16"
-N_CAMS, INPUT_SIZE, DOWNSAMPLE, C_TRANS = 6, (256, 704), 16, 128
+DOWNSAMPLE, C_TRANS = 16, 128
 PLANES, NUMS, STRIDES = [128, 256, 512, 1024], [2, 2, 2, 2], [1, 2, 2, 2]
-EMBED, QUERIES, CLASSES, DEC_LAYERS, HEADS = 192, 100, 17, 9, 6
-GRID = "nusc_200"
+EMBED, QUERIES, DEC_LAYERS, HEADS = 192, 100, 9, 6
+# the workload (occformer_b200.synth.WORKLOADS): default = BASELINE.json configs[2], the configuration the metric is quoted
+# on; --workload kitti = configs[1] (its own metric string says so)
+WL = "nusc_200"
+WORKLOAD = "nusc_r50_6cam_256x704_to_200x200x16"
+N_CAMS, INPUT_SIZE, CLASSES, GRID = 6, (256, 704), 17, "nusc_200"
 PC_RANGE = [-40.0, -40.0, -1.0, 40.0, 40.0, 5.4]
+OCC_SIZE = [200, 200, 16]
+HEAD_TYPE = "Mask2FormerNuscOccHead"
+
+
+def set_workload(name):
+    global WL, WORKLOAD, N_CAMS, INPUT_SIZE, CLASSES, GRID, PC_RANGE, OCC_SIZE, HEAD_TYPE, METRIC
+    from occformer_b200 import synth
+    w = synth.WORKLOADS[name]
+    WL, WORKLOAD, N_CAMS, INPUT_SIZE, CLASSES, GRID = name, w["name"], w["cams"], tuple(w["input_size"]), w["classes"], w["grid"]
+    PC_RANGE, OCC_SIZE, HEAD_TYPE = list(w["pc"]), list(w["occ"]), w["head"]
+    if name != "nusc_200":
+        METRIC = f"samples/sec ({w['name']} voxel fwd)"
 
 
 def peaks():
@@ -105,7 +120,6 @@ class ClockSampler:
 # workload construction
 # ----------------------------------------------------------------------------------------------------------------------
 NECK = dict(strides=[2, 4, 8, 16], layers=6, heads=8, levels=3, points=4, ffn=4 * EMBED)
-OCC_SIZE = [200, 200, 16]
 STAGES_ALL = ["view_transformer(lift_splat)", "occupancy_encoder", "msdeform_pixel_decoder_3d", "mask2former_head.simple_test"]
 
 
@@ -136,7 +150,7 @@ def build_b200(dev):
                                                                           NECK["ffn"])))
     neck.load_state_dict(synth.make_neck_state(PLANES, EMBED, NECK["layers"], NECK["heads"], NECK["levels"], NECK["points"],
                                                NECK["ffn"], seed=2), strict=True)
-    head = HEAD_REG.build(dict(type="Mask2FormerNuscOccHead", **head_cfg(EMBED, QUERIES, CLASSES, DEC_LAYERS, HEADS, PC_RANGE)))
+    head = HEAD_REG.build(dict(type=HEAD_TYPE, **head_cfg(EMBED, QUERIES, CLASSES, DEC_LAYERS, HEADS, PC_RANGE)))
     head.load_state_dict(synth.make_head_state(EMBED, QUERIES, CLASSES, DEC_LAYERS, 3, seed=1), strict=True)
     return vt, enc.to(dev).eval(), neck.to(dev).eval(), head.to(dev).eval()
 
@@ -148,7 +162,7 @@ def host_inputs(batch, seed):
     D = 112
     dd, feat = synth.lift_inputs(batch, N_CAMS, D, fH, fW, C_TRANS, seed=seed)
     x = torch.cat([dd, feat], dim=1).view(batch, N_CAMS, D + C_TRANS, fH, fW).contiguous()
-    cams = synth.nusc_cameras(batch, N_CAMS, INPUT_SIZE)
+    cams = synth.workload_cameras(WL, batch)
     out = {"x": x, **cams}
     return {k: (v.pin_memory() if torch.cuda.is_available() else v) for k, v in out.items()}
 
@@ -188,7 +202,7 @@ def cpu_sample(threads):
     torch.set_num_threads(threads)
     gc = synth.grid_config(GRID)
     frustum = port.create_frustum(INPUT_SIZE, DOWNSAMPLE, gc["dbound"])
-    cams = synth.nusc_cameras(1, N_CAMS, INPUT_SIZE)
+    cams = synth.workload_cameras(WL, 1)
     D, fH, fW = frustum.shape[:3]
     dd, feat = synth.lift_inputs(1, N_CAMS, D, fH, fW, C_TRANS, seed=0)
     dx, bx, nx = port.gen_dx_bx(gc["xbound"], gc["ybound"], gc["zbound"])
@@ -283,7 +297,8 @@ def rooflines(pipe, dev, peak):
     Algorithmic work per launch = SURVEY.md 8(d) per-unit figures x units per launch."""
     from occformer_b200 import ops, synth
     B = pipe.batch
-    X, Y, Z, C = 200, 200, 16, 128
+    C = 128
+    X, Y, Z = pipe.vt.grid_size()
     flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     # ---- 1. Conv3d 3x3x3, C = 128, stage-0 grid: the largest FLOP item of the step
     x = ops.to_split(torch.randn(B, X, Y, Z, C, device=dev))
@@ -293,7 +308,7 @@ def rooflines(pipe, dev, peak):
     ms = _time_cuda(lambda: ops.conv(x, w2, ks, gn_stats=stats, cpg=4), dev, flush=flush)
     flops = 2.0 * 27 * C * C * B * X * Y * Z
     ach = flops / (ms * 1e-3) / 1e12
-    conv = {"kernel": "gemm_bf16x3_kernel<conv3d 3x3x3, C=128, 200x200x16>", "bound": "tensor", "achieved": ach,
+    conv = {"kernel": f"gemm_bf16x3_kernel<conv3d 3x3x3, C=128, {X}x{Y}x{Z}>", "bound": "tensor", "achieved": ach,
             "peak": peak["tf"], "unit": "TFLOP/s", "frac": ach / peak["tf"], "traffic": None, "passes": 3,
             "frac_of_3pass_ceiling": 3.0 * ach / peak["tf"], "ms_per_launch": ms,
             "peak_src": f"bf16 dense burst, {peak['src']}",
@@ -311,7 +326,7 @@ def rooflines(pipe, dev, peak):
     nwin = B * (Z + 1) * ((X + 6) // 7) * ((Y + 6) // 7)
     fl = nwin * 4.0 * 49 * 49 * C  # QK^T + PV per window, all heads (4*49^2*C)
     by = rows * 4.0 * C * 4       # qkv read + out write
-    wattn = {"kernel": "window_attn_tc_kernel (stage 0, 200x200x(16+1) images)", "bound": "hbm",
+    wattn = {"kernel": f"window_attn_tc_kernel (stage 0, {X}x{Y}x({Z}+1) images)", "bound": "hbm",
              "achieved": by / (ms * 1e-3) / 1e9, "peak": peak["hbm"], "unit": "GB/s", "frac": by / (ms * 1e-3) / 1e9 / peak["hbm"],
              "traffic": None, "ms_per_launch": ms, "algorithmic_tflops": fl / (ms * 1e-3) / 1e12,
              "tensor_frac_algorithmic": fl / (ms * 1e-3) / 1e12 / peak["tf"], "peak_src": peak["src"],
@@ -323,7 +338,7 @@ def rooflines(pipe, dev, peak):
     fH, fW = INPUT_SIZE[0] // DOWNSAMPLE, INPUT_SIZE[1] // DOWNSAMPLE
     dd, feat = synth.lift_inputs(B, N_CAMS, 112, fH, fW, C_TRANS, seed=0)
     dd, feat = dd.to(dev), feat.to(dev)
-    cams = {k: v.to(dev) for k, v in synth.nusc_cameras(B, N_CAMS, INPUT_SIZE).items()}
+    cams = {k: v.to(dev) for k, v in synth.workload_cameras(WL, B).items()}
     vt = pipe.vt
     dxbx = vt._host_params()
     geom = vt.get_geometry(**cams)
@@ -333,7 +348,7 @@ def rooflines(pipe, dev, peak):
     npts = B * N_CAMS * 112 * fH * fW
     V = B * X * Y * Z
     by = npts * 4 + B * N_CAMS * fH * fW * C_TRANS * 4 + npts * 12 + V * C_TRANS * 4  # SURVEY 8(d) fused-lift formula
-    pool = {"kernel": "vp_index_geom + vp_pool_kernel (fused lift-splat, 6 cams -> 200x200x16)", "bound": "hbm",
+    pool = {"kernel": f"vp_index_geom + vp_pool_kernel (fused lift-splat, {N_CAMS} cams -> {X}x{Y}x{Z})", "bound": "hbm",
             "achieved": by / (ms_pool * 1e-3) / 1e9, "peak": peak["hbm"], "unit": "GB/s",
             "frac": by / (ms_pool * 1e-3) / 1e9 / peak["hbm"], "traffic": None, "ms_per_launch": ms_pool,
             "with_prologue": {"ms": ms_all, "achieved": by / (ms_all * 1e-3) / 1e9, "frac": by / (ms_all * 1e-3) / 1e9 / peak["hbm"]},
@@ -489,10 +504,13 @@ def main():
     ap.add_argument("--batch", type=int, default=4,
                     help="samples per GPU per step (4 = BASELINE.json configs[3]: batch 32 over 8 GPUs)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="nusc_200", choices=["nusc_200", "nusc_ref", "kitti", "nusc_r101"],
+                    help="nusc_200 = BASELINE.json configs[2] (the metric's configuration); kitti = configs[1]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    set_workload(args.workload)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -10,6 +10,7 @@ GRIDS = {
     "pr1": ([-20.0, 20.0, 0.8], [-20.0, 20.0, 0.8], [-2.0, 4.4, 0.8]),          # 50 x 50 x 8
     "nusc_ref": ([-51.2, 51.2, 0.8], [-51.2, 51.2, 0.8], [-5.0, 3.0, 0.5]),     # 128 x 128 x 16
     "nusc_200": ([-40.0, 40.0, 0.4], [-40.0, 40.0, 0.4], [-1.0, 5.4, 0.4]),     # 200 x 200 x 16
+    "kitti": ([0.0, 51.2, 0.4], [-25.6, 25.6, 0.4], [-2.0, 4.4, 0.4]),          # 128 x 128 x 16 (occformer_kitti.py:22-46)
 }
 DBOUND = [2.0, 58.0, 0.5]
 
@@ -26,6 +27,24 @@ def _yaw(deg):
 
 
 CAM2EGO_AXES = torch.tensor([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+
+
+# the workloads of BASELINE.json `configs` (shapes: SURVEY.md section 8 legend): cameras, input, lift grid, output grid, classes
+WORKLOADS = {
+    "nusc_200": dict(name="nusc_r50_6cam_256x704_to_200x200x16", cams=6, input_size=(256, 704), grid="nusc_200",
+                     occ=[200, 200, 16], pc=[-40.0, -40.0, -1.0, 40.0, 40.0, 5.4], classes=17, head="Mask2FormerNuscOccHead"),
+    "nusc_ref": dict(name="nusc_r50_6cam_256x704_to_128x128x16_occ256x256x32", cams=6, input_size=(256, 704), grid="nusc_ref",
+                     occ=[256, 256, 32], pc=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], classes=17, head="Mask2FormerNuscOccHead"),
+    "kitti": dict(name="semantickitti_1cam_384x1280_to_128x128x16_occ256x256x32", cams=1, input_size=(384, 1280), grid="kitti",
+                  occ=[256, 256, 32], pc=[0.0, -25.6, -2.0, 51.2, 25.6, 4.4], classes=20, head="Mask2FormerOccHead"),
+    "nusc_r101": dict(name="nusc_r101_6cam_896x1600_to_200x200x16", cams=6, input_size=(896, 1600), grid="nusc_200",
+                      occ=[200, 200, 16], pc=[-40.0, -40.0, -1.0, 40.0, 40.0, 5.4], classes=17, head="Mask2FormerNuscOccHead"),
+}
+
+
+def workload_cameras(wl, B=1):
+    w = WORKLOADS[wl]
+    return kitti_camera(B, w["input_size"]) if wl == "kitti" else nusc_cameras(B, w["cams"], w["input_size"])
 
 
 def nusc_cameras(B=1, N=6, input_size=(256, 704)):
@@ -48,6 +67,22 @@ def nusc_cameras(B=1, N=6, input_size=(256, 704)):
 
     return dict(rots=rep(rots), trans=rep(trans), intrins=rep(intrins), post_rots=rep(post_rots),
                 post_trans=rep(post_trans), bda=rep(bda))
+
+
+def kitti_camera(B=1, input_size=(384, 1280)):
+    """SemanticKITTI-like single left camera (BASELINE.json configs[1]): 4x4 P2 intrinsics with the shift column
+    (semantic_kitti_lss_dataset.py:62-64 hands a 4x4 matrix over), camera -> LiDAR axes, 4x4 homogeneous bda."""
+    H, W = input_size
+    resize = W / 1226.0
+    rots = (_yaw(0.0) @ CAM2EGO_AXES).view(1, 1, 3, 3).repeat(B, 1, 1, 1)
+    trans = torch.tensor([0.27, 0.0, -0.08]).view(1, 1, 3).repeat(B, 1, 1)
+    K = torch.eye(4)
+    K[:3, :4] = torch.tensor([[707.09, 0.0, 604.08, 45.76], [0.0, 707.09, 180.51, -0.35], [0.0, 0.0, 1.0, 0.005]])
+    post_rots = torch.diag(torch.tensor([resize, resize, 1.0])).view(1, 1, 3, 3).repeat(B, 1, 1, 1)
+    post_trans = torch.tensor([0.0, -float(int(370 * resize) - H), 0.0]).view(1, 1, 3).repeat(B, 1, 1)
+    return dict(rots=rots.contiguous(), trans=trans.contiguous(), intrins=K.view(1, 1, 4, 4).repeat(B, 1, 1, 1).contiguous(),
+                post_rots=post_rots.contiguous(), post_trans=post_trans.contiguous(),
+                bda=torch.eye(4).view(1, 4, 4).repeat(B, 1, 1).contiguous())
 
 
 def pr1_camera(B=1):

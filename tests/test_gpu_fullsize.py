@@ -4,6 +4,8 @@ simple_test), against the CPU oracle (oracle/port.py, pinned to the reference) o
 
   * nusc_200: BASELINE.json configs[2]  (6 cams 256x704 -> 200x200x16, occ 200x200x16)      = bench.py's workload
   * nusc_ref: the reference's own grid  (128x128x16 -> occ 256x256x32, occformer_nusc_r50_256x704.py:17-20,41-46)
+  * kitti   : BASELINE.json configs[1]  (1 cam 384x1280, 4x4 P2 intrinsics, 4x4 bda, K = 20, Mask2FormerOccHead,
+              128x128x16 -> occ 256x256x32, occformer_kitti.py)
 
 Gate = SURVEY.md 8(d), both criteria, per output tensor (tests/util.py::assert_close); voxel bookkeeping bit exact;
 bool attention-mask flips counted per decoder layer and allowed only where |pooled logit| < 1e-4 * max|logit|.
@@ -20,15 +22,12 @@ from util import assert_close
 
 pytestmark = pytest.mark.gpu
 
-N_CAMS, INPUT_SIZE, DOWNSAMPLE, C_TRANS = 6, (256, 704), 16, 128
+DOWNSAMPLE, C_TRANS = 16, 128
 PLANES, NUMS, STRIDES = [128, 256, 512, 1024], [2, 2, 2, 2], [1, 2, 2, 2]
-EMBED, QUERIES, CLASSES, DEC_LAYERS, HEADS = 192, 100, 17, 9, 6
+EMBED, QUERIES, DEC_LAYERS, HEADS = 192, 100, 9, 6
 NECK = dict(strides=[2, 4, 8, 16], layers=6, heads=8, levels=3, points=4, ffn=4 * EMBED)
 
-CASES = {
-    "nusc_200": dict(grid="nusc_200", occ=[200, 200, 16], pc=[-40.0, -40.0, -1.0, 40.0, 40.0, 5.4]),
-    "nusc_ref": dict(grid="nusc_ref", occ=[256, 256, 32], pc=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]),
-}
+CASES = synth.WORKLOADS
 
 
 class _PassThroughDepthNet(torch.nn.Module):
@@ -49,6 +48,7 @@ def _neck_available():
 
 def _oracle(case, x, cams, sd_e, sd_n, sd_h, head_feats):
     gc = synth.grid_config(case["grid"])
+    N_CAMS, INPUT_SIZE = case["cams"], case["input_size"]
     frustum = port.create_frustum(INPUT_SIZE, DOWNSAMPLE, gc["dbound"])
     D = frustum.shape[0]
     geom = port.get_geometry(frustum, **cams)
@@ -68,11 +68,12 @@ def _oracle(case, x, cams, sd_e, sd_n, sd_h, head_feats):
                 vox=res["output_voxels"][0], prob=prob)
 
 
-@pytest.mark.parametrize("name", ["nusc_200", "nusc_ref"])
+@pytest.mark.parametrize("name", ["nusc_200", "nusc_ref", "kitti"])
 def test_full_size_pipeline_vs_oracle(cuda, name):
     from occformer_b200 import BACKBONES, HEADS as HEAD_REG, NECKS
     from occformer_b200.head import head_cfg
     case = CASES[name]
+    N_CAMS, INPUT_SIZE, CLASSES = case["cams"], case["input_size"], case["classes"]
     threads = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(threads)
     gc = synth.grid_config(case["grid"])
@@ -81,7 +82,7 @@ def test_full_size_pipeline_vs_oracle(cuda, name):
     D = 112
     dd, feat = synth.lift_inputs(1, N_CAMS, D, fH, fW, C_TRANS, seed=0)
     x = torch.cat([dd, feat], dim=1).contiguous()
-    cams = synth.nusc_cameras(1, N_CAMS, INPUT_SIZE)
+    cams = synth.workload_cameras(name, 1)
     sd_e = synth.make_encoder_state(C_TRANS, PLANES, NUMS, STRIDES, seed=0)
     sd_h = synth.make_head_state(EMBED, QUERIES, CLASSES, DEC_LAYERS, 3, seed=1)
     connected = _neck_available()
@@ -99,7 +100,7 @@ def test_full_size_pipeline_vs_oracle(cuda, name):
                                norm_cfg=dict(type="GN", num_groups=32, requires_grad=True), with_cp=True))
     enc.load_state_dict(sd_e, strict=True)
     enc = enc.to(cuda).eval()
-    head = HEAD_REG.build(dict(type="Mask2FormerNuscOccHead", **head_cfg(EMBED, QUERIES, CLASSES, DEC_LAYERS, HEADS,
+    head = HEAD_REG.build(dict(type=case["head"], **head_cfg(EMBED, QUERIES, CLASSES, DEC_LAYERS, HEADS,
                                                                         case["pc"])))
     head.load_state_dict(sd_h, strict=True)
     head = head.to(cuda).eval()

@@ -140,6 +140,43 @@ def test_lift_splat_nusc_properties(cuda):
     print(f"nusc_200: n_pts={idx.shape[0]} n_kept={int(kept.sum())} nonempty={int(ws.counts.ne(0).sum())}")
 
 
+@pytest.mark.parametrize("wl", ["nusc_r101", "kitti"])
+def test_lift_splat_other_workloads(cuda, wl):
+    """BASELINE.json configs[4] frustum (R101: 6 cams 896x1600 -> 56x100x112 x 6 = 3 763 200 points, ~8x the density of the
+    R50 frustum: voxel lists of several hundred points) and configs[1] (KITTI: one 24x80x112 frustum, 4x4 P2 intrinsics):
+    bookkeeping identical to the oracle's index math, mass conservation, list-length statistics reported."""
+    from occformer_b200.view_transformer import ViewTransformerLiftSplatShootVoxel
+    from occformer_b200 import ops
+    w = synth.WORKLOADS[wl]
+    B, N, C = 1, w["cams"], 32
+    gc, geom, dx, bx, nx, dd, feat = _setup(w["grid"], synth.workload_cameras(wl, B), w["input_size"], B, N, C, seed=9)
+    vt = ViewTransformerLiftSplatShootVoxel(grid_config=gc, data_config={"input_size": w["input_size"]}, numC_input=64,
+                                            numC_Trans=C).to(cuda)
+    geom_gpu = vt.get_geometry(**{k: v.to(cuda) for k, v in synth.workload_cameras(wl, B).items()})
+    grid, prob = vt.lift_splat(dd.to(cuda), feat.to(cuda), geom.to(cuda), B, N)
+    idx = port.voxel_index(geom, dx, bx).view(-1, 3)
+    gf = torch.cat((idx, torch.zeros(idx.shape[0], 1, dtype=torch.long)), 1)
+    kept = port.kept_mask(gf, nx)
+    X, Y, Z = vt.grid_size()
+    ws = ops._workspace(idx.shape[0], B, X, Y, Z, cuda)
+    torch.cuda.synchronize()
+    _check_bookkeeping(ws, gf, kept, B, X, Y, Z)
+    prob_ref = dd.softmax(1)
+    D, HW = prob_ref.shape[1], prob_ref.shape[2] * prob_ref.shape[3]
+    wsum = (prob_ref.reshape(N, D, HW) * kept.view(N, D, HW)).sum(1)
+    expect = torch.einsum("np,ncp->c", wsum.double(), feat.reshape(N, C, HW).double())
+    assert_close(grid.double().sum(dim=(0, 1, 2, 3)).cpu(), expect, 1e-5, f"{wl} mass conservation")
+    # the geometry kernel agrees with the oracle geometry except within 1e-4 cells of a cell boundary
+    ia = port.voxel_index(geom_gpu.cpu(), dx, bx)
+    diff = (ia.view(-1, 3) != idx).any(-1)
+    frac = ((geom.view(-1, 3) - (bx - dx / 2.0)) / dx)
+    near = ((frac - frac.round()).abs() < 1e-4).any(-1)
+    assert bool((~diff | near).all()), "index flips away from cell boundaries"
+    counts = ws.counts.cpu()
+    print(f"{wl}: n_pts={idx.shape[0]} n_kept={int(kept.sum())} nonempty={int(counts.ne(0).sum())} "
+          f"max_list={int(counts.max())} mean_list={float(counts[counts > 0].float().mean()):.1f} geom_flips={int(diff.sum())}")
+
+
 @pytest.mark.parametrize("kind", ["nusc", "kitti", "kitti4x4"])
 def test_geometry_kernel_vs_oracle(cuda, kind):
     """occ_lss_geometry vs the oracle's literal get_geometry (torch.inverse + batched matmuls): fp32 rounding only;
