@@ -194,7 +194,8 @@ int occ_query_head(const float* query_in, const float* n2w, const float* n2b, fl
                    const float* pn_b, const float* clsT, const float* cls_b, int NC, const float* m0T, const float* m0b,
                    const float* m1T, const float* m1b, const float* m2T, const float* m2b, float* cls_out,
                    float* membed_out, const float* query_pos, int Q, const float* wqT, const float* bq, float scale,
-                   float* qh_out, int rows, int E, occ_stream_t stream);
+                   float* qh_out, const float* ffn_part /*(nparts, rows, E) FFN column-block partials, added to query_in
+                   in the order 0..nparts-1; may be NULL with nparts = 0*/, int nparts, int rows, int E, occ_stream_t stream);
 /* adaptive_max_pool3d of the mask logits (:463), general windows -> pooled (B, Xo*Yo*Zo, Q) as order-preserving ints
  * (see occ_mask_gemm_pool); row_flag[b*Q+q] = 1 iff some key of the row is un-blocked (pooled >= 0), else the row
  * attends everywhere (:652-653).  attn_mask == pooled < 0. */
@@ -220,10 +221,12 @@ int occ_cross_merge(const float* part, int nchunk, int H, const float* query, co
                     const float* sa_inb, float scale, float* query1, float* sa_qkv, int rows, int E,
                     occ_stream_t stream);
 /* self attention over the Q queries -> out_proj -> +identity -> LN(norms.1) -> x1; FFN(ReLU) + identity accumulated
- * into ybuf (= x1 + FFN(x1), F/E column blocks, fp32 atomics); the closing LN(norms.2) runs in occ_query_head. */
+ * as F/E column blocks: ybuf = x1 + b2, ffn_part (F/E, rows, E) = the blocks' contributions; occ_query_head adds them in
+ * a fixed order (bit-reproducible, no floating-point atomics) and applies the closing LN(norms.2). */
 int occ_self_attn_ffn(const float* sa_qkv, const float* query1, int Q, const float* woT, const float* bo,
                       const float* n1w, const float* n1b, const float* f1T, const float* f1b, const float* f2T,
-                      const float* f2b, int F, float* x1, float* ybuf, int rows, int E, int H, occ_stream_t stream);
+                      const float* f2b, int F, float* x1, float* ybuf, float* ffn_part, int rows, int E, int H,
+                      occ_stream_t stream);
 /* simple_test tail (:725-736, format_results :691-696): trilinear upsample (align_corners=True) -> sigmoid ->
  * einsum with softmax(cls)[..., :-1]; mask (B, X*Y*Z, Q), cls (B, Q, NC) -> out (B, NC-1, Xo, Yo, Zo); labels (optional,
  * (B, Xo, Yo, Zo) uint8) = argmax over the class axis (post_process_semantic, occupancyformer.py:238-243) */

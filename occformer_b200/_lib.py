@@ -42,15 +42,15 @@ SIGNATURES = {
     "occ_gn_stats": (c_int, [P, P, c_int, c_int, c_int, c_int, STREAM]),
     "occ_sine_pos3d": (c_int, [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, STREAM]),
     "occ_head_prep": (c_int, [P, c_int, P, P, P, P, c_int, c_longlong, c_int, STREAM]),
-    "occ_query_head": (c_int, [P, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P, P, c_float, P, c_int, c_int,
-                                STREAM]),
+    "occ_query_head": (c_int, [P, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, P, P, c_float, P, P, c_int,
+                                c_int, c_int, STREAM]),
     "occ_mask_pool": (c_int, [P, P, P] + [c_int] * 8 + [STREAM]),
     "occ_mask_gemm_pool": (c_int, [P, P, P, P, P] + [c_int] * 9 + [STREAM]),
     "occ_cross_attn_tc_partials": (c_int, [c_int]),
     "occ_mask_bits": (c_int, [P, P, c_int, c_int, c_int, STREAM]),
     "occ_cross_attn_tc": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P] + [c_int] * 5 + [STREAM]),
     "occ_cross_merge": (c_int, [P, c_int, c_int, P, P, c_int, P, P, P, P, P, P, c_float, P, P, c_int, c_int, STREAM]),
-    "occ_self_attn_ffn": (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, STREAM]),
+    "occ_self_attn_ffn": (c_int, [P, P, c_int, P, P, P, P, P, P, P, P, c_int, P, P, P, c_int, c_int, c_int, STREAM]),
     "occ_classmix": (c_int, [P, P, P, P] + [c_int] * 9 + [STREAM]),
     "occ_transpose_sq": (c_int, [P, P, c_int, c_longlong, c_int, STREAM]),
     "occ_ssc_counts": (c_int, [P, P, c_longlong, c_int, c_int, P, P, STREAM]),

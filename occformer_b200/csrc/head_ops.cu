@@ -184,7 +184,7 @@ query_head_kernel(const float* __restrict__ query_in, const float* __restrict__ 
                   const float* __restrict__ m1b, const float* __restrict__ m2T, const float* __restrict__ m2b,
                   float* __restrict__ cls_out, float* __restrict__ membed_out, const float* __restrict__ query_pos,
                   int Q, const float* __restrict__ wqT, const float* __restrict__ bq, float scale,
-                  float* __restrict__ qh_out, int rows, int E) {
+                  float* __restrict__ qh_out, const float* __restrict__ ffn_part, int nparts, int rows, int E) {
   extern __shared__ __align__(16) float sm[];  // xs[QG*E], part[QG*QG*E], red[32]
   float* xs = sm;
   float* part = xs + QG * E;
@@ -192,6 +192,7 @@ query_head_kernel(const float* __restrict__ query_in, const float* __restrict__ 
   const int j = threadIdx.x % E, g = threadIdx.x / E;
   const int row = blockIdx.x * QG + g;  // rows % QG == 0
   float q = query_in[(size_t)row * E + j];
+  for (int c = 0; c < nparts; ++c) q += ffn_part[((size_t)c * rows + row) * E + j];  // FFN column blocks, fixed order
   if (n2w) {  // last norm of the decoder layer (norms.2) on the FFN accumulator -> the layer's output query
     q = group_layernorm(q, g, j, E, n2w, n2b, red);
     query_state[(size_t)row * E + j] = q;
@@ -371,11 +372,12 @@ self_attn_kernel(const float* __restrict__ sa_qkv, const float* __restrict__ que
 }
 
 // FFN (mmcv FFN: Linear-ReLU-Linear + identity) as F/E independent column blocks: CTA (blockIdx.y = c) computes the
-// hidden units f in [c*E, (c+1)*E) of four rows and accumulates their contribution to the output into ybuf with
-// fp32 atomics (summation order over the F/E blocks is not fixed: differences at the 1e-7 level run to run).
+// hidden units f in [c*E, (c+1)*E) of four rows and writes their contribution to the output as partial c
+// (ypart (F/E, rows, E)); query_head_kernel adds the partials to ybuf in the fixed order c = 0, 1, ... -- the decoder
+// is bit-reproducible run to run (no floating-point atomics).
 __global__ void __launch_bounds__(1024)
 ffn_block_kernel(const float* __restrict__ x1, const float* __restrict__ f1T /*(E, F)*/, const float* __restrict__ f1b,
-                 const float* __restrict__ f2T /*(F, E)*/, int F, float* __restrict__ ybuf, int E) {
+                 const float* __restrict__ f2T /*(F, E)*/, int F, float* __restrict__ ypart, int E) {
   extern __shared__ __align__(16) float sm[];  // xs[QG*E], hs[QG*E], part[QG*QG*E]
   float* xs = sm;
   float* hs = xs + QG * E;
@@ -389,7 +391,7 @@ ffn_block_kernel(const float* __restrict__ x1, const float* __restrict__ f1T /*(
   hs[g * E + j] = hval;
   __syncthreads();
   const float y = matvec4(f2T + (size_t)c * E * E, E, nullptr, hs, E, j, g, E, part);
-  atomicAdd(ybuf + (size_t)row * E + j, y);
+  ypart[((size_t)c * gridDim.x * QG + row) * E + j] = y;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -598,16 +600,17 @@ extern "C" int occ_query_head(const float* query_in, const float* n2w, const flo
                               const float* pn_w, const float* pn_b, const float* clsT, const float* cls_b, int NC,
                               const float* m0T, const float* m0b, const float* m1T, const float* m1b, const float* m2T,
                               const float* m2b, float* cls_out, float* membed_out, const float* query_pos, int Q,
-                              const float* wqT, const float* bq, float scale, float* qh_out, int rows, int E,
-                              cudaStream_t stream) {
+                              const float* wqT, const float* bq, float scale, float* qh_out, const float* ffn_part,
+                              int nparts, int rows, int E, cudaStream_t stream) {
   OCC_REQUIRE(query_in && pn_w && pn_b && clsT && cls_b && m0T && m0b && m1T && m1b && m2T && m2b && cls_out && membed_out);
   OCC_REQUIRE(rows > 0 && rows % QG == 0 && E % 32 == 0 && E <= 256 && NC > 0 && NC <= E);
   OCC_REQUIRE((n2w == nullptr) == (n2b == nullptr) && (n2w == nullptr || query_state != nullptr));
   OCC_REQUIRE(wqT == nullptr || (bq && query_pos && qh_out && Q > 0));
+  OCC_REQUIRE(nparts >= 0 && (nparts == 0 || ffn_part != nullptr));
   const size_t smem = ((QG + QG * QG) * E + 32) * sizeof(float);
   query_head_kernel<<<rows / QG, E * QG, smem, stream>>>(query_in, n2w, n2b, query_state, pn_w, pn_b, clsT, cls_b, NC, m0T,
                                                          m0b, m1T, m1b, m2T, m2b, cls_out, membed_out, query_pos, Q, wqT,
-                                                         bq, scale, qh_out, rows, E);
+                                                         bq, scale, qh_out, ffn_part, nparts, rows, E);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -642,17 +645,17 @@ extern "C" int occ_cross_merge(const float* part, int nchunk, int H, const float
 
 extern "C" int occ_self_attn_ffn(const float* sa_qkv, const float* query1, int Q, const float* woT, const float* bo,
                                  const float* n1w, const float* n1b, const float* f1T, const float* f1b,
-                                 const float* f2T, const float* f2b, int F, float* x1, float* ybuf, int rows, int E,
-                                 int H, cudaStream_t stream) {
+                                 const float* f2T, const float* f2b, int F, float* x1, float* ybuf, float* ffn_part,
+                                 int rows, int E, int H, cudaStream_t stream) {
   OCC_REQUIRE(E == H * XA_HD);
-  OCC_REQUIRE(sa_qkv && query1 && woT && bo && n1w && n1b && f1T && f1b && f2T && f2b && x1 && ybuf);
+  OCC_REQUIRE(sa_qkv && query1 && woT && bo && n1w && n1b && f1T && f1b && f2T && f2b && x1 && ybuf && ffn_part);
   OCC_REQUIRE(rows > 0 && rows % QG == 0 && Q > 0 && Q <= 128 && E % 32 == 0 && E <= 256 && F > 0 && F % E == 0 &&
               rows % Q == 0 && F / E <= 65535);
   const size_t smem = ((QG + QG * QG) * E + 32) * sizeof(float);
   self_attn_kernel<<<rows / QG, E * QG, smem, stream>>>(sa_qkv, query1, Q, woT, bo, n1w, n1b, f2b, x1, ybuf, E);
   OCC_LAUNCH_CHECK();
   const size_t smem2 = (2 * QG + QG * QG) * E * sizeof(float);
-  ffn_block_kernel<<<dim3(rows / QG, F / E), E * QG, smem2, stream>>>(x1, f1T, f1b, f2T, F, ybuf, E);
+  ffn_block_kernel<<<dim3(rows / QG, F / E), E * QG, smem2, stream>>>(x1, f1T, f1b, f2T, F, ffn_part, E);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

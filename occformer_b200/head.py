@@ -257,12 +257,12 @@ class _Mask2FormerOccBase(nn.Module):
         query = self.query_feat.weight.detach().float().unsqueeze(0).expand(B, Q, E).reshape(B * Q, E).contiguous()
         qpos = P["query_pos"]
 
-        def forward_head(query_in, target, norm2=None, next_layer=None):
+        def forward_head(query_in, target, norm2=None, next_layer=None, ffn_part=None):
             nq = None
             if next_layer is not None:
                 Ln = P["layers"][next_layer]
                 nq = (qpos, Q, Ln["ca_wqT"], Ln["ca_bq"], scale)
-            cls, membed, query, qh = ops.query_head(query_in, P["head"], NC, norm2=norm2, next_q=nq)
+            cls, membed, query, qh = ops.query_head(query_in, P["head"], NC, norm2=norm2, next_q=nq, ffn_part=ffn_part)
             if target is not None and ops.pool_fusable(grid, target):
                 # einsum + adaptive max pool + threshold bookkeeping in one kernel; the (B,V,Q) logits are only
                 # written when the caller wants every layer's mask_pred
@@ -286,11 +286,11 @@ class _Mask2FormerOccBase(nn.Module):
             off = P["slots"][i] * E
             part, nchunk = ops.cross_attn_tc(qh, Kp[lvl], Vp[lvl], lds[lvl], off, off, pooled, flag, B, S, Q, E, H)
             q1, sa = ops.cross_merge(part, nchunk, H, query, qpos, Q, Lw, scale)
-            ybuf = ops.self_attn_ffn(sa, q1, Q, Lw, H)
+            ybuf, ffn_part = ops.self_attn_ffn(sa, q1, Q, Lw, H)
             last = i == L - 1
             cls, mask, pooled, flag, query, qh = forward_head(ybuf, None if last else sizes[(i + 1) % nl],
                                                               norm2=(Lw["n2w"], Lw["n2b"]),
-                                                              next_layer=None if last else i + 1)
+                                                              next_layer=None if last else i + 1, ffn_part=ffn_part)
             cls_list.append(cls)
             if keep_all_masks or last:
                 mask_list.append(mask)

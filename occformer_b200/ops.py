@@ -391,7 +391,7 @@ def head_prep(x, channel_last, level_embed=None, pos=None):
     return mem, kpos
 
 
-def query_head(query_in, W, NC, norm2=None, next_q=None):
+def query_head(query_in, W, NC, norm2=None, next_q=None, ffn_part=None):
     """forward_head query side.  norm2 = (w, b): query_in is the FFN accumulator, LN(norms.2) gives the layer output
     (returned as `query`); next_q = (query_pos, Q, wqT, bq, scale): also project the next layer's cross-attn queries."""
     rows, E = query_in.shape
@@ -404,7 +404,8 @@ def query_head(query_in, W, NC, norm2=None, next_q=None):
     check(lib().occ_query_head(_ptr(query_in), _ptr(n2w), _ptr(n2b), _ptr(query) if norm2 is not None else None,
                                _ptr(W["pn_w"]), _ptr(W["pn_b"]), _ptr(W["clsT"]), _ptr(W["cls_b"]), NC, _ptr(W["m0T"]),
                                _ptr(W["m0b"]), _ptr(W["m1T"]), _ptr(W["m1b"]), _ptr(W["m2T"]), _ptr(W["m2b"]), _ptr(cls),
-                               _ptr(membed), _ptr(qpos), Q, _ptr(wqT), _ptr(bq), scale, _ptr(qh), rows, E, _stream()),
+                               _ptr(membed), _ptr(qpos), Q, _ptr(wqT), _ptr(bq), scale, _ptr(qh), _ptr(ffn_part),
+                               ffn_part.shape[0] if ffn_part is not None else 0, rows, E, _stream()),
           "occ_query_head")
     LAUNCH_COUNT[0] += 1
     return cls, membed, query, qh
@@ -477,16 +478,18 @@ def cross_merge(part, nchunk, H, query, query_pos, Q, L, scale):
 
 
 def self_attn_ffn(sa, q1, Q, L, H):
-    """-> ybuf = x1 + FFN(x1) (pre-norms.2 accumulator of the decoder layer)."""
+    """-> (ybuf = x1 + b2, ffn_part (F/E, rows, E)): the pre-norms.2 accumulator of the decoder layer and the FFN
+    column-block partials that occ_query_head adds to it in a fixed order."""
     rows, E = q1.shape
     x1 = torch.empty_like(q1)
     ybuf = torch.empty_like(q1)
     F = L["f1b"].numel()
+    part = torch.empty((F // E, rows, E), dtype=torch.float32, device=q1.device)
     check(lib().occ_self_attn_ffn(_ptr(sa), _ptr(q1), Q, _ptr(L["sa_woT"]), _ptr(L["sa_bo"]), _ptr(L["n1w"]), _ptr(L["n1b"]),
                                   _ptr(L["f1T"]), _ptr(L["f1b"]), _ptr(L["f2T"]), _ptr(L["f2b"]), F, _ptr(x1), _ptr(ybuf),
-                                  rows, E, H, _stream()), "occ_self_attn_ffn")
+                                  _ptr(part), rows, E, H, _stream()), "occ_self_attn_ffn")
     LAUNCH_COUNT[0] += 2
-    return ybuf
+    return ybuf, part
 
 
 def classmix(mask, cls, B, grid, out_grid, Q, NC, with_labels=False):
