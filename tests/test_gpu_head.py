@@ -172,3 +172,15 @@ def test_query_stationary_mask_pool_full_grid(cuda, target):
     assert_close(got, ref_pool, 5e-5, f"query-stationary pooled maxima full grid ->{target}")
     assert torch.equal(flag.view(B, Q) != 0, (got >= 0).any(1))
     assert not bool(flag.view(B, Q)[:, 5].any())
+
+
+def test_head_bit_reproducible(cuda):
+    """The whole decoder is deterministic run to run (FFN column blocks are summed in a fixed order, no fp atomics)."""
+    E, Q, K, L = 192, 100, 17, 3
+    sd = port.make_head_state(E, Q, K, L, 3, seed=3)
+    feats = [f.to(cuda) for f in synth.head_inputs(1, E, [(50, 50, 8), (25, 25, 4), (13, 13, 2), (7, 7, 1)], seed=4)]
+    head = _head(cuda, E, Q, K, L, None, sd)
+    metas = [dict(occ_size=[50, 50, 8], pc_range=PC)]
+    a = head.simple_test(feats, metas)["output_voxels"][0].clone()
+    for _ in range(3):
+        assert torch.equal(head.simple_test(feats, metas)["output_voxels"][0], a), "decoder output differs run to run"
