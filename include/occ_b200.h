@@ -64,6 +64,19 @@ int occ_lift_splat(const float* depth_prob, const float* feat_cl, const float* g
                    int B, int N, int D, int HW, int C, float dx0, float dx1, float dx2, float bx0, float bx1, float bx2,
                    float nx0, float nx1, float nx2, int X, int Y, int Z, void* workspace, size_t workspace_bytes,
                    occ_stream_t stream);
+/* The whole ViewTransformerLiftSplatShootVoxel.forward after DepthNet (ViewTransformerLSSVoxel.py:107-119) in three
+ * launches: depth softmax + get_geometry + voxel index + per-voxel lists + NCHW->NHWC of the context features in one
+ * front kernel (the (B,N,D,fH,fW,3) geometry tensor is never written), then the pooling kernel.  depth_logits
+ * (B*N, D, HW) and img_feat (B*N, C, HW) with logits_stride / feat_stride floats between cameras (channel slices of
+ * DepthNet's (B*N, D + C, fH, fW) output are passed without a copy), frustum (D*HW, 3), camera matrices as
+ * occ_lss_geometry; outputs: depth_prob (B*N, D, HW), feat_cl (B*N, HW, C), out (B,X,Y,Z,C) fp32, out_split (optional) S32. */
+int occ_lift_splat_fused(const float* depth_logits, long long logits_stride, const float* img_feat,
+                         long long feat_stride, const float* frustum, const float* rots,
+                         const float* trans, const float* intrins, int intrin_rows, int intrin_cols,
+                         const float* post_rots, const float* post_trans, const float* bda, int bda_dim,
+                         float* depth_prob, float* feat_cl, float* out, float* out_split, int B, int N, int D, int HW,
+                         int C, float dx0, float dx1, float dx2, float bx0, float bx1, float bx2, float nx0, float nx1,
+                         float nx2, int X, int Y, int Z, void* workspace, size_t workspace_bytes, occ_stream_t stream);
 /* voxel_pooling(geom, volume) with a materialised volume: feats (B*points_per_batch, C), geom (same rows, 3)
  * (ViewTransformerLSSVoxel.py:77-100) */
 int occ_voxel_pool_geom(const float* feats, const float* geom, float* out, int B, int points_per_batch, int C,

@@ -21,6 +21,9 @@ SIGNATURES = {
     "occ_lift_prologue": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, STREAM]),
     "occ_lift_splat": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int] + [c_float] * 9 +
                        [c_int, c_int, c_int, P, c_size_t, STREAM]),
+    "occ_lift_splat_fused": (c_int, [P, c_longlong, P, c_longlong, P, P, P, P, c_int, c_int, P, P, P, c_int, P, P, P, P] +
+                             [c_int] * 5 + [c_float] * 9 +
+                             [c_int, c_int, c_int, P, c_size_t, STREAM]),
     "occ_voxel_pool_geom": (c_int, [P, P, P, c_int, c_int, c_int] + [c_float] * 9 + [c_int, c_int, c_int, P, c_size_t, STREAM]),
     "occ_bev_pool": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_size_t, STREAM]),
     "occ_gemm_bf16x3": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int, c_int, P, c_int, c_int, STREAM]),

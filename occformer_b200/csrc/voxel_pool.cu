@@ -30,31 +30,44 @@ namespace occ {
 // ------------------------------------------------------------------------------------------------ index
 // geom: (P,3) fp32 ego coordinates of frustum point p = ((b*N+n)*D+d)*fH*fW + pix.  vox_id[p] = linear voxel
 // id ((b*X+x)*Y+y)*Z+z or -1 when dropped.
-__global__ void vp_index_geom_kernel(const float* __restrict__ geom, int P, int points_per_batch, float dx0,
-                                     float dx1, float dx2, float bx0, float bx1, float bx2, float nx0, float nx1,
-                                     float nx2, int X, int Y, int Z, int* __restrict__ vox_id,
-                                     int* __restrict__ counts, int* __restrict__ head, int* __restrict__ next) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const float gx = geom[3 * (size_t)p + 0], gy = geom[3 * (size_t)p + 1], gz = geom[3 * (size_t)p + 2];
+struct VpGrid {
+  float dx0, dx1, dx2, bx0, bx1, bx2, nx0, nx1, nx2;
+  int X, Y, Z;
+};
+
+// ego point -> linear voxel id of sample b (or -1 when dropped), the reference's index arithmetic bit for bit
+__device__ __forceinline__ int vp_voxel_of(float gx, float gy, float gz, int b, const VpGrid& g) {
   // ViewTransformerLSSVoxel.py:84 -- fp32 sub, fp32 div (IEEE, no contraction), .long() truncation
-  const float ox = __fsub_rn(bx0, __fdiv_rn(dx0, 2.0f));
-  const float oy = __fsub_rn(bx1, __fdiv_rn(dx1, 2.0f));
-  const float oz = __fsub_rn(bx2, __fdiv_rn(dx2, 2.0f));
-  const long long ix = (long long)__fdiv_rn(__fsub_rn(gx, ox), dx0);
-  const long long iy = (long long)__fdiv_rn(__fsub_rn(gy, oy), dx1);
-  const long long iz = (long long)__fdiv_rn(__fsub_rn(gz, oz), dx2);
+  const float ox = __fsub_rn(g.bx0, __fdiv_rn(g.dx0, 2.0f));
+  const float oy = __fsub_rn(g.bx1, __fdiv_rn(g.dx1, 2.0f));
+  const float oz = __fsub_rn(g.bx2, __fdiv_rn(g.dx2, 2.0f));
+  const long long ix = (long long)__fdiv_rn(__fsub_rn(gx, ox), g.dx0);
+  const long long iy = (long long)__fdiv_rn(__fsub_rn(gy, oy), g.dx1);
+  const long long iz = (long long)__fdiv_rn(__fsub_rn(gz, oz), g.dx2);
   // :90-92 -- int64 index compared with the *float* nx, upper bound exclusive
-  const bool kept = ix >= 0 && (float)ix < nx0 && iy >= 0 && (float)iy < nx1 && iz >= 0 && (float)iz < nx2 &&
-                    ix < X && iy < Y && iz < Z;
-  int v = -1;
-  if (kept) {
-    const int b = p / points_per_batch;
-    v = ((b * X + (int)ix) * Y + (int)iy) * Z + (int)iz;
+  const bool kept = ix >= 0 && (float)ix < g.nx0 && iy >= 0 && (float)iy < g.nx1 && iz >= 0 && (float)iz < g.nx2 &&
+                    ix < g.X && iy < g.Y && iz < g.Z;
+  return kept ? ((b * g.X + (int)ix) * g.Y + (int)iy) * g.Z + (int)iz : -1;
+}
+
+// push point p onto the list of voxel v (1-based ids: 0 = end of list / empty voxel) and count it
+__device__ __forceinline__ void vp_push(int p, int v, int* __restrict__ vox_id, int* __restrict__ counts,
+                                        int* __restrict__ head, int* __restrict__ next) {
+  if (v >= 0) {
     atomicAdd(&counts[v], 1);
-    next[p] = atomicExch(&head[v], p + 1);  // 1-based ids: 0 = end of list / empty voxel
+    next[p] = atomicExch(&head[v], p + 1);
   }
   vox_id[p] = v;
+}
+
+__global__ void vp_index_geom_kernel(const float* __restrict__ geom, int P, int points_per_batch, const VpGrid g,
+                                     int* __restrict__ vox_id, int* __restrict__ counts, int* __restrict__ head,
+                                     int* __restrict__ next) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int v = vp_voxel_of(geom[3 * (size_t)p + 0], geom[3 * (size_t)p + 1], geom[3 * (size_t)p + 2],
+                            p / points_per_batch, g);
+  vp_push(p, v, vox_id, counts, head, next);
 }
 
 // coords: (n,4) int64 (x,y,z,b) as handed to mmdet3d.ops.bev_pool.bev_pool (already range-filtered by the
@@ -326,8 +339,8 @@ extern "C" int occ_lift_splat(const float* depth_prob, const float* feat_cl, con
   OCC_REQUIRE(vp_layout(workspace, P, V, &ws) <= workspace_bytes);
   // head[V] and counts[V] are adjacent in the workspace: one memset
   OCC_CUDA(cudaMemsetAsync(ws.head, 0, reinterpret_cast<char*>(ws.counts + V) - reinterpret_cast<char*>(ws.head), stream));
-  vp_index_geom_kernel<<<(P + 255) / 256, 256, 0, stream>>>(geom, P, N * D * HW, dx0, dx1, dx2, bx0, bx1, bx2, nx0,
-                                                             nx1, nx2, X, Y, Z, ws.vox_id, ws.counts, ws.head, ws.next);
+  const VpGrid vg{dx0, dx1, dx2, bx0, bx1, bx2, nx0, nx1, nx2, X, Y, Z};
+  vp_index_geom_kernel<<<(P + 255) / 256, 256, 0, stream>>>(geom, P, N * D * HW, vg, ws.vox_id, ws.counts, ws.head, ws.next);
   OCC_LAUNCH_CHECK();
   vp_pool_kernel<0><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, depth_prob, feat_cl,
                                                                  make_fastdiv((uint32_t)D * HW), make_fastdiv(HW), out,
@@ -399,8 +412,9 @@ extern "C" int occ_voxel_pool_geom(const float* feats, const float* geom, float*
   VpWorkspace ws;
   OCC_REQUIRE(vp_layout(workspace, P, V, &ws) <= workspace_bytes);
   OCC_CUDA(cudaMemsetAsync(ws.head, 0, reinterpret_cast<char*>(ws.counts + V) - reinterpret_cast<char*>(ws.head), stream));
-  vp_index_geom_kernel<<<(P + 255) / 256, 256, 0, stream>>>(geom, P, points_per_batch, dx0, dx1, dx2, bx0, bx1, bx2,
-                                                             nx0, nx1, nx2, X, Y, Z, ws.vox_id, ws.counts, ws.head, ws.next);
+  const VpGrid vg{dx0, dx1, dx2, bx0, bx1, bx2, nx0, nx1, nx2, X, Y, Z};
+  vp_index_geom_kernel<<<(P + 255) / 256, 256, 0, stream>>>(geom, P, points_per_batch, vg, ws.vox_id, ws.counts, ws.head,
+                                                             ws.next);
   OCC_LAUNCH_CHECK();
   vp_pool_kernel<1><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, nullptr, feats, make_fastdiv(1),
                                                                  make_fastdiv(1), out, nullptr);
@@ -433,51 +447,153 @@ __device__ __forceinline__ void mv3(const float* m, float x, float y, float z, f
   oz = fmaf(m[8], z, fmaf(m[7], y, m[6] * x));
 }
 
+// Per-camera constants of get_geometry in shared memory (36 floats): inverse post-rotation, rots * inverse(K), the
+// translations, the KITTI P2 shift column and the BEV augmentation matrix.
+struct CamConst {
+  float ipr[9], comb[9], vec[9], bda[16];
+};
+
+__device__ __forceinline__ void cam_const_build(CamConst* c, int bn, int b, const float* __restrict__ rots,
+                                                const float* __restrict__ trans, const float* __restrict__ intrins,
+                                                int intrin_rows, int intrin_cols, const float* __restrict__ post_rots,
+                                                const float* __restrict__ post_trans, const float* __restrict__ bda,
+                                                int bda_dim) {
+  inv3x3(post_rots + (size_t)bn * 9, c->ipr);
+  float K[9], iK[9];
+  const float* I = intrins + (size_t)bn * intrin_rows * intrin_cols;  // (3,3), (3,4) or KITTI's 4x4 P2 per camera
+  for (int r = 0; r < 3; ++r)
+    for (int cc = 0; cc < 3; ++cc) K[r * 3 + cc] = I[r * intrin_cols + cc];
+  inv3x3(K, iK);
+  const float* R = rots + (size_t)bn * 9;
+  for (int r = 0; r < 3; ++r)
+    for (int cc = 0; cc < 3; ++cc)
+      c->comb[r * 3 + cc] = fmaf(R[r * 3 + 2], iK[6 + cc], fmaf(R[r * 3 + 1], iK[3 + cc], R[r * 3] * iK[cc]));
+  for (int k = 0; k < 3; ++k) {
+    c->vec[k] = post_trans[(size_t)bn * 3 + k];
+    c->vec[3 + k] = trans[(size_t)bn * 3 + k];
+    c->vec[6 + k] = intrin_cols == 4 ? I[k * 4 + 3] : 0.f;  // KITTI P2 shift (:134-137), rows 0..2 of the last column
+  }
+  for (int k = 0; k < bda_dim * bda_dim; ++k) c->bda[k] = bda[(size_t)b * bda_dim * bda_dim + k];
+}
+
+// frustum point (fx, fy, fz) = (u, v, depth) -> ego coordinates (ViewTransformerLSSBEVDepth.py:117-150)
+__device__ __forceinline__ void cam_point(const CamConst& c, int bda_dim, float fx, float fy, float fz, float& ox, float& oy,
+                                          float& oz) {
+  float x = fx - c.vec[0], y = fy - c.vec[1], z = fz - c.vec[2];
+  float u, v, w;
+  mv3(c.ipr, x, y, z, u, v, w);
+  u = u * w - c.vec[6]; v = v * w - c.vec[7]; w = w - c.vec[8];
+  mv3(c.comb, u, v, w, x, y, z);
+  x += c.vec[3]; y += c.vec[4]; z += c.vec[5];
+  if (bda_dim == 4) {
+    ox = fmaf(c.bda[2], z, fmaf(c.bda[1], y, c.bda[0] * x)) + c.bda[3];
+    oy = fmaf(c.bda[6], z, fmaf(c.bda[5], y, c.bda[4] * x)) + c.bda[7];
+    oz = fmaf(c.bda[10], z, fmaf(c.bda[9], y, c.bda[8] * x)) + c.bda[11];
+  } else {
+    mv3(c.bda, x, y, z, ox, oy, oz);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 lss_geometry_kernel(const float* __restrict__ frustum /*(P,3)*/, int P, const float* __restrict__ rots,
                     const float* __restrict__ trans, const float* __restrict__ intrins, int intrin_rows, int intrin_cols,
                     const float* __restrict__ post_rots, const float* __restrict__ post_trans,
                     const float* __restrict__ bda, int bda_dim, int N, float* __restrict__ geom) {
-  __shared__ float s_ipr[9], s_comb[9], s_vec[9], s_bda[16];
+  __shared__ CamConst cam;
   const int bn = blockIdx.y, b = bn / N;
-  if (threadIdx.x == 0) {
-    inv3x3(post_rots + (size_t)bn * 9, s_ipr);
-    float K[9], iK[9];
-    const float* I = intrins + (size_t)bn * intrin_rows * intrin_cols;  // (3,3), (3,4) or KITTI's 4x4 P2 per camera
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) K[r * 3 + c] = I[r * intrin_cols + c];
-    inv3x3(K, iK);
-    const float* R = rots + (size_t)bn * 9;
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c)
-        s_comb[r * 3 + c] = fmaf(R[r * 3 + 2], iK[6 + c], fmaf(R[r * 3 + 1], iK[3 + c], R[r * 3] * iK[c]));
-    for (int k = 0; k < 3; ++k) {
-      s_vec[k] = post_trans[(size_t)bn * 3 + k];
-      s_vec[3 + k] = trans[(size_t)bn * 3 + k];
-      s_vec[6 + k] = intrin_cols == 4 ? I[k * 4 + 3] : 0.f;  // KITTI P2 shift (:134-137), rows 0..2 of the last column
-    }
-    for (int k = 0; k < bda_dim * bda_dim; ++k) s_bda[k] = bda[(size_t)b * bda_dim * bda_dim + k];
-  }
+  if (threadIdx.x == 0) cam_const_build(&cam, bn, b, rots, trans, intrins, intrin_rows, intrin_cols, post_rots, post_trans, bda, bda_dim);
   __syncthreads();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  float x = frustum[3 * (size_t)p] - s_vec[0], y = frustum[3 * (size_t)p + 1] - s_vec[1],
-        z = frustum[3 * (size_t)p + 2] - s_vec[2];
-  float u, v, w;
-  mv3(s_ipr, x, y, z, u, v, w);
-  u = u * w - s_vec[6]; v = v * w - s_vec[7]; w = w - s_vec[8];
-  mv3(s_comb, u, v, w, x, y, z);
-  x += s_vec[3]; y += s_vec[4]; z += s_vec[5];
   float ox, oy, oz;
-  if (bda_dim == 4) {
-    ox = fmaf(s_bda[2], z, fmaf(s_bda[1], y, s_bda[0] * x)) + s_bda[3];
-    oy = fmaf(s_bda[6], z, fmaf(s_bda[5], y, s_bda[4] * x)) + s_bda[7];
-    oz = fmaf(s_bda[10], z, fmaf(s_bda[9], y, s_bda[8] * x)) + s_bda[11];
-  } else {
-    mv3(s_bda, x, y, z, ox, oy, oz);
-  }
+  cam_point(cam, bda_dim, frustum[3 * (size_t)p], frustum[3 * (size_t)p + 1], frustum[3 * (size_t)p + 2], ox, oy, oz);
   float* o = geom + ((size_t)bn * P + p) * 3;
   o[0] = ox; o[1] = oy; o[2] = oz;
+}
+
+// ------------------------------------------------------------------------------------------------ fused lift front end
+// One launch for everything in front of the pooling kernel (ViewTransformerLSSVoxel.forward :107-116, voxel_pooling
+// :84-95, get_geometry): depth softmax over D, frustum -> ego geometry -> voxel index -> per-voxel point lists, and the
+// NCHW -> NHWC transpose of the context features.  The (B,N,D,fH,fW,3) geometry tensor is never written.
+//   blocks [0, nb_front): (camera bn, 32-pixel tile): 32 pixels x 8 depth groups; a thread owns D/8 depth bins of one pixel
+//   blocks [nb_front, ..): 32x32 tiles of the (C, HW) -> (HW, C) transpose
+constexpr int LF_DG = 8;      // depth groups per pixel
+constexpr int LF_MAXD = 32;   // depth bins per thread (D <= 256)
+
+__global__ void __launch_bounds__(256)
+lift_front_kernel(const float* __restrict__ logits /*(BN, D, HW)*/, const float* __restrict__ img_feat /*(BN, C, HW)*/,
+                  const float* __restrict__ frustum /*(D*HW, 3)*/, const float* __restrict__ rots,
+                  const float* __restrict__ trans, const float* __restrict__ intrins, int intrin_rows, int intrin_cols,
+                  const float* __restrict__ post_rots, const float* __restrict__ post_trans,
+                  const float* __restrict__ bda, int bda_dim, int N, int D, int HW, int C, long long lstride,
+                  long long fstride, const VpGrid g, float* __restrict__ prob, float* __restrict__ feat_cl, int* __restrict__ vox_id,
+                  int* __restrict__ counts, int* __restrict__ head, int* __restrict__ next, int nb_front, int tiles_p,
+                  int tiles_c) {
+  __shared__ CamConst cam;
+  __shared__ float red[LF_DG][32];
+  __shared__ float tile[32][33];
+  if ((int)blockIdx.x >= nb_front) {  // ---- context features (BN, C, HW) -> (BN, HW, C)
+    int t = blockIdx.x - nb_front;
+    const int tp = t % tiles_p; t /= tiles_p;
+    const int tc = t % tiles_c;
+    const int bn = t / tiles_c;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int c0 = tc * 32, p0 = tp * 32;
+    for (int i = ly; i < 32; i += 8) {
+      const int c = c0 + i, p = p0 + lx;
+      tile[i][lx] = (c < C && p < HW) ? img_feat[(size_t)bn * fstride + (size_t)c * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ly; i < 32; i += 8) {
+      const int p = p0 + i, c = c0 + lx;
+      if (p < HW && c < C) feat_cl[((size_t)bn * HW + p) * C + c] = tile[lx][i];
+    }
+    return;
+  }
+  const int bn = blockIdx.x / tiles_p, b = bn / N;
+  const int lx = threadIdx.x & 31, dg = threadIdx.x >> 5;
+  const int pix = (blockIdx.x % tiles_p) * 32 + lx;
+  if (threadIdx.x == 0) cam_const_build(&cam, bn, b, rots, trans, intrins, intrin_rows, intrin_cols, post_rots, post_trans, bda, bda_dim);
+  const bool live = pix < HW;
+  const int dper = (D + LF_DG - 1) / LF_DG;
+  const int d0 = dg * dper, d1 = min(d0 + dper, D);
+  float l[LF_MAXD];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < LF_MAXD; ++i) {
+    l[i] = -INFINITY;
+    if (live && d0 + i < d1) l[i] = logits[(size_t)bn * lstride + (size_t)(d0 + i) * HW + pix];
+    m = fmaxf(m, l[i]);
+  }
+  red[dg][lx] = m;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < LF_DG; ++k) m = fmaxf(m, red[k][lx]);
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LF_MAXD; ++i) {
+    l[i] = (live && d0 + i < d1) ? expf(l[i] - m) : 0.f;
+    sum += l[i];
+  }
+  red[dg][lx] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < LF_DG; ++k) sum += red[k][lx];  // same order for every thread of the pixel
+  if (!live) return;
+#pragma unroll
+  for (int i = 0; i < LF_MAXD; ++i) {
+    const int d = d0 + i;
+    if (d < d1) {
+      const int p = (bn * D + d) * HW + pix;
+      prob[p] = l[i] / sum;
+      const float* f = frustum + 3 * ((size_t)d * HW + pix);
+      float ox, oy, oz;
+      cam_point(cam, bda_dim, f[0], f[1], f[2], ox, oy, oz);
+      vp_push(p, vp_voxel_of(ox, oy, oz, b, g), vox_id, counts, head, next);
+    }
+  }
 }
 
 }  // namespace occ
@@ -493,6 +609,50 @@ extern "C" int occ_lss_geometry(const float* frustum, int P, const float* rots, 
   occ::lss_geometry_kernel<<<grid, 256, 0, stream>>>(frustum, P, rots, trans, intrins, intrin_rows, intrin_cols, post_rots,
                                                      post_trans,
                                                      bda, bda_dim, N, geom);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+
+// Fused lift-splat from the view transformer's raw inputs: depth_logits (B*N, D, HW), img_feat (B*N, C, HW) (NCHW, as
+// DepthNet returns them), frustum (D*HW, 3) and the camera matrices of occ_lss_geometry.  Three launches: memset of the
+// list heads, the front kernel (softmax + geometry + voxel index + lists + NHWC transpose), the pooling kernel.
+// depth_prob (B*N, D, HW) and feat_cl (B*N, HW, C) are outputs (depth_prob is the module's second return value).
+// logits_stride / feat_stride: floats between consecutive cameras of depth_logits / img_feat (both may be channel
+// slices of DepthNet's (B*N, D + C, fH, fW) output: no copy).
+extern "C" int occ_lift_splat_fused(const float* depth_logits, long long logits_stride, const float* img_feat,
+                                    long long feat_stride, const float* frustum,
+                                    const float* rots, const float* trans, const float* intrins, int intrin_rows,
+                                    int intrin_cols, const float* post_rots, const float* post_trans, const float* bda,
+                                    int bda_dim, float* depth_prob, float* feat_cl, float* out, float* out_split, int B,
+                                    int N, int D, int HW, int C, float dx0, float dx1, float dx2, float bx0, float bx1,
+                                    float bx2, float nx0, float nx1, float nx2, int X, int Y, int Z, void* workspace,
+                                    size_t workspace_bytes, cudaStream_t stream) {
+  OCC_REQUIRE(depth_logits && img_feat && frustum && rots && trans && intrins && post_rots && post_trans && bda);
+  OCC_REQUIRE(depth_prob && feat_cl && out && workspace);
+  OCC_REQUIRE(!out_split || C % 32 == 0);
+  OCC_REQUIRE(logits_stride >= (long long)D * HW && feat_stride >= (long long)C * HW);
+  OCC_REQUIRE(B > 0 && N > 0 && D > 0 && D <= occ::LF_DG * occ::LF_MAXD && HW > 0 && C > 0 && C % 4 == 0 && X > 0 && Y > 0 && Z > 0);
+  OCC_REQUIRE((intrin_cols == 3 || intrin_cols == 4) && intrin_rows >= 3 && intrin_rows <= 4 && (bda_dim == 3 || bda_dim == 4));
+  const long long Pll = (long long)B * N * D * HW, Vll = (long long)B * X * Y * Z;
+  OCC_REQUIRE(Pll < (1ll << 31) && Vll < (1ll << 31));
+  const int P = (int)Pll, V = (int)Vll;
+  VpWorkspace ws;
+  OCC_REQUIRE(vp_layout(workspace, P, V, &ws) <= workspace_bytes);
+  OCC_CUDA(cudaMemsetAsync(ws.head, 0, reinterpret_cast<char*>(ws.counts + V) - reinterpret_cast<char*>(ws.head), stream));
+  const VpGrid vg{dx0, dx1, dx2, bx0, bx1, bx2, nx0, nx1, nx2, X, Y, Z};
+  const int tiles_p = (HW + 31) / 32, tiles_c = (C + 31) / 32;
+  const int nb_front = B * N * tiles_p;
+  const long long nb = (long long)nb_front + (long long)B * N * tiles_p * tiles_c;
+  OCC_REQUIRE(nb < (1ll << 31));
+  lift_front_kernel<<<(unsigned)nb, 256, 0, stream>>>(depth_logits, img_feat, frustum, rots, trans, intrins, intrin_rows,
+                                                      intrin_cols, post_rots, post_trans, bda, bda_dim, N, D, HW, C,
+                                                      logits_stride, feat_stride, vg,
+                                                      depth_prob, feat_cl, ws.vox_id, ws.counts, ws.head, ws.next, nb_front,
+                                                      tiles_p, tiles_c);
+  OCC_LAUNCH_CHECK();
+  vp_pool_kernel<0><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, depth_prob, feat_cl,
+                                                                 make_fastdiv((uint32_t)D * HW), make_fastdiv(HW), out,
+                                                                 out_split);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

@@ -182,6 +182,42 @@ def lift_splat(depth_prob, feat_cl, geom, B, N, dx, bx, nx, grid, return_workspa
     return (res, ws) if return_workspace else res
 
 
+def lift_splat_fused(depth_logits, img_feat, frustum, rots, trans, intrins, post_rots, post_trans, bda, B, N, dx, bx, nx,
+                     grid, with_split=False):
+    """The view transformer after DepthNet in three launches (memset, front kernel, pooling): depth_logits (BN,D,fH,fW),
+    img_feat (BN,C,fH,fW) -> (grid (B,X,Y,Z,C) [, S32 twin], depth_prob (BN,D,fH,fW))."""
+    BN, D, fH, fW = depth_logits.shape
+    C = img_feat.shape[1]
+    X, Y, Z = grid
+    HW = fH * fW
+
+    def plane(t, name):  # (BN, ch, fH, fW) fp32 whose cameras may be strided (channel slice of a bigger tensor): no copy
+        t = t.float()
+        if t.stride()[1:] != (HW, fW, 1):
+            t = t.contiguous()
+        if not t.is_cuda:
+            raise RuntimeError(f"occformer_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
+        return t, t.stride(0)
+
+    depth_logits, ls = plane(depth_logits, "depth_logits")
+    img_feat, fs = plane(img_feat, "img_feat")
+    f = lambda t: _chk(t.float().contiguous(), "camera matrix")  # noqa: E731
+    fr, r, t, k, pr, pt, bd = f(frustum), f(rots), f(trans), f(intrins), f(post_rots), f(post_trans), f(bda)
+    dev = depth_logits.device
+    ws = _workspace(BN * D * HW, B, X, Y, Z, dev)
+    prob = torch.empty((BN, D, fH, fW), dtype=torch.float32, device=dev)
+    feat_cl = torch.empty((BN, HW, C), dtype=torch.float32, device=dev)
+    out = torch.empty((B, X, Y, Z, C), dtype=torch.float32, device=dev)
+    out_s = torch.empty_like(out) if with_split else None
+    fl = [float(v) for v in (*dx, *bx, *nx)]
+    check(lib().occ_lift_splat_fused(_ptr(depth_logits), ls, _ptr(img_feat), fs, _ptr(fr), _ptr(r), _ptr(t), _ptr(k), k.shape[-2],
+                                     k.shape[-1], _ptr(pr), _ptr(pt), _ptr(bd), bd.shape[-1], _ptr(prob), _ptr(feat_cl),
+                                     _ptr(out), _ptr(out_s), B, N, D, HW, C, *fl, X, Y, Z, _ptr(ws.buf), ws.nbytes,
+                                     _stream(prob)), "occ_lift_splat_fused")
+    LAUNCH_COUNT[0] += 3
+    return ((out, out_s) if with_split else out), prob
+
+
 def voxel_pool_geom(feats, geom, B, dx, bx, nx, grid, return_workspace=False):
     """Materialised-volume voxel pooling: feats (P,C), geom (P,3) -> (B,X,Y,Z,C)."""
     _chk(feats, "feats"), _chk(geom, "geom")

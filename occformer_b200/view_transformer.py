@@ -192,9 +192,14 @@ class ViewTransformerLiftSplatShootVoxel(nn.Module):
         x = self.depth_net(x, mlp_input) if self._depth_net_takes_mlp else self.depth_net(x)
         depth_digit = x[:, :self.D, ...]
         img_feat = x[:, self.D:self.D + self.numC_Trans, ...]
-        geom = self.get_geometry(rots, trans, intrins, post_rots, post_trans, bda)
+        if not x.is_cuda:
+            raise RuntimeError("occformer_b200: the view transformer runs on CUDA tensors only (no CPU fallback)")
+        # depth softmax + get_geometry + voxel index + point lists + NHWC transpose in ONE front kernel, then the pooling
+        # kernel (occ_lift_splat_fused); get_geometry / lift_splat stay available as separate calls
         split = self.numC_Trans % 32 == 0
-        grid, depth_prob = self.lift_splat(depth_digit, img_feat, geom, B, N, with_split=split)
+        dx, bx, nx = self._host_params()
+        grid, depth_prob = ops.lift_splat_fused(depth_digit, img_feat, self.frustum.data, rots, trans, intrins, post_rots, post_trans, bda, B, N,
+                                                dx, bx, nx, self.grid_size(), with_split=split)
         if split:
             out = grid[0].permute(0, 4, 1, 2, 3)
             out._occ_s32 = grid[1]  # operand of the encoder's first conv (occformer_b200.encoder picks it up)

@@ -213,3 +213,49 @@ def test_geometry_kernel_vs_oracle(cuda, kind):
     near = ((frac - frac.round()).abs() < 1e-4).any(-1)
     assert bool((~diff | near).all()), "index flips away from cell boundaries"
     print(f"geometry {kind}: {int(diff.sum())} of {diff.numel()} points change voxel (all within 1e-4 cells of a boundary)")
+
+
+class _PassThrough(torch.nn.Module):
+    def forward(self, x, mlp_input=None):
+        return x
+
+
+@pytest.mark.parametrize("wl,B", [("pr1", 2), ("kitti", 2), ("nusc_200", 1)])
+def test_forward_fused_front_end_vs_oracle(cuda, wl, B):
+    """ViewTransformerLiftSplatShootVoxel.forward(input) = one fused front kernel (depth softmax + get_geometry + voxel
+    index + lists + NHWC transpose) + the pooling kernel, fed with channel slices of the (B*N, D+C, fH, fW) map (no copies):
+    same voxel bookkeeping as the oracle's index math on the oracle geometry, same sums, same depth_prob."""
+    from occformer_b200 import ops
+    from occformer_b200.view_transformer import ViewTransformerLiftSplatShootVoxel
+    C = 32
+    if wl == "pr1":
+        grid_name, size, N, cams = "pr1", (128, 128), 1, synth.pr1_camera(B)
+    else:
+        w = synth.WORKLOADS[wl]
+        grid_name, size, N, cams = w["grid"], w["input_size"], w["cams"], synth.workload_cameras(wl, B)
+    gc, geom, dx, bx, nx, dd, feat = _setup(grid_name, cams, size, B, N, C, seed=13)
+    D, fH, fW = dd.shape[1:]
+    vt = ViewTransformerLiftSplatShootVoxel(grid_config=gc, data_config={"input_size": size}, numC_input=D + C, numC_Trans=C,
+                                            depth_net=_PassThrough()).to(cuda)
+    x = torch.cat([dd, feat], 1).view(B, N, D + C, fH, fW).to(cuda)
+    mats = [cams[k].to(cuda) for k in ("rots", "trans", "intrins", "post_rots", "post_trans", "bda")]
+    voxel, prob = vt([x] + mats + [vt.get_mlp_input(*mats)])
+    vol, prob_ref = port.lift(dd, feat, B, N)
+    ref, gf, kept = port.voxel_pooling(geom, vol, dx, bx, nx)
+    assert_close(prob, prob_ref, 1e-5, f"{wl} forward depth_prob")
+    X, Y, Z = vt.grid_size()
+    ws = ops._workspace(gf.shape[0], B, X, Y, Z, cuda)
+    torch.cuda.synchronize()
+    vox = ws.vox_id.cpu().long()
+    ref_lin = ((gf[:, 3] * X + gf[:, 0]) * Y + gf[:, 1]) * Z + gf[:, 2]
+    ref_vox = torch.where(kept, ref_lin, torch.full_like(ref_lin, -1))
+    flips = vox != ref_vox
+    # the geometry is recomputed in-kernel: a point may change voxel only within 1e-4 cells of a cell boundary
+    frac = ((geom.view(-1, 3) - (bx - dx / 2.0)) / dx)
+    near = ((frac - frac.round()).abs() < 1e-4).any(-1)
+    assert bool((~flips | near).all()), "index flips away from cell boundaries"
+    if int(flips.sum()) == 0:
+        assert_close(voxel, ref, 1e-5, f"{wl} forward pooled grid")
+        assert torch.equal(ops.to_split(voxel.permute(0, 2, 3, 4, 1).contiguous()).view(torch.int32),
+                           voxel._occ_s32.view(torch.int32))
+    print(f"{wl}: forward front-end flips {int(flips.sum())} of {flips.numel()}")
