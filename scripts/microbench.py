@@ -1,16 +1,14 @@
 """Per-kernel timings at BASELINE sizes (CUDA events, L2 flushed between iterations).  Development aid;
-bench.py is the contract benchmark."""
+bench.py is the contract benchmark.  usage: python scripts/microbench.py [conv gemm attn tail neck lift]"""
 import json
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 
 from occformer_b200 import ops, synth
-from occformer_b200.view_transformer import ViewTransformerLiftSplatShootVoxel
 
 dev = torch.device("cuda:0")
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -34,80 +32,98 @@ def timeit(fn, iters=5, warm=2):
 
 def main():
     res = {}
-    which = sys.argv[1:] or ["pool", "fill", "gemm", "conv", "attn", "block"]
+    which = sys.argv[1:] or ["conv", "gemm", "attn", "tail", "neck", "lift"]
     X, Y, Z, C = 200, 200, 16, 128
-    if "pool" in which:
-        from oracle import port  # geometry only (inputs), not on the measured path
-        gc = synth.grid_config("nusc_200")
-        vt = ViewTransformerLiftSplatShootVoxel(grid_config=gc, data_config={"input_size": (256, 704)}, numC_Trans=C).to(dev)
-        cams = {k: v.to(dev) for k, v in synth.nusc_cameras(1, 6).items()}
-        geom = vt.get_geometry(**cams).contiguous()
-        dd, feat = synth.lift_inputs(1, 6, 112, 16, 44, C)
-        dd, feat = dd.to(dev), feat.to(dev)
-        prob, feat_cl = ops.lift_prologue(dd, feat)
-        dx, bx, nx = vt._host_params()
-        t = timeit(lambda: ops.lift_splat(prob, feat_cl, geom, 1, 6, dx, bx, nx, vt.grid_size()))
-        P = geom.numel() // 3
-        alg = P * 4 + 6 * 16 * 44 * C * 4 + P * 12 + X * Y * Z * C * 4
-        res["lift_splat_ms"] = t
-        res["lift_splat_GBps_fused_formula"] = alg / t / 1e6
-        t2 = timeit(lambda: ops.lift_prologue(dd, feat))
-        res["lift_prologue_ms"] = t2
-    if "fill" in which:
-        big = torch.empty(1, X, Y, Z, C, device=dev)
-        t = timeit(lambda: big.zero_())
-        res["torch_zero_328MB_ms"] = t
-        res["torch_zero_GBps"] = big.numel() * 4 / t / 1e6
-        src = torch.randn(1, X, Y, Z, C, device=dev)
-        t = timeit(lambda: big.copy_(src))
-        res["torch_copy_328MB_ms"] = t
-        res["torch_copy_GBps(read+write)"] = 2 * big.numel() * 4 / t / 1e6
-    if "gemm" in which:
-        M = X * Y * (Z + 1)
-        a = torch.randn(M, C, device=dev)
-        for N in (384, 128):
-            w = torch.randn(N, C, device=dev)
-            b = torch.randn(N, device=dev)
-            t = timeit(lambda: ops.gemm(a, w, bias=b))
-            res[f"gemm_M{M}_N{N}_K{C}_ms"] = t
-            res[f"gemm_M{M}_N{N}_K{C}_TFLOPs"] = 2.0 * M * N * C / t / 1e9
+    rows = X * Y * (Z + 1)
     if "conv" in which:
         x = torch.randn(1, X, Y, Z, C, device=dev)
-        w2, ks = ops.repack_conv_weight(torch.randn(C, C, 3, 3, 3, device=dev))
+        xs = ops.to_split(x)
+        w = torch.randn(C, C, 3, 3, 3) * 0.02
+        w2, ks = ops.repack_conv_weight(w)
+        w2 = w2.to(dev)
         stats = torch.zeros(1, 32, 2, dtype=torch.float64, device=dev)
-        t = timeit(lambda: ops.conv(x, w2, ks, gn_stats=stats, cpg=4))
-        res["conv3d_200x200x16_c128_ms"] = t
-        res["conv3d_TFLOPs"] = 2.0 * 27 * C * C * X * Y * Z / t / 1e9
-        xl = torch.randn(1, X, Y, Z, C, device=dev).permute(0, 4, 1, 2, 3).contiguous(memory_format=torch.channels_last_3d)
-        wt = torch.randn(C, C, 3, 3, 3, device=dev).contiguous(memory_format=torch.channels_last_3d)
-        t = timeit(lambda: torch.nn.functional.conv3d(xl, wt, padding=1))
-        res["cudnn_conv3d_ms(for context)"] = t
+        t = timeit(lambda: ops.conv(xs, w2, ks, gn_stats=stats, cpg=4))
+        fl = 2 * 27 * C * C * X * Y * Z
+        res["conv3d_c128_bf16x3_ms"] = t
+        res["conv3d_c128_alg_TFs"] = fl / t / 1e9
+        # library context: cuDNN channels-last-3d, TF32 (1 pass, ~4e-4 error) and strict fp32
+        xc = x.permute(0, 4, 1, 2, 3).contiguous(memory_format=torch.channels_last_3d)
+        wc = w.to(dev).contiguous(memory_format=torch.channels_last_3d)
+        for name, flag in (("tf32", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = flag
+            torch.backends.cudnn.benchmark = True
+            try:
+                res[f"cudnn_conv3d_{name}_ms(context)"] = timeit(lambda: torch.nn.functional.conv3d(xc, wc, padding=1), iters=3)
+            except Exception as e:  # noqa: BLE001
+                res[f"cudnn_conv3d_{name}_ms(context)"] = str(e)[:80]
+        # neck output conv 192 -> 192
+        E = 192
+        xe = ops.to_split(torch.randn(1, X, Y, Z, E, device=dev))
+        we, ke = ops.repack_conv_weight(torch.randn(E, E, 3, 3, 3) * 0.02)
+        we = we.to(dev)
+        t = timeit(lambda: ops.conv(xe, we, ke), iters=3)
+        res["conv3d_c192_bf16x3_ms"] = t
+        res["conv3d_c192_alg_TFs"] = 2 * 27 * E * E * X * Y * Z / t / 1e9
+        del x, xs, xc, xe
+    if "gemm" in which:
+        a = ops.to_split(torch.randn(rows, C, device=dev))
+        w = ops.split_weight(torch.randn(3 * C, C) * C ** -0.5).to(dev)
+        b = torch.randn(3 * C, device=dev)
+        res["gemm_qkv_split_out_ms"] = timeit(lambda: ops.gemm(a, w, bias=b, split_out=True))
+        a2 = ops.to_split(torch.randn(91250, 192, device=dev))
+        w2 = ops.split_weight(torch.randn(768, 192) * 192 ** -0.5).to(dev)
+        res["gemm_neck_ffn1_91250x768x192_ms"] = timeit(lambda: ops.gemm(a2, w2, act=1, split_out=True))
+        del a, a2
     if "attn" in which:
-        M = X * Y * (Z + 1)
-        qkv = torch.randn(M, 3 * C, device=dev)
-        qb = torch.randn(3 * C, device=dev)
-        bd = torch.randn(4, 2404, device=dev)
-        t = timeit(lambda: ops.window_attention(qkv, qb, bd, 1, X, Y, Z, C, 4, True))
-        res["window_attn_tc_ms"] = t
-        res["window_attn_tc_head_major_ms"] = timeit(lambda: ops.window_attention(qkv, qb, bd, 1, X, Y, Z, C, 4, True, head_major=True))
-        res["window_attn_GBps"] = (M * 3 * C * 4 + M * C * 4) / t / 1e6
-    if "swin" in which:
-        M = X * Y * (Z + 1)
-        att = ops.round_tf32_(torch.randn(M, C, device=dev))
+        heads = C // 32
+        tokn = ops.to_split(torch.randn(rows, C, device=dev))
+        wq = ops.split_weight(torch.randn(3 * C, C) * C ** -0.5).to(dev)
+        bq = torch.randn(3 * C, device=dev) * 0.1
+        bqs = ops.split_weight(bq.cpu().view(1, -1)).view(-1).to(dev)
+        bias_pad = torch.randn(heads, 2404, device=dev) * 0.1
+        qkv = ops.gemm(tokn, wq, bias=bq, split_out=True)
+        res["window_attn_tc_ms"] = timeit(lambda: ops.window_attention(qkv, bqs, bias_pad, 1, X, Y, Z, C, heads, True, head_major=True))
+        res["swin_qkv_attn_fused_ms"] = timeit(lambda: ops.swin_qkv_attention(tokn, wq, bq, bias_pad, 1, X, Y, Z, C, heads, True))
+        del qkv, tokn
+    if "tail" in which:
+        M = rows
+        att = ops.to_split(torch.randn(M, C, device=dev))
         tok = torch.randn(M, C, device=dev)
-        ws = [ops.round_tf32_(torch.randn(C, C, device=dev) * C ** -0.5) for _ in range(3)]
-        bs = [0.1 * torch.randn(C, device=dev) for _ in range(3)]
+        ws = [ops.split_weight(torch.randn(C, C) * C ** -0.5).to(dev) for _ in range(3)]
+        bs = [torch.randn(C, device=dev) * 0.1 for _ in range(3)]
         lw, lb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
-        t = timeit(lambda: ops.swin_proj_ffn(att, tok, ws[0], bs[0], lw, lb, ws[1], bs[1], ws[2], bs[2]))
-        res["swin_proj_ffn_fused_ms"] = t
-        res["swin_proj_ffn_GBps"] = 3 * M * C * 4 / t / 1e6
-    if "block" in which:
-        from occformer_b200.encoder import OccupancyEncoder
-        enc = OccupancyEncoder(in_channels=128, num_stage=4, block_numbers=[2, 2, 2, 2], block_inplanes=[128, 256, 512, 1024],
-                               block_strides=[1, 2, 2, 2], out_indices=(0, 1, 2, 3), norm_cfg=dict(type="GN", num_groups=32)).to(dev).eval()
-        x = torch.randn(1, X, Y, Z, C, device=dev)
-        t = timeit(lambda: enc.forward_cl(x), iters=3, warm=1)
-        res["encoder_200x200x16_ms"] = t
+        res["swin_mlp_fused_ms"] = timeit(lambda: ops.swin_proj_ffn(att, tok, ws[0], bs[0], lw, lb, ws[1], bs[1], ws[2], bs[2]))
+        del att, tok
+    if "neck" in which:
+        E, H, L, P = 192, 8, 3, 4
+        grids = [(25, 25, 2), (50, 50, 4), (100, 100, 8)]
+        Nq = sum(a * b * c for a, b, c in grids)
+        v = torch.randn(Nq, E, device=dev)
+        ow = torch.cat([torch.randn(Nq, H * L * P * 3, device=dev) * 1.5, torch.randn(Nq, H * L * P, device=dev)], 1).contiguous()
+        res["ms_deform_attn_91250_ms"] = timeit(lambda: ops.ms_deform_attn(v, ow, grids, [16, 8, 4], 1, E, H, P))
+        res["neck_token_prep_ms"] = timeit(lambda: ops.neck_token_prep(v, grids, 1, ln=(torch.ones(E, device=dev), torch.zeros(E, device=dev)),
+                                                                   pos=v, want_pos=True))
+    if "lift" in which:
+        from occformer_b200.view_transformer import ViewTransformerLiftSplatShootVoxel
+        gc = synth.grid_config("nusc_200")
+        vt = ViewTransformerLiftSplatShootVoxel(grid_config=gc, data_config={"input_size": (256, 704)}, numC_input=64,
+                                                numC_Trans=C).to(dev)
+        cams = {k: v.to(dev) for k, v in synth.nusc_cameras(1, 6).items()}
+        dd, feat = synth.lift_inputs(1, 6, 112, 16, 44, C)
+        dd, feat = dd.to(dev), feat.to(dev)
+        dx, bx, nx = vt._host_params()
+        t = timeit(lambda: ops.lift_splat_fused(dd, feat, vt.frustum.data, cams["rots"], cams["trans"], cams["intrins"],
+                                                cams["post_rots"], cams["post_trans"], cams["bda"], 1, 6, dx, bx, nx,
+                                                vt.grid_size(), with_split=True))
+        Pn = 6 * 112 * 16 * 44
+        alg = Pn * 4 + 6 * 16 * 44 * C * 4 + Pn * 12 + X * Y * Z * C * 4
+        res["lift_splat_fused_ms(3 launches, with S32 twin)"] = t
+        res["lift_splat_fused_GBps_fused_formula"] = alg / t / 1e6
+        t = timeit(lambda: ops.lift_splat_fused(dd, feat, vt.frustum.data, cams["rots"], cams["trans"], cams["intrins"],
+                                                cams["post_rots"], cams["post_trans"], cams["bda"], 1, 6, dx, bx, nx,
+                                                vt.grid_size(), with_split=False))
+        res["lift_splat_fused_ms(no twin)"] = t
+        res["lift_splat_fused_GBps_no_twin"] = alg / t / 1e6
     print(json.dumps(res, indent=1))
 
 
