@@ -17,6 +17,7 @@
 namespace occ {
 
 constexpr int NK_MAX_LEVELS = 4;
+constexpr int NK_PASSES = 8;  // token rows per CTA of the deformable gather = NK_PASSES * (256 / (E/4))
 
 struct NeckLevels {
   int L, B;
@@ -112,19 +113,22 @@ token_prep_kernel(const float* __restrict__ in, const float* __restrict__ ln_w, 
 //   out   (rows, E)  S32       sum_{l,p} softmax(logits)[l,p] * trilinear(value level l)(loc), zeros outside,
 //                              align_corners=False;  loc = ref + offset / (Z_l, Y_l, X_l),  ref = voxel centre of the
 //                              query in its own level, normalised to [0,1] (the same point for every value level)
-// One CTA = NQ queries x (E/4) threads; thread = (query, float4 of channels) -> head = 4*t / hd.  The 8 corner rows of a
-// sampling point are 8 independent 16-byte loads per thread (96-byte runs per head: whole 32-byte sectors); neighbouring
-// queries sample neighbouring voxels, so most of the traffic is served by L1 / L2 (the value tensor, 70 MB at 91 250
-// tokens, is L2 resident).
+// One CTA = NQ queries x (E/4) threads per pass, NK_PASSES passes over consecutive token rows (z fastest, then y: a compact
+// patch of the volume, so that the corner rows fetched for one query are L1 hits for its neighbours); thread = (query,
+// float4 of channels) -> head = 4*t / hd.  The 8 corner rows of a sampling point are 8 independent 16-byte loads per
+// thread (96-byte runs per head: whole 32-byte sectors); the value tensor (70 MB at 91 250 tokens) is L2 resident.
 template <int L, int P>
 __global__ void __launch_bounds__(256)
 ms_deform_attn_kernel(const float* __restrict__ value, const float* __restrict__ ow, float* __restrict__ out,
                       const NeckLevels g, int E, int H, int NQ) {
   const int T = E >> 2;  // threads per query
   const int ql = threadIdx.x / T, t = threadIdx.x - ql * T;
-  const long long row = (long long)blockIdx.x * NQ + ql;
-  if (ql >= NQ || row >= g.rows) return;
+  if (ql >= NQ) return;
   const int hd = E / H;
+#pragma unroll 1
+  for (int pass = 0; pass < NK_PASSES; ++pass) {
+  const long long row = ((long long)blockIdx.x * NK_PASSES + pass) * NQ + ql;
+  if (row >= g.rows) return;
   const int h = (4 * t) / hd;
   int lq, b, local;
   nk_locate(g, row, lq, b, local);
@@ -192,6 +196,7 @@ ms_deform_attn_kernel(const float* __restrict__ value, const float* __restrict__
     }
   }
   store_split4(out + row * E, 4 * t, acc);
+  }  // pass
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -335,7 +340,7 @@ extern "C" int occ_ms_deform_attn(const float* value, const float* ow, float* ou
   OCC_REQUIRE(fill_levels(g, L, B, grids, strides) == OCC_OK);
   const int T = E / 4;
   const int NQ = 256 / T >= 1 ? 256 / T : 1;
-  const unsigned blocks = (unsigned)((g.rows + NQ - 1) / NQ);
+  const unsigned blocks = (unsigned)((g.rows + (long long)NQ * NK_PASSES - 1) / ((long long)NQ * NK_PASSES));
   if (L == 3 && P == 4) ms_deform_attn_kernel<3, 4><<<blocks, NQ * T, 0, stream>>>(value, ow, out, g, E, H, NQ);
   else if (L == 1 && P == 4) ms_deform_attn_kernel<1, 4><<<blocks, NQ * T, 0, stream>>>(value, ow, out, g, E, H, NQ);
   else if (L == 2 && P == 4) ms_deform_attn_kernel<2, 4><<<blocks, NQ * T, 0, stream>>>(value, ow, out, g, E, H, NQ);
