@@ -109,6 +109,11 @@ int occ_conv_bf16x3(const float* x, const float* w2, float* out, int B, int X, i
                     int KY, int KZ, int stride, int dil, const float* bias, const float* residual, int act,
                     int split_out, double* gn_stats, int cpg, void* workspace, size_t workspace_bytes,
                     occ_stream_t stream);
+/* Several same-input stride-1 convolutions in ONE launch via an explicit tap table: taps = ntaps x (dx, dy, dz) input offsets
+ * (HOST ints), w2 (Cout, ntaps*Cin) S32 tap-major in the table's order (zero where a branch does not use a tap).  The four
+ * ASPP branches (1x1 + three dilated 3x3, P/occformer/backbones/modules/aspp.py:107-113) become one 25-tap launch. */
+int occ_conv_taps_bf16x3(const float* x, const float* w2, float* out, int B, int X, int Y, int Z, int Cin, int Cout,
+                         int ntaps, const int* taps, double* gn_stats, int cpg, occ_stream_t stream);
 /* fp32 rows (rows, C) <-> S32 (C % 32 == 0) */
 int occ_split_rows(const float* in, float* out, long long rows, int C, occ_stream_t stream);
 int occ_unsplit_rows(const float* in, float* out, long long rows, int C, occ_stream_t stream);

@@ -30,6 +30,10 @@ constexpr int BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 4;
 constexpr int EPI_BUF_BYTES = 32 * 128;                 // one 32-row x 32-column fp32 chunk, 128-byte swizzled rows
 constexpr int EPI_BYTES = 8 /*warps*/ * EPI_BUF_BYTES;
+constexpr int CTRL_BYTES = 2048;   // mbarriers + TMEM pointer + fp64 GroupNorm partial sums of up to 64 groups; a multiple
+                                   // of 1024 so that the swizzled epilogue staging buffers behind it stay 1024-byte aligned
+constexpr int MAX_STAT_GROUPS = 64;
+constexpr int MAX_TAPS = 28;
 
 struct GemmParams {
   int M, N, K, num_k_blocks;
@@ -63,6 +67,10 @@ struct GemmParams {
   int cpg;
   int rows_per_batch;  // plain mode: rows per batch sample (for gn_stats), else 0
   int* splitk_sem;     // [SPLITK_SEMS], see above (required when splits > 1)
+  // explicit tap table (conv mode, stride 1): tap t reads the input at voxel + (tdx, tdy, tdz)[t] (dilation and padding
+  // folded in); 0 = the regular KX x KY x KZ stencil.  Lets several dilated branches share one launch (ASPP).
+  int ntaps;
+  signed char tdx[MAX_TAPS], tdy[MAX_TAPS], tdz[MAX_TAPS];
 };
 
 // Split-K ordering: sem[(m, n) tile] counts the splits that have added their partial sum.  Split s adds after split
@@ -128,8 +136,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  double* stat_acc = reinterpret_cast<double*>(tmem_ptr + 2);  // [64] doubles: (sum, sumsq) per group, <= 32 groups
-  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES + 1024;  // 4 warps x 2 buffers x 4 KB, 1024-byte aligned
+  double* stat_acc = reinterpret_cast<double*>(tmem_ptr + 2);  // (sum, sumsq) per group, <= MAX_STAT_GROUPS groups
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES + CTRL_BYTES;  // 8 warps x 4 KB, 1024-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -157,7 +165,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_ptr);
   if (threadIdx.x >= 128) {
-    for (int i = threadIdx.x - 128; i < 64; i += 256) stat_acc[i] = 0.0;
+    for (int i = threadIdx.x - 128; i < 2 * MAX_STAT_GROUPS; i += 256) stat_acc[i] = 0.0;
   }
   tc_fence_before();
   __syncthreads();
@@ -205,10 +213,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           if (p.conv) {
+            // input offset of this tap: regular stencil (dilated, padding folded into c?0) or the explicit table
+            const int ox = p.ntaps ? p.tdx[tap] : tx_ * p.dil, oy = p.ntaps ? p.tdy[tap] : ty_ * p.dil,
+                      oz = p.ntaps ? p.tdz[tap] : tz_ * p.dil;
 #pragma unroll
             for (int sub = 0; sub < MT; ++sub)
-              tma_load_5d(sa + sub * A_STAGE_BYTES, &tmA, &full_bar[stage], kc * BK, cz0[sub] + tz_ * p.dil,
-                          cy0[sub] + ty_ * p.dil, cx0[sub] + tx_ * p.dil, cb[sub]);
+              tma_load_5d(sa + sub * A_STAGE_BYTES, &tmA, &full_bar[stage], kc * BK, cz0[sub] + oz, cy0[sub] + oy,
+                          cx0[sub] + ox, cb[sub]);
             if (++kc == cblocks) {
               kc = 0;
               ++tap;
@@ -622,8 +633,7 @@ conv_gn_stats_kernel(const float* __restrict__ out, double* __restrict__ stats, 
 template <int BN, int STAGES, int MT = 1>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        int num_tiles, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (MT * A_STAGE_BYTES + BN * BK * 4) + 1024 /*align*/ +
-                          1024 /*barriers+stats*/ + EPI_BYTES;
+  constexpr size_t smem = (size_t)STAGES * (MT * A_STAGE_BYTES + BN * BK * 4) + 1024 /*align*/ + CTRL_BYTES + EPI_BYTES;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   OCC_ENSURE_SMEM((gemm_bf16x3_kernel<BN, STAGES, MT>), smem);
   int grid = num_tiles < sm_count() ? num_tiles : sm_count();
@@ -672,7 +682,7 @@ extern "C" int occ_gemm_bf16x3(const float* A, const float* W, float* out, int M
   OCC_REQUIRE(!split_out || N % 32 == 0);   // S32 output rows
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   OCC_REQUIRE(act >= 0 && act <= 2);
-  if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && N % cpg == 0 && N / cpg <= 32 &&
+  if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && N % cpg == 0 && N / cpg <= MAX_STAT_GROUPS &&
                             rows_per_batch > 0 && rows_per_batch % BM == 0);
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.num_k_blocks = (K + BK - 1) / BK;
@@ -713,7 +723,7 @@ extern "C" int occ_conv_bf16x3(const float* x, const float* w2, float* out, int 
   OCC_REQUIRE(stride == 1 || stride == 2);
   OCC_REQUIRE(dil >= 1 && act >= 0 && act <= 2);
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0);
-  if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && Cout % cpg == 0 && Cout / cpg <= 32);
+  if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && Cout % cpg == 0 && Cout / cpg <= MAX_STAT_GROUPS);
   GemmParams p{};
   p.conv = 1;
   p.Cin = Cin; p.KX = KX; p.KY = KY; p.KZ = KZ; p.dil = dil; p.stride = stride;
@@ -796,6 +806,54 @@ extern "C" int occ_conv_bf16x3(const float* x, const float* w2, float* out, int 
   return OCC_OK;
 }
 
+
+// Several same-input stride-1 convolutions in one launch: an explicit tap table instead of a regular stencil.
+// x (B,X,Y,Z,Cin) S32; taps: ntaps x (dx, dy, dz) input offsets (HOST ints, |offset| <= 127); w2 (Cout, ntaps*Cin) S32,
+// tap-major in the table's order (a branch that does not use a tap has zero weights there); out (B,X,Y,Z,Cout) raw fp32;
+// gn_stats as occ_conv_bf16x3 (up to 64 groups).  Used for the four ASPP branches (1x1 + three dilated 3x3,
+// P/occformer/backbones/modules/aspp.py:107-113): one launch with 25 taps instead of four.
+extern "C" int occ_conv_taps_bf16x3(const float* x, const float* w2, float* out, int B, int X, int Y, int Z, int Cin,
+                                    int Cout, int ntaps, const int* taps, double* gn_stats, int cpg, cudaStream_t stream) {
+  OCC_REQUIRE(x && w2 && out && taps);
+  OCC_REQUIRE(B > 0 && X > 0 && Y > 0 && Z > 0 && Cin > 0 && Cout > 0 && Cin % BK == 0 && ntaps >= 1 && ntaps <= MAX_TAPS);
+  OCC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(out) & 15) == 0 && Cout % 4 == 0);
+  if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && Cout % cpg == 0 && Cout / cpg <= MAX_STAT_GROUPS);
+  GemmParams p{};
+  p.conv = 1;
+  p.Cin = Cin; p.KX = p.KY = p.KZ = 1; p.dil = 1; p.stride = 1; p.padx = p.pady = p.padz = 0;
+  p.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) {
+    OCC_REQUIRE(taps[3 * t] >= -127 && taps[3 * t] <= 127 && taps[3 * t + 1] >= -127 && taps[3 * t + 1] <= 127 &&
+                taps[3 * t + 2] >= -127 && taps[3 * t + 2] <= 127);
+    p.tdx[t] = (signed char)taps[3 * t]; p.tdy[t] = (signed char)taps[3 * t + 1]; p.tdz[t] = (signed char)taps[3 * t + 2];
+  }
+  p.B = B; p.Xo = X; p.Yo = Y; p.Zo = Z;
+  p.bz = next_pow2(Z) < BM ? next_pow2(Z) : BM;
+  p.by = next_pow2(Y) < BM / p.bz ? next_pow2(Y) : BM / p.bz;
+  p.bx = BM / (p.bz * p.by);
+  p.tiles_x = (X + p.bx - 1) / p.bx; p.tiles_y = (Y + p.by - 1) / p.by; p.tiles_z = (Z + p.bz - 1) / p.bz;
+  p.N = Cout; p.K = ntaps * Cin; p.num_k_blocks = p.K / BK; p.M = B * X * Y * Z;
+  p.out = out; p.ldo = Cout; p.ldr = Cout; p.act = 0; p.split_out = 0;
+  p.gn_stats = gn_stats; p.cpg = cpg; p.rows_per_batch = 0; p.store_out = 1; p.splits = 1;
+  CUtensorMap tmA;
+  uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)Z, (uint64_t)Y, (uint64_t)X, (uint64_t)B};
+  uint64_t strides[4] = {(uint64_t)Cin * 4, (uint64_t)Z * Cin * 4, (uint64_t)Y * Z * Cin * 4, (uint64_t)X * Y * Z * Cin * 4};
+  uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.bz, (uint32_t)p.by, (uint32_t)p.bx, 1};
+  int rc = make_tmap_f32(&tmA, x, 5, dims, strides, box, nullptr);
+  if (rc) return rc;
+  const int ez = p.bz < 32 ? p.bz : 32;
+  const int ey = p.by < 32 / ez ? p.by : 32 / ez;
+  const int ex = 32 / (ez * ey);
+  CUtensorMap tmC;
+  uint64_t cd[5] = {(uint64_t)Cout, (uint64_t)Z, (uint64_t)Y, (uint64_t)X, (uint64_t)B};
+  uint64_t cs[4] = {(uint64_t)Cout * 4, (uint64_t)Z * Cout * 4, (uint64_t)Y * Z * Cout * 4, (uint64_t)X * Y * Z * Cout * 4};
+  uint32_t cb[5] = {32u, (uint32_t)ez, (uint32_t)ey, (uint32_t)ex, 1u};
+  rc = make_tmap_f32(&tmC, out, 5, cd, cs, cb, nullptr);
+  if (rc) return rc;
+  p.use_tma_store = 1;
+  return dispatch_gemm(tmA, tmC, w2, p, B * p.tiles_x * p.tiles_y * p.tiles_z, stream);
+}
 
 // Decoder mask logits with fused attention-mask pooling (mask2former_nusc_occ.py:457-466):
 //   mask[b, v, q] = <mask_feature[b, v, :], mask_embed[b, q, :]>   (1x1x1 "conv" over the voxel grid, K = E)

@@ -158,6 +158,28 @@ class DualpathTransformerBlock(nn.Module):
         P["w_a_in"], P["k1"] = ops.repack_conv_weight(a.input_conv[0].weight)
         for i in (1, 2, 3, 4):
             P[f"w_a{i}"], P[f"k_a{i}"] = ops.repack_conv_weight(getattr(a.aspp, f"aspp{i}").atrous_conv.weight)
+        # the four ASPP branches (1x1 + three dilated 3x3 on the same input) as ONE tap-table convolution when their
+        # 4 * inner_groups GroupNorm groups fit the conv epilogue's statistics (stage 0: 4 x 16): taps = centre + 8 x 3 rings
+        ch = a.input_conv[0].weight.shape[0]
+        P["aspp_merged"] = None
+        ks = [tuple(getattr(a.aspp, f"aspp{i}").atrous_conv.weight.shape[-2:]) for i in (1, 2, 3, 4)]
+        if 4 * a.inner_groups <= 64 and ks == [(1, 1), (3, 3), (3, 3), (3, 3)] and ch % 32 == 0:
+            taps = [(0, 0, 0)]
+            for d in a.dilations[1:]:
+                taps += [(i * d, j * d, 0) for i in (-1, 0, 1) for j in (-1, 0, 1) if (i, j) != (0, 0)]
+            wm = torch.zeros(4 * ch, len(taps), ch)
+            wm[0:ch, 0] = a.aspp.aspp1.atrous_conv.weight.detach().float().cpu()[:, :, 0, 0]
+            for bi, d in enumerate(a.dilations[1:], start=1):
+                wb = getattr(a.aspp, f"aspp{bi + 1}").atrous_conv.weight.detach().float().cpu()  # (ch, ch, 3, 3) [kx][ky]
+                for i in (-1, 0, 1):
+                    for j in (-1, 0, 1):
+                        t = 0 if (i, j) == (0, 0) else taps.index((i * d, j * d, 0))
+                        wm[bi * ch:(bi + 1) * ch, t] = wb[:, :, i + 1, j + 1]
+            dev = a.input_conv[0].weight.device
+            gns = [getattr(a.aspp, f"aspp{i}").bn for i in (1, 2, 3, 4)]
+            P["aspp_merged"] = dict(taps=taps, w=ops.split_weight(wm.reshape(4 * ch, -1)).to(dev),
+                                    gw=torch.cat([g.weight.detach().float() for g in gns]).contiguous(),
+                                    gb=torch.cat([g.bias.detach().float() for g in gns]).contiguous())
         P["w_gap"] = a.aspp.global_avg_pool[1].weight.detach().float().reshape(a.aspp.global_avg_pool[1].weight.shape[0], -1).contiguous()
         P["w_a_c1"], _ = ops.repack_conv_weight(a.aspp.conv1.weight)
         P["w_a_out"], _ = ops.repack_conv_weight(a.output_conv[0].weight)
@@ -178,7 +200,7 @@ class DualpathTransformerBlock(nn.Module):
         B, X0, Y0, Z0, Cin = x_s.shape
         C, G, s = self.channels, self.groups, self.stride
         dev = x_s.device
-        stats = torch.zeros((10, B, 32, 2), dtype=torch.float64, device=dev)
+        stats = torch.zeros((10, B, 64, 2), dtype=torch.float64, device=dev)
         # (A4) Conv3d 3x3x3 (+stride) -> raw output + GroupNorm statistics from the GEMM epilogue
         y_raw = ops.conv(x_s, P["w_in"], P["k_in"], stride=s, gn_stats=stats[0], cpg=C // G)
         _, X, Y, Z, _ = y_raw.shape
@@ -232,7 +254,14 @@ class DualpathTransformerBlock(nn.Module):
         t = conv2d(ops.to_split(x_bev), P["w_a_in"], (1, 1, 1), st=stats[1], cpg=ch // go)
         y, y_s = ops.gn_apply(t, stats[1], a.input_conv[1].weight, a.input_conv[1].bias, XY, go, want_split=True)
         cat_s = torch.empty((B * XY, 5 * ch), dtype=torch.float32, device=x_bev.device)  # S32 concat buffer
-        for i, d in zip((1, 2, 3, 4), a.dilations):
+        mg = P["aspp_merged"]
+        if mg is not None:
+            # all four branches in one 25-tap launch; their GroupNorms are one GroupNorm(4 * gi groups) over 4 * ch channels
+            t = ops.conv_taps(y_s.view(B, X, Y, 1, ch), mg["w"], mg["taps"], gn_stats=stats[2].view(-1)[:B * 4 * gi * 2].view(B, 4 * gi, 2),
+                              cpg=ch // gi).view(B * XY, 4 * ch)
+            ops.gn_apply(t, stats[2].view(-1)[:B * 4 * gi * 2].view(B, 4 * gi, 2), mg["gw"], mg["gb"], XY, 4 * gi, want_f32=False,
+                         split_into=cat_s, out_off=0)
+        for i, d in zip((1, 2, 3, 4) if mg is None else (), a.dilations):
             m = getattr(a.aspp, f"aspp{i}")
             k = P[f"k_a{i}"]
             t = conv2d(y_s, P[f"w_a{i}"], k, dil=d if k[0] == 3 else 1, st=stats[1 + i], cpg=ch // gi)

@@ -300,6 +300,24 @@ def conv(x_cl, w2, ksize, stride=1, dil=1, bias=None, residual=None, act=0, spli
     return out
 
 
+def conv_taps(x_cl, w2, taps, gn_stats=None, cpg=0):
+    """Stride-1 convolution over an explicit tap table (several dilated branches in one launch): x_cl (B,X,Y,Z,Cin) S32,
+    taps = [(dx, dy, dz), ...], w2 (Cout, len(taps)*Cin) S32 tap-major -> raw (B,X,Y,Z,Cout) fp32."""
+    _chk(x_cl, "x_cl"), _chk(w2, "w2")
+    B, X, Y, Z, Cin = x_cl.shape
+    Cout = w2.shape[0]
+    assert w2.shape[1] == len(taps) * Cin
+    out = torch.empty((B, X, Y, Z, Cout), dtype=torch.float32, device=x_cl.device)
+    flat = [int(v) for t in taps for v in t]
+    arr = (ctypes.c_int * len(flat))(*flat)
+    if gn_stats is not None:
+        _chk(gn_stats, "gn_stats", torch.float64)
+    check(lib().occ_conv_taps_bf16x3(_ptr(x_cl), _ptr(w2), _ptr(out), B, X, Y, Z, Cin, Cout, len(taps), arr, _ptr(gn_stats),
+                                     cpg, _stream(x_cl)), "occ_conv_taps_bf16x3")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- encoder glue
 def gn_relu_zmean_ln(y, stats, gn_w, gn_b, ln_w, ln_b, B, XY, Z, C, groups):
     rows = B * XY * (Z + 1)

@@ -109,3 +109,37 @@ def test_gemm_rejects_bad_args(cuda):
         ops.gemm(a, w)
     with pytest.raises(RuntimeError):
         ops.gemm(torch.zeros(8, 32), torch.zeros(16, 32))  # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("B,X,Y,ch", [(1, 50, 50, 32), (2, 25, 30, 32), (1, 20, 20, 64)])
+def test_conv_taps_merged_aspp_branches(cuda, B, X, Y, ch):
+    """occ_conv_taps_bf16x3: the four ASPP branches (1x1 + 3x3 dilated 6 / 12 / 18, same input) as one 25-tap launch vs
+    four torch convolutions; GroupNorm statistics of the 4 x groups from the epilogue."""
+    from occformer_b200 import ops
+    g = torch.Generator().manual_seed(X + ch)
+    x = torch.randn(B, ch, X, Y, generator=g)
+    dil = (1, 6, 12, 18)
+    ws = [torch.randn(ch, ch, 1, 1, generator=g) * ch ** -0.5] + [torch.randn(ch, ch, 3, 3, generator=g) * (9 * ch) ** -0.5
+                                                                 for _ in range(3)]
+    ref = torch.cat([F.conv2d(x.double(), w.double(), padding=0 if w.shape[-1] == 1 else d, dilation=d)
+                     for w, d in zip(ws, dil)], 1)
+    taps = [(0, 0, 0)]
+    for d in dil[1:]:
+        taps += [(i * d, j * d, 0) for i in (-1, 0, 1) for j in (-1, 0, 1) if (i, j) != (0, 0)]
+    wm = torch.zeros(4 * ch, len(taps), ch)
+    wm[:ch, 0] = ws[0][:, :, 0, 0]
+    for bi, d in enumerate(dil[1:], start=1):
+        for i in (-1, 0, 1):
+            for j in (-1, 0, 1):
+                t = 0 if (i, j) == (0, 0) else taps.index((i * d, j * d, 0))
+                wm[bi * ch:(bi + 1) * ch, t] = ws[bi][:, :, i + 1, j + 1]
+    groups = 4 * (ch // 2)
+    if groups > 64:
+        groups = 64
+    cpg = 4 * ch // groups
+    stats = torch.zeros(B, groups, 2, dtype=torch.float64, device=cuda)
+    xs = ops.to_split(x.permute(0, 2, 3, 1).contiguous().to(cuda)).view(B, X, Y, 1, ch)
+    out = ops.conv_taps(xs, ops.split_weight(wm.reshape(4 * ch, -1)).to(cuda), taps, gn_stats=stats, cpg=cpg)
+    assert_close(out.view(B, X, Y, 4 * ch).permute(0, 3, 1, 2), ref, TOL, f"merged ASPP branches {X}x{Y} ch={ch}")
+    r = ref.reshape(B, groups, -1)
+    assert_close(stats, torch.stack((r.sum(-1), (r * r).sum(-1)), -1), 1e-4, "merged ASPP gn_stats")
