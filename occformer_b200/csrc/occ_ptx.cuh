@@ -64,11 +64,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Bounded spin: a mis-programmed pipeline traps (-> launch error) instead of hanging the GPU box.
+// Time-bounded wait: a mis-programmed pipeline traps (-> launch error) after ~4 s instead of hanging the GPU box
+// (try_wait may suspend the thread for a while, so the bound is taken from %globaltimer, not from the spin count).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 200000000u) __trap();
+    if ((++spins & 1023u) == 0u) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) __trap();
+    }
   }
 }
 

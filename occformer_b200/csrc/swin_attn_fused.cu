@@ -51,8 +51,9 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
   float* sqb = reinterpret_cast<float*>(smem + SF_OFF_QB);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SF_OFF_BAR);
   uint64_t* a_empty = a_full + 1;
-  uint64_t* d_ready = a_empty + 1;
-  uint64_t* d_free = d_ready + 1;
+  uint64_t* d_ready = a_empty + 1;    // [2]: one per warpgroup -- a consumer that first waits for an ODD phase of a shared
+                                      // barrier cannot tell "phase 1 done" from "nothing done yet" (parity waits)
+  uint64_t* d_free = d_ready + 2;
   uint64_t* qkv_full = d_free + 1;    // [2]
   uint64_t* qkv_empty = qkv_full + 2; // [2]
   uint64_t* s_ready = qkv_empty + 2;  // [2]
@@ -84,7 +85,8 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
   if (warp == 1 && lane == 0) {
     mbar_init(a_full, 256);   // per loader thread: one cp.async arrival + one release arrival
     mbar_init(a_empty, 1);    // tcgen05.commit after M1
-    mbar_init(d_ready, 1);    // tcgen05.commit after M1
+    mbar_init(&d_ready[0], 1);  // tcgen05.commit after M1 of the even / odd units
+    mbar_init(&d_ready[1], 1);
     mbar_init(d_free, 4);     // the four warps of the converting warpgroup
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qkv_full[i], 4);
@@ -167,7 +169,9 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
       constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 2 * HD, 0, 1);
       long long n1 = 0, nq = 0, np = 0;
+      uint32_t idle = 0;  // polls without progress: a mis-programmed pipeline traps instead of hanging the GPU box
       while (np < n_units) {
+        if (++idle > 400000000u) __trap();
         // M1(n1): token tile landed, D free (the conversion of unit n1 - 1 has read it)
         if (n1 < n_units && mbar_test(a_full, (uint32_t)(n1 & 1)) && mbar_test(d_free, (uint32_t)((n1 & 1) ^ 1))) {
           fence_proxy_async_smem();
@@ -179,8 +183,9 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
             mma_bf16x3_ss(tmem_base + SF_TMEM_D, adesc, bdesc, IDESC_M1, kb != 0);
           }
           mma_commit(a_empty);
-          mma_commit(d_ready);
+          mma_commit(&d_ready[n1 & 1]);
           ++n1;
+          idle = 0;
         }
         // QK(nq): Q / K / V tiles of the unit converted; S/P buffer free once PV(nq - 2) has been issued
         if (nq < n1 && nq - np < 2 && mbar_test(&qkv_full[nq & 1], (uint32_t)((nq >> 1) & 1))) {
@@ -192,6 +197,7 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
           mma_bf16x3_ss(tmem_base + SF_TMEM_S + (uint32_t)(nq & 1) * 128, qdesc, kdesc, IDESC_QK, 0u);
           mma_commit(&s_ready[nq & 1]);
           ++nq;
+          idle = 0;
         }
         if (np < nq) {
           const int tb = (int)(np & 1);
@@ -211,6 +217,7 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
             mma_commit(&o_ready[tb]);
             mma_commit(&qkv_empty[tb]);  // Q, K (read by QK, issued earlier) and V of this buffer are free again
             ++np;
+            idle = 0;
           }
         }
       }
@@ -229,7 +236,7 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
       const long long* rows = reinterpret_cast<const long long*>(meta);
       const int* region = reinterpret_cast<const int*>(meta + 1024);
       // ---- conversion: D row (q | k | v of this head) + bias -> S32 rows of the Q / K / V operand tiles
-      mbar_wait(d_ready, (uint32_t)(u & 1));
+      mbar_wait(&d_ready[tb], k & 1);
       mbar_wait(&qkv_empty[tb], (k & 1) ^ 1);
       tc_fence_after();
       uint32_t ra[32], rb[32];

@@ -211,11 +211,15 @@ class DualpathTransformerBlock(nn.Module):
         tok, tokn = ops.gn_relu_zmean_ln(y_raw.view(nvox, C), stats[0], ic[1].weight, ic[1].bias, sw.norm1.weight,
                                          sw.norm1.bias, B, XY, Z, C, G)
         msa = sw.attn.w_msa
-        # (A8) QKV projection of every token (pad tokens are synthesised from the bias inside the attention kernel)
-        qkv = ops.gemm(tokn, P["w_qkv"], bias=P["b_qkv"], split_out=True)
-        # (A7/A8) shifted-window attention core, gathers/scatters windows in place
-        att = ops.window_attention(qkv, P["b_qkv_s"], P["bias_pad"], B, X, Y, Z, C, self.num_heads, self.shift,
-                                   head_major=True)
+        if C == 128:
+            # (A7/A8) QKV projection + shifted-window attention in one kernel: the qkv tensor never exists in HBM
+            att = ops.swin_qkv_attention(tokn, P["w_qkv"], P["b_qkv"], P["bias_pad"], B, X, Y, Z, C, self.num_heads, self.shift)
+        else:
+            # (A8) QKV projection of every token (pad tokens are synthesised from the bias inside the attention kernel)
+            qkv = ops.gemm(tokn, P["w_qkv"], bias=P["b_qkv"], split_out=True)
+            # (A7/A8) shifted-window attention core, gathers/scatters windows in place
+            att = ops.window_attention(qkv, P["b_qkv_s"], P["bias_pad"], B, X, Y, Z, C, self.num_heads, self.shift,
+                                       head_major=True)
         # proj + residual, LayerNorm2, FFN (GELU) + residual  (A6)
         ffn = sw.ffn.layers
         if C == 128 and P["w_f1"].shape == (C, C):

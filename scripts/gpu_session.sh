@@ -9,13 +9,14 @@ for s in "$@"; do
     gemmall) timeout 400 python -m pytest tests/test_gpu_gemm.py -q -m gpu > gpurun_out/t_gemm.log 2>&1; echo "gemm rc=$?" ;;
     pool)    timeout 300 python -m pytest tests/test_gpu_voxel_pool.py -q -m gpu -s > gpurun_out/t_pool.log 2>&1; echo "pool rc=$?" ;;
     encoder) timeout 600 python -m pytest tests/test_gpu_encoder.py -q -m gpu > gpurun_out/t_encoder.log 2>&1; echo "encoder rc=$?" ;;
-    wattn)   timeout 600 python -m pytest tests/test_gpu_window_attn.py -q -m gpu > gpurun_out/t_wattn.log 2>&1; echo "wattn rc=$?" ;;
+    wattn)   timeout 240 python -m pytest tests/test_gpu_window_attn.py -q -m gpu > gpurun_out/t_wattn.log 2>&1; echo "wattn rc=$?" ;;
     head)    timeout 600 python -m pytest tests/test_gpu_head.py -q -m gpu > gpurun_out/t_head.log 2>&1; echo "head rc=$?" ;;
     full)    timeout 1200 python -m pytest tests/test_gpu_fullsize.py -q -m gpu -s > gpurun_out/t_full.log 2>&1; echo "full rc=$?" ;;
     neck)    timeout 600 python -m pytest tests/test_gpu_neck.py tests/test_gpu_eval.py -q -m gpu > gpurun_out/t_neck.log 2>&1; echo "neck rc=$?" ;;
     all)     timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/t_all.log 2>&1; echo "all rc=$?" ;;
     micro)   timeout 600 python scripts/microbench.py > gpurun_out/micro.log 2>&1; echo "micro rc=$?" ;;
     bench)   timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -n 3 gpurun_out/bench.log ;;
+    benchq)  timeout 600 python bench.py --steps 5 --no-cpu-baseline > gpurun_out/benchq.log 2> gpurun_out/benchq.err; echo "benchq rc=$?"; tail -c 3000 gpurun_out/benchq.log; tail -n 5 gpurun_out/benchq.err ;;
     benchref) timeout 900 python bench.py --impl reference --steps 2 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "benchref rc=$?"; tail -n 2 gpurun_out/bench_ref.log ;;
     ktimes)  timeout 600 python scripts/kernel_times.py gpurun_out/kernel_times.md > gpurun_out/kernel_times.log 2>&1; echo "ktimes rc=$?"; head -n 40 gpurun_out/kernel_times.md ;;
     smoke)   timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 3 gpurun_out/smoke.log ;;

@@ -134,7 +134,9 @@ def test_full_size_pipeline_vs_oracle(cuda, name):
     # voxel pooling: set of non-empty voxels identical, sums to fp32 summation-order accuracy
     g_cuda = voxel.float().cpu()
     assert torch.equal(g_cuda.abs().sum(1) != 0, ref["grid"].abs().sum(1) != 0), "non-empty voxel sets differ"
-    assert_close(g_cuda, ref["grid"], 1e-5, f"{tag} pooled voxel grid {tuple(ref['grid'].shape)}")
+    # (1e-4: the summation order inside a voxel is unspecified -- the reference's argsort is unstable -- and depth_prob
+    # itself carries the ~1e-6 of an fp32 exp; a few near-cancelling sums out of 1e8 exceed 1e-5 * rms)
+    assert_close(g_cuda, ref["grid"], 1e-4, f"{tag} pooled voxel grid {tuple(ref['grid'].shape)}")
     for i, (o, r) in enumerate(zip(enc_outs, ref["enc"])):
         assert_close(o, r, what=f"{tag} encoder out[{i}] {tuple(r.shape)}")
     if connected:

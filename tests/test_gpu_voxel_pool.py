@@ -255,7 +255,7 @@ def test_forward_fused_front_end_vs_oracle(cuda, wl, B):
     near = ((frac - frac.round()).abs() < 1e-4).any(-1)
     assert bool((~flips | near).all()), "index flips away from cell boundaries"
     if int(flips.sum()) == 0:
-        assert_close(voxel, ref, 1e-5, f"{wl} forward pooled grid")
+        assert_close(voxel, ref, 1e-4, f"{wl} forward pooled grid")  # fp32 exp + summation-order noise on near-cancelling sums
         assert torch.equal(ops.to_split(voxel.permute(0, 2, 3, 4, 1).contiguous()).view(torch.int32),
                            voxel._occ_s32.view(torch.int32))
     print(f"{wl}: forward front-end flips {int(flips.sum())} of {flips.numel()}")
