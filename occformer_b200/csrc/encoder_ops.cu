@@ -199,32 +199,47 @@ layernorm_generic_kernel(const float* __restrict__ in, const float* __restrict__
 // GroupNorm apply for the small 2-D maps of BottleNeckASPP (aspp.py:49-172) and the strided skip path:
 //   o = act(gn(in[row, c])) (+ residual[row, c]);  out[row, c] = o (fp32, optional) and / or
 //   out_split[row, out_off + c] = o in the S32 split format (row pitch ldo; operand of the next conv);  rows = B * rows_per_batch.
+// grid (row chunks, B): a CTA never straddles two samples, so the per-channel scale / shift of its sample
+// (rstd * gamma, beta - mean * rstd * gamma; fp64 division + sqrt once per (CTA, group)) sit in shared memory and an
+// element costs one FMA.
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ in, const double* __restrict__ stats, const float* __restrict__ w,
                 const float* __restrict__ b, const float* __restrict__ residual, float* __restrict__ out,
-                float* __restrict__ out_split, long long rows, int rows_per_batch, int C, int groups, int ldo,
-                int out_off, int relu) {
-  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int C4 = C >> 2;
-  if (i4 >= rows * C4) return;
-  const long long row = i4 / C4;
-  const int c0 = (int)(i4 % C4) * 4;
-  const int bidx = (int)(row / rows_per_batch);
+                float* __restrict__ out_split, int rows_per_batch, int C, int groups, int ldo, int out_off, int relu,
+                int rows_per_cta) {
+  extern __shared__ float gsm[];  // scale[C], shift[C]
+  float* sc = gsm;
+  float* sh = gsm + C;
+  const int bidx = blockIdx.y;
   const int cpg = C / groups;
   const double count = (double)rows_per_batch * cpg;
-  const float4 t = *reinterpret_cast<const float4*>(in + row * C + c0);
-  float v[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
-    gn_mean_rstd(stats, bidx, groups, (c0 + j) / cpg, count, &mean, &rstd);
-    float o = (v[j] - mean) * rstd * w[c0 + j] + b[c0 + j];
-    if (relu) o = fmaxf(o, 0.f);
-    if (residual) o += residual[row * C + c0 + j];
-    v[j] = o;
+    gn_mean_rstd(stats, bidx, groups, c / cpg, count, &mean, &rstd);
+    const float a = rstd * w[c];
+    sc[c] = a;
+    sh[c] = b[c] - mean * a;
   }
-  if (out) *reinterpret_cast<float4*>(out + row * C + c0) = make_float4(v[0], v[1], v[2], v[3]);
-  if (out_split) store_split4(out_split + row * ldo, out_off + c0, make_float4(v[0], v[1], v[2], v[3]));
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, rows_per_batch);
+  const long long base = (long long)bidx * rows_per_batch;
+  for (long long i4 = (long long)r0 * C4 + threadIdx.x; i4 < (long long)r1 * C4; i4 += blockDim.x) {
+    const long long row = base + i4 / C4;
+    const int c0 = (int)(i4 % C4) * 4;
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(in + row * C + c0));
+    const float4 a = *reinterpret_cast<const float4*>(sc + c0), d = *reinterpret_cast<const float4*>(sh + c0);
+    // (v - mean) * rstd * gamma + beta, evaluated as v * (rstd*gamma) + (beta - mean*rstd*gamma)
+    float4 o = make_float4(fmaf(t.x, a.x, d.x), fmaf(t.y, a.y, d.y), fmaf(t.z, a.z, d.z), fmaf(t.w, a.w, d.w));
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (residual) {
+      const float4 r = *reinterpret_cast<const float4*>(residual + row * C + c0);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    if (out) *reinterpret_cast<float4*>(out + row * C + c0) = o;
+    if (out_split) store_split4(out_split + row * ldo, out_off + c0, o);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -458,9 +473,14 @@ extern "C" int occ_gn_apply(const float* in, const double* stats, const float* w
   OCC_REQUIRE(in && stats && w && b && (out || out_split) && rows > 0 && rows_per_batch > 0 && rows % rows_per_batch == 0);
   OCC_REQUIRE(C % 4 == 0 && groups > 0 && C % groups == 0);
   if (out_split) OCC_REQUIRE(C % 32 == 0 && ldo % 32 == 0 && out_off % 32 == 0 && out_off + C <= ldo);
-  const long long n4 = rows * (C / 4);
-  gn_apply_kernel<<<(int)((n4 + 255) / 256), 256, 0, stream>>>(in, stats, w, b, residual, out, out_split, rows,
-                                                               rows_per_batch, C, groups, ldo, out_off, relu);
+  OCC_REQUIRE(C <= 4096 && rows / rows_per_batch <= 65535);
+  const int B = (int)(rows / rows_per_batch);
+  // rows per CTA: ~2048 float4 per CTA pass, at least 4 waves of CTAs on big tensors
+  int rpc = (2048 * 4 + C / 4 - 1) / (C / 4);
+  if (rpc < 1) rpc = 1;
+  dim3 grid((rows_per_batch + rpc - 1) / rpc, B);
+  gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(in, stats, w, b, residual, out, out_split, rows_per_batch, C,
+                                                                groups, ldo, out_off, relu, rpc);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

@@ -17,7 +17,7 @@
 namespace occ {
 
 constexpr int NK_MAX_LEVELS = 4;
-constexpr int NK_PASSES = 8;  // token rows per CTA of the deformable gather = NK_PASSES * (256 / (E/4))
+constexpr int NK_PX = 4, NK_PY = 4;  // query patch of the deformable gather: NK_PX x NK_PY x Z_l tokens of one level
 
 struct NeckLevels {
   int L, B;
@@ -25,6 +25,8 @@ struct NeckLevels {
   int start[NK_MAX_LEVELS];  // first token of the level inside one sample's Nq tokens (levels coarse -> fine)
   int n[NK_MAX_LEVELS];      // X*Y*Z
   float stride[NK_MAX_LEVELS];
+  int pstart[NK_MAX_LEVELS]; // first query patch of the level (deformable gather grid), all samples
+  int npatches;
   long long rows;            // B * Nq
 };
 
@@ -113,30 +115,44 @@ token_prep_kernel(const float* __restrict__ in, const float* __restrict__ ln_w, 
 //   out   (rows, E)  S32       sum_{l,p} softmax(logits)[l,p] * trilinear(value level l)(loc), zeros outside,
 //                              align_corners=False;  loc = ref + offset / (Z_l, Y_l, X_l),  ref = voxel centre of the
 //                              query in its own level, normalised to [0,1] (the same point for every value level)
-// One CTA = NQ queries x (E/4) threads per pass, NK_PASSES passes over consecutive token rows (z fastest, then y: a compact
-// patch of the volume, so that the corner rows fetched for one query are L1 hits for its neighbours); thread = (query,
-// float4 of channels) -> head = 4*t / hd.  The 8 corner rows of a sampling point are 8 independent 16-byte loads per
-// thread (96-byte runs per head: whole 32-byte sectors); the value tensor (70 MB at 91 250 tokens) is L2 resident.
+// One CTA = (patch of NK_PX x NK_PY x Z_l queries of one level, one head): QP queries x (hd/4) threads per pass.  A CTA's
+// value working set is then the patch plus the halo its sampling offsets reach, in ONE head's 96-byte slices (~70 KB at
+// a 2-voxel halo): it lives in L1 while the 8 corner rows of a sampling point (8 independent 16-byte loads per thread)
+// are shared between neighbouring queries and points -- L2 / HBM only see each slice about once per patch instead of the
+// ~30 times it is sampled.  (Queries ordered row by row spread a patch's neighbours over many SMs: 7.5 TB/s of L2 traffic.)
 template <int L, int P>
 __global__ void __launch_bounds__(256)
 ms_deform_attn_kernel(const float* __restrict__ value, const float* __restrict__ ow, float* __restrict__ out,
-                      const NeckLevels g, int E, int H, int NQ) {
-  const int T = E >> 2;  // threads per query
-  const int ql = threadIdx.x / T, t = threadIdx.x - ql * T;
-  if (ql >= NQ) return;
+                      const NeckLevels g, int E, int H, int QP) {
   const int hd = E / H;
+  const int T1 = hd >> 2;  // threads per (query, head)
+  const int ql = threadIdx.x / T1, tt = threadIdx.x - ql * T1;
+  if (ql >= QP) return;
+  const int h = blockIdx.y;
+  const int T = E >> 2;            // float4 per value row
+  const int t = h * T1 + tt;       // this thread's float4 inside the row
+  // patch -> (level, sample, px, py)
+  int lq = 0;
+#pragma unroll
+  for (int l = 1; l < NK_MAX_LEVELS; ++l)
+    if (l < g.L && (int)blockIdx.x >= g.pstart[l]) lq = l;
+  const int Zq = g.Z[lq], Yq = g.Y[lq], Xq = g.X[lq];
+  int pid = blockIdx.x - g.pstart[lq];
+  const int npy = (Yq + NK_PY - 1) / NK_PY, npx = (Xq + NK_PX - 1) / NK_PX;
+  const int py = pid % npy; pid /= npy;
+  const int px = pid % npx;
+  const int b = pid / npx;
+  const int nq = NK_PX * NK_PY * Zq;
 #pragma unroll 1
-  for (int pass = 0; pass < NK_PASSES; ++pass) {
-  const long long row = ((long long)blockIdx.x * NK_PASSES + pass) * NQ + ql;
-  if (row >= g.rows) return;
-  const int h = (4 * t) / hd;
-  int lq, b, local;
-  nk_locate(g, row, lq, b, local);
+  for (int q = ql; q < nq; q += QP) {
+  const int z = q % Zq, iy = (q / Zq) % NK_PY, ix = q / (Zq * NK_PY);
+  const int x = px * NK_PX + ix, y = py * NK_PY + iy;
+  if (x >= Xq || y >= Yq) continue;
+  const int local = (x * Yq + y) * Zq + z;
+  const long long row = (long long)g.B * g.start[lq] + (long long)b * g.n[lq] + local;
   // reference point (normalised voxel centre), computed as the reference does: ((i + 0.5) * stride) / (dim * stride)
   float rz, ry, rx;
   {
-    const int Zq = g.Z[lq], Yq = g.Y[lq], Xq = g.X[lq];
-    const int z = local % Zq, y = (local / Zq) % Yq, x = local / (Zq * Yq);
     const float st = g.stride[lq];
     rz = ((float)z + 0.5f) * st / ((float)Zq * st);
     ry = ((float)y + 0.5f) * st / ((float)Yq * st);
@@ -196,39 +212,41 @@ ms_deform_attn_kernel(const float* __restrict__ value, const float* __restrict__
     }
   }
   store_split4(out + row * E, 4 * t, acc);
-  }  // pass
+  }  // queries of the patch
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // FPN step (multiscale_deformattn_3d.py:228-240): y = GroupNorm(lateral conv raw output) + trilinear upsample
 // (align_corners=False) of the coarser level; written in S32 (operand of the 3x3x3 output conv).
 //   cur (B, X, Y, Z, C) raw lateral conv output + its GN statistics;  coarse (B, Xc, Yc, Zc, C) fp32.
+// grid (voxel chunks, B); per-channel GroupNorm scale / shift of the sample in shared memory.
 __global__ void __launch_bounds__(256)
 gn_upsample_add_kernel(const float* __restrict__ cur, const double* __restrict__ stats, const float* __restrict__ gw,
                        const float* __restrict__ gb, int groups, const float* __restrict__ coarse, float* __restrict__ out_s,
-                       int B, int X, int Y, int Z, int Xc, int Yc, int Zc, int C) {
-  const int C4 = C >> 2;
-  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                       int X, int Y, int Z, int Xc, int Yc, int Zc, int C, int vox_per_cta) {
+  extern __shared__ float gsm[];  // scale[C], shift[C]
+  float* sc = gsm;
+  float* sh = gsm + C;
+  const int b = blockIdx.y;
   const long long V = (long long)X * Y * Z;
-  if (i4 >= (long long)B * V * C4) return;
-  const long long row = i4 / C4;
-  const int c0 = (int)(i4 - row * C4) * 4;
-  const int b = (int)(row / V);
-  const long long r = row - (long long)b * V;
-  const int z = (int)(r % Z), y = (int)((r / Z) % Y), x = (int)(r / ((long long)Z * Y));
-  const int cpg = C / groups;
-  const double count = (double)V * cpg;
-  const float4 raw = __ldcs(reinterpret_cast<const float4*>(cur + row * C + c0));
-  float v[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int gi = (c0 + j) / cpg;
-    const double s = stats[((size_t)b * groups + gi) * 2], q = stats[((size_t)b * groups + gi) * 2 + 1];
-    const double mean = s / count;
-    double var = q / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    v[j] = (v[j] - (float)mean) * (float)(1.0 / sqrt(var + 1e-5)) * __ldg(gw + c0 + j) + __ldg(gb + c0 + j);
+  {
+    const int cpg = C / groups;
+    const double count = (double)V * cpg;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int gi = c / cpg;
+      const double s = stats[((size_t)b * groups + gi) * 2], q = stats[((size_t)b * groups + gi) * 2 + 1];
+      const double mean = s / count;
+      double var = q / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float a = (float)(1.0 / sqrt(var + 1e-5)) * gw[c];
+      sc[c] = a;
+      sh[c] = gb[c] - (float)mean * a;
+    }
   }
+  __syncthreads();
+  const int C4 = C >> 2;
+  const long long v0 = (long long)blockIdx.x * vox_per_cta;
+  const long long v1 = v0 + vox_per_cta < V ? v0 + vox_per_cta : V;
   // F.interpolate(trilinear, align_corners=False): src = (dst + 0.5) * (in / out) - 0.5, clamped at 0; the upper
   // neighbour index is clamped to the last element (its weight is then irrelevant: both neighbours coincide)
   auto axis = [](int d, int n_out, int n_in, int& i0, int& i1, float& t) {
@@ -239,23 +257,35 @@ gn_upsample_add_kernel(const float* __restrict__ cur, const double* __restrict__
     i1 = i0 + 1 < n_in ? i0 + 1 : n_in - 1;
     t = s - (float)i0;
   };
-  int x0, x1, y0, y1, z0, z1;
-  float tx, ty, tz;
-  axis(x, X, Xc, x0, x1, tx);
-  axis(y, Y, Yc, y0, y1, ty);
-  axis(z, Z, Zc, z0, z1, tz);
-  const float4* cb = reinterpret_cast<const float4*>(coarse + (size_t)b * Xc * Yc * Zc * C + c0);
-  auto ld = [&](int xx, int yy, int zz) { return __ldg(cb + (((size_t)xx * Yc + yy) * Zc + zz) * C4); };
-  float up[4] = {0.f, 0.f, 0.f, 0.f};
+  const float4* cb = reinterpret_cast<const float4*>(coarse + (size_t)b * Xc * Yc * Zc * C);
+  for (long long i4 = v0 * C4 + threadIdx.x; i4 < v1 * C4; i4 += blockDim.x) {
+    const long long r = i4 / C4;
+    const int c4 = (int)(i4 - r * C4);
+    const int z = (int)(r % Z), y = (int)((r / Z) % Y), x = (int)(r / ((long long)Z * Y));
+    const long long row = (long long)b * V + r;
+    const float4 raw = __ldcs(reinterpret_cast<const float4*>(cur + row * C) + c4);
+    const float4 a = *reinterpret_cast<const float4*>(sc + 4 * c4), d = *reinterpret_cast<const float4*>(sh + 4 * c4);
+    float4 o = make_float4(fmaf(raw.x, a.x, d.x), fmaf(raw.y, a.y, d.y), fmaf(raw.z, a.z, d.z), fmaf(raw.w, a.w, d.w));
+    int x0, x1, y0, y1, z0, z1;
+    float tx, ty, tz;
+    axis(x, X, Xc, x0, x1, tx);
+    axis(y, Y, Yc, y0, y1, ty);
+    axis(z, Z, Zc, z0, z1, tz);
+    float4 cv[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int dz = k & 1, dy = (k >> 1) & 1, dx = k >> 2;
-    const float wgt = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
-    const float4 cv = ld(dx ? x1 : x0, dy ? y1 : y0, dz ? z1 : z0);
-    up[0] = fmaf(wgt, cv.x, up[0]); up[1] = fmaf(wgt, cv.y, up[1]);
-    up[2] = fmaf(wgt, cv.z, up[2]); up[3] = fmaf(wgt, cv.w, up[3]);
+    for (int k = 0; k < 8; ++k) {
+      const int dz = k & 1, dy = (k >> 1) & 1, dx = k >> 2;
+      cv[k] = __ldg(cb + (((size_t)(dx ? x1 : x0) * Yc + (dy ? y1 : y0)) * Zc + (dz ? z1 : z0)) * C4 + c4);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int dz = k & 1, dy = (k >> 1) & 1, dx = k >> 2;
+      const float wgt = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
+      o.x = fmaf(wgt, cv[k].x, o.x); o.y = fmaf(wgt, cv[k].y, o.y);
+      o.z = fmaf(wgt, cv[k].z, o.z); o.w = fmaf(wgt, cv[k].w, o.w);
+    }
+    store_split4(out_s + row * C, 4 * c4, o);
   }
-  store_split4(out_s + row * C, c0, make_float4(v[0] + up[0], v[1] + up[1], v[2] + up[2], v[3] + up[3]));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -273,7 +303,15 @@ gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int row
   const float* base = x + ((size_t)b * rows_per_batch + r0) * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f, q = 0.f;
-    for (int r = 0; r < nr; ++r) {
+    int r = 0;
+    for (; r + 8 <= nr; r += 8) {  // eight independent row loads in flight
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(base + (size_t)(r + k) * C + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s += v[k]; q = fmaf(v[k], v[k], q); }
+    }
+    for (; r < nr; ++r) {
       const float v = __ldg(base + (size_t)r * C + c);
       s += v;
       q = fmaf(v, v, q);
@@ -302,6 +340,12 @@ static int fill_levels(NeckLevels& g, int L, int B, const int* grids, const floa
     }
   }
   g.rows = (long long)B * start;
+  int ps = 0;
+  for (int l = 0; l < NK_MAX_LEVELS; ++l) {
+    g.pstart[l] = l < L ? ps : 0x3fffffff;
+    if (l < L) ps += B * ((g.X[l] + NK_PX - 1) / NK_PX) * ((g.Y[l] + NK_PY - 1) / NK_PY);
+  }
+  g.npatches = ps;
   return OCC_OK;
 }
 
@@ -338,13 +382,14 @@ extern "C" int occ_ms_deform_attn(const float* value, const float* ow, float* ou
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(value) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   NeckLevels g;
   OCC_REQUIRE(fill_levels(g, L, B, grids, strides) == OCC_OK);
-  const int T = E / 4;
-  const int NQ = 256 / T >= 1 ? 256 / T : 1;
-  const unsigned blocks = (unsigned)((g.rows + (long long)NQ * NK_PASSES - 1) / ((long long)NQ * NK_PASSES));
-  if (L == 3 && P == 4) ms_deform_attn_kernel<3, 4><<<blocks, NQ * T, 0, stream>>>(value, ow, out, g, E, H, NQ);
-  else if (L == 1 && P == 4) ms_deform_attn_kernel<1, 4><<<blocks, NQ * T, 0, stream>>>(value, ow, out, g, E, H, NQ);
-  else if (L == 2 && P == 4) ms_deform_attn_kernel<2, 4><<<blocks, NQ * T, 0, stream>>>(value, ow, out, g, E, H, NQ);
-  else if (L == 4 && P == 4) ms_deform_attn_kernel<4, 4><<<blocks, NQ * T, 0, stream>>>(value, ow, out, g, E, H, NQ);
+  const int T1 = E / H / 4;
+  const int QP = 256 / T1;
+  OCC_REQUIRE(H <= 65535 && QP >= 1);
+  dim3 grid((unsigned)g.npatches, (unsigned)H);
+  if (L == 3 && P == 4) ms_deform_attn_kernel<3, 4><<<grid, QP * T1, 0, stream>>>(value, ow, out, g, E, H, QP);
+  else if (L == 1 && P == 4) ms_deform_attn_kernel<1, 4><<<grid, QP * T1, 0, stream>>>(value, ow, out, g, E, H, QP);
+  else if (L == 2 && P == 4) ms_deform_attn_kernel<2, 4><<<grid, QP * T1, 0, stream>>>(value, ow, out, g, E, H, QP);
+  else if (L == 4 && P == 4) ms_deform_attn_kernel<4, 4><<<grid, QP * T1, 0, stream>>>(value, ow, out, g, E, H, QP);
   else return OCC_EUNSUPPORTED;
   OCC_LAUNCH_CHECK();
   return OCC_OK;
@@ -355,9 +400,12 @@ extern "C" int occ_gn_upsample_add(const float* cur, const double* stats, const 
                                    int C, cudaStream_t stream) {
   OCC_REQUIRE(cur && stats && gw && gb && coarse && out_s);
   OCC_REQUIRE(B > 0 && X > 0 && Y > 0 && Z > 0 && Xc > 0 && Yc > 0 && Zc > 0 && C % 32 == 0 && groups > 0 && C % groups == 0);
-  const long long n4 = (long long)B * X * Y * Z * (C / 4);
-  gn_upsample_add_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(cur, stats, gw, gb, groups, coarse, out_s, B, X,
-                                                                          Y, Z, Xc, Yc, Zc, C);
+  OCC_REQUIRE(B <= 65535 && C <= 4096);
+  const long long V = (long long)X * Y * Z;
+  int vpc = (2048 * 4 + C / 4 - 1) / (C / 4);
+  dim3 grid((unsigned)((V + vpc - 1) / vpc), B);
+  gn_upsample_add_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(cur, stats, gw, gb, groups, coarse, out_s, X, Y, Z, Xc,
+                                                                       Yc, Zc, C, vpc);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

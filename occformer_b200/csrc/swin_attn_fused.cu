@@ -12,10 +12,13 @@
 //   MMA      (warp 0)       M1: D[128 x 96] = A W_h^T            (4 k-blocks x 6 tcgen05.mma 128x96x16: three bf16 passes)
 //                           QK: S = Q K^T, PV: O' = [P_hi; P_lo][V_hi | V_lo]   (as in window_attn.cu)
 //   two warpgroups (warps 4-7 / 8-11, even / odd units):
-//       convert : tcgen05.ld D -> + bias -> split -> Q / K / V operand tiles in shared memory (double buffered)
+//       convert : tcgen05.ld D -> + bias -> split -> Q / K operand tiles (single: free again as soon as QK^T of the previous
+//                 unit has been read) and V operand tile (double buffered: read by PV one softmax later)
 //       softmax : S row -> scale, relative-position bias, shift mask, exp2 -> P (TMEM, split)      (unchanged)
 //       epilogue: O -> normalise -> S32 scatter to the token-ordered output (A operand of the projection GEMM)
-// The conversion of unit u+1 (other warpgroup) overlaps the softmax of unit u; M1(u+1) overlaps both.
+// The token tiles arrive through a ring of six 16 KB k-block slots (1.5 units of gathers in flight per CTA: the gather
+// latency, not the bandwidth, is what a single-buffered tile would expose).  The conversion of unit u+1 (other
+// warpgroup) overlaps the softmax of unit u; M1(u+1) overlaps both.
 // HBM: tokens in (rows*C*4) + attention out (rows*C*4); the 4 head-CTAs of a group walk the same window pairs at the
 // same time, so three of the four token reads are L2 hits.
 #include "window_geom.cuh"
@@ -25,17 +28,18 @@ namespace occ {
 constexpr int SF_C = 128;
 constexpr int SF_KB = SF_C / 32;                      // k-blocks of the projection
 constexpr int SF_W_BYTES = SF_KB * 96 * 128;          // 49152: W_h as 4 K-major SWIZZLE_128B tiles of 96 rows
-constexpr int SF_A_BYTES = SF_KB * 128 * 128;         // 65536: token tile, 4 k-blocks of 128 rows
-constexpr int SF_QKV_BYTES = 3 * WA_TILE;             // 49152: Q, K, V operand tiles of one unit
-constexpr int SF_META_BYTES = 1792;                   // rows (1024) + region (512) + same masks (144), padded
-constexpr int SF_META_SLOTS = 4;
-constexpr int SF_OFF_A = SF_W_BYTES;
-constexpr int SF_OFF_QKV = SF_OFF_A + SF_A_BYTES;                       // 114688
-constexpr int SF_OFF_BIAS = SF_OFF_QKV + 2 * SF_QKV_BYTES;              // 212992: relative-position bias (49, 52) * log2 e
+constexpr int SF_SLOT = 128 * 128;                    // 16384: one k-block of the token tile (128 rows x 128 B)
+constexpr int SF_NSLOT = 6;                           // ring of k-block slots = 1.5 token tiles
+constexpr int SF_META_BYTES = 832;                    // rows int32 (512) + region bytes (128) + same masks (144), padded
+constexpr int SF_META_SLOTS = 8;                      // units u-4 .. u+1 can be live at once (loader ahead, epilogue behind)
+constexpr int SF_OFF_A = SF_W_BYTES;                                    // 49152
+constexpr int SF_OFF_Q = SF_OFF_A + SF_NSLOT * SF_SLOT;                 // 147456: Q tile, then K tile (single buffered)
+constexpr int SF_OFF_V = SF_OFF_Q + 2 * WA_TILE;                        // 180224: V tiles (double buffered)
+constexpr int SF_OFF_BIAS = SF_OFF_V + 2 * WA_TILE;                     // 212992: relative-position bias (49, 52) * log2 e
 constexpr int SF_OFF_QB = SF_OFF_BIAS + WA_BIAS_BYTES;                  // 223232: this head's 96 qkv bias values
 constexpr int SF_OFF_META = SF_OFF_QB + 384;                            // 223616
-constexpr int SF_OFF_BAR = SF_OFF_META + SF_META_SLOTS * SF_META_BYTES; // 230784
-constexpr int SF_SMEM = SF_OFF_BAR + 256 + 1024;                        // 232064 <= 232448 (227 KB)
+constexpr int SF_OFF_BAR = SF_OFF_META + SF_META_SLOTS * SF_META_BYTES; // 230272
+constexpr int SF_SMEM = SF_OFF_BAR + 384 + 1024;                        // 231680 <= 232448 (227 KB)
 constexpr uint32_t SF_TMEM_D = 0, SF_TMEM_S = 128, SF_TMEM_O = 384;     // D: 96 cols, S/P: 2 x 128, O: 2 x 64
 
 __global__ void __launch_bounds__(WA_THREADS, 1)
@@ -49,17 +53,18 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
   uint8_t* sa = smem + SF_OFF_A;
   float* sb = reinterpret_cast<float*>(smem + SF_OFF_BIAS);
   float* sqb = reinterpret_cast<float*>(smem + SF_OFF_QB);
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SF_OFF_BAR);
-  uint64_t* a_empty = a_full + 1;
-  uint64_t* d_ready = a_empty + 1;    // [2]: one per warpgroup -- a consumer that first waits for an ODD phase of a shared
-                                      // barrier cannot tell "phase 1 done" from "nothing done yet" (parity waits)
-  uint64_t* d_free = d_ready + 2;
-  uint64_t* qkv_full = d_free + 1;    // [2]
-  uint64_t* qkv_empty = qkv_full + 2; // [2]
-  uint64_t* s_ready = qkv_empty + 2;  // [2]
-  uint64_t* p_ready = s_ready + 2;    // [2]
-  uint64_t* o_ready = p_ready + 2;    // [2]
-  uint64_t* o_free = o_ready + 2;     // [2]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SF_OFF_BAR);  // [SF_NSLOT] k-block slot filled
+  uint64_t* a_empty = a_full + SF_NSLOT;                              // [SF_NSLOT] k-block slot consumed by M1
+  uint64_t* d_ready = a_empty + SF_NSLOT;  // [2] (one per warpgroup: a consumer that first waits for an ODD phase of a
+                                           // shared barrier cannot tell "phase 1 done" from "nothing done yet")
+  uint64_t* d_free = d_ready + 2;          // D has been read by the conversion
+  uint64_t* qkv_full = d_free + 1;         // [2] Q, K, V[tb] of the unit are in shared memory
+  uint64_t* qk_free = qkv_full + 2;        // [2] QK^T of the even / odd units has been read out of the Q / K tiles
+  uint64_t* v_empty = qk_free + 2;         // [2] PV has been read out of V[tb]
+  uint64_t* s_ready = v_empty + 2;         // [2]
+  uint64_t* p_ready = s_ready + 2;         // [2]
+  uint64_t* o_ready = p_ready + 2;         // [2]
+  uint64_t* o_free = o_ready + 2;          // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,14 +88,17 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
     sb[i] = c < WT ? bias_pad[(size_t)h * WA_BIAS_FLOATS + r * WT + c] * 1.4426950408889634f : 0.f;
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(a_full, 256);   // per loader thread: one cp.async arrival + one release arrival
-    mbar_init(a_empty, 1);    // tcgen05.commit after M1
-    mbar_init(&d_ready[0], 1);  // tcgen05.commit after M1 of the even / odd units
+    for (int i = 0; i < SF_NSLOT; ++i) {
+      mbar_init(&a_full[i], 256);  // per loader thread: one cp.async arrival + one release arrival
+      mbar_init(&a_empty[i], 1);   // tcgen05.commit after the k-block's MMAs
+    }
+    mbar_init(&d_ready[0], 1);     // tcgen05.commit after M1 of the even / odd units
     mbar_init(&d_ready[1], 1);
-    mbar_init(d_free, 4);     // the four warps of the converting warpgroup
+    mbar_init(d_free, 4);          // the four warps of the converting warpgroup
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qkv_full[i], 4);
-      mbar_init(&qkv_empty[i], 1);
+      mbar_init(&qk_free[i], 1);
+      mbar_init(&v_empty[i], 1);
       mbar_init(&s_ready[i], 1);
       mbar_init(&p_ready[i], 4);
       mbar_init(&o_ready[i], 1);
@@ -108,58 +116,55 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
   if (warp >= 12) {
     // ===================================================================== loaders
     const int l = threadIdx.x - 12 * 32;  // 0..127
+    long long it = 0;                      // running k-block counter -> ring slot / phase
     for (long long u = 0; u < n_units; ++u) {
       const long long pair = pair0 + u * pair_stride;
       uint8_t* meta = smem + SF_OFF_META + (size_t)(u % SF_META_SLOTS) * SF_META_BYTES;
-      long long* rows = reinterpret_cast<long long*>(meta);
-      int* region = reinterpret_cast<int*>(meta + 1024);
-      mbar_wait(a_empty, (uint32_t)((u & 1) ^ 1));
+      int* rows = reinterpret_cast<int*>(meta);
+      uint8_t* region = meta + 512;
+      int my_reg = 0;
       {
         const long long win = 2 * pair + (l >> 6);
         const int t = l & 63;
         long long r = -2;  // -2: MMA padding row, -1: window pad token (zero token: q/k/v = bias)
-        int reg = 0;
         if (t < WT && win < g.nwin) {
           long long w = win;
           const int wy = (int)(w % g.nWy); w /= g.nWy;
           const int wx = (int)(w % g.nWx); w /= g.nWx;
-          r = window_token_row(g, (int)w, wx, wy, t, &reg);
+          r = window_token_row(g, (int)w, wx, wy, t, &my_reg);
         }
-        rows[l] = r;
-        region[l] = reg;
+        rows[l] = (int)r;
+        region[l] = (uint8_t)my_reg;
       }
       {
         const int t = l & 63, wl = l >> 5;
         const bool tok = t < WT;
-        uint32_t* same32 = reinterpret_cast<uint32_t*>(meta + 1536);
+        uint32_t* same32 = reinterpret_cast<uint32_t*>(meta + 640);
 #pragma unroll
         for (int r = 0; r < 9; ++r) {
-          const uint32_t bal = __ballot_sync(0xffffffffu, tok && region[l] == r);
+          const uint32_t bal = __ballot_sync(0xffffffffu, tok && my_reg == r);
           if (lane == 0) same32[((wl >> 1) * 9 + r) * 2 + (wl & 1)] = bal;
         }
       }
       named_bar_sync(2, 128);
-      {  // thread l copies 16-byte chunk c = l & 7 of rows (l >> 3) + 16*rr, for the 4 k-blocks of the token row
-        const int c = l & 7, rb = l >> 3;
-        const int off = (c ^ (rb & 7)) << 4;
+      // thread l copies 16-byte chunk c = l & 7 of rows (l >> 3) + 16*rr of every k-block of the token row
+      const int c = l & 7, rb = l >> 3;
+      const int off = (c ^ (rb & 7)) << 4;
+#pragma unroll 1
+      for (int kb = 0; kb < SF_KB; ++kb, ++it) {
+        const int slot = (int)(it % SF_NSLOT);
+        mbar_wait(&a_empty[slot], (uint32_t)(((it / SF_NSLOT) & 1) ^ 1));
+        uint8_t* dslot = sa + (size_t)slot * SF_SLOT + off;
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
           const int r = rb + 16 * rr;
-          const long long grow = rows[r];
-          uint8_t* drow = sa + r * 128 + off;
-          if (grow < 0) {  // zero token: the projection adds the bias in the conversion step
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int kb = 0; kb < SF_KB; ++kb) *reinterpret_cast<float4*>(drow + kb * (128 * 128)) = z;
-          } else {
-            const float* src = tokn + grow * SF_C + c * 4;
-#pragma unroll
-            for (int kb = 0; kb < SF_KB; ++kb) cp_async_16(drow + kb * (128 * 128), src + kb * 32);
-          }
+          const int grow = rows[r];
+          if (grow < 0) *reinterpret_cast<float4*>(dslot + r * 128) = make_float4(0.f, 0.f, 0.f, 0.f);  // zero token
+          else cp_async_16(dslot + r * 128, tokn + (size_t)grow * SF_C + kb * 32 + c * 4);
         }
+        cp_async_mbar_arrive_noinc(&a_full[slot]);
+        mbar_arrive(&a_full[slot]);
       }
-      cp_async_mbar_arrive_noinc(a_full);
-      mbar_arrive(a_full);
     }
     cp_async_wait<0>();
   } else if (warp == 0) {
@@ -168,34 +173,41 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
       constexpr uint32_t IDESC_M1 = make_idesc_bf16(128, 96, 0, 0);
       constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 2 * HD, 0, 1);
-      long long n1 = 0, nq = 0, np = 0;
-      uint32_t idle = 0;  // polls without progress: a mis-programmed pipeline traps instead of hanging the GPU box
+      long long n1 = 0, nq = 0, np = 0, it = 0;
+      int kb1 = 0;          // next k-block of M1(n1)
+      uint32_t idle = 0;    // polls without progress: a mis-programmed pipeline traps instead of hanging the GPU box
       while (np < n_units) {
         if (++idle > 400000000u) __trap();
-        // M1(n1): token tile landed, D free (the conversion of unit n1 - 1 has read it)
-        if (n1 < n_units && mbar_test(a_full, (uint32_t)(n1 & 1)) && mbar_test(d_free, (uint32_t)((n1 & 1) ^ 1))) {
-          fence_proxy_async_smem();
-          tc_fence_after();
-#pragma unroll
-          for (int kb = 0; kb < SF_KB; ++kb) {
-            const uint64_t adesc = make_sw128_desc(smem_u32(sa + kb * (128 * 128)), 1024, 16);
-            const uint64_t bdesc = make_sw128_desc(smem_u32(sw + kb * (96 * 128)), 1024, 16);
-            mma_bf16x3_ss(tmem_base + SF_TMEM_D, adesc, bdesc, IDESC_M1, kb != 0);
+        // M1(n1), k-block kb1: its slot landed; for the first k-block D must be free (conversion of unit n1 - 1 has read it)
+        if (n1 < n_units) {
+          const int slot = (int)(it % SF_NSLOT);
+          if (mbar_test(&a_full[slot], (uint32_t)((it / SF_NSLOT) & 1)) &&
+              (kb1 != 0 || mbar_test(d_free, (uint32_t)((n1 & 1) ^ 1)))) {
+            fence_proxy_async_smem();
+            tc_fence_after();
+            const uint64_t adesc = make_sw128_desc(smem_u32(sa + (size_t)slot * SF_SLOT), 1024, 16);
+            const uint64_t bdesc = make_sw128_desc(smem_u32(sw + kb1 * (96 * 128)), 1024, 16);
+            mma_bf16x3_ss(tmem_base + SF_TMEM_D, adesc, bdesc, IDESC_M1, kb1 != 0);
+            mma_commit(&a_empty[slot]);
+            ++it;
+            if (++kb1 == SF_KB) {
+              kb1 = 0;
+              mma_commit(&d_ready[n1 & 1]);
+              ++n1;
+            }
+            idle = 0;
           }
-          mma_commit(a_empty);
-          mma_commit(&d_ready[n1 & 1]);
-          ++n1;
-          idle = 0;
         }
         // QK(nq): Q / K / V tiles of the unit converted; S/P buffer free once PV(nq - 2) has been issued
         if (nq < n1 && nq - np < 2 && mbar_test(&qkv_full[nq & 1], (uint32_t)((nq >> 1) & 1))) {
           fence_proxy_async_smem();
           tc_fence_after();
-          const uint32_t qaddr = smem_u32(smem + SF_OFF_QKV + (size_t)(nq & 1) * SF_QKV_BYTES);
+          const uint32_t qaddr = smem_u32(smem + SF_OFF_Q);
           const uint64_t qdesc = make_sw128_desc(qaddr, 1024, 16);
           const uint64_t kdesc = make_sw128_desc(qaddr + WA_TILE, 1024, 16);
           mma_bf16x3_ss(tmem_base + SF_TMEM_S + (uint32_t)(nq & 1) * 128, qdesc, kdesc, IDESC_QK, 0u);
           mma_commit(&s_ready[nq & 1]);
+          mma_commit(&qk_free[nq & 1]);  // the single Q / K tiles may be overwritten by the next unit's conversion
           ++nq;
           idle = 0;
         }
@@ -204,7 +216,7 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
           const uint32_t k = (uint32_t)(np >> 1);
           if (mbar_test(&p_ready[tb], k & 1) && mbar_test(&o_free[tb], (k & 1) ^ 1)) {
             tc_fence_after();
-            const uint32_t vaddr = smem_u32(smem + SF_OFF_QKV + (size_t)tb * SF_QKV_BYTES + 2 * WA_TILE);
+            const uint32_t vaddr = smem_u32(smem + SF_OFF_V + (size_t)tb * WA_TILE);
             const uint64_t vdesc = make_sw128_desc(vaddr, 1024, 1024);
             const uint32_t p_tmem = tmem_base + SF_TMEM_S + tb * 128;
             const uint32_t o_tmem = tmem_base + SF_TMEM_O + tb * 2 * HD;
@@ -215,7 +227,7 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
               mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);
             }
             mma_commit(&o_ready[tb]);
-            mma_commit(&qkv_empty[tb]);  // Q, K (read by QK, issued earlier) and V of this buffer are free again
+            mma_commit(&v_empty[tb]);
             ++np;
             idle = 0;
           }
@@ -233,25 +245,26 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
     for (long long u = wg; u < n_units; u += 2) {
       const uint32_t k = (uint32_t)(u >> 1);
       const uint8_t* meta = smem + SF_OFF_META + (size_t)(u % SF_META_SLOTS) * SF_META_BYTES;
-      const long long* rows = reinterpret_cast<const long long*>(meta);
-      const int* region = reinterpret_cast<const int*>(meta + 1024);
+      const int* rows = reinterpret_cast<const int*>(meta);
+      const uint8_t* region = meta + 512;
       // ---- conversion: D row (q | k | v of this head) + bias -> S32 rows of the Q / K / V operand tiles
       mbar_wait(&d_ready[tb], k & 1);
-      mbar_wait(&qkv_empty[tb], (k & 1) ^ 1);
       tc_fence_after();
       uint32_t ra[32], rb[32];
       {
-        uint8_t* qkv_s = smem + SF_OFF_QKV + (size_t)tb * SF_QKV_BYTES;
         const int sw7 = i & 7;
 #pragma unroll 1
-        for (int which = 0; which < 3; ++which) {  // q, k, v: 32 accumulator columns each (one at a time: register budget)
+        for (int step = 0; step < 3; ++step) {  // v first (its buffer is free early), then q, k (wait for QK of unit u - 1)
+          const int which = step == 0 ? 2 : step - 1;
+          if (step == 0) mbar_wait(&v_empty[tb], (k & 1) ^ 1);
+          if (step == 1 && u > 0) mbar_wait(&qk_free[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1));
           tmem_ld_32x32(lane_base + SF_TMEM_D + which * 32, ra);
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + sqb[which * 32 + j];
           split_chunk32(v, rb);
-          uint8_t* drow = qkv_s + which * WA_TILE + i * 128;
+          uint8_t* drow = smem + (which == 2 ? SF_OFF_V + tb * WA_TILE : SF_OFF_Q + which * WA_TILE) + i * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             *reinterpret_cast<uint4*>(drow + ((c ^ sw7) << 4)) = make_uint4(rb[4 * c], rb[4 * c + 1], rb[4 * c + 2], rb[4 * c + 3]);
@@ -269,7 +282,7 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
       tc_fence_after();
       const long long my_row = rows[i];
       const int my_reg = region[i];
-      const uint2 same = reinterpret_cast<const uint2*>(meta + 1536)[half * 9 + my_reg];
+      const uint2 same = reinterpret_cast<const uint2*>(meta + 640)[half * 9 + my_reg];
       const uint32_t diff_lo = ~same.x, diff_hi = ~same.y & 0x1FFFFu;
       const bool uniform = (diff_lo | diff_hi) == 0u;
       const float4* brow4 = reinterpret_cast<const float4*>(sb + (t < WT ? t : 0) * WA_BIAS_LD);
