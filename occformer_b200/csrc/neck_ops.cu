@@ -115,22 +115,28 @@ token_prep_kernel(const float* __restrict__ in, const float* __restrict__ ln_w, 
 //   out   (rows, E)  S32       sum_{l,p} softmax(logits)[l,p] * trilinear(value level l)(loc), zeros outside,
 //                              align_corners=False;  loc = ref + offset / (Z_l, Y_l, X_l),  ref = voxel centre of the
 //                              query in its own level, normalised to [0,1] (the same point for every value level)
-// One CTA = (patch of NK_PX x NK_PY x Z_l queries of one level, one head): QP queries x (hd/4) threads per pass.  A CTA's
-// value working set is then the patch plus the halo its sampling offsets reach, in ONE head's 96-byte slices (~70 KB at
-// a 2-voxel halo): it lives in L1 while the 8 corner rows of a sampling point (8 independent 16-byte loads per thread)
-// are shared between neighbouring queries and points -- L2 / HBM only see each slice about once per patch instead of the
-// ~30 times it is sampled.  (Queries ordered row by row spread a patch's neighbours over many SMs: 7.5 TB/s of L2 traffic.)
+// One CTA = (patch of NK_PX x NK_PY x Z_l queries of one level, one head), NK_QP queries per pass.  A CTA's value working
+// set is then the patch plus the halo its sampling offsets reach, in ONE head's slices (~70 KB at a 2-voxel halo): it
+// lives in L1 and L2 / HBM see each slice about once per patch instead of the ~30 times it is sampled.
+// A pass has three phases so that the scalar work is done once per sample instead of once per gather thread:
+//   0: one thread per query        : softmax of the head's L*P logits                      -> s_w
+//   1: one thread per (query, l, p): sampling location -> 8 (value row, softmax * trilinear weight) taps -> s_tap
+//   2: hd/4 threads per query      : acc += weight * value[row] over the L*P*8 taps (16-byte loads, 8 in flight)
+// Out-of-volume corners keep weight 0 and point at row 0 (zeros padding of grid_sample).
+constexpr int NK_QP = 32;
 template <int L, int P>
 __global__ void __launch_bounds__(256)
 ms_deform_attn_kernel(const float* __restrict__ value, const float* __restrict__ ow, float* __restrict__ out,
-                      const NeckLevels g, int E, int H, int QP) {
+                      const NeckLevels g, int E, int H) {
+  constexpr int LP = L * P, NT = LP * 8, TSTR = NT + 1;  // +1: queries of a warp land in different banks
+  extern __shared__ uint2 s_tap[];                       // [NK_QP][TSTR] (value row, weight bits), tap = corner * LP + i
+  __shared__ float s_w[NK_QP][LP];
+  __shared__ int s_dim[3][L];
+  __shared__ long long s_row0[L];
   const int hd = E / H;
   const int T1 = hd >> 2;  // threads per (query, head)
-  const int ql = threadIdx.x / T1, tt = threadIdx.x - ql * T1;
-  if (ql >= QP) return;
   const int h = blockIdx.y;
-  const int T = E >> 2;            // float4 per value row
-  const int t = h * T1 + tt;       // this thread's float4 inside the row
+  const int T = E >> 2;    // float4 per value row
   // patch -> (level, sample, px, py)
   int lq = 0;
 #pragma unroll
@@ -143,76 +149,107 @@ ms_deform_attn_kernel(const float* __restrict__ value, const float* __restrict__
   const int px = pid % npx;
   const int b = pid / npx;
   const int nq = NK_PX * NK_PY * Zq;
-#pragma unroll 1
-  for (int q = ql; q < nq; q += QP) {
-  const int z = q % Zq, iy = (q / Zq) % NK_PY, ix = q / (Zq * NK_PY);
-  const int x = px * NK_PX + ix, y = py * NK_PY + iy;
-  if (x >= Xq || y >= Yq) continue;
-  const int local = (x * Yq + y) * Zq + z;
-  const long long row = (long long)g.B * g.start[lq] + (long long)b * g.n[lq] + local;
-  // reference point (normalised voxel centre), computed as the reference does: ((i + 0.5) * stride) / (dim * stride)
-  float rz, ry, rx;
-  {
-    const float st = g.stride[lq];
-    rz = ((float)z + 0.5f) * st / ((float)Zq * st);
-    ry = ((float)y + 0.5f) * st / ((float)Yq * st);
-    rx = ((float)x + 0.5f) * st / ((float)Xq * st);
+  if (threadIdx.x < L) {
+    const int l = threadIdx.x;
+    s_dim[0][l] = g.X[l]; s_dim[1][l] = g.Y[l]; s_dim[2][l] = g.Z[l];
+    s_row0[l] = (long long)g.B * g.start[l] + (long long)b * g.n[l];
   }
-  const int LP = L * P;
-  const float* orow = ow + row * (size_t)(H * LP * 4);
-  const float* offs = orow + (size_t)h * LP * 3;
-  const float* logit = orow + (size_t)H * LP * 3 + (size_t)h * LP;
-  float w[L * P];
-  float m = -INFINITY;
+  const float st = g.stride[lq];
+  const long long qrow0 = (long long)g.B * g.start[lq] + (long long)b * g.n[lq];
+  // query q of the patch -> voxel (x, y, z); false when outside the volume
+  auto locate = [&](int q, int& x, int& y, int& z) {
+    z = q % Zq;
+    const int iy = (q / Zq) % NK_PY, ix = q / (Zq * NK_PY);
+    x = px * NK_PX + ix; y = py * NK_PY + iy;
+    return q < nq && x < Xq && y < Yq;
+  };
+  const int gq = threadIdx.x / T1, gt = threadIdx.x - gq * T1;  // phase 2: query of the pass, float4 of the head slice
+  const float4* vbase = reinterpret_cast<const float4*>(value) + h * T1 + gt;
+#pragma unroll 1
+  for (int q0 = 0; q0 < nq; q0 += NK_QP) {
+    __syncthreads();  // s_dim ready (first pass) / previous pass's taps consumed
+    if (threadIdx.x < NK_QP) {
+      int x, y, z;
+      if (locate(q0 + threadIdx.x, x, y, z)) {
+        const long long row = qrow0 + ((long long)x * Yq + y) * Zq + z;
+        const float* logit = ow + row * (size_t)(H * LP * 4) + (size_t)H * LP * 3 + (size_t)h * LP;
+        float w[LP];
+        float m = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < L * P; ++i) { w[i] = __ldg(logit + i); m = fmaxf(m, w[i]); }
-  float den = 0.f;
+        for (int i = 0; i < LP; ++i) { w[i] = __ldg(logit + i); m = fmaxf(m, w[i]); }
+        float den = 0.f;
 #pragma unroll
-  for (int i = 0; i < L * P; ++i) { w[i] = expf(w[i] - m); den += w[i]; }
-  const float inv = 1.0f / den;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4* vbase = reinterpret_cast<const float4*>(value) + t;
+        for (int i = 0; i < LP; ++i) { w[i] = expf(w[i] - m); den += w[i]; }
+        const float inv = 1.0f / den;
 #pragma unroll
-  for (int l = 0; l < L; ++l) {
-    const int Xl = g.X[l], Yl = g.Y[l], Zl = g.Z[l];
-    const long long lrow0 = (long long)g.B * g.start[l] + (long long)b * g.n[l];
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      const int i = l * P + p;
+        for (int i = 0; i < LP; ++i) s_w[threadIdx.x][i] = w[i] * inv;
+      }
+    }
+    __syncthreads();
+    for (int task = threadIdx.x; task < NK_QP * LP; task += blockDim.x) {
+      const int ql = task / LP, i = task - ql * LP, l = i / P;
+      int x, y, z;
+      if (!locate(q0 + ql, x, y, z)) continue;
+      const long long row = qrow0 + ((long long)x * Yq + y) * Zq + z;
+      const float* offs = ow + row * (size_t)(H * LP * 4) + (size_t)h * LP * 3 + 3 * i;
+      const int Xl = s_dim[0][l], Yl = s_dim[1][l], Zl = s_dim[2][l];
+      // reference point (normalised voxel centre), computed as the reference does: ((i + 0.5) * stride) / (dim * stride)
+      const float rz = ((float)z + 0.5f) * st / ((float)Zq * st);
+      const float ry = ((float)y + 0.5f) * st / ((float)Yq * st);
+      const float rx = ((float)x + 0.5f) * st / ((float)Xq * st);
       // grid_sample(align_corners=False) un-normalisation, in torch's own form: ((g + 1) * size - 1) / 2 with g = 2 loc - 1
-      const float lz = rz + __ldg(offs + 3 * i + 0) / (float)Zl;
-      const float ly = ry + __ldg(offs + 3 * i + 1) / (float)Yl;
-      const float lx = rx + __ldg(offs + 3 * i + 2) / (float)Xl;
+      const float lz = rz + __ldg(offs + 0) / (float)Zl;
+      const float ly = ry + __ldg(offs + 1) / (float)Yl;
+      const float lx = rx + __ldg(offs + 2) / (float)Xl;
       const float fz = (((2.0f * lz - 1.0f) + 1.0f) * (float)Zl - 1.0f) * 0.5f;
       const float fy = (((2.0f * ly - 1.0f) + 1.0f) * (float)Yl - 1.0f) * 0.5f;
       const float fx = (((2.0f * lx - 1.0f) + 1.0f) * (float)Xl - 1.0f) * 0.5f;
       const float z0f = floorf(fz), y0f = floorf(fy), x0f = floorf(fx);
-      const int z0 = (int)z0f, y0 = (int)y0f, x0 = (int)x0f;
+      // (clamped before the int conversion: a wild offset must not overflow; anything outside is dropped below)
+      const int z0 = (int)fminf(fmaxf(z0f, -2.f), (float)Zl), y0 = (int)fminf(fmaxf(y0f, -2.f), (float)Yl),
+                x0 = (int)fminf(fmaxf(x0f, -2.f), (float)Xl);
       const float tz = fz - z0f, ty = fy - y0f, tx = fx - x0f;
-      const float wa = w[i] * inv;
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 c[8];
-      float cw[8];
+      const float wa = s_w[ql][i];
+      const long long lrow0 = s_row0[l];
+      uint2* tp = s_tap + ql * TSTR + i;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int dz = k & 1, dy = (k >> 1) & 1, dx = k >> 2;
         const int zz = z0 + dz, yy = y0 + dy, xx = x0 + dx;
         const bool ok = zz >= 0 && zz < Zl && yy >= 0 && yy < Yl && xx >= 0 && xx < Xl;
-        cw[k] = ok ? (dz ? tz : 1.f - tz) * (dy ? ty : 1.f - ty) * (dx ? tx : 1.f - tx) : 0.f;
-        c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) c[k] = __ldg(vbase + (lrow0 + ((long long)xx * Yl + yy) * Zl + zz) * T);
+        const float cw = (dz ? tz : 1.f - tz) * (dy ? ty : 1.f - ty) * (dx ? tx : 1.f - tx);
+        uint2 e;
+        e.x = ok ? (uint32_t)(lrow0 + ((long long)xx * Yl + yy) * Zl + zz) : 0u;
+        e.y = ok ? __float_as_uint(wa * cw) : 0u;
+        tp[k * LP] = e;
       }
+    }
+    __syncthreads();
+    {
+      int x, y, z;
+      if (gq < NK_QP && locate(q0 + gq, x, y, z)) {
+        const uint2* tp = s_tap + gq * TSTR;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int s0 = 0; s0 < NT; s0 += 8) {
+          uint2 e[8];
+          float4 c[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        s.x = fmaf(cw[k], c[k].x, s.x); s.y = fmaf(cw[k], c[k].y, s.y);
-        s.z = fmaf(cw[k], c[k].z, s.z); s.w = fmaf(cw[k], c[k].w, s.w);
+          for (int k = 0; k < 8; ++k) e[k] = tp[s0 + k];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) c[k] = __ldg(vbase + (size_t)e[k].x * T);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float w = __uint_as_float(e[k].y);
+            acc.x = fmaf(w, c[k].x, acc.x); acc.y = fmaf(w, c[k].y, acc.y);
+            acc.z = fmaf(w, c[k].z, acc.z); acc.w = fmaf(w, c[k].w, acc.w);
+          }
+        }
+        const long long row = qrow0 + ((long long)x * Yq + y) * Zq + z;
+        store_split4(out + row * E, 4 * (h * T1 + gt), acc);
       }
-      acc.x = fmaf(wa, s.x, acc.x); acc.y = fmaf(wa, s.y, acc.y);
-      acc.z = fmaf(wa, s.z, acc.z); acc.w = fmaf(wa, s.w, acc.w);
     }
   }
-  store_split4(out + row * E, 4 * t, acc);
-  }  // queries of the patch
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -383,14 +420,18 @@ extern "C" int occ_ms_deform_attn(const float* value, const float* ow, float* ou
   NeckLevels g;
   OCC_REQUIRE(fill_levels(g, L, B, grids, strides) == OCC_OK);
   const int T1 = E / H / 4;
-  const int QP = 256 / T1;
-  OCC_REQUIRE(H <= 65535 && QP >= 1);
+  OCC_REQUIRE(H <= 65535 && T1 >= 1 && T1 <= 8 && g.rows < (1ll << 31));
   dim3 grid((unsigned)g.npatches, (unsigned)H);
-  if (L == 3 && P == 4) ms_deform_attn_kernel<3, 4><<<grid, QP * T1, 0, stream>>>(value, ow, out, g, E, H, QP);
-  else if (L == 1 && P == 4) ms_deform_attn_kernel<1, 4><<<grid, QP * T1, 0, stream>>>(value, ow, out, g, E, H, QP);
-  else if (L == 2 && P == 4) ms_deform_attn_kernel<2, 4><<<grid, QP * T1, 0, stream>>>(value, ow, out, g, E, H, QP);
-  else if (L == 4 && P == 4) ms_deform_attn_kernel<4, 4><<<grid, QP * T1, 0, stream>>>(value, ow, out, g, E, H, QP);
-  else return OCC_EUNSUPPORTED;
+  const int threads = NK_QP * T1;
+  const size_t smem = (size_t)NK_QP * (L * P * 8 + 1) * sizeof(uint2);
+#define MSDA_CASE(l)                                                                                    \
+  if (L == l && P == 4) {                                                                               \
+    OCC_ENSURE_SMEM((ms_deform_attn_kernel<l, 4>), smem);                                               \
+    ms_deform_attn_kernel<l, 4><<<grid, threads, smem, stream>>>(value, ow, out, g, E, H);              \
+  } else
+  MSDA_CASE(3) MSDA_CASE(1) MSDA_CASE(2) MSDA_CASE(4)
+#undef MSDA_CASE
+    return OCC_EUNSUPPORTED;
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
