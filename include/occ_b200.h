@@ -179,11 +179,12 @@ int occ_swin_qkv_attention(const float* tokn, const float* wqkv, const float* bq
 int occ_neck_token_prep(const float* in, const float* ln_w, const float* ln_b, const float* pos, float* out_f32,
                         float* out_s32, float* out_pos, int L, int B, const int* grids, int C, occ_stream_t stream);
 /* multi_scale_deformable_attn_pytorch + the sampling-location arithmetic of MultiScaleDeformableAttention3D.forward:
- * value (rows, E) = value_proj output; ow (rows, H*L*P*4) = [sampling_offsets (h,l,p,(z,y,x)) | attention logits (h,l,p)];
+ * value (rows, value_ld) = value_proj output, head h at columns [h*head_ld, h*head_ld + E/H) (head_ld = E/H, or E/H
+ * rounded up to 32 floats so that a head slice is one 128-byte line); ow (rows, H*L*P*4) = [sampling_offsets (h,l,p,(z,y,x)) | attention logits (h,l,p)];
  * out (rows, E) S32 = sum_{l,p} softmax(logits) * trilinear(value level l)(ref + offset / (Z_l,Y_l,X_l)), zeros outside,
  * align_corners=False; strides = the L feature strides (HOST floats; reference-point arithmetic). */
-int occ_ms_deform_attn(const float* value, const float* ow, float* out, int L, int B, const int* grids,
-                       const float* strides, int E, int H, int P, occ_stream_t stream);
+int occ_ms_deform_attn(const float* value, int value_ld, int head_ld, const float* ow, float* out, int L, int B,
+                       const int* grids, const float* strides, int E, int H, int P, occ_stream_t stream);
 /* FPN step (:228-240): out_s (S32) = GroupNorm(cur raw lateral-conv output, stats) + trilinear upsample
  * (align_corners=False) of coarse (B, Xc, Yc, Zc, C) fp32 */
 int occ_gn_upsample_add(const float* cur, const double* stats, const float* gw, const float* gb, int groups,

@@ -41,7 +41,7 @@ SIGNATURES = {
     "occ_window_attention": (c_int, [P, P, P, P] + [c_int] * 8 + [STREAM]),
     "occ_swin_qkv_attention": (c_int, [P] * 5 + [c_int] * 7 + [STREAM]),
     "occ_neck_token_prep": (c_int, [P] * 7 + [c_int, c_int, P, c_int, STREAM]),
-    "occ_ms_deform_attn": (c_int, [P, P, P, c_int, c_int, P, P, c_int, c_int, c_int, STREAM]),
+    "occ_ms_deform_attn": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_int, c_int, c_int, STREAM]),
     "occ_gn_upsample_add": (c_int, [P] * 4 + [c_int, P, P] + [c_int] * 8 + [STREAM]),
     "occ_gn_stats": (c_int, [P, P, c_int, c_int, c_int, c_int, STREAM]),
     "occ_sine_pos3d": (c_int, [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, STREAM]),

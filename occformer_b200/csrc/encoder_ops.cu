@@ -202,6 +202,10 @@ layernorm_generic_kernel(const float* __restrict__ in, const float* __restrict__
 // grid (row chunks, B): a CTA never straddles two samples, so the per-channel scale / shift of its sample
 // (rstd * gamma, beta - mean * rstd * gamma; fp64 division + sqrt once per (CTA, group)) sit in shared memory and an
 // element costs one FMA.
+// A thread owns ONE float4 column (scale / shift in registers) and walks rows: no per-element index division, and
+// GA_UNROLL independent 16-byte loads in flight (a tensor of 5 MB is latency-, not bandwidth-bound).  C/4 > 256: the
+// column loop runs more than once.
+constexpr int GA_UNROLL = 4;
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ in, const double* __restrict__ stats, const float* __restrict__ w,
                 const float* __restrict__ b, const float* __restrict__ residual, float* __restrict__ out,
@@ -222,23 +226,39 @@ gn_apply_kernel(const float* __restrict__ in, const double* __restrict__ stats, 
   }
   __syncthreads();
   const int C4 = C >> 2;
+  const int cols = C4 < 256 ? C4 : 256;       // float4 columns handled per pass
+  const int rstep = 256 / cols;               // rows handled per pass
+  const int rl = threadIdx.x / cols, cl = threadIdx.x - rl * cols;
+  if (rl >= rstep) return;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(r0 + rows_per_cta, rows_per_batch);
-  const long long base = (long long)bidx * rows_per_batch;
-  for (long long i4 = (long long)r0 * C4 + threadIdx.x; i4 < (long long)r1 * C4; i4 += blockDim.x) {
-    const long long row = base + i4 / C4;
-    const int c0 = (int)(i4 % C4) * 4;
-    const float4 t = __ldcs(reinterpret_cast<const float4*>(in + row * C + c0));
+  const size_t base = (size_t)bidx * rows_per_batch;
+  for (int c4 = cl; c4 < C4; c4 += cols) {
+    const int c0 = c4 * 4;
     const float4 a = *reinterpret_cast<const float4*>(sc + c0), d = *reinterpret_cast<const float4*>(sh + c0);
-    // (v - mean) * rstd * gamma + beta, evaluated as v * (rstd*gamma) + (beta - mean*rstd*gamma)
-    float4 o = make_float4(fmaf(t.x, a.x, d.x), fmaf(t.y, a.y, d.y), fmaf(t.z, a.z, d.z), fmaf(t.w, a.w, d.w));
-    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    if (residual) {
-      const float4 r = *reinterpret_cast<const float4*>(residual + row * C + c0);
-      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    for (int r = r0 + rl; r < r1; r += GA_UNROLL * rstep) {
+      float4 t[GA_UNROLL], rs[GA_UNROLL];
+#pragma unroll
+      for (int u = 0; u < GA_UNROLL; ++u) {
+        const int rr = r + u * rstep;
+        if (rr < r1) {
+          t[u] = __ldcs(reinterpret_cast<const float4*>(in + (base + rr) * C + c0));
+          if (residual) rs[u] = *reinterpret_cast<const float4*>(residual + (base + rr) * C + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < GA_UNROLL; ++u) {
+        const int rr = r + u * rstep;
+        if (rr < r1) {
+          // (v - mean) * rstd * gamma + beta, evaluated as v * (rstd*gamma) + (beta - mean*rstd*gamma)
+          float4 o = make_float4(fmaf(t[u].x, a.x, d.x), fmaf(t[u].y, a.y, d.y), fmaf(t[u].z, a.z, d.z), fmaf(t[u].w, a.w, d.w));
+          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (residual) { o.x += rs[u].x; o.y += rs[u].y; o.z += rs[u].z; o.w += rs[u].w; }
+          if (out) *reinterpret_cast<float4*>(out + (base + rr) * C + c0) = o;
+          if (out_split) store_split4(out_split + (base + rr) * ldo, out_off + c0, o);
+        }
+      }
     }
-    if (out) *reinterpret_cast<float4*>(out + row * C + c0) = o;
-    if (out_split) store_split4(out_split + row * ldo, out_off + c0, o);
   }
 }
 
@@ -475,9 +495,13 @@ extern "C" int occ_gn_apply(const float* in, const double* stats, const float* w
   if (out_split) OCC_REQUIRE(C % 32 == 0 && ldo % 32 == 0 && out_off % 32 == 0 && out_off + C <= ldo);
   OCC_REQUIRE(C <= 4096 && rows / rows_per_batch <= 65535);
   const int B = (int)(rows / rows_per_batch);
-  // rows per CTA: ~2048 float4 per CTA pass, at least 4 waves of CTAs on big tensors
-  int rpc = (2048 * 4 + C / 4 - 1) / (C / 4);
-  if (rpc < 1) rpc = 1;
+  // rows per CTA: k * GA_UNROLL rows per thread and column pass, k in 1..8 chosen for >= ~4 waves of 3 CTAs per SM
+  // (the fp64 scale / shift prologue is per CTA: big tensors amortise it over more rows)
+  const int cols = C / 4 < 256 ? C / 4 : 256;
+  const int unit = (256 / cols) * GA_UNROLL;
+  long long k = rows / ((long long)unit * 12 * sm_count());
+  k = k < 1 ? 1 : (k > 8 ? 8 : k);
+  int rpc = unit * (int)k;
   dim3 grid((rows_per_batch + rpc - 1) / rpc, B);
   gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(in, stats, w, b, residual, out, out_split, rows_per_batch, C,
                                                                 groups, ldo, out_off, relu, rpc);

@@ -110,7 +110,9 @@ token_prep_kernel(const float* __restrict__ in, const float* __restrict__ ln_w, 
 
 // ---------------------------------------------------------------------------------------------------------
 // Multi-scale deformable attention core, 3-D (multi_scale_deform_attn_3d.py:17-80 + the location arithmetic of :258-272).
-//   value (rows, E)            value_proj output, level-major, head h = channels [h*hd, (h+1)*hd)
+//   value (rows, value_ld)     value_proj output, level-major, head h = channels [h*head_ld, h*head_ld + hd): with
+//                              head_ld = hd rounded up to 32 floats a head slice is one 128-byte line (the kernel is
+//                              bound by L1 wavefronts = distinct lines touched: 1 instead of 1.5 per 96-byte slice)
 //   ow    (rows, H*L*P*4)      [ sampling_offsets (h, l, p, 3: z, y, x) | attention logits (h, l, p) ] of the same token
 //   out   (rows, E)  S32       sum_{l,p} softmax(logits)[l,p] * trilinear(value level l)(loc), zeros outside,
 //                              align_corners=False;  loc = ref + offset / (Z_l, Y_l, X_l),  ref = voxel centre of the
@@ -127,7 +129,7 @@ constexpr int NK_QP = 32;
 template <int L, int P>
 __global__ void __launch_bounds__(256)
 ms_deform_attn_kernel(const float* __restrict__ value, const float* __restrict__ ow, float* __restrict__ out,
-                      const NeckLevels g, int E, int H) {
+                      const NeckLevels g, int E, int H, int value_ld, int head_ld) {
   constexpr int LP = L * P, NT = LP * 8, TSTR = NT + 1;  // +1: queries of a warp land in different banks
   extern __shared__ uint2 s_tap[];                       // [NK_QP][TSTR] (value row, weight bits), tap = corner * LP + i
   __shared__ float s_w[NK_QP][LP];
@@ -136,7 +138,7 @@ ms_deform_attn_kernel(const float* __restrict__ value, const float* __restrict__
   const int hd = E / H;
   const int T1 = hd >> 2;  // threads per (query, head)
   const int h = blockIdx.y;
-  const int T = E >> 2;    // float4 per value row
+  const int T = value_ld >> 2;  // float4 per value row
   // patch -> (level, sample, px, py)
   int lq = 0;
 #pragma unroll
@@ -164,7 +166,7 @@ ms_deform_attn_kernel(const float* __restrict__ value, const float* __restrict__
     return q < nq && x < Xq && y < Yq;
   };
   const int gq = threadIdx.x / T1, gt = threadIdx.x - gq * T1;  // phase 2: query of the pass, float4 of the head slice
-  const float4* vbase = reinterpret_cast<const float4*>(value) + h * T1 + gt;
+  const float4* vbase = reinterpret_cast<const float4*>(value) + h * (head_ld >> 2) + gt;
 #pragma unroll 1
   for (int q0 = 0; q0 < nq; q0 += NK_QP) {
     __syncthreads();  // s_dim ready (first pass) / previous pass's taps consumed
@@ -410,12 +412,14 @@ extern "C" int occ_neck_token_prep(const float* in, const float* ln_w, const flo
   return OCC_OK;
 }
 
-// value (rows, E), ow (rows, H*L*P*4) = [offsets (h,l,p,3) | logits (h,l,p)], out (rows, E) S32.
+// value (rows, value_ld) with head h at columns [h*head_ld, h*head_ld + E/H), ow (rows, H*L*P*4) = [offsets (h,l,p,3) |
+// logits (h,l,p)], out (rows, E) S32.
 // strides: the L feature strides of the levels (reference-point arithmetic, multiscale_deformattn_3d.py:166-171).
-extern "C" int occ_ms_deform_attn(const float* value, const float* ow, float* out, int L, int B, const int* grids,
-                                  const float* strides, int E, int H, int P, cudaStream_t stream) {
+extern "C" int occ_ms_deform_attn(const float* value, int value_ld, int head_ld, const float* ow, float* out, int L, int B,
+                                  const int* grids, const float* strides, int E, int H, int P, cudaStream_t stream) {
   OCC_REQUIRE(value && ow && out && grids && strides);
   OCC_REQUIRE(E % 32 == 0 && H > 0 && E % H == 0 && (E / H) % 4 == 0 && E / 4 <= 256);
+  OCC_REQUIRE(head_ld >= E / H && head_ld % 4 == 0 && value_ld >= (H - 1) * head_ld + E / H && value_ld % 4 == 0);
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(value) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   NeckLevels g;
   OCC_REQUIRE(fill_levels(g, L, B, grids, strides) == OCC_OK);
@@ -427,7 +431,7 @@ extern "C" int occ_ms_deform_attn(const float* value, const float* ow, float* ou
 #define MSDA_CASE(l)                                                                                    \
   if (L == l && P == 4) {                                                                               \
     OCC_ENSURE_SMEM((ms_deform_attn_kernel<l, 4>), smem);                                               \
-    ms_deform_attn_kernel<l, 4><<<grid, threads, smem, stream>>>(value, ow, out, g, E, H);              \
+    ms_deform_attn_kernel<l, 4><<<grid, threads, smem, stream>>>(value, ow, out, g, E, H, value_ld, head_ld); \
   } else
   MSDA_CASE(3) MSDA_CASE(1) MSDA_CASE(2) MSDA_CASE(4)
 #undef MSDA_CASE

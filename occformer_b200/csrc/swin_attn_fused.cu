@@ -8,17 +8,19 @@
 // Work unit = (pair of windows, head), one head per CTA (gridDim.x is a multiple of the head count): the head's 96 x 128
 // slice of the qkv weight (rows [q | k | v] x 32, head-major) stays resident in shared memory for the whole kernel.
 // Per unit:
-//   loaders  (warps 12-15)  cp.async gather of the 128 token rows (49 + 49 real, S32) -> A tile, 4 K-major k-blocks
+//   loaders  (warps 1-3)    cp.async gather of the 128 token rows (49 + 49 real, S32) -> A tile, 4 K-major k-blocks
 //   MMA      (warp 0)       M1: D[128 x 96] = A W_h^T            (4 k-blocks x 6 tcgen05.mma 128x96x16: three bf16 passes)
 //                           QK: S = Q K^T, PV: O' = [P_hi; P_lo][V_hi | V_lo]   (as in window_attn.cu)
-//   two warpgroups (warps 4-7 / 8-11, even / odd units):
-//       convert : tcgen05.ld D -> + bias -> split -> Q / K operand tiles (single: free again as soon as QK^T of the previous
-//                 unit has been read) and V operand tile (double buffered: read by PV one softmax later)
+//   three warpgroups (warps 4-7 / 8-11 / 12-15, unit u -> warpgroup u % 3), each running its unit start to end:
+//       convert : tcgen05.ld D -> + bias -> split -> V operand tile (one per warpgroup), then Q / K operand tiles (single:
+//                 free again as soon as QK^T of the previous unit has been read)
 //       softmax : S row -> scale, relative-position bias, shift mask, exp2 -> P (TMEM, split)      (unchanged)
 //       epilogue: O -> normalise -> S32 scatter to the token-ordered output (A operand of the projection GEMM)
-// The token tiles arrive through a ring of six 16 KB k-block slots (1.5 units of gathers in flight per CTA: the gather
-// latency, not the bandwidth, is what a single-buffered tile would expose).  The conversion of unit u+1 (other
-// warpgroup) overlaps the softmax of unit u; M1(u+1) overlaps both.
+// A warpgroup's unit is a serial chain of TMEM round trips (~5 k cycles, IPC ~0.15 per warp: ncu of the two-warpgroup
+// version, profiles/r02_ncu_swin_qkv_attn_v2.md), so the kernel's rate is (warpgroups in flight) / chain: three units are
+// in flight, each with its own TMEM slot of 128 columns that holds D, then S, then P of the unit (D is dead once
+// converted, S once exponentiated), plus two O buffers.  The token tiles arrive through a ring of five 16 KB k-block
+// slots (the gather latency, not the bandwidth, is what a single-buffered tile would expose).
 // HBM: tokens in (rows*C*4) + attention out (rows*C*4); the 4 head-CTAs of a group walk the same window pairs at the
 // same time, so three of the four token reads are L2 hits.
 #include "window_geom.cuh"
@@ -29,18 +31,20 @@ constexpr int SF_C = 128;
 constexpr int SF_KB = SF_C / 32;                      // k-blocks of the projection
 constexpr int SF_W_BYTES = SF_KB * 96 * 128;          // 49152: W_h as 4 K-major SWIZZLE_128B tiles of 96 rows
 constexpr int SF_SLOT = 128 * 128;                    // 16384: one k-block of the token tile (128 rows x 128 B)
-constexpr int SF_NSLOT = 6;                           // ring of k-block slots = 1.5 token tiles
+constexpr int SF_NSLOT = 5;                           // ring of k-block slots = 1.25 token tiles
+constexpr int SF_NWG = 3;                             // converting warpgroups = units in flight
+constexpr int SF_LOADERS = 96;                        // warps 1-3
 constexpr int SF_META_BYTES = 832;                    // rows int32 (512) + region bytes (128) + same masks (144), padded
 constexpr int SF_META_SLOTS = 8;                      // units u-4 .. u+1 can be live at once (loader ahead, epilogue behind)
 constexpr int SF_OFF_A = SF_W_BYTES;                                    // 49152
-constexpr int SF_OFF_Q = SF_OFF_A + SF_NSLOT * SF_SLOT;                 // 147456: Q tile, then K tile (single buffered)
-constexpr int SF_OFF_V = SF_OFF_Q + 2 * WA_TILE;                        // 180224: V tiles (double buffered)
-constexpr int SF_OFF_BIAS = SF_OFF_V + 2 * WA_TILE;                     // 212992: relative-position bias (49, 52) * log2 e
+constexpr int SF_OFF_Q = SF_OFF_A + SF_NSLOT * SF_SLOT;                 // 131072: Q tile, then K tile (single buffered)
+constexpr int SF_OFF_V = SF_OFF_Q + 2 * WA_TILE;                        // 163840: V tiles (one per warpgroup)
+constexpr int SF_OFF_BIAS = SF_OFF_V + SF_NWG * WA_TILE;                     // 212992: relative-position bias (49, 52) * log2 e
 constexpr int SF_OFF_QB = SF_OFF_BIAS + WA_BIAS_BYTES;                  // 223232: this head's 96 qkv bias values
 constexpr int SF_OFF_META = SF_OFF_QB + 384;                            // 223616
 constexpr int SF_OFF_BAR = SF_OFF_META + SF_META_SLOTS * SF_META_BYTES; // 230272
 constexpr int SF_SMEM = SF_OFF_BAR + 384 + 1024;                        // 231680 <= 232448 (227 KB)
-constexpr uint32_t SF_TMEM_D = 0, SF_TMEM_S = 128, SF_TMEM_O = 384;     // D: 96 cols, S/P: 2 x 128, O: 2 x 64
+constexpr uint32_t SF_TMEM_U = 0, SF_TMEM_O = 384;  // unit slots 3 x 128 (D 96 cols -> S -> P), O: 2 x 64
 
 __global__ void __launch_bounds__(WA_THREADS, 1)
 swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const float* __restrict__ wqkv /*(384, 128) S32,
@@ -55,17 +59,18 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
   float* sqb = reinterpret_cast<float*>(smem + SF_OFF_QB);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SF_OFF_BAR);  // [SF_NSLOT] k-block slot filled
   uint64_t* a_empty = a_full + SF_NSLOT;                              // [SF_NSLOT] k-block slot consumed by M1
-  uint64_t* d_ready = a_empty + SF_NSLOT;  // [2] (one per warpgroup: a consumer that first waits for an ODD phase of a
-                                           // shared barrier cannot tell "phase 1 done" from "nothing done yet")
-  uint64_t* d_free = d_ready + 2;          // D has been read by the conversion
-  uint64_t* qkv_full = d_free + 1;         // [2] Q, K, V[tb] of the unit are in shared memory
-  uint64_t* qk_free = qkv_full + 2;        // [2] QK^T of the even / odd units has been read out of the Q / K tiles
-  uint64_t* v_empty = qk_free + 2;         // [2] PV has been read out of V[tb]
-  uint64_t* s_ready = v_empty + 2;         // [2]
-  uint64_t* p_ready = s_ready + 2;         // [2]
-  uint64_t* o_ready = p_ready + 2;         // [2]
-  uint64_t* o_free = o_ready + 2;          // [2]
+  // every barrier below has ONE waiter: the warpgroup (or the MMA thread) that owns index u % 3 -- a waiter that first
+  // waits for an odd phase of a shared barrier cannot tell "phase 1 done" from "nothing done yet"
+  uint64_t* d_ready = a_empty + SF_NSLOT;  // [3] M1 of unit u landed in TMEM slot u % 3
+  uint64_t* qkv_full = d_ready + SF_NWG;   // [3] Q, K, V[u % 3] of the unit are in shared memory
+  uint64_t* qk_free = qkv_full + SF_NWG;   // [3] QK^T of unit u has been read out of the Q / K tiles (waiter: unit u + 1)
+  uint64_t* v_empty = qk_free + SF_NWG;    // [3] PV has been read out of V[u % 3]
+  uint64_t* s_ready = v_empty + SF_NWG;    // [3]
+  uint64_t* p_ready = s_ready + SF_NWG;    // [3]
+  uint64_t* o_ready = p_ready + SF_NWG;    // [3]
+  uint64_t* o_free = o_ready + SF_NWG;     // [2] O buffer u & 1 has been read by the epilogue (waiter: MMA thread)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 2);
+  static_assert((2 * SF_NSLOT + 7 * SF_NWG + 2) * 8 + 4 <= 384, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long npairs = (g.nwin + 1) / 2;
@@ -89,21 +94,20 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < SF_NSLOT; ++i) {
-      mbar_init(&a_full[i], 256);  // per loader thread: one cp.async arrival + one release arrival
-      mbar_init(&a_empty[i], 1);   // tcgen05.commit after the k-block's MMAs
+      mbar_init(&a_full[i], 2 * SF_LOADERS);  // per loader thread: one cp.async arrival + one release arrival
+      mbar_init(&a_empty[i], 1);              // tcgen05.commit after the k-block's MMAs
     }
-    mbar_init(&d_ready[0], 1);     // tcgen05.commit after M1 of the even / odd units
-    mbar_init(&d_ready[1], 1);
-    mbar_init(d_free, 4);          // the four warps of the converting warpgroup
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&qkv_full[i], 4);
+    for (int i = 0; i < SF_NWG; ++i) {
+      mbar_init(&d_ready[i], 1);
+      mbar_init(&qkv_full[i], 4);  // the four warps of the converting warpgroup
       mbar_init(&qk_free[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_ready[i], 1);
       mbar_init(&p_ready[i], 4);
       mbar_init(&o_ready[i], 1);
-      mbar_init(&o_free[i], 4);
     }
+    mbar_init(&o_free[0], 4);
+    mbar_init(&o_free[1], 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_ptr);
@@ -113,19 +117,22 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp >= 12) {
+  if (warp >= 1 && warp < 4) {
     // ===================================================================== loaders
-    const int l = threadIdx.x - 12 * 32;  // 0..127
-    long long it = 0;                      // running k-block counter -> ring slot / phase
+    const int l = threadIdx.x - 32;  // 0..95
+    const int lw = warp - 1;
+    long long it = 0;                // running k-block counter -> ring slot / phase
     for (long long u = 0; u < n_units; ++u) {
       const long long pair = pair0 + u * pair_stride;
       uint8_t* meta = smem + SF_OFF_META + (size_t)(u % SF_META_SLOTS) * SF_META_BYTES;
       int* rows = reinterpret_cast<int*>(meta);
       uint8_t* region = meta + 512;
-      int my_reg = 0;
-      {
-        const long long win = 2 * pair + (l >> 6);
-        const int t = l & 63;
+      uint32_t* same32 = reinterpret_cast<uint32_t*>(meta + 640);
+      for (int rw = lw; rw < 4; rw += 3) {  // 32-row chunk rw of the tile: window rw >> 1, tokens (rw & 1) * 32 + lane
+        const int li = rw * 32 + lane;
+        const long long win = 2 * pair + (li >> 6);
+        const int t = li & 63;
+        int my_reg = 0;
         long long r = -2;  // -2: MMA padding row, -1: window pad token (zero token: q/k/v = bias)
         if (t < WT && win < g.nwin) {
           long long w = win;
@@ -133,34 +140,29 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
           const int wx = (int)(w % g.nWx); w /= g.nWx;
           r = window_token_row(g, (int)w, wx, wy, t, &my_reg);
         }
-        rows[l] = (int)r;
-        region[l] = (uint8_t)my_reg;
-      }
-      {
-        const int t = l & 63, wl = l >> 5;
+        rows[li] = (int)r;
+        region[li] = (uint8_t)my_reg;
         const bool tok = t < WT;
-        uint32_t* same32 = reinterpret_cast<uint32_t*>(meta + 640);
 #pragma unroll
-        for (int r = 0; r < 9; ++r) {
-          const uint32_t bal = __ballot_sync(0xffffffffu, tok && my_reg == r);
-          if (lane == 0) same32[((wl >> 1) * 9 + r) * 2 + (wl & 1)] = bal;
+        for (int rg = 0; rg < 9; ++rg) {
+          const uint32_t bal = __ballot_sync(0xffffffffu, tok && my_reg == rg);
+          if (lane == 0) same32[((rw >> 1) * 9 + rg) * 2 + (rw & 1)] = bal;
         }
       }
-      named_bar_sync(2, 128);
-      // thread l copies 16-byte chunk c = l & 7 of rows (l >> 3) + 16*rr of every k-block of the token row
-      const int c = l & 7, rb = l >> 3;
-      const int off = (c ^ (rb & 7)) << 4;
+      named_bar_sync(2, SF_LOADERS);
 #pragma unroll 1
       for (int kb = 0; kb < SF_KB; ++kb, ++it) {
         const int slot = (int)(it % SF_NSLOT);
         mbar_wait(&a_empty[slot], (uint32_t)(((it / SF_NSLOT) & 1) ^ 1));
-        uint8_t* dslot = sa + (size_t)slot * SF_SLOT + off;
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-          const int r = rb + 16 * rr;
+        uint8_t* dslot = sa + (size_t)slot * SF_SLOT;
+        // 16-byte chunk c of row r of the k-block: 1024 chunks over the 96 loader threads
+#pragma unroll 1
+        for (int idx = l; idx < 128 * 8; idx += SF_LOADERS) {
+          const int r = idx >> 3, c = idx & 7;
           const int grow = rows[r];
-          if (grow < 0) *reinterpret_cast<float4*>(dslot + r * 128) = make_float4(0.f, 0.f, 0.f, 0.f);  // zero token
-          else cp_async_16(dslot + r * 128, tokn + (size_t)grow * SF_C + kb * 32 + c * 4);
+          uint8_t* dst = dslot + r * 128 + ((c ^ (r & 7)) << 4);
+          if (grow < 0) *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);  // zero token
+          else cp_async_16(dst, tokn + (size_t)grow * SF_C + kb * 32 + c * 4);
         }
         cp_async_mbar_arrive_noinc(&a_full[slot]);
         mbar_arrive(&a_full[slot]);
@@ -181,69 +183,69 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
         // M1(n1), k-block kb1: its slot landed; for the first k-block D must be free (conversion of unit n1 - 1 has read it)
         if (n1 < n_units) {
           const int slot = (int)(it % SF_NSLOT);
-          if (mbar_test(&a_full[slot], (uint32_t)((it / SF_NSLOT) & 1)) &&
-              (kb1 != 0 || mbar_test(d_free, (uint32_t)((n1 & 1) ^ 1)))) {
+          // the first k-block overwrites TMEM slot n1 % 3 = the P of unit n1 - 3: its PV must have been issued (in order)
+          if ((kb1 != 0 || n1 - np < SF_NWG) && mbar_test(&a_full[slot], (uint32_t)((it / SF_NSLOT) & 1))) {
             fence_proxy_async_smem();
             tc_fence_after();
             const uint64_t adesc = make_sw128_desc(smem_u32(sa + (size_t)slot * SF_SLOT), 1024, 16);
             const uint64_t bdesc = make_sw128_desc(smem_u32(sw + kb1 * (96 * 128)), 1024, 16);
-            mma_bf16x3_ss(tmem_base + SF_TMEM_D, adesc, bdesc, IDESC_M1, kb1 != 0);
+            mma_bf16x3_ss(tmem_base + SF_TMEM_U + (uint32_t)(n1 % SF_NWG) * 128, adesc, bdesc, IDESC_M1, kb1 != 0);
             mma_commit(&a_empty[slot]);
             ++it;
             if (++kb1 == SF_KB) {
               kb1 = 0;
-              mma_commit(&d_ready[n1 & 1]);
+              mma_commit(&d_ready[n1 % SF_NWG]);
               ++n1;
             }
             idle = 0;
           }
         }
-        // QK(nq): Q / K / V tiles of the unit converted; S/P buffer free once PV(nq - 2) has been issued
-        if (nq < n1 && nq - np < 2 && mbar_test(&qkv_full[nq & 1], (uint32_t)((nq >> 1) & 1))) {
+        // QK(nq): Q / K / V tiles of the unit converted (D of the unit, in the same TMEM slot, is dead by then)
+        if (nq < n1 && mbar_test(&qkv_full[nq % SF_NWG], (uint32_t)((nq / SF_NWG) & 1))) {
           fence_proxy_async_smem();
           tc_fence_after();
           const uint32_t qaddr = smem_u32(smem + SF_OFF_Q);
           const uint64_t qdesc = make_sw128_desc(qaddr, 1024, 16);
           const uint64_t kdesc = make_sw128_desc(qaddr + WA_TILE, 1024, 16);
-          mma_bf16x3_ss(tmem_base + SF_TMEM_S + (uint32_t)(nq & 1) * 128, qdesc, kdesc, IDESC_QK, 0u);
-          mma_commit(&s_ready[nq & 1]);
-          mma_commit(&qk_free[nq & 1]);  // the single Q / K tiles may be overwritten by the next unit's conversion
+          mma_bf16x3_ss(tmem_base + SF_TMEM_U + (uint32_t)(nq % SF_NWG) * 128, qdesc, kdesc, IDESC_QK, 0u);
+          mma_commit(&s_ready[nq % SF_NWG]);
+          mma_commit(&qk_free[nq % SF_NWG]);  // the single Q / K tiles may be overwritten by the next unit's conversion
           ++nq;
           idle = 0;
         }
         if (np < nq) {
-          const int tb = (int)(np & 1);
-          const uint32_t k = (uint32_t)(np >> 1);
-          if (mbar_test(&p_ready[tb], k & 1) && mbar_test(&o_free[tb], (k & 1) ^ 1)) {
+          const int sl = (int)(np % SF_NWG), ob = (int)(np & 1);
+          if (mbar_test(&p_ready[sl], (uint32_t)((np / SF_NWG) & 1)) && mbar_test(&o_free[ob], (uint32_t)(((np >> 1) & 1) ^ 1))) {
             tc_fence_after();
-            const uint32_t vaddr = smem_u32(smem + SF_OFF_V + (size_t)tb * WA_TILE);
+            const uint32_t vaddr = smem_u32(smem + SF_OFF_V + (size_t)sl * WA_TILE);
             const uint64_t vdesc = make_sw128_desc(vaddr, 1024, 1024);
-            const uint32_t p_tmem = tmem_base + SF_TMEM_S + tb * 128;
-            const uint32_t o_tmem = tmem_base + SF_TMEM_O + tb * 2 * HD;
+            const uint32_t p_tmem = tmem_base + SF_TMEM_U + sl * 128;
+            const uint32_t o_tmem = tmem_base + SF_TMEM_O + ob * 2 * HD;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
               const uint32_t pc = p_tmem + (kk >> 1) * 32 + (kk & 1) * 8;
               mma_bf16_ts(o_tmem, pc, vdesc + (uint64_t)(kk * 128), IDESC_PV, kk != 0);
               mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);
             }
-            mma_commit(&o_ready[tb]);
-            mma_commit(&v_empty[tb]);
+            mma_commit(&o_ready[sl]);
+            mma_commit(&v_empty[sl]);
             ++np;
             idle = 0;
           }
         }
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4) {
     // ===================================================================== conversion / softmax / epilogue warpgroups
     const int wg = (warp - 4) >> 2;
     const int i = ((warp & 3) << 5) + lane;  // token row of the tile = TMEM lane
     const int half = i >> 6, t = i & 63;
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const float scale = 0.17677669529663687f;  // 32^-0.5
-    const int tb = wg;
-    for (long long u = wg; u < n_units; u += 2) {
-      const uint32_t k = (uint32_t)(u >> 1);
+    const int tb = wg;  // TMEM slot, V tile and barrier index of this warpgroup's units (u % 3 == wg)
+    for (long long u = wg; u < n_units; u += SF_NWG) {
+      const uint32_t k = (uint32_t)(u / SF_NWG);
+      const int ob = (int)(u & 1);
       const uint8_t* meta = smem + SF_OFF_META + (size_t)(u % SF_META_SLOTS) * SF_META_BYTES;
       const int* rows = reinterpret_cast<const int*>(meta);
       const uint8_t* region = meta + 512;
@@ -257,8 +259,8 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
         for (int step = 0; step < 3; ++step) {  // v first (its buffer is free early), then q, k (wait for QK of unit u - 1)
           const int which = step == 0 ? 2 : step - 1;
           if (step == 0) mbar_wait(&v_empty[tb], (k & 1) ^ 1);
-          if (step == 1 && u > 0) mbar_wait(&qk_free[(u - 1) & 1], (uint32_t)(((u - 1) >> 1) & 1));
-          tmem_ld_32x32(lane_base + SF_TMEM_D + which * 32, ra);
+          if (step == 1 && u > 0) mbar_wait(&qk_free[(u - 1) % SF_NWG], (uint32_t)(((u - 1) / SF_NWG) & 1));
+          tmem_ld_32x32(lane_base + SF_TMEM_U + tb * 128 + which * 32, ra);
           tmem_ld_wait();
           float v[32];
 #pragma unroll
@@ -272,10 +274,7 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(d_free);
-          mbar_arrive(&qkv_full[tb]);
-        }
+        if (lane == 0) mbar_arrive(&qkv_full[tb]);
       }
       // ---- softmax (as window_attn.cu)
       mbar_wait(&s_ready[tb], k & 1);
@@ -286,7 +285,7 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
       const uint32_t diff_lo = ~same.x, diff_hi = ~same.y & 0x1FFFFu;
       const bool uniform = (diff_lo | diff_hi) == 0u;
       const float4* brow4 = reinterpret_cast<const float4*>(sb + (t < WT ? t : 0) * WA_BIAS_LD);
-      const uint32_t s_col = lane_base + SF_TMEM_S + tb * 128 + half * 64;
+      const uint32_t s_col = lane_base + SF_TMEM_U + tb * 128 + half * 64;
       tmem_ld_32x32(s_col, ra);
       tmem_ld_32x32(s_col + 32, rb);
       tmem_ld_wait();
@@ -345,7 +344,7 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
       tmem_st_32x32(s_col + 32, rb);
 #pragma unroll
       for (int j = 0; j < 32; ++j) ra[j] = 0u;
-      const uint32_t o_col = lane_base + SF_TMEM_S + tb * 128 + (half ^ 1) * 64;
+      const uint32_t o_col = lane_base + SF_TMEM_U + tb * 128 + (half ^ 1) * 64;
       tmem_st_32x32(o_col, ra);
       tmem_st_32x32(o_col + 32, ra);
       tmem_st_wait();
@@ -355,12 +354,12 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
       // ---- epilogue
       mbar_wait(&o_ready[tb], k & 1);
       tc_fence_after();
-      tmem_ld_32x32(lane_base + SF_TMEM_O + tb * 2 * HD, ra);
-      tmem_ld_32x32(lane_base + SF_TMEM_O + tb * 2 * HD + HD, rb);
+      tmem_ld_32x32(lane_base + SF_TMEM_O + ob * 2 * HD, ra);
+      tmem_ld_32x32(lane_base + SF_TMEM_O + ob * 2 * HD + HD, rb);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_free[tb]);
+      if (lane == 0) mbar_arrive(&o_free[ob]);
       if (t < WT && my_row >= 0) {
         const float inv = 1.0f / sum;
         float o[32];

@@ -129,8 +129,11 @@ class MSDeformAttnPixelDecoder3D(nn.Module):
         for lyr in self.encoder.layers:
             a = lyr.attentions[0]
             ffn = lyr.ffns[0].layers
+            # value_proj rows padded per head to a 128-byte slice (24 -> 32 floats at the reference width): the gather
+            # kernel is bound by the number of distinct lines it touches
+            wv_p, bv_p = ops.pad_head_rows(a.value_proj.weight, a.value_proj.bias, a.num_heads)
             P["layers"].append(dict(
-                wv=sw(a.value_proj.weight), wo=sw(a.output_proj.weight),
+                wv=sw(wv_p), bv=bv_p, wo=sw(a.output_proj.weight),
                 # sampling offsets and attention logits of a token come from ONE GEMM: N = H*L*P*3 + H*L*P
                 wow=sw(torch.cat([a.sampling_offsets.weight.detach().float(), a.attention_weights.weight.detach().float()], 0)),
                 bow=torch.cat([a.sampling_offsets.bias.detach().float(), a.attention_weights.bias.detach().float()], 0).contiguous(),
@@ -188,7 +191,7 @@ class MSDeformAttnPixelDecoder3D(nn.Module):
         nl = len(self.encoder.layers)
         for li, (lyr, W) in enumerate(zip(self.encoder.layers, P["layers"])):
             a, ffn = lyr.attentions[0], lyr.ffns[0].layers
-            v = ops.gemm(x_s, W["wv"], bias=a.value_proj.bias)
+            v = ops.gemm(x_s, W["wv"], bias=W["bv"])
             ow = ops.gemm(xq_s, W["wow"], bias=W["bow"])
             att = ops.ms_deform_attn(v, ow, grids, strides, B, E, H, self.num_points)
             y = ops.gemm(att, W["wo"], bias=a.output_proj.bias, residual=x)

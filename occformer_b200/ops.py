@@ -609,14 +609,31 @@ def neck_token_prep(x, grids, B, ln=None, pos=None, want_f32=True, want_s32=True
 
 
 def ms_deform_attn(value, ow, grids, strides, B, E, H, P):
-    """3-D multi-scale deformable attention core on level-major rows -> (rows, E) in S32."""
+    """3-D multi-scale deformable attention core on level-major rows -> (rows, E) in S32.  value (rows, H * head_ld): head h
+    in columns [h*head_ld, h*head_ld + E/H) -- head_ld = E/H, or E/H rounded up to 32 (``pad_head_rows``)."""
     _chk(value, "value"), _chk(ow, "ow")
-    out = torch.empty_like(value)
+    assert value.shape[1] % H == 0 and value.shape[1] // H >= E // H
+    out = torch.empty(value.shape[0], E, dtype=torch.float32, device=value.device)
     st = (ctypes.c_float * len(strides))(*[float(v) for v in strides])
-    check(lib().occ_ms_deform_attn(_ptr(value), _ptr(ow), _ptr(out), len(grids), B, _grids_arr(grids), st, E, H, P,
-                                   _stream(value)), "occ_ms_deform_attn")
+    check(lib().occ_ms_deform_attn(_ptr(value), value.shape[1], value.shape[1] // H, _ptr(ow), _ptr(out), len(grids), B,
+                                   _grids_arr(grids), st, E, H, P, _stream(value)), "occ_ms_deform_attn")
     LAUNCH_COUNT[0] += 1
     return out
+
+
+def pad_head_rows(w, b, H):
+    """value_proj (E, K) weight / (E,) bias -> (H * hp, K) / (H * hp,) with hp = E/H rounded up to 32 and zero rows in the
+    pad: the projection then writes every head slice into its own 128-byte line (see occ_ms_deform_attn)."""
+    E = w.shape[0]
+    hd = E // H
+    hp = (hd + 31) // 32 * 32
+    if hp == hd:
+        return w.detach().float().contiguous(), b.detach().float().contiguous()
+    wp = torch.zeros(H, hp, w.shape[1], dtype=torch.float32, device=w.device)
+    wp[:, :hd] = w.detach().float().view(H, hd, -1)
+    bp = torch.zeros(H, hp, dtype=torch.float32, device=w.device)
+    bp[:, :hd] = b.detach().float().view(H, hd)
+    return wp.view(H * hp, -1).contiguous(), bp.view(-1).contiguous()
 
 
 def gn_upsample_add(cur, stats, gw, gb, groups, coarse):

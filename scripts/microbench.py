@@ -101,6 +101,16 @@ def main():
         v = torch.randn(Nq, E, device=dev)
         ow = torch.cat([torch.randn(Nq, H * L * P * 3, device=dev) * 1.5, torch.randn(Nq, H * L * P, device=dev)], 1).contiguous()
         res["ms_deform_attn_91250_ms"] = timeit(lambda: ops.ms_deform_attn(v, ow, grids, [16, 8, 4], 1, E, H, P))
+        vp = torch.zeros(Nq, H, 32, device=dev)
+        vp[:, :, :E // H] = v.view(Nq, H, E // H)
+        vp = vp.view(Nq, H * 32)
+        res["ms_deform_attn_91250_padded_heads_ms"] = timeit(lambda: ops.ms_deform_attn(vp, ow, grids, [16, 8, 4], 1, E, H, P))
+        # the FFN pair of one encoder layer (192 -> 768 -> 192) as two GEMMs
+        x_s = ops.to_split(v)
+        w1 = ops.split_weight(torch.randn(4 * E, E) * E ** -0.5).to(dev)
+        w2 = ops.split_weight(torch.randn(E, 4 * E) * (4 * E) ** -0.5).to(dev)
+        b1, b2 = torch.zeros(4 * E, device=dev), torch.zeros(E, device=dev)
+        res["neck_ffn_two_gemms_ms"] = timeit(lambda: ops.gemm(ops.gemm(x_s, w1, bias=b1, act=1, split_out=True), w2, bias=b2, residual=v))
         res["neck_token_prep_ms"] = timeit(lambda: ops.neck_token_prep(v, grids, 1, ln=(torch.ones(E, device=dev), torch.zeros(E, device=dev)),
                                                                    pos=v, want_pos=True))
     if "lift" in which:

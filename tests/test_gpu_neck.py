@@ -44,6 +44,12 @@ def test_ms_deform_attn_core_vs_port(cuda, B):
     ow_rows = lm(torch.cat([off.reshape(B, Nq, -1), logits.reshape(B, Nq, -1)], -1)).to(cuda)
     got = ops.from_split(ops.ms_deform_attn(v_rows, ow_rows, grids, strides, B, E, H, P))
     assert_close(got, lm(want), 2e-5, f"ms_deform_attn core B={B}")
+    # head slices padded to one 128-byte line each (the layout the neck's value_proj writes): same result, bit for bit
+    hd = E // H
+    v_pad = torch.zeros(v_rows.shape[0], H, 32, device=cuda)
+    v_pad[:, :, :hd] = v_rows.view(-1, H, hd)
+    got_p = ops.from_split(ops.ms_deform_attn(v_pad.view(-1, H * 32), ow_rows, grids, strides, B, E, H, P))
+    assert torch.equal(got_p, got)
 
 
 def test_token_prep_and_upsample_add(cuda):
