@@ -297,33 +297,40 @@ gn_upsample_add_kernel(const float* __restrict__ cur, const double* __restrict__
     t = s - (float)i0;
   };
   const float4* cb = reinterpret_cast<const float4*>(coarse + (size_t)b * Xc * Yc * Zc * C);
-  for (long long i4 = v0 * C4 + threadIdx.x; i4 < v1 * C4; i4 += blockDim.x) {
-    const long long r = i4 / C4;
-    const int c4 = (int)(i4 - r * C4);
-    const int z = (int)(r % Z), y = (int)((r / Z) % Y), x = (int)(r / ((long long)Z * Y));
-    const long long row = (long long)b * V + r;
-    const float4 raw = __ldcs(reinterpret_cast<const float4*>(cur + row * C) + c4);
+  // a thread owns one float4 column (scale / shift in registers) and walks voxels: 32-bit index arithmetic per voxel,
+  // 9 independent 16-byte loads in flight
+  const int cols = C4 < 256 ? C4 : 256, rstep = 256 / cols;
+  const int rl = threadIdx.x / cols, cl = threadIdx.x - rl * cols;
+  if (rl >= rstep) return;
+  for (int c4 = cl; c4 < C4; c4 += cols) {
     const float4 a = *reinterpret_cast<const float4*>(sc + 4 * c4), d = *reinterpret_cast<const float4*>(sh + 4 * c4);
-    float4 o = make_float4(fmaf(raw.x, a.x, d.x), fmaf(raw.y, a.y, d.y), fmaf(raw.z, a.z, d.z), fmaf(raw.w, a.w, d.w));
-    int x0, x1, y0, y1, z0, z1;
-    float tx, ty, tz;
-    axis(x, X, Xc, x0, x1, tx);
-    axis(y, Y, Yc, y0, y1, ty);
-    axis(z, Z, Zc, z0, z1, tz);
-    float4 cv[8];
+#pragma unroll 2
+    for (int r = (int)v0 + rl; r < (int)v1; r += rstep) {
+      const int z = r % Z, t2 = r / Z;
+      const int y = t2 % Y, x = t2 / Y;
+      const long long row = (long long)b * V + r;
+      const float4 raw = __ldcs(reinterpret_cast<const float4*>(cur + row * C) + c4);
+      float4 o = make_float4(fmaf(raw.x, a.x, d.x), fmaf(raw.y, a.y, d.y), fmaf(raw.z, a.z, d.z), fmaf(raw.w, a.w, d.w));
+      int x0, x1, y0, y1, z0, z1;
+      float tx, ty, tz;
+      axis(x, X, Xc, x0, x1, tx);
+      axis(y, Y, Yc, y0, y1, ty);
+      axis(z, Z, Zc, z0, z1, tz);
+      float4 cv[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int dz = k & 1, dy = (k >> 1) & 1, dx = k >> 2;
-      cv[k] = __ldg(cb + (((size_t)(dx ? x1 : x0) * Yc + (dy ? y1 : y0)) * Zc + (dz ? z1 : z0)) * C4 + c4);
-    }
+      for (int k = 0; k < 8; ++k) {
+        const int dz = k & 1, dy = (k >> 1) & 1, dx = k >> 2;
+        cv[k] = __ldg(cb + (((size_t)(dx ? x1 : x0) * Yc + (dy ? y1 : y0)) * Zc + (dz ? z1 : z0)) * C4 + c4);
+      }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int dz = k & 1, dy = (k >> 1) & 1, dx = k >> 2;
-      const float wgt = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
-      o.x = fmaf(wgt, cv[k].x, o.x); o.y = fmaf(wgt, cv[k].y, o.y);
-      o.z = fmaf(wgt, cv[k].z, o.z); o.w = fmaf(wgt, cv[k].w, o.w);
+      for (int k = 0; k < 8; ++k) {
+        const int dz = k & 1, dy = (k >> 1) & 1, dx = k >> 2;
+        const float wgt = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
+        o.x = fmaf(wgt, cv[k].x, o.x); o.y = fmaf(wgt, cv[k].y, o.y);
+        o.z = fmaf(wgt, cv[k].z, o.z); o.w = fmaf(wgt, cv[k].w, o.w);
+      }
+      store_split4(out_s + row * C, 4 * c4, o);
     }
-    store_split4(out_s + row * C, 4 * c4, o);
   }
 }
 
@@ -447,6 +454,7 @@ extern "C" int occ_gn_upsample_add(const float* cur, const double* stats, const 
   OCC_REQUIRE(B > 0 && X > 0 && Y > 0 && Z > 0 && Xc > 0 && Yc > 0 && Zc > 0 && C % 32 == 0 && groups > 0 && C % groups == 0);
   OCC_REQUIRE(B <= 65535 && C <= 4096);
   const long long V = (long long)X * Y * Z;
+  OCC_REQUIRE(V < (1ll << 31));
   int vpc = (2048 * 4 + C / 4 - 1) / (C / 4);
   dim3 grid((unsigned)((V + vpc - 1) / vpc), B);
   gn_upsample_add_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(cur, stats, gw, gb, groups, coarse, out_s, X, Y, Z, Xc,

@@ -109,6 +109,18 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// Row gather: four rows r0..r3 of a 2-D tensor (box = {cols, 1}), columns [c0, c0 + box cols), land as four consecutive
+// box rows at dst (swizzled by shared-memory address as usual); rows outside the tensor (negative included) are zero
+// filled and still count their bytes on the mbarrier.
+__device__ __forceinline__ void tma_gather4_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int r0, int r1,
+                                               int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2),
+      "r"(r3)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ TMA stores (shared::cta -> global, bulk async group)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

@@ -8,7 +8,8 @@
 // Work unit = (pair of windows, head), one head per CTA (gridDim.x is a multiple of the head count): the head's 96 x 128
 // slice of the qkv weight (rows [q | k | v] x 32, head-major) stays resident in shared memory for the whole kernel.
 // Per unit:
-//   loaders  (warps 1-3)    cp.async gather of the 128 token rows (49 + 49 real, S32) -> A tile, 4 K-major k-blocks
+//   loader   (warp 1)       window geometry of the unit, then TMA row gathers (tile::gather4: lane l fetches tile rows
+//                           4l..4l+3 of a k-block, pad tokens are out-of-tensor rows = zero fill) -> 4 K-major k-blocks
 //   MMA      (warp 0)       M1: D[128 x 96] = A W_h^T            (4 k-blocks x 6 tcgen05.mma 128x96x16: three bf16 passes)
 //                           QK: S = Q K^T, PV: O' = [P_hi; P_lo][V_hi | V_lo]   (as in window_attn.cu)
 //   three warpgroups (warps 4-7 / 8-11 / 12-15, unit u -> warpgroup u % 3), each running its unit start to end:
@@ -33,7 +34,6 @@ constexpr int SF_W_BYTES = SF_KB * 96 * 128;          // 49152: W_h as 4 K-major
 constexpr int SF_SLOT = 128 * 128;                    // 16384: one k-block of the token tile (128 rows x 128 B)
 constexpr int SF_NSLOT = 5;                           // ring of k-block slots = 1.25 token tiles
 constexpr int SF_NWG = 3;                             // converting warpgroups = units in flight
-constexpr int SF_LOADERS = 96;                        // warps 1-3
 constexpr int SF_META_BYTES = 832;                    // rows int32 (512) + region bytes (128) + same masks (144), padded
 constexpr int SF_META_SLOTS = 8;                      // units u-4 .. u+1 can be live at once (loader ahead, epilogue behind)
 constexpr int SF_OFF_A = SF_W_BYTES;                                    // 49152
@@ -47,7 +47,8 @@ constexpr int SF_SMEM = SF_OFF_BAR + 384 + 1024;                        // 23168
 constexpr uint32_t SF_TMEM_U = 0, SF_TMEM_O = 384;  // unit slots 3 x 128 (D 96 cols -> S -> P), O: 2 x 64
 
 __global__ void __launch_bounds__(WA_THREADS, 1)
-swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const float* __restrict__ wqkv /*(384, 128) S32,
+swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*(rows, 128) S32 tokens, box 32 x 1*/,
+                     const float* __restrict__ wqkv /*(384, 128) S32,
                      head-major rows*/, const float* __restrict__ bqkv /*(384) fp32, head-major*/,
                      const float* __restrict__ bias_pad /*(heads, 2404)*/, float* __restrict__ out, const WinGeom g) {
   extern __shared__ uint8_t smem_raw[];
@@ -94,7 +95,7 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < SF_NSLOT; ++i) {
-      mbar_init(&a_full[i], 2 * SF_LOADERS);  // per loader thread: one cp.async arrival + one release arrival
+      mbar_init(&a_full[i], 1);               // expect_tx by the loader; the 32 row gathers complete the bytes
       mbar_init(&a_empty[i], 1);              // tcgen05.commit after the k-block's MMAs
     }
     for (int i = 0; i < SF_NWG; ++i) {
@@ -117,10 +118,8 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp >= 1 && warp < 4) {
-    // ===================================================================== loaders
-    const int l = threadIdx.x - 32;  // 0..95
-    const int lw = warp - 1;
+  if (warp == 1) {
+    // ===================================================================== loader (one warp: metadata + TMA row gathers)
     long long it = 0;                // running k-block counter -> ring slot / phase
     for (long long u = 0; u < n_units; ++u) {
       const long long pair = pair0 + u * pair_stride;
@@ -128,7 +127,8 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
       int* rows = reinterpret_cast<int*>(meta);
       uint8_t* region = meta + 512;
       uint32_t* same32 = reinterpret_cast<uint32_t*>(meta + 640);
-      for (int rw = lw; rw < 4; rw += 3) {  // 32-row chunk rw of the tile: window rw >> 1, tokens (rw & 1) * 32 + lane
+#pragma unroll 1
+      for (int rw = 0; rw < 4; ++rw) {  // 32-row chunk rw of the tile: window rw >> 1, tokens (rw & 1) * 32 + lane
         const int li = rw * 32 + lane;
         const long long win = 2 * pair + (li >> 6);
         const int t = li & 63;
@@ -149,26 +149,20 @@ swin_qkv_attn_kernel(const float* __restrict__ tokn /*(rows, 128) S32*/, const f
           if (lane == 0) same32[((rw >> 1) * 9 + rg) * 2 + (rw & 1)] = bal;
         }
       }
-      named_bar_sync(2, SF_LOADERS);
+      __syncwarp();
+      // lane l gathers tile rows 4l .. 4l+3: one tile::gather4 per k-block (negative row = outside the tensor = zeros)
+      const int4 rr = *reinterpret_cast<const int4*>(rows + 4 * lane);
 #pragma unroll 1
       for (int kb = 0; kb < SF_KB; ++kb, ++it) {
         const int slot = (int)(it % SF_NSLOT);
-        mbar_wait(&a_empty[slot], (uint32_t)(((it / SF_NSLOT) & 1) ^ 1));
-        uint8_t* dslot = sa + (size_t)slot * SF_SLOT;
-        // 16-byte chunk c of row r of the k-block: 1024 chunks over the 96 loader threads
-#pragma unroll 1
-        for (int idx = l; idx < 128 * 8; idx += SF_LOADERS) {
-          const int r = idx >> 3, c = idx & 7;
-          const int grow = rows[r];
-          uint8_t* dst = dslot + r * 128 + ((c ^ (r & 7)) << 4);
-          if (grow < 0) *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);  // zero token
-          else cp_async_16(dst, tokn + (size_t)grow * SF_C + kb * 32 + c * 4);
+        if (lane == 0) {
+          mbar_wait(&a_empty[slot], (uint32_t)(((it / SF_NSLOT) & 1) ^ 1));
+          mbar_expect_tx(&a_full[slot], SF_SLOT);
         }
-        cp_async_mbar_arrive_noinc(&a_full[slot]);
-        mbar_arrive(&a_full[slot]);
+        __syncwarp();
+        tma_gather4_2d(sa + (size_t)slot * SF_SLOT + lane * 512, &tmap_tok, &a_full[slot], kb * 32, rr.x, rr.y, rr.z, rr.w);
       }
     }
-    cp_async_wait<0>();
   } else if (warp == 0) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
@@ -410,7 +404,14 @@ extern "C" int occ_swin_qkv_attention(const float* tokn, const float* wqkv, cons
   long long groups = sm_count() / heads;
   if (groups > npairs) groups = npairs;
   if (groups < 1) groups = 1;
-  swin_qkv_attn_kernel<<<(int)(groups * heads), WA_THREADS, SF_SMEM, stream>>>(tokn, wqkv, bqkv, bias_pad, out, g);
+  CUtensorMap tm;
+  {
+    const long long rows = g.vox_rows + (long long)B * X * Y;
+    const uint64_t dims[2] = {(uint64_t)SF_C, (uint64_t)rows}, strides[1] = {(uint64_t)SF_C * 4};
+    const uint32_t box[2] = {32, 1};
+    OCC_REQUIRE(make_tmap_f32(&tm, tokn, 2, dims, strides, box, nullptr) == OCC_OK);
+  }
+  swin_qkv_attn_kernel<<<(int)(groups * heads), WA_THREADS, SF_SMEM, stream>>>(tm, wqkv, bqkv, bias_pad, out, g);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

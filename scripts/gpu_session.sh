@@ -19,6 +19,7 @@ for s in "$@"; do
     benchq)  timeout 600 python bench.py --steps 5 --no-cpu-baseline > gpurun_out/benchq.log 2> gpurun_out/benchq.err; echo "benchq rc=$?"; tail -c 3000 gpurun_out/benchq.log; tail -n 5 gpurun_out/benchq.err ;;
     benchref) timeout 900 python bench.py --impl reference --steps 2 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "benchref rc=$?"; tail -n 2 gpurun_out/bench_ref.log ;;
     ktimes)  timeout 600 python scripts/kernel_times.py gpurun_out/kernel_times.md > gpurun_out/kernel_times.log 2>&1; echo "ktimes rc=$?"; head -n 40 gpurun_out/kernel_times.md ;;
+    ktimes4) OCC_BATCH=4 timeout 600 python scripts/kernel_times.py gpurun_out/kernel_times_b4.md > gpurun_out/kernel_times_b4.log 2>&1; echo "ktimes4 rc=$?"; head -n 30 gpurun_out/kernel_times_b4.md ;;
     smoke)   timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 3 gpurun_out/smoke.log ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-1500} -c ${NCU_COUNT:-900} --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?" ;;
     ncupool) timeout 900 ncu --set full --clock-control none --import-source on -k regex:vp_ -s 12 -c 6 -f -o gpurun_out/prof_vp_pool python scripts/microbench.py pool > gpurun_out/ncu_vp_pool.log 2>&1; echo "ncupool rc=$?" ;;

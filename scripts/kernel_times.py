@@ -40,7 +40,7 @@ for e in prof.events():
         t = getattr(e, "device_time", None) or getattr(e, "cuda_time", 0.0)
         seq.append((e.time_range.start, e.name.split("(")[0].replace("void ", "").replace("occ::", "")[:48], t))
 seq.sort()
-with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "kernel_seq.txt"), "w") as f:
+with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "kernel_seq.txt" if BATCH == 1 else f"kernel_seq_b{BATCH}.txt"), "w") as f:
     for _, n, t in seq:
         f.write(f"{t:9.1f}  {n}\n")
 txt = "\n".join(out)
