@@ -122,10 +122,14 @@ int occ_unsplit_rows(const float* in, float* out, long long rows, int C, occ_str
  * Dual-path encoder block glue (P/occformer/backbones/dualpath_block.py:65-82).
  * Token rows: voxel tokens ((b*X+x)*Y+y)*Z+z, then BEV tokens B*X*Y*Z + (b*X+x)*Y+y. */
 /* GroupNorm+ReLU of the raw conv output, Z-mean, LayerNorm1 (dualpath_block.py:43-48,69; window_attention.py:355):
- * tok fp32 (residual), tokn S32 (operand of the QKV GEMM) */
+ * tok fp32 (residual), tokn S32 (operand of the QKV GEMM).
+ * win_shift < 0: tokn rows in token order;  win_shift = 0 / 1 (needs X, XY % X == 0): tokn in the WINDOW LAYOUT of the
+ * un-shifted / shifted 7x7 partition -- token (img, x, y) at row window*64 + t, occ_window_layout_rows() rows in total,
+ * zero-initialised once by the caller (pad positions are never written) -- the operand of occ_swin_qkv_attention. */
 int occ_gn_relu_zmean_ln(const float* y, const double* stats, const float* gn_w, const float* gn_b,
                          const float* ln_w, const float* ln_b, float* tok, float* tokn, int B, int XY, int Z, int C,
-                         int groups, occ_stream_t stream);
+                         int groups, int X, int win_shift, occ_stream_t stream);
+long long occ_window_layout_rows(int B, int X, int Y, int Z);
 int occ_layernorm(const float* in, const float* w, const float* b, float* out, long long rows, int C, int split_out,
                   occ_stream_t stream);
 /* o = act(gn(in[row, c])) (+ residual[row, c]) -- ASPP / neck norms (aspp.py:42-46,117-120,166-172): out[row, c] = o
@@ -160,8 +164,9 @@ int occ_window_attention(const float* qkv /*S32*/, const float* qkv_bias /*S32 r
                          float* out /*S32*/, int B, int X, int Y, int Z, int C, int heads, int shift,
                          int qkv_head_major, occ_stream_t stream);
 
-/* The same attention with the QKV projection fused in (C == 128; csrc/swin_attn_fused.cu): tokn (rows, 128) S32 =
- * LayerNorm1'ed tokens, wqkv (384, 128) S32 / bqkv (384) fp32 = WindowMSA.qkv with HEAD-MAJOR rows [head][q|k|v][32]; the
+/* The same attention with the QKV projection fused in (C == 128; csrc/swin_attn_fused.cu): tokn
+ * (occ_window_layout_rows(B,X,Y,Z), 128) S32 = LayerNorm1'ed tokens in the window layout of THIS shift (see
+ * occ_gn_relu_zmean_ln), out (B*X*Y*(Z+1), 128) S32 in token order; wqkv (384, 128) S32 / bqkv (384) fp32 = WindowMSA.qkv with HEAD-MAJOR rows [head][q|k|v][32]; the
  * q/k/v tensor never exists in HBM.  Returns -2 for C != 128 (use occ_gemm_bf16x3 + occ_window_attention). */
 int occ_swin_qkv_attention(const float* tokn, const float* wqkv, const float* bqkv, const float* bias_pad, float* out,
                            int B, int X, int Y, int Z, int C, int heads, int shift, occ_stream_t stream);

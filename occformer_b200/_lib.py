@@ -32,7 +32,8 @@ SIGNATURES = {
     "occ_conv_taps_bf16x3": (c_int, [P, P, P] + [c_int] * 7 + [P, P, c_int, STREAM]),
     "occ_split_rows": (c_int, [P, P, c_longlong, c_int, STREAM]),
     "occ_unsplit_rows": (c_int, [P, P, c_longlong, c_int, STREAM]),
-    "occ_gn_relu_zmean_ln": (c_int, [P] * 8 + [c_int] * 5 + [STREAM]),
+    "occ_gn_relu_zmean_ln": (c_int, [P] * 8 + [c_int] * 7 + [STREAM]),
+    "occ_window_layout_rows": (c_longlong, [c_int] * 4),
     "occ_layernorm": (c_int, [P, P, P, P, c_longlong, c_int, c_int, STREAM]),
     "occ_gn_apply": (c_int, [P] * 7 + [c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, STREAM]),
     "occ_aspp_gap_branch": (c_int, [P] * 6 + [c_int] * 6 + [STREAM]),

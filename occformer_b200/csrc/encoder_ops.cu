@@ -8,6 +8,7 @@
 // disappear: every one of the B*(Z+1) images is addressed in place.
 #include "occ_common.cuh"
 #include "occ_ptx.cuh"
+#include "window_geom.cuh"
 
 namespace occ {
 
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(512)
 gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gn_w,
                         const float* __restrict__ gn_b, const float* __restrict__ ln_w,
                         const float* __restrict__ ln_b, float* __restrict__ tok, float* __restrict__ tokn, int B,
-                        int XY, int Z, int C, int groups, int cols) {
+                        int XY, int Z, int C, int groups, int cols, const WinGeom wg, int win_layout) {
   extern __shared__ float col_smem[];  // [cols][Z][C]
   __shared__ float s_mean[16][32], s_rstd[16][32];  // GroupNorm mean / rstd per (column of this CTA, group): the fp64
                                                     // division + sqrt runs once per CTA, not once per lane and row
@@ -118,8 +119,13 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       warp_layernorm<NV>(v[r], C, ln_w, ln_b, lane);
+      long long orow = row0 + r;
+      if (win_layout) {  // tokn in window layout (operand of the fused QKV + attention kernel)
+        const int b = (int)(col / XY), xy = (int)(col - (long long)b * XY);
+        orow = window_layout_row(wg, b * Z + z0 + r, xy / wg.Y, xy % wg.Y);
+      }
 #pragma unroll
-      for (int i = 0; i < NV; ++i) store_split4(tokn + (row0 + r) * C, (i * 32 + lane) * 4, v[r][i]);
+      for (int i = 0; i < NV; ++i) store_split4(tokn + orow * C, (i * 32 + lane) * 4, v[r][i]);
     }
   }
   __syncthreads();
@@ -139,8 +145,13 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
       *reinterpret_cast<float4*>(tok + brow * C + c0) = a;
     }
     warp_layernorm<NV>(v[0], C, ln_w, ln_b, lane);
+    long long orow = brow;
+    if (win_layout) {
+      const int b = (int)(col / XY), xy = (int)(col - (long long)b * XY);
+      orow = window_layout_row(wg, B * Z + b, xy / wg.Y, xy % wg.Y);
+    }
 #pragma unroll
-    for (int i = 0; i < NV; ++i) store_split4(tokn + brow * C, (i * 32 + lane) * 4, v[0][i]);
+    for (int i = 0; i < NV; ++i) store_split4(tokn + orow * C, (i * 32 + lane) * 4, v[0][i]);
   }
 }
 
@@ -452,8 +463,13 @@ using namespace occ;
 
 extern "C" int occ_gn_relu_zmean_ln(const float* y, const double* stats, const float* gn_w, const float* gn_b,
                                     const float* ln_w, const float* ln_b, float* tok, float* tokn, int B, int XY,
-                                    int Z, int C, int groups, cudaStream_t stream) {
+                                    int Z, int C, int groups, int X, int win_shift, cudaStream_t stream) {
   OCC_REQUIRE(y && stats && gn_w && gn_b && ln_w && ln_b && tok && tokn);
+  // win_shift < 0: tokn in token order (rows as tok); 0 / 1: tokn in the window layout of the un-shifted / shifted
+  // partition (occ_swin_qkv_attention's operand; the buffer must be zero where no token lands: occ_window_layout_rows)
+  OCC_REQUIRE(win_shift < 0 || (X > 0 && XY % X == 0));
+  const WinGeom wg = make_win_geom(B, win_shift < 0 ? 1 : X, win_shift < 0 ? XY : XY / X, Z, C, C / HD, win_shift > 0);
+  const int wl = win_shift >= 0;
   OCC_REQUIRE(B > 0 && XY > 0 && Z > 0 && Z <= 16 && C % 128 == 0 && groups > 0 && groups <= 32 && C % groups == 0 &&
               (C / groups) % 4 == 0);
   // rows per warp: 4 for the narrow (C = 128) stage when Z allows it, else 1; 16 warps per CTA where possible
@@ -471,10 +487,10 @@ extern "C" int occ_gn_relu_zmean_ln(const float* y, const double* stats, const f
   OCC_REQUIRE(threads <= 512);
   if (R == 4) {
     gn_relu_zmean_ln_kernel<1, 4><<<blocks, threads, smem, stream>>>(y, stats, gn_w, gn_b, ln_w, ln_b, tok, tokn, B, XY, Z,
-                                                                     C, groups, cols);
+                                                                     C, groups, cols, wg, wl);
   } else {
     DISPATCH_NV(C, (gn_relu_zmean_ln_kernel<NV, 1><<<blocks, threads, smem, stream>>>(y, stats, gn_w, gn_b, ln_w, ln_b, tok,
-                                                                                    tokn, B, XY, Z, C, groups, cols)));
+                                                                                    tokn, B, XY, Z, C, groups, cols, wg, wl)));
   }
   OCC_LAUNCH_CHECK();
   return OCC_OK;
@@ -573,4 +589,13 @@ extern "C" int occ_unsplit_rows(const float* in, float* out, long long rows, int
   unsplit_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(in, out, n4, C);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
+}
+
+// Rows of the window-layout token buffer for a (B, X, Y, Z) grid: one 128-row tile per pair of 7x7 windows over the
+// B * (Z + 1) X-Y images (voxel slices, then the BEV image).  The buffer must be zero-initialised once: window pad
+// positions and rows 49..63 of every window are never written.
+extern "C" long long occ_window_layout_rows(int B, int X, int Y, int Z) {
+  if (B <= 0 || X <= 0 || Y <= 0 || Z <= 0) return -1;
+  const WinGeom g = make_win_geom(B, X, Y, Z, 128, 4, 0);
+  return (g.nwin + 1) / 2 * 128;
 }

@@ -8,8 +8,11 @@
 // Work unit = (pair of windows, head), one head per CTA (gridDim.x is a multiple of the head count): the head's 96 x 128
 // slice of the qkv weight (rows [q | k | v] x 32, head-major) stays resident in shared memory for the whole kernel.
 // Per unit:
-//   loader   (warp 1)       window geometry of the unit, then TMA row gathers (tile::gather4: lane l fetches tile rows
-//                           4l..4l+3 of a k-block, pad tokens are out-of-tensor rows = zero fill) -> 4 K-major k-blocks
+//   loader   (warp 1)       window geometry of the unit (row / region metadata for the softmax and the output scatter) and
+//                           one TMA box (32 channels x 128 rows) per k-block: the tokens arrive in WINDOW LAYOUT
+//                           (window_geom.cuh: the LayerNorm producer writes token (img, x, y) to row window * 64 + t),
+//                           so a pair of windows is a contiguous tile.  (Per-row gathers -- cp.async or tile::gather4,
+//                           ~110 cycles per 512-byte gather4 -- could not feed the MMAs: r02_ncu_swin_qkv_attn_v3/v4.)
 //   MMA      (warp 0)       M1: D[128 x 96] = A W_h^T            (4 k-blocks x 6 tcgen05.mma 128x96x16: three bf16 passes)
 //                           QK: S = Q K^T, PV: O' = [P_hi; P_lo][V_hi | V_lo]   (as in window_attn.cu)
 //   three warpgroups (warps 4-7 / 8-11 / 12-15, unit u -> warpgroup u % 3), each running its unit start to end:
@@ -47,7 +50,7 @@ constexpr int SF_SMEM = SF_OFF_BAR + 384 + 1024;                        // 23168
 constexpr uint32_t SF_TMEM_U = 0, SF_TMEM_O = 384;  // unit slots 3 x 128 (D 96 cols -> S -> P), O: 2 x 64
 
 __global__ void __launch_bounds__(WA_THREADS, 1)
-swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*(rows, 128) S32 tokens, box 32 x 1*/,
+swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*window-layout tokens (npairs*128, 128) S32, box 32 x 128*/,
                      const float* __restrict__ wqkv /*(384, 128) S32,
                      head-major rows*/, const float* __restrict__ bqkv /*(384) fp32, head-major*/,
                      const float* __restrict__ bias_pad /*(heads, 2404)*/, float* __restrict__ out, const WinGeom g) {
@@ -150,17 +153,15 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*(rows, 128) 
         }
       }
       __syncwarp();
-      // lane l gathers tile rows 4l .. 4l+3: one tile::gather4 per k-block (negative row = outside the tensor = zeros)
-      const int4 rr = *reinterpret_cast<const int4*>(rows + 4 * lane);
+      // the pair's 128 token rows are one tile of the window-layout buffer: one TMA box per k-block
 #pragma unroll 1
       for (int kb = 0; kb < SF_KB; ++kb, ++it) {
         const int slot = (int)(it % SF_NSLOT);
         if (lane == 0) {
           mbar_wait(&a_empty[slot], (uint32_t)(((it / SF_NSLOT) & 1) ^ 1));
           mbar_expect_tx(&a_full[slot], SF_SLOT);
+          tma_load_2d(sa + (size_t)slot * SF_SLOT, &tmap_tok, &a_full[slot], kb * 32, (int)(pair * 128));
         }
-        __syncwarp();
-        tma_gather4_2d(sa + (size_t)slot * SF_SLOT + lane * 512, &tmap_tok, &a_full[slot], kb * 32, rr.x, rr.y, rr.z, rr.w);
       }
     }
   } else if (warp == 0) {
@@ -379,7 +380,8 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*(rows, 128) 
 
 using namespace occ;
 
-// tokn (rows, 128) S32 = LayerNorm1'ed tokens (rows = B*X*Y*(Z+1), voxel tokens then BEV tokens); wqkv (384, 128) S32 and
+// tokn (occ_window_layout_rows(B,X,Y,Z), 128) S32 = LayerNorm1'ed tokens in the WINDOW LAYOUT of this block's partition
+// (shift), zero where no token lands (occ_gn_relu_zmean_ln with win_shift = shift writes it); wqkv (384, 128) S32 and
 // bqkv (384) fp32 with HEAD-MAJOR rows [head][q|k|v][32]; bias_pad as occ_window_attention; out (rows, 128) S32.
 // Returns -2 (unsupported) for C != 128: the caller then runs occ_gemm_bf16x3 + occ_window_attention.
 extern "C" int occ_swin_qkv_attention(const float* tokn, const float* wqkv, const float* bqkv, const float* bias_pad,
@@ -390,13 +392,7 @@ extern "C" int occ_swin_qkv_attention(const float* tokn, const float* wqkv, cons
   if (C != SF_C) return OCC_EUNSUPPORTED;
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(tokn) & 15) == 0 && (reinterpret_cast<uintptr_t>(wqkv) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(bias_pad) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  WinGeom g;
-  g.B = B; g.X = X; g.Y = Y; g.Z = Z; g.C = C; g.heads = heads; g.shift = shift ? 1 : 0;
-  g.head_major = 1;
-  g.nWx = (X + WS - 1) / WS; g.nWy = (Y + WS - 1) / WS;
-  g.Xp = g.nWx * WS; g.Yp = g.nWy * WS;
-  g.vox_rows = (long long)B * X * Y * Z;
-  g.nwin = (long long)B * (Z + 1) * g.nWx * g.nWy;
+  const WinGeom g = make_win_geom(B, X, Y, Z, C, heads, shift);
   OCC_REQUIRE(g.nwin < (1ll << 31));
   static_assert(SF_SMEM <= 227 * 1024, "shared memory budget");
   OCC_ENSURE_SMEM(swin_qkv_attn_kernel, SF_SMEM);
@@ -406,9 +402,9 @@ extern "C" int occ_swin_qkv_attention(const float* tokn, const float* wqkv, cons
   if (groups < 1) groups = 1;
   CUtensorMap tm;
   {
-    const long long rows = g.vox_rows + (long long)B * X * Y;
+    const long long rows = (g.nwin + 1) / 2 * 128;  // occ_window_layout_rows
     const uint64_t dims[2] = {(uint64_t)SF_C, (uint64_t)rows}, strides[1] = {(uint64_t)SF_C * 4};
-    const uint32_t box[2] = {32, 1};
+    const uint32_t box[2] = {32, 128};
     OCC_REQUIRE(make_tmap_f32(&tm, tokn, 2, dims, strides, box, nullptr) == OCC_OK);
   }
   swin_qkv_attn_kernel<<<(int)(groups * heads), WA_THREADS, SF_SMEM, stream>>>(tm, wqkv, bqkv, bias_pad, out, g);

@@ -54,4 +54,30 @@ __device__ __forceinline__ long long window_token_row(const WinGeom& g, int img,
   return g.vox_rows + ((long long)b * g.X + x) * g.Y + y;
 }
 
+// Inverse of window_token_row for real tokens: token (img, x, y) -> row of the WINDOW-LAYOUT buffer, window * 64 + t (the
+// 49 tokens of a window are 49 consecutive rows, windows are 64 rows apart, rows 49..63 stay zero; a pair of windows is
+// one 128-row MMA tile that a single TMA box fetches).  Window pad tokens (positions >= X or >= Y of the padded image)
+// have no source token: their rows are never written and stay zero.
+__device__ __forceinline__ long long window_layout_row(const WinGeom& g, int img, int x, int y) {
+  int xs = x, ys = y;
+  if (g.shift) {
+    xs = x - 3; if (xs < 0) xs += g.Xp;
+    ys = y - 3; if (ys < 0) ys += g.Yp;
+  }
+  const int wx = xs / WS, wy = ys / WS;
+  const int t = (xs - wx * WS) * WS + (ys - wy * WS);
+  return (((long long)img * g.nWx + wx) * g.nWy + wy) * 64 + t;
+}
+
+inline WinGeom make_win_geom(int B, int X, int Y, int Z, int C, int heads, int shift) {
+  WinGeom g;
+  g.B = B; g.X = X; g.Y = Y; g.Z = Z; g.C = C; g.heads = heads; g.shift = shift ? 1 : 0;
+  g.head_major = 1;
+  g.nWx = (X + WS - 1) / WS; g.nWy = (Y + WS - 1) / WS;
+  g.Xp = g.nWx * WS; g.Yp = g.nWy * WS;
+  g.vox_rows = (long long)B * X * Y * Z;
+  g.nwin = (long long)B * (Z + 1) * g.nWx * g.nWy;
+  return g;
+}
+
 }  // namespace occ

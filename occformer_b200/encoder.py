@@ -208,8 +208,9 @@ class DualpathTransformerBlock(nn.Module):
         nvox = B * XY * Z
         ic, sw = self.input_conv, self.bev_encoder
         # (A4/A5/A6) GN + ReLU, Z-mean BEV token, LayerNorm1 -- one pass; tok fp32 (residual), tokn S32 (GEMM operand)
+        # (at C == 128 tokn is written straight into the window layout the fused attention kernel loads by TMA)
         tok, tokn = ops.gn_relu_zmean_ln(y_raw.view(nvox, C), stats[0], ic[1].weight, ic[1].bias, sw.norm1.weight,
-                                         sw.norm1.bias, B, XY, Z, C, G)
+                                         sw.norm1.bias, B, XY, Z, C, G, X=X, win_shift=self.shift if C == 128 else None)
         msa = sw.attn.w_msa
         if C == 128:
             # (A7/A8) QKV projection + shifted-window attention in one kernel: the qkv tensor never exists in HBM

@@ -319,12 +319,62 @@ def conv_taps(x_cl, w2, taps, gn_stats=None, cpg=0):
 
 
 # ----------------------------------------------------------------------------------------------- encoder glue
-def gn_relu_zmean_ln(y, stats, gn_w, gn_b, ln_w, ln_b, B, XY, Z, C, groups):
+_WL = {}
+
+
+def window_layout_buffer(B, X, Y, Z, C, shift, device):
+    """Zero-initialised window-layout token buffer (occ_window_layout_rows, C), cached per (grid, shift, device, stream):
+    the producer overwrites exactly the rows of real tokens on every call, the pad rows stay zero for ever."""
+    key = (B, X, Y, Z, C, int(bool(shift)), str(device), torch.cuda.current_stream(device).cuda_stream)
+    buf = _WL.get(key)
+    if buf is None:
+        rows = lib().occ_window_layout_rows(B, X, Y, Z)
+        assert rows > 0
+        buf = _WL[key] = torch.zeros((rows, C), dtype=torch.float32, device=device)
+    return buf
+
+
+def window_layout_index(B, X, Y, Z, shift):
+    """Token row (voxel tokens, then BEV tokens) -> row of the window-layout buffer, as an int64 tensor (host arithmetic,
+    independent of the kernels: tests and callers that hold token-ordered rows)."""
+    WS = 7
+    nWx, nWy = (X + WS - 1) // WS, (Y + WS - 1) // WS
+    Xp, Yp = nWx * WS, nWy * WS
+    x = torch.arange(X).view(X, 1)
+    y = torch.arange(Y).view(1, Y)
+    xs, ys = ((x - 3) % Xp, (y - 3) % Yp) if shift else (x, y)
+    win_xy = (xs // WS) * nWy + (ys // WS)              # (X, Y)
+    t = (xs % WS) * WS + (ys % WS)                      # (X, Y)
+    b = torch.arange(B).view(B, 1, 1, 1)
+    z = torch.arange(Z).view(1, 1, 1, Z)
+    img = b * Z + z                                     # voxel slice image index
+    vox = (img * (nWx * nWy) + win_xy.view(1, X, Y, 1)) * 64 + t.view(1, X, Y, 1)        # (B, X, Y, Z)
+    bev = ((B * Z + torch.arange(B).view(B, 1, 1)) * (nWx * nWy) + win_xy.view(1, X, Y)) * 64 + t.view(1, X, Y)
+    return torch.cat([vox.reshape(-1), bev.reshape(-1)]).long()
+
+
+def to_window_layout(tokn_s, B, X, Y, Z, shift):
+    """token-ordered (rows, C) rows -> window-layout buffer (fresh tensor)"""
+    rows = lib().occ_window_layout_rows(B, X, Y, Z)
+    out = torch.zeros((rows, tokn_s.shape[1]), dtype=tokn_s.dtype, device=tokn_s.device)
+    out[window_layout_index(B, X, Y, Z, shift).to(tokn_s.device)] = tokn_s
+    return out
+
+
+def gn_relu_zmean_ln(y, stats, gn_w, gn_b, ln_w, ln_b, B, XY, Z, C, groups, X=0, win_shift=None):
+    """-> tok (fp32, token order), tokn (S32): token order, or -- win_shift = 0 / 1 -- the window layout of that partition
+    (operand of swin_qkv_attention)."""
     rows = B * XY * (Z + 1)
     tok = torch.empty((rows, C), dtype=torch.float32, device=y.device)
-    tokn = torch.empty((rows, C), dtype=torch.float32, device=y.device)
+    if win_shift is None:
+        tokn = torch.empty((rows, C), dtype=torch.float32, device=y.device)
+        ws = -1
+    else:
+        assert X > 0 and XY % X == 0
+        tokn = window_layout_buffer(B, X, XY // X, Z, C, win_shift, y.device)
+        ws = int(bool(win_shift))
     check(lib().occ_gn_relu_zmean_ln(_ptr(y), _ptr(stats), _ptr(gn_w), _ptr(gn_b), _ptr(ln_w), _ptr(ln_b), _ptr(tok),
-                                     _ptr(tokn), B, XY, Z, C, groups, _stream()), "occ_gn_relu_zmean_ln")
+                                     _ptr(tokn), B, XY, Z, C, groups, X, ws, _stream()), "occ_gn_relu_zmean_ln")
     LAUNCH_COUNT[0] += 1
     return tok, tokn
 
@@ -409,15 +459,16 @@ def window_attention(qkv, qkv_bias, bias_pad, B, X, Y, Z, C, heads, shift, head_
     return out
 
 
-def swin_qkv_attention(tokn, w_qkv, b_qkv, bias_pad, B, X, Y, Z, C, heads, shift):
-    """QKV projection + (shifted) window attention in one kernel (C == 128): tokn (rows, C) S32, w_qkv (3C, C) S32 and
-    b_qkv (3C,) fp32 with head-major rows -> attention output (rows, C) S32."""
-    _chk(tokn, "tokn"), _chk(w_qkv, "w_qkv"), _chk(b_qkv, "b_qkv")
+def swin_qkv_attention(tokn_wl, w_qkv, b_qkv, bias_pad, B, X, Y, Z, C, heads, shift):
+    """QKV projection + (shifted) window attention in one kernel (C == 128): tokn_wl (window_layout rows, C) S32 in the
+    window layout of ``shift`` (gn_relu_zmean_ln(win_shift=shift) / to_window_layout), w_qkv (3C, C) S32 and b_qkv (3C,)
+    fp32 with head-major rows -> attention output (B*X*Y*(Z+1), C) S32 in token order."""
+    _chk(tokn_wl, "tokn_wl"), _chk(w_qkv, "w_qkv"), _chk(b_qkv, "b_qkv")
     rows = B * X * Y * (Z + 1)
-    assert tokn.shape == (rows, C) and w_qkv.shape == (3 * C, C)
-    out = torch.empty((rows, C), dtype=torch.float32, device=tokn.device)
-    check(lib().occ_swin_qkv_attention(_ptr(tokn), _ptr(w_qkv), _ptr(b_qkv), _ptr(bias_pad), _ptr(out), B, X, Y, Z, C, heads,
-                                       int(shift), _stream(tokn)), "occ_swin_qkv_attention")
+    assert tokn_wl.shape == (lib().occ_window_layout_rows(B, X, Y, Z), C) and w_qkv.shape == (3 * C, C)
+    out = torch.empty((rows, C), dtype=torch.float32, device=tokn_wl.device)
+    check(lib().occ_swin_qkv_attention(_ptr(tokn_wl), _ptr(w_qkv), _ptr(b_qkv), _ptr(bias_pad), _ptr(out), B, X, Y, Z, C, heads,
+                                       int(shift), _stream(tokn_wl)), "occ_swin_qkv_attention")
     LAUNCH_COUNT[0] += 1
     return out
 

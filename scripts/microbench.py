@@ -83,7 +83,9 @@ def main():
         bias_pad = torch.randn(heads, 2404, device=dev) * 0.1
         qkv = ops.gemm(tokn, wq, bias=bq, split_out=True)
         res["window_attn_tc_ms"] = timeit(lambda: ops.window_attention(qkv, bqs, bias_pad, 1, X, Y, Z, C, heads, True, head_major=True))
-        res["swin_qkv_attn_fused_ms"] = timeit(lambda: ops.swin_qkv_attention(tokn, wq, bq, bias_pad, 1, X, Y, Z, C, heads, True))
+        tokn_wl = ops.to_window_layout(tokn, 1, X, Y, Z, True)
+        res["swin_qkv_attn_fused_ms"] = timeit(lambda: ops.swin_qkv_attention(tokn_wl, wq, bq, bias_pad, 1, X, Y, Z, C, heads, True))
+        del tokn_wl
         del qkv, tokn
     if "tail" in which:
         M = rows

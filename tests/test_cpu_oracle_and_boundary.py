@@ -289,3 +289,38 @@ def test_class_guided_sampling_host_functions():
     lidar = [torch.cat([torch.rand(30, 3) * 20 - 10, torch.ones(30, 1)], 1)]
     c = S.get_nusc_lidarseg_point_coords(torch.randn(2, 1, *shape), lidar, [gt_labels], 40, 3.0, 0.75, [-10, -10, -10, 10, 10, 10])
     assert c.shape == (2, 40, 3)
+
+
+def test_window_layout_index_matches_window_token_row():
+    """ops.window_layout_index (token row -> row of the window-layout buffer the fused attention kernel loads by TMA) is the
+    inverse of the window -> token map of ShiftWindowMSA (window_attention.py:168-242: pad, roll by -3, 7x7 partition),
+    restated here window by window."""
+    import torch
+    from occformer_b200 import ops
+
+    def brute(B, X, Y, Z, shift):
+        nWx, nWy = (X + 6) // 7, (Y + 6) // 7
+        Xp, Yp = nWx * 7, nWy * 7
+        out = torch.full((B * X * Y * (Z + 1),), -1, dtype=torch.long)
+        for img in range(B * (Z + 1)):
+            for wx in range(nWx):
+                for wy in range(nWy):
+                    for t in range(49):
+                        i, j = divmod(t, 7)
+                        x, y = wx * 7 + i, wy * 7 + j
+                        if shift:
+                            x, y = (x + 3) % Xp, (y + 3) % Yp
+                        if x >= X or y >= Y:
+                            continue
+                        if img < B * Z:
+                            b, z = divmod(img, Z)
+                            r = ((b * X + x) * Y + y) * Z + z
+                        else:
+                            r = B * X * Y * Z + ((img - B * Z) * X + x) * Y + y
+                        out[r] = ((img * nWx + wx) * nWy + wy) * 64 + t
+        return out
+
+    for cfg in [(1, 14, 7, 1, False), (1, 10, 16, 2, True), (2, 15, 10, 4, False), (1, 33, 40, 3, True)]:
+        got = ops.window_layout_index(*cfg)
+        assert torch.equal(got, brute(*cfg)), cfg
+        assert got.unique().numel() == got.numel()

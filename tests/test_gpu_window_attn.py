@@ -75,7 +75,9 @@ def test_fused_qkv_window_attention_vs_oracle(cuda, B, X, Y, Z, shift):
     w_hm = ops.split_weight(sd["w_msa.qkv.weight"][perm]).to(cuda)
     b_hm = sd["w_msa.qkv.bias"][perm].contiguous().to(cuda)
     tokn = ops.to_split(rows.to(cuda))
-    out_s = ops.swin_qkv_attention(tokn, w_hm, b_hm, bias_pad, B, X, Y, Z, C, heads, shift)
+    # the kernel's operand is the window layout of this shift; to_window_layout is host index arithmetic, independent of
+    # the device-side mapping in window_geom.cuh (which the encoder tests exercise through occ_gn_relu_zmean_ln)
+    out_s = ops.swin_qkv_attention(ops.to_window_layout(tokn, B, X, Y, Z, shift), w_hm, b_hm, bias_pad, B, X, Y, Z, C, heads, shift)
     ref_rows = _rows_from_images(ref, B, X, Y, Z)
     assert_close(ops.from_split(out_s), ref_rows, 1e-4, f"fused qkv+window attention B{B} {X}x{Y}x{Z} shift={shift}")
     qkv = ops.gemm(tokn, w_hm, bias=b_hm, split_out=True)
