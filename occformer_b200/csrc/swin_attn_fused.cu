@@ -37,16 +37,15 @@ constexpr int SF_W_BYTES = SF_KB * 96 * 128;          // 49152: W_h as 4 K-major
 constexpr int SF_SLOT = 128 * 128;                    // 16384: one k-block of the token tile (128 rows x 128 B)
 constexpr int SF_NSLOT = 5;                           // ring of k-block slots = 1.25 token tiles
 constexpr int SF_NWG = 3;                             // converting warpgroups = units in flight
-constexpr int SF_META_BYTES = 832;                    // rows int32 (512) + region bytes (128) + same masks (144), padded
-constexpr int SF_META_SLOTS = 8;                      // units u-4 .. u+1 can be live at once (loader ahead, epilogue behind)
+constexpr int SF_SAME_BYTES = 192;                    // per warpgroup: 2 window halves x 9 regions x 64-bit key masks (144), padded
 constexpr int SF_OFF_A = SF_W_BYTES;                                    // 49152
 constexpr int SF_OFF_Q = SF_OFF_A + SF_NSLOT * SF_SLOT;                 // 131072: Q tile, then K tile (single buffered)
 constexpr int SF_OFF_V = SF_OFF_Q + 2 * WA_TILE;                        // 163840: V tiles (one per warpgroup)
 constexpr int SF_OFF_BIAS = SF_OFF_V + SF_NWG * WA_TILE;                     // 212992: relative-position bias (49, 52) * log2 e
 constexpr int SF_OFF_QB = SF_OFF_BIAS + WA_BIAS_BYTES;                  // 223232: this head's 96 qkv bias values
-constexpr int SF_OFF_META = SF_OFF_QB + 384;                            // 223616
-constexpr int SF_OFF_BAR = SF_OFF_META + SF_META_SLOTS * SF_META_BYTES; // 230272
-constexpr int SF_SMEM = SF_OFF_BAR + 384 + 1024;                        // 231680 <= 232448 (227 KB)
+constexpr int SF_OFF_SAME = SF_OFF_QB + 384;                            // 223616
+constexpr int SF_OFF_BAR = SF_OFF_SAME + SF_NWG * SF_SAME_BYTES;        // 224192
+constexpr int SF_SMEM = SF_OFF_BAR + 384 + 1024;                        // 225600 <= 232448 (227 KB)
 constexpr uint32_t SF_TMEM_U = 0, SF_TMEM_O = 384;  // unit slots 3 x 128 (D 96 cols -> S -> P), O: 2 x 64
 
 __global__ void __launch_bounds__(WA_THREADS, 1)
@@ -122,112 +121,95 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*window-layou
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 1) {
-    // ===================================================================== loader (one warp: metadata + TMA row gathers)
-    long long it = 0;                // running k-block counter -> ring slot / phase
-    for (long long u = 0; u < n_units; ++u) {
-      const long long pair = pair0 + u * pair_stride;
-      uint8_t* meta = smem + SF_OFF_META + (size_t)(u % SF_META_SLOTS) * SF_META_BYTES;
-      int* rows = reinterpret_cast<int*>(meta);
-      uint8_t* region = meta + 512;
-      uint32_t* same32 = reinterpret_cast<uint32_t*>(meta + 640);
+    // ===================================================================== loader: one TMA box per k-block
+    if (lane == 0) {
+      uint32_t slot = 0, par = 1;  // parity of the "slot is empty" phase to wait for (fresh barriers pass parity 1)
+      for (uint32_t u = 0; u < (uint32_t)n_units; ++u) {
+        const int row0 = (int)((pair0 + (long long)u * pair_stride) * 128);
 #pragma unroll 1
-      for (int rw = 0; rw < 4; ++rw) {  // 32-row chunk rw of the tile: window rw >> 1, tokens (rw & 1) * 32 + lane
-        const int li = rw * 32 + lane;
-        const long long win = 2 * pair + (li >> 6);
-        const int t = li & 63;
-        int my_reg = 0;
-        long long r = -2;  // -2: MMA padding row, -1: window pad token (zero token: q/k/v = bias)
-        if (t < WT && win < g.nwin) {
-          long long w = win;
-          const int wy = (int)(w % g.nWy); w /= g.nWy;
-          const int wx = (int)(w % g.nWx); w /= g.nWx;
-          r = window_token_row(g, (int)w, wx, wy, t, &my_reg);
-        }
-        rows[li] = (int)r;
-        region[li] = (uint8_t)my_reg;
-        const bool tok = t < WT;
-#pragma unroll
-        for (int rg = 0; rg < 9; ++rg) {
-          const uint32_t bal = __ballot_sync(0xffffffffu, tok && my_reg == rg);
-          if (lane == 0) same32[((rw >> 1) * 9 + rg) * 2 + (rw & 1)] = bal;
-        }
-      }
-      __syncwarp();
-      // the pair's 128 token rows are one tile of the window-layout buffer: one TMA box per k-block
-#pragma unroll 1
-      for (int kb = 0; kb < SF_KB; ++kb, ++it) {
-        const int slot = (int)(it % SF_NSLOT);
-        if (lane == 0) {
-          mbar_wait(&a_empty[slot], (uint32_t)(((it / SF_NSLOT) & 1) ^ 1));
+        for (int kb = 0; kb < SF_KB; ++kb) {
+          mbar_wait(&a_empty[slot], par);
           mbar_expect_tx(&a_full[slot], SF_SLOT);
-          tma_load_2d(sa + (size_t)slot * SF_SLOT, &tmap_tok, &a_full[slot], kb * 32, (int)(pair * 128));
+          tma_load_2d(sa + (size_t)slot * SF_SLOT, &tmap_tok, &a_full[slot], kb * 32, row0);
+          if (++slot == SF_NSLOT) { slot = 0; par ^= 1; }
         }
       }
     }
   } else if (warp == 0) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t IDESC_M1 = make_idesc_bf16(128, 96, 0, 0);
-      constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 2 * HD, 0, 1);
-      long long n1 = 0, nq = 0, np = 0, it = 0;
-      int kb1 = 0;          // next k-block of M1(n1)
-      uint32_t idle = 0;    // polls without progress: a mis-programmed pipeline traps instead of hanging the GPU box
-      while (np < n_units) {
-        if (++idle > 400000000u) __trap();
-        // M1(n1), k-block kb1: its slot landed; for the first k-block D must be free (conversion of unit n1 - 1 has read it)
-        if (n1 < n_units) {
-          const int slot = (int)(it % SF_NSLOT);
-          // the first k-block overwrites TMEM slot n1 % 3 = the P of unit n1 - 3: its PV must have been issued (in order)
-          if ((kb1 != 0 || n1 - np < SF_NWG) && mbar_test(&a_full[slot], (uint32_t)((it / SF_NSLOT) & 1))) {
-            fence_proxy_async_smem();
-            tc_fence_after();
-            const uint64_t adesc = make_sw128_desc(smem_u32(sa + (size_t)slot * SF_SLOT), 1024, 16);
-            const uint64_t bdesc = make_sw128_desc(smem_u32(sw + kb1 * (96 * 128)), 1024, 16);
-            mma_bf16x3_ss(tmem_base + SF_TMEM_U + (uint32_t)(n1 % SF_NWG) * 128, adesc, bdesc, IDESC_M1, kb1 != 0);
-            mma_commit(&a_empty[slot]);
-            ++it;
-            if (++kb1 == SF_KB) {
-              kb1 = 0;
-              mma_commit(&d_ready[n1 % SF_NWG]);
-              ++n1;
-            }
-            idle = 0;
-          }
+    // The whole warp runs the (warp-uniform) control flow with 32-bit counters that advance incrementally, one elected
+    // lane issues: the first version -- a single lane with 64-bit counters, % and / per poll -- spent ~1.9 k cycles per
+    // k-block in its own instruction stream and starved the tensor pipe (profiles/r02_ncu_swin_qkv_attn_v5.md).
+    constexpr uint32_t IDESC_M1 = make_idesc_bf16(128, 96, 0, 0);
+    constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 2 * HD, 0, 1);
+    const uint32_t nu = (uint32_t)n_units;
+    uint32_t n1 = 0, nq = 0, np = 0;   // units whose M1 / QK / PV have been issued
+    uint32_t kb1 = 0;                  // next k-block of M1(n1)
+    uint32_t a_slot = 0, a_par = 0;    // ring slot of that k-block, parity of its "full" phase
+    uint32_t s1 = 0, sq = 0, sp = 0;   // n1 % 3, nq % 3, np % 3
+    uint32_t pq = 0, pp = 0;           // (nq / 3) & 1, (np / 3) & 1
+    uint32_t idle = 0;                 // polls without progress: a mis-programmed pipeline traps instead of hanging the box
+    const uint64_t adesc0 = make_sw128_desc(smem_u32(sa), 1024, 16);
+    const uint64_t bdesc0 = make_sw128_desc(smem_u32(sw), 1024, 16);
+    const uint64_t qdesc = make_sw128_desc(smem_u32(smem + SF_OFF_Q), 1024, 16);
+    const uint64_t kdesc = make_sw128_desc(smem_u32(smem + SF_OFF_Q) + WA_TILE, 1024, 16);
+    const uint64_t vdesc0 = make_sw128_desc(smem_u32(smem + SF_OFF_V), 1024, 1024);
+    while (np < nu) {
+      if (++idle > 400000000u) __trap();
+      // M1(n1), k-block kb1: its slot landed.  The first k-block overwrites TMEM slot n1 % 3 = the P of unit n1 - 3, whose
+      // PV must have been issued (the tensor pipe runs in issue order).
+      if (n1 < nu && (kb1 != 0 || n1 - np < (uint32_t)SF_NWG) && __all_sync(0xffffffffu, mbar_test(&a_full[a_slot], a_par))) {
+        tc_fence_after();
+        if (elect_one()) {
+          mma_bf16x3_ss(tmem_base + SF_TMEM_U + s1 * 128, adesc0 + (uint64_t)(a_slot * (SF_SLOT >> 4)),
+                        bdesc0 + (uint64_t)(kb1 * ((96 * 128) >> 4)), IDESC_M1, kb1 != 0);
+          mma_commit(&a_empty[a_slot]);
+          if (kb1 == SF_KB - 1) mma_commit(&d_ready[s1]);
         }
-        // QK(nq): Q / K / V tiles of the unit converted (D of the unit, in the same TMEM slot, is dead by then)
-        if (nq < n1 && mbar_test(&qkv_full[nq % SF_NWG], (uint32_t)((nq / SF_NWG) & 1))) {
-          fence_proxy_async_smem();
-          tc_fence_after();
-          const uint32_t qaddr = smem_u32(smem + SF_OFF_Q);
-          const uint64_t qdesc = make_sw128_desc(qaddr, 1024, 16);
-          const uint64_t kdesc = make_sw128_desc(qaddr + WA_TILE, 1024, 16);
-          mma_bf16x3_ss(tmem_base + SF_TMEM_U + (uint32_t)(nq % SF_NWG) * 128, qdesc, kdesc, IDESC_QK, 0u);
-          mma_commit(&s_ready[nq % SF_NWG]);
-          mma_commit(&qk_free[nq % SF_NWG]);  // the single Q / K tiles may be overwritten by the next unit's conversion
-          ++nq;
-          idle = 0;
+        __syncwarp();
+        if (++a_slot == SF_NSLOT) { a_slot = 0; a_par ^= 1; }
+        if (++kb1 == SF_KB) {
+          kb1 = 0;
+          ++n1;
+          if (++s1 == SF_NWG) s1 = 0;
         }
-        if (np < nq) {
-          const int sl = (int)(np % SF_NWG), ob = (int)(np & 1);
-          if (mbar_test(&p_ready[sl], (uint32_t)((np / SF_NWG) & 1)) && mbar_test(&o_free[ob], (uint32_t)(((np >> 1) & 1) ^ 1))) {
-            tc_fence_after();
-            const uint32_t vaddr = smem_u32(smem + SF_OFF_V + (size_t)sl * WA_TILE);
-            const uint64_t vdesc = make_sw128_desc(vaddr, 1024, 1024);
-            const uint32_t p_tmem = tmem_base + SF_TMEM_U + sl * 128;
-            const uint32_t o_tmem = tmem_base + SF_TMEM_O + ob * 2 * HD;
+        idle = 0;
+      }
+      // QK(nq): Q / K / V tiles of the unit converted (D of the unit, in the same TMEM slot, is dead by then)
+      if (nq < n1 && __all_sync(0xffffffffu, mbar_test(&qkv_full[sq], pq))) {
+        fence_proxy_async_smem();
+        tc_fence_after();
+        if (elect_one()) {
+          mma_bf16x3_ss(tmem_base + SF_TMEM_U + sq * 128, qdesc, kdesc, IDESC_QK, 0u);
+          mma_commit(&s_ready[sq]);
+          mma_commit(&qk_free[sq]);  // the single Q / K tiles may be overwritten by the next unit's conversion
+        }
+        __syncwarp();
+        ++nq;
+        if (++sq == SF_NWG) { sq = 0; pq ^= 1; }
+        idle = 0;
+      }
+      // PV(np): P of the unit is in TMEM, the O buffer np & 1 has been read by the epilogue of unit np - 2
+      if (np < nq && __all_sync(0xffffffffu, mbar_test(&p_ready[sp], pp) && mbar_test(&o_free[np & 1], ((np >> 1) & 1) ^ 1))) {
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t vdesc = vdesc0 + (uint64_t)(sp * (WA_TILE >> 4));
+          const uint32_t p_tmem = tmem_base + SF_TMEM_U + sp * 128;
+          const uint32_t o_tmem = tmem_base + SF_TMEM_O + (np & 1) * 2 * HD;
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const uint32_t pc = p_tmem + (kk >> 1) * 32 + (kk & 1) * 8;
-              mma_bf16_ts(o_tmem, pc, vdesc + (uint64_t)(kk * 128), IDESC_PV, kk != 0);
-              mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);
-            }
-            mma_commit(&o_ready[sl]);
-            mma_commit(&v_empty[sl]);
-            ++np;
-            idle = 0;
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t pc = p_tmem + (kk >> 1) * 32 + (kk & 1) * 8;
+            mma_bf16_ts(o_tmem, pc, vdesc + (uint64_t)(kk * 128), IDESC_PV, kk != 0);
+            mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);
           }
+          mma_commit(&o_ready[sp]);
+          mma_commit(&v_empty[sp]);
         }
+        __syncwarp();
+        ++np;
+        if (++sp == SF_NWG) { sp = 0; pp ^= 1; }
+        idle = 0;
       }
     }
   } else if (warp >= 4) {
@@ -241,9 +223,29 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*window-layou
     for (long long u = wg; u < n_units; u += SF_NWG) {
       const uint32_t k = (uint32_t)(u / SF_NWG);
       const int ob = (int)(u & 1);
-      const uint8_t* meta = smem + SF_OFF_META + (size_t)(u % SF_META_SLOTS) * SF_META_BYTES;
-      const int* rows = reinterpret_cast<const int*>(meta);
-      const uint8_t* region = meta + 512;
+      // ---- metadata of this thread's tile row (computed while M1 of the unit is still in flight): global token row for
+      // the output scatter, shift-mask region, and -- two ballots per window half, exchanged through shared memory --
+      // the 64-bit sets of the window's keys that lie in each of the 9 regions
+      long long my_row = -2;  // -2: MMA padding row, -1: window pad token
+      int my_reg = 0;
+      {
+        const int win = (int)(2 * (pair0 + u * pair_stride)) + half;
+        if (t < WT && win < (int)g.nwin) {
+          const int wy = win % g.nWy, w2 = win / g.nWy;
+          my_row = window_token_row(g, w2 / g.nWx, w2 % g.nWx, wy, t, &my_reg);
+        }
+      }
+      uint32_t* same32 = reinterpret_cast<uint32_t*>(smem + SF_OFF_SAME + wg * SF_SAME_BYTES);
+      {
+        const int wq = warp & 3;  // window half wq >> 1, tokens (wq & 1) * 32 + lane
+#pragma unroll
+        for (int rg = 0; rg < 9; ++rg) {
+          const uint32_t bal = __ballot_sync(0xffffffffu, t < WT && my_reg == rg);
+          if (lane == 0) same32[((wq >> 1) * 9 + rg) * 2 + (wq & 1)] = bal;
+        }
+      }
+      named_bar_sync(3 + wg, 128);
+      const uint2 same = reinterpret_cast<const uint2*>(same32)[half * 9 + my_reg];
       // ---- conversion: D row (q | k | v of this head) + bias -> S32 rows of the Q / K / V operand tiles
       mbar_wait(&d_ready[tb], k & 1);
       tc_fence_after();
@@ -274,9 +276,6 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*window-layou
       // ---- softmax (as window_attn.cu)
       mbar_wait(&s_ready[tb], k & 1);
       tc_fence_after();
-      const long long my_row = rows[i];
-      const int my_reg = region[i];
-      const uint2 same = reinterpret_cast<const uint2*>(meta + 640)[half * 9 + my_reg];
       const uint32_t diff_lo = ~same.x, diff_hi = ~same.y & 0x1FFFFu;
       const bool uniform = (diff_lo | diff_hi) == 0u;
       const float4* brow4 = reinterpret_cast<const float4*>(sb + (t < WT ? t : 0) * WA_BIAS_LD);
