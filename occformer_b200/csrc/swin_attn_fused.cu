@@ -13,8 +13,8 @@
 //                           (window_geom.cuh: the LayerNorm producer writes token (img, x, y) to row window * 64 + t),
 //                           so a pair of windows is a contiguous tile.  (Per-row gathers -- cp.async or tile::gather4,
 //                           ~110 cycles per 512-byte gather4 -- could not feed the MMAs: r02_ncu_swin_qkv_attn_v3/v4.)
-//   MMA      (warp 0)       M1: D[128 x 96] = A W_h^T            (4 k-blocks x 6 tcgen05.mma 128x96x16: three bf16 passes)
-//                           QK: S = Q K^T, PV: O' = [P_hi; P_lo][V_hi | V_lo]   (as in window_attn.cu)
+//   MMA      (warps 0/2/3)  M1: D[128 x 96] = A W_h^T            (4 k-blocks x 6 tcgen05.mma 128x96x16: three bf16 passes)
+//                           QK: S = Q K^T, PV: O' = [P_hi; P_lo][V_hi | V_lo]   (as in window_attn.cu); one issuer each
 //   three warpgroups (warps 4-7 / 8-11 / 12-15, unit u -> warpgroup u % 3), each running its unit start to end:
 //       convert : tcgen05.ld D -> + bias -> split -> V operand tile (one per warpgroup), then Q / K operand tiles (single:
 //                 free again as soon as QK^T of the previous unit has been read)
@@ -135,81 +135,69 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*window-layou
         }
       }
     }
-  } else if (warp == 0) {
-    // ===================================================================== MMA issuer
-    // The whole warp runs the (warp-uniform) control flow with 32-bit counters that advance incrementally, one elected
-    // lane issues: the first version -- a single lane with 64-bit counters, % and / per poll -- spent ~1.9 k cycles per
-    // k-block in its own instruction stream and starved the tensor pipe (profiles/r02_ncu_swin_qkv_attn_v5.md).
+  } else if (warp == 0 || warp == 2 || warp == 3) {
+    // ===================================================================== MMA issuers: M1 (warp 0), QK (warp 2), PV (warp 3)
+    // One issuing lane per kind, each blocking on its own operands only, 32-bit counters advanced incrementally.  (A single
+    // lane polling for all three kinds -- with 64-bit counters, % and / in the first version -- needed ~1 k cycles per
+    // poll round, i.e. per M1 k-block: the issuer's own instruction stream, not the tensor pipe, set the pace:
+    // profiles/r02_ncu_swin_qkv_attn_v5/v6.md.)  tcgen05.commit tracks the issuing thread's own MMAs, and every
+    // dependency between the three kinds is a completion barrier, so nothing relies on cross-thread issue order.
     constexpr uint32_t IDESC_M1 = make_idesc_bf16(128, 96, 0, 0);
     constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 2 * HD, 0, 1);
     const uint32_t nu = (uint32_t)n_units;
-    uint32_t n1 = 0, nq = 0, np = 0;   // units whose M1 / QK / PV have been issued
-    uint32_t kb1 = 0;                  // next k-block of M1(n1)
-    uint32_t a_slot = 0, a_par = 0;    // ring slot of that k-block, parity of its "full" phase
-    uint32_t s1 = 0, sq = 0, sp = 0;   // n1 % 3, nq % 3, np % 3
-    uint32_t pq = 0, pp = 0;           // (nq / 3) & 1, (np / 3) & 1
-    uint32_t idle = 0;                 // polls without progress: a mis-programmed pipeline traps instead of hanging the box
-    const uint64_t adesc0 = make_sw128_desc(smem_u32(sa), 1024, 16);
-    const uint64_t bdesc0 = make_sw128_desc(smem_u32(sw), 1024, 16);
-    const uint64_t qdesc = make_sw128_desc(smem_u32(smem + SF_OFF_Q), 1024, 16);
-    const uint64_t kdesc = make_sw128_desc(smem_u32(smem + SF_OFF_Q) + WA_TILE, 1024, 16);
-    const uint64_t vdesc0 = make_sw128_desc(smem_u32(smem + SF_OFF_V), 1024, 1024);
-    while (np < nu) {
-      if (++idle > 400000000u) __trap();
-      // M1(n1), k-block kb1: its slot landed.  The first k-block overwrites TMEM slot n1 % 3 = the P of unit n1 - 3, whose
-      // PV must have been issued (the tensor pipe runs in issue order).
-      if (n1 < nu && (kb1 != 0 || n1 - np < (uint32_t)SF_NWG) && __all_sync(0xffffffffu, mbar_test(&a_full[a_slot], a_par))) {
-        tc_fence_after();
-        if (elect_one()) {
-          mma_bf16x3_ss(tmem_base + SF_TMEM_U + s1 * 128, adesc0 + (uint64_t)(a_slot * (SF_SLOT >> 4)),
-                        bdesc0 + (uint64_t)(kb1 * ((96 * 128) >> 4)), IDESC_M1, kb1 != 0);
-          mma_commit(&a_empty[a_slot]);
-          if (kb1 == SF_KB - 1) mma_commit(&d_ready[s1]);
+    if (lane == 0 && warp == 0) {
+      const uint64_t adesc0 = make_sw128_desc(smem_u32(sa), 1024, 16);
+      const uint64_t bdesc0 = make_sw128_desc(smem_u32(sw), 1024, 16);
+      uint32_t slot = 0, par = 0;  // ring slot of the next k-block, parity of its "full" phase
+      uint32_t s1 = 0, p1 = 1;     // u % 3; parity of the v_empty phase that frees TMEM slot s1 (first use: no wait)
+      for (uint32_t u = 0; u < nu; ++u) {
+        // TMEM slot s1 still holds the P of unit u - 3 until its PV has completed
+        if (u >= (uint32_t)SF_NWG) mbar_wait(&v_empty[s1], p1);
+#pragma unroll 1
+        for (uint32_t kb = 0; kb < (uint32_t)SF_KB; ++kb) {
+          mbar_wait(&a_full[slot], par);
+          tc_fence_after();
+          mma_bf16x3_ss(tmem_base + SF_TMEM_U + s1 * 128, adesc0 + (uint64_t)(slot * (SF_SLOT >> 4)),
+                        bdesc0 + (uint64_t)(kb * ((96 * 128) >> 4)), IDESC_M1, kb != 0);
+          mma_commit(&a_empty[slot]);
+          if (++slot == SF_NSLOT) { slot = 0; par ^= 1; }
         }
-        __syncwarp();
-        if (++a_slot == SF_NSLOT) { a_slot = 0; a_par ^= 1; }
-        if (++kb1 == SF_KB) {
-          kb1 = 0;
-          ++n1;
-          if (++s1 == SF_NWG) s1 = 0;
-        }
-        idle = 0;
+        mma_commit(&d_ready[s1]);
+        if (++s1 == SF_NWG) { s1 = 0; p1 ^= 1; }
       }
-      // QK(nq): Q / K / V tiles of the unit converted (D of the unit, in the same TMEM slot, is dead by then)
-      if (nq < n1 && __all_sync(0xffffffffu, mbar_test(&qkv_full[sq], pq))) {
+    } else if (lane == 0 && warp == 2) {
+      const uint64_t qdesc = make_sw128_desc(smem_u32(smem + SF_OFF_Q), 1024, 16);
+      const uint64_t kdesc = make_sw128_desc(smem_u32(smem + SF_OFF_Q) + WA_TILE, 1024, 16);
+      uint32_t sq = 0, pq = 0;
+      for (uint32_t u = 0; u < nu; ++u) {
+        mbar_wait(&qkv_full[sq], pq);  // Q / K / V tiles converted (D of the unit, in the same TMEM slot, is dead by then)
         fence_proxy_async_smem();
         tc_fence_after();
-        if (elect_one()) {
-          mma_bf16x3_ss(tmem_base + SF_TMEM_U + sq * 128, qdesc, kdesc, IDESC_QK, 0u);
-          mma_commit(&s_ready[sq]);
-          mma_commit(&qk_free[sq]);  // the single Q / K tiles may be overwritten by the next unit's conversion
-        }
-        __syncwarp();
-        ++nq;
+        mma_bf16x3_ss(tmem_base + SF_TMEM_U + sq * 128, qdesc, kdesc, IDESC_QK, 0u);
+        mma_commit(&s_ready[sq]);
+        mma_commit(&qk_free[sq]);  // the single Q / K tiles may be overwritten by the next unit's conversion
         if (++sq == SF_NWG) { sq = 0; pq ^= 1; }
-        idle = 0;
       }
-      // PV(np): P of the unit is in TMEM, the O buffer np & 1 has been read by the epilogue of unit np - 2
-      if (np < nq && __all_sync(0xffffffffu, mbar_test(&p_ready[sp], pp) && mbar_test(&o_free[np & 1], ((np >> 1) & 1) ^ 1))) {
+    } else if (lane == 0 && warp == 3) {
+      const uint64_t vdesc0 = make_sw128_desc(smem_u32(smem + SF_OFF_V), 1024, 1024);
+      uint32_t sp = 0, pp = 0;
+      for (uint32_t u = 0; u < nu; ++u) {
+        mbar_wait(&p_ready[sp], pp);                          // P of the unit is in TMEM
+        mbar_wait(&o_free[u & 1], ((u >> 1) & 1) ^ 1);        // O buffer u & 1 read by the epilogue of unit u - 2
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t vdesc = vdesc0 + (uint64_t)(sp * (WA_TILE >> 4));
-          const uint32_t p_tmem = tmem_base + SF_TMEM_U + sp * 128;
-          const uint32_t o_tmem = tmem_base + SF_TMEM_O + (np & 1) * 2 * HD;
+        const uint64_t vdesc = vdesc0 + (uint64_t)(sp * (WA_TILE >> 4));
+        const uint32_t p_tmem = tmem_base + SF_TMEM_U + sp * 128;
+        const uint32_t o_tmem = tmem_base + SF_TMEM_O + (u & 1) * 2 * HD;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t pc = p_tmem + (kk >> 1) * 32 + (kk & 1) * 8;
-            mma_bf16_ts(o_tmem, pc, vdesc + (uint64_t)(kk * 128), IDESC_PV, kk != 0);
-            mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);
-          }
-          mma_commit(&o_ready[sp]);
-          mma_commit(&v_empty[sp]);
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t pc = p_tmem + (kk >> 1) * 32 + (kk & 1) * 8;
+          mma_bf16_ts(o_tmem, pc, vdesc + (uint64_t)(kk * 128), IDESC_PV, kk != 0);
+          mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);
         }
-        __syncwarp();
-        ++np;
+        mma_commit(&o_ready[sp]);
+        mma_commit(&v_empty[sp]);
         if (++sp == SF_NWG) { sp = 0; pp ^= 1; }
-        idle = 0;
       }
     }
   } else if (warp >= 4) {

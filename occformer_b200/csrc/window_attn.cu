@@ -156,14 +156,35 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
     // the loaders never wait for their own copies: up to WA_STAGES units of gathers are in flight per CTA
     for (long long u = 0; u < n_units; ++u) issue(u);
     cp_async_wait<0>();
-  } else if (warp == 0) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 2 * HD, 0, 1);  // B = V tile, MN-major (hi | lo of d contiguous)
-      auto do_pv = [&](long long v) {
-        const int tb = (int)(v & 1), s = (int)(v % WA_STAGES);
-        const uint32_t k = (uint32_t)(v >> 1);
+  } else if (warp == 0 || warp == 3) {
+    // ===================================================================== MMA issuers: QK (warp 0), PV (warp 3)
+    // One issuing lane per kind, each blocking on its own operands only, 32-bit counters advanced incrementally: PV(u) must
+    // not queue behind the gathers of unit u+1, and QK(u+1) must not queue behind the softmax of unit u.  (One lane
+    // polling for both kinds with 64-bit counters spent more time in its own instruction stream than the MMAs take; see
+    // swin_attn_fused.cu.)  tcgen05.commit tracks the issuing thread's own MMAs and every dependency between the two kinds
+    // is a completion barrier: S/P buffer (u & 1) is free for QK(u) once PV(u - 2) has COMPLETED (o_ready).
+    constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 2 * HD, 0, 1);  // B = V tile, MN-major (hi | lo of d contiguous)
+    const uint32_t nu = (uint32_t)n_units;
+    if (lane == 0 && warp == 0) {
+      uint32_t s = 0, par = 0;  // stage of unit u, parity of its "full" phase
+      for (uint32_t u = 0; u < nu; ++u) {
+        const uint32_t tb = u & 1, k = u >> 1;
+        if (u >= 2) mbar_wait(&o_ready[tb], (k - 1) & 1);
+        mbar_wait(&full_bar[s], par);
+        fence_proxy_async_smem();  // cp.async / st.shared (generic proxy) -> tcgen05.mma operand reads (async proxy)
+        tc_fence_after();
+        const uint32_t qaddr = smem_u32(smem + (size_t)s * WA_STAGE_BYTES);
+        const uint64_t qdesc = make_sw128_desc(qaddr, 1024, 16);
+        const uint64_t kdesc = make_sw128_desc(qaddr + WA_TILE, 1024, 16);
+        mma_bf16x3_ss(tmem_base + tb * 128, qdesc, kdesc, IDESC_QK, 0u);
+        mma_commit(&s_ready[tb]);
+        if (++s == WA_STAGES) { s = 0; par ^= 1; }
+      }
+    } else if (lane == 0 && warp == 3) {
+      uint32_t s = 0;
+      for (uint32_t u = 0; u < nu; ++u) {
+        const uint32_t tb = u & 1, k = u >> 1;
         mbar_wait(&p_ready[tb], k & 1);
         mbar_wait(&o_free[tb], (k & 1) ^ 1);
         tc_fence_after();
@@ -180,36 +201,7 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         }
         mma_commit(&o_ready[tb]);
         mma_commit(&empty_bar[s]);
-      };
-      auto do_qk = [&](long long u) {
-        const int tb = (int)(u & 1), s = (int)(u % WA_STAGES);
-        fence_proxy_async_smem();  // cp.async / st.shared (generic proxy) -> tcgen05.mma operand reads (async proxy)
-        tc_fence_after();
-        const uint32_t qaddr = smem_u32(smem + (size_t)s * WA_STAGE_BYTES);
-        const uint64_t qdesc = make_sw128_desc(qaddr, 1024, 16);
-        const uint64_t kdesc = make_sw128_desc(qaddr + WA_TILE, 1024, 16);
-        const uint32_t s_tmem = tmem_base + tb * 128;
-        mma_bf16x3_ss(s_tmem, qdesc, kdesc, IDESC_QK, 0u);
-        mma_commit(&s_ready[tb]);
-      };
-      // Polling state machine instead of a fixed QK/PV order: PV(u) must not queue behind the gathers of unit u+1,
-      // and QK(u+1) must not queue behind the softmax of unit u.  S/P buffer (u & 1) is free once PV(u-2) was issued
-      // (tcgen05 ops execute in issue order), hence the nq - np < 2 window.
-      long long nq = 0, np = 0;
-      while (np < n_units) {
-        if (nq < n_units && nq - np < 2 &&
-            mbar_test(&full_bar[nq % WA_STAGES], (uint32_t)((nq / WA_STAGES) & 1))) {
-          do_qk(nq);
-          ++nq;
-        }
-        if (np < nq) {
-          const int tb = (int)(np & 1);
-          const uint32_t k = (uint32_t)(np >> 1);
-          if (mbar_test(&p_ready[tb], k & 1) && mbar_test(&o_free[tb], (k & 1) ^ 1)) {
-            do_pv(np);
-            ++np;
-          }
-        }
+        if (++s == WA_STAGES) s = 0;
       }
     }
   } else if (warp >= 4 && warp < 12) {
