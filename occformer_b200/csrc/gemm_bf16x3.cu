@@ -115,10 +115,21 @@ __device__ __forceinline__ void warp_butterfly32(float (&v)[32], int lane) {
 // MT = M-tiles per CTA tile.  MT = 2 (stage-0 convs, N = 128): two 128-row accumulators share every B k-block, so the
 // TMA engine writes 48 KB instead of 64 KB of shared memory per two tiles -- the 128x128 tile is bound by the
 // shared-memory port (TMA writes + MMA operand reads), not by the tensor pipe.
-template <int BN, int STAGES, int MT>
+template <int BN, int STAGES, int MT, bool LEAN>
 __global__ void __launch_bounds__(384, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  // LEAN = plain GEMM, whole 32-column chunks, TMA store, no conv addressing / pooling / GroupNorm statistics / split-K:
+  // those branches compile away.  (The Linears of the neck and of the C >= 256 Swin stages have 6-24 k-blocks per tile:
+  // their pace is set by the epilogue warps' instruction stream -- 2.1 k instructions per warp and tile in the generic
+  // kernel, profiles/r02_ncu_neck_ffn_gemms.md -- not by the 4.6 k tensor cycles of the tile.)
+  const bool f_conv = !LEAN && p.conv != 0;
+  const bool f_pool = !LEAN && p.pool_out != nullptr;
+  const bool f_stats = !LEAN && p.gn_stats != nullptr;
+  const int f_splits = LEAN ? 1 : p.splits;
+  const bool f_tma = LEAN || p.use_tma_store != 0;
+  const bool f_store = LEAN || p.store_out != 0;
+
   constexpr int B_STAGE_BYTES = BN * BK * 4;
   constexpr int A_BYTES = MT * A_STAGE_BYTES;
   constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
@@ -143,9 +154,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int lane = threadIdx.x & 31;
 
   const int num_n_tiles = (p.N + BN - 1) / BN;
-  const int num_m_tiles = p.conv ? p.B * p.tiles_x * p.tiles_y * p.tiles_z : (p.M + BM - 1) / BM;
+  const int num_m_tiles = f_conv ? p.B * p.tiles_x * p.tiles_y * p.tiles_z : (p.M + BM - 1) / BM;
   const int num_m_groups = (num_m_tiles + MT - 1) / MT;
-  const int num_tiles = num_m_groups * num_n_tiles * p.splits;
+  const int num_tiles = num_m_groups * num_n_tiles * f_splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -177,18 +188,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int cblocks = p.conv ? (p.Cin / BK) : 0;
+      const int cblocks = f_conv ? (p.Cin / BK) : 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile % p.splits;
-        const int n_tile = (tile / p.splits) % num_n_tiles;
-        const int m_group = tile / (p.splits * num_n_tiles);
-        const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
-        const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
+        const int split = tile % f_splits;
+        const int n_tile = (tile / f_splits) % num_n_tiles;
+        const int m_group = tile / (f_splits * num_n_tiles);
+        const int kb0 = (int)(((long long)split * p.num_k_blocks) / f_splits);
+        const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / f_splits);
         int cb[MT], cx0[MT], cy0[MT], cz0[MT];
 #pragma unroll
         for (int sub = 0; sub < MT; ++sub) {
           cb[sub] = cx0[sub] = cy0[sub] = cz0[sub] = 0;
-          if (p.conv) {
+          if (f_conv) {
             int t = m_group * MT + sub;  // past the last tile: cb == B, the TMA box is out of bounds and zero-filled
             const int tz = t % p.tiles_z; t /= p.tiles_z;
             const int ty = t % p.tiles_y; t /= p.tiles_y;
@@ -200,7 +211,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
         int tap = 0, kc = 0, tx_ = 0, ty_ = 0, tz_ = 0;
-        if (p.conv && kb0 > 0) {  // split-K: start in the middle of the tap sequence
+        if (f_conv && kb0 > 0) {  // split-K: start in the middle of the tap sequence
           tap = kb0 / cblocks;
           kc = kb0 % cblocks;
           tz_ = tap % p.KZ;
@@ -212,7 +223,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          if (p.conv) {
+          if (f_conv) {
             // input offset of this tap: regular stencil (dilated, padding folded into c?0) or the explicit table
             const int ox = p.ntaps ? p.tdx[tap] : tx_ * p.dil, oy = p.ntaps ? p.tdy[tap] : ty_ * p.dil,
                       oz = p.ntaps ? p.tdz[tap] : tz_ * p.dil;
@@ -250,9 +261,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&tmem_empty[buf], (((it >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
-        const int split = tile % p.splits;
-        const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
-        const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
+        const int split = tile % f_splits;
+        const int kb0 = (int)(((long long)split * p.num_k_blocks) / f_splits);
+        const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / f_splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -280,7 +291,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int et = ew * 32 + lane;   // thread index inside the warpgroup
     const int row = ew * 32 + lane;
     uint8_t* stage_buf = epi_smem + (warp - 4) * EPI_BUF_BYTES;
-    if (p.pool_out != nullptr) {  // pooled mode never stores through the staging buffers: they hold the cell maxima
+    if (f_pool) {  // pooled mode never stores through the staging buffers: they hold the cell maxima
       for (int i = threadIdx.x - 128; i < 8192; i += 256) reinterpret_cast<int*>(epi_smem)[i] = ENC_NEG;
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
@@ -290,8 +301,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int cur_b = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      const int n_tile = (tile / p.splits) % num_n_tiles;
-      const int m_group = tile / (p.splits * num_n_tiles);
+      const int n_tile = (tile / f_splits) % num_n_tiles;
+      const int m_group = tile / (f_splits * num_n_tiles);
       const int n0 = n_tile * BN;
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
@@ -302,7 +313,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // ---- output row of this thread
       long long m = -1;
       int tile_b = 0, tile_x0 = 0, tile_y0 = 0, tile_z0 = 0;
-      if (p.conv) {
+      if (f_conv) {
         int t = m_tile;
         const int tz = t % p.tiles_z; t /= p.tiles_z;
         const int ty = t % p.tiles_y; t /= p.tiles_y;
@@ -324,7 +335,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // pooled mode: this row's cell inside the tile and the (cell, column) slots this thread drains, once per tile
       int pool_cl = 0, pool_n = 0;
       long long pool_dst[8];
-      if (p.pool_out != nullptr) {
+      if (f_pool) {
         const int dz = row % p.bz, dy = (row / p.bz) % p.by, dx = row / (p.bz * p.by);
         pool_cl = ((dx / p.pool_cwx) * p.pool_ncy + dy / p.pool_cwy) * p.pool_ncz + dz / p.pool_cwz;
         const int ncell = (p.bx / p.pool_cwx) * p.pool_ncy * p.pool_ncz;
@@ -343,7 +354,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
 
-      if (p.gn_stats != nullptr && tile_b != cur_b) {
+      if (f_stats && tile_b != cur_b) {
         // flush the per-CTA fp64 partial sums of the previous batch sample
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (cur_b >= 0) {
@@ -358,10 +369,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         cur_b = tile_b;
       }
 
-      if (p.splits > 1) {  // wait until the lower splits of this tile have added their partial sums
+      if (f_splits > 1) {  // wait until the lower splits of this tile have added their partial sums
         if (threadIdx.x == 128) {
-          const int want = tile % p.splits;
-          volatile int* sem = p.splitk_sem + ((tile / p.splits) & (SPLITK_SEMS - 1));
+          const int want = tile % f_splits;
+          volatile int* sem = p.splitk_sem + ((tile / f_splits) & (SPLITK_SEMS - 1));
           for (int spin = 0; *sem != want && spin < (1 << 16); ++spin) __nanosleep(64);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -379,7 +390,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rnext[j]);
         if (c + 2 < BN / 32 && nc + 64 < p.N) tmem_ld_32x32(t_row + (c + 2) * 32, rnext);
-        if (p.gn_stats != nullptr) {
+        if (f_stats) {
           // per-group sum / sumsq of the raw conv output, butterfly-reduced over the 32 rows of the warp
           const int cpg = p.cpg;  // power of two in [1, 32]
           if (cpg == 1) {
@@ -413,7 +424,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
         // ---- epilogue math in the thread = row domain (32 consecutive output columns in registers)
-        const bool full_chunk = (nc + 32 <= p.N);
+        const bool full_chunk = LEAN || (nc + 32 <= p.N);
         if (p.bias) {
           if (full_chunk && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
 #pragma unroll
@@ -454,7 +465,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(w[j]);
         }
-        if (p.pool_out != nullptr) {
+        if (f_pool) {
           // ---- fused adaptive max pool (windows are powers of two >= 2 that divide the grid).  The G lanes of this
           // warp's (ex, ey, ez) voxel sub-box that share a pooling cell reduce their 32 columns with a halving
           // butterfly (lane keeps 32/G column maxima: 32 - 32/G shuffles instead of 32 log2 G), the partial maxima of
@@ -504,9 +515,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
         }
-        if (!p.store_out) {
+        if (!f_store) {
           // nothing else to write
-        } else if (p.use_tma_store) {
+        } else if (f_tma) {
           // registers -> 128B-swizzled smem chunk (conflict-free) -> one TMA store per warp and chunk; the TMA unit
           // generates the row addresses and clips rows >= M / columns >= N / voxels outside the grid
           uint8_t* sb = stage_buf;
@@ -519,16 +530,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (p.conv) {
+            if (f_conv) {
               // rows ew*32 .. ew*32+31 of the tile form a sub-box (ex, ey, ez) of the (bx, by, bz) voxel box
               const int r0 = ew * 32;
-              if (p.splits > 1)
+              if (f_splits > 1)
                 tma_reduce_add_5d(&tmC, sb, nc, tile_z0 + r0 % p.bz, tile_y0 + (r0 / p.bz) % p.by,
                                   tile_x0 + r0 / (p.bz * p.by), tile_b);
               else
                 tma_store_5d(&tmC, sb, nc, tile_z0 + r0 % p.bz, tile_y0 + (r0 / p.bz) % p.by,
                              tile_x0 + r0 / (p.bz * p.by), tile_b);
-            } else if (p.splits > 1) {
+            } else if (f_splits > 1) {
               tma_reduce_add_2d(&tmC, sb, nc, m_tile * BM + ew * 32);
             } else {
               tma_store_2d(&tmC, sb, nc, m_tile * BM + ew * 32);
@@ -546,17 +557,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-      if (p.splits > 1) {  // publish: this split's reduce-adds are complete
+      if (f_splits > 1) {  // publish: this split's reduce-adds are complete
         if (lane == 0) tma_store_wait_all();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 128) {
           __threadfence();
-          const int split = tile % p.splits;
-          atomicExch(p.splitk_sem + ((tile / p.splits) & (SPLITK_SEMS - 1)), split == p.splits - 1 ? 0 : split + 1);
+          const int split = tile % f_splits;
+          atomicExch(p.splitk_sem + ((tile / f_splits) & (SPLITK_SEMS - 1)), split == f_splits - 1 ? 0 : split + 1);
         }
       }
     }
-    if (p.gn_stats != nullptr) {
+    if (f_stats) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (cur_b >= 0) {
         const int ngroups2 = 2 * (p.N / p.cpg);
@@ -630,15 +641,15 @@ conv_gn_stats_kernel(const float* __restrict__ out, double* __restrict__ stats, 
   if (threadIdx.x < 2 * groups) atomicAdd(&stats[(size_t)b * 2 * groups + threadIdx.x], sg[threadIdx.x]);
 }
 
-template <int BN, int STAGES, int MT = 1>
+template <int BN, int STAGES, int MT = 1, bool LEAN = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        int num_tiles, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * (MT * A_STAGE_BYTES + BN * BK * 4) + 1024 /*align*/ + CTRL_BYTES + EPI_BYTES;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  OCC_ENSURE_SMEM((gemm_bf16x3_kernel<BN, STAGES, MT>), smem);
+  OCC_ENSURE_SMEM((gemm_bf16x3_kernel<BN, STAGES, MT, LEAN>), smem);
   int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   if (grid < 1) grid = 1;
-  gemm_bf16x3_kernel<BN, STAGES, MT><<<grid, 384, smem, stream>>>(tmA, tmB, tmC, p);
+  gemm_bf16x3_kernel<BN, STAGES, MT, LEAN><<<grid, 384, smem, stream>>>(tmA, tmB, tmC, p);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -660,6 +671,19 @@ static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmC, const v
   if (BN == 128 && p.conv && p.splits == 1 && p.pool_out == nullptr && p.use_tma_store &&
       num_m_tiles >= 4 * sm_count())
     return launch_gemm<128, 4, 2>(tmA, tmB, tmC, p, ((num_m_tiles + 1) / 2) * ((p.N + BN - 1) / BN), stream);
+  // plain Linear with whole 32-column chunks through the TMA store: the lean instantiation (shorter epilogue)
+  const bool lean = !p.conv && p.splits == 1 && p.pool_out == nullptr && p.gn_stats == nullptr && p.use_tma_store &&
+                    p.store_out && p.N % 32 == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 &&
+                    (p.residual == nullptr || ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && p.ldr % 4 == 0));
+  if (lean) {
+    switch (BN) {
+      case 32: break;
+      case 64: return launch_gemm<64, 8, 1, true>(tmA, tmB, tmC, p, num_tiles, stream);
+      case 128: return launch_gemm<128, 5, 1, true>(tmA, tmB, tmC, p, num_tiles, stream);
+      case 192: return launch_gemm<192, 4, 1, true>(tmA, tmB, tmC, p, num_tiles, stream);
+      default: return launch_gemm<256, 4, 1, true>(tmA, tmB, tmC, p, num_tiles, stream);
+    }
+  }
   switch (BN) {
     case 32: return launch_gemm<32, 8>(tmA, tmB, tmC, p, num_tiles, stream);
     case 64: return launch_gemm<64, 8>(tmA, tmB, tmC, p, num_tiles, stream);
