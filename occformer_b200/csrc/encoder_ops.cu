@@ -364,8 +364,8 @@ gap_broadcast_kernel(const float* __restrict__ vals /*(B, ch)*/, float* __restri
 // identity = block input (stride 1) or GroupNorm(downsample conv raw output) (stride 2; :36-41).
 // R consecutive rows per warp: the x, identity and bev loads of all R rows are issued before the first reduction, so a
 // warp keeps R x 1.5 KB (C = 128) in flight (one row per warp: 2.9 TB/s on load latency alone).
-template <int NV, int R>
-__global__ void __launch_bounds__(256)
+template <int NV, int R, int MB = 1>
+__global__ void __launch_bounds__(256, MB)
 fuse_kernel(const float* __restrict__ x, const float* __restrict__ bev, const float* __restrict__ cw, float cbias,
             const float* __restrict__ identity, int identity_split, const double* __restrict__ id_stats,
             const float* __restrict__ id_w, const float* __restrict__ id_b, int groups, float* __restrict__ out,
@@ -562,13 +562,34 @@ extern "C" int occ_dualpath_fuse(const float* x, const float* bev, const float* 
   OCC_REQUIRE(x && bev && cw && identity && (out || out_split) && B > 0 && XY > 0 && Z > 0 && C % 128 == 0);
   if (id_stats) OCC_REQUIRE(id_w && id_b && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0);
   const long long rows = (long long)B * XY * Z;
-  DISPATCH_NV(C, ({
-                constexpr int R = NV == 1 ? 4 : (NV == 2 ? 2 : 1);
-                const int blocks = (int)((rows + 8 * R - 1) / (8 * R));
-                fuse_kernel<NV, R><<<blocks, 256, 0, stream>>>(x, bev, cw, cbias, identity, identity_split, id_stats, id_w,
-                                                               id_b, groups > 0 ? groups : 1, out, out_split, rows, Z,
-                                                               (long long)XY * Z, C);
-              }));
+#define FUSE_LAUNCH(NV_, R_, MB_)                                                                                       \
+  do {                                                                                                                  \
+    const int blocks = (int)((rows + 8 * (R_) - 1) / (8 * (R_)));                                                       \
+    fuse_kernel<NV_, R_, MB_><<<blocks, 256, 0, stream>>>(x, bev, cw, cbias, identity, identity_split, id_stats, id_w,  \
+                                                          id_b, groups > 0 ? groups : 1, out, out_split, rows, Z,       \
+                                                          (long long)XY * Z, C);                                        \
+  } while (0)
+  if (C == 128) {
+    // EXPERIMENT (to be removed): rows per warp / minimum resident CTAs
+    const char* e = getenv("OCC_FUSE_VARIANT");
+    const int v = e ? atoi(e) : 0;
+    switch (v) {
+      case 1: FUSE_LAUNCH(1, 4, 3); break;
+      case 2: FUSE_LAUNCH(1, 2, 4); break;
+      case 3: FUSE_LAUNCH(1, 2, 6); break;
+      case 4: FUSE_LAUNCH(1, 1, 8); break;
+      default: FUSE_LAUNCH(1, 4, 1); break;
+    }
+  } else if (C == 256) {
+    FUSE_LAUNCH(2, 2, 1);
+  } else if (C == 512) {
+    FUSE_LAUNCH(4, 1, 1);
+  } else if (C == 1024) {
+    FUSE_LAUNCH(8, 1, 1);
+  } else {
+    return OCC_EUNSUPPORTED;
+  }
+#undef FUSE_LAUNCH
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

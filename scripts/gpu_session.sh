@@ -15,6 +15,7 @@ for s in "$@"; do
     neck)    timeout 600 python -m pytest tests/test_gpu_neck.py tests/test_gpu_eval.py -q -m gpu > gpurun_out/t_neck.log 2>&1; echo "neck rc=$?" ;;
     all)     timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/t_all.log 2>&1; echo "all rc=$?" ;;
     micro)   timeout 600 python scripts/microbench.py > gpurun_out/micro.log 2>&1; echo "micro rc=$?" ;;
+    microelem) timeout 600 python scripts/microbench.py elem > gpurun_out/micro_elem.log 2>&1; echo "microelem rc=$?"; tail -n 20 gpurun_out/micro_elem.log ;;
     bench)   timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -n 3 gpurun_out/bench.log ;;
     benchq)  timeout 600 python bench.py --steps 5 --no-cpu-baseline > gpurun_out/benchq.log 2> gpurun_out/benchq.err; echo "benchq rc=$?"; tail -c 3000 gpurun_out/benchq.log; tail -n 5 gpurun_out/benchq.err ;;
     benchref) timeout 900 python bench.py --impl reference --steps 2 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "benchref rc=$?"; tail -n 2 gpurun_out/bench_ref.log ;;

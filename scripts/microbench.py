@@ -117,6 +117,30 @@ def main():
         res["neck_ffn_two_gemms_ms"] = timeit(lambda: ops.gemm(ops.gemm(x_s, w1, bias=b1, act=1, split_out=True), w2, bias=b2, residual=v))
         res["neck_token_prep_ms"] = timeit(lambda: ops.neck_token_prep(v, grids, 1, ln=(torch.ones(E, device=dev), torch.zeros(E, device=dev)),
                                                                    pos=v, want_pos=True))
+    if "elem" in which:
+        import os
+        Bc, Xc_, Yc_, Zc_ = 1, 200, 200, 16
+        nv = Xc_ * Yc_ * Zc_
+        xv = torch.randn(nv, 128, device=dev)
+        bev = torch.randn(Xc_ * Yc_, 128, device=dev)
+        ident = ops.to_split(torch.randn(nv, 128, device=dev))
+        cw = torch.randn(128, device=dev) * 0.1
+        for var in (0, 1, 2, 3, 4):
+            os.environ["OCC_FUSE_VARIANT"] = str(var)
+            res[f"fuse_c128_s32_only_variant{var}_ms"] = timeit(lambda: ops.dualpath_fuse(xv, bev, cw, 0.1, ident, Bc, Xc_ * Yc_, Zc_, 128,
+                                                                                        identity_split=True, want_f32=False))
+            res[f"fuse_c128_f32_and_s32_variant{var}_ms"] = timeit(lambda: ops.dualpath_fuse(xv, bev, cw, 0.1, ident, Bc, Xc_ * Yc_, Zc_, 128,
+                                                                                           identity_split=True, want_f32=True))
+        os.environ.pop("OCC_FUSE_VARIANT", None)
+        del xv, ident
+        E = 192
+        cur = torch.randn(1, 200, 200, 16, E, device=dev)
+        coarse = torch.randn(1, 100, 100, 8, E, device=dev)
+        st = ops.gn_stats(cur.view(-1, E), 1, 200 * 200 * 16, E, 32)
+        gw, gb = torch.ones(E, device=dev), torch.zeros(E, device=dev)
+        res["gn_upsample_add_200x200x16x192_ms"] = timeit(lambda: ops.gn_upsample_add(cur, st, gw, gb, 32, coarse))
+        res["gn_stats_200x200x16x192_ms"] = timeit(lambda: ops.gn_stats(cur.view(-1, E), 1, 200 * 200 * 16, E, 32))
+        del cur, coarse
     if "lift" in which:
         from occformer_b200.view_transformer import ViewTransformerLiftSplatShootVoxel
         gc = synth.grid_config("nusc_200")
