@@ -395,30 +395,56 @@ gn_upsample_add_x2_kernel(const float* __restrict__ cur, const double* __restric
     tile[i] = v;
   }
   __syncthreads();
+  // thread = (float4 l8 of the chunk, dz, dy parity): the z-axis terms are per-thread constants, the y-axis terms live in
+  // registers for the thread's four dy values, the x-axis terms are computed once per dx
   const int l8 = threadIdx.x & 7;
+  const int dz = (threadIdx.x >> 3) & (UA_BZ - 1), yofs = threadIdx.x >> 7;
+  static_assert(UA_BZ == 16 && UA_BY == 8, "thread mapping");
   const float4 a = *reinterpret_cast<const float4*>(sc + 4 * l8), d = *reinterpret_cast<const float4*>(sh + 4 * l8);
-#pragma unroll 2
-  for (int v = threadIdx.x >> 3; v < UA_BX * UA_BY * UA_BZ; v += 32) {
-    const int dz = v % UA_BZ, dy = (v / UA_BZ) % UA_BY, dx = v / (UA_BZ * UA_BY);
-    const int x = x0 + dx, y = y0 + dy, z = z0 + dz;
-    if (x >= X || y >= Y || z >= Z) continue;
-    const long long row = (long long)b * V + ((long long)x * Y + y) * Z + z;
-    const float4 raw = __ldcs(reinterpret_cast<const float4*>(cur + row * C) + chunk * 8 + l8);
-    float4 o = make_float4(fmaf(raw.x, a.x, d.x), fmaf(raw.y, a.y, d.y), fmaf(raw.z, a.z, d.z), fmaf(raw.w, a.w, d.w));
-    int xa, xb, ya, yb, za, zb;
-    float tx, ty, tz;
-    axis(x, X, Xc, xa, xb, tx);
-    axis(y, Y, Yc, ya, yb, ty);
-    axis(z, Z, Zc, za, zb, tz);
+  const int z = z0 + dz;
+  if (z >= Z) return;
+  int za, zb;
+  float tz;
+  axis(z, Z, Zc, za, zb, tz);
+  const int oz[2] = {(za - cz0) * 8 + l8, (zb - cz0) * 8 + l8};
+  const float wz[2] = {1.f - tz, tz};
+  int oy[4][2];
+  float wy[4][2];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int kz = k & 1, ky = (k >> 1) & 1, kx = k >> 2;
-      const float4 cv = tile[((((kx ? xb : xa) - cx0) * UA_CY + ((ky ? yb : ya) - cy0)) * UA_CZ + ((kz ? zb : za) - cz0)) * 8 + l8];
-      const float wgt = (kx ? tx : 1.f - tx) * (ky ? ty : 1.f - ty) * (kz ? tz : 1.f - tz);
-      o.x = fmaf(wgt, cv.x, o.x); o.y = fmaf(wgt, cv.y, o.y);
-      o.z = fmaf(wgt, cv.z, o.z); o.w = fmaf(wgt, cv.w, o.w);
+  for (int j = 0; j < 4; ++j) {
+    int ya, yb;
+    float ty;
+    const int y = y0 + 2 * j + yofs;
+    axis(y < Y ? y : Y - 1, Y, Yc, ya, yb, ty);
+    oy[j][0] = (ya - cy0) * UA_CZ * 8; oy[j][1] = (yb - cy0) * UA_CZ * 8;
+    wy[j][0] = 1.f - ty; wy[j][1] = ty;
+  }
+#pragma unroll 1
+  for (int dx = 0; dx < UA_BX; ++dx) {
+    const int x = x0 + dx;
+    if (x >= X) break;
+    int xa, xb;
+    float tx;
+    axis(x, X, Xc, xa, xb, tx);
+    const int ox[2] = {(xa - cx0) * UA_CY * UA_CZ * 8, (xb - cx0) * UA_CY * UA_CZ * 8};
+    const float wx[2] = {1.f - tx, tx};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int y = y0 + 2 * j + yofs;
+      if (y >= Y) continue;
+      const long long row = (long long)b * V + ((long long)x * Y + y) * Z + z;
+      const float4 raw = __ldcs(reinterpret_cast<const float4*>(cur + row * C) + chunk * 8 + l8);
+      float4 o = make_float4(fmaf(raw.x, a.x, d.x), fmaf(raw.y, a.y, d.y), fmaf(raw.z, a.z, d.z), fmaf(raw.w, a.w, d.w));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int kz = k & 1, ky = (k >> 1) & 1, kx = k >> 2;
+        const float4 cv = tile[ox[kx] + oy[j][ky] + oz[kz]];
+        const float wgt = wx[kx] * wy[j][ky] * wz[kz];
+        o.x = fmaf(wgt, cv.x, o.x); o.y = fmaf(wgt, cv.y, o.y);
+        o.z = fmaf(wgt, cv.z, o.z); o.w = fmaf(wgt, cv.w, o.w);
+      }
+      store_split4(out_s + row * C, chunk * 32 + 4 * l8, o);
     }
-    store_split4(out_s + row * C, chunk * 32 + 4 * l8, o);
   }
 }
 

@@ -118,20 +118,16 @@ def main():
         res["neck_token_prep_ms"] = timeit(lambda: ops.neck_token_prep(v, grids, 1, ln=(torch.ones(E, device=dev), torch.zeros(E, device=dev)),
                                                                    pos=v, want_pos=True))
     if "elem" in which:
-        import os
         Bc, Xc_, Yc_, Zc_ = 1, 200, 200, 16
         nv = Xc_ * Yc_ * Zc_
         xv = torch.randn(nv, 128, device=dev)
         bev = torch.randn(Xc_ * Yc_, 128, device=dev)
         ident = ops.to_split(torch.randn(nv, 128, device=dev))
         cw = torch.randn(128, device=dev) * 0.1
-        for var in (0, 1, 2, 3, 4):
-            os.environ["OCC_FUSE_VARIANT"] = str(var)
-            res[f"fuse_c128_s32_only_variant{var}_ms"] = timeit(lambda: ops.dualpath_fuse(xv, bev, cw, 0.1, ident, Bc, Xc_ * Yc_, Zc_, 128,
-                                                                                        identity_split=True, want_f32=False))
-            res[f"fuse_c128_f32_and_s32_variant{var}_ms"] = timeit(lambda: ops.dualpath_fuse(xv, bev, cw, 0.1, ident, Bc, Xc_ * Yc_, Zc_, 128,
-                                                                                           identity_split=True, want_f32=True))
-        os.environ.pop("OCC_FUSE_VARIANT", None)
+        res["fuse_c128_s32_only_ms"] = timeit(lambda: ops.dualpath_fuse(xv, bev, cw, 0.1, ident, Bc, Xc_ * Yc_, Zc_, 128,
+                                                                        identity_split=True, want_f32=False))
+        res["fuse_c128_f32_and_s32_ms"] = timeit(lambda: ops.dualpath_fuse(xv, bev, cw, 0.1, ident, Bc, Xc_ * Yc_, Zc_, 128,
+                                                                           identity_split=True, want_f32=True))
         del xv, ident
         E = 192
         cur = torch.randn(1, 200, 200, 16, E, device=dev)
