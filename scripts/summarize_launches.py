@@ -24,8 +24,8 @@ def main():
         lines = [l for l in f if l.startswith('"')]
     for r in csv.DictReader(lines):
         rows.append((int(r["ID"]), short(r["Kernel Name"]), float(r["Metric Value"]), r["Grid Size"], r["Block Size"]))
-    marks = [i for i, r in enumerate(rows) if r[1].startswith("vp_index_geom_kernel")]
-    if len(marks) >= 3:
+    marks = [i for i, r in enumerate(rows) if (r[1].startswith("vp_index_geom_kernel") or r[1].startswith("lift_front_kernel"))]
+    if len(marks) >= 2:
         lo, hi = marks[-2], marks[-1]
     else:
         lo, hi = 0, len(rows)
