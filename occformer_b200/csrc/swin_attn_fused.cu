@@ -161,6 +161,8 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*window-layou
           mma_bf16x3_ss(tmem_base + SF_TMEM_U + s1 * 128, adesc0 + (uint64_t)(slot * (SF_SLOT >> 4)),
                         bdesc0 + (uint64_t)(kb * ((96 * 128) >> 4)), IDESC_M1, kb != 0);
           mma_commit(&a_empty[slot]);
+          // (holding the projection to one k-block in flight, so that QK^T / PV never queue behind 24 MMAs, was measured
+          // slower: 0.54 vs 0.48 ms)
           if (++slot == SF_NSLOT) { slot = 0; par ^= 1; }
         }
         mma_commit(&d_ready[s1]);
