@@ -116,8 +116,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 vp_pool_kernel(const int* __restrict__ head, const int* __restrict__ next, int V, int C,
                const float* __restrict__ depth_prob, const float* __restrict__ feat, FastDiv div_dhw, FastDiv div_hw,
-               float* __restrict__ out, float* __restrict__ out_split /*optional S32 copy of the grid (conv operand)*/,
-               int skip_empty /*the rows of empty voxels are already zero (zero-fill CTAs of lift_front_kernel)*/) {
+               float* __restrict__ out, float* __restrict__ out_split /*optional S32 copy of the grid (conv operand)*/) {
   const int lane = threadIdx.x & 31;
   const int C4 = C >> 2;
   const int batch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -127,7 +126,7 @@ vp_pool_kernel(const int* __restrict__ head, const int* __restrict__ next, int V
   const int h0 = lane < nv ? __ldg(head + vb + lane) : 0;
   const uint32_t valid = nv == 32 ? 0xffffffffu : ((1u << nv) - 1u);
   const uint32_t occupied = __ballot_sync(0xffffffffu, h0 != 0);
-  if (!skip_empty) {
+  {
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (uint32_t e = valid & ~occupied; e != 0u; e &= e - 1u) {
       float4* orow = reinterpret_cast<float4*>(out + (size_t)(vb + __ffs(e) - 1) * C);
@@ -345,7 +344,7 @@ extern "C" int occ_lift_splat(const float* depth_prob, const float* feat_cl, con
   OCC_LAUNCH_CHECK();
   vp_pool_kernel<0><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, depth_prob, feat_cl,
                                                                  make_fastdiv((uint32_t)D * HW), make_fastdiv(HW), out,
-                                                                 out_split, 0);
+                                                                 out_split);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -369,7 +368,7 @@ extern "C" int occ_bev_pool(const float* feats, const long long* coords, float* 
     OCC_LAUNCH_CHECK();
   }
   vp_pool_kernel<1><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, nullptr, feats, make_fastdiv(1),
-                                                                 make_fastdiv(1), out, nullptr, 0);
+                                                                 make_fastdiv(1), out, nullptr);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -418,7 +417,7 @@ extern "C" int occ_voxel_pool_geom(const float* feats, const float* geom, float*
                                                              ws.next);
   OCC_LAUNCH_CHECK();
   vp_pool_kernel<1><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, nullptr, feats, make_fastdiv(1),
-                                                                 make_fastdiv(1), out, nullptr, 0);
+                                                                 make_fastdiv(1), out, nullptr);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
@@ -529,23 +528,8 @@ lift_front_kernel(const float* __restrict__ logits /*(BN, D, HW)*/, const float*
                   const float* __restrict__ bda, int bda_dim, int N, int D, int HW, int C, long long lstride,
                   long long fstride, const VpGrid g, float* __restrict__ prob, float* __restrict__ feat_cl, int* __restrict__ vox_id,
                   int* __restrict__ counts, int* __restrict__ head, int* __restrict__ next, int nb_front, int tiles_p,
-                  int tiles_c, int nb_work, float4* __restrict__ zero_a, float4* __restrict__ zero_b, long long zero_n4) {
+                  int tiles_c) {
   __shared__ CamConst cam;
-  if ((int)blockIdx.x >= nb_work) {
-    // ---- zero-fill CTAs: the pooled grid (and its S32 twin) is mostly empty voxels; their zero rows do not depend on
-    // the lists, so they stream out while the front CTAs (latency-bound: softmax, geometry, list pushes) run on the
-    // other SMs.  The pooling kernel then only writes the rows of occupied voxels.
-    const long long nz = gridDim.x - nb_work;
-    const long long per = (zero_n4 + nz - 1) / nz;
-    const long long i0 = ((long long)blockIdx.x - nb_work) * per;
-    const long long i1 = i0 + per < zero_n4 ? i0 + per : zero_n4;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
-      __stcs(zero_a + i, z4);
-      if (zero_b) __stcs(zero_b + i, z4);
-    }
-    return;
-  }
   __shared__ float red[LF_DG][32];
   __shared__ float tile[32][33];
   if ((int)blockIdx.x >= nb_front) {  // ---- context features (BN, C, HW) -> (BN, HW, C)
@@ -631,8 +615,7 @@ extern "C" int occ_lss_geometry(const float* frustum, int P, const float* rots, 
 
 // Fused lift-splat from the view transformer's raw inputs: depth_logits (B*N, D, HW), img_feat (B*N, C, HW) (NCHW, as
 // DepthNet returns them), frustum (D*HW, 3) and the camera matrices of occ_lss_geometry.  Three launches: memset of the
-// list heads, the front kernel (softmax + geometry + voxel index + lists + NHWC transpose, and -- on the SMs the front
-// CTAs leave free -- the zero-fill of the grid), the pooling kernel (rows of occupied voxels only).
+// list heads, the front kernel (softmax + geometry + voxel index + lists + NHWC transpose), the pooling kernel.
 // depth_prob (B*N, D, HW) and feat_cl (B*N, HW, C) are outputs (depth_prob is the module's second return value).
 // logits_stride / feat_stride: floats between consecutive cameras of depth_logits / img_feat (both may be channel
 // slices of DepthNet's (B*N, D + C, fH, fW) output: no copy).
@@ -659,24 +642,17 @@ extern "C" int occ_lift_splat_fused(const float* depth_logits, long long logits_
   const VpGrid vg{dx0, dx1, dx2, bx0, bx1, bx2, nx0, nx1, nx2, X, Y, Z};
   const int tiles_p = (HW + 31) / 32, tiles_c = (C + 31) / 32;
   const int nb_front = B * N * tiles_p;
-  const long long nb_work = (long long)nb_front + (long long)B * N * tiles_p * tiles_c;
-  const long long zero_n4 = (long long)V * (C / 4);
-  // zero-fill CTAs: ~64 KB of grid (x2 with the twin) each, at least two waves of them
-  long long nb_zero = (zero_n4 * 16 + 65535) / 65536;
-  if (nb_zero < 2 * sm_count()) nb_zero = 2 * sm_count();
-  const long long nb = nb_work + nb_zero;
-  OCC_REQUIRE(nb < (1ll << 31) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-              (reinterpret_cast<uintptr_t>(out_split) & 15) == 0);
+  const long long nb = (long long)nb_front + (long long)B * N * tiles_p * tiles_c;
+  OCC_REQUIRE(nb < (1ll << 31));
   lift_front_kernel<<<(unsigned)nb, 256, 0, stream>>>(depth_logits, img_feat, frustum, rots, trans, intrins, intrin_rows,
                                                       intrin_cols, post_rots, post_trans, bda, bda_dim, N, D, HW, C,
                                                       logits_stride, feat_stride, vg,
                                                       depth_prob, feat_cl, ws.vox_id, ws.counts, ws.head, ws.next, nb_front,
-                                                      tiles_p, tiles_c, (int)nb_work, reinterpret_cast<float4*>(out),
-                                                      reinterpret_cast<float4*>(out_split), zero_n4);
+                                                      tiles_p, tiles_c);
   OCC_LAUNCH_CHECK();
   vp_pool_kernel<0><<<((V + 31) / 32 + 7) / 8, 256, 0, stream>>>(ws.head, ws.next, V, C, depth_prob, feat_cl,
                                                                  make_fastdiv((uint32_t)D * HW), make_fastdiv(HW), out,
-                                                                 out_split, 1);
+                                                                 out_split);
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }
