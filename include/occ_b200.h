@@ -114,6 +114,13 @@ int occ_conv_bf16x3(const float* x, const float* w2, float* out, int B, int X, i
  * ASPP branches (1x1 + three dilated 3x3, P/occformer/backbones/modules/aspp.py:107-113) become one 25-tap launch. */
 int occ_conv_taps_bf16x3(const float* x, const float* w2, float* out, int B, int X, int Y, int Z, int Cin, int Cout,
                          int ntaps, const int* taps, double* gn_stats, int cpg, occ_stream_t stream);
+/* Tensor-core passes per 32-k operand block, library-wide launch-time setting (host side; every launcher reads it when it
+ * is called).  3 (default) = fp32-faithful: hi*hi + lo*hi + hi*lo, the mode of every parity claim against the reference.
+ * 1 = single-pass bf16 operands (hi halves only): BASELINE config 5's "bf16" -- a third of the tensor work, ~3e-3
+ * relative error per contraction; the reference has no twin of it, it is validated against the fp32 oracle at
+ * its own tolerance.  occ_set_mma_passes returns the previous value, or -1 for an unsupported count. */
+int occ_set_mma_passes(int passes);
+int occ_get_mma_passes(void);
 /* fp32 rows (rows, C) <-> S32 (C % 32 == 0) */
 int occ_split_rows(const float* in, float* out, long long rows, int C, occ_stream_t stream);
 int occ_unsplit_rows(const float* in, float* out, long long rows, int C, occ_stream_t stream);

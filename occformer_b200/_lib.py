@@ -30,6 +30,8 @@ SIGNATURES = {
     "occ_conv_workspace_bytes": (c_size_t, []),
     "occ_conv_bf16x3": (c_int, [P, P, P] + [c_int] * 11 + [P, P, c_int, c_int, P, c_int, P, c_size_t, STREAM]),
     "occ_conv_taps_bf16x3": (c_int, [P, P, P] + [c_int] * 7 + [P, P, c_int, STREAM]),
+    "occ_set_mma_passes": (c_int, [c_int]),
+    "occ_get_mma_passes": (c_int, []),
     "occ_split_rows": (c_int, [P, P, c_longlong, c_int, STREAM]),
     "occ_unsplit_rows": (c_int, [P, P, c_longlong, c_int, STREAM]),
     "occ_gn_relu_zmean_ln": (c_int, [P] * 8 + [c_int] * 7 + [STREAM]),

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1)
 cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const float* __restrict__ qh, int koff, int voff, const uint32_t* __restrict__ bits /*(B,NW,Q)*/,
                      const int* __restrict__ row_flag, float* __restrict__ part, int S, int Q, int E, int H,
-                     int tiles_per_chunk, int nchunk) {
+                     int tiles_per_chunk, int nchunk, int passes) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -117,7 +117,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
           tc_fence_after();
           const uint64_t kdesc = make_sw128_desc(smem_u32(smem + (size_t)(nq % XT_STAGES) * XT_STAGE_BYTES), 1024, 16);
           const uint32_t s_tmem = tmem_base + (nq & 1) * 128;
-          mma_bf16x3_ss(s_tmem, qdesc, kdesc, IDESC_QK, 0u);
+          mma_bf16x3_ss(s_tmem, qdesc, kdesc, IDESC_QK, 0u, passes);
           mma_commit(&s_ready[nq & 1]);
           ++nq;
         }
@@ -133,7 +133,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
             for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA = two 8-key (1024 B) atoms of V rows
               const uint32_t pc = p_tmem + (kk >> 1) * 32 + (kk & 1) * 8;
               mma_bf16_ts(o_tmem, pc, vdesc + (uint64_t)(kk * 128), IDESC_PV, kk != 0);  // P_hi [V_hi | V_lo]
-              mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);  // P_lo [V_hi | V_lo]
+              if (passes == 3) mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);  // P_lo [V_hi | V_lo]
             }
             mma_commit(&o_ready[tb]);
             mma_commit(&empty_bar[s]);
@@ -314,7 +314,7 @@ extern "C" int occ_cross_attn_tc(const float* qh, const float* Kp, const float* 
   OCC_ENSURE_SMEM(cross_attn_tc_kernel, smem);
   dim3 grid(nchunk, H, B);
   cross_attn_tc_kernel<<<grid, XT_THREADS, smem, stream>>>(tmK, tmV, qh, koff, voff, bits, row_flag, part, S, Q, E, H, tpc,
-                                                           nchunk);
+                                                           nchunk, mma_passes());
   OCC_LAUNCH_CHECK();
   return OCC_OK;
 }

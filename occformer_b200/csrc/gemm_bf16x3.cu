@@ -46,6 +46,7 @@ struct GemmParams {
                   // (zero-initialised by the host) through TMA reduce-add; no bias / act / stats in the kernel
   int act;        // 0 none, 1 relu, 2 gelu(erf)
   int split_out;  // write the result in the S32 split format (the consumer is another tensor-core contraction)
+  int passes;     // tensor-core passes per 32-k block (occ_common.cuh: mma_passes)
   // conv mode
   int conv;
   int Cin, KX, KY, KZ, dil, stride;
@@ -274,7 +275,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int sub = 0; sub < MT; ++sub) {
             const uint64_t adesc = make_sw128_desc(sa + sub * A_STAGE_BYTES, 1024, 16);
             // one S32 row block = 32 k values: hi*hi + lo*hi + hi*lo, six K=16 MMAs stepping 32 bytes inside the row
-            mma_bf16x3_ss(d_tmem + sub * BN, adesc, bdesc, IDESC, kb != kb0);
+            mma_bf16x3_ss(d_tmem + sub * BN, adesc, bdesc, IDESC, kb != kb0, p.passes);
           }
           mma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -709,6 +710,7 @@ extern "C" int occ_gemm_bf16x3(const float* A, const float* W, float* out, int M
   if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && N % cpg == 0 && N / cpg <= MAX_STAT_GROUPS &&
                             rows_per_batch > 0 && rows_per_batch % BM == 0);
   GemmParams p{};
+  p.passes = mma_passes();
   p.M = M; p.N = N; p.K = K; p.num_k_blocks = (K + BK - 1) / BK;
   p.out = out; p.ldo = N; p.bias = bias; p.residual = residual; p.ldr = N; p.act = act; p.split_out = split_out;
   p.conv = 0; p.gn_stats = gn_stats; p.cpg = cpg; p.rows_per_batch = gn_stats ? rows_per_batch : 0;
@@ -749,6 +751,7 @@ extern "C" int occ_conv_bf16x3(const float* x, const float* w2, float* out, int 
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0);
   if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && Cout % cpg == 0 && Cout / cpg <= MAX_STAT_GROUPS);
   GemmParams p{};
+  p.passes = mma_passes();
   p.conv = 1;
   p.Cin = Cin; p.KX = KX; p.KY = KY; p.KZ = KZ; p.dil = dil; p.stride = stride;
   p.padx = dil * (KX - 1) / 2; p.pady = dil * (KY - 1) / 2; p.padz = dil * (KZ - 1) / 2;
@@ -844,6 +847,7 @@ extern "C" int occ_conv_taps_bf16x3(const float* x, const float* w2, float* out,
               (reinterpret_cast<uintptr_t>(out) & 15) == 0 && Cout % 4 == 0);
   if (gn_stats) OCC_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && Cout % cpg == 0 && Cout / cpg <= MAX_STAT_GROUPS);
   GemmParams p{};
+  p.passes = mma_passes();
   p.conv = 1;
   p.Cin = Cin; p.KX = p.KY = p.KZ = 1; p.dil = 1; p.stride = 1; p.padx = p.pady = p.padz = 0;
   p.ntaps = ntaps;
@@ -906,6 +910,7 @@ extern "C" int occ_mask_gemm_pool(const float* mf, const float* membed, float* m
   OCC_CUDA(cudaMemsetAsync(flag, 0, (size_t)B * Q * sizeof(int), stream));
   for (int b = 0; b < B; ++b) {
     GemmParams p{};
+    p.passes = mma_passes();
     p.conv = 1;
     p.Cin = E; p.KX = p.KY = p.KZ = 1; p.dil = 1; p.stride = 1; p.padx = p.pady = p.padz = 0;
     p.B = 1; p.Xo = X; p.Yo = Y; p.Zo = Z;

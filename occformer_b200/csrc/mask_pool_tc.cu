@@ -29,6 +29,7 @@ struct MaskPoolParams {
   int Q, E, KB, stages;
   int tiles_y, tiles_z, n_tiles;  // tiles of one sample
   int Xo, Yo, Zo;
+  int passes;  // tensor-core passes per 32-k block (occ_common.cuh: mma_passes)
 };
 
 __device__ __forceinline__ int ordered_int(float f) {
@@ -122,7 +123,7 @@ mask_pool_tc_kernel(const __grid_constant__ CUtensorMap tmB, const MaskPoolParam
           tc_fence_after();
           const uint64_t adesc = make_sw128_desc(smem_u32(sa + (size_t)kb * MP_KB_BYTES), 1024, 16);
           const uint64_t bdesc = make_sw128_desc(smem_u32(ring + (size_t)s * MP_KB_BYTES), 1024, 16);
-          mma_bf16x3_ss(d_tmem, adesc, bdesc, IDESC, kb != 0);
+          mma_bf16x3_ss(d_tmem, adesc, bdesc, IDESC, kb != 0, p.passes);
           mma_commit(&empty_bar[s]);
         }
         mma_commit(&acc_full[buf]);
@@ -214,6 +215,7 @@ int mask_pool_query_stationary(const float* mf, const float* membed, int* pooled
   const int wx = X / Xo, wy = Y / Yo, wz = Z / Zo;
   if (wx != wy || wy != wz || E % 32 != 0 || Q > 128 || B > 65535) return 1;
   MaskPoolParams p{};
+  p.passes = mma_passes();
   p.membed = membed; p.pooled = pooled; p.flag = flag;
   p.Q = Q; p.E = E; p.KB = E / 32; p.Xo = Xo; p.Yo = Yo; p.Zo = Zo;
   const int budget = 227 * 1024 - 1024 - 256 - p.KB * MP_KB_BYTES;

@@ -86,6 +86,11 @@ inline int sm_count() {
     }                                                                                                             \
   } while (0)
 
+// Tensor-core passes per 32-k operand block: 3 = fp32-faithful (hi*hi + lo*hi + hi*lo, the default and the only mode the
+// parity gate covers), 1 = single-pass bf16 (hi*hi only; occ_set_mma_passes, csrc/config.cu).  Host-side setting, read by
+// every launcher at launch time and handed to the kernel as an argument.
+int mma_passes();
+
 // fp32 tensor map, rank <= 5, 128-byte swizzle, zero OOB fill.  dims/box/estr innermost first;
 // strides_bytes[i] = byte stride of dim i+1.
 inline int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,

@@ -274,22 +274,26 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 // The three passes of one 32-k S32 row block (A, B K-major SWIZZLE_128B tiles in shared memory): 6 MMAs of K = 16.
 // `acc0` = accumulate flag of the very first MMA.
 __device__ __forceinline__ void mma_bf16x3_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                              uint32_t acc0) {
+                                              uint32_t acc0, int passes = 3) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     mma_bf16_ss(d_tmem, adesc + 2 * h, bdesc + 2 * h, idesc, h ? 1u : acc0);  // hi * hi
-    mma_bf16_ss(d_tmem, adesc + 2 * (2 + h), bdesc + 2 * h, idesc, 1u);       // lo * hi
-    mma_bf16_ss(d_tmem, adesc + 2 * h, bdesc + 2 * (2 + h), idesc, 1u);       // hi * lo
+    if (passes == 3) {  // (warp-uniform) single-pass bf16 mode stops here: occ_set_mma_passes(1)
+      mma_bf16_ss(d_tmem, adesc + 2 * (2 + h), bdesc + 2 * h, idesc, 1u);     // lo * hi
+      mma_bf16_ss(d_tmem, adesc + 2 * h, bdesc + 2 * (2 + h), idesc, 1u);     // hi * lo
+    }
   }
 }
 // Same with the A block in TMEM: 32 columns = [16 packed hi | 16 packed lo] of 32 k values.
 __device__ __forceinline__ void mma_bf16x3_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                              uint32_t acc0) {
+                                              uint32_t acc0, int passes = 3) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     mma_bf16_ts(d_tmem, a_tmem + 8 * h, bdesc + 2 * h, idesc, h ? 1u : acc0);       // hi * hi
-    mma_bf16_ts(d_tmem, a_tmem + 16 + 8 * h, bdesc + 2 * h, idesc, 1u);             // lo * hi
-    mma_bf16_ts(d_tmem, a_tmem + 8 * h, bdesc + 2 * (2 + h), idesc, 1u);            // hi * lo
+    if (passes == 3) {
+      mma_bf16_ts(d_tmem, a_tmem + 16 + 8 * h, bdesc + 2 * h, idesc, 1u);           // lo * hi
+      mma_bf16_ts(d_tmem, a_tmem + 8 * h, bdesc + 2 * (2 + h), idesc, 1u);          // hi * lo
+    }
   }
 }
 

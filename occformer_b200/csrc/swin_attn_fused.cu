@@ -159,7 +159,7 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*window-layou
           mbar_wait(&a_full[slot], par);
           tc_fence_after();
           mma_bf16x3_ss(tmem_base + SF_TMEM_U + s1 * 128, adesc0 + (uint64_t)(slot * (SF_SLOT >> 4)),
-                        bdesc0 + (uint64_t)(kb * ((96 * 128) >> 4)), IDESC_M1, kb != 0);
+                        bdesc0 + (uint64_t)(kb * ((96 * 128) >> 4)), IDESC_M1, kb != 0, g.passes);
           mma_commit(&a_empty[slot]);
           // (holding the projection to one k-block in flight, so that QK^T / PV never queue behind 24 MMAs, was measured
           // slower: 0.54 vs 0.48 ms)
@@ -176,7 +176,7 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*window-layou
         mbar_wait(&qkv_full[sq], pq);  // Q / K / V tiles converted (D of the unit, in the same TMEM slot, is dead by then)
         fence_proxy_async_smem();
         tc_fence_after();
-        mma_bf16x3_ss(tmem_base + SF_TMEM_U + sq * 128, qdesc, kdesc, IDESC_QK, 0u);
+        mma_bf16x3_ss(tmem_base + SF_TMEM_U + sq * 128, qdesc, kdesc, IDESC_QK, 0u, g.passes);
         mma_commit(&s_ready[sq]);
         mma_commit(&qk_free[sq]);  // the single Q / K tiles may be overwritten by the next unit's conversion
         if (++sq == SF_NWG) { sq = 0; pq ^= 1; }
@@ -195,7 +195,7 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*window-layou
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t pc = p_tmem + (kk >> 1) * 32 + (kk & 1) * 8;
           mma_bf16_ts(o_tmem, pc, vdesc + (uint64_t)(kk * 128), IDESC_PV, kk != 0);
-          mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);
+          if (g.passes == 3) mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);
         }
         mma_commit(&o_ready[sp]);
         mma_commit(&v_empty[sp]);

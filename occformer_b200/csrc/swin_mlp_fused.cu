@@ -38,6 +38,7 @@ struct SwinMlpParams {
   float* out;        // (M, 128)
   long long M;
   int n_tiles;
+  int passes;  // tensor-core passes per 32-k block (occ_common.cuh: mma_passes)
 };
 
 // GELU(x) = x * Phi(x) with erfc(z) = P(t) exp(-z^2), t = 1 / (1 + p z) (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7):
@@ -164,7 +165,7 @@ swin_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tc_fence_after();
           const uint64_t adesc = make_sw128_desc(smem_u32(att_ring + (size_t)sa * SMF_SLOT), 1024, 16);
           const uint64_t bdesc = make_sw128_desc(smem_u32(w_ring + (size_t)sw * SMF_SLOT), 1024, 16);
-          mma_bf16x3_ss(d_tmem, adesc, bdesc, IDESC, kb != 0);
+          mma_bf16x3_ss(d_tmem, adesc, bdesc, IDESC, kb != 0, p.passes);
           mma_commit(&att_empty[sa]);
           mma_commit(&w_empty[sw]);
         }
@@ -181,7 +182,7 @@ swin_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tc_fence_after();
           const uint64_t bdesc = make_sw128_desc(smem_u32(w_ring + (size_t)sw * SMF_SLOT), 1024, 16);
           // A block kb in TMEM: 32 columns = [16 packed hi | 16 packed lo] of k = 32 kb .. 32 kb + 31
-          mma_bf16x3_ts(d_tmem, a_tmem + kb * 32, bdesc, IDESC, (third || kb != 0) ? 1u : 0u);
+          mma_bf16x3_ts(d_tmem, a_tmem + kb * 32, bdesc, IDESC, (third || kb != 0) ? 1u : 0u, p.passes);
           mma_commit(&w_empty[sw]);
         }
         mma_commit(d23_ready);
@@ -350,6 +351,7 @@ extern "C" int occ_swin_proj_ffn(const float* att, const float* tok, const float
     if (rc) return rc;
   }
   SwinMlpParams p{};
+  p.passes = mma_passes();
   p.tok = tok; p.bp = bp; p.lnw = ln_w; p.lnb = ln_b; p.b1 = b1; p.b2 = b2; p.out = out; p.M = M;
   p.n_tiles = (int)((M + 127) / 128);
   const size_t smem = (size_t)(SMF_ATT_SLOTS + SMF_W_SLOTS + 4) * SMF_SLOT + (5 * SMF_C + 8 * 128) * sizeof(float) + 1024 /*align*/ + 512;

@@ -177,7 +177,7 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         const uint32_t qaddr = smem_u32(smem + (size_t)s * WA_STAGE_BYTES);
         const uint64_t qdesc = make_sw128_desc(qaddr, 1024, 16);
         const uint64_t kdesc = make_sw128_desc(qaddr + WA_TILE, 1024, 16);
-        mma_bf16x3_ss(tmem_base + tb * 128, qdesc, kdesc, IDESC_QK, 0u);
+        mma_bf16x3_ss(tmem_base + tb * 128, qdesc, kdesc, IDESC_QK, 0u, g.passes);
         mma_commit(&s_ready[tb]);
         if (++s == WA_STAGES) { s = 0; par ^= 1; }
       }
@@ -197,7 +197,7 @@ window_attn_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ q
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t pc = p_tmem + (kk >> 1) * 32 + (kk & 1) * 8;
           mma_bf16_ts(o_tmem, pc, vdesc + (uint64_t)(kk * 128), IDESC_PV, kk != 0);       // P_hi [V_hi | V_lo]
-          mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);       // P_lo [V_hi | V_lo]
+          if (g.passes == 3) mma_bf16_ts(o_tmem, pc + 16, vdesc + (uint64_t)(kk * 128), IDESC_PV, 1u);  // P_lo [V_hi | V_lo]
         }
         mma_commit(&o_ready[tb]);
         mma_commit(&empty_bar[s]);
@@ -339,13 +339,8 @@ extern "C" int occ_window_attention(const float* qkv, const float* qkv_bias, con
   OCC_REQUIRE(B > 0 && X > 0 && Y > 0 && Z > 0 && heads > 0 && C == heads * HD);
   OCC_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv_bias) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(bias_pad) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  WinGeom g;
-  g.B = B; g.X = X; g.Y = Y; g.Z = Z; g.C = C; g.heads = heads; g.shift = shift ? 1 : 0;
+  WinGeom g = make_win_geom(B, X, Y, Z, C, heads, shift);
   g.head_major = qkv_head_major ? 1 : 0;
-  g.nWx = (X + WS - 1) / WS; g.nWy = (Y + WS - 1) / WS;
-  g.Xp = g.nWx * WS; g.Yp = g.nWy * WS;
-  g.vox_rows = (long long)B * X * Y * Z;
-  g.nwin = (long long)B * (Z + 1) * g.nWx * g.nWy;
   OCC_REQUIRE(g.nwin < (1ll << 31));
   const size_t smem = (size_t)WA_STAGES * WA_STAGE_BYTES + WA_BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   OCC_ENSURE_SMEM(window_attn_tc_kernel, smem);

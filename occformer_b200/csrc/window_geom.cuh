@@ -29,6 +29,7 @@ struct WinGeom {
   int Xp, Yp, nWx, nWy;
   long long vox_rows;  // B*X*Y*Z
   long long nwin;
+  int passes;  // tensor-core passes per 32-k block (occ_common.cuh: mma_passes)
 };
 
 // token t of window (img, wx, wy) -> global token row (or -1 for a pad token) and shift-mask region id
@@ -77,6 +78,7 @@ inline WinGeom make_win_geom(int B, int X, int Y, int Z, int C, int heads, int s
   g.Xp = g.nWx * WS; g.Yp = g.nWy * WS;
   g.vox_rows = (long long)B * X * Y * Z;
   g.nwin = (long long)B * (Z + 1) * g.nWx * g.nWy;
+  g.passes = mma_passes();
   return g;
 }
 

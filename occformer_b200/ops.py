@@ -38,6 +38,32 @@ def _chk(t, name, dtype=torch.float32):
 # Operands of every tensor-core contraction are fp32 values stored as bf16 hi | lo halves per 32-column chunk (csrc/
 # occ_ptx.cuh, include/occ_b200.h): same bytes and row pitch as the fp32 tensor, ~1e-5 relative error after the three
 # bf16 passes.  Weights are split once at load time (torch ops below), activations by the producing kernel's epilogue.
+def set_precision(mode):
+    """"fp32" (default): every contraction in three bf16 tensor-core passes on hi/lo split operands (fp32-faithful, the
+    mode of every parity claim).  "bf16": single pass on the hi halves (BASELINE config 5; ~3e-3 relative error per
+    contraction, no reference twin).  Library-wide, takes effect for kernels launched afterwards.  Returns the old mode."""
+    passes = {"fp32": 3, "bf16": 1}[mode]
+    prev = lib().occ_set_mma_passes(passes)
+    if prev < 0:
+        raise RuntimeError("occ_set_mma_passes failed")
+    return {3: "fp32", 1: "bf16"}[prev]
+
+
+class precision:
+    """``with ops.precision("bf16"): ...`` -- scoped set_precision."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = set_precision(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        set_precision(self.prev)
+        return False
+
+
 def split_weight(w):
     """(N, K) fp32 torch tensor (any device), K % 32 == 0 -> the same tensor in S32 (fp32 container, same shape)."""
     w = w.detach().float().contiguous()
