@@ -137,6 +137,9 @@ int occ_gn_relu_zmean_ln(const float* y, const double* stats, const float* gn_w,
                          const float* ln_w, const float* ln_b, float* tok, float* tokn, int B, int XY, int Z, int C,
                          int groups, int X, int win_shift, occ_stream_t stream);
 long long occ_window_layout_rows(int B, int X, int Y, int Z);
+/* GroupNorm statistics from a conv / GEMM epilogue at a finer power-of-two grouping -> the module's groups:
+ * out (B, groups_out, 2) = sums of `factor` consecutive entries of in (B, groups_out * factor, 2), fp64. */
+int occ_stats_regroup(const double* in, double* out, int B, int groups_out, int factor, occ_stream_t stream);
 int occ_layernorm(const float* in, const float* w, const float* b, float* out, long long rows, int C, int split_out,
                   occ_stream_t stream);
 /* o = act(gn(in[row, c])) (+ residual[row, c]) -- ASPP / neck norms (aspp.py:42-46,117-120,166-172): out[row, c] = o

@@ -36,6 +36,7 @@ SIGNATURES = {
     "occ_unsplit_rows": (c_int, [P, P, c_longlong, c_int, STREAM]),
     "occ_gn_relu_zmean_ln": (c_int, [P] * 8 + [c_int] * 7 + [STREAM]),
     "occ_window_layout_rows": (c_longlong, [c_int] * 4),
+    "occ_stats_regroup": (c_int, [P, P, c_int, c_int, c_int, STREAM]),
     "occ_layernorm": (c_int, [P, P, P, P, c_longlong, c_int, c_int, STREAM]),
     "occ_gn_apply": (c_int, [P] * 7 + [c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, STREAM]),
     "occ_aspp_gap_branch": (c_int, [P] * 6 + [c_int] * 6 + [STREAM]),

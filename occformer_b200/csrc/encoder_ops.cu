@@ -614,3 +614,23 @@ extern "C" long long occ_window_layout_rows(int B, int X, int Y, int Z) {
   const WinGeom g = make_win_geom(B, X, Y, Z, 128, 4, 0);
   return (g.nwin + 1) / 2 * 128;
 }
+
+// GroupNorm statistics gathered by a conv epilogue at a finer, power-of-two grouping (cpg' channels) -> the module's
+// groups of factor * cpg' channels: out[b][g] = sum_f in[b][g * factor + f]  (192 channels / 32 groups: cpg = 6 = 3 pairs).
+__global__ void stats_regroup_kernel(const double* __restrict__ in, double* __restrict__ out, int n_out, int factor) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (b, g, {sum, sumsq}) flattened
+  if (i >= n_out) return;
+  const int bg = i >> 1, w = i & 1;
+  double a = 0.0;
+  for (int f = 0; f < factor; ++f) a += in[((size_t)bg * factor + f) * 2 + w];
+  out[i] = a;
+}
+
+extern "C" int occ_stats_regroup(const double* in, double* out, int B, int groups_out, int factor, cudaStream_t stream) {
+  OCC_REQUIRE(in && out && B > 0 && groups_out > 0 && factor > 0);
+  const int n = B * groups_out * 2;
+  stats_regroup_kernel<<<(n + 127) / 128, 128, 0, stream>>>(in, out, n, factor);
+  OCC_LAUNCH_CHECK();
+  return OCC_OK;
+}
+

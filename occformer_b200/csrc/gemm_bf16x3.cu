@@ -30,9 +30,9 @@ constexpr int BK = 32;  // 32 fp32 = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 4;
 constexpr int EPI_BUF_BYTES = 32 * 128;                 // one 32-row x 32-column fp32 chunk, 128-byte swizzled rows
 constexpr int EPI_BYTES = 8 /*warps*/ * EPI_BUF_BYTES;
-constexpr int CTRL_BYTES = 2048;   // mbarriers + TMEM pointer + fp64 GroupNorm partial sums of up to 64 groups; a multiple
+constexpr int CTRL_BYTES = 2048;   // mbarriers + TMEM pointer + fp64 GroupNorm partial sums of up to 96 groups; a multiple
                                    // of 1024 so that the swizzled epilogue staging buffers behind it stay 1024-byte aligned
-constexpr int MAX_STAT_GROUPS = 64;
+constexpr int MAX_STAT_GROUPS = 96;  // 2 * 96 doubles = 1536 B of CTRL_BYTES (barriers + TMEM pointer < 256 B)
 constexpr int MAX_TAPS = 28;
 
 struct GemmParams {

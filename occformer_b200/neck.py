@@ -146,6 +146,17 @@ class MSDeformAttnPixelDecoder3D(nn.Module):
         self._prep = P
         return P
 
+    @staticmethod
+    def _conv_stats(x_s, w, k, B, E, G, plan):
+        """conv + the GroupNorm statistics (B, G, 2) of its raw output"""
+        if plan is None:
+            out = ops.conv(x_s, w, k)
+            return out, ops.gn_stats(out.view(-1, E), B, out.shape[1] * out.shape[2] * out.shape[3], E, G)
+        sub, factor = plan
+        sub_stats = torch.zeros(B, E // sub, 2, dtype=torch.float64, device=x_s.device)
+        out = ops.conv(x_s, w, k, gn_stats=sub_stats, cpg=sub)
+        return out, ops.stats_regroup(sub_stats, G, factor)
+
     def _pos_rows(self, grids, device):
         """query_pos of the encoder (:160-163): sine encoding of every level + its level embedding, (Nq, E), cached per grid"""
         key = (tuple(grids), str(device))
@@ -207,13 +218,13 @@ class MSDeformAttnPixelDecoder3D(nn.Module):
         mf_s = None
         for i in range(nin - L - 1, -1, -1):
             lat, oc = self.lateral_convs[i], self.output_convs[i]
-            cur = ops.conv(self._operand(feats[i]), P["lat"][i], (1, 1, 1))
+            # GroupNorm statistics of both convs ride in their epilogues (at the power-of-two sub-group, regrouped after)
+            plan = ops.epilogue_stats_plan(E, G)
+            cur, st = self._conv_stats(self._operand(feats[i]), P["lat"][i], (1, 1, 1), B, E, G, plan)
             Bc, X, Y, Z, _ = cur.shape
-            st = ops.gn_stats(cur.view(-1, E), B, X * Y * Z, E, G)
             y_s = ops.gn_upsample_add(cur, st, lat.gn.weight, lat.gn.bias, G, outs[-1])
             w3, k3 = P["out"][i]
-            o_raw = ops.conv(y_s, w3, k3)
-            st = ops.gn_stats(o_raw.view(-1, E), B, X * Y * Z, E, G)
+            o_raw, st = self._conv_stats(y_s, w3, k3, B, E, G, plan)
             need_f32 = i > 0  # a finer FPN level up-samples it; the finest one only feeds mask_feature
             o, o_s = ops.gn_apply(o_raw.view(-1, E), st, oc.gn.weight, oc.gn.bias, X * Y * Z, G, relu=True,
                                   want_f32=need_f32, want_split=True)

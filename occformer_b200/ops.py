@@ -661,6 +661,28 @@ def _grids_arr(grids):
     return (ctypes.c_int * len(flat))(*flat)
 
 
+def epilogue_stats_plan(C, groups):
+    """GroupNorm statistics can ride in the conv / GEMM epilogue when the group size is a power of two; otherwise (192
+    channels / 32 groups: 6 = 2 * 3) the epilogue gathers them at the largest power-of-two sub-group and stats_regroup sums
+    `factor` of those.  -> (cpg_epilogue, factor) or None when the epilogue cannot hold the sub-groups (> 96)."""
+    cpg = C // groups
+    sub = cpg & -cpg  # largest power-of-two divisor
+    if sub > 32:
+        sub = 32
+    factor = cpg // sub
+    return (sub, factor) if C // sub <= 96 else None
+
+
+def stats_regroup(sub_stats, groups, factor):
+    B = sub_stats.shape[0]
+    if factor == 1:
+        return sub_stats
+    out = torch.empty((B, groups, 2), dtype=torch.float64, device=sub_stats.device)
+    check(lib().occ_stats_regroup(_ptr(sub_stats), _ptr(out), B, groups, factor, _stream(sub_stats)), "occ_stats_regroup")
+    LAUNCH_COUNT[0] += 1
+    return out
+
+
 def gn_stats(x, B, rows_per_batch, C, groups):
     """fp64 (sum, sumsq) per (sample, group) of x (B*rows_per_batch, C) -> (B, groups, 2); for the group sizes the conv
     epilogue does not accumulate (C / groups not a power of two)."""
