@@ -336,6 +336,37 @@ def rooflines(pipe, dev, peak):
              "note": f"unfused attention core: rows*(3C+C)*4 = {by / 1e9:.2f} GB in/out per launch bound it by HBM; "
                      f"algorithmic QK^T+PV = {fl / 1e9:.1f} GF; tensor-pipe % from ncu: profiles/"}
     del qkv
+    # ---- 2b. the kernel the pipeline runs at stage 0: QKV projection + shifted-window attention fused (swin_attn_fused.cu)
+    tokn_wl = ops.to_window_layout(ops.to_split(torch.randn(rows, C, device=dev)), B, X, Y, Z, True)
+    wq = ops.split_weight(torch.randn(3 * C, C) * C ** -0.5).to(dev)
+    bq = torch.randn(3 * C, device=dev) * 0.1
+    ms_f = _time_cuda(lambda: ops.swin_qkv_attention(tokn_wl, wq, bq, bias_pad, B, X, Y, Z, C, heads, True), dev, flush=flush)
+    fl_f = 2.0 * rows * C * 3 * C + fl          # QKV projection of every token + QK^T + PV per window
+    by_f = tokn_wl.numel() * 4.0 + rows * C * 4.0
+    ach_f = fl_f / (ms_f * 1e-3) / 1e12
+    fused = {"kernel": f"swin_qkv_attn_kernel (stage 0, {X}x{Y}x({Z}+1) images: QKV projection + window attention)", "bound": "tensor",
+             "achieved": ach_f, "peak": peak["tf"], "unit": "TFLOP/s", "frac": ach_f / peak["tf"], "passes": PASSES,
+             "frac_of_3pass_ceiling": PASSES * ach_f / peak["tf"], "traffic": None, "ms_per_launch": ms_f,
+             "hbm_GBps": by_f / (ms_f * 1e-3) / 1e9, "peak_src": f"bf16 dense burst, {peak['src']}",
+             "note": f"algorithmic FLOPs 2*rows*C*3C + nwin*4*49^2*C = {fl_f / 1e9:.1f} GF per launch (real tokens only: the kernel "
+                     f"pads 98 -> 128 rows per window pair, 1.31x executed); ncu tensor-pipe active 48 % "
+                     f"(profiles/r02_ncu_swin_qkv_attn_v7.md); bytes = window-layout tokens in + attention out = {by_f / 1e9:.2f} GB"}
+    del tokn_wl
+    # ---- 2c. Conv3d 3x3x3 of stage 1 (C = 256, half-resolution grid): the <256, 4, 1> instantiation
+    X1, Y1, Z1 = X // 2, Y // 2, Z // 2
+    x1 = ops.to_split(torch.randn(B, X1, Y1, Z1, 256, device=dev) * 0.5)
+    w21, ks1 = ops.repack_conv_weight(torch.randn(256, 256, 3, 3, 3) * 0.02)
+    w21 = w21.to(dev)
+    st1 = torch.zeros(B, 32, 2, dtype=torch.float64, device=dev)
+    ms_1 = _time_cuda(lambda: ops.conv(x1, w21, ks1, gn_stats=st1, cpg=8), dev, flush=flush)
+    fl_1 = 2.0 * 27 * 256 * 256 * B * X1 * Y1 * Z1
+    ach_1 = fl_1 / (ms_1 * 1e-3) / 1e12
+    conv256 = {"kernel": f"gemm_bf16x3_kernel<256, 4, 1> (conv3d 3x3x3, C=256, {X1}x{Y1}x{Z1})", "bound": "tensor", "achieved": ach_1,
+               "peak": peak["tf"], "unit": "TFLOP/s", "frac": ach_1 / peak["tf"], "passes": PASSES,
+               "frac_of_3pass_ceiling": PASSES * ach_1 / peak["tf"], "traffic": None, "ms_per_launch": ms_1,
+               "peak_src": f"bf16 dense burst, {peak['src']}",
+               "note": f"algorithmic FLOPs 2*27*256*256*V = {fl_1 / 1e9:.1f} GF per launch"}
+    del x1
     # ---- 3. voxel pooling (fused lift-splat), with and without the prologue (depth softmax, NCHW->NHWC, geometry)
     gc = synth.grid_config(GRID)
     fH, fW = INPUT_SIZE[0] // DOWNSAMPLE, INPUT_SIZE[1] // DOWNSAMPLE
@@ -376,7 +407,7 @@ def rooflines(pipe, dev, peak):
                     f"launch, all three launches of the call timed together; the pipeline's call also writes the S32 twin of the grid "
                     f"({grid_b / 1e6:.0f} MB, operand of the encoder's first conv): 'shipped_with_s32_twin' counts those bytes as traffic; "
                     f"'index_and_pool_kernels_only' = vp_index_geom + vp_pool on a materialised geometry tensor (+ n_pts*12 bytes)"}
-    return conv, {"window_attn": wattn, "voxel_pool": pool}
+    return conv, {"window_attn": wattn, "swin_qkv_attn_fused": fused, "conv_c256": conv256, "voxel_pool": pool}
 
 
 def run_b200(args, rank, world, local_rank):

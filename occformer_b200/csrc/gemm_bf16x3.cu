@@ -608,13 +608,13 @@ static int next_pow2(int v) {
 constexpr int GS_ROWS = 32;
 __global__ void __launch_bounds__(256)
 conv_gn_stats_kernel(const float* __restrict__ out, double* __restrict__ stats, int rows_per_batch, int C, int cpg) {
-  __shared__ double sg[64];
+  __shared__ double sg[2 * MAX_STAT_GROUPS];
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * GS_ROWS;
   const int nr = min(GS_ROWS, rows_per_batch - r0);
   const int groups = C / cpg;
   const int C4 = C >> 2;
-  if (threadIdx.x < 64) sg[threadIdx.x] = 0.0;
+  if (threadIdx.x < 2 * MAX_STAT_GROUPS) sg[threadIdx.x] = 0.0;
   __syncthreads();
   const float4* base = reinterpret_cast<const float4*>(out + ((size_t)b * rows_per_batch + r0) * C);
   for (int c4 = threadIdx.x; c4 < C4; c4 += 256) {
