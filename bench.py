@@ -344,7 +344,7 @@ def rooflines(pipe, dev, peak):
     fl_f = 2.0 * rows * C * 3 * C + fl          # QKV projection of every token + QK^T + PV per window
     by_f = tokn_wl.numel() * 4.0 + rows * C * 4.0
     ach_f = fl_f / (ms_f * 1e-3) / 1e12
-    fused = {"kernel": f"swin_qkv_attn_kernel (stage 0, {X}x{Y}x({Z}+1) images: QKV projection + window attention)", "bound": "tensor",
+    fused_attn = {"kernel": f"swin_qkv_attn_kernel (stage 0, {X}x{Y}x({Z}+1) images: QKV projection + window attention)", "bound": "tensor",
              "achieved": ach_f, "peak": peak["tf"], "unit": "TFLOP/s", "frac": ach_f / peak["tf"], "passes": PASSES,
              "frac_of_3pass_ceiling": PASSES * ach_f / peak["tf"], "traffic": None, "ms_per_launch": ms_f,
              "hbm_GBps": by_f / (ms_f * 1e-3) / 1e9, "peak_src": f"bf16 dense burst, {peak['src']}",
@@ -407,7 +407,7 @@ def rooflines(pipe, dev, peak):
                     f"launch, all three launches of the call timed together; the pipeline's call also writes the S32 twin of the grid "
                     f"({grid_b / 1e6:.0f} MB, operand of the encoder's first conv): 'shipped_with_s32_twin' counts those bytes as traffic; "
                     f"'index_and_pool_kernels_only' = vp_index_geom + vp_pool on a materialised geometry tensor (+ n_pts*12 bytes)"}
-    return conv, {"window_attn": wattn, "swin_qkv_attn_fused": fused, "conv_c256": conv256, "voxel_pool": pool}
+    return conv, {"window_attn": wattn, "swin_qkv_attn_fused": fused_attn, "conv_c256": conv256, "voxel_pool": pool}
 
 
 def run_b200(args, rank, world, local_rank):
