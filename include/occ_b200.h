@@ -131,7 +131,8 @@ int occ_unsplit_rows(const float* in, float* out, long long rows, int C, occ_str
 /* GroupNorm+ReLU of the raw conv output, Z-mean, LayerNorm1 (dualpath_block.py:43-48,69; window_attention.py:355):
  * tok fp32 (residual), tokn S32 (operand of the QKV GEMM).
  * win_shift < 0: tokn rows in token order;  win_shift = 0 / 1 (needs X, XY % X == 0): tokn in the WINDOW LAYOUT of the
- * un-shifted / shifted 7x7 partition -- token (img, x, y) at row window*64 + t, occ_window_layout_rows() rows in total,
+ * un-shifted / shifted 7x7 partition -- token (img, x, y) at row window*64 + t with window = (wx*nWy + wy)*n_images + img,
+ * occ_window_layout_rows() rows in total,
  * zero-initialised once by the caller (pad positions are never written) -- the operand of occ_swin_qkv_attention. */
 int occ_gn_relu_zmean_ln(const float* y, const double* stats, const float* gn_w, const float* gn_b,
                          const float* ln_w, const float* ln_b, float* tok, float* tokn, int B, int XY, int Z, int C,

@@ -221,8 +221,9 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*window-layou
       {
         const int win = (int)(2 * (pair0 + u * pair_stride)) + half;
         if (t < WT && win < (int)g.nwin) {
-          const int wy = win % g.nWy, w2 = win / g.nWy;
-          my_row = window_token_row(g, w2 / g.nWx, w2 % g.nWx, wy, t, &my_reg);
+          const int nimg = g.B * (g.Z + 1);  // window index = (wx * nWy + wy) * n_images + img (window_geom.cuh)
+          const int img = win % nimg, w2 = win / nimg;
+          my_row = window_token_row(g, img, w2 / g.nWy, w2 % g.nWy, t, &my_reg);
         }
       }
       uint32_t* same32 = reinterpret_cast<uint32_t*>(smem + SF_OFF_SAME + wg * SF_SAME_BYTES);

@@ -55,7 +55,8 @@ __device__ __forceinline__ long long window_token_row(const WinGeom& g, int img,
   return g.vox_rows + ((long long)b * g.X + x) * g.Y + y;
 }
 
-// Inverse of window_token_row for real tokens: token (img, x, y) -> row of the WINDOW-LAYOUT buffer, window * 64 + t (the
+// Inverse of window_token_row for real tokens: token (img, x, y) -> row of the WINDOW-LAYOUT buffer, window * 64 + t with
+// window = (wx * nWy + wy) * n_images + img (the
 // 49 tokens of a window are 49 consecutive rows, windows are 64 rows apart, rows 49..63 stay zero; a pair of windows is
 // one 128-row MMA tile that a single TMA box fetches).  Window pad tokens (positions >= X or >= Y of the padded image)
 // have no source token: their rows are never written and stay zero.
@@ -67,7 +68,10 @@ __device__ __forceinline__ long long window_layout_row(const WinGeom& g, int img
   }
   const int wx = xs / WS, wy = ys / WS;
   const int t = (xs - wx * WS) * WS + (ys - wy * WS);
-  return (((long long)img * g.nWx + wx) * g.nWy + wy) * 64 + t;
+  // window index = (wx, wy) major, image minor: the Z + 1 images of a (b, x, y) column -- which the producer handles
+  // together -- land 32 KB apart instead of one whole image (27 MB at 200 x 200) apart, and a pair of windows is the
+  // same (wx, wy) in two adjacent height slices, whose output rows are neighbours in token order
+  return (((long long)wx * g.nWy + wy) * ((long long)g.B * (g.Z + 1)) + img) * 64 + t;
 }
 
 inline WinGeom make_win_geom(int B, int X, int Y, int Z, int C, int heads, int shift) {

@@ -374,8 +374,9 @@ def window_layout_index(B, X, Y, Z, shift):
     b = torch.arange(B).view(B, 1, 1, 1)
     z = torch.arange(Z).view(1, 1, 1, Z)
     img = b * Z + z                                     # voxel slice image index
-    vox = (img * (nWx * nWy) + win_xy.view(1, X, Y, 1)) * 64 + t.view(1, X, Y, 1)        # (B, X, Y, Z)
-    bev = ((B * Z + torch.arange(B).view(B, 1, 1)) * (nWx * nWy) + win_xy.view(1, X, Y)) * 64 + t.view(1, X, Y)
+    nimg = B * (Z + 1)                                  # window index = (wx * nWy + wy) * n_images + image
+    vox = (win_xy.view(1, X, Y, 1) * nimg + img) * 64 + t.view(1, X, Y, 1)                # (B, X, Y, Z)
+    bev = (win_xy.view(1, X, Y) * nimg + (B * Z + torch.arange(B).view(B, 1, 1))) * 64 + t.view(1, X, Y)
     return torch.cat([vox.reshape(-1), bev.reshape(-1)]).long()
 
 

@@ -317,7 +317,7 @@ def test_window_layout_index_matches_window_token_row():
                             r = ((b * X + x) * Y + y) * Z + z
                         else:
                             r = B * X * Y * Z + ((img - B * Z) * X + x) * Y + y
-                        out[r] = ((img * nWx + wx) * nWy + wy) * 64 + t
+                        out[r] = ((wx * nWy + wy) * (B * (Z + 1)) + img) * 64 + t
         return out
 
     for cfg in [(1, 14, 7, 1, False), (1, 10, 16, 2, True), (2, 15, 10, 4, False), (1, 33, 40, 3, True)]:
