@@ -70,7 +70,8 @@ __device__ __forceinline__ long long window_layout_row(const WinGeom& g, int img
   const int t = (xs - wx * WS) * WS + (ys - wy * WS);
   // window index = (wx, wy) major, image minor: the Z + 1 images of a (b, x, y) column -- which the producer handles
   // together -- land 32 KB apart instead of one whole image (27 MB at 200 x 200) apart, and a pair of windows is the
-  // same (wx, wy) in two adjacent height slices, whose output rows are neighbours in token order
+  // same (wx, wy) in two adjacent height slices, whose output rows are neighbours in token order (measured neutral
+  // against the image-major order: neither the producer's scatter nor the attention kernel is bound by that locality)
   return (((long long)wx * g.nWy + wy) * ((long long)g.B * (g.Z + 1)) + img) * 64 + t;
 }
 
