@@ -116,14 +116,19 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
         *reinterpret_cast<float4*>(col_smem + ((size_t)col_local * Z + z0 + r) * C + c0) = t;
       }
     }
+    // tokn in window layout (operand of the fused QKV + attention kernel): window index = (wx, wy) major, image minor
+    // (window_geom.cuh), so the rows of this column's height slices are 64 rows apart -- one 32-bit index computation
+    // per warp
+    long long wl_row0 = 0;
+    if (win_layout) {
+      const int ci = (int)col, b = ci / XY, xy = ci - b * XY;
+      wl_row0 = window_layout_row(wg, b * Z + z0, xy / wg.Y, xy % wg.Y);
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       warp_layernorm<NV>(v[r], C, ln_w, ln_b, lane);
       long long orow = row0 + r;
-      if (win_layout) {  // tokn in window layout (operand of the fused QKV + attention kernel)
-        const int b = (int)(col / XY), xy = (int)(col - (long long)b * XY);
-        orow = window_layout_row(wg, b * Z + z0 + r, xy / wg.Y, xy % wg.Y);
-      }
+      if (win_layout) orow = wl_row0 + (long long)r * 64;  // next height slice = next image of the same window
 #pragma unroll
       for (int i = 0; i < NV; ++i) store_split4(tokn + orow * C, (i * 32 + lane) * 4, v[r][i]);
     }
@@ -147,7 +152,7 @@ gn_relu_zmean_ln_kernel(const float* __restrict__ y, const double* __restrict__ 
     warp_layernorm<NV>(v[0], C, ln_w, ln_b, lane);
     long long orow = brow;
     if (win_layout) {
-      const int b = (int)(col / XY), xy = (int)(col - (long long)b * XY);
+      const int ci = (int)col, b = ci / XY, xy = ci - b * XY;
       orow = window_layout_row(wg, B * Z + b, xy / wg.Y, xy % wg.Y);
     }
 #pragma unroll
@@ -468,6 +473,7 @@ extern "C" int occ_gn_relu_zmean_ln(const float* y, const double* stats, const f
   // win_shift < 0: tokn in token order (rows as tok); 0 / 1: tokn in the window layout of the un-shifted / shifted
   // partition (occ_swin_qkv_attention's operand; the buffer must be zero where no token lands: occ_window_layout_rows)
   OCC_REQUIRE(win_shift < 0 || (X > 0 && XY % X == 0));
+  OCC_REQUIRE((long long)B * XY < (1ll << 31));
   const WinGeom wg = make_win_geom(B, win_shift < 0 ? 1 : X, win_shift < 0 ? XY : XY / X, Z, C, C / HD, win_shift > 0);
   const int wl = win_shift >= 0;
   OCC_REQUIRE(B > 0 && XY > 0 && Z > 0 && Z <= 16 && C % 128 == 0 && groups > 0 && groups <= 32 && C % groups == 0 &&
