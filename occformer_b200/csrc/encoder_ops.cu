@@ -382,7 +382,7 @@ fuse_kernel(const float* __restrict__ x, const float* __restrict__ bev, const fl
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const long long row = row0 + r < rows ? row0 + r : rows - 1;  // tail rows are loaded twice, stored once
-    const long long col = row / Z;
+    const long long col = (int)row / Z;  // 32-bit division (rows < 2^31, checked by the launcher): a 64-bit one is ~100 instructions
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c0 = (i * 32 + lane) * 4;
@@ -406,7 +406,7 @@ fuse_kernel(const float* __restrict__ x, const float* __restrict__ bev, const fl
     }
     dot = warp_sum(dot) + cbias;
     const float coeff = 1.0f / (1.0f + expf(-dot));
-    const int bidx = (int)(row / rows_per_batch);
+    const int bidx = (int)row / (int)rows_per_batch;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c0 = (i * 32 + lane) * 4;
@@ -439,8 +439,8 @@ split_rows_kernel(const float* __restrict__ in, float* __restrict__ out, long lo
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 >= n4) return;
   const int C4 = C >> 2;
-  const long long row = i4 / C4;
-  const int c0 = (int)(i4 % C4) * 4;
+  const long long row = i4 < (1ll << 31) ? (long long)((int)i4 / C4) : i4 / C4;
+  const int c0 = (int)(i4 - row * C4) * 4;
   store_split4(out + row * C, c0, __ldg(reinterpret_cast<const float4*>(in + row * C + c0)));
 }
 __global__ void __launch_bounds__(256)
@@ -568,6 +568,7 @@ extern "C" int occ_dualpath_fuse(const float* x, const float* bev, const float* 
   OCC_REQUIRE(x && bev && cw && identity && (out || out_split) && B > 0 && XY > 0 && Z > 0 && C % 128 == 0);
   if (id_stats) OCC_REQUIRE(id_w && id_b && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0);
   const long long rows = (long long)B * XY * Z;
+  OCC_REQUIRE(rows < (1ll << 31));
 #define FUSE_LAUNCH(NV_, R_, MB_)                                                                                       \
   do {                                                                                                                  \
     const int blocks = (int)((rows + 8 * (R_) - 1) / (8 * (R_)));                                                       \
