@@ -324,3 +324,25 @@ def test_window_layout_index_matches_window_token_row():
         got = ops.window_layout_index(*cfg)
         assert torch.equal(got, brute(*cfg)), cfg
         assert got.unique().numel() == got.numel()
+
+
+def test_host_helpers_pad_head_rows_and_stats_plan():
+    """host-side operand helpers of the neck: per-head padding of value_proj (128-byte head slices) and the sub-group plan
+    of the GroupNorm statistics gathered in a conv epilogue"""
+    import torch
+    from occformer_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    E, H = 192, 8
+    w, b = torch.randn(E, E, generator=g), torch.randn(E, generator=g)
+    wp, bp = ops.pad_head_rows(w, b, H)
+    assert wp.shape == (H * 32, E) and bp.shape == (H * 32,)
+    x = torch.randn(5, E, generator=g)
+    y, yp = x @ w.t() + b, (x @ wp.t() + bp).view(5, H, 32)
+    assert torch.allclose(yp[:, :, :24].reshape(5, E), y, atol=1e-5) and float(yp[:, :, 24:].abs().max()) == 0.0
+    w32, b32 = ops.pad_head_rows(torch.randn(256, 64, generator=g), torch.randn(256, generator=g), 8)  # hd = 32: unchanged
+    assert w32.shape == (256, 64)
+    assert ops.epilogue_stats_plan(192, 32) == (2, 3)      # 6 channels per group = 3 pairs
+    assert ops.epilogue_stats_plan(128, 32) == (4, 1)
+    assert ops.epilogue_stats_plan(96, 32) == (1, 3)
+    assert ops.epilogue_stats_plan(384, 32) == (4, 3)      # 12 = 4 * 3 -> 96 sub-groups of 4: fits
+    assert ops.epilogue_stats_plan(576, 32) is None         # 18 = 2 * 9 -> 288 pairs: too many for the epilogue
