@@ -451,7 +451,9 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
         l0 = ops.LAUNCH_COUNT[0]
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # capture on the stream of the warm-up above: per-stream caches of the package (window-layout token buffers, conv
+        # workspaces) are then already allocated and zero-initialised outside the graph
+        with torch.cuda.graph(graph, stream=side):
             graph_out = pipe.run(resident)
         launches_per_step = ops.LAUNCH_COUNT[0] - l0
         for _ in range(2):
