@@ -425,31 +425,29 @@ classmix_kernel(const float* __restrict__ mask, const float* __restrict__ cls, f
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
   if (identity) {
-    // The CTA's 128 voxel rows are one contiguous run of 128 * Q floats: staged in shared memory with coalesced 16-byte
-    // loads (row pitch Q + 1: thread = voxel then reads its row conflict-free).  Reading the rows straight from global
-    // (25 16-byte loads per thread, each touching 32 different lines of a warp) cost 8x the tensor's bytes in L1 traffic.
-    float* rows = sm + Q * KMAX;  // [CM_THREADS][Q + 1]
-    const int pitch = Q + 1;
-    const long long nvox = Vo - v0 < CM_THREADS ? Vo - v0 : CM_THREADS;
-    const float4* src = reinterpret_cast<const float4*>(mask + ((size_t)b * Vo + v0) * Q);
-    const int n4 = (int)(nvox * Q) >> 2;  // Q % 4 == 0
-    for (int i = threadIdx.x; i < n4; i += CM_THREADS) {
-      const float4 a = __ldcs(src + i);
-      const int e = i << 2, r = e / Q, c = e - r * Q;
-      float* d = rows + r * pitch + c;
-      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
-    }
+    // thread = voxel: its Q logits are one contiguous run, read straight into registers in 32-byte pieces (no staging,
+    // no barrier after the class table: the occupancy hides the latency; every line is consumed completely)
     __syncthreads();
     if (v < Vo) {
-      const float* my = rows + threadIdx.x * pitch;
-      for (int q = 0; q < Q; ++q) {
-        const float s = 1.0f / (1.0f + __expf(-my[q]));
-        const float* pq = P + q * KMAX;
+      const float4* r4 = reinterpret_cast<const float4*>(mask + ((size_t)b * Vo + v) * Q);
+      for (int q8 = 0; q8 < Q; q8 += 8) {
+        float lg[8];
+        const float4 a = __ldcs(r4 + (q8 >> 2));
+        lg[0] = a.x; lg[1] = a.y; lg[2] = a.z; lg[3] = a.w;
+        const bool two = q8 + 4 < Q;
+        const float4 c = two ? __ldcs(r4 + (q8 >> 2) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        lg[4] = c.x; lg[5] = c.y; lg[6] = c.z; lg[7] = c.w;
 #pragma unroll
-        for (int k = 0; k < KMAX; k += 4) {
-          const float4 pp = *reinterpret_cast<const float4*>(pq + k);
-          acc[k] = fmaf(pp.x, s, acc[k]); acc[k + 1] = fmaf(pp.y, s, acc[k + 1]);
-          acc[k + 2] = fmaf(pp.z, s, acc[k + 2]); acc[k + 3] = fmaf(pp.w, s, acc[k + 3]);
+        for (int e = 0; e < 8; ++e) {
+          if (e >= 4 && !two) break;
+          const float s = 1.0f / (1.0f + __expf(-lg[e]));
+          const float* pq = P + (q8 + e) * KMAX;
+#pragma unroll
+          for (int k = 0; k < KMAX; k += 4) {
+            const float4 pp = *reinterpret_cast<const float4*>(pq + k);
+            acc[k] = fmaf(pp.x, s, acc[k]); acc[k + 1] = fmaf(pp.y, s, acc[k + 1]);
+            acc[k + 2] = fmaf(pp.z, s, acc[k + 2]); acc[k + 3] = fmaf(pp.w, s, acc[k + 3]);
+          }
         }
       }
     }
@@ -669,8 +667,7 @@ extern "C" int occ_classmix(const float* mask, const float* cls, float* out, uns
   const long long Vo = (long long)Xo * Yo * Zo;
   const int kmax = (NC - 1 <= 20) ? 20 : 32;
   OCC_REQUIRE(Q % 4 == 0);
-  const bool identity = X == Xo && Y == Yo && Z == Zo;
-  const size_t smem = ((size_t)Q * kmax + (identity ? (size_t)CM_THREADS * (Q + 1) : 0)) * sizeof(float);
+  const size_t smem = (size_t)Q * kmax * sizeof(float);
   OCC_REQUIRE(smem <= 200 * 1024);
   dim3 grid((unsigned)((Vo + CM_THREADS - 1) / CM_THREADS), B);
   if (NC - 1 <= 20) {
