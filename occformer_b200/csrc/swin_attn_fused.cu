@@ -8,25 +8,26 @@
 // Work unit = (pair of windows, head), one head per CTA (gridDim.x is a multiple of the head count): the head's 96 x 128
 // slice of the qkv weight (rows [q | k | v] x 32, head-major) stays resident in shared memory for the whole kernel.
 // Per unit:
-//   loader   (warp 1)       window geometry of the unit (row / region metadata for the softmax and the output scatter) and
-//                           one TMA box (32 channels x 128 rows) per k-block: the tokens arrive in WINDOW LAYOUT
+//   loader   (warp 1)       one TMA box (32 channels x 128 rows) per k-block: the tokens arrive in WINDOW LAYOUT
 //                           (window_geom.cuh: the LayerNorm producer writes token (img, x, y) to row window * 64 + t),
 //                           so a pair of windows is a contiguous tile.  (Per-row gathers -- cp.async or tile::gather4,
 //                           ~110 cycles per 512-byte gather4 -- could not feed the MMAs: r02_ncu_swin_qkv_attn_v3/v4.)
 //   MMA      (warps 0/2/3)  M1: D[128 x 96] = A W_h^T            (4 k-blocks x 6 tcgen05.mma 128x96x16: three bf16 passes)
 //                           QK: S = Q K^T, PV: O' = [P_hi; P_lo][V_hi | V_lo]   (as in window_attn.cu); one issuer each
 //   three warpgroups (warps 4-7 / 8-11 / 12-15, unit u -> warpgroup u % 3), each running its unit start to end:
+//       metadata: token row / shift-mask region of the thread's tile row, key-region bitmasks by two ballots per window
+//                 half (computed while M1 of the unit is in flight)
 //       convert : tcgen05.ld D -> + bias -> split -> V operand tile (one per warpgroup), then Q / K operand tiles (single:
 //                 free again as soon as QK^T of the previous unit has been read)
 //       softmax : S row -> scale, relative-position bias, shift mask, exp2 -> P (TMEM, split)      (unchanged)
 //       epilogue: O -> normalise -> S32 scatter to the token-ordered output (A operand of the projection GEMM)
-// A warpgroup's unit is a serial chain of TMEM round trips (~5 k cycles, IPC ~0.15 per warp: ncu of the two-warpgroup
-// version, profiles/r02_ncu_swin_qkv_attn_v2.md), so the kernel's rate is (warpgroups in flight) / chain: three units are
+// A warpgroup's unit is a serial chain of TMEM round trips (IPC ~0.2 per warp), so the kernel's rate is (warpgroups in
+// flight) / chain: three units are
 // in flight, each with its own TMEM slot of 128 columns that holds D, then S, then P of the unit (D is dead once
 // converted, S once exponentiated), plus two O buffers.  The token tiles arrive through a ring of five 16 KB k-block
-// slots (the gather latency, not the bandwidth, is what a single-buffered tile would expose).
-// HBM: tokens in (rows*C*4) + attention out (rows*C*4); the 4 head-CTAs of a group walk the same window pairs at the
-// same time, so three of the four token reads are L2 hits.
+// slots.  Measured (profiles/r02_ncu_swin_qkv_attn_v7.md): 0.48 ms per launch at 200x200x(16+1), tensor pipe 48 % active.
+// HBM: tokens in (window layout: 64 rows per window) + attention out (rows*C*4); the 4 head-CTAs of a group walk the
+// same window pairs at the same time, so three of the four token reads are L2 hits.
 #include "window_geom.cuh"
 
 namespace occ {
