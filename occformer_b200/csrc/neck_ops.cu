@@ -112,7 +112,8 @@ token_prep_kernel(const float* __restrict__ in, const float* __restrict__ ln_w, 
 // Multi-scale deformable attention core, 3-D (multi_scale_deform_attn_3d.py:17-80 + the location arithmetic of :258-272).
 //   value (rows, value_ld)     value_proj output, level-major, head h = channels [h*head_ld, h*head_ld + hd): with
 //                              head_ld = hd rounded up to 32 floats a head slice is one 128-byte line (the kernel is
-//                              bound by L1 wavefronts = distinct lines touched: 1 instead of 1.5 per 96-byte slice)
+//                              bound by the L1 data stage -- LSU wavefronts 92 % of peak in ncu: a 16-byte load per thread
+//                              moves 64 bytes per cycle whatever the alignment; the padding measured 5 %: 0.566 -> 0.539 ms)
 //   ow    (rows, H*L*P*4)      [ sampling_offsets (h, l, p, 3: z, y, x) | attention logits (h, l, p) ] of the same token
 //   out   (rows, E)  S32       sum_{l,p} softmax(logits)[l,p] * trilinear(value level l)(loc), zeros outside,
 //                              align_corners=False;  loc = ref + offset / (Z_l, Y_l, X_l),  ref = voxel centre of the
