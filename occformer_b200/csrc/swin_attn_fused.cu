@@ -227,17 +227,18 @@ swin_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_tok /*window-layou
           my_row = window_token_row(g, img, w2 / g.nWy, w2 % g.nWy, t, &my_reg);
         }
       }
-      uint32_t* same32 = reinterpret_cast<uint32_t*>(smem + SF_OFF_SAME + wg * SF_SAME_BYTES);
-      {
+      uint2 same = make_uint2(0xffffffffu, 0x1ffffu);  // un-shifted partition: one region, every key of the window
+      if (g.shift) {
+        uint32_t* same32 = reinterpret_cast<uint32_t*>(smem + SF_OFF_SAME + wg * SF_SAME_BYTES);
         const int wq = warp & 3;  // window half wq >> 1, tokens (wq & 1) * 32 + lane
 #pragma unroll
         for (int rg = 0; rg < 9; ++rg) {
           const uint32_t bal = __ballot_sync(0xffffffffu, t < WT && my_reg == rg);
           if (lane == 0) same32[((wq >> 1) * 9 + rg) * 2 + (wq & 1)] = bal;
         }
+        named_bar_sync(3 + wg, 128);
+        same = reinterpret_cast<const uint2*>(same32)[half * 9 + my_reg];
       }
-      named_bar_sync(3 + wg, 128);
-      const uint2 same = reinterpret_cast<const uint2*>(same32)[half * 9 + my_reg];
       // ---- conversion: D row (q | k | v of this head) + bias -> S32 rows of the Q / K / V operand tiles
       mbar_wait(&d_ready[tb], k & 1);
       tc_fence_after();

@@ -85,7 +85,9 @@ def main():
         res["window_attn_tc_ms"] = timeit(lambda: ops.window_attention(qkv, bqs, bias_pad, 1, X, Y, Z, C, heads, True, head_major=True))
         tokn_wl = ops.to_window_layout(tokn, 1, X, Y, Z, True)
         res["swin_qkv_attn_fused_ms"] = timeit(lambda: ops.swin_qkv_attention(tokn_wl, wq, bq, bias_pad, 1, X, Y, Z, C, heads, True))
-        del tokn_wl
+        tokn_wl0 = ops.to_window_layout(tokn, 1, X, Y, Z, False)
+        res["swin_qkv_attn_fused_unshifted_ms"] = timeit(lambda: ops.swin_qkv_attention(tokn_wl0, wq, bq, bias_pad, 1, X, Y, Z, C, heads, False))
+        del tokn_wl, tokn_wl0
         del qkv, tokn
     if "tail" in which:
         M = rows
