@@ -25,6 +25,7 @@ for s in "$@"; do
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-1500} -c ${NCU_COUNT:-900} --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1; echo "launches rc=$?" ;;
     ncupool) timeout 900 ncu --set full --clock-control none --import-source on -k regex:vp_ -s 12 -c 6 -f -o gpurun_out/prof_vp_pool python scripts/microbench.py pool > gpurun_out/ncu_vp_pool.log 2>&1; echo "ncupool rc=$?" ;;
     ncuhead) timeout 900 ncu --set full --clock-control none --import-source on -k regex:cross_attn_tc -s 11 -c 1 -f -o gpurun_out/prof_cross_attn python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_cross_attn.log 2>&1; echo "ncuhead rc=$?" ;;
+    ncuelem) timeout 600 ncu --set full --clock-control none --import-source on -k regex:"fuse_kernel|gn_upsample_add_x2" -s 2 -c 2 -f -o gpurun_out/prof_elem python scripts/microbench.py elem > gpurun_out/ncu_elem.log 2>&1; echo "ncuelem rc=$?" ;;
     ncuneckgemm) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16x3 -s 4 -c 2 -f -o gpurun_out/prof_neck_gemm python scripts/microbench.py neck > gpurun_out/ncu_neck_gemm.log 2>&1; echo "ncuneckgemm rc=$?" ;;
     ncu_*)   k=${s#ncu_}; case $k in gemm_bf16x3*) w=conv ;; swin_qkv*|window_attn*) w=attn ;; swin_mlp*) w=tail ;; vp_pool*|lift_front*) w=lift ;; ms_deform*|token_prep*) w=neck ;; *) w=${NCU_WHICH:-conv} ;; esac
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s ${NCU_SKIP:-2} -c 1 -f -o gpurun_out/prof_$k python scripts/microbench.py $w > gpurun_out/ncu_$k.log 2>&1; echo "ncu $k rc=$?" ;;
